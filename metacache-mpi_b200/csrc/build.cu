@@ -1,0 +1,570 @@
+// build.cu -- K2: database shard construction and maintenance.
+//
+// Reference semantics reproduced (not its layout):
+//   sketch_database.h:519-563  add_target_distributed (shard = target_id % nshards, :540)
+//   sketch_database.h:1079-1097 add_all_window_sketches: every feature of every window
+//                               is inserted with location {tgt,win}; lists are cut to
+//                               maxlocs (first come = smallest (tgt,win), quirk Q11)
+//   hash_multimap.h:653,706,720,779  insert / shrink / clear(bucket) / find
+//   sketch_database.h:398-417,1060-1075 + mode_build.cpp:847-1074 overpopulated-feature removal
+//
+// HBM layout of a finalized shard:
+//   keys [nkeys]  uint32 ascending        sizes[nkeys] uint8 (0 = emptied "dead" key)
+//   offs [nkeys+1] uint64 (CSR)           locs [nlocs] uint64 = tgt << 32 | win
+//   table[cap]    uint4 {key, size, off_lo, off_hi}: open addressing, linear probing,
+//                 slot = umulhi(slot_mix(key), cap), empty key = 0xFFFFFFFF
+#include "common.cuh"
+
+#include <algorithm>
+#include <numeric>
+
+namespace mcg {
+
+int copy_in(mcg_ctx* c, void* d, const void* h, size_t bytes);
+int copy_out(mcg_ctx* c, void* h, const void* d, size_t bytes);
+int exclusive_scan_u32_to_u32(mcg_ctx* c, const uint32_t* d_in, uint32_t* d_out, uint64_t n);
+
+constexpr uint32_t EMPTY_KEY = 0xFFFFFFFFu;
+constexpr double TABLE_LOAD = 0.6;
+
+// first index with sorted_keys[i] == 0xFFFFFFFF (padding slots sort to the end)
+__global__ void count_valid_kernel(const uint32_t* keys, uint64_t n, uint64_t* out)
+{
+    uint64_t lo = 0, hi = n;
+    while(lo < hi) {
+        const uint64_t mid = (lo + hi) >> 1;
+        if(keys[mid] == EMPTY_KEY) hi = mid; else lo = mid + 1;
+    }
+    *out = lo;
+}
+
+__global__ void head_flags_kernel(const uint32_t* keys, uint64_t n, uint32_t* head)
+{
+    const uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
+    if(i < n) head[i] = (i == 0 || keys[i] != keys[i - 1]) ? 1u : 0u;
+}
+
+// hs = exclusive scan of head flags.  For every run head: record key and run start.
+__global__ void run_starts_kernel(const uint32_t* keys, const uint32_t* hs, uint64_t n,
+                                  uint32_t* ukeys, uint32_t* ustart, uint32_t nkeys)
+{
+    const uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
+    if(i < n) {
+        const bool head = (i == 0 || keys[i] != keys[i - 1]);
+        if(head) {
+            const uint32_t j = hs[i];
+            ukeys[j] = keys[i];
+            ustart[j] = uint32_t(i);
+        }
+    }
+    if(i == 0) ustart[nkeys] = uint32_t(n);
+}
+
+__global__ void run_sizes_kernel(const uint32_t* ustart, uint32_t nkeys, uint32_t maxlocs, uint8_t* sizes)
+{
+    const uint64_t j = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
+    if(j < nkeys) {
+        const uint32_t len = ustart[j + 1] - ustart[j];
+        sizes[j] = uint8_t(len < maxlocs ? len : maxlocs);
+    }
+}
+
+// element i of the sorted slot list -> location, if it is among the first maxlocs of its run
+__global__ void emit_locations_kernel(const uint32_t* keys, const uint32_t* slots, const uint32_t* hs,
+                                      const uint32_t* ustart, const uint64_t* offs, uint64_t n,
+                                      uint32_t maxlocs, uint32_t sketchlen,
+                                      const uint64_t* tgt_firstwin, const uint32_t* tgt_id, uint32_t ntgt,
+                                      uint64_t* locs)
+{
+    const uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
+    if(i >= n) return;
+    const bool head = (i == 0 || keys[i] != keys[i - 1]);
+    const uint32_t j = hs[i] + (head ? 1u : 0u) - 1u;
+    const uint32_t r = uint32_t(i) - ustart[j];
+    if(r >= maxlocs) return;
+    const uint64_t gw = slots[i] / sketchlen;          // global window of the shard
+    uint32_t lo = 0, hi = ntgt;                        // largest t with firstwin[t] <= gw
+    while(hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if(tgt_firstwin[mid] <= gw) lo = mid; else hi = mid;
+    }
+    const uint64_t win = gw - tgt_firstwin[lo];
+    locs[offs[j] + r] = (uint64_t(tgt_id[lo]) << 32) | win;
+}
+
+__global__ void table_clear_kernel(uint4* table, uint64_t cap)
+{
+    const uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
+    if(i < cap) table[i] = make_uint4(EMPTY_KEY, 0u, 0u, 0u);
+}
+
+__device__ __forceinline__ uint64_t table_slot(uint32_t key, uint64_t cap)
+{
+    // cap < 2^40: two-step multiply-high keeps all 32 hash bits in play
+    return (uint64_t(slot_mix(key)) * cap) >> 32;
+}
+
+__global__ void table_insert_kernel(uint4* table, uint64_t cap, const uint32_t* ukeys, const uint8_t* sizes,
+                                    const uint64_t* offs, uint32_t nkeys)
+{
+    const uint64_t j = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
+    if(j >= nkeys) return;
+    const uint32_t key = ukeys[j];
+    uint64_t s = table_slot(key, cap);
+    for(;;) {
+        const uint32_t old = atomicCAS(&table[s].x, EMPTY_KEY, key);
+        if(old == EMPTY_KEY) {
+            const uint64_t o = offs[j];
+            table[s].y = sizes[j];
+            table[s].z = uint32_t(o);
+            table[s].w = uint32_t(o >> 32);
+            return;
+        }
+        if(++s == cap) s = 0;
+    }
+}
+
+// clear(bucket) for a list of keys: hash_multimap.h:720 -- the key stays, its list is emptied
+__global__ void remove_keys_kernel(uint4* table, uint64_t cap, const uint32_t* ukeys, uint8_t* sizes, uint32_t nkeys,
+                                   const uint32_t* rem, uint64_t nrem, unsigned long long* removed)
+{
+    const uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
+    if(i >= nrem) return;
+    const uint32_t key = rem[i];
+    uint32_t lo = 0, hi = nkeys;
+    while(lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if(ukeys[mid] < key) lo = mid + 1; else hi = mid;
+    }
+    if(lo >= nkeys || ukeys[lo] != key) return;
+    atomicAdd(removed, 1ull);                       // found (reference counts found keys, :410-413)
+    sizes[lo] = 0;
+    uint64_t s = table_slot(key, cap);
+    for(;;) {
+        const uint32_t k = table[s].x;
+        if(k == key) { table[s].y = 0; return; }
+        if(k == EMPTY_KEY) return;
+        if(++s == cap) s = 0;
+    }
+}
+
+__global__ void count_sizes_kernel(const uint8_t* sizes, uint32_t nkeys, unsigned long long* out /* [2] */)
+{
+    __shared__ unsigned long long s_ne, s_nl;
+    if(threadIdx.x == 0) { s_ne = 0; s_nl = 0; }
+    __syncthreads();
+    unsigned long long ne = 0, nl = 0;
+    for(uint64_t j = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; j < nkeys; j += uint64_t(gridDim.x) * blockDim.x) {
+        const uint32_t s = sizes[j];
+        ne += s != 0;
+        nl += s;
+    }
+    for(int d = 16; d > 0; d >>= 1) {
+        ne += __shfl_down_sync(0xFFFFFFFFu, ne, d);
+        nl += __shfl_down_sync(0xFFFFFFFFu, nl, d);
+    }
+    if((threadIdx.x & 31) == 0) { atomicAdd(&s_ne, ne); atomicAdd(&s_nl, nl); }
+    __syncthreads();
+    if(threadIdx.x == 0) { atomicAdd(&out[0], s_ne); atomicAdd(&out[1], s_nl); }
+}
+
+static inline unsigned grid_for(uint64_t n, int threads = 256) { return unsigned((n + threads - 1) / threads); }
+
+static int build_table(mcg_db* db)
+{
+    mcg_ctx* c = db->ctx;
+    uint64_t cap = uint64_t(double(db->nkeys) / TABLE_LOAD) + 64;
+    MCG_TRY(db->table.reserve(cap * sizeof(uint4)));
+    db->table_cap = cap;
+    table_clear_kernel<<<grid_for(cap), 256, 0, c->stream>>>(db->table.as<uint4>(), cap);
+    c->launches++;
+    if(db->nkeys > 0) {
+        table_insert_kernel<<<grid_for(db->nkeys), 256, 0, c->stream>>>(
+            db->table.as<uint4>(), cap, db->keys.as<uint32_t>(), db->sizes.as<uint8_t>(), db->offs.as<uint64_t>(),
+            uint32_t(db->nkeys));
+        c->launches++;
+    }
+    MCG_CUDA(cudaGetLastError());
+    return MCG_OK;
+}
+
+int db_finalize(mcg_db* db)
+{
+    mcg_ctx* c = db->ctx;
+    MCG_CUDA(cudaSetDevice(c->device));
+    const uint32_t s = uint32_t(db->cfg.sketchlen);
+    const uint64_t nslots = db->nwin * s;
+    MCG_REQUIRE(nslots < (1ull << 32), "shard holds %llu feature slots; the device build supports < 2^32 per shard",
+                (unsigned long long)nslots);
+    db->nkeys = 0;
+    db->nlocs = 0;
+    if(nslots == 0) {
+        MCG_TRY(db->keys.reserve(16)); MCG_TRY(db->sizes.reserve(16)); MCG_TRY(db->offs.reserve(16)); MCG_TRY(db->locs.reserve(16));
+        MCG_CUDA(cudaMemsetAsync(db->offs.p, 0, 16, c->stream));
+        MCG_TRY(build_table(db));
+        db->finalized = true;
+        return MCG_OK;
+    }
+    // (1) sort slots by feature, stable; value = slot index (window-major => (tgt,win) order)
+    MCG_TRY(c->tmp0.reserve(nslots * 4));     // slot ids
+    MCG_TRY(c->tmp1.reserve(nslots * 4));     // keys alt
+    MCG_TRY(c->tmp2.reserve(nslots * 4));     // vals alt
+    uint32_t* skeys = db->feat.as<uint32_t>();
+    uint32_t* svals = c->tmp0.as<uint32_t>();
+    MCG_TRY(radix_sort_pairs(c, skeys, svals, c->tmp1.as<uint32_t>(), c->tmp2.as<uint32_t>(), nslots, 32, true));
+    // (2) drop the padding tail
+    MCG_TRY(c->tmp3.reserve(64));
+    uint64_t* d_scalar = c->tmp3.as<uint64_t>();
+    count_valid_kernel<<<1, 1, 0, c->stream>>>(skeys, nslots, d_scalar);
+    c->launches++;
+    uint64_t nvalid = 0;
+    MCG_CUDA(cudaMemcpyAsync(&nvalid, d_scalar, 8, cudaMemcpyDeviceToHost, c->stream));
+    MCG_CUDA(cudaStreamSynchronize(c->stream));
+    // (3) runs of equal feature
+    uint32_t* hs = c->tmp1.as<uint32_t>();    // reuse (needs nvalid+1 <= nslots+... entries)
+    MCG_TRY(c->tmp1.reserve((nslots + 2) * 4));
+    hs = c->tmp1.as<uint32_t>();
+    uint32_t nkeys = 0;
+    if(nvalid > 0) {
+        head_flags_kernel<<<grid_for(nvalid), 256, 0, c->stream>>>(skeys, nvalid, hs);
+        c->launches++;
+        MCG_TRY(exclusive_scan_u32_to_u32(c, hs, hs, nvalid));
+        MCG_CUDA(cudaMemcpyAsync(&nkeys, hs + nvalid, 4, cudaMemcpyDeviceToHost, c->stream));
+        MCG_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    db->nkeys = nkeys;
+    MCG_TRY(db->keys.reserve((uint64_t(nkeys) + 1) * 4));
+    MCG_TRY(db->sizes.reserve(uint64_t(nkeys) + 16));
+    MCG_TRY(db->offs.reserve((uint64_t(nkeys) + 2) * 8));
+    MCG_TRY(c->tmp2.reserve((uint64_t(nkeys) + 2) * 4));
+    uint32_t* ustart = c->tmp2.as<uint32_t>();
+    if(nkeys > 0) {
+        run_starts_kernel<<<grid_for(nvalid), 256, 0, c->stream>>>(skeys, hs, nvalid, db->keys.as<uint32_t>(), ustart, nkeys);
+        run_sizes_kernel<<<grid_for(nkeys), 256, 0, c->stream>>>(ustart, nkeys, uint32_t(db->maxlocs), db->sizes.as<uint8_t>());
+        c->launches += 2;
+    }
+    MCG_TRY(exclusive_scan_u8_to_u64(c, db->sizes.as<uint8_t>(), db->offs.as<uint64_t>(), nkeys));
+    uint64_t nlocs = 0;
+    MCG_CUDA(cudaMemcpyAsync(&nlocs, db->offs.as<uint64_t>() + nkeys, 8, cudaMemcpyDeviceToHost, c->stream));
+    MCG_CUDA(cudaStreamSynchronize(c->stream));
+    db->nlocs = nlocs;
+    MCG_TRY(db->locs.reserve((nlocs + 2) * 8));
+    // (4) locations
+    if(nvalid > 0) {
+        const uint32_t ntgt = uint32_t(db->h_tgt_id.size());
+        MCG_TRY(c->tmp3.reserve((size_t(ntgt) + 2) * 8 + 64));
+        MCG_TRY(c->tmp4.reserve((size_t(ntgt) + 2) * 4 + 64));
+        MCG_CUDA(cudaMemcpyAsync(c->tmp3.p, db->h_tgt_firstwin.data(), (size_t(ntgt) + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+        MCG_CUDA(cudaMemcpyAsync(c->tmp4.p, db->h_tgt_id.data(), size_t(ntgt) * 4, cudaMemcpyHostToDevice, c->stream));
+        emit_locations_kernel<<<grid_for(nvalid), 256, 0, c->stream>>>(
+            skeys, svals, hs, ustart, db->offs.as<uint64_t>(), nvalid, uint32_t(db->maxlocs), s,
+            c->tmp3.as<uint64_t>(), c->tmp4.as<uint32_t>(), ntgt, db->locs.as<uint64_t>());
+        c->launches++;
+        MCG_CUDA(cudaStreamSynchronize(c->stream));     // host vectors were the copy source
+    }
+    // (5) open-addressing table over the unique keys
+    MCG_TRY(build_table(db));
+    MCG_CUDA(cudaStreamSynchronize(c->stream));
+    db->feat.release();
+    c->tmp0.release(); c->tmp1.release(); c->tmp2.release();
+    db->finalized = true;
+    return MCG_OK;
+}
+
+int db_counts(mcg_db* db, uint64_t* nkeys, uint64_t* nonempty, uint64_t* nlocs)
+{
+    mcg_ctx* c = db->ctx;
+    MCG_CUDA(cudaSetDevice(c->device));
+    unsigned long long h[2] = {0, 0};
+    if(db->nkeys > 0) {
+        MCG_TRY(c->tmp3.reserve(64));
+        MCG_CUDA(cudaMemsetAsync(c->tmp3.p, 0, 16, c->stream));
+        count_sizes_kernel<<<kNumSMs * 4, 256, 0, c->stream>>>(db->sizes.as<uint8_t>(), uint32_t(db->nkeys),
+                                                              c->tmp3.as<unsigned long long>());
+        c->launches++;
+        MCG_CUDA(cudaMemcpyAsync(h, c->tmp3.p, 16, cudaMemcpyDeviceToHost, c->stream));
+        MCG_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    if(nkeys) *nkeys = db->nkeys;
+    if(nonempty) *nonempty = h[0];
+    if(nlocs) *nlocs = h[1];
+    return MCG_OK;
+}
+
+int db_remove_keys_dev(mcg_db* db, const uint32_t* d_keys, uint64_t n, uint64_t* removed)
+{
+    mcg_ctx* c = db->ctx;
+    unsigned long long h = 0;
+    if(n > 0 && db->nkeys > 0) {
+        MCG_TRY(c->tmp3.reserve(64));
+        MCG_CUDA(cudaMemsetAsync(c->tmp3.p, 0, 8, c->stream));
+        remove_keys_kernel<<<grid_for(n), 256, 0, c->stream>>>(db->table.as<uint4>(), db->table_cap, db->keys.as<uint32_t>(),
+                                                              db->sizes.as<uint8_t>(), uint32_t(db->nkeys), d_keys, n,
+                                                              c->tmp3.as<unsigned long long>());
+        c->launches++;
+        MCG_CUDA(cudaMemcpyAsync(&h, c->tmp3.p, 8, cudaMemcpyDeviceToHost, c->stream));
+        MCG_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    if(removed) *removed = h;
+    return MCG_OK;
+}
+
+}  // namespace mcg
+
+using namespace mcg;
+
+extern "C" {
+
+int mcg_db_create(mcg_ctx* c, const mcg_sketch_cfg* cfg, int32_t maxlocs, int32_t shard, int32_t nshards, mcg_db** out)
+{
+    MCG_REQUIRE(c != nullptr && cfg != nullptr && out != nullptr, "mcg_db_create: NULL argument");
+    *out = nullptr;
+    MCG_REQUIRE(cfg->k >= 1 && cfg->k <= MCG_MAX_K, "kmerlen %d outside 1..%d", cfg->k, MCG_MAX_K);
+    MCG_REQUIRE(cfg->sketchlen >= 1 && cfg->sketchlen <= MCG_MAX_SKETCH, "sketchlen %d outside 1..%d", cfg->sketchlen, MCG_MAX_SKETCH);
+    MCG_REQUIRE(cfg->winlen >= 1 && cfg->winstride >= 1, "window length / stride must be >= 1");
+    MCG_REQUIRE(nshards >= 1 && shard >= 0 && shard < nshards, "shard %d / %d out of range", shard, nshards);
+    mcg_db* db = new mcg_db;
+    db->ctx = c;
+    db->cfg = *cfg;
+    // sketch_database.h:356-368 on a uint8 argument (mode_build.cpp:659; quirk Q7)
+    int m = int(uint8_t(maxlocs));
+    if(m < 1) m = 1;
+    if(m >= MCG_MAX_LOCS) m = MCG_MAX_LOCS;
+    db->maxlocs = m;
+    db->shard = shard;
+    db->nshards = nshards;
+    db->h_tgt_firstwin.push_back(0);
+    *out = db;
+    return MCG_OK;
+}
+
+int mcg_db_destroy(mcg_db* db)
+{
+    if(db == nullptr) return MCG_OK;
+    cudaSetDevice(db->ctx->device);
+    cudaStreamSynchronize(db->ctx->stream);
+    db->feat.release(); db->keys.release(); db->offs.release(); db->sizes.release(); db->locs.release(); db->table.release();
+    delete db;
+    return MCG_OK;
+}
+
+int mcg_db_add_targets(mcg_db* db, const char* seq_bytes, const int64_t* seq_offsets,
+                       const uint32_t* target_ids, int64_t n, uint32_t* out_windows)
+{
+    MCG_REQUIRE(db != nullptr && seq_offsets != nullptr && target_ids != nullptr, "mcg_db_add_targets: NULL argument");
+    MCG_REQUIRE(n >= 0, "n < 0");
+    if(db->finalized) { set_error("database already finalized"); return MCG_ERR_STATE; }
+    mcg_ctx* c = db->ctx;
+    MCG_CUDA(cudaSetDevice(c->device));
+    const int s = db->cfg.sketchlen;
+    // owned targets of this call, packed back to back
+    std::vector<int64_t> offs{0};
+    std::vector<int64_t> src;           // index into the caller's arrays
+    for(int64_t i = 0; i < n; ++i) {
+        if(out_windows) out_windows[i] = 0;
+        const uint32_t t = target_ids[i];
+        if(i > 0) MCG_REQUIRE(t > target_ids[i - 1], "target ids must be strictly ascending");
+        if(!db->h_tgt_id.empty()) MCG_REQUIRE(t > db->h_tgt_id.back() || int(t % uint32_t(db->nshards)) != db->shard,
+                                              "target ids must ascend across calls");
+        if(int(t % uint32_t(db->nshards)) != db->shard) continue;      // sketch_database.h:540
+        const int64_t len = seq_offsets[i + 1] - seq_offsets[i];
+        MCG_REQUIRE(len >= 0, "negative sequence length");
+        src.push_back(i);
+        offs.push_back(offs.back() + len);
+    }
+    const int64_t m = int64_t(src.size());
+    if(m == 0) return MCG_OK;
+    const int64_t total = offs.back();
+    int64_t nwin = 0;
+    std::vector<uint64_t> wins(m);
+    for(int64_t j = 0; j < m; ++j) {
+        wins[j] = uint64_t(num_windows(offs[j + 1] - offs[j], db->cfg.winlen, db->cfg.winstride));
+        MCG_REQUIRE(wins[j] < (1ull << 32), "more than 2^32-1 windows in one target");     // window_id = uint32
+        nwin += int64_t(wins[j]);
+    }
+    MCG_REQUIRE((db->nwin + uint64_t(nwin)) * uint64_t(s) < (1ull << 32),
+                "shard would exceed 2^32-1 feature slots");
+    // stage the owned sequences contiguously on the device
+    MCG_TRY(c->seq.reserve(size_t(total) + 64));
+    MCG_TRY(c->seqoff.reserve(size_t(m + 1) * 8));
+    {
+        int64_t j = 0;
+        while(j < m) {                  // coalesce runs of adjacent source targets into one copy
+            int64_t e = j;
+            while(e + 1 < m && src[e + 1] == src[e] + 1) ++e;
+            const int64_t b0 = seq_offsets[src[j]], b1 = seq_offsets[src[e] + 1];
+            MCG_TRY(copy_in(c, c->seq.as<char>() + offs[j], seq_bytes + b0, size_t(b1 - b0)));
+            j = e + 1;
+        }
+    }
+    MCG_TRY(copy_in(c, c->seqoff.p, offs.data(), size_t(m + 1) * 8));
+    // append the sketches of the new windows to the slot array
+    MCG_TRY(db->feat.reserve_keep((db->nwin + uint64_t(nwin)) * s * 4, db->nwin * s * 4, c->stream));
+    MCG_TRY(c->winfirst.reserve(size_t(m + 2) * 4));
+    MCG_TRY(window_prefix(c, db->cfg.winlen, db->cfg.winstride, c->seqoff.as<int64_t>(), m, c->winfirst.as<uint32_t>(), nullptr));
+    MCG_TRY(sketch_launch(c, db->cfg, s, db->cfg.winlen, db->cfg.winstride, c->seq.as<char>(), total,
+                          c->seqoff.as<int64_t>(), m, c->winfirst.as<uint32_t>(), c->winfirst.as<uint32_t>(),
+                          uint64_t(nwin), db->feat.as<uint32_t>() + db->nwin * s, nullptr));
+    MCG_CUDA(cudaStreamSynchronize(c->stream));       // offs (host vector) was a copy source
+    for(int64_t j = 0; j < m; ++j) {
+        db->h_tgt_id.push_back(target_ids[src[j]]);
+        db->h_tgt_firstwin.push_back(db->h_tgt_firstwin.back() + wins[j]);
+        if(out_windows) out_windows[src[j]] = uint32_t(wins[j]);
+    }
+    db->nwin += uint64_t(nwin);
+    return MCG_OK;
+}
+
+int mcg_db_finalize(mcg_db* db)
+{
+    MCG_REQUIRE(db != nullptr, "db is NULL");
+    if(db->finalized) return MCG_OK;
+    return db_finalize(db);
+}
+
+int mcg_db_counts(mcg_db* db, uint64_t* nkeys, uint64_t* nkeys_nonempty, uint64_t* nlocs)
+{
+    MCG_REQUIRE(db != nullptr, "db is NULL");
+    if(!db->finalized) { set_error("database not finalized"); return MCG_ERR_STATE; }
+    return db_counts(db, nkeys, nkeys_nonempty, nlocs);
+}
+
+static int fetch_csr(mcg_db* db, std::vector<uint32_t>& keys, std::vector<uint8_t>& sizes, std::vector<uint64_t>& offs)
+{
+    mcg_ctx* c = db->ctx;
+    keys.resize(db->nkeys); sizes.resize(db->nkeys); offs.resize(db->nkeys + 1);
+    MCG_TRY(copy_out(c, keys.data(), db->keys.p, db->nkeys * 4));
+    MCG_TRY(copy_out(c, sizes.data(), db->sizes.p, db->nkeys));
+    MCG_TRY(copy_out(c, offs.data(), db->offs.p, (db->nkeys + 1) * 8));
+    MCG_CUDA(cudaStreamSynchronize(c->stream));
+    return MCG_OK;
+}
+
+int mcg_db_export(mcg_db* db, uint32_t* keys, uint32_t* sizes, uint32_t* tgts, uint32_t* wins)
+{
+    MCG_REQUIRE(db != nullptr, "db is NULL");
+    if(!db->finalized) { set_error("database not finalized"); return MCG_ERR_STATE; }
+    mcg_ctx* c = db->ctx;
+    MCG_CUDA(cudaSetDevice(c->device));
+    std::vector<uint32_t> k; std::vector<uint8_t> sz; std::vector<uint64_t> of;
+    MCG_TRY(fetch_csr(db, k, sz, of));
+    std::vector<uint64_t> locs(db->nlocs);
+    MCG_TRY(copy_out(c, locs.data(), db->locs.p, db->nlocs * 8));
+    MCG_CUDA(cudaStreamSynchronize(c->stream));
+    uint64_t ko = 0, lo = 0;
+    for(uint64_t j = 0; j < db->nkeys; ++j) {
+        if(sz[j] == 0) continue;
+        if(keys) keys[ko] = k[j];
+        if(sizes) sizes[ko] = sz[j];
+        ++ko;
+        for(uint32_t t = 0; t < sz[j]; ++t, ++lo) {
+            const uint64_t l = locs[of[j] + t];
+            if(tgts) tgts[lo] = uint32_t(l >> 32);
+            if(wins) wins[lo] = uint32_t(l);
+        }
+    }
+    return MCG_OK;
+}
+
+int mcg_db_key_sizes(mcg_db* db, uint32_t* keys, uint32_t* sizes)
+{
+    return mcg_db_export(db, keys, sizes, nullptr, nullptr);
+}
+
+int mcg_db_import(mcg_db* db, const uint32_t* keys, const uint32_t* sizes,
+                  const uint32_t* tgts, const uint32_t* wins, uint64_t nkeys, uint64_t nlocs)
+{
+    MCG_REQUIRE(db != nullptr, "db is NULL");
+    MCG_REQUIRE(nkeys == 0 || (keys && sizes), "keys/sizes NULL");
+    MCG_REQUIRE(nlocs == 0 || (tgts && wins), "tgts/wins NULL");
+    MCG_REQUIRE(nkeys < (1ull << 32), "too many keys");
+    if(db->finalized || db->nwin > 0) { set_error("import needs an empty database"); return MCG_ERR_STATE; }
+    mcg_ctx* c = db->ctx;
+    MCG_CUDA(cudaSetDevice(c->device));
+    // bucket order of a reference-written file is table order: sort by key on the host
+    std::vector<uint64_t> start(nkeys + 1, 0);
+    for(uint64_t j = 0; j < nkeys; ++j) {
+        MCG_REQUIRE(sizes[j] <= 255, "bucket larger than 255");
+        start[j + 1] = start[j] + sizes[j];
+    }
+    MCG_REQUIRE(start[nkeys] == nlocs, "sizes do not add up to nlocs");
+    std::vector<uint32_t> order(nkeys);
+    std::iota(order.begin(), order.end(), 0u);
+    if(!std::is_sorted(keys, keys + nkeys))
+        std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return keys[a] < keys[b]; });
+    std::vector<uint32_t> k(nkeys); std::vector<uint8_t> sz(nkeys); std::vector<uint64_t> of(nkeys + 1, 0), locs(nlocs);
+    uint64_t lo = 0;
+    for(uint64_t j = 0; j < nkeys; ++j) {
+        const uint32_t o = order[j];
+        if(j > 0) MCG_REQUIRE(keys[o] != k[j - 1], "duplicate key %u", keys[o]);
+        MCG_REQUIRE(keys[o] != EMPTY_KEY, "0xFFFFFFFF is not a valid feature");
+        k[j] = keys[o];
+        sz[j] = uint8_t(sizes[o] > uint32_t(db->maxlocs) ? uint32_t(db->maxlocs) : sizes[o]);   // sketch_database.h:361-364
+        of[j] = lo;
+        for(uint32_t t = 0; t < sz[j]; ++t) locs[lo++] = (uint64_t(tgts[start[o] + t]) << 32) | wins[start[o] + t];
+    }
+    of[nkeys] = lo;
+    db->nkeys = nkeys;
+    db->nlocs = lo;
+    MCG_TRY(db->keys.reserve((nkeys + 1) * 4)); MCG_TRY(db->sizes.reserve(nkeys + 16));
+    MCG_TRY(db->offs.reserve((nkeys + 2) * 8)); MCG_TRY(db->locs.reserve((lo + 2) * 8));
+    MCG_TRY(copy_in(c, db->keys.p, k.data(), nkeys * 4));
+    MCG_TRY(copy_in(c, db->sizes.p, sz.data(), nkeys));
+    MCG_TRY(copy_in(c, db->offs.p, of.data(), (nkeys + 1) * 8));
+    MCG_TRY(copy_in(c, db->locs.p, locs.data(), lo * 8));
+    MCG_TRY(build_table(db));
+    MCG_CUDA(cudaStreamSynchronize(c->stream));
+    db->finalized = true;
+    return MCG_OK;
+}
+
+int mcg_db_remove_keys(mcg_db* db, const uint32_t* keys, uint64_t n, uint64_t* removed)
+{
+    MCG_REQUIRE(db != nullptr, "db is NULL");
+    if(!db->finalized) { set_error("database not finalized"); return MCG_ERR_STATE; }
+    if(removed) *removed = 0;
+    if(n == 0) return MCG_OK;
+    mcg_ctx* c = db->ctx;
+    MCG_CUDA(cudaSetDevice(c->device));
+    MCG_TRY(c->tmp4.reserve(n * 4));
+    MCG_TRY(copy_in(c, c->tmp4.p, keys, n * 4));
+    return db_remove_keys_dev(db, c->tmp4.as<uint32_t>(), n, removed);
+}
+
+int mcg_remove_overpopulated(mcg_db** shards, int32_t P, uint64_t* removed)
+{
+    MCG_REQUIRE(shards != nullptr && P >= 1, "bad arguments");
+    // mode_build.cpp:847-1074: sum of the per-rank (capped) bucket sizes per key; keys whose
+    // sum exceeds maxlocs-1 are cleared on every rank
+    std::vector<std::vector<uint32_t>> keys(P), sizes(P);
+    for(int r = 0; r < P; ++r) {
+        uint64_t nk = 0, ne = 0, nl = 0;
+        MCG_TRY(mcg_db_counts(shards[r], &nk, &ne, &nl));
+        keys[r].resize(ne); sizes[r].resize(ne);
+        MCG_TRY(mcg_db_key_sizes(shards[r], keys[r].data(), sizes[r].data()));
+    }
+    const uint32_t limit = uint32_t(shards[0]->maxlocs) - 1u;
+    std::vector<size_t> idx(P, 0);
+    std::vector<uint32_t> rem;
+    for(;;) {
+        bool have = false;
+        uint32_t key = 0;
+        for(int r = 0; r < P; ++r)
+            if(idx[r] < keys[r].size() && (!have || keys[r][idx[r]] < key)) { key = keys[r][idx[r]]; have = true; }
+        if(!have) break;
+        uint32_t total = 0;
+        for(int r = 0; r < P; ++r)
+            if(idx[r] < keys[r].size() && keys[r][idx[r]] == key) total += sizes[r][idx[r]++];
+        if(total > limit) rem.push_back(key);
+    }
+    uint64_t tot = 0;
+    for(int r = 0; r < P; ++r) {
+        uint64_t x = 0;
+        MCG_TRY(mcg_db_remove_keys(shards[r], rem.data(), rem.size(), &x));
+        tot += x;
+    }
+    if(removed) *removed = tot;
+    return MCG_OK;
+}
+
+}  // extern "C"

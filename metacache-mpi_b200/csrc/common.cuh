@@ -1,0 +1,141 @@
+// common.cuh -- shared host/device helpers of libmcgpu (sm_100a only)
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/mcgpu.h"
+
+namespace mcg {
+
+// ------------------------------------------------------------------ errors
+void set_error(const char* fmt, ...);
+
+#define MCG_CUDA(call)                                                              \
+    do {                                                                            \
+        cudaError_t e__ = (call);                                                   \
+        if(e__ != cudaSuccess) {                                                    \
+            mcg::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call,            \
+                           cudaGetErrorString(e__));                                \
+            return MCG_ERR_CUDA;                                                    \
+        }                                                                           \
+    } while(0)
+
+#define MCG_TRY(call)                                                               \
+    do {                                                                            \
+        int s__ = (call);                                                           \
+        if(s__ != MCG_OK) return s__;                                               \
+    } while(0)
+
+#define MCG_REQUIRE(cond, ...)                                                      \
+    do {                                                                            \
+        if(!(cond)) {                                                               \
+            mcg::set_error(__VA_ARGS__);                                            \
+            return MCG_ERR_ARG;                                                     \
+        }                                                                           \
+    } while(0)
+
+constexpr int kNumSMs = 148;          // B200: 2 dies x 74 SMs
+
+// ------------------------------------------------------------------ device memory
+// grow-only device buffer (cudaMalloc is synchronising; buffers are reused across calls)
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes);        // contents are NOT preserved
+    int reserve_keep(size_t bytes, size_t used, cudaStream_t st);   // contents preserved
+    void release();
+    template<class T> T* as() const { return static_cast<T*>(p); }
+};
+
+}  // namespace mcg
+
+// ------------------------------------------------------------------ context / db
+struct mcg_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int64_t launches = 0;
+    // taxonomy tables (replicated per GPU)
+    mcg::DevBuf lineage, rank;
+    int64_t ntaxa = 0, ntargets = 0;
+    // scratch
+    mcg::DevBuf seq, seqoff, winfirst, outfirst, tmp0, tmp1, tmp2, tmp3, tmp4, tmp5, scan_tmp;
+    mcg::DevBuf q_feat, q_flen, q_foff, q_fpos, q_loc, q_rinfo, q_cls, q_out_tax, q_out_hits, q_out_n;
+    mcg::DevBuf m_tax, m_hits, m_n, m_o_tax, m_o_hits, m_o_n, m_best, m_brank, m_stats;
+    void* pinned = nullptr;           // small pinned staging area for scalars
+    size_t pinned_cap = 0;
+};
+
+struct mcg_db {
+    mcg_ctx* ctx = nullptr;
+    mcg_sketch_cfg cfg{};
+    int maxlocs = 254;
+    int shard = 0, nshards = 1;
+    bool finalized = false;
+    // insert phase: feature slots [nslots] in window-major order + per-window (tgt,win)
+    mcg::DevBuf feat;                 // uint32[nwin_total * sketchlen]
+    uint64_t nwin = 0;
+    std::vector<uint32_t> h_tgt_id;   // owned targets in insertion order
+    std::vector<uint64_t> h_tgt_firstwin;   // first global window of each owned target (+ sentinel)
+    // finalized: CSR + open-addressing table
+    mcg::DevBuf keys, offs, sizes;    // unique keys ascending, uint64 offsets, uint8 sizes
+    mcg::DevBuf locs;                 // uint64 (tgt << 32 | win)
+    mcg::DevBuf table;                // uint4 slots {key, size, off_lo, off_hi}
+    uint64_t nkeys = 0, nlocs = 0, table_cap = 0;
+};
+
+namespace mcg {
+
+// ------------------------------------------------------------------ device helpers
+__host__ __device__ __forceinline__ uint32_t tmh(uint32_t x)
+{
+    x = ((x >> 16) ^ x) * 0x45d9f3bu;
+    x = ((x >> 16) ^ x) * 0x45d9f3bu;
+    return (x >> 16) ^ x;
+}
+
+// slot hash of the feature -> list table (features are bottom-s hash values and
+// therefore crowd the low end of the range: re-mix before reducing)
+__host__ __device__ __forceinline__ uint32_t slot_mix(uint32_t x)
+{
+    x *= 0x9E3779B1u;
+    x ^= x >> 15;
+    x *= 0x85EBCA77u;
+    x ^= x >> 13;
+    return x;
+}
+
+__host__ __device__ __forceinline__ int64_t num_windows(int64_t len, int64_t winlen, int64_t stride)
+{
+    if(len <= winlen) return 1;
+    const int64_t nfull = (len - winlen) / stride + 1;
+    return nfull + ((nfull * stride < len) ? 1 : 0);
+}
+
+inline int64_t div_up(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ------------------------------------------------------------------ primitives (scan.cu, radix_sort.cu)
+// exclusive prefix sum of n uint32 -> uint64 out[n+1] (out[n] = total)
+int exclusive_scan_u32_to_u64(mcg_ctx* c, const uint32_t* d_in, uint64_t* d_out, uint64_t n);
+// exclusive prefix sum of n uint8 -> uint64 out[n+1]
+int exclusive_scan_u8_to_u64(mcg_ctx* c, const uint8_t* d_in, uint64_t* d_out, uint64_t n);
+// stable LSD radix sort of (key,val) uint32 pairs on bits [0, key_bits); result in keys/vals
+// (alt buffers are scratch of the same size)
+int radix_sort_pairs(mcg_ctx* c, uint32_t* keys, uint32_t* vals, uint32_t* keys_alt, uint32_t* vals_alt,
+                     uint64_t n, int key_bits, bool iota_vals);
+
+// ------------------------------------------------------------------ stages
+int sketch_launch(mcg_ctx* c, const mcg_sketch_cfg& cfg, int sketchlen, int64_t winlen, int64_t stride,
+                  const char* d_seq, int64_t total_bytes, const int64_t* d_seq_off, int64_t nseq,
+                  const uint32_t* d_win_first, const uint32_t* d_out_first, uint64_t nwin,
+                  uint32_t* d_out_feat, uint32_t* d_out_cnt);
+int window_prefix(mcg_ctx* c, int64_t winlen, int64_t stride, const int64_t* d_seq_off, int64_t nseq,
+                  uint32_t* d_win_first /* nseq+1 */, uint64_t* h_total);
+
+}  // namespace mcg

@@ -1,0 +1,782 @@
+// query.cu -- K3..K6: per-shard query, cross-shard merge and decision.
+//
+// Reference semantics reproduced:
+//   sketch_database.h:806-823  accumulate_matches: for every query window, every
+//                              feature found in the table contributes its whole list
+//   querying.h:90-106          merge_sort: total order by (tgt,win), sketch_database.h:172-177
+//   candidates.h:119-180       for_all_contiguous_window_ranges: per target the largest
+//                              number of hits inside < numWindows consecutive windows
+//   classification.cpp:210-226 numWindows = 2 + max(len1+len2, insertSizeMax)/target stride
+//   candidates.h:236-285       sorted top list, stable, optional lift to -lowest + max-merge
+//   querying.h:905-971         cross-rank merge = insert in rank order
+//   classification.cpp:236-265 threshold + ranked LCA (taxonomy.h:531-537)
+//   classification_statistics.h:70-78 assign
+//
+// Pipeline per batch (all on the ctx stream):
+//   window counts -> 3 scans -> K1 (mate 1, mate 2) -> find (one 16-byte slot probe per
+//   feature) -> scan of list lengths -> read binning -> gather -> per-read bitonic sort
+//   in shared memory + window-range scan + top list (size-binned: warp / CTA / big CTA /
+//   global-memory fallback).
+#include "common.cuh"
+
+namespace mcg {
+
+int copy_in(mcg_ctx* c, void* d, const void* h, size_t bytes);
+int copy_out(mcg_ctx* c, void* h, const void* d, size_t bytes);
+int exclusive_scan_u32_to_u32(mcg_ctx* c, const uint32_t* d_in, uint32_t* d_out, uint64_t n);
+
+constexpr uint32_t EMPTY_KEY = 0xFFFFFFFFu;
+constexpr int Q_SMALL = 512;       // matches per read handled by one warp
+constexpr int Q_MED = 4096;        // by one 256-thread CTA
+constexpr int Q_LARGE = 16384;     // by one 512-thread CTA with 192 KB of shared memory
+
+static inline unsigned grid_for(uint64_t n, int threads = 256) { return unsigned((n + threads - 1) / threads); }
+
+// ------------------------------------------------------------------ window bookkeeping
+__global__ void q_window_counts_kernel(const int64_t* offs1, const int64_t* offs2, int64_t n,
+                                       int64_t winlen, int64_t stride,
+                                       uint32_t* nw1, uint32_t* nw2, uint32_t* nws)
+{
+    const int64_t r = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+    if(r >= n) return;
+    const uint32_t a = uint32_t(num_windows(offs1[r + 1] - offs1[r], winlen, stride));
+    const uint32_t b = offs2 ? uint32_t(num_windows(offs2[r + 1] - offs2[r], winlen, stride)) : 0u;
+    nw1[r] = a;
+    nw2[r] = b;
+    nws[r] = a + b;
+}
+
+__global__ void q_out_first2_kernel(const uint32_t* W, const uint32_t* wf1, int64_t n, uint32_t* of2)
+{
+    const int64_t r = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+    if(r < n) of2[r] = W[r] + (wf1[r + 1] - wf1[r]);
+}
+
+// ------------------------------------------------------------------ K3: find
+__device__ __forceinline__ uint64_t table_slot(uint32_t key, uint64_t cap)
+{
+    return (uint64_t(slot_mix(key)) * cap) >> 32;
+}
+
+// hash_multimap.h:779-789 / 1034-1047 find: probe until key or unused slot
+__global__ void __launch_bounds__(256)
+q_find_kernel(const uint32_t* __restrict__ feat, uint64_t nslots, const uint4* __restrict__ table, uint64_t cap,
+              uint8_t* __restrict__ flen, uint64_t* __restrict__ foff)
+{
+    const uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
+    if(i >= nslots) return;
+    const uint32_t f = feat[i];
+    uint32_t len = 0;
+    uint64_t off = 0;
+    if(f != EMPTY_KEY) {
+        uint64_t s = table_slot(f, cap);
+        for(;;) {
+            const uint4 e = __ldg(&table[s]);
+            if(e.x == f) { len = e.y; off = uint64_t(e.z) | (uint64_t(e.w) << 32); break; }
+            if(e.x == EMPTY_KEY) break;
+            if(++s == cap) s = 0;
+        }
+    }
+    flen[i] = uint8_t(len);
+    foff[i] = off;
+}
+
+// ------------------------------------------------------------------ read binning
+// counters: [0] small [1] medium [2] large [3] xl
+__global__ void q_bin_reads_kernel(const uint64_t* fpos, const uint32_t* W, int s, int64_t n,
+                                   uint32_t* lists /* [4][n] */, uint32_t* counters,
+                                   int32_t* out_n)
+{
+    const int64_t r = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+    if(r >= n) return;
+    const uint64_t m = fpos[uint64_t(W[r + 1]) * s] - fpos[uint64_t(W[r]) * s];
+    if(m == 0) { out_n[r] = 0; return; }
+    const int cls = m <= Q_SMALL ? 0 : (m <= Q_MED ? 1 : (m <= Q_LARGE ? 2 : 3));
+    const uint32_t p = atomicAdd(&counters[cls], 1u);
+    lists[uint64_t(cls) * n + p] = uint32_t(r);
+}
+
+// ------------------------------------------------------------------ gather
+__global__ void __launch_bounds__(256)
+q_gather_kernel(const uint8_t* __restrict__ flen, const uint64_t* __restrict__ foff, const uint64_t* __restrict__ fpos,
+                uint64_t nslots, const uint64_t* __restrict__ locs, uint64_t* __restrict__ out)
+{
+    const int lane = threadIdx.x & 31;
+    const uint64_t slot = (blockIdx.x * uint64_t(blockDim.x) + threadIdx.x);
+    uint32_t len = 0;
+    uint64_t off = 0, pos = 0;
+    if(slot < nslots) {
+        len = flen[slot];
+        if(len) { off = foff[slot]; pos = fpos[slot]; }
+    }
+    if(len > 0 && len <= 2) {
+        out[pos] = locs[off];
+        if(len == 2) out[pos + 1] = locs[off + 1];
+    }
+    uint32_t big = __ballot_sync(0xFFFFFFFFu, len > 2);
+    while(big) {
+        const int src = __ffs(big) - 1;
+        big &= big - 1;
+        const uint32_t L = __shfl_sync(0xFFFFFFFFu, len, src);
+        const uint64_t O = __shfl_sync(0xFFFFFFFFu, off, src);
+        const uint64_t P = __shfl_sync(0xFFFFFFFFu, pos, src);
+        for(uint32_t t = lane; t < L; t += 32) out[P + t] = locs[O + t];
+    }
+}
+
+// ------------------------------------------------------------------ top list (candidates.h:236-285)
+struct TopK {
+    int32_t tax[MCG_MAX_CAND];
+    uint32_t hits[MCG_MAX_CAND];
+    int n;
+};
+
+__device__ __forceinline__ void topk_insert(TopK& L, int K, int32_t tax, uint32_t hits, int lowest,
+                                            const int32_t* __restrict__ lineage, const uint8_t* __restrict__ rank)
+{
+    if(tax < 0) return;
+    if(lowest > MCG_RANK_SEQUENCE) {
+        const int32_t anc = lineage[int64_t(tax) * MCG_NUM_RANKS + lowest];
+        if(anc >= 0) tax = anc;
+    }
+    int pos = -1;
+    if(rank[tax] != MCG_RANK_SEQUENCE) {
+        for(int i = 0; i < L.n; ++i) if(L.tax[i] == tax) { pos = i; break; }
+    }
+    if(pos >= 0) {
+        // taxon already listed: keep the larger hit count, restore order (stable)
+        uint32_t h = L.hits[pos];
+        if(hits > h) h = hits;
+        int j = pos;
+        while(j > 0 && L.hits[j - 1] < h) { L.tax[j] = L.tax[j - 1]; L.hits[j] = L.hits[j - 1]; --j; }
+        L.tax[j] = tax;
+        L.hits[j] = h;
+        return;
+    }
+    int i = 0;
+    while(i < L.n && L.hits[i] >= hits) ++i;         // upper_bound in a descending list
+    if(i < L.n || L.n < K) {
+        const int last = L.n < K ? L.n : K - 1;
+        for(int j = last; j > i; --j) { L.tax[j] = L.tax[j - 1]; L.hits[j] = L.hits[j - 1]; }
+        L.tax[i] = tax;
+        L.hits[i] = hits;
+        if(L.n < K) L.n++;
+    }
+}
+
+// ------------------------------------------------------------------ K4 + K5
+struct CandParams {
+    const uint64_t* fpos;
+    const uint32_t* W;
+    int s;
+    const int64_t* offs1;
+    const int64_t* offs2;
+    int64_t insertsize;
+    int64_t tstride;
+    uint64_t* loc;
+    uint32_t* hits_scratch;      // only for the global-memory class
+    const uint32_t* list;
+    const uint32_t* list_count;
+    int K;
+    int lowest;
+    const int32_t* lineage;
+    const uint8_t* rank;
+    int32_t* out_tax;
+    uint32_t* out_hits;
+    int32_t* out_n;
+    int write_sorted;
+};
+
+template<bool WARP>
+__device__ __forceinline__ void gsync()
+{
+    if(WARP) __syncwarp(); else __syncthreads();
+}
+
+// ascending bitonic network in the "flip" formulation: every comparator is (lo < hi,
+// ascending), so elements beyond m behave as +infinity without being stored
+template<bool WARP>
+__device__ __forceinline__ void bitonic_sort(uint64_t* A, uint32_t m, int tid, int nt)
+{
+    uint32_t P = 1;
+    while(P < m) P <<= 1;
+    const uint32_t half = P >> 1;
+    for(uint32_t k = 2; k <= P; k <<= 1) {
+        const uint32_t hk = k >> 1;
+        for(uint32_t t = tid; t < half; t += nt) {
+            const uint32_t blk = t / hk, o = t % hk;
+            const uint32_t lo = blk * k + o, hi = blk * k + k - 1 - o;
+            if(hi < m) {
+                const uint64_t a = A[lo], b = A[hi];
+                if(a > b) { A[lo] = b; A[hi] = a; }
+            }
+        }
+        gsync<WARP>();
+        for(uint32_t j = hk >> 1; j > 0; j >>= 1) {
+            for(uint32_t t = tid; t < half; t += nt) {
+                const uint32_t lo = (t / j) * (j << 1) + (t % j), hi = lo + j;
+                if(hi < m) {
+                    const uint64_t a = A[lo], b = A[hi];
+                    if(a > b) { A[lo] = b; A[hi] = a; }
+                }
+            }
+            gsync<WARP>();
+        }
+    }
+}
+
+// one read: A = its matches (shared or global memory), Hh = scratch of m uint32
+template<bool WARP>
+__device__ __forceinline__ void process_read(const CandParams& p, uint32_t r, uint64_t* A, uint32_t* Hh, uint32_t m,
+                                             uint64_t* gsrc, bool staged, int tid, int nt)
+{
+    if(staged) {
+        for(uint32_t i = tid; i < m; i += nt) A[i] = gsrc[i];
+        gsync<WARP>();
+    }
+    bitonic_sort<WARP>(A, m, tid, nt);
+    if(staged && p.write_sorted) {
+        for(uint32_t i = tid; i < m; i += nt) gsrc[i] = A[i];
+    }
+    // window-range width of this read (classification.cpp:217-219)
+    int64_t span = p.offs1[r + 1] - p.offs1[r];
+    if(p.offs2) span += p.offs2[r + 1] - p.offs2[r];
+    if(p.insertsize > span) span = p.insertsize;
+    const uint32_t numwin = uint32_t(2 + span / p.tstride);
+    // hits of the best range ENDING at each element
+    for(uint32_t i = tid; i < m; i += nt) {
+        const uint64_t key = A[i];
+        const uint32_t win = uint32_t(key);
+        const uint64_t lowkey = (key & 0xFFFFFFFF00000000ull) | (win >= numwin - 1 ? win - (numwin - 1) : 0u);
+        uint32_t lo = 0, hi = i;                 // first index with A[idx] >= lowkey, in [0, i]
+        while(lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if(A[mid] < lowkey) lo = mid + 1; else hi = mid;
+        }
+        Hh[i] = i - lo + 1;
+    }
+    gsync<WARP>();
+    // the last element of each target run collects the run's maximum
+    for(uint32_t i = tid; i < m; i += nt) {
+        const uint32_t tgt = uint32_t(A[i] >> 32);
+        if(i + 1 < m && uint32_t(A[i + 1] >> 32) == tgt) continue;
+        uint32_t best = Hh[i];
+        for(uint32_t j = i; j > 0 && uint32_t(A[j - 1] >> 32) == tgt; --j) best = max(best, Hh[j - 1]);
+        Hh[i] = best;
+    }
+    gsync<WARP>();
+    if(tid == 0) {
+        TopK L;
+        L.n = 0;
+        for(uint32_t i = 0; i < m; ++i) {
+            const uint32_t tgt = uint32_t(A[i] >> 32);
+            if(i + 1 < m && uint32_t(A[i + 1] >> 32) == tgt) continue;
+            topk_insert(L, p.K, int32_t(tgt), Hh[i], p.lowest, p.lineage, p.rank);
+        }
+        for(int c = 0; c < p.K; ++c) {
+            p.out_tax[uint64_t(r) * p.K + c] = c < L.n ? L.tax[c] : -1;
+            p.out_hits[uint64_t(r) * p.K + c] = c < L.n ? L.hits[c] : 0u;
+        }
+        p.out_n[r] = L.n;
+    }
+    gsync<WARP>();
+}
+
+// small reads: one warp per read
+__global__ void __launch_bounds__(256)
+q_cand_warp_kernel(const CandParams p)
+{
+    extern __shared__ __align__(16) unsigned char sm[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint64_t* A = reinterpret_cast<uint64_t*>(sm) + size_t(warp) * Q_SMALL;
+    uint32_t* Hh = reinterpret_cast<uint32_t*>(sm + size_t(8) * Q_SMALL * 8) + size_t(warp) * Q_SMALL;
+    const uint32_t cnt = *p.list_count;
+    for(uint32_t it = blockIdx.x * 8 + warp; it < cnt; it += gridDim.x * 8) {
+        const uint32_t r = p.list[it];
+        const uint64_t beg = p.fpos[uint64_t(p.W[r]) * p.s];
+        const uint32_t m = uint32_t(p.fpos[uint64_t(p.W[r + 1]) * p.s] - beg);
+        process_read<true>(p, r, A, Hh, m, p.loc + beg, true, lane, 32);
+    }
+}
+
+// medium / large reads: one CTA per read, capacity fixed by the launch
+__global__ void q_cand_cta_kernel(const CandParams p, uint32_t capacity)
+{
+    extern __shared__ __align__(16) unsigned char sm[];
+    uint64_t* A = reinterpret_cast<uint64_t*>(sm);
+    uint32_t* Hh = reinterpret_cast<uint32_t*>(sm + size_t(capacity) * 8);
+    const uint32_t cnt = *p.list_count;
+    for(uint32_t it = blockIdx.x; it < cnt; it += gridDim.x) {
+        const uint32_t r = p.list[it];
+        const uint64_t beg = p.fpos[uint64_t(p.W[r]) * p.s];
+        const uint32_t m = uint32_t(p.fpos[uint64_t(p.W[r + 1]) * p.s] - beg);
+        process_read<false>(p, r, A, Hh, m, p.loc + beg, true, threadIdx.x, blockDim.x);
+    }
+}
+
+// oversized reads: sorted in place in global memory by one CTA (correctness fallback)
+__global__ void __launch_bounds__(1024)
+q_cand_global_kernel(const CandParams p)
+{
+    const uint32_t cnt = *p.list_count;
+    for(uint32_t it = blockIdx.x; it < cnt; it += gridDim.x) {
+        const uint32_t r = p.list[it];
+        const uint64_t beg = p.fpos[uint64_t(p.W[r]) * p.s];
+        const uint64_t m64 = p.fpos[uint64_t(p.W[r + 1]) * p.s] - beg;
+        process_read<false>(p, r, p.loc + beg, p.hits_scratch + beg, uint32_t(m64), p.loc + beg, false, threadIdx.x, blockDim.x);
+    }
+}
+
+__global__ void q_split_locs_kernel(const uint64_t* loc, uint64_t n, uint32_t* tg, uint32_t* wn)
+{
+    const uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
+    if(i < n) { tg[i] = uint32_t(loc[i] >> 32); wn[i] = uint32_t(loc[i]); }
+}
+
+__global__ void q_read_counts_kernel(const uint64_t* fpos, const uint32_t* W, int s, int64_t n, int64_t* out)
+{
+    const int64_t r = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+    if(r < n) out[r] = int64_t(fpos[uint64_t(W[r + 1]) * s] - fpos[uint64_t(W[r]) * s]);
+}
+
+// ------------------------------------------------------------------ K6: merge + classify + statistics
+struct MergeParams {
+    const int32_t* cand_tax;
+    const uint32_t* cand_hits;
+    const int32_t* cand_n;
+    int P;
+    int64_t n;
+    int K;
+    int lowest, highest, hitmin;
+    float hitdiff;
+    const int32_t* lineage;
+    const uint8_t* rank;
+    int32_t* out_tax;
+    uint32_t* out_hits;
+    int32_t* out_n;
+    int32_t* out_best;
+    int32_t* out_brank;
+    unsigned long long* stats;
+};
+
+__global__ void __launch_bounds__(128)
+q_merge_classify_kernel(const MergeParams p)
+{
+    __shared__ unsigned int s_stats[22];
+    if(threadIdx.x < 22) s_stats[threadIdx.x] = 0;
+    __syncthreads();
+    const int64_t r = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+    if(r < p.n) {
+        TopK L;
+        L.n = 0;
+        for(int q = 0; q < p.P; ++q) {                       // rank order (querying.h:905-971)
+            const int64_t row = int64_t(q) * p.n + r;
+            const int cnt = p.cand_n[row];
+            for(int c = 0; c < cnt; ++c)
+                topk_insert(L, p.K, p.cand_tax[row * p.K + c], p.cand_hits[row * p.K + c], p.lowest, p.lineage, p.rank);
+        }
+        for(int c = 0; c < p.K; ++c) {
+            p.out_tax[r * p.K + c] = c < L.n ? L.tax[c] : -1;
+            p.out_hits[r * p.K + c] = c < L.n ? L.hits[c] : 0u;
+        }
+        p.out_n[r] = L.n;
+        // classification.cpp:236-265
+        int32_t lca = -1;
+        if(L.n > 0 && L.hits[0] >= uint32_t(p.hitmin)) {
+            lca = L.tax[0];
+            const float thr = L.hits[0] > uint32_t(p.hitmin)
+                            ? __fmul_rn(__uint2float_rn(L.hits[0] - uint32_t(p.hitmin)), p.hitdiff) : 0.0f;
+            for(int i = 1; i < L.n; ++i) {
+                if(!(__uint2float_rn(L.hits[i]) > thr)) break;
+                // taxonomy.h:531-537 ranked_lca
+                const int32_t* la = p.lineage + int64_t(lca) * MCG_NUM_RANKS;
+                const int32_t* lb = p.lineage + int64_t(L.tax[i]) * MCG_NUM_RANKS;
+                int32_t x = -1;
+                for(int k = 0; k < MCG_NUM_RANKS; ++k) {
+                    const int32_t a = la[k];
+                    if(a >= 0 && a == lb[k]) { x = a; break; }
+                }
+                lca = x;
+                if(lca < 0 || int(p.rank[lca]) > p.highest) { lca = -1; break; }
+            }
+            if(lca >= 0 && int(p.rank[lca]) > p.highest) lca = -1;
+        }
+        const int br = lca >= 0 ? int(p.rank[lca]) : MCG_RANK_NONE;
+        p.out_best[r] = lca;
+        p.out_brank[r] = br;
+        // classification_statistics.h:70-78
+        if(br >= MCG_RANK_NONE) atomicAdd(&s_stats[MCG_RANK_NONE], 1u);
+        else for(int k = br; k < MCG_NUM_RANKS; ++k) atomicAdd(&s_stats[k], 1u);
+    }
+    __syncthreads();
+    if(p.stats != nullptr && threadIdx.x < 22 && s_stats[threadIdx.x] != 0)
+        atomicAdd(&p.stats[threadIdx.x], (unsigned long long)s_stats[threadIdx.x]);
+}
+
+// ------------------------------------------------------------------ host orchestration
+struct QueryRun {
+    uint64_t nwin = 0, nslots = 0, total = 0;
+    uint32_t cls[4] = {0, 0, 0, 0};
+};
+
+static int check_opts(const mcg_db* db, const mcg_query_opts* o)
+{
+    MCG_REQUIRE(o->sketchlen >= 1 && o->sketchlen <= MCG_MAX_SKETCH, "query sketchlen %d outside 1..%d", o->sketchlen, MCG_MAX_SKETCH);
+    MCG_REQUIRE(o->winlen >= 1 && o->winstride >= 1, "query window length / stride must be >= 1");
+    MCG_REQUIRE(o->maxcand >= 1 && o->maxcand <= MCG_MAX_CAND, "maxcand %d outside 1..%d (unlimited lists are not supported on the device)", o->maxcand, MCG_MAX_CAND);
+    MCG_REQUIRE(o->lowest >= 0 && o->lowest < MCG_NUM_RANKS && o->highest >= 0 && o->highest < MCG_NUM_RANKS, "rank out of range");
+    (void)db;
+    return MCG_OK;
+}
+
+// stages a..g: everything up to (and including) the gather.  Reads are on the device.
+static int query_front(mcg_db* db, const mcg_query_opts* o,
+                       const char* d1, const int64_t* doffs1, int64_t bytes1,
+                       const char* d2, const int64_t* doffs2, int64_t bytes2, int64_t n,
+                       int32_t* d_out_n, QueryRun* run)
+{
+    mcg_ctx* c = db->ctx;
+    const int s = o->sketchlen;
+    // window bookkeeping: wf1, wf2 (processing-order prefixes), W (output prefix), of2
+    MCG_TRY(c->tmp0.reserve(size_t(n + 2) * 4));
+    MCG_TRY(c->tmp1.reserve(size_t(n + 2) * 4));
+    MCG_TRY(c->tmp2.reserve(size_t(n + 2) * 4));
+    MCG_TRY(c->tmp3.reserve(size_t(n + 2) * 4));
+    uint32_t* wf1 = c->tmp0.as<uint32_t>();
+    uint32_t* wf2 = c->tmp1.as<uint32_t>();
+    uint32_t* W = c->tmp2.as<uint32_t>();
+    uint32_t* of2 = c->tmp3.as<uint32_t>();
+    q_window_counts_kernel<<<grid_for(n), 256, 0, c->stream>>>(doffs1, d2 ? doffs2 : nullptr, n, o->winlen, o->winstride, wf1, wf2, W);
+    c->launches++;
+    MCG_TRY(exclusive_scan_u32_to_u32(c, wf1, wf1, n));
+    MCG_TRY(exclusive_scan_u32_to_u32(c, wf2, wf2, n));
+    MCG_TRY(exclusive_scan_u32_to_u32(c, W, W, n));
+    q_out_first2_kernel<<<grid_for(n), 256, 0, c->stream>>>(W, wf1, n, of2);
+    c->launches++;
+    uint32_t h_tot[3] = {0, 0, 0};
+    MCG_CUDA(cudaMemcpyAsync(&h_tot[0], wf1 + n, 4, cudaMemcpyDeviceToHost, c->stream));
+    MCG_CUDA(cudaMemcpyAsync(&h_tot[1], wf2 + n, 4, cudaMemcpyDeviceToHost, c->stream));
+    MCG_CUDA(cudaMemcpyAsync(&h_tot[2], W + n, 4, cudaMemcpyDeviceToHost, c->stream));
+    MCG_CUDA(cudaStreamSynchronize(c->stream));
+    const uint64_t nwin = h_tot[2];
+    const uint64_t nslots = nwin * uint64_t(s);
+    run->nwin = nwin;
+    run->nslots = nslots;
+    // K1 on both mates, sketches land read-major
+    MCG_TRY(c->q_feat.reserve((nslots + 1) * 4));
+    mcg_sketch_cfg cfg = db->cfg;
+    MCG_TRY(sketch_launch(c, cfg, s, o->winlen, o->winstride, d1, bytes1, doffs1, n, wf1, W, h_tot[0], c->q_feat.as<uint32_t>(), nullptr));
+    if(d2) MCG_TRY(sketch_launch(c, cfg, s, o->winlen, o->winstride, d2, bytes2, doffs2, n, wf2, of2, h_tot[1], c->q_feat.as<uint32_t>(), nullptr));
+    // K3: find
+    MCG_TRY(c->q_flen.reserve(nslots + 16));
+    MCG_TRY(c->q_foff.reserve((nslots + 1) * 8));
+    MCG_TRY(c->q_fpos.reserve((nslots + 2) * 8));
+    if(nslots > 0) {
+        q_find_kernel<<<grid_for(nslots), 256, 0, c->stream>>>(c->q_feat.as<uint32_t>(), nslots, db->table.as<uint4>(), db->table_cap,
+                                                              c->q_flen.as<uint8_t>(), c->q_foff.as<uint64_t>());
+        c->launches++;
+    }
+    MCG_TRY(exclusive_scan_u8_to_u64(c, c->q_flen.as<uint8_t>(), c->q_fpos.as<uint64_t>(), nslots));
+    // binning (also writes out_n = 0 for reads without matches)
+    MCG_TRY(c->q_cls.reserve(size_t(4) * size_t(n) * 4 + 64));
+    MCG_TRY(c->q_rinfo.reserve(64));
+    uint32_t* counters = c->q_rinfo.as<uint32_t>();
+    MCG_CUDA(cudaMemsetAsync(counters, 0, 16, c->stream));
+    q_bin_reads_kernel<<<grid_for(n), 256, 0, c->stream>>>(c->q_fpos.as<uint64_t>(), W, s, n, c->q_cls.as<uint32_t>(), counters, d_out_n);
+    c->launches++;
+    uint64_t total = 0;
+    MCG_CUDA(cudaMemcpyAsync(&total, c->q_fpos.as<uint64_t>() + nslots, 8, cudaMemcpyDeviceToHost, c->stream));
+    MCG_CUDA(cudaMemcpyAsync(run->cls, counters, 16, cudaMemcpyDeviceToHost, c->stream));
+    MCG_CUDA(cudaStreamSynchronize(c->stream));
+    run->total = total;
+    // gather
+    MCG_TRY(c->q_loc.reserve((total + 2) * 8));
+    if(nslots > 0 && total > 0) {
+        q_gather_kernel<<<grid_for(nslots), 256, 0, c->stream>>>(c->q_flen.as<uint8_t>(), c->q_foff.as<uint64_t>(), c->q_fpos.as<uint64_t>(),
+                                                                nslots, db->locs.as<uint64_t>(), c->q_loc.as<uint64_t>());
+        c->launches++;
+    }
+    MCG_CUDA(cudaGetLastError());
+    return MCG_OK;
+}
+
+static int query_back(mcg_db* db, const mcg_query_opts* o, const int64_t* doffs1, const int64_t* doffs2, int64_t n,
+                      const QueryRun& run, int32_t* d_out_tax, uint32_t* d_out_hits, int32_t* d_out_n, int write_sorted)
+{
+    mcg_ctx* c = db->ctx;
+    CandParams p;
+    p.fpos = c->q_fpos.as<uint64_t>();
+    p.W = c->tmp2.as<uint32_t>();
+    p.s = o->sketchlen;
+    p.offs1 = doffs1;
+    p.offs2 = doffs2;
+    p.insertsize = o->insertsize;
+    p.tstride = db->cfg.winstride;
+    p.loc = c->q_loc.as<uint64_t>();
+    p.hits_scratch = nullptr;
+    p.K = o->maxcand;
+    p.lowest = o->lowest;
+    p.lineage = c->lineage.as<int32_t>();
+    p.rank = c->rank.as<uint8_t>();
+    p.out_tax = d_out_tax;
+    p.out_hits = d_out_hits;
+    p.out_n = d_out_n;
+    p.write_sorted = write_sorted;
+    const uint32_t* lists = c->q_cls.as<uint32_t>();
+    const uint32_t* counters = c->q_rinfo.as<uint32_t>();
+    static bool configured = false;
+    if(!configured) {
+        MCG_CUDA(cudaFuncSetAttribute(q_cand_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * Q_SMALL * 12));
+        MCG_CUDA(cudaFuncSetAttribute(q_cand_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Q_LARGE * 12));
+        configured = true;
+    }
+    if(run.cls[0] > 0) {
+        p.list = lists; p.list_count = counters;
+        const unsigned g = unsigned(std::min<uint64_t>((run.cls[0] + 7) / 8, uint64_t(kNumSMs) * 16));
+        q_cand_warp_kernel<<<g, 256, 8 * Q_SMALL * 12, c->stream>>>(p);
+        c->launches++;
+    }
+    if(run.cls[1] > 0) {
+        p.list = lists + uint64_t(n); p.list_count = counters + 1;
+        const unsigned g = unsigned(std::min<uint64_t>(run.cls[1], uint64_t(kNumSMs) * 8));
+        q_cand_cta_kernel<<<g, 256, Q_MED * 12, c->stream>>>(p, Q_MED);
+        c->launches++;
+    }
+    if(run.cls[2] > 0) {
+        p.list = lists + uint64_t(2) * n; p.list_count = counters + 2;
+        const unsigned g = unsigned(std::min<uint64_t>(run.cls[2], uint64_t(kNumSMs) * 2));
+        q_cand_cta_kernel<<<g, 512, Q_LARGE * 12, c->stream>>>(p, Q_LARGE);
+        c->launches++;
+    }
+    if(run.cls[3] > 0) {
+        MCG_TRY(c->tmp4.reserve((run.total + 2) * 4));
+        p.hits_scratch = c->tmp4.as<uint32_t>();
+        p.list = lists + uint64_t(3) * n; p.list_count = counters + 3;
+        const unsigned g = unsigned(std::min<uint64_t>(run.cls[3], uint64_t(kNumSMs) * 2));
+        q_cand_global_kernel<<<g, 1024, 0, c->stream>>>(p);
+        c->launches++;
+    }
+    MCG_CUDA(cudaGetLastError());
+    return MCG_OK;
+}
+
+int query_batch_dev(mcg_db* db, const mcg_query_opts* o,
+                    const char* d1, const int64_t* doffs1, int64_t bytes1,
+                    const char* d2, const int64_t* doffs2, int64_t bytes2, int64_t n,
+                    int32_t* d_out_tax, uint32_t* d_out_hits, int32_t* d_out_n, int write_sorted, QueryRun* run_out)
+{
+    mcg_ctx* c = db->ctx;
+    MCG_CUDA(cudaSetDevice(c->device));
+    MCG_TRY(check_opts(db, o));
+    if(!db->finalized) { set_error("database not finalized"); return MCG_ERR_STATE; }
+    if(c->lineage.p == nullptr) { set_error("taxonomy not uploaded (mcg_tax_upload)"); return MCG_ERR_STATE; }
+    if(n == 0) return MCG_OK;
+    MCG_REQUIRE(n < (1ll << 31), "more than 2^31-1 reads in one batch");
+    const int K = o->maxcand;
+    // unused slots: taxon -1, hits 0
+    MCG_CUDA(cudaMemsetAsync(d_out_tax, 0xFF, size_t(n) * K * 4, c->stream));
+    MCG_CUDA(cudaMemsetAsync(d_out_hits, 0, size_t(n) * K * 4, c->stream));
+    QueryRun run;
+    MCG_TRY(query_front(db, o, d1, doffs1, bytes1, d2, doffs2, bytes2, n, d_out_n, &run));
+    MCG_TRY(query_back(db, o, doffs1, d2 ? doffs2 : nullptr, n, run, d_out_tax, d_out_hits, d_out_n, write_sorted));
+    if(run_out) *run_out = run;
+    return MCG_OK;
+}
+
+// host reads -> device staging (reads1 | reads2 share one buffer)
+static int stage_reads(mcg_ctx* c, const char* reads1, const int64_t* offs1, const char* reads2, const int64_t* offs2, int64_t n,
+                       const char** d1, const int64_t** do1, int64_t* b1, const char** d2, const int64_t** do2, int64_t* b2)
+{
+    MCG_REQUIRE(offs1 != nullptr && offs1[0] == 0, "offs1[0] must be 0");
+    *b1 = offs1[n];
+    *b2 = 0;
+    if(reads2 != nullptr) {
+        MCG_REQUIRE(offs2 != nullptr && offs2[0] == 0, "offs2[0] must be 0");
+        *b2 = offs2[n];
+    }
+    const size_t pad1 = (size_t(*b1) + 63) & ~size_t(63);
+    MCG_TRY(c->seq.reserve(pad1 + size_t(*b2) + 64));
+    MCG_TRY(c->seqoff.reserve(size_t(2) * size_t(n + 1) * 8));
+    MCG_TRY(copy_in(c, c->seq.p, reads1, size_t(*b1)));
+    MCG_TRY(copy_in(c, c->seqoff.p, offs1, size_t(n + 1) * 8));
+    *d1 = c->seq.as<char>();
+    *do1 = c->seqoff.as<int64_t>();
+    *d2 = nullptr;
+    *do2 = nullptr;
+    if(reads2 != nullptr) {
+        MCG_TRY(copy_in(c, c->seq.as<char>() + pad1, reads2, size_t(*b2)));
+        MCG_TRY(copy_in(c, c->seqoff.as<int64_t>() + (n + 1), offs2, size_t(n + 1) * 8));
+        *d2 = c->seq.as<char>() + pad1;
+        *do2 = c->seqoff.as<int64_t>() + (n + 1);
+    }
+    return MCG_OK;
+}
+
+}  // namespace mcg
+
+using namespace mcg;
+
+extern "C" {
+
+int mcg_tax_upload(mcg_ctx* c, const int32_t* lineage, const uint8_t* rank, int64_t ntaxa, int64_t ntargets)
+{
+    MCG_REQUIRE(c != nullptr && lineage != nullptr && rank != nullptr, "mcg_tax_upload: NULL argument");
+    MCG_REQUIRE(ntaxa >= 1 && ntargets >= 0 && ntargets <= ntaxa && ntaxa < (1ll << 31), "bad taxon counts");
+    for(int64_t t = 0; t < ntaxa; ++t) {
+        MCG_REQUIRE(rank[t] <= MCG_RANK_NONE, "taxon %lld has rank %d", (long long)t, int(rank[t]));
+        for(int r = 0; r < MCG_NUM_RANKS; ++r) {
+            const int32_t x = lineage[t * MCG_NUM_RANKS + r];
+            MCG_REQUIRE(x >= -1 && x < ntaxa, "lineage entry out of range");
+        }
+    }
+    MCG_CUDA(cudaSetDevice(c->device));
+    MCG_TRY(c->lineage.reserve(size_t(ntaxa) * MCG_NUM_RANKS * 4));
+    MCG_TRY(c->rank.reserve(size_t(ntaxa)));
+    MCG_TRY(copy_in(c, c->lineage.p, lineage, size_t(ntaxa) * MCG_NUM_RANKS * 4));
+    MCG_TRY(copy_in(c, c->rank.p, rank, size_t(ntaxa)));
+    MCG_CUDA(cudaStreamSynchronize(c->stream));
+    c->ntaxa = ntaxa;
+    c->ntargets = ntargets;
+    return MCG_OK;
+}
+
+int mcg_query_batch_dev(mcg_db* db, const mcg_query_opts* o,
+                        const char* d_reads1, const int64_t* d_offs1, int64_t bytes1,
+                        const char* d_reads2, const int64_t* d_offs2, int64_t bytes2,
+                        int64_t n, int64_t max_read_len,
+                        int32_t* d_out_tax, uint32_t* d_out_hits, int32_t* d_out_ncand)
+{
+    MCG_REQUIRE(db != nullptr && o != nullptr && d_reads1 != nullptr && d_offs1 != nullptr, "mcg_query_batch_dev: NULL argument");
+    MCG_REQUIRE(n >= 0, "n < 0");
+    (void)max_read_len;
+    return query_batch_dev(db, o, d_reads1, d_offs1, bytes1, d_reads2, d_offs2, bytes2, n,
+                           d_out_tax, d_out_hits, d_out_ncand, 0, nullptr);
+}
+
+int mcg_query_batch(mcg_db* db, const mcg_query_opts* o,
+                    const char* reads1, const int64_t* offs1,
+                    const char* reads2, const int64_t* offs2, int64_t n,
+                    int32_t* out_tax, uint32_t* out_hits, int32_t* out_ncand)
+{
+    MCG_REQUIRE(db != nullptr && o != nullptr && reads1 != nullptr && offs1 != nullptr, "mcg_query_batch: NULL argument");
+    MCG_REQUIRE(n >= 0, "n < 0");
+    if(n == 0) return MCG_OK;
+    MCG_REQUIRE(out_tax && out_hits && out_ncand, "output buffers are NULL");
+    mcg_ctx* c = db->ctx;
+    MCG_CUDA(cudaSetDevice(c->device));
+    MCG_TRY(check_opts(db, o));
+    const char *d1, *d2; const int64_t *do1, *do2; int64_t b1, b2;
+    MCG_TRY(stage_reads(c, reads1, offs1, reads2, offs2, n, &d1, &do1, &b1, &d2, &do2, &b2));
+    const int K = o->maxcand;
+    MCG_TRY(c->q_out_tax.reserve(size_t(n) * K * 4));
+    MCG_TRY(c->q_out_hits.reserve(size_t(n) * K * 4));
+    MCG_TRY(c->q_out_n.reserve(size_t(n) * 4));
+    MCG_TRY(query_batch_dev(db, o, d1, do1, b1, d2, do2, b2, n, c->q_out_tax.as<int32_t>(), c->q_out_hits.as<uint32_t>(),
+                            c->q_out_n.as<int32_t>(), 0, nullptr));
+    MCG_TRY(copy_out(c, out_tax, c->q_out_tax.p, size_t(n) * K * 4));
+    MCG_TRY(copy_out(c, out_hits, c->q_out_hits.p, size_t(n) * K * 4));
+    MCG_TRY(copy_out(c, out_ncand, c->q_out_n.p, size_t(n) * 4));
+    MCG_CUDA(cudaStreamSynchronize(c->stream));
+    return MCG_OK;
+}
+
+int mcg_query_matches(mcg_db* db, const mcg_query_opts* o,
+                      const char* reads1, const int64_t* offs1,
+                      const char* reads2, const int64_t* offs2, int64_t n,
+                      int64_t* out_counts, uint32_t* out_tgts, uint32_t* out_wins)
+{
+    MCG_REQUIRE(db != nullptr && o != nullptr && reads1 != nullptr && offs1 != nullptr && out_counts != nullptr,
+                "mcg_query_matches: NULL argument");
+    if(n == 0) return MCG_OK;
+    mcg_ctx* c = db->ctx;
+    MCG_CUDA(cudaSetDevice(c->device));
+    MCG_TRY(check_opts(db, o));
+    const char *d1, *d2; const int64_t *do1, *do2; int64_t b1, b2;
+    MCG_TRY(stage_reads(c, reads1, offs1, reads2, offs2, n, &d1, &do1, &b1, &d2, &do2, &b2));
+    const int K = o->maxcand;
+    MCG_TRY(c->q_out_tax.reserve(size_t(n) * K * 4));
+    MCG_TRY(c->q_out_hits.reserve(size_t(n) * K * 4));
+    MCG_TRY(c->q_out_n.reserve(size_t(n) * 4));
+    QueryRun run;
+    MCG_TRY(query_batch_dev(db, o, d1, do1, b1, d2, do2, b2, n, c->q_out_tax.as<int32_t>(), c->q_out_hits.as<uint32_t>(),
+                            c->q_out_n.as<int32_t>(), 1, &run));
+    MCG_TRY(c->m_tax.reserve(size_t(n) * 8));
+    q_read_counts_kernel<<<grid_for(n), 256, 0, c->stream>>>(c->q_fpos.as<uint64_t>(), c->tmp2.as<uint32_t>(), o->sketchlen, n,
+                                                            c->m_tax.as<int64_t>());
+    c->launches++;
+    MCG_TRY(copy_out(c, out_counts, c->m_tax.p, size_t(n) * 8));
+    if(out_tgts != nullptr && out_wins != nullptr && run.total > 0) {
+        MCG_TRY(c->m_hits.reserve(run.total * 4));
+        MCG_TRY(c->m_n.reserve(run.total * 4));
+        q_split_locs_kernel<<<grid_for(run.total), 256, 0, c->stream>>>(c->q_loc.as<uint64_t>(), run.total,
+                                                                       c->m_hits.as<uint32_t>(), c->m_n.as<uint32_t>());
+        c->launches++;
+        MCG_TRY(copy_out(c, out_tgts, c->m_hits.p, run.total * 4));
+        MCG_TRY(copy_out(c, out_wins, c->m_n.p, run.total * 4));
+    }
+    MCG_CUDA(cudaStreamSynchronize(c->stream));
+    return MCG_OK;
+}
+
+int mcg_merge_classify_dev(mcg_ctx* c, const mcg_query_opts* o,
+                           const int32_t* d_cand_tax, const uint32_t* d_cand_hits,
+                           const int32_t* d_cand_n, int32_t nshards, int64_t n,
+                           int32_t* d_out_tax, uint32_t* d_out_hits, int32_t* d_out_ncand,
+                           int32_t* d_out_best, int32_t* d_out_best_rank, uint64_t* d_stats22)
+{
+    MCG_REQUIRE(c != nullptr && o != nullptr, "mcg_merge_classify_dev: NULL argument");
+    MCG_REQUIRE(nshards >= 1 && n >= 0, "bad shard / read count");
+    MCG_REQUIRE(o->maxcand >= 1 && o->maxcand <= MCG_MAX_CAND, "maxcand %d outside 1..%d", o->maxcand, MCG_MAX_CAND);
+    MCG_REQUIRE(o->lowest >= 0 && o->lowest < MCG_NUM_RANKS && o->highest >= 0 && o->highest < MCG_NUM_RANKS, "rank out of range");
+    if(c->lineage.p == nullptr) { set_error("taxonomy not uploaded (mcg_tax_upload)"); return MCG_ERR_STATE; }
+    if(n == 0) return MCG_OK;
+    MCG_CUDA(cudaSetDevice(c->device));
+    MergeParams p;
+    p.cand_tax = d_cand_tax; p.cand_hits = d_cand_hits; p.cand_n = d_cand_n;
+    p.P = nshards; p.n = n; p.K = o->maxcand;
+    p.lowest = o->lowest; p.highest = o->highest; p.hitmin = o->hitmin; p.hitdiff = o->hitdiff;
+    p.lineage = c->lineage.as<int32_t>(); p.rank = c->rank.as<uint8_t>();
+    p.out_tax = d_out_tax; p.out_hits = d_out_hits; p.out_n = d_out_ncand;
+    p.out_best = d_out_best; p.out_brank = d_out_best_rank;
+    p.stats = reinterpret_cast<unsigned long long*>(d_stats22);
+    q_merge_classify_kernel<<<grid_for(n, 128), 128, 0, c->stream>>>(p);
+    c->launches++;
+    MCG_CUDA(cudaGetLastError());
+    return MCG_OK;
+}
+
+int mcg_merge_classify(mcg_ctx* c, const mcg_query_opts* o,
+                       const int32_t* cand_tax, const uint32_t* cand_hits,
+                       const int32_t* cand_n, int32_t nshards, int64_t n,
+                       int32_t* out_tax, uint32_t* out_hits, int32_t* out_ncand,
+                       int32_t* out_best, int32_t* out_best_rank, uint64_t* out_stats22)
+{
+    MCG_REQUIRE(c != nullptr && o != nullptr, "mcg_merge_classify: NULL argument");
+    MCG_REQUIRE(nshards >= 1 && n >= 0, "bad shard / read count");
+    if(n == 0) return MCG_OK;
+    MCG_REQUIRE(o->maxcand >= 1 && o->maxcand <= MCG_MAX_CAND, "maxcand %d outside 1..%d", o->maxcand, MCG_MAX_CAND);
+    MCG_CUDA(cudaSetDevice(c->device));
+    const size_t K = size_t(o->maxcand), rows = size_t(nshards) * size_t(n);
+    MCG_TRY(c->m_tax.reserve(rows * K * 4)); MCG_TRY(c->m_hits.reserve(rows * K * 4)); MCG_TRY(c->m_n.reserve(rows * 4));
+    MCG_TRY(c->m_o_tax.reserve(size_t(n) * K * 4)); MCG_TRY(c->m_o_hits.reserve(size_t(n) * K * 4)); MCG_TRY(c->m_o_n.reserve(size_t(n) * 4));
+    MCG_TRY(c->m_best.reserve(size_t(n) * 4)); MCG_TRY(c->m_brank.reserve(size_t(n) * 4)); MCG_TRY(c->m_stats.reserve(22 * 8));
+    MCG_TRY(copy_in(c, c->m_tax.p, cand_tax, rows * K * 4));
+    MCG_TRY(copy_in(c, c->m_hits.p, cand_hits, rows * K * 4));
+    MCG_TRY(copy_in(c, c->m_n.p, cand_n, rows * 4));
+    MCG_CUDA(cudaMemsetAsync(c->m_stats.p, 0, 22 * 8, c->stream));
+    MCG_TRY(mcg_merge_classify_dev(c, o, c->m_tax.as<int32_t>(), c->m_hits.as<uint32_t>(), c->m_n.as<int32_t>(), nshards, n,
+                                   c->m_o_tax.as<int32_t>(), c->m_o_hits.as<uint32_t>(), c->m_o_n.as<int32_t>(),
+                                   c->m_best.as<int32_t>(), c->m_brank.as<int32_t>(), c->m_stats.as<uint64_t>()));
+    if(out_tax) MCG_TRY(copy_out(c, out_tax, c->m_o_tax.p, size_t(n) * K * 4));
+    if(out_hits) MCG_TRY(copy_out(c, out_hits, c->m_o_hits.p, size_t(n) * K * 4));
+    if(out_ncand) MCG_TRY(copy_out(c, out_ncand, c->m_o_n.p, size_t(n) * 4));
+    if(out_best) MCG_TRY(copy_out(c, out_best, c->m_best.p, size_t(n) * 4));
+    if(out_best_rank) MCG_TRY(copy_out(c, out_best_rank, c->m_brank.p, size_t(n) * 4));
+    uint64_t st[22];
+    MCG_TRY(copy_out(c, st, c->m_stats.p, 22 * 8));
+    MCG_CUDA(cudaStreamSynchronize(c->stream));
+    if(out_stats22) for(int i = 0; i < 22; ++i) out_stats22[i] += st[i];
+    return MCG_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,132 @@
+"""K3..K6 parity: sorted match lists, per-shard candidate lists, merged lists, classification
+and statistics from the CUDA path == oracle, bit-exact, at P = 1, 2, 4 shards"""
+import numpy as np
+import pytest
+
+from metacache_mpi_b200 import api, synth
+from oracle import pyoracle as po
+from util import World
+
+pytestmark = pytest.mark.gpu
+
+CONFIGS = [  # maxcand, lowest, hitmin, hitdiff
+    (4, 4, 4, 0.8),      # the authors' script settings: -lowest species -maxcand 4 -hitmin 4 -hitdiff 80
+    (2, 0, 5, 1.0),      # reference defaults
+    (3, 6, 2, 0.5),      # -lowest genus
+    (16, 10, 1, 0.1),    # wide list, -lowest family
+]
+
+
+def _gpu_full(ctx, dbs, q, b1, o1, b2, o2):
+    ct, ch, cn = [], [], []
+    for d in dbs:
+        t, h, n = d.query_batch(q, b1, o1, b2, o2)
+        ct.append(t); ch.append(h); cn.append(n)
+    ct, ch, cn = np.stack(ct), np.stack(ch), np.stack(cn)
+    return (ct, ch, cn) + ctx.merge_classify(q, ct, ch, cn)
+
+
+def _oracle_local(dbs, tax, oq, b1, o1, b2, o2, K):
+    n = len(o1) - 1
+    ct = np.full((len(dbs), n, K), -1, np.int32)
+    ch = np.zeros((len(dbs), n, K), np.uint32)
+    cn = np.zeros((len(dbs), n), np.int32)
+    for r, d in enumerate(dbs):
+        for i in range(n):
+            s2 = b2[o2[i]:o2[i + 1]] if b2 is not None else b""
+            t, h = d.query_local(tax, oq, b1[o1[i]:o1[i + 1]], s2)
+            cn[r, i] = len(t)
+            ct[r, i, :len(t)] = t
+            ch[r, i, :len(t)] = h
+    return ct, ch, cn
+
+
+@pytest.mark.parametrize("P", [1, 2, 4])
+def test_pairs_all_stages(ctx, oracle, P):
+    w = World(G=8, L=30000, npairs=400)
+    ctx.upload_taxonomy(w.tabs.lineage, w.tabs.rank, w.G)
+    od = w.oracle_shards(oracle, P)
+    gd = w.gpu_shards(api, ctx, P)
+    # sorted match lists (querying.h:798-811)
+    q0 = api.make_query_opts()
+    oq0 = po.make_qopt()
+    for r in range(P):
+        cnt, tg, wn = gd[r].query_matches(q0, w.b1, w.o1, w.b2, w.o2)
+        pos = 0
+        for i in range(len(w.o1) - 1):
+            mt, mw = od[r].matches(oq0, w.b1[w.o1[i]:w.o1[i + 1]], w.b2[w.o2[i]:w.o2[i + 1]])
+            assert cnt[i] == len(mt)
+            assert (tg[pos:pos + cnt[i]] == mt).all() and (wn[pos:pos + cnt[i]] == mw).all()
+            pos += int(cnt[i])
+    for maxcand, lowest, hitmin, hitdiff in CONFIGS:
+        q = api.make_query_opts(maxcand=maxcand, lowest=lowest, hitmin=hitmin, hitdiff=hitdiff)
+        oq = po.make_qopt(maxcand=maxcand, lowest=lowest, hitmin=hitmin, hitdiff=hitdiff)
+        ct, ch, cn, mt, mh, mn, best, brank, stats = _gpu_full(ctx, gd, q, w.b1, w.o1, w.b2, w.o2)
+        ot, oh, on = _oracle_local(od, w.tax, oq, w.b1, w.o1, w.b2, w.o2, maxcand)
+        assert (cn == on).all() and (ct == ot).all() and (ch == oh).all()
+        et, eh, en, eb, er, es = oracle.query_batch(od, w.tax, oq, w.b1, w.o1, w.b2, w.o2)
+        assert (mn == en).all() and (mt == et).all() and (mh == eh).all()
+        assert (best == eb).all() and (brank == er).all()
+        assert (stats == es).all()
+        assert stats[20] + stats[21] == len(w.o1) - 1
+
+
+def test_single_end_and_ragged_reads(ctx, oracle):
+    w = World(G=6, L=20000, npairs=10)
+    ctx.upload_taxonomy(w.tabs.lineage, w.tabs.rank, w.G)
+    od = w.oracle_shards(oracle, 2)
+    gd = w.gpu_shards(api, ctx, 2)
+    rng = np.random.default_rng(9)
+    reads = [b"", b"ACGT", b"N" * 150]
+    for n in (16, 50, 128, 129, 241, 500, 2000):
+        g = w.genomes[int(rng.integers(0, w.G))]
+        p = int(rng.integers(0, len(g) - n))
+        reads.append(g[p:p + n].copy())
+    b1, o1 = po.concat(reads)
+    q = api.make_query_opts(maxcand=4, lowest=4, hitmin=2, hitdiff=0.8)
+    oq = po.make_qopt(maxcand=4, lowest=4, hitmin=2, hitdiff=0.8)
+    ct, ch, cn, mt, mh, mn, best, brank, stats = _gpu_full(ctx, gd, q, b1, o1, None, None)
+    et, eh, en, eb, er, es = oracle.query_batch(od, w.tax, oq, b1, o1, None, None)
+    assert (mn == en).all() and (mt == et).all() and (mh == eh).all() and (best == eb).all() and (stats == es).all()
+
+
+def test_long_reads_many_windows(ctx, oracle):
+    """config 5 shape at test size: 10 kbp reads, ~89 windows each, all size classes of the sorter"""
+    w = World(G=6, L=100000, npairs=4)
+    ctx.upload_taxonomy(w.tabs.lineage, w.tabs.rank, w.G)
+    # identical genomes make every feature hit 3 locations per shard -> thousands of matches per read
+    w.genomes = [w.genomes[g % 2].copy() for g in range(6)]
+    w.buf, w.offs = po.concat(w.genomes)
+    od = w.oracle_shards(oracle, 2)
+    gd = w.gpu_shards(api, ctx, 2)
+    buf, offs, _ = synth.make_long_reads(w.genomes, 24, readlen=10000, sub=0.02)
+    extra = [w.genomes[0][:90000].copy(), w.genomes[1][100:300].copy()]     # > 16384 matches: global-memory class
+    b_all, o_all = po.concat([buf[offs[i]:offs[i + 1]] for i in range(len(offs) - 1)] + extra)
+    q = api.make_query_opts(maxcand=4, lowest=4, hitmin=4, hitdiff=0.8)
+    oq = po.make_qopt(maxcand=4, lowest=4, hitmin=4, hitdiff=0.8)
+    for r in range(2):
+        cnt, tg, wn = gd[r].query_matches(q, b_all, o_all)
+        pos = 0
+        for i in range(len(o_all) - 1):
+            mt, mw = od[r].matches(oq, b_all[o_all[i]:o_all[i + 1]])
+            assert cnt[i] == len(mt)
+            assert (tg[pos:pos + cnt[i]] == mt).all() and (wn[pos:pos + cnt[i]] == mw).all()
+            pos += int(cnt[i])
+        assert cnt.max() > 16384 and cnt.min() < 512
+    ct, ch, cn, mt, mh, mn, best, brank, stats = _gpu_full(ctx, gd, q, b_all, o_all, None, None)
+    et, eh, en, eb, er, es = oracle.query_batch(od, w.tax, oq, b_all, o_all, None, None)
+    assert (mn == en).all() and (mt == et).all() and (mh == eh).all() and (best == eb).all() and (stats == es).all()
+
+
+def test_query_window_overrides(ctx, oracle):
+    """-winlen / -winstride / -sketchlen given at query time (query_options.cpp:40-75)"""
+    w = World(G=6, L=20000, npairs=200)
+    ctx.upload_taxonomy(w.tabs.lineage, w.tabs.rank, w.G)
+    od = w.oracle_shards(oracle, 2)
+    gd = w.gpu_shards(api, ctx, 2)
+    for sk, wl, st in ((8, 128, 113), (16, 100, 100), (24, 150, 150)):
+        q = api.make_query_opts(sketchlen=sk, winlen=wl, winstride=st, maxcand=4, lowest=4, hitmin=2, hitdiff=0.8, insertsize=600)
+        oq = po.make_qopt(sketchlen=sk, winlen=wl, stride=st, maxcand=4, lowest=4, hitmin=2, hitdiff=0.8, insertsize=600)
+        ct, ch, cn, mt, mh, mn, best, brank, stats = _gpu_full(ctx, gd, q, w.b1, w.o1, w.b2, w.o2)
+        et, eh, en, eb, er, es = oracle.query_batch(od, w.tax, oq, w.b1, w.o1, w.b2, w.o2)
+        assert (mn == en).all() and (mt == et).all() and (mh == eh).all() and (best == eb).all() and (stats == es).all()
