@@ -59,22 +59,27 @@ def make_read_pairs(genomes, npairs, readlen=150, seed=7, sub=0.01, insert=(300,
     (1 in 5 an 'N').  Returns (buf1, offs1, buf2, offs2, truth_genome)"""
     rng = np.random.Generator(np.random.PCG64(seed))
     G = len(genomes)
+    lens = np.array([len(g) for g in genomes], np.int64)
+    starts = np.concatenate([[0], np.cumsum(lens)[:-1]])
+    cat = np.concatenate(genomes) if G > 1 else genomes[0]
     gsel = rng.integers(0, G, size=npairs)
-    ins = rng.integers(insert[0], insert[1] + 1, size=npairs)
+    ins = np.minimum(rng.integers(insert[0], insert[1] + 1, size=npairs), lens[gsel])
+    rl = int(min(readlen, ins.min())) if npairs else readlen
+    assert rl == readlen, "genomes shorter than the read length"
+    p = (rng.random(npairs) * (lens[gsel] - ins + 1)).astype(np.int64) + starts[gsel]
+    ar = np.arange(readlen, dtype=np.int64)
     b1 = np.empty(npairs * readlen, np.uint8)
     b2 = np.empty(npairs * readlen, np.uint8)
-    for i in range(npairs):
-        gs = genomes[gsel[i]]
-        L = len(gs)
-        il = min(int(ins[i]), L)
-        rl = min(readlen, il)
-        p = int(rng.integers(0, L - il + 1))
-        frag = gs[p:p + il]
-        b1[i * readlen:(i + 1) * readlen][:rl] = frag[:rl]
-        b2[i * readlen:(i + 1) * readlen][:rl] = revcomp_ascii(frag[il - rl:])
+    step = 1 << 18
+    for lo in range(0, npairs, step):
+        hi = min(lo + step, npairs)
+        b1[lo * readlen:hi * readlen] = cat[(p[lo:hi, None] + ar[None, :]).ravel()]
+        # mate 2: reverse complement of the fragment's last readlen bases
+        e = p[lo:hi] + ins[lo:hi] - 1
+        b2[lo * readlen:hi * readlen] = COMP[cat[(e[:, None] - ar[None, :]).ravel()]]
     for b in (b1, b2):
         nsub = int(sub * b.size)
-        pos = rng.integers(0, b.size, size=nsub)
+        pos = rng.integers(0, max(b.size, 1), size=nsub)
         newb = random_bases(rng, nsub)
         newb[rng.integers(0, 5, size=nsub) == 0] = ord("N")
         b[pos] = newb
