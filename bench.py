@@ -401,9 +401,9 @@ def run_extras(args, ctx, api, synth, taxonomy, torch, dist, dev, stream, world,
         if rc != 0:
             raise RuntimeError(L.mcg_last_error().decode())
         if world > 1:
-            dist.all_gather_into_tensor(gt, lt)
-            dist.all_gather_into_tensor(gh, lh)
-            dist.all_gather_into_tensor(gn, ln)
+            dist.all_gather_into_tensor(gt.view(world * npairs, Kc), lt)
+            dist.all_gather_into_tensor(gh.view(world * npairs, Kc), lh)
+            dist.all_gather_into_tensor(gn.view(world * npairs), ln)
             ct, ch, cn = gt, gh, gn
         else:
             ct, ch, cn = lt, lh, ln

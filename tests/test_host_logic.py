@@ -1,0 +1,42 @@
+"""host-side logic: synthetic data determinism, taxonomy flattening, option defaults"""
+import numpy as np
+
+from metacache_mpi_b200 import api, synth, taxonomy
+
+
+def test_synth_is_deterministic_and_shaped():
+    a, b = synth.genome(3, 10000), synth.genome(3, 10000)
+    assert (a == b).all() and len(a) == 10000
+    even, odd = synth.genome(2, 20000), synth.genome(3, 20000)
+    same = (np.char.upper(even.view("S1")) == np.char.upper(odd.view("S1"))).mean()
+    assert 0.93 < same < 0.99          # odd genome = 5 % substitutions of its even sibling
+    assert (a == ord("N")).sum() >= 50 and np.isin(a, np.frombuffer(b"ACGTNacgt", np.uint8)).all()
+    g = [synth.genome(i, 5000) for i in range(3)]
+    b1, o1, b2, o2, t = synth.make_read_pairs(g, 50, seed=1)
+    c1, p1, c2, p2, t2 = synth.make_read_pairs(g, 50, seed=1)
+    assert (b1 == c1).all() and (b2 == c2).all() and (t == t2).all()
+    assert len(b1) == 50 * 150 and o1[-1] == 50 * 150 and (np.diff(o1) == 150).all()
+
+
+def test_taxonomy_tables_shape_and_walk():
+    ids, par, rk, species = synth.make_taxonomy(6)
+    t = taxonomy.TaxonomyTables(ids, par, rk, species)
+    assert t.lineage.shape == (6 + len(ids), 21) and t.lineage.dtype == np.int32
+    for g in range(6):
+        lin = t.lineage[g]
+        assert lin[0] == g                                   # sequence level = the target itself
+        assert t.taxid[lin[4]] == 100000 + g                 # species
+        assert t.taxid[lin[6]] == 10000 + g // 2             # genus (through an unranked node)
+        assert t.taxid[lin[10]] == 1000 + g // 4             # family
+        assert t.taxid[lin[19]] == 2 and t.taxid[lin[20]] == 1
+        assert (lin[[1, 2, 3, 5, 7, 8, 9]] == -1).all()
+    # unknown parent / parent < 1: lineage ends at the target
+    t2 = taxonomy.TaxonomyTables(ids, par, rk, np.array([0, -5, 999999, 100000, 100001, 100002]))
+    assert (t2.lineage[0][1:] == -1).all() and (t2.lineage[1][1:] == -1).all() and (t2.lineage[2][1:] == -1).all()
+    assert t2.parent_id[1] == 0
+
+
+def test_option_defaults_follow_reference():
+    assert api.default_hitmin(16) == 5 and api.default_hitmin(5) == 2 and api.default_hitmin(3) == 1   # mode_query.cpp:247
+    q = api.make_query_opts(hitdiff=float(np.float32(np.float64(np.float32(80.0)) * 0.01)))       # query_options.cpp:167
+    assert abs(q.hitdiff - 0.8) < 1e-6
