@@ -23,6 +23,8 @@ constexpr int SK_THREADS = 256;
 constexpr int SK_WARPS = SK_THREADS / 32;
 constexpr int SK_CBUF = 128;              // per-warp compaction buffer (hashes)
 constexpr uint32_t NOF = 0xFFFFFFFFu;
+constexpr int SK_DEFAULT_VARIANT = 0;
+constexpr int SK_PITCH_DEFAULT = 290;       // pitch of the default shape (k=16, winlen=128, stride=113)
 
 struct SketchParams {
     const uint8_t* seq;
@@ -31,6 +33,9 @@ struct SketchParams {
     int64_t nseq;
     const uint32_t* win_first;   // [nseq+1] window prefix in processing order
     const uint32_t* out_first;   // [nseq]   output index of each sequence's first window
+    const uint32_t* cta_seq;     // [nblocks+1] sequence holding the first window of each CTA
+    int dbg;                     // timing experiments only (MCG_SK_DEBUG): 1 = no selection, 2 = no hashing, 4 = no packing
+    uint32_t c65536;             // 65536 as a run-time value (keeps x >> 16 as IMAD.HI on the FMA pipe)
     uint64_t nwin;
     uint32_t* out_feat;
     uint32_t* out_cnt;
@@ -40,6 +45,27 @@ struct SketchParams {
     int ngroups;                 // 16-base groups of span capacity
     int pitch;                   // row pitch of the transposed hash array (words)
 };
+
+// The hash array holds the hash BEFORE its last xor-shift: y = ((x1>>16)^x1)*C, h = y ^ (y>>16).
+// h and y share their upper 16 bits, so "h < T" == "y < T" for thresholds that are multiples of
+// 65536; the last step is applied to the few survivors only.  h == 0xFFFFFFFF <=> y == NOH.
+constexpr uint32_t NOH = 0xFFFF0000u;
+
+// m = 65536 at run time: __umulhi(x, m) == x >> 16, issued as IMAD.HI on the FMA pipe so that
+// the ALU pipe (the busiest one in this kernel) is relieved of two shifts per k-mer
+template<bool MULHI>
+__device__ __forceinline__ uint32_t tmh_head(uint32_t x, uint32_t m)
+{
+    if(MULHI) {
+        x = (__umulhi(x, m) ^ x) * 0x45d9f3bu;
+        x = (__umulhi(x, m) ^ x) * 0x45d9f3bu;
+    } else {
+        x = ((x >> 16) ^ x) * 0x45d9f3bu;
+        x = ((x >> 16) ^ x) * 0x45d9f3bu;
+    }
+    return x;
+}
+__device__ __forceinline__ uint32_t tmh_tail(uint32_t y) { return y ^ (y >> 16); }
 
 // ---- 4 ASCII bases -> 4 x 2-bit codes (first base in the high bits) + validity diff
 // code: A/a=0 C/c=1 G/g=2 T/t=3 (dna_encoding.h:330-336)
@@ -70,19 +96,47 @@ __device__ __forceinline__ uint32_t rc16(uint32_t w)
     return ~r;
 }
 
+// ascending 32-lane bitonic sort, "flip" formulation: the first step of every merge pairs lane
+// with its mirror inside the block (xor k-1), later steps pair lane ^ j; every comparator is
+// ascending, so the direction of a step depends on ONE lane bit (5 loop-invariant predicates)
 __device__ __forceinline__ uint32_t sort32(uint32_t v, int lane)
 {
 #pragma unroll
     for(int k = 2; k <= 32; k <<= 1) {
+        {
+            const uint32_t o = __shfl_xor_sync(0xFFFFFFFFu, v, k - 1);
+            v = (lane & (k >> 1)) ? max(v, o) : min(v, o);
+        }
 #pragma unroll
-        for(int j = k >> 1; j > 0; j >>= 1) {
+        for(int j = k >> 2; j > 0; j >>= 1) {
             const uint32_t o = __shfl_xor_sync(0xFFFFFFFFu, v, j);
-            const bool up = (lane & k) == 0;
-            const bool lower = (lane & j) == 0;
-            v = (up == lower) ? min(v, o) : max(v, o);
+            v = (lane & j) ? max(v, o) : min(v, o);
         }
     }
     return v;
+}
+
+// two independent sorts, interleaved stage by stage (twice the shuffles in flight)
+__device__ __forceinline__ void sort32x2(uint32_t& a, uint32_t& b, int lane)
+{
+#pragma unroll
+    for(int k = 2; k <= 32; k <<= 1) {
+        {
+            const uint32_t oa = __shfl_xor_sync(0xFFFFFFFFu, a, k - 1);
+            const uint32_t ob = __shfl_xor_sync(0xFFFFFFFFu, b, k - 1);
+            const bool up = (lane & (k >> 1)) != 0;
+            a = up ? max(a, oa) : min(a, oa);
+            b = up ? max(b, ob) : min(b, ob);
+        }
+#pragma unroll
+        for(int j = k >> 2; j > 0; j >>= 1) {
+            const uint32_t oa = __shfl_xor_sync(0xFFFFFFFFu, a, j);
+            const uint32_t ob = __shfl_xor_sync(0xFFFFFFFFu, b, j);
+            const bool up = (lane & j) != 0;
+            a = up ? max(a, oa) : min(a, oa);
+            b = up ? max(b, ob) : min(b, ob);
+        }
+    }
 }
 
 // sorts a bitonic sequence ascending
@@ -149,18 +203,111 @@ __device__ __forceinline__ uint32_t merge_chunk(uint32_t kept, uint32_t v, bool 
     return r;
 }
 
-__global__ void __launch_bounds__(SK_THREADS)
+// hashes the 16 k-mer starts of group j (K16: k == 16 known at compile time; PITCH > 0:
+// row pitch of the transposed hash array known at compile time)
+template<bool K16, bool CHECK, int PITCH, bool MULHI>
+__device__ __forceinline__ void hash_group(uint32_t w0, uint32_t w1, uint32_t a, int k, uint32_t* hrow, int pitch_rt, uint32_t m16)
+{
+    const int pitch = PITCH > 0 ? PITCH : pitch_rt;
+    const uint32_t r0 = rc16(w0), r1 = rc16(w1);
+    const int fsh = 32 - 2 * k;
+    const uint32_t kmask = 0xFFFFFFFFu >> fsh;
+    const int ash = 32 - k;
+#pragma unroll
+    for(int r = 0; r < 16; ++r) {
+        uint32_t f = __funnelshift_l(w1, w0, 2 * r);
+        uint32_t c = __funnelshift_r(r0, r1, 2 * r);
+        if(!K16) { f >>= fsh; c &= kmask; }
+        uint32_t y = tmh_head<MULHI>(min(f, c), m16);
+        if(CHECK) { if(((a << r) >> ash) != 0u) y = NOH; }
+        hrow[r * pitch] = y;
+    }
+}
+
+// fast path of the selection: threshold filter + ballot compaction of the (<= 128) k-mer
+// hashes of one window into cb; returns the number of survivors
+__device__ __forceinline__ int filter_compact(const uint32_t* hp, int rel0, int nk, uint32_t T, uint32_t* cb, uint32_t ltmask)
+{
+    int cnt = 0;
+    if(T != 0u) {
+#pragma unroll
+        for(int i = 0; i < 4; ++i) {
+            const uint32_t y = hp[2 * i];
+            const bool pass = (uint32_t(rel0 + 32 * i) < uint32_t(nk)) && (y < T);
+            const uint32_t b = __ballot_sync(0xFFFFFFFFu, pass);
+            if(pass) cb[cnt + __popc(b & ltmask)] = y;
+            cnt += __popc(b);
+        }
+    } else {
+#pragma unroll
+        for(int i = 0; i < 4; ++i) {
+            const uint32_t y = hp[2 * i];
+            const bool pass = (uint32_t(rel0 + 32 * i) < uint32_t(nk)) && (y != NOH);
+            const uint32_t b = __ballot_sync(0xFFFFFFFFu, pass);
+            if(pass) cb[cnt + __popc(b & ltmask)] = y;
+            cnt += __popc(b);
+        }
+    }
+    return cnt;
+}
+
+__device__ __noinline__ uint32_t chunked_select(const uint32_t* cb, int cnt, int sp, int lane, uint32_t* tmp, int& nout)
+{
+    const bool wide = sp > 16;
+    uint32_t kept = NOF;
+    bool first = true;
+    for(int c0 = 0; c0 < cnt; c0 += 32) {
+        const uint32_t v = (c0 + lane < cnt) ? tmh_tail(cb[c0 + lane]) : NOF;
+        kept = merge_chunk(kept, v, first, wide, lane, tmp);
+        first = false;
+    }
+    nout = __popc(__ballot_sync(0xFFFFFFFFu, kept != NOF));
+    return kept;
+}
+
+// exact selection over all k-mer hashes of a window, 32 at a time (any window length)
+__device__ __noinline__ uint32_t exact_select(const uint32_t* hp, int rel0, int nk, int span, int sp, int lane,
+                                              uint32_t* tmp, int& nout)
+{
+    const bool wide = sp > 16;
+    uint32_t kept = NOF;
+    bool first = true;
+    for(int i = 0; i * 32 < span; ++i) {
+        const uint32_t y = hp[2 * i];
+        const bool in = uint32_t(rel0 + 32 * i) < uint32_t(nk);
+        const uint32_t h = (in && y != NOH) ? tmh_tail(y) : NOF;
+        if(__ballot_sync(0xFFFFFFFFu, h != NOF) == 0u) continue;
+        kept = merge_chunk(kept, h, first, wide, lane, tmp);
+        first = false;
+    }
+    nout = __popc(__ballot_sync(0xFFFFFFFFu, kept != NOF));
+    return kept;
+}
+
+// threshold with ~1.5 s expected survivors among nk hashes; a multiple of 65536 (see NOH);
+// 0 = accept everything
+__device__ __forceinline__ uint32_t select_threshold(int nk, int sp)
+{
+    if(nk <= 32) return 0u;
+    const float pr = 1.5f * float(sp) / float(nk);
+    return pr < 0.999f ? (uint32_t(pr * 65536.0f) << 16) : 0u;
+}
+
+template<bool K16, int PITCH, bool PAIR, bool MULHI, int MINB>
+__global__ void __launch_bounds__(SK_THREADS, MINB)
 sketch_kernel(const SketchParams p)
 {
     extern __shared__ __align__(16) uint32_t smem[];
+    const int pitch = PITCH > 0 ? PITCH : p.pitch;
     uint32_t* pk   = smem;                                 // [ngroups + 2]
     uint32_t* amb  = pk + p.ngroups + 2;                   // [ngroups + 2]
     uint32_t* H    = amb + p.ngroups + 2;                  // [16 * pitch]
-    uint32_t* cbuf = H + 16 * p.pitch;                     // [SK_WARPS * SK_CBUF]
-    uint32_t* tmpb = cbuf + SK_WARPS * SK_CBUF;            // [SK_WARPS * 32]
-    int32_t*  wpos = reinterpret_cast<int32_t*>(tmpb + SK_WARPS * 32);   // [wpc]
-    int32_t*  wlen = wpos + p.wpc;                         // [wpc]
-    uint32_t* wout = reinterpret_cast<uint32_t*>(wlen + p.wpc);          // [wpc]
+    uint32_t* cbuf = H + 16 * pitch;                       // [2 * SK_WARPS * SK_CBUF]
+    uint32_t* tmpb = cbuf + 2 * SK_WARPS * SK_CBUF;        // [SK_WARPS * 32]
+    int32_t*  wpos = reinterpret_cast<int32_t*>(tmpb + SK_WARPS * 32);   // [wpc] start in span
+    int32_t*  wnk  = wpos + p.wpc;                         // [wpc] number of k-mer starts (may be <= 0)
+    uint32_t* wout = reinterpret_cast<uint32_t*>(wnk + p.wpc);           // [wpc] output window
+    uint32_t* wthr = wout + p.wpc;                         // [wpc] selection threshold
     __shared__ int64_t s_abs[64];
     __shared__ int64_t s_span_begin;
     __shared__ int32_t s_span_len;
@@ -172,9 +319,11 @@ sketch_kernel(const SketchParams p)
     const int nw = int(min(uint64_t(p.wpc), p.nwin - g0));
 
     // ---- resolve the CTA's windows: global window -> (sequence, window) -> bytes
+    int my_len = 0;
     if(tid < nw) {
         const uint32_t g = uint32_t(g0 + tid);
-        int64_t lo = 0, hi = p.nseq;               // largest q with win_first[q] <= g
+        // largest q with win_first[q] <= g, bracketed by the CTA's precomputed sequence range
+        int64_t lo = p.cta_seq[blockIdx.x], hi = int64_t(p.cta_seq[blockIdx.x + 1]) + 1;
         while(hi - lo > 1) {
             const int64_t mid = (lo + hi) >> 1;
             if(p.win_first[mid] <= g) lo = mid; else hi = mid;
@@ -186,15 +335,19 @@ sketch_kernel(const SketchParams p)
         int64_t b = 0, e = len;
         if(len > p.winlen) { b = w * p.stride; e = min(b + p.winlen, len); }
         s_abs[tid] = so + b;
-        wlen[tid] = int32_t(e - b);
+        my_len = int(e - b);
+        const int nk = my_len - p.k + 1;
+        const int sp = nk < p.s ? (nk < 0 ? 0 : nk) : p.s;
+        wnk[tid] = nk;
         wout[tid] = p.out_first[q] + uint32_t(w);
+        wthr[tid] = select_threshold(nk, sp);
     }
     __syncthreads();
-    if(tid == 0) {
+    if(tid == nw - 1) {
         const int64_t a0 = s_abs[0];
         const int64_t sb = a0 - int64_t((reinterpret_cast<uintptr_t>(p.seq) + uint64_t(a0)) & 15u);
         s_span_begin = sb;
-        s_span_len = int32_t(s_abs[nw - 1] + wlen[nw - 1] - sb);
+        s_span_len = int32_t(s_abs[tid] + my_len - sb);
     }
     __syncthreads();
     const int64_t span_begin = s_span_begin;
@@ -205,6 +358,7 @@ sketch_kernel(const SketchParams p)
     // ---- (1) load + pack
     for(int j = tid; j < ng + 2; j += SK_THREADS) {
         uint32_t w = 0, a = 0xFFFFu;
+        if(p.dbg & 4) { pk[j] = j * 2654435761u; amb[j] = 0; continue; }
         if(j < ng) {
             const int64_t off = span_begin + int64_t(j) * 16;
             uint4 v;
@@ -236,87 +390,107 @@ sketch_kernel(const SketchParams p)
     }
     __syncthreads();
 
-    // ---- (2) hash every k-mer start of the span
-    {
-        const int k = p.k;
-        const int fsh = 32 - 2 * k;
-        const uint32_t kmask = 0xFFFFFFFFu >> fsh;
-        const int ash = 32 - k;
-        for(int j = tid; j < ng; j += SK_THREADS) {
-            const uint32_t w0 = pk[j], w1 = pk[j + 1];
-            const uint32_t r0 = rc16(w0), r1 = rc16(w1);
-            const uint32_t a = (amb[j] << 16) | amb[j + 1];
-            uint32_t* hrow = H + j;
-#pragma unroll
-            for(int r = 0; r < 16; ++r) {
-                const uint32_t f = __funnelshift_l(w1, w0, 2 * r) >> fsh;
-                const uint32_t c = __funnelshift_r(r0, r1, 2 * r) & kmask;
-                uint32_t h = tmh(min(f, c));
-                if(((a << r) >> ash) != 0u) h = NOF;
-                hrow[r * p.pitch] = h;
-            }
-        }
+    // ---- (2) hash every k-mer start of the span (ambiguity checks only where needed)
+    for(int j = tid; j < ng; j += SK_THREADS) {
+        if(p.dbg & 2) break;
+        const uint32_t w0 = pk[j], w1 = pk[j + 1];
+        const uint32_t a = (amb[j] << 16) | amb[j + 1];
+        if(a == 0u) hash_group<K16, false, PITCH, MULHI>(w0, w1, a, p.k, H + j, pitch, p.c65536);
+        else        hash_group<K16, true, PITCH, MULHI>(w0, w1, a, p.k, H + j, pitch, p.c65536);
     }
     __syncthreads();
 
-    // ---- (3) per-window bottom-s unique
-    uint32_t* mycb = cbuf + warp * SK_CBUF;
+    // ---- (3) per-window bottom-s unique: every warp takes two windows at a time so that two
+    // independent sorting networks are in flight (shuffle latency, not issue, was the limiter)
+    uint32_t* cb0 = cbuf + warp * (2 * SK_CBUF);
+    uint32_t* cb1 = cb0 + SK_CBUF;
     uint32_t* mytmp = tmpb + warp * 32;
     const uint32_t ltmask = (1u << lane) - 1u;
-    for(int wi = warp; wi < nw; wi += SK_WARPS) {
-        const int pos = wpos[wi];
-        const int nk = wlen[wi] - p.k + 1;
-        const uint32_t oidx = wout[wi];
-        const int sp = nk < p.s ? (nk < 0 ? 0 : nk) : p.s;
-        uint32_t kept = NOF;
-        if(sp > 0) {
-            uint32_t T = NOF;
-            if(nk > 32) {
-                const float pr = (1.45f * float(sp) + 2.0f) / float(nk);
-                if(pr < 1.0f) T = uint32_t(pr * 4294967296.0f);
-            }
-            const bool wide = sp > 16;
-            for(;;) {
-                kept = NOF;
-                bool first = true;
-                if(nk <= SK_CBUF) {
-                    int cnt = 0;
-                    for(int c0 = 0; c0 < nk; c0 += 32) {
-                        const int q = pos + c0 + lane;
-                        const uint32_t h = (c0 + lane < nk) ? H[(q & 15) * p.pitch + (q >> 4)] : NOF;
-                        const bool pass = h < T;
-                        const uint32_t b = __ballot_sync(0xFFFFFFFFu, pass);
-                        if(pass) mycb[cnt + __popc(b & ltmask)] = h;
-                        cnt += __popc(b);
-                    }
-                    __syncwarp();
-                    for(int c0 = 0; c0 < cnt; c0 += 32) {
-                        const uint32_t v = (c0 + lane < cnt) ? mycb[c0 + lane] : NOF;
-                        kept = merge_chunk(kept, v, first, wide, lane, mytmp);
-                        first = false;
-                    }
-                    __syncwarp();
-                } else {
-                    for(int c0 = 0; c0 < nk; c0 += 32) {
-                        const int q = pos + c0 + lane;
-                        uint32_t h = (c0 + lane < nk) ? H[(q & 15) * p.pitch + (q >> 4)] : NOF;
-                        if(h >= T) h = NOF;
-                        if(__ballot_sync(0xFFFFFFFFu, h != NOF) == 0u) continue;
-                        kept = merge_chunk(kept, h, first, wide, lane, mytmp);
-                        first = false;
-                    }
-                }
-                const int nuniq = __popc(__ballot_sync(0xFFFFFFFFu, kept != NOF));
-                if(nuniq >= sp || T == NOF) break;
-                T = NOF;        // too few survivors below the threshold: exact pass
+    // lane-constant part of the transposed address of position (16*j0 + lane + 32*i)
+    const uint32_t* hlane = H + (lane & 15) * pitch + (lane >> 4);
+    uint32_t* olane = p.out_feat + lane;
+    for(int wi = warp; wi < nw; wi += (PAIR ? 2 : 1) * SK_WARPS) {
+        if(p.dbg & 1) { if(lane < p.s) olane[uint64_t(wout[wi]) * uint32_t(p.s)] = hlane[wpos[wi] >> 4]; continue; }
+        const int wj = wi + SK_WARPS;
+        const bool two = PAIR && wj < nw;
+        // window A
+        const int posA = wpos[wi], nkA = wnk[wi];
+        const uint32_t TA = wthr[wi];
+        const int spA = min(p.s, max(nkA, 0));
+        const uint32_t* hpA = hlane + (posA >> 4);
+        const int relA = lane - (posA & 15);
+        const int spanA = nkA + (posA & 15);
+        // window B (a copy of A's parameters when absent; its results are discarded)
+        const int wjj = two ? wj : wi;
+        const int posB = wpos[wjj], nkB = wnk[wjj];
+        const uint32_t TB = wthr[wjj];
+        const int spB = min(p.s, max(nkB, 0));
+        const uint32_t* hpB = hlane + (posB >> 4);
+        const int relB = lane - (posB & 15);
+        const int spanB = nkB + (posB & 15);
+
+        uint32_t keptA = NOF, keptB = NOF;
+        int noutA = 0, noutB = 0;
+        bool doneA = spA <= 0, doneB = !two || spB <= 0;
+        int cntA = 0, cntB = 0;
+        const bool fastA = !doneA && spanA <= 128, fastB = !doneB && spanB <= 128;
+        if(fastA) cntA = filter_compact(hpA, relA, nkA, TA, cb0, ltmask);
+        if(fastB) cntB = filter_compact(hpB, relB, nkB, TB, cb1, ltmask);
+        __syncwarp();
+        const bool sortA = fastA && cntA <= 32 && (cntA >= spA || TA == 0u);
+        const bool sortB = fastB && cntB <= 32 && (cntB >= spB || TB == 0u);
+        if(sortA || sortB) {
+            uint32_t va = (sortA && lane < cntA) ? tmh_tail(cb0[lane]) : NOF;
+            uint32_t vb = (sortB && lane < cntB) ? tmh_tail(cb1[lane]) : NOF;
+            sort32x2(va, vb, lane);
+            const uint32_t pa = __shfl_up_sync(0xFFFFFFFFu, va, 1);
+            const uint32_t pb = __shfl_up_sync(0xFFFFFFFFu, vb, 1);
+            const bool dup = (lane > 0) && ((va == pa && va != NOF) || (vb == pb && vb != NOF));
+            if(__any_sync(0xFFFFFFFFu, dup)) {
+                va = dedup_sorted(va, lane, mytmp);
+                vb = dedup_sorted(vb, lane, mytmp);
+                if(sortA) { keptA = va; noutA = __popc(__ballot_sync(0xFFFFFFFFu, va != NOF)); doneA = noutA >= spA || TA == 0u; }
+                if(sortB) { keptB = vb; noutB = __popc(__ballot_sync(0xFFFFFFFFu, vb != NOF)); doneB = noutB >= spB || TB == 0u; }
+            } else {
+                if(sortA) { keptA = va; noutA = cntA; doneA = true; }
+                if(sortB) { keptB = vb; noutB = cntB; doneB = true; }
             }
         }
-        if(lane < p.s) p.out_feat[uint64_t(oidx) * p.s + lane] = (lane < sp) ? kept : NOF;
-        if(p.out_cnt != nullptr) {
-            const int c = __popc(__ballot_sync(0xFFFFFFFFu, lane < sp && kept != NOF));
-            if(lane == 0) p.out_cnt[oidx] = uint32_t(c);
+        // rare: more than 32 survivors -> merge the compacted survivors 32 at a time
+        if(!doneA && fastA && cntA > 32) { keptA = chunked_select(cb0, cntA, spA, lane, mytmp, noutA); doneA = noutA >= spA || TA == 0u; }
+        if(!doneB && fastB && cntB > 32) { keptB = chunked_select(cb1, cntB, spB, lane, mytmp, noutB); doneB = noutB >= spB || TB == 0u; }
+        // rare: too few distinct hashes below the threshold (or a long window) -> exact pass
+        if(!doneA) keptA = exact_select(hpA, relA, nkA, spanA, spA, lane, mytmp, noutA);
+        if(!doneB) keptB = exact_select(hpB, relB, nkB, spanB, spB, lane, mytmp, noutB);
+        __syncwarp();
+
+        {
+            const uint32_t oidx = wout[wi];
+            if(lane < p.s) olane[uint64_t(oidx) * uint32_t(p.s)] = (lane < spA) ? keptA : NOF;
+            if(p.out_cnt != nullptr && lane == 0) p.out_cnt[oidx] = uint32_t(min(noutA, spA));
+        }
+        if(two) {
+            const uint32_t oidx = wout[wj];
+            if(lane < p.s) olane[uint64_t(oidx) * uint32_t(p.s)] = (lane < spB) ? keptB : NOF;
+            if(p.out_cnt != nullptr && lane == 0) p.out_cnt[oidx] = uint32_t(min(noutB, spB));
         }
     }
+}
+
+// sequence that holds the first window of every CTA (one binary search per CTA, done up front
+// so that the main kernel starts with one load instead of a chain of dependent ones)
+__global__ void cta_seq_kernel(const uint32_t* win_first, int64_t nseq, int wpc, uint32_t nblocks, uint32_t* cta_seq)
+{
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if(b > nblocks) return;
+    if(b == nblocks) { cta_seq[b] = uint32_t(nseq - 1); return; }
+    const uint32_t g = b * uint32_t(wpc);
+    int64_t lo = 0, hi = nseq;
+    while(hi - lo > 1) {
+        const int64_t mid = (lo + hi) >> 1;
+        if(win_first[mid] <= g) lo = mid; else hi = mid;
+    }
+    cta_seq[b] = uint32_t(lo);
 }
 
 // ---- window counts per sequence -----------------------------------------------------
@@ -348,18 +522,21 @@ int sketch_config(const mcg_sketch_cfg& cfg, int sketchlen, int64_t winlen, int6
     MCG_REQUIRE(winlen >= 1 && stride >= 1, "window length and stride must be >= 1");
     const int64_t adv = winlen > stride ? winlen : stride;
     MCG_REQUIRE(adv <= 32768, "window length / stride above 32768 are not supported on the device");
-    int w = 32;
+    // as many windows as keep the 16-base groups of a typical span within one pass of the CTA
+    int w = int((int64_t(SK_THREADS) * 16 - 30 - winlen) / stride) + 1;
+    if(w > 40) w = 40;
+    if(w < 1) w = 1;
     for(;;) {
         const int64_t span = (int64_t(w) * adv + 15 + 15) / 16 * 16 + 16;
         const int ng = int(span / 16);
         const int pt = ((ng + 31) / 32) * 32 + 2;
-        const size_t bytes = (size_t(2) * (ng + 2) + size_t(16) * pt + SK_WARPS * SK_CBUF + SK_WARPS * 32 + 3 * size_t(w)) * 4;
-        if(bytes <= 200 * 1024 || w == 1) {
+        const size_t bytes = (size_t(2) * (ng + 2) + size_t(16) * pt + 2 * SK_WARPS * SK_CBUF + SK_WARPS * 32 + 4 * size_t(w)) * 4;
+        if((bytes <= 48 * 1024 && ng <= 2 * SK_THREADS) || w == 1) {
             MCG_REQUIRE(bytes <= 200 * 1024, "window too long for the device sketcher");
             *wpc = w; *ngroups = ng; *pitch = pt; *smem = bytes;
             return MCG_OK;
         }
-        w >>= 1;
+        w = w > 8 ? w - 4 : w - 1;
     }
 }
 
@@ -385,14 +562,41 @@ int sketch_launch(mcg_ctx* c, const mcg_sketch_cfg& cfg, int sketchlen, int64_t 
     p.s = sketchlen;
     p.winlen = winlen;
     p.stride = stride;
-    static size_t configured = 0;
-    if(smem > 48 * 1024 && smem > configured) {
-        MCG_CUDA(cudaFuncSetAttribute(sketch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-        configured = smem;
-    }
     const uint64_t nblocks = (nwin + p.wpc - 1) / p.wpc;
     MCG_REQUIRE(nblocks < (1ull << 31), "too many windows in one launch");
-    sketch_kernel<<<unsigned(nblocks), SK_THREADS, smem, c->stream>>>(p);
+    MCG_REQUIRE(nseq < (1ll << 32), "too many sequences in one launch");
+    MCG_TRY(c->outfirst.reserve((nblocks + 2) * sizeof(uint32_t)));
+    cta_seq_kernel<<<unsigned((nblocks + 256) / 256), 256, 0, c->stream>>>(d_win_first, nseq, p.wpc, uint32_t(nblocks),
+                                                                          c->outfirst.as<uint32_t>());
+    c->launches++;
+    p.cta_seq = c->outfirst.as<uint32_t>();
+    p.c65536 = 65536u;
+    { const char* e = getenv("MCG_SK_DEBUG"); p.dbg = e ? atoi(e) : 0; }
+    static int variant = -1;
+    if(variant < 0) { const char* e = getenv("MCG_SK_VARIANT"); variant = e ? atoi(e) : SK_DEFAULT_VARIANT; }
+#define SK_LAUNCH(K16, PT, PAIR, MULHI, MINB)                                                                     \
+    do {                                                                                                          \
+        auto kern = sketch_kernel<K16, PT, PAIR, MULHI, MINB>;                                                    \
+        if(smem > 48 * 1024) MCG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))); \
+        kern<<<unsigned(nblocks), SK_THREADS, smem, c->stream>>>(p);                                              \
+    } while(0)
+    if(cfg.k == 16 && p.pitch == SK_PITCH_DEFAULT) {
+        switch(variant & 7) {
+            case 0: SK_LAUNCH(true, SK_PITCH_DEFAULT, false, false, 6); break;
+            case 1: SK_LAUNCH(true, SK_PITCH_DEFAULT, true, false, 6); break;
+            case 2: SK_LAUNCH(true, SK_PITCH_DEFAULT, false, true, 6); break;
+            case 3: SK_LAUNCH(true, SK_PITCH_DEFAULT, true, true, 6); break;
+            case 4: SK_LAUNCH(true, SK_PITCH_DEFAULT, false, false, 4); break;
+            case 5: SK_LAUNCH(true, SK_PITCH_DEFAULT, true, false, 4); break;
+            case 6: SK_LAUNCH(true, SK_PITCH_DEFAULT, false, true, 4); break;
+            default: SK_LAUNCH(true, SK_PITCH_DEFAULT, true, true, 4); break;
+        }
+    } else if(cfg.k == 16) {
+        SK_LAUNCH(true, 0, false, false, 4);
+    } else {
+        SK_LAUNCH(false, 0, false, false, 4);
+    }
+#undef SK_LAUNCH
     c->launches++;
     MCG_CUDA(cudaGetLastError());
     return MCG_OK;
