@@ -107,8 +107,9 @@ int64_t mcg_count_windows(const mcg_sketch_cfg*, const int64_t* seq_offsets, int
 int  mcg_sketch_windows(mcg_ctx*, const mcg_sketch_cfg*,
                         const char* seq_bytes, const int64_t* seq_offsets, int64_t nseq,
                         uint32_t* out_features, uint32_t* out_counts, int64_t* out_nwin);
-/* same on resident data; d_seq must be readable up to total_bytes rounded up
- * to 16; d_seq_offsets[nseq+1] on the device; nwin = mcg_count_windows(...) */
+/* same on resident data; d_seq must be 16-byte aligned and readable up to
+ * total_bytes + 64 (the TMA span copies are 16-byte granular);
+ * d_seq_offsets[nseq+1] on the device; nwin = mcg_count_windows(...) */
 int  mcg_sketch_windows_dev(mcg_ctx*, const mcg_sketch_cfg*,
                             const char* d_seq, int64_t total_bytes,
                             const int64_t* d_seq_offsets, int64_t nseq, int64_t nwin,

@@ -17,13 +17,14 @@
 //       with an exact unfiltered multi-chunk fallback.
 #include "common.cuh"
 
+#include <algorithm>
+
 namespace mcg {
 
 constexpr int SK_THREADS = 256;
 constexpr int SK_WARPS = SK_THREADS / 32;
 constexpr int SK_CBUF = 128;              // per-warp compaction buffer (hashes)
 constexpr uint32_t NOF = 0xFFFFFFFFu;
-constexpr int SK_DEFAULT_VARIANT = 0;
 constexpr int SK_PITCH_DEFAULT = 290;       // pitch of the default shape (k=16, winlen=128, stride=113)
 
 struct SketchParams {
@@ -33,9 +34,7 @@ struct SketchParams {
     int64_t nseq;
     const uint32_t* win_first;   // [nseq+1] window prefix in processing order
     const uint32_t* out_first;   // [nseq]   output index of each sequence's first window
-    const uint32_t* cta_seq;     // [nblocks+1] sequence holding the first window of each CTA
-    int dbg;                     // timing experiments only (MCG_SK_DEBUG): 1 = no selection, 2 = no hashing, 4 = no packing
-    uint32_t c65536;             // 65536 as a run-time value (keeps x >> 16 as IMAD.HI on the FMA pipe)
+    const uint32_t* cta_seq;     // [ntiles+1] sequence holding the first window of each tile
     uint64_t nwin;
     uint32_t* out_feat;
     uint32_t* out_cnt;
@@ -51,18 +50,10 @@ struct SketchParams {
 // 65536; the last step is applied to the few survivors only.  h == 0xFFFFFFFF <=> y == NOH.
 constexpr uint32_t NOH = 0xFFFF0000u;
 
-// m = 65536 at run time: __umulhi(x, m) == x >> 16, issued as IMAD.HI on the FMA pipe so that
-// the ALU pipe (the busiest one in this kernel) is relieved of two shifts per k-mer
-template<bool MULHI>
-__device__ __forceinline__ uint32_t tmh_head(uint32_t x, uint32_t m)
+__host__ __device__ __forceinline__ uint32_t tmh_head(uint32_t x)
 {
-    if(MULHI) {
-        x = (__umulhi(x, m) ^ x) * 0x45d9f3bu;
-        x = (__umulhi(x, m) ^ x) * 0x45d9f3bu;
-    } else {
-        x = ((x >> 16) ^ x) * 0x45d9f3bu;
-        x = ((x >> 16) ^ x) * 0x45d9f3bu;
-    }
+    x = ((x >> 16) ^ x) * 0x45d9f3bu;
+    x = ((x >> 16) ^ x) * 0x45d9f3bu;
     return x;
 }
 __device__ __forceinline__ uint32_t tmh_tail(uint32_t y) { return y ^ (y >> 16); }
@@ -114,29 +105,6 @@ __device__ __forceinline__ uint32_t sort32(uint32_t v, int lane)
         }
     }
     return v;
-}
-
-// two independent sorts, interleaved stage by stage (twice the shuffles in flight)
-__device__ __forceinline__ void sort32x2(uint32_t& a, uint32_t& b, int lane)
-{
-#pragma unroll
-    for(int k = 2; k <= 32; k <<= 1) {
-        {
-            const uint32_t oa = __shfl_xor_sync(0xFFFFFFFFu, a, k - 1);
-            const uint32_t ob = __shfl_xor_sync(0xFFFFFFFFu, b, k - 1);
-            const bool up = (lane & (k >> 1)) != 0;
-            a = up ? max(a, oa) : min(a, oa);
-            b = up ? max(b, ob) : min(b, ob);
-        }
-#pragma unroll
-        for(int j = k >> 2; j > 0; j >>= 1) {
-            const uint32_t oa = __shfl_xor_sync(0xFFFFFFFFu, a, j);
-            const uint32_t ob = __shfl_xor_sync(0xFFFFFFFFu, b, j);
-            const bool up = (lane & j) != 0;
-            a = up ? max(a, oa) : min(a, oa);
-            b = up ? max(b, ob) : min(b, ob);
-        }
-    }
 }
 
 // sorts a bitonic sequence ascending
@@ -205,8 +173,8 @@ __device__ __forceinline__ uint32_t merge_chunk(uint32_t kept, uint32_t v, bool 
 
 // hashes the 16 k-mer starts of group j (K16: k == 16 known at compile time; PITCH > 0:
 // row pitch of the transposed hash array known at compile time)
-template<bool K16, bool CHECK, int PITCH, bool MULHI>
-__device__ __forceinline__ void hash_group(uint32_t w0, uint32_t w1, uint32_t a, int k, uint32_t* hrow, int pitch_rt, uint32_t m16)
+template<bool K16, bool CHECK, int PITCH>
+__device__ __forceinline__ void hash_group(uint32_t w0, uint32_t w1, uint32_t a, int k, uint32_t* hrow, int pitch_rt)
 {
     const int pitch = PITCH > 0 ? PITCH : pitch_rt;
     const uint32_t r0 = rc16(w0), r1 = rc16(w1);
@@ -218,7 +186,7 @@ __device__ __forceinline__ void hash_group(uint32_t w0, uint32_t w1, uint32_t a,
         uint32_t f = __funnelshift_l(w1, w0, 2 * r);
         uint32_t c = __funnelshift_r(r0, r1, 2 * r);
         if(!K16) { f >>= fsh; c &= kmask; }
-        uint32_t y = tmh_head<MULHI>(min(f, c), m16);
+        uint32_t y = tmh_head(min(f, c));
         if(CHECK) { if(((a << r) >> ash) != 0u) y = NOH; }
         hrow[r * pitch] = y;
     }
@@ -293,187 +261,264 @@ __device__ __forceinline__ uint32_t select_threshold(int nk, int sp)
     return pr < 0.999f ? (uint32_t(pr * 65536.0f) << 16) : 0u;
 }
 
-template<bool K16, int PITCH, bool PAIR, bool MULHI, int MINB>
-__global__ void __launch_bounds__(SK_THREADS, MINB)
+// ---- mbarrier + TMA (cp.async.bulk) helpers ---------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// 1-D bulk copy global -> shared through the TMA unit; completion is signalled on the mbarrier
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// per-tile window table (one per pipeline stage)
+struct TileTab {
+    int32_t* wpos;      // [wpc] start of the window inside the span
+    int32_t* wnk;       // [wpc] number of k-mer starts (may be <= 0)
+    uint32_t* wout;     // [wpc] output window index
+    uint32_t* wthr;     // [wpc] selection threshold
+    int32_t* meta;      // [4]: nw, span_len, -, -
+};
+
+// Persistent kernel: each CTA loops over tiles of `wpc` consecutive windows.  While tile t is
+// packed, hashed and reduced, warp 0 has already resolved tile t+grid and the TMA unit is copying
+// its bytes into the other raw buffer, so neither the dependent index loads nor the DRAM latency
+// of the span sit on the critical path.
+template<bool K16, int PITCH>
+__global__ void __launch_bounds__(SK_THREADS, 6)
 sketch_kernel(const SketchParams p)
 {
-    extern __shared__ __align__(16) uint32_t smem[];
+    extern __shared__ __align__(128) uint32_t smem[];
     const int pitch = PITCH > 0 ? PITCH : p.pitch;
-    uint32_t* pk   = smem;                                 // [ngroups + 2]
+    const int rawcap = (p.ngroups + 2) * 16;                // bytes per raw stage
+    uint8_t*  raw0 = reinterpret_cast<uint8_t*>(smem);
+    uint8_t*  raw1 = raw0 + rawcap;
+    uint32_t* pk   = reinterpret_cast<uint32_t*>(raw1 + rawcap);   // [ngroups + 2]
     uint32_t* amb  = pk + p.ngroups + 2;                   // [ngroups + 2]
     uint32_t* H    = amb + p.ngroups + 2;                  // [16 * pitch]
-    uint32_t* cbuf = H + 16 * pitch;                       // [2 * SK_WARPS * SK_CBUF]
-    uint32_t* tmpb = cbuf + 2 * SK_WARPS * SK_CBUF;        // [SK_WARPS * 32]
-    int32_t*  wpos = reinterpret_cast<int32_t*>(tmpb + SK_WARPS * 32);   // [wpc] start in span
-    int32_t*  wnk  = wpos + p.wpc;                         // [wpc] number of k-mer starts (may be <= 0)
-    uint32_t* wout = reinterpret_cast<uint32_t*>(wnk + p.wpc);           // [wpc] output window
-    uint32_t* wthr = wout + p.wpc;                         // [wpc] selection threshold
-    __shared__ int64_t s_abs[64];
-    __shared__ int64_t s_span_begin;
-    __shared__ int32_t s_span_len;
+    uint32_t* cbuf = H + 16 * pitch;                       // [SK_WARPS * SK_CBUF]
+    uint32_t* tmpb = cbuf + SK_WARPS * SK_CBUF;            // [SK_WARPS * 32]
+    int32_t*  tabs = reinterpret_cast<int32_t*>(tmpb + SK_WARPS * 32);   // 2 x (4 * wpc + 4)
+    __shared__ __align__(8) uint64_t s_bar[2];
+    __shared__ int s_next;
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
-    const uint64_t g0 = uint64_t(blockIdx.x) * p.wpc;
-    const int nw = int(min(uint64_t(p.wpc), p.nwin - g0));
+    const int tabsz = 4 * p.wpc + 4;
+    const uint64_t ntiles = (p.nwin + p.wpc - 1) / p.wpc;
 
-    // ---- resolve the CTA's windows: global window -> (sequence, window) -> bytes
-    int my_len = 0;
-    if(tid < nw) {
-        const uint32_t g = uint32_t(g0 + tid);
-        // largest q with win_first[q] <= g, bracketed by the CTA's precomputed sequence range
-        int64_t lo = p.cta_seq[blockIdx.x], hi = int64_t(p.cta_seq[blockIdx.x + 1]) + 1;
-        while(hi - lo > 1) {
-            const int64_t mid = (lo + hi) >> 1;
-            if(p.win_first[mid] <= g) lo = mid; else hi = mid;
-        }
-        const int64_t q = lo;
-        const int64_t w = g - p.win_first[q];
-        const int64_t so = p.seq_off[q];
-        const int64_t len = p.seq_off[q + 1] - so;
-        int64_t b = 0, e = len;
-        if(len > p.winlen) { b = w * p.stride; e = min(b + p.winlen, len); }
-        s_abs[tid] = so + b;
-        my_len = int(e - b);
-        const int nk = my_len - p.k + 1;
-        const int sp = nk < p.s ? (nk < 0 ? 0 : nk) : p.s;
-        wnk[tid] = nk;
-        wout[tid] = p.out_first[q] + uint32_t(w);
-        wthr[tid] = select_threshold(nk, sp);
-    }
-    __syncthreads();
-    if(tid == nw - 1) {
-        const int64_t a0 = s_abs[0];
-        const int64_t sb = a0 - int64_t((reinterpret_cast<uintptr_t>(p.seq) + uint64_t(a0)) & 15u);
-        s_span_begin = sb;
-        s_span_len = int32_t(s_abs[tid] + my_len - sb);
-    }
-    __syncthreads();
-    const int64_t span_begin = s_span_begin;
-    const int span_len = s_span_len;
-    if(tid < nw) wpos[tid] = int32_t(s_abs[tid] - span_begin);
-    const int ng = (span_len + 15) >> 4;           // groups holding data
+    auto tab_of = [&](int stage) {
+        TileTab t;
+        int32_t* base = tabs + stage * tabsz;
+        t.wpos = base;
+        t.wnk = base + p.wpc;
+        t.wout = reinterpret_cast<uint32_t*>(base + 2 * p.wpc);
+        t.wthr = reinterpret_cast<uint32_t*>(base + 3 * p.wpc);
+        t.meta = base + 4 * p.wpc;
+        return t;
+    };
 
-    // ---- (1) load + pack
-    for(int j = tid; j < ng + 2; j += SK_THREADS) {
-        uint32_t w = 0, a = 0xFFFFu;
-        if(p.dbg & 4) { pk[j] = j * 2654435761u; amb[j] = 0; continue; }
-        if(j < ng) {
-            const int64_t off = span_begin + int64_t(j) * 16;
-            uint4 v;
-            if(off >= 0 && off + 16 <= p.total_bytes) {
-                v = __ldg(reinterpret_cast<const uint4*>(p.seq + off));
-            } else {
-                uint32_t t[4] = {0x4E4E4E4Eu, 0x4E4E4E4Eu, 0x4E4E4E4Eu, 0x4E4E4E4Eu};   // 'N'
-                for(int i = 0; i < 16; ++i) {
-                    const int64_t o = off + i;
-                    if(o >= 0 && o < p.total_bytes) {
-                        t[i >> 2] = (t[i >> 2] & ~(0xFFu << ((i & 3) * 8))) | (uint32_t(p.seq[o]) << ((i & 3) * 8));
-                    }
+    // warp 0: resolve tile `tile` into table `stage` and start its TMA copy
+    auto prefetch = [&](uint64_t tile, int stage) {
+        TileTab t = tab_of(stage);
+        const uint64_t g0 = tile * uint64_t(p.wpc);
+        const int nw = int(min(uint64_t(p.wpc), p.nwin - g0));
+        int64_t first_abs = 0, last_end = 0;
+        int64_t my_abs[2] = {0, 0};
+        for(int r = 0; r < 2; ++r) {
+            const int i = lane + 32 * r;
+            if(i < nw) {
+                const uint32_t g = uint32_t(g0 + i);
+                int64_t lo = p.cta_seq[tile], hi = int64_t(p.cta_seq[tile + 1]) + 1;
+                while(hi - lo > 1) {
+                    const int64_t mid = (lo + hi) >> 1;
+                    if(p.win_first[mid] <= g) lo = mid; else hi = mid;
                 }
-                v = make_uint4(t[0], t[1], t[2], t[3]);
+                const int64_t q = lo;
+                const int64_t w = g - p.win_first[q];
+                const int64_t so = p.seq_off[q];
+                const int64_t len = p.seq_off[q + 1] - so;
+                int64_t b = 0, e = len;
+                if(len > p.winlen) { b = w * p.stride; e = min(b + p.winlen, len); }
+                my_abs[r] = so + b;
+                const int nk = int(e - b) - p.k + 1;
+                const int sp = nk < p.s ? (nk < 0 ? 0 : nk) : p.s;
+                t.wnk[i] = nk;
+                t.wout[i] = p.out_first[q] + uint32_t(w);
+                t.wthr[i] = select_threshold(nk, sp);
+                if(i == 0) first_abs = so + b;
+                if(i == nw - 1) last_end = so + e;
             }
+        }
+        first_abs = __shfl_sync(0xFFFFFFFFu, first_abs, 0);
+        const int last = nw - 1;
+        last_end = __shfl_sync(0xFFFFFFFFu, last_end, last & 31);
+        const int64_t sb = first_abs - int64_t((reinterpret_cast<uintptr_t>(p.seq) + uint64_t(first_abs)) & 15u);
+        for(int r = 0; r < 2; ++r) {
+            const int i = lane + 32 * r;
+            if(i < nw) t.wpos[i] = int32_t(my_abs[r] - sb);
+        }
+        const int span_len = int(last_end - sb);
+        if(lane == 0) {
+            t.meta[0] = nw;
+            t.meta[1] = span_len;
+            const uint32_t bytes = uint32_t(((span_len + 15) >> 4) + 2) * 16u;
+            // order earlier generic-proxy reads of this raw buffer before the async-proxy write
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_expect_tx(&s_bar[stage], bytes);
+            tma_load_1d(stage ? raw1 : raw0, p.seq + sb, bytes, &s_bar[stage]);
+        }
+        __syncwarp();
+    };
+
+    if(tid == 0) {
+        mbar_init(&s_bar[0], 1);
+        mbar_init(&s_bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        s_next = 0;
+    }
+    __syncthreads();
+    if(warp == 0 && blockIdx.x < ntiles) prefetch(blockIdx.x, 0);
+
+    uint32_t* mycb = cbuf + warp * SK_CBUF;
+    uint32_t* mytmp = tmpb + warp * 32;
+    const uint32_t ltmask = (1u << lane) - 1u;
+    const uint32_t* hlane = H + (lane & 15) * pitch + (lane >> 4);
+    uint32_t* olane = p.out_feat + lane;
+
+    int it = 0;
+    for(uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        const int stage = it & 1;
+        const uint32_t parity = (it >> 1) & 1;
+        // start the next tile's copy into the other buffer (its previous readers passed the
+        // barrier at the end of the previous iteration)
+        if(warp == 0 && tile + gridDim.x < ntiles) prefetch(tile + gridDim.x, stage ^ 1);
+        __syncthreads();                                   // (a) window table of `stage` visible to all
+        const TileTab t = tab_of(stage);
+        const int nw = t.meta[0];
+        const int ng = (t.meta[1] + 15) >> 4;
+        mbar_wait(&s_bar[stage], parity);
+
+        // ---- (1) pack: raw ASCII (shared) -> 2-bit words + ambiguity bits
+        const uint4* rawv = reinterpret_cast<const uint4*>(stage ? raw1 : raw0);
+        for(int j = tid; j < ng + 2; j += SK_THREADS) {
+            const uint4 v = rawv[j];
             uint32_t c0, c1, c2, c3, d0, d1, d2, d3;
             pack4(v.x, c0, d0);
             pack4(v.y, c1, d1);
             pack4(v.z, c2, d2);
             pack4(v.w, c3, d3);
-            w = (c0 << 24) | (c1 << 16) | (c2 << 8) | c3;
-            a = 0;
+            uint32_t a = 0;
             if((d0 | d1 | d2 | d3) != 0u) {
                 a = (nzmask4(d0) << 12) | (nzmask4(d1) << 8) | (nzmask4(d2) << 4) | nzmask4(d3);
             }
+            pk[j] = (c0 << 24) | (c1 << 16) | (c2 << 8) | c3;
+            amb[j] = a;
         }
-        pk[j] = w;
-        amb[j] = a;
-    }
-    __syncthreads();
+        __syncthreads();                                   // (b)
 
-    // ---- (2) hash every k-mer start of the span (ambiguity checks only where needed)
-    for(int j = tid; j < ng; j += SK_THREADS) {
-        if(p.dbg & 2) break;
-        const uint32_t w0 = pk[j], w1 = pk[j + 1];
-        const uint32_t a = (amb[j] << 16) | amb[j + 1];
-        if(a == 0u) hash_group<K16, false, PITCH, MULHI>(w0, w1, a, p.k, H + j, pitch, p.c65536);
-        else        hash_group<K16, true, PITCH, MULHI>(w0, w1, a, p.k, H + j, pitch, p.c65536);
-    }
-    __syncthreads();
+        // ---- (2) hash every k-mer start of the span (ambiguity checks only where needed)
+        for(int j = tid; j < ng; j += SK_THREADS) {
+            const uint32_t w0 = pk[j], w1 = pk[j + 1];
+            const uint32_t a = (amb[j] << 16) | amb[j + 1];
+            if(a == 0u) hash_group<K16, false, PITCH>(w0, w1, a, p.k, H + j, pitch);
+            else        hash_group<K16, true, PITCH>(w0, w1, a, p.k, H + j, pitch);
+        }
+        __syncthreads();                                   // (c)
 
-    // ---- (3) per-window bottom-s unique: every warp takes two windows at a time so that two
-    // independent sorting networks are in flight (shuffle latency, not issue, was the limiter)
-    uint32_t* cb0 = cbuf + warp * (2 * SK_CBUF);
-    uint32_t* cb1 = cb0 + SK_CBUF;
-    uint32_t* mytmp = tmpb + warp * 32;
-    const uint32_t ltmask = (1u << lane) - 1u;
-    // lane-constant part of the transposed address of position (16*j0 + lane + 32*i)
-    const uint32_t* hlane = H + (lane & 15) * pitch + (lane >> 4);
-    uint32_t* olane = p.out_feat + lane;
-    for(int wi = warp; wi < nw; wi += (PAIR ? 2 : 1) * SK_WARPS) {
-        if(p.dbg & 1) { if(lane < p.s) olane[uint64_t(wout[wi]) * uint32_t(p.s)] = hlane[wpos[wi] >> 4]; continue; }
-        const int wj = wi + SK_WARPS;
-        const bool two = PAIR && wj < nw;
-        // window A
-        const int posA = wpos[wi], nkA = wnk[wi];
-        const uint32_t TA = wthr[wi];
-        const int spA = min(p.s, max(nkA, 0));
-        const uint32_t* hpA = hlane + (posA >> 4);
-        const int relA = lane - (posA & 15);
-        const int spanA = nkA + (posA & 15);
-        // window B (a copy of A's parameters when absent; its results are discarded)
-        const int wjj = two ? wj : wi;
-        const int posB = wpos[wjj], nkB = wnk[wjj];
-        const uint32_t TB = wthr[wjj];
-        const int spB = min(p.s, max(nkB, 0));
-        const uint32_t* hpB = hlane + (posB >> 4);
-        const int relB = lane - (posB & 15);
-        const int spanB = nkB + (posB & 15);
-
-        uint32_t keptA = NOF, keptB = NOF;
-        int noutA = 0, noutB = 0;
-        bool doneA = spA <= 0, doneB = !two || spB <= 0;
-        int cntA = 0, cntB = 0;
-        const bool fastA = !doneA && spanA <= 128, fastB = !doneB && spanB <= 128;
-        if(fastA) cntA = filter_compact(hpA, relA, nkA, TA, cb0, ltmask);
-        if(fastB) cntB = filter_compact(hpB, relB, nkB, TB, cb1, ltmask);
-        __syncwarp();
-        const bool sortA = fastA && cntA <= 32 && (cntA >= spA || TA == 0u);
-        const bool sortB = fastB && cntB <= 32 && (cntB >= spB || TB == 0u);
-        if(sortA || sortB) {
-            uint32_t va = (sortA && lane < cntA) ? tmh_tail(cb0[lane]) : NOF;
-            uint32_t vb = (sortB && lane < cntB) ? tmh_tail(cb1[lane]) : NOF;
-            sort32x2(va, vb, lane);
-            const uint32_t pa = __shfl_up_sync(0xFFFFFFFFu, va, 1);
-            const uint32_t pb = __shfl_up_sync(0xFFFFFFFFu, vb, 1);
-            const bool dup = (lane > 0) && ((va == pa && va != NOF) || (vb == pb && vb != NOF));
-            if(__any_sync(0xFFFFFFFFu, dup)) {
-                va = dedup_sorted(va, lane, mytmp);
-                vb = dedup_sorted(vb, lane, mytmp);
-                if(sortA) { keptA = va; noutA = __popc(__ballot_sync(0xFFFFFFFFu, va != NOF)); doneA = noutA >= spA || TA == 0u; }
-                if(sortB) { keptB = vb; noutB = __popc(__ballot_sync(0xFFFFFFFFu, vb != NOF)); doneB = noutB >= spB || TB == 0u; }
-            } else {
-                if(sortA) { keptA = va; noutA = cntA; doneA = true; }
-                if(sortB) { keptB = vb; noutB = cntB; doneB = true; }
+        // ---- (3) per-window bottom-s unique; warps draw windows from a shared counter so that
+        // the rare expensive windows do not serialise behind a static assignment
+        for(;;) {
+            int wi = 0;
+            if(lane == 0) wi = atomicAdd(&s_next, 1);
+            wi = __shfl_sync(0xFFFFFFFFu, wi, 0);
+            if(wi >= nw) break;
+            const int pos = t.wpos[wi];
+            const int nk = t.wnk[wi];
+            const uint32_t oidx = t.wout[wi];
+            uint32_t T = t.wthr[wi];
+            const int sp = min(p.s, max(nk, 0));
+            uint32_t kept = NOF;
+            int nout = 0;
+            if(sp > 0) {
+                const int off = pos & 15;
+                const uint32_t* hp = hlane + (pos >> 4);
+                const int span = nk + off;
+                const int rel0 = lane - off;
+                bool done = false;
+                if(span <= 128) {
+                    int cnt = filter_compact(hp, rel0, nk, T, mycb, ltmask);
+                    __syncwarp();
+                    if(cnt > 32 && T != 0u) {
+                        // too many survivors: filter the survivors again with 3/4 of the threshold
+                        const uint32_t T2 = ((T >> 16) * 3u / 4u) << 16;
+                        const uint32_t y0 = mycb[lane];
+                        const uint32_t y1 = (lane + 32 < cnt) ? mycb[lane + 32] : NOH;
+                        const uint32_t y2 = (lane + 64 < cnt) ? mycb[lane + 64] : NOH;
+                        const uint32_t y3 = (lane + 96 < cnt) ? mycb[lane + 96] : NOH;
+                        __syncwarp();
+                        int c2 = 0;
+                        const uint32_t ys[4] = {y0, y1, y2, y3};
+#pragma unroll
+                        for(int i = 0; i < 4; ++i) {
+                            const bool pass = ys[i] < T2;
+                            const uint32_t b = __ballot_sync(0xFFFFFFFFu, pass);
+                            if(pass) mycb[c2 + __popc(b & ltmask)] = ys[i];
+                            c2 += __popc(b);
+                        }
+                        __syncwarp();
+                        if(c2 >= sp && c2 <= 32) cnt = c2; else cnt = 0;      // 0 -> exact pass below
+                    }
+                    if(cnt <= 32 && (cnt >= sp || T == 0u) && cnt > 0) {
+                        uint32_t v = lane < cnt ? tmh_tail(mycb[lane]) : NOF;
+                        v = sort32(v, lane);
+                        const uint32_t prev = __shfl_up_sync(0xFFFFFFFFu, v, 1);
+                        const bool dup = (lane > 0) && (v == prev) && (v != NOF);
+                        if(__any_sync(0xFFFFFFFFu, dup)) {
+                            kept = dedup_sorted(v, lane, mytmp);
+                            nout = __popc(__ballot_sync(0xFFFFFFFFu, kept != NOF));
+                        } else {
+                            kept = v;
+                            nout = cnt;
+                        }
+                        done = (nout >= sp) || (T == 0u);
+                    } else if(T == 0u && cnt > 32) {
+                        kept = chunked_select(mycb, cnt, sp, lane, mytmp, nout);
+                        done = true;
+                    } else if(T == 0u && cnt == 0) {
+                        done = true;                       // no valid k-mer at all
+                    }
+                    __syncwarp();
+                }
+                if(!done) kept = exact_select(hp, rel0, nk, span, sp, lane, mytmp, nout);
+                if(nout > sp) nout = sp;
             }
+            if(lane < p.s) olane[uint64_t(oidx) * uint32_t(p.s)] = (lane < sp) ? kept : NOF;
+            if(p.out_cnt != nullptr && lane == 0) p.out_cnt[oidx] = uint32_t(nout);
         }
-        // rare: more than 32 survivors -> merge the compacted survivors 32 at a time
-        if(!doneA && fastA && cntA > 32) { keptA = chunked_select(cb0, cntA, spA, lane, mytmp, noutA); doneA = noutA >= spA || TA == 0u; }
-        if(!doneB && fastB && cntB > 32) { keptB = chunked_select(cb1, cntB, spB, lane, mytmp, noutB); doneB = noutB >= spB || TB == 0u; }
-        // rare: too few distinct hashes below the threshold (or a long window) -> exact pass
-        if(!doneA) keptA = exact_select(hpA, relA, nkA, spanA, spA, lane, mytmp, noutA);
-        if(!doneB) keptB = exact_select(hpB, relB, nkB, spanB, spB, lane, mytmp, noutB);
-        __syncwarp();
-
-        {
-            const uint32_t oidx = wout[wi];
-            if(lane < p.s) olane[uint64_t(oidx) * uint32_t(p.s)] = (lane < spA) ? keptA : NOF;
-            if(p.out_cnt != nullptr && lane == 0) p.out_cnt[oidx] = uint32_t(min(noutA, spA));
-        }
-        if(two) {
-            const uint32_t oidx = wout[wj];
-            if(lane < p.s) olane[uint64_t(oidx) * uint32_t(p.s)] = (lane < spB) ? keptB : NOF;
-            if(p.out_cnt != nullptr && lane == 0) p.out_cnt[oidx] = uint32_t(min(noutB, spB));
-        }
+        __syncthreads();                                   // (d) H / pk / table of `stage` free again
+        if(tid == 0) s_next = 0;
     }
 }
 
@@ -530,7 +575,8 @@ int sketch_config(const mcg_sketch_cfg& cfg, int sketchlen, int64_t winlen, int6
         const int64_t span = (int64_t(w) * adv + 15 + 15) / 16 * 16 + 16;
         const int ng = int(span / 16);
         const int pt = ((ng + 31) / 32) * 32 + 2;
-        const size_t bytes = (size_t(2) * (ng + 2) + size_t(16) * pt + 2 * SK_WARPS * SK_CBUF + SK_WARPS * 32 + 4 * size_t(w)) * 4;
+        const size_t bytes = (size_t(2) * (ng + 2) + size_t(16) * pt + SK_WARPS * SK_CBUF + SK_WARPS * 32 + 2 * (4 * size_t(w) + 4)) * 4
+                           + size_t(2) * (ng + 2) * 16 + 128;
         if((bytes <= 48 * 1024 && ng <= 2 * SK_THREADS) || w == 1) {
             MCG_REQUIRE(bytes <= 200 * 1024, "window too long for the device sketcher");
             *wpc = w; *ngroups = ng; *pitch = pt; *smem = bytes;
@@ -570,32 +616,19 @@ int sketch_launch(mcg_ctx* c, const mcg_sketch_cfg& cfg, int sketchlen, int64_t 
                                                                           c->outfirst.as<uint32_t>());
     c->launches++;
     p.cta_seq = c->outfirst.as<uint32_t>();
-    p.c65536 = 65536u;
-    { const char* e = getenv("MCG_SK_DEBUG"); p.dbg = e ? atoi(e) : 0; }
-    static int variant = -1;
-    if(variant < 0) { const char* e = getenv("MCG_SK_VARIANT"); variant = e ? atoi(e) : SK_DEFAULT_VARIANT; }
-#define SK_LAUNCH(K16, PT, PAIR, MULHI, MINB)                                                                     \
+#define SK_LAUNCH(K16, PT)                                                                                        \
     do {                                                                                                          \
-        auto kern = sketch_kernel<K16, PT, PAIR, MULHI, MINB>;                                                    \
+        auto kern = sketch_kernel<K16, PT>;                                                                       \
         if(smem > 48 * 1024) MCG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))); \
-        kern<<<unsigned(nblocks), SK_THREADS, smem, c->stream>>>(p);                                              \
+        int per_sm = 1;                                                                                           \
+        MCG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, SK_THREADS, smem));                 \
+        if(per_sm < 1) per_sm = 1;                                                                                \
+        const uint64_t grid = std::min<uint64_t>(nblocks, uint64_t(kNumSMs) * uint64_t(per_sm));                  \
+        kern<<<unsigned(grid), SK_THREADS, smem, c->stream>>>(p);                                                 \
     } while(0)
-    if(cfg.k == 16 && p.pitch == SK_PITCH_DEFAULT) {
-        switch(variant & 7) {
-            case 0: SK_LAUNCH(true, SK_PITCH_DEFAULT, false, false, 6); break;
-            case 1: SK_LAUNCH(true, SK_PITCH_DEFAULT, true, false, 6); break;
-            case 2: SK_LAUNCH(true, SK_PITCH_DEFAULT, false, true, 6); break;
-            case 3: SK_LAUNCH(true, SK_PITCH_DEFAULT, true, true, 6); break;
-            case 4: SK_LAUNCH(true, SK_PITCH_DEFAULT, false, false, 4); break;
-            case 5: SK_LAUNCH(true, SK_PITCH_DEFAULT, true, false, 4); break;
-            case 6: SK_LAUNCH(true, SK_PITCH_DEFAULT, false, true, 4); break;
-            default: SK_LAUNCH(true, SK_PITCH_DEFAULT, true, true, 4); break;
-        }
-    } else if(cfg.k == 16) {
-        SK_LAUNCH(true, 0, false, false, 4);
-    } else {
-        SK_LAUNCH(false, 0, false, false, 4);
-    }
+    if(cfg.k == 16 && p.pitch == SK_PITCH_DEFAULT) SK_LAUNCH(true, SK_PITCH_DEFAULT);
+    else if(cfg.k == 16)                           SK_LAUNCH(true, 0);
+    else                                           SK_LAUNCH(false, 0);
 #undef SK_LAUNCH
     c->launches++;
     MCG_CUDA(cudaGetLastError());
