@@ -25,7 +25,7 @@ constexpr int SK_THREADS = 256;
 constexpr int SK_WARPS = SK_THREADS / 32;
 constexpr int SK_CBUF = 128;              // per-warp compaction buffer (hashes)
 constexpr uint32_t NOF = 0xFFFFFFFFu;
-constexpr int SK_PITCH_DEFAULT = 290;       // pitch of the default shape (k=16, winlen=128, stride=113)
+constexpr int SK_PITCH_DEFAULT = 38;        // pitch of the default shape (k=16, winlen=128, stride=113)
 
 struct SketchParams {
     const uint8_t* seq;
@@ -40,7 +40,8 @@ struct SketchParams {
     uint32_t* out_cnt;
     int k, s;
     int64_t winlen, stride;
-    int wpc;                     // windows per CTA
+    int wpc;                     // windows per warp tile
+    int warp_smem;               // bytes of shared memory per warp
     int ngroups;                 // 16-base groups of span capacity
     int pitch;                   // row pitch of the transposed hash array (words)
 };
@@ -291,138 +292,194 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-// per-tile window table (one per pipeline stage)
-struct TileTab {
-    int32_t* wpos;      // [wpc] start of the window inside the span
-    int32_t* wnk;       // [wpc] number of k-mer starts (may be <= 0)
-    uint32_t* wout;     // [wpc] output window index
-    uint32_t* wthr;     // [wpc] selection threshold
-    int32_t* meta;      // [4]: nw, span_len, -, -
+// ---- per-warp selection state of one window
+struct Win {
+    const uint32_t* hp;     // lane's first hash slot
+    int rel0;               // lane's k-mer index of that slot (may be negative)
+    int nk, sp, span;
+    uint32_t T, oidx;
 };
 
-// Persistent kernel: each CTA loops over tiles of `wpc` consecutive windows.  While tile t is
-// packed, hashed and reduced, warp 0 has already resolved tile t+grid and the TMA unit is copying
-// its bytes into the other raw buffer, so neither the dependent index loads nor the DRAM latency
-// of the span sit on the critical path.
+// Threshold filter (+ one refinement when more than 32 hashes survive).  Returns the number of
+// survivors in cb, or -1 when the window needs the exact pass.
+__device__ __forceinline__ int prefilter(const Win& w, uint32_t* cb, int lane, uint32_t ltmask)
+{
+    int cnt = filter_compact(w.hp, w.rel0, w.nk, w.T, cb, ltmask);
+    __syncwarp();
+    if(cnt <= 32) return (cnt >= w.sp || w.T == 0u) ? cnt : -1;
+    if(w.T == 0u) return cnt;                       // no threshold: chunked merge of everything
+    // too many survivors: filter them again with 3/4 of the threshold
+    const uint32_t T2 = ((w.T >> 16) * 3u / 4u) << 16;
+    uint32_t ys[4];
+#pragma unroll
+    for(int i = 0; i < 4; ++i) ys[i] = (lane + 32 * i < cnt) ? cb[lane + 32 * i] : NOH;
+    __syncwarp();
+    int c2 = 0;
+#pragma unroll
+    for(int i = 0; i < 4; ++i) {
+        const bool pass = ys[i] < T2;
+        const uint32_t b = __ballot_sync(0xFFFFFFFFu, pass);
+        if(pass) cb[c2 + __popc(b & ltmask)] = ys[i];
+        c2 += __popc(b);
+    }
+    __syncwarp();
+    return (c2 >= w.sp && c2 <= 32) ? c2 : -1;
+}
+
+// two independent 32-lane sorts, interleaved stage by stage (two shuffles in flight)
+__device__ __forceinline__ void sort32x2(uint32_t& a, uint32_t& b, int lane)
+{
+#pragma unroll
+    for(int k = 2; k <= 32; k <<= 1) {
+        {
+            const uint32_t oa = __shfl_xor_sync(0xFFFFFFFFu, a, k - 1);
+            const uint32_t ob = __shfl_xor_sync(0xFFFFFFFFu, b, k - 1);
+            const bool up = (lane & (k >> 1)) != 0;
+            a = up ? max(a, oa) : min(a, oa);
+            b = up ? max(b, ob) : min(b, ob);
+        }
+#pragma unroll
+        for(int j = k >> 2; j > 0; j >>= 1) {
+            const uint32_t oa = __shfl_xor_sync(0xFFFFFFFFu, a, j);
+            const uint32_t ob = __shfl_xor_sync(0xFFFFFFFFu, b, j);
+            const bool up = (lane & j) != 0;
+            a = up ? max(a, oa) : min(a, oa);
+            b = up ? max(b, ob) : min(b, ob);
+        }
+    }
+}
+
+// finishes one window whose (<= 32 or unfiltered) survivors sit in cb: sorted/unique/cut
+__device__ __forceinline__ uint32_t finish_window(const Win& w, int cnt, uint32_t v, bool sorted, const uint32_t* cb,
+                                                  int lane, uint32_t* tmp, int& nout)
+{
+    uint32_t kept = NOF;
+    bool done = false;
+    nout = 0;
+    if(w.sp <= 0) return NOF;
+    if(sorted) {
+        const uint32_t prev = __shfl_up_sync(0xFFFFFFFFu, v, 1);
+        const bool dup = (lane > 0) && (v == prev) && (v != NOF);
+        if(__any_sync(0xFFFFFFFFu, dup)) {
+            kept = dedup_sorted(v, lane, tmp);
+            nout = __popc(__ballot_sync(0xFFFFFFFFu, kept != NOF));
+        } else {
+            kept = v;
+            nout = cnt;
+        }
+        done = (nout >= w.sp) || (w.T == 0u);
+    } else if(cnt > 32) {                            // only without threshold
+        kept = chunked_select(cb, cnt, w.sp, lane, tmp, nout);
+        done = true;
+    }
+    if(!done) kept = exact_select(w.hp, w.rel0, w.nk, w.span, w.sp, lane, tmp, nout);
+    if(nout > w.sp) nout = w.sp;
+    return kept;
+}
+
+// Persistent, warp-autonomous kernel.  A warp owns tiles of `wpt` consecutive windows (4 at the
+// default shape: one 16-base group per lane).  No block-wide barrier exists: all staging lives in
+// the warp's private slice of shared memory and is ordered by __syncwarp / the warp's own
+// mbarriers.  While a tile is processed, the warp has already resolved the next tile and the TMA
+// unit (cp.async.bulk) is copying its bytes into the warp's other raw buffer.
 template<bool K16, int PITCH>
-__global__ void __launch_bounds__(SK_THREADS, 6)
+__global__ void __launch_bounds__(SK_THREADS, 5)
 sketch_kernel(const SketchParams p)
 {
-    extern __shared__ __align__(128) uint32_t smem[];
+    extern __shared__ __align__(128) uint8_t smem_raw[];
     const int pitch = PITCH > 0 ? PITCH : p.pitch;
-    const int rawcap = (p.ngroups + 2) * 16;                // bytes per raw stage
-    uint8_t*  raw0 = reinterpret_cast<uint8_t*>(smem);
-    uint8_t*  raw1 = raw0 + rawcap;
-    uint32_t* pk   = reinterpret_cast<uint32_t*>(raw1 + rawcap);   // [ngroups + 2]
-    uint32_t* amb  = pk + p.ngroups + 2;                   // [ngroups + 2]
-    uint32_t* H    = amb + p.ngroups + 2;                  // [16 * pitch]
-    uint32_t* cbuf = H + 16 * pitch;                       // [SK_WARPS * SK_CBUF]
-    uint32_t* tmpb = cbuf + SK_WARPS * SK_CBUF;            // [SK_WARPS * 32]
-    int32_t*  tabs = reinterpret_cast<int32_t*>(tmpb + SK_WARPS * 32);   // 2 x (4 * wpc + 4)
-    __shared__ __align__(8) uint64_t s_bar[2];
-    __shared__ int s_next;
-
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
-    const int tabsz = 4 * p.wpc + 4;
-    const uint64_t ntiles = (p.nwin + p.wpc - 1) / p.wpc;
+    const int ngc = p.ngroups;                               // group capacity of a tile span
+    const int rawcap = (ngc + 2) * 16;
+    // per-warp slice
+    uint8_t*  base = smem_raw + size_t(warp) * p.warp_smem;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(base);      // [2]
+    uint8_t*  raw0 = base + 16;
+    uint8_t*  raw1 = raw0 + rawcap;
+    uint32_t* pk   = reinterpret_cast<uint32_t*>(raw1 + rawcap);   // [ngc + 2]
+    uint32_t* amb  = pk + ngc + 2;                           // [ngc + 2]
+    uint32_t* H    = amb + ngc + 2;                          // [16 * pitch]
+    uint32_t* cb0  = H + 16 * pitch;                         // [SK_CBUF]
+    uint32_t* cb1  = cb0 + SK_CBUF;                          // [SK_CBUF]
+    uint32_t* tmp  = cb1 + SK_CBUF;                          // [32]
+    int32_t*  tabs = reinterpret_cast<int32_t*>(tmp + 32);   // 2 x (4 * wpt + 2)
+    const int wpt = p.wpc;
+    const int tabsz = 4 * wpt + 2;
+    const uint64_t ntiles = (p.nwin + wpt - 1) / wpt;
+    const uint64_t nwarps = uint64_t(gridDim.x) * SK_WARPS;
+    const uint64_t gw = uint64_t(blockIdx.x) * SK_WARPS + warp;
 
-    auto tab_of = [&](int stage) {
-        TileTab t;
-        int32_t* base = tabs + stage * tabsz;
-        t.wpos = base;
-        t.wnk = base + p.wpc;
-        t.wout = reinterpret_cast<uint32_t*>(base + 2 * p.wpc);
-        t.wthr = reinterpret_cast<uint32_t*>(base + 3 * p.wpc);
-        t.meta = base + 4 * p.wpc;
-        return t;
-    };
-
-    // warp 0: resolve tile `tile` into table `stage` and start its TMA copy
+    // resolve tile `tile` into table `stage` and start the TMA copy of its bytes
     auto prefetch = [&](uint64_t tile, int stage) {
-        TileTab t = tab_of(stage);
-        const uint64_t g0 = tile * uint64_t(p.wpc);
-        const int nw = int(min(uint64_t(p.wpc), p.nwin - g0));
+        int32_t* tb = tabs + stage * tabsz;
+        const uint64_t g0 = tile * uint64_t(wpt);
+        const int nw = int(min(uint64_t(wpt), p.nwin - g0));
         int64_t first_abs = 0, last_end = 0;
-        int64_t my_abs[2] = {0, 0};
-        for(int r = 0; r < 2; ++r) {
-            const int i = lane + 32 * r;
+        for(int i0 = 0; i0 < nw; i0 += 32) {
+            const int i = i0 + lane;
+            int64_t abs_i = 0, end_i = 0;
             if(i < nw) {
                 const uint32_t g = uint32_t(g0 + i);
-                int64_t lo = p.cta_seq[tile], hi = int64_t(p.cta_seq[tile + 1]) + 1;
-                while(hi - lo > 1) {
-                    const int64_t mid = (lo + hi) >> 1;
-                    if(p.win_first[mid] <= g) lo = mid; else hi = mid;
-                }
-                const int64_t q = lo;
+                int64_t q = p.cta_seq[tile];
+                while(p.win_first[q + 1] <= g) ++q;          // few steps: tiles are short
                 const int64_t w = g - p.win_first[q];
                 const int64_t so = p.seq_off[q];
                 const int64_t len = p.seq_off[q + 1] - so;
                 int64_t b = 0, e = len;
                 if(len > p.winlen) { b = w * p.stride; e = min(b + p.winlen, len); }
-                my_abs[r] = so + b;
+                abs_i = so + b;
+                end_i = so + e;
                 const int nk = int(e - b) - p.k + 1;
                 const int sp = nk < p.s ? (nk < 0 ? 0 : nk) : p.s;
-                t.wnk[i] = nk;
-                t.wout[i] = p.out_first[q] + uint32_t(w);
-                t.wthr[i] = select_threshold(nk, sp);
-                if(i == 0) first_abs = so + b;
-                if(i == nw - 1) last_end = so + e;
+                tb[wpt + i] = nk;
+                reinterpret_cast<uint32_t*>(tb)[2 * wpt + i] = p.out_first[q] + uint32_t(w);
+                reinterpret_cast<uint32_t*>(tb)[3 * wpt + i] = select_threshold(nk, sp);
             }
+            if(i0 == 0) first_abs = __shfl_sync(0xFFFFFFFFu, abs_i, 0);
+            const int sb_lo = int((reinterpret_cast<uintptr_t>(p.seq) + uint64_t(first_abs)) & 15u);
+            if(i < nw) tb[i] = int32_t(abs_i - first_abs) + sb_lo;
+            if(i0 + 32 >= nw) last_end = __shfl_sync(0xFFFFFFFFu, end_i, (nw - 1) & 31);
         }
-        first_abs = __shfl_sync(0xFFFFFFFFu, first_abs, 0);
-        const int last = nw - 1;
-        last_end = __shfl_sync(0xFFFFFFFFu, last_end, last & 31);
         const int64_t sb = first_abs - int64_t((reinterpret_cast<uintptr_t>(p.seq) + uint64_t(first_abs)) & 15u);
-        for(int r = 0; r < 2; ++r) {
-            const int i = lane + 32 * r;
-            if(i < nw) t.wpos[i] = int32_t(my_abs[r] - sb);
-        }
         const int span_len = int(last_end - sb);
         if(lane == 0) {
-            t.meta[0] = nw;
-            t.meta[1] = span_len;
+            tb[4 * wpt] = nw;
+            tb[4 * wpt + 1] = span_len;
             const uint32_t bytes = uint32_t(((span_len + 15) >> 4) + 2) * 16u;
-            // order earlier generic-proxy reads of this raw buffer before the async-proxy write
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            mbar_expect_tx(&s_bar[stage], bytes);
-            tma_load_1d(stage ? raw1 : raw0, p.seq + sb, bytes, &s_bar[stage]);
+            mbar_expect_tx(&bars[stage], bytes);
+            tma_load_1d(stage ? raw1 : raw0, p.seq + sb, bytes, &bars[stage]);
         }
         __syncwarp();
     };
 
-    if(tid == 0) {
-        mbar_init(&s_bar[0], 1);
-        mbar_init(&s_bar[1], 1);
+    if(lane == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        s_next = 0;
     }
-    __syncthreads();
-    if(warp == 0 && blockIdx.x < ntiles) prefetch(blockIdx.x, 0);
+    __syncwarp();
+    if(gw < ntiles) prefetch(gw, 0);
 
-    uint32_t* mycb = cbuf + warp * SK_CBUF;
-    uint32_t* mytmp = tmpb + warp * 32;
     const uint32_t ltmask = (1u << lane) - 1u;
     const uint32_t* hlane = H + (lane & 15) * pitch + (lane >> 4);
     uint32_t* olane = p.out_feat + lane;
 
     int it = 0;
-    for(uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    for(uint64_t tile = gw; tile < ntiles; tile += nwarps, ++it) {
         const int stage = it & 1;
         const uint32_t parity = (it >> 1) & 1;
-        // start the next tile's copy into the other buffer (its previous readers passed the
-        // barrier at the end of the previous iteration)
-        if(warp == 0 && tile + gridDim.x < ntiles) prefetch(tile + gridDim.x, stage ^ 1);
-        __syncthreads();                                   // (a) window table of `stage` visible to all
-        const TileTab t = tab_of(stage);
-        const int nw = t.meta[0];
-        const int ng = (t.meta[1] + 15) >> 4;
-        mbar_wait(&s_bar[stage], parity);
+        if(tile + nwarps < ntiles) prefetch(tile + nwarps, stage ^ 1);
+        const int32_t* tb = tabs + stage * tabsz;
+        const int nw = tb[4 * wpt];
+        const int ng = (tb[4 * wpt + 1] + 15) >> 4;
+        mbar_wait(&bars[stage], parity);
 
         // ---- (1) pack: raw ASCII (shared) -> 2-bit words + ambiguity bits
         const uint4* rawv = reinterpret_cast<const uint4*>(stage ? raw1 : raw0);
-        for(int j = tid; j < ng + 2; j += SK_THREADS) {
+        for(int j = lane; j < ng + 2; j += 32) {
             const uint4 v = rawv[j];
             uint32_t c0, c1, c2, c3, d0, d1, d2, d3;
             pack4(v.x, c0, d0);
@@ -436,89 +493,60 @@ sketch_kernel(const SketchParams p)
             pk[j] = (c0 << 24) | (c1 << 16) | (c2 << 8) | c3;
             amb[j] = a;
         }
-        __syncthreads();                                   // (b)
+        __syncwarp();
 
-        // ---- (2) hash every k-mer start of the span (ambiguity checks only where needed)
-        for(int j = tid; j < ng; j += SK_THREADS) {
+        // ---- (2) hash every k-mer start of the span
+        for(int j = lane; j < ng; j += 32) {
             const uint32_t w0 = pk[j], w1 = pk[j + 1];
             const uint32_t a = (amb[j] << 16) | amb[j + 1];
             if(a == 0u) hash_group<K16, false, PITCH>(w0, w1, a, p.k, H + j, pitch);
             else        hash_group<K16, true, PITCH>(w0, w1, a, p.k, H + j, pitch);
         }
-        __syncthreads();                                   // (c)
+        __syncwarp();
 
-        // ---- (3) per-window bottom-s unique; warps draw windows from a shared counter so that
-        // the rare expensive windows do not serialise behind a static assignment
-        for(;;) {
-            int wi = 0;
-            if(lane == 0) wi = atomicAdd(&s_next, 1);
-            wi = __shfl_sync(0xFFFFFFFFu, wi, 0);
-            if(wi >= nw) break;
-            const int pos = t.wpos[wi];
-            const int nk = t.wnk[wi];
-            const uint32_t oidx = t.wout[wi];
-            uint32_t T = t.wthr[wi];
-            const int sp = min(p.s, max(nk, 0));
-            uint32_t kept = NOF;
-            int nout = 0;
-            if(sp > 0) {
-                const int off = pos & 15;
-                const uint32_t* hp = hlane + (pos >> 4);
-                const int span = nk + off;
-                const int rel0 = lane - off;
-                bool done = false;
-                if(span <= 128) {
-                    int cnt = filter_compact(hp, rel0, nk, T, mycb, ltmask);
-                    __syncwarp();
-                    if(cnt > 32 && T != 0u) {
-                        // too many survivors: filter the survivors again with 3/4 of the threshold
-                        const uint32_t T2 = ((T >> 16) * 3u / 4u) << 16;
-                        const uint32_t y0 = mycb[lane];
-                        const uint32_t y1 = (lane + 32 < cnt) ? mycb[lane + 32] : NOH;
-                        const uint32_t y2 = (lane + 64 < cnt) ? mycb[lane + 64] : NOH;
-                        const uint32_t y3 = (lane + 96 < cnt) ? mycb[lane + 96] : NOH;
-                        __syncwarp();
-                        int c2 = 0;
-                        const uint32_t ys[4] = {y0, y1, y2, y3};
-#pragma unroll
-                        for(int i = 0; i < 4; ++i) {
-                            const bool pass = ys[i] < T2;
-                            const uint32_t b = __ballot_sync(0xFFFFFFFFu, pass);
-                            if(pass) mycb[c2 + __popc(b & ltmask)] = ys[i];
-                            c2 += __popc(b);
-                        }
-                        __syncwarp();
-                        if(c2 >= sp && c2 <= 32) cnt = c2; else cnt = 0;      // 0 -> exact pass below
-                    }
-                    if(cnt <= 32 && (cnt >= sp || T == 0u) && cnt > 0) {
-                        uint32_t v = lane < cnt ? tmh_tail(mycb[lane]) : NOF;
-                        v = sort32(v, lane);
-                        const uint32_t prev = __shfl_up_sync(0xFFFFFFFFu, v, 1);
-                        const bool dup = (lane > 0) && (v == prev) && (v != NOF);
-                        if(__any_sync(0xFFFFFFFFu, dup)) {
-                            kept = dedup_sorted(v, lane, mytmp);
-                            nout = __popc(__ballot_sync(0xFFFFFFFFu, kept != NOF));
-                        } else {
-                            kept = v;
-                            nout = cnt;
-                        }
-                        done = (nout >= sp) || (T == 0u);
-                    } else if(T == 0u && cnt > 32) {
-                        kept = chunked_select(mycb, cnt, sp, lane, mytmp, nout);
-                        done = true;
-                    } else if(T == 0u && cnt == 0) {
-                        done = true;                       // no valid k-mer at all
-                    }
-                    __syncwarp();
-                }
-                if(!done) kept = exact_select(hp, rel0, nk, span, sp, lane, mytmp, nout);
-                if(nout > sp) nout = sp;
+        // ---- (3) bottom-s unique, two windows at a time
+        for(int wi = 0; wi < nw; wi += 2) {
+            const bool two = wi + 1 < nw;
+            const int wj = two ? wi + 1 : wi;
+            Win A, B;
+            {
+                const int pos = tb[wi];
+                A.nk = tb[wpt + wi];
+                A.oidx = reinterpret_cast<const uint32_t*>(tb)[2 * wpt + wi];
+                A.T = reinterpret_cast<const uint32_t*>(tb)[3 * wpt + wi];
+                A.sp = min(p.s, max(A.nk, 0));
+                A.hp = hlane + (pos >> 4);
+                A.rel0 = lane - (pos & 15);
+                A.span = A.nk + (pos & 15);
             }
-            if(lane < p.s) olane[uint64_t(oidx) * uint32_t(p.s)] = (lane < sp) ? kept : NOF;
-            if(p.out_cnt != nullptr && lane == 0) p.out_cnt[oidx] = uint32_t(nout);
+            {
+                const int pos = tb[wj];
+                B.nk = tb[wpt + wj];
+                B.oidx = reinterpret_cast<const uint32_t*>(tb)[2 * wpt + wj];
+                B.T = reinterpret_cast<const uint32_t*>(tb)[3 * wpt + wj];
+                B.sp = two ? min(p.s, max(B.nk, 0)) : 0;
+                B.hp = hlane + (pos >> 4);
+                B.rel0 = lane - (pos & 15);
+                B.span = B.nk + (pos & 15);
+            }
+            int cntA = -1, cntB = -1;
+            if(A.sp > 0 && A.span <= 128) cntA = prefilter(A, cb0, lane, ltmask);
+            if(B.sp > 0 && B.span <= 128) cntB = prefilter(B, cb1, lane, ltmask);
+            const bool sA = cntA >= 0 && cntA <= 32, sB = cntB >= 0 && cntB <= 32;
+            uint32_t va = (sA && lane < cntA) ? tmh_tail(cb0[lane]) : NOF;
+            uint32_t vb = (sB && lane < cntB) ? tmh_tail(cb1[lane]) : NOF;
+            if(sA || sB) sort32x2(va, vb, lane);
+            int noutA, noutB;
+            const uint32_t keptA = finish_window(A, cntA, va, sA, cb0, lane, tmp, noutA);
+            if(lane < p.s) olane[uint64_t(A.oidx) * uint32_t(p.s)] = (lane < A.sp) ? keptA : NOF;
+            if(p.out_cnt != nullptr && lane == 0) p.out_cnt[A.oidx] = uint32_t(noutA);
+            if(two) {
+                const uint32_t keptB = finish_window(B, cntB, vb, sB, cb1, lane, tmp, noutB);
+                if(lane < p.s) olane[uint64_t(B.oidx) * uint32_t(p.s)] = (lane < B.sp) ? keptB : NOF;
+                if(p.out_cnt != nullptr && lane == 0) p.out_cnt[B.oidx] = uint32_t(noutB);
+            }
+            __syncwarp();
         }
-        __syncthreads();                                   // (d) H / pk / table of `stage` free again
-        if(tid == 0) s_next = 0;
     }
 }
 
@@ -560,30 +588,27 @@ int window_prefix(mcg_ctx* c, int64_t winlen, int64_t stride, const int64_t* d_s
 }
 
 int sketch_config(const mcg_sketch_cfg& cfg, int sketchlen, int64_t winlen, int64_t stride,
-                  int* wpc, int* ngroups, int* pitch, size_t* smem)
+                  int* wpt, int* ngroups, int* pitch, size_t* warp_smem)
 {
     MCG_REQUIRE(cfg.k >= 1 && cfg.k <= MCG_MAX_K, "kmerlen %d outside 1..%d", cfg.k, MCG_MAX_K);
     MCG_REQUIRE(sketchlen >= 1 && sketchlen <= MCG_MAX_SKETCH, "sketchlen %d outside 1..%d", sketchlen, MCG_MAX_SKETCH);
     MCG_REQUIRE(winlen >= 1 && stride >= 1, "window length and stride must be >= 1");
     const int64_t adv = winlen > stride ? winlen : stride;
-    MCG_REQUIRE(adv <= 32768, "window length / stride above 32768 are not supported on the device");
-    // as many windows as keep the 16-base groups of a typical span within one pass of the CTA
-    int w = int((int64_t(SK_THREADS) * 16 - 30 - winlen) / stride) + 1;
-    if(w > 40) w = 40;
+    MCG_REQUIRE(adv <= 8192, "window length / stride above 8192 are not supported on the device");
+    // windows per warp tile: a typical span (same sequence) fits one 16-base group per lane
+    int64_t w = (512 - 30 - winlen) / stride + 1;
+    if(winlen > 512 - 30) w = 1;
+    if(w > 16) w = 16;
     if(w < 1) w = 1;
-    for(;;) {
-        const int64_t span = (int64_t(w) * adv + 15 + 15) / 16 * 16 + 16;
-        const int ng = int(span / 16);
-        const int pt = ((ng + 31) / 32) * 32 + 2;
-        const size_t bytes = (size_t(2) * (ng + 2) + size_t(16) * pt + SK_WARPS * SK_CBUF + SK_WARPS * 32 + 2 * (4 * size_t(w) + 4)) * 4
-                           + size_t(2) * (ng + 2) * 16 + 128;
-        if((bytes <= 48 * 1024 && ng <= 2 * SK_THREADS) || w == 1) {
-            MCG_REQUIRE(bytes <= 200 * 1024, "window too long for the device sketcher");
-            *wpc = w; *ngroups = ng; *pitch = pt; *smem = bytes;
-            return MCG_OK;
-        }
-        w = w > 8 ? w - 4 : w - 1;
-    }
+    // capacity for the worst case (every window in a different sequence)
+    const int ng = int((w * adv + 30 + 15) / 16) + 1;
+    int pt = ng + 4;
+    while((pt & 3) != 2) ++pt;                  // pitch/2 odd: conflict-free transposed reads
+    size_t bytes = 16 + size_t(2) * (ng + 2) * 16 + (size_t(2) * (ng + 2) + size_t(16) * pt + 2 * SK_CBUF + 32 + 2 * (4 * size_t(w) + 2)) * 4;
+    bytes = (bytes + 127) & ~size_t(127);
+    MCG_REQUIRE(bytes * SK_WARPS <= 220 * 1024, "window too long for the device sketcher");
+    *wpt = int(w); *ngroups = ng; *pitch = pt; *warp_smem = bytes;
+    return MCG_OK;
 }
 
 int sketch_launch(mcg_ctx* c, const mcg_sketch_cfg& cfg, int sketchlen, int64_t winlen, int64_t stride,
@@ -593,8 +618,10 @@ int sketch_launch(mcg_ctx* c, const mcg_sketch_cfg& cfg, int sketchlen, int64_t 
 {
     if(nwin == 0) return MCG_OK;
     SketchParams p;
-    size_t smem = 0;
-    MCG_TRY(sketch_config(cfg, sketchlen, winlen, stride, &p.wpc, &p.ngroups, &p.pitch, &smem));
+    size_t wsmem = 0;
+    MCG_TRY(sketch_config(cfg, sketchlen, winlen, stride, &p.wpc, &p.ngroups, &p.pitch, &wsmem));
+    p.warp_smem = int(wsmem);
+    const size_t smem = wsmem * SK_WARPS;
     p.seq = reinterpret_cast<const uint8_t*>(d_seq);
     p.total_bytes = total_bytes;
     p.seq_off = d_seq_off;
@@ -623,7 +650,7 @@ int sketch_launch(mcg_ctx* c, const mcg_sketch_cfg& cfg, int sketchlen, int64_t 
         int per_sm = 1;                                                                                           \
         MCG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, SK_THREADS, smem));                 \
         if(per_sm < 1) per_sm = 1;                                                                                \
-        const uint64_t grid = std::min<uint64_t>(nblocks, uint64_t(kNumSMs) * uint64_t(per_sm));                  \
+        const uint64_t grid = std::min<uint64_t>((nblocks + SK_WARPS - 1) / SK_WARPS, uint64_t(kNumSMs) * uint64_t(per_sm));                   \
         kern<<<unsigned(grid), SK_THREADS, smem, c->stream>>>(p);                                                 \
     } while(0)
     if(cfg.k == 16 && p.pitch == SK_PITCH_DEFAULT) SK_LAUNCH(true, SK_PITCH_DEFAULT);
