@@ -383,7 +383,7 @@ __device__ __forceinline__ uint32_t finish_window(const Win& w, int cnt, uint32_
 // mbarriers.  While a tile is processed, the warp has already resolved the next tile and the TMA
 // unit (cp.async.bulk) is copying its bytes into the warp's other raw buffer.
 template<bool K16, int PITCH>
-__global__ void __launch_bounds__(SK_THREADS, 5)
+__global__ void __launch_bounds__(SK_THREADS, 4)
 sketch_kernel(const SketchParams p)
 {
     extern __shared__ __align__(128) uint8_t smem_raw[];
