@@ -160,7 +160,7 @@ def run_reference(args):
     else:
         impl, kind = po.Oracle(), "port"
     # bounded sample of the same workload: ~22 Mbp/s/core => a few seconds per step
-    sample_mbp = int(min(args.mbp, max(10, 8 * cores)))
+    sample_mbp = int(min(args.mbp, max(10, 16 * cores)))
     G = max(sample_mbp // 5, 1)
     buf, offs = make_genome_block(0, G, GENOME_LEN)
     bp = int(offs[-1])
@@ -319,7 +319,7 @@ def run_mcgpu(args):
             from oracle import pyoracle as po
             cores = os.cpu_count() or 1
             impl, kind = (po.Reference(), "reference") if po.have_reference() else (po.Oracle(), "port")
-            sg = int(max(2, min(G, 2 * cores)))
+            sg = int(max(2, min(G, 40 * cores)))          # ~20 core-seconds of the reference's sketcher
             t, cs, nw = impl.sketch_throughput(hbuf[:sg * GENOME_LEN], offs[:sg + 1].copy(), K, S, WINLEN, STRIDE, threads=cores)
             line["cpu_baseline"] = {"value": sg * GENOME_LEN / t, "unit": "bp/s", "cores": cores, "kind": kind,
                                     "sample": "%d of the %d genomes (%d Mbp), %d threads, %.1f s" % (sg, G, sg * 5, cores, t)}

@@ -3,6 +3,7 @@
 #include "common.cuh"
 
 #include <cstdarg>
+#include <algorithm>
 
 namespace mcg {
 
@@ -145,6 +146,10 @@ int mcg_ctx_destroy(mcg_ctx* c)
                       &c->m_brank, &c->m_stats};
     for(DevBuf* b : bufs) b->release();
     if(c->pinned != nullptr) cudaFreeHost(c->pinned);
+    if(c->s_h2d) cudaStreamDestroy(c->s_h2d);
+    if(c->s_d2h) cudaStreamDestroy(c->s_d2h);
+    for(int i = 0; i < 4; ++i) { if(c->ev_h2d[i]) cudaEventDestroy(c->ev_h2d[i]); if(c->ev_k[i]) cudaEventDestroy(c->ev_k[i]); }
+    if(c->ev_misc) cudaEventDestroy(c->ev_misc);
     if(c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
     return MCG_OK;
@@ -226,6 +231,23 @@ int mcg_sketch_windows_dev(mcg_ctx* c, const mcg_sketch_cfg* cfg,
                          d_out_features, d_out_counts);
 }
 
+static int ensure_pipeline(mcg_ctx* c)
+{
+    if(c->s_h2d != nullptr) return MCG_OK;
+    MCG_CUDA(cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
+    MCG_CUDA(cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
+    for(int i = 0; i < 4; ++i) {
+        MCG_CUDA(cudaEventCreateWithFlags(&c->ev_h2d[i], cudaEventDisableTiming));
+        MCG_CUDA(cudaEventCreateWithFlags(&c->ev_k[i], cudaEventDisableTiming));
+    }
+    MCG_CUDA(cudaEventCreateWithFlags(&c->ev_misc, cudaEventDisableTiming));
+    return MCG_OK;
+}
+
+// Host path: the input is cut into chunks of windows; chunk i+1 is copied to the device
+// (H2D stream) while chunk i is sketched (ctx stream) and the sketches of chunk i-1 travel
+// back (D2H stream).  PCIe is full duplex, so the call costs about max(H2D, D2H) instead
+// of H2D + K1 + D2H.
 int mcg_sketch_windows(mcg_ctx* c, const mcg_sketch_cfg* cfg,
                        const char* seq_bytes, const int64_t* seq_offsets, int64_t nseq,
                        uint32_t* out_features, uint32_t* out_counts, int64_t* out_nwin)
@@ -234,24 +256,79 @@ int mcg_sketch_windows(mcg_ctx* c, const mcg_sketch_cfg* cfg,
     MCG_REQUIRE(nseq >= 0, "nseq < 0");
     const int64_t nwin = mcg_count_windows(cfg, seq_offsets, nseq);
     MCG_REQUIRE(nwin >= 0, "bad window parameters");
+    MCG_REQUIRE(nwin < (1ll << 32), "more than 2^32-1 windows in one call");
     if(out_nwin != nullptr) *out_nwin = nwin;
     if(nseq == 0 || nwin == 0) return MCG_OK;
-    MCG_REQUIRE(out_features != nullptr, "out_features is NULL");
+    MCG_REQUIRE(out_features != nullptr && seq_bytes != nullptr, "NULL buffer");
+    MCG_REQUIRE(seq_offsets[0] == 0, "seq_offsets[0] must be 0");
     MCG_CUDA(cudaSetDevice(c->device));
-    const int64_t base = seq_offsets[0];
-    const int64_t total = seq_offsets[nseq] - base;
-    MCG_REQUIRE(base == 0, "seq_offsets[0] must be 0");
+    MCG_TRY(ensure_pipeline(c));
+    const int64_t total = seq_offsets[nseq];
     const int s = cfg->sketchlen;
-    MCG_TRY(c->seq.reserve(size_t(total) + 64));
+    int wpt = 0;
+    MCG_TRY(sketch_config(*cfg, s, cfg->winlen, cfg->winstride, &wpt, nullptr, nullptr, nullptr));
+    // chunking by windows: ~32 MB of sequence per chunk
+    const int64_t adv = cfg->winstride;
+    int64_t wchunk = (int64_t(32) << 20) / (adv > 0 ? adv : 1);
+    wchunk = (wchunk / wpt + 1) * wpt;
+    const int64_t nchunks = (nwin + wchunk - 1) / wchunk;
+    MCG_TRY(c->seq.reserve(size_t(total) + 128));
     MCG_TRY(c->seqoff.reserve(size_t(nseq + 1) * sizeof(int64_t)));
+    MCG_TRY(c->winfirst.reserve(size_t(nseq + 2) * sizeof(uint32_t)));
     MCG_TRY(c->q_feat.reserve(size_t(nwin) * s * sizeof(uint32_t)));
     if(out_counts != nullptr) MCG_TRY(c->tmp0.reserve(size_t(nwin) * sizeof(uint32_t)));
-    MCG_TRY(copy_in(c, c->seq.p, seq_bytes, size_t(total)));
+    MCG_TRY(c->outfirst.reserve(size_t(nwin / wpt + 8 * nchunks + 64) * sizeof(uint32_t)));
+    // window prefix per sequence on the host (chunk boundaries) and on the device (kernel)
+    std::vector<uint64_t> wf(size_t(nseq) + 1, 0);
+    for(int64_t i = 0; i < nseq; ++i)
+        wf[i + 1] = wf[i] + uint64_t(num_windows(seq_offsets[i + 1] - seq_offsets[i], cfg->winlen, cfg->winstride));
     MCG_TRY(copy_in(c, c->seqoff.p, seq_offsets, size_t(nseq + 1) * sizeof(int64_t)));
-    MCG_TRY(mcg_sketch_windows_dev(c, cfg, c->seq.as<char>(), total, c->seqoff.as<int64_t>(), nseq, nwin,
-                                   c->q_feat.as<uint32_t>(), out_counts ? c->tmp0.as<uint32_t>() : nullptr));
-    MCG_TRY(copy_out(c, out_features, c->q_feat.p, size_t(nwin) * s * sizeof(uint32_t)));
-    if(out_counts != nullptr) MCG_TRY(copy_out(c, out_counts, c->tmp0.p, size_t(nwin) * sizeof(uint32_t)));
+    MCG_TRY(window_prefix(c, cfg->winlen, cfg->winstride, c->seqoff.as<int64_t>(), nseq, c->winfirst.as<uint32_t>(), nullptr));
+    MCG_CUDA(cudaEventRecord(c->ev_misc, c->stream));
+    MCG_CUDA(cudaStreamWaitEvent(c->s_h2d, c->ev_misc, 0));     // scratch buffers are ours from here on
+    MCG_CUDA(cudaStreamWaitEvent(c->s_d2h, c->ev_misc, 0));
+
+    // end byte (exclusive) of window g
+    auto window_end = [&](uint64_t g) -> int64_t {
+        size_t lo = 0, hi = size_t(nseq);
+        while(hi - lo > 1) { const size_t mid = (lo + hi) / 2; if(wf[mid] <= g) lo = mid; else hi = mid; }
+        const int64_t len = seq_offsets[lo + 1] - seq_offsets[lo];
+        if(len <= cfg->winlen) return seq_offsets[lo + 1];
+        const int64_t b = int64_t(g - wf[lo]) * cfg->winstride;
+        return seq_offsets[lo] + (b + cfg->winlen < len ? b + cfg->winlen : len);
+    };
+
+    int64_t copied = 0;
+    uint64_t tile_off = 0;
+    for(int64_t ch = 0; ch < nchunks; ++ch) {
+        const uint64_t ga = uint64_t(ch) * uint64_t(wchunk);
+        const uint64_t gb = std::min<uint64_t>(uint64_t(nwin), ga + uint64_t(wchunk));
+        const int slot = int(ch & 3);
+        // (1) bytes up to the end of the chunk's last window
+        const int64_t hi = (ch + 1 == nchunks) ? total : window_end(gb - 1);
+        if(hi > copied) {
+            MCG_CUDA(cudaMemcpyAsync(c->seq.as<char>() + copied, seq_bytes + copied, size_t(hi - copied),
+                                     cudaMemcpyHostToDevice, c->s_h2d));
+            copied = hi;
+        }
+        MCG_CUDA(cudaEventRecord(c->ev_h2d[slot], c->s_h2d));
+        // (2) sketch the chunk
+        MCG_CUDA(cudaStreamWaitEvent(c->stream, c->ev_h2d[slot], 0));
+        MCG_TRY(sketch_launch(c, *cfg, s, cfg->winlen, cfg->winstride, c->seq.as<char>(), total, c->seqoff.as<int64_t>(), nseq,
+                              c->winfirst.as<uint32_t>(), c->winfirst.as<uint32_t>(), gb, c->q_feat.as<uint32_t>(),
+                              out_counts ? c->tmp0.as<uint32_t>() : nullptr, ga, c->stream,
+                              c->outfirst.as<uint32_t>() + tile_off));
+        tile_off += (gb - ga) / uint64_t(wpt) + 4;
+        MCG_CUDA(cudaEventRecord(c->ev_k[slot], c->stream));
+        // (3) results of the chunk back to the host
+        MCG_CUDA(cudaStreamWaitEvent(c->s_d2h, c->ev_k[slot], 0));
+        MCG_CUDA(cudaMemcpyAsync(out_features + ga * uint64_t(s), c->q_feat.as<uint32_t>() + ga * uint64_t(s),
+                                 size_t(gb - ga) * s * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->s_d2h));
+        if(out_counts != nullptr)
+            MCG_CUDA(cudaMemcpyAsync(out_counts + ga, c->tmp0.as<uint32_t>() + ga, size_t(gb - ga) * sizeof(uint32_t),
+                                     cudaMemcpyDeviceToHost, c->s_d2h));
+    }
+    MCG_CUDA(cudaStreamSynchronize(c->s_d2h));
     MCG_CUDA(cudaStreamSynchronize(c->stream));
     return MCG_OK;
 }

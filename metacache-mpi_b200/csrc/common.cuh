@@ -70,6 +70,11 @@ struct mcg_ctx {
     mcg::DevBuf m_tax, m_hits, m_n, m_o_tax, m_o_hits, m_o_n, m_best, m_brank, m_stats;
     void* pinned = nullptr;           // small pinned staging area for scalars
     size_t pinned_cap = 0;
+    // copy streams + events of the pipelined host entry points
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+    cudaEvent_t ev_h2d[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_k[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_misc = nullptr;
 };
 
 struct mcg_db {
@@ -134,7 +139,10 @@ int radix_sort_pairs(mcg_ctx* c, uint32_t* keys, uint32_t* vals, uint32_t* keys_
 int sketch_launch(mcg_ctx* c, const mcg_sketch_cfg& cfg, int sketchlen, int64_t winlen, int64_t stride,
                   const char* d_seq, int64_t total_bytes, const int64_t* d_seq_off, int64_t nseq,
                   const uint32_t* d_win_first, const uint32_t* d_out_first, uint64_t nwin,
-                  uint32_t* d_out_feat, uint32_t* d_out_cnt);
+                  uint32_t* d_out_feat, uint32_t* d_out_cnt, uint64_t win_lo = 0, cudaStream_t stream = nullptr,
+                  uint32_t* d_tile_scratch = nullptr);
+int sketch_config(const mcg_sketch_cfg& cfg, int sketchlen, int64_t winlen, int64_t stride,
+                  int* wpt, int* ngroups, int* pitch, size_t* warp_smem);
 int window_prefix(mcg_ctx* c, int64_t winlen, int64_t stride, const int64_t* d_seq_off, int64_t nseq,
                   uint32_t* d_win_first /* nseq+1 */, uint64_t* h_total);
 

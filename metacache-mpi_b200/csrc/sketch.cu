@@ -35,7 +35,8 @@ struct SketchParams {
     const uint32_t* win_first;   // [nseq+1] window prefix in processing order
     const uint32_t* out_first;   // [nseq]   output index of each sequence's first window
     const uint32_t* cta_seq;     // [ntiles+1] sequence holding the first window of each tile
-    uint64_t nwin;
+    uint64_t nwin;               // end of the window range of this launch (global window index)
+    uint64_t win_lo;             // first window of this launch
     uint32_t* out_feat;
     uint32_t* out_cnt;
     int k, s;
@@ -407,14 +408,14 @@ sketch_kernel(const SketchParams p)
     int32_t*  tabs = reinterpret_cast<int32_t*>(tmp + 32);   // 2 x (4 * wpt + 2)
     const int wpt = p.wpc;
     const int tabsz = 4 * wpt + 2;
-    const uint64_t ntiles = (p.nwin + wpt - 1) / wpt;
+    const uint64_t ntiles = (p.nwin - p.win_lo + wpt - 1) / wpt;
     const uint64_t nwarps = uint64_t(gridDim.x) * SK_WARPS;
     const uint64_t gw = uint64_t(blockIdx.x) * SK_WARPS + warp;
 
     // resolve tile `tile` into table `stage` and start the TMA copy of its bytes
     auto prefetch = [&](uint64_t tile, int stage) {
         int32_t* tb = tabs + stage * tabsz;
-        const uint64_t g0 = tile * uint64_t(wpt);
+        const uint64_t g0 = p.win_lo + tile * uint64_t(wpt);
         const int nw = int(min(uint64_t(wpt), p.nwin - g0));
         int64_t first_abs = 0, last_end = 0;
         for(int i0 = 0; i0 < nw; i0 += 32) {
@@ -552,12 +553,12 @@ sketch_kernel(const SketchParams p)
 
 // sequence that holds the first window of every CTA (one binary search per CTA, done up front
 // so that the main kernel starts with one load instead of a chain of dependent ones)
-__global__ void cta_seq_kernel(const uint32_t* win_first, int64_t nseq, int wpc, uint32_t nblocks, uint32_t* cta_seq)
+__global__ void cta_seq_kernel(const uint32_t* win_first, int64_t nseq, int wpc, uint32_t nblocks, uint64_t win_lo, uint32_t* cta_seq)
 {
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if(b > nblocks) return;
     if(b == nblocks) { cta_seq[b] = uint32_t(nseq - 1); return; }
-    const uint32_t g = b * uint32_t(wpc);
+    const uint32_t g = uint32_t(win_lo + uint64_t(b) * uint32_t(wpc));
     int64_t lo = 0, hi = nseq;
     while(hi - lo > 1) {
         const int64_t mid = (lo + hi) >> 1;
@@ -590,6 +591,10 @@ int window_prefix(mcg_ctx* c, int64_t winlen, int64_t stride, const int64_t* d_s
 int sketch_config(const mcg_sketch_cfg& cfg, int sketchlen, int64_t winlen, int64_t stride,
                   int* wpt, int* ngroups, int* pitch, size_t* warp_smem)
 {
+    int dummy_i; size_t dummy_s;
+    if(!ngroups) ngroups = &dummy_i;
+    if(!pitch) pitch = &dummy_i;
+    if(!warp_smem) warp_smem = &dummy_s;
     MCG_REQUIRE(cfg.k >= 1 && cfg.k <= MCG_MAX_K, "kmerlen %d outside 1..%d", cfg.k, MCG_MAX_K);
     MCG_REQUIRE(sketchlen >= 1 && sketchlen <= MCG_MAX_SKETCH, "sketchlen %d outside 1..%d", sketchlen, MCG_MAX_SKETCH);
     MCG_REQUIRE(winlen >= 1 && stride >= 1, "window length and stride must be >= 1");
@@ -614,9 +619,10 @@ int sketch_config(const mcg_sketch_cfg& cfg, int sketchlen, int64_t winlen, int6
 int sketch_launch(mcg_ctx* c, const mcg_sketch_cfg& cfg, int sketchlen, int64_t winlen, int64_t stride,
                   const char* d_seq, int64_t total_bytes, const int64_t* d_seq_off, int64_t nseq,
                   const uint32_t* d_win_first, const uint32_t* d_out_first, uint64_t nwin,
-                  uint32_t* d_out_feat, uint32_t* d_out_cnt)
+                  uint32_t* d_out_feat, uint32_t* d_out_cnt, uint64_t win_lo, cudaStream_t stream, uint32_t* d_tile_scratch)
 {
-    if(nwin == 0) return MCG_OK;
+    if(nwin <= win_lo) return MCG_OK;
+    if(stream == nullptr) stream = c->stream;
     SketchParams p;
     size_t wsmem = 0;
     MCG_TRY(sketch_config(cfg, sketchlen, winlen, stride, &p.wpc, &p.ngroups, &p.pitch, &wsmem));
@@ -629,20 +635,25 @@ int sketch_launch(mcg_ctx* c, const mcg_sketch_cfg& cfg, int sketchlen, int64_t 
     p.win_first = d_win_first;
     p.out_first = d_out_first;
     p.nwin = nwin;
+    p.win_lo = win_lo;
     p.out_feat = d_out_feat;
     p.out_cnt = d_out_cnt;
     p.k = cfg.k;
     p.s = sketchlen;
     p.winlen = winlen;
     p.stride = stride;
-    const uint64_t nblocks = (nwin + p.wpc - 1) / p.wpc;
+    const uint64_t nblocks = (nwin - win_lo + p.wpc - 1) / p.wpc;
     MCG_REQUIRE(nblocks < (1ull << 31), "too many windows in one launch");
     MCG_REQUIRE(nseq < (1ll << 32), "too many sequences in one launch");
-    MCG_TRY(c->outfirst.reserve((nblocks + 2) * sizeof(uint32_t)));
-    cta_seq_kernel<<<unsigned((nblocks + 256) / 256), 256, 0, c->stream>>>(d_win_first, nseq, p.wpc, uint32_t(nblocks),
-                                                                          c->outfirst.as<uint32_t>());
+    // per-launch tile table (pipelined callers pass disjoint slices of a buffer they reserved)
+    uint32_t* tile_seq = d_tile_scratch;
+    if(tile_seq == nullptr) {
+        MCG_TRY(c->outfirst.reserve((nblocks + 4) * sizeof(uint32_t)));
+        tile_seq = c->outfirst.as<uint32_t>();
+    }
+    cta_seq_kernel<<<unsigned((nblocks + 256) / 256), 256, 0, stream>>>(d_win_first, nseq, p.wpc, uint32_t(nblocks), win_lo, tile_seq);
     c->launches++;
-    p.cta_seq = c->outfirst.as<uint32_t>();
+    p.cta_seq = tile_seq;
 #define SK_LAUNCH(K16, PT)                                                                                        \
     do {                                                                                                          \
         auto kern = sketch_kernel<K16, PT>;                                                                       \
@@ -651,7 +662,7 @@ int sketch_launch(mcg_ctx* c, const mcg_sketch_cfg& cfg, int sketchlen, int64_t 
         MCG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, SK_THREADS, smem));                 \
         if(per_sm < 1) per_sm = 1;                                                                                \
         const uint64_t grid = std::min<uint64_t>((nblocks + SK_WARPS - 1) / SK_WARPS, uint64_t(kNumSMs) * uint64_t(per_sm));                   \
-        kern<<<unsigned(grid), SK_THREADS, smem, c->stream>>>(p);                                                 \
+        kern<<<unsigned(grid), SK_THREADS, smem, stream>>>(p);                                                 \
     } while(0)
     if(cfg.k == 16 && p.pitch == SK_PITCH_DEFAULT) SK_LAUNCH(true, SK_PITCH_DEFAULT);
     else if(cfg.k == 16)                           SK_LAUNCH(true, 0);
