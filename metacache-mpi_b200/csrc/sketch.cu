@@ -25,7 +25,7 @@ constexpr int SK_THREADS = 256;
 constexpr int SK_WARPS = SK_THREADS / 32;
 constexpr int SK_CBUF = 128;              // per-warp compaction buffer (hashes)
 constexpr uint32_t NOF = 0xFFFFFFFFu;
-constexpr int SK_PITCH_DEFAULT = 38;        // pitch of the default shape (k=16, winlen=128, stride=113)
+constexpr int SK_PITCH_DEFAULT = 42;        // pitch of the default shape (k=16, winlen=128, stride=113)
 
 struct SketchParams {
     const uint8_t* seq;
