@@ -1,0 +1,832 @@
+// metacache_b200 -- C++ host driver of the B200 build/query path (links libmcgpu.so through the
+// C-ABI of include/mcgpu.h only).  It keeps the reference's command line, shard files and
+// output format for that path:
+//
+//   metacache_b200 build <db> <fasta files / directories ...> [-gpus P] [-kmerlen 16]
+//       [-sketchlen 16] [-winlen 128] [-winstride winlen-k+1] [-max-locations-per-feature 254]
+//       [-remove-overpopulated-features] [-taxonomy dir]                  (mode_build.cpp:93-138)
+//   metacache_b200 query <db> <r1.fq> <r2.fq> -pairfiles [-gpus P] [-lowest rank] [-highest rank]
+//       [-hitmin n] [-hitdiff f] [-maxcand n] [-insertsize n] [-winlen n] [-winstride n]
+//       [-sketchlen n] [-out file] [-tophits] [-queryids] [-taxids|-taxids-only] [-lineage]
+//       [-mapped-only|-nomap] [-no-summary] [-no-query-params]            (query_options.cpp)
+//
+// `-gpus P` replaces `mpirun -np P`: the database has P shards (shard = target_id % P,
+// sketch_database.h:540), shard r is written to / read from `<db>.db_<r>` in the reference's own
+// binary format (sketch_database.h:858-999, hash_multimap.h:923-1029) and lives on GPU
+// r % device_count.  One host process drives all shards.
+//
+// What is host glue here and OUT OF SCOPE of the GPU path: option parsing,
+// FASTA/FASTQ reading, NCBI taxonomy files, text output.  They are written from the formats the
+// reference reads and writes, not from its code.
+#include <algorithm>
+#include <chrono>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <map>
+#include <set>
+#include <sstream>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include <dirent.h>
+#include <sys/stat.h>
+
+#include "../../include/mcgpu.h"
+
+namespace {
+
+// ------------------------------------------------------------------------------- utilities
+[[noreturn]] void die(const std::string& msg)
+{
+    std::cerr << "metacache_b200: " << msg << std::endl;
+    std::exit(1);
+}
+
+void check(int rc, const char* what)
+{
+    if(rc != MCG_OK) die(std::string(what) + ": " + mcg_last_error());
+}
+
+const char* const RANK_NAMES[22] = {"sequence", "form", "variety", "subspecies", "species", "subgenus", "genus",
+                                    "subtribe", "tribe", "subfamily", "family", "suborder", "order", "subclass",
+                                    "class", "subphylum", "phylum", "subkingdom", "kingdom", "domain", "root", "none"};
+
+// taxonomy.h:174-214 rank_from_name
+int rank_from_name(std::string n)
+{
+    std::transform(n.begin(), n.end(), n.begin(), ::tolower);
+    static const std::map<std::string, int> m = {
+        {"sequence", 0}, {"genome", 0}, {"form", 1}, {"forma", 1}, {"variety", 2}, {"varietas", 2}, {"subspecies", 3},
+        {"species", 4}, {"species group", 5}, {"species subgroup", 5}, {"subgenus", 5}, {"genus", 6}, {"subtribe", 7},
+        {"tribe", 8}, {"subfamily", 9}, {"family", 10}, {"superfamily", 11}, {"parvorder", 11}, {"infraorder", 11},
+        {"suborder", 11}, {"order", 12}, {"superorder", 13}, {"infraclass", 13}, {"subclass", 13}, {"class", 14},
+        {"superclass", 15}, {"subphylum", 15}, {"phylum", 16}, {"division", 16}, {"superphylum", 17}, {"subkingdom", 17},
+        {"kingdom", 18}, {"subdomain", 18}, {"superkingdom", 19}, {"domain", 19}, {"root", 20}};
+    auto it = m.find(n);
+    return it == m.end() ? 21 : it->second;
+}
+
+struct Args {
+    std::vector<std::string> pos;                 // positional arguments after the mode
+    std::map<std::string, std::string> opt;       // -name [value]
+    bool has(std::initializer_list<const char*> names) const
+    {
+        for(auto n : names) if(opt.count(n)) return true;
+        return false;
+    }
+    std::string get(std::initializer_list<const char*> names, const std::string& def) const
+    {
+        for(auto n : names) { auto it = opt.find(n); if(it != opt.end() && !it->second.empty()) return it->second; }
+        return def;
+    }
+    long long geti(std::initializer_list<const char*> names, long long def) const
+    {
+        const std::string s = get(names, "");
+        return s.empty() ? def : std::atoll(s.c_str());
+    }
+};
+
+Args parse_args(int argc, char** argv, int first)
+{
+    Args a;
+    for(int i = first; i < argc; ++i) {
+        std::string s = argv[i];
+        if(s.size() > 1 && s[0] == '-' && !(s[1] >= '0' && s[1] <= '9')) {
+            std::string name = s.substr(1);
+            std::string val;
+            if(i + 1 < argc && !(argv[i + 1][0] == '-' && !(argv[i + 1][1] >= '0' && argv[i + 1][1] <= '9') && argv[i + 1][1] != 0)) {
+                val = argv[i + 1];
+                // flags without value must not swallow the next positional argument
+                static const std::set<std::string> flags = {
+                    "pairfiles", "pair-files", "pairseq", "tophits", "top-hits", "queryids", "query-ids", "taxids",
+                    "taxid", "taxids-only", "taxidsonly", "lineage", "mapped-only", "mappedonly", "nomap", "no-map",
+                    "no-summary", "nosummary", "no-query-params", "noqueryparams", "remove-overpopulated-features",
+                    "silent", "verbose", "omit-ranks", "separate-cols"};
+                if(flags.count(name)) val.clear(); else ++i;
+            }
+            a.opt[name] = val;
+        } else {
+            a.pos.push_back(s);
+        }
+    }
+    return a;
+}
+
+std::string db_name(std::string n)            // args_handling.cpp:34-45
+{
+    if(n.find(".db") == std::string::npos) n += ".db";
+    return n;
+}
+
+template<class T> void wr(std::ostream& os, T x) { os.write(reinterpret_cast<const char*>(&x), sizeof(x)); }
+template<class T> void rd(std::istream& is, T& x) { is.read(reinterpret_cast<char*>(&x), sizeof(x)); }
+void wr_str(std::ostream& os, const std::string& s) { wr<uint64_t>(os, s.size()); os.write(s.data(), std::streamsize(s.size())); }
+void rd_str(std::istream& is, std::string& s)
+{
+    uint64_t n = 0; rd(is, n); s.assign(size_t(n), '\0');
+    if(n) is.read(&s[0], std::streamsize(n));
+}
+
+// ------------------------------------------------------------------------------- taxonomy
+struct Taxon {
+    int64_t id = 0, parent = 0;
+    uint8_t rank = 21;
+    std::string name = "--", file;
+    uint64_t index = 0, windows = 0;
+};
+
+struct Taxonomy {
+    std::map<int64_t, Taxon> taxa;                // ascending id, like the reference's std::set
+
+    // nodes.dmp / names.dmp / merged.dmp: taxonomy_io.cpp:57-180
+    void load(const std::string& dir)
+    {
+        std::map<int64_t, std::string> names;
+        {
+            std::ifstream is(dir + "/names.dmp");
+            std::string line;
+            while(std::getline(is, line)) {
+                std::vector<std::string> f = split_dmp(line);
+                if(f.size() >= 4 && f[3].find("scientific") != std::string::npos) names.emplace(std::atoll(f[0].c_str()), f[1]);
+            }
+        }
+        std::map<int64_t, int64_t> merged;
+        {
+            std::ifstream is(dir + "/merged.dmp");
+            std::string line;
+            while(std::getline(is, line)) {
+                std::vector<std::string> f = split_dmp(line);
+                if(f.size() >= 2) {
+                    const int64_t o = std::atoll(f[0].c_str()), n = std::atoll(f[1].c_str());
+                    merged[o] = n;
+                    Taxon t; t.id = o; t.parent = n; t.name = ""; t.rank = 21;
+                    taxa[o] = t;
+                }
+            }
+        }
+        std::ifstream is(dir + "/nodes.dmp");
+        if(!is.good()) die("could not read taxonomic nodes file " + dir + "/nodes.dmp");
+        std::string line;
+        while(std::getline(is, line)) {
+            std::vector<std::string> f = split_dmp(line);
+            if(f.size() < 3) continue;
+            int64_t id = std::atoll(f[0].c_str()), par = std::atoll(f[1].c_str());
+            auto nm = names.find(id);
+            std::string name = nm != names.end() ? nm->second : "--";
+            if(name.empty()) name = "<" + std::to_string(id) + ">";
+            auto mi = merged.find(id); if(mi != merged.end()) id = mi->second;
+            mi = merged.find(par); if(mi != merged.end()) par = mi->second;
+            if(id == 0) continue;
+            Taxon t; t.id = id; t.parent = par; t.name = name; t.rank = uint8_t(rank_from_name(f[2]));
+            if(!taxa.count(id)) taxa[id] = t;      // std::set::emplace keeps the first
+        }
+        auto r = taxa.find(1);
+        if(r != taxa.end()) r->second.rank = 20;   // root
+    }
+
+    static std::vector<std::string> split_dmp(const std::string& line)
+    {
+        std::vector<std::string> f;
+        size_t p = 0;
+        while(p <= line.size()) {
+            size_t q = line.find('|', p);
+            if(q == std::string::npos) q = line.size();
+            std::string x = line.substr(p, q - p);
+            size_t a = x.find_first_not_of(" \t"), b = x.find_last_not_of(" \t");
+            f.push_back(a == std::string::npos ? "" : x.substr(a, b - a + 1));
+            p = q + 1;
+        }
+        return f;
+    }
+};
+
+// flattened tables for mcg_tax_upload: index t < ntargets = target t, then the higher taxa
+struct TaxTables {
+    std::vector<int64_t> taxid;
+    std::vector<const Taxon*> tax;
+    std::vector<int32_t> lineage;
+    std::vector<uint8_t> rank;
+    int64_t ntargets = 0;
+    std::unordered_map<int64_t, int32_t> index_of;
+
+    void build(const Taxonomy& t, int64_t ntgt)
+    {
+        ntargets = ntgt;
+        taxid.clear(); tax.clear(); index_of.clear();
+        for(int64_t i = 0; i < ntgt; ++i) {
+            auto it = t.taxa.find(-i - 1);
+            if(it == t.taxa.end()) die("database lacks the sequence-level taxon of target " + std::to_string(i));
+            taxid.push_back(-i - 1); tax.push_back(&it->second);
+        }
+        for(auto& kv : t.taxa) if(kv.first >= 0) { taxid.push_back(kv.first); tax.push_back(&kv.second); }
+        for(size_t i = 0; i < taxid.size(); ++i) index_of[taxid[i]] = int32_t(i);
+        const size_t n = taxid.size();
+        rank.resize(n);
+        lineage.assign(n * 21, -1);
+        for(size_t i = 0; i < n; ++i) {
+            rank[i] = tax[i]->rank;
+            // taxonomy.h:576-597 ranks(): walk to the root, ranked taxa fill their slot, later overwrite
+            int64_t id = taxid[i];
+            size_t guard = 0;
+            while(id != 0 && guard++ <= n) {
+                auto it = index_of.find(id);
+                if(it == index_of.end()) break;
+                const Taxon* x = tax[it->second];
+                if(x->rank != 21) lineage[i * 21 + x->rank] = it->second;
+                if(x->parent == id) break;
+                id = x->parent;
+            }
+        }
+    }
+};
+
+// ------------------------------------------------------------------------------- sequence files
+struct Record { std::string header, data; };
+
+bool read_text_file(const std::string& path, std::string& out)
+{
+    std::ifstream is(path, std::ios::binary);
+    if(!is.good()) return false;
+    is.seekg(0, std::ios::end);
+    const std::streamoff n = is.tellg();
+    is.seekg(0);
+    out.resize(size_t(n));
+    if(n) is.read(&out[0], n);
+    return true;
+}
+
+// FASTA ('>') or FASTQ ('@'); sequence_io.cpp:121-170, 253-284.  Zero-length FASTA records and
+// everything after them in the file are dropped like in the reference (its reader throws there).
+void parse_sequences(const std::string& txt, std::vector<Record>& out)
+{
+    size_t p = 0;
+    const size_t n = txt.size();
+    auto line_end = [&](size_t s) { size_t e = txt.find('\n', s); return e == std::string::npos ? n : e; };
+    while(p < n && (txt[p] == '\n' || txt[p] == '\r')) ++p;
+    if(p >= n) return;
+    if(txt[p] == '>') {
+        while(p < n && txt[p] == '>') {
+            size_t e = line_end(p);
+            Record r;
+            r.header = txt.substr(p + 1, e - p - 1);
+            if(!r.header.empty() && r.header.back() == '\r') r.header.pop_back();
+            p = e + 1;
+            while(p < n && txt[p] != '>') {
+                e = line_end(p);
+                size_t len = e - p;
+                if(len && txt[p + len - 1] == '\r') --len;
+                r.data.append(txt, p, len);
+                p = e + 1;
+            }
+            if(r.data.empty()) return;
+            out.push_back(std::move(r));
+        }
+    } else if(txt[p] == '@') {
+        while(p < n && txt[p] == '@') {
+            size_t e = line_end(p);
+            Record r;
+            r.header = txt.substr(p + 1, e - p - 1);
+            if(!r.header.empty() && r.header.back() == '\r') r.header.pop_back();
+            p = e + 1;
+            if(p > n) break;
+            e = line_end(p);
+            r.data = txt.substr(p, e - p);
+            if(!r.data.empty() && r.data.back() == '\r') r.data.pop_back();
+            p = e + 1;
+            if(p >= n || txt[p] != '+') break;
+            p = line_end(p) + 1;               // quality header
+            p = line_end(p) + 1;               // qualities
+            out.push_back(std::move(r));
+        }
+    }
+}
+
+std::string trimmed(const std::string& s)
+{
+    size_t a = s.find_first_not_of(" \t\r\n"), b = s.find_last_not_of(" \t\r\n");
+    return a == std::string::npos ? "" : s.substr(a, b - a + 1);
+}
+
+// sequence id = NCBI-style accession (sequence_io.cpp:576-716): known prefix + version, plain
+// "name.version" at the start of the text, prefix without version, or gi number
+size_t end_of_accession(const std::string& t, size_t start)
+{
+    if(start >= t.size()) return t.size();
+    for(char c : {'|', ' ', '-', '_', ','}) { size_t k = t.find(c, start); if(k != std::string::npos) return k; }
+    return t.size();
+}
+
+std::string extract_accession(const std::string& text)
+{
+    static const char* const prefixes[] = {"GCF_", "AC_", "NC_", "NG_", "NS_", "NT_", "NW_", "NZ_", "MKHE", "AE", "AJ", "AL", "AM",
+        "AP", "AY", "BA", "BK", "BX", "CC", "CM", "CP", "CR", "CT", "CU", "FM", "FN", "FO", "FP", "FQ", "FR"};
+    if(text.size() < 2) return "";
+    for(auto p : prefixes) {
+        size_t i = text.find(p);
+        if(i == std::string::npos) continue;
+        size_t s = text.find('.', i + std::strlen(p));
+        if(s == std::string::npos || (s - i) > 25) continue;
+        return trimmed(text.substr(i, end_of_accession(text, s + 1) - i));
+    }
+    size_t s = text.find('.', 1);
+    if(s < 25) return trimmed(text.substr(0, end_of_accession(text, s + 1)));
+    for(auto p : prefixes) {
+        size_t i = text.find(p);
+        if(i == std::string::npos) continue;
+        size_t j = i + std::strlen(p), k = end_of_accession(text, j), l = text.find('.', j);
+        if(l < k) k = l;
+        return trimmed(text.substr(i, k - i));
+    }
+    size_t i = text.find("gi|");
+    if(i != std::string::npos) {
+        i += 3;
+        size_t j = text.find('|', i);
+        if(j == std::string::npos) { j = text.find(' ', i); if(j == std::string::npos) j = text.size(); }
+        return trimmed(text.substr(i, j - i));
+    }
+    return "";
+}
+
+int64_t extract_taxid(const std::string& text)          // sequence_io.cpp:724-748
+{
+    size_t i = text.find("taxid");
+    if(i == std::string::npos) return 0;
+    i += 6;
+    if(i >= text.size()) return 0;
+    size_t j = text.find('|', i);
+    if(j == std::string::npos) { j = text.find(' ', i); if(j == std::string::npos) j = text.size(); }
+    const std::string num = text.substr(i, j - i);
+    if(num.empty() || !(num[0] >= '0' && num[0] <= '9')) return 0;
+    return std::atoll(num.c_str());
+}
+
+void list_files(const std::string& path, std::vector<std::string>& out)
+{
+    struct stat st;
+    if(stat(path.c_str(), &st) != 0) return;
+    if(S_ISDIR(st.st_mode)) {
+        DIR* d = opendir(path.c_str());
+        if(!d) return;
+        std::vector<std::string> names;
+        while(dirent* e = readdir(d)) { std::string n = e->d_name; if(n != "." && n != "..") names.push_back(n); }
+        closedir(d);
+        for(auto& n : names) list_files(path + "/" + n, out);
+    } else {
+        out.push_back(path);
+    }
+}
+
+// ------------------------------------------------------------------------------- shard files
+struct DbMeta {
+    mcg_sketch_cfg tcfg{16, 16, 128, 113};
+    uint64_t qsketch = 16, qwinlen = 128, qstride = 113, maxlocs = 254;
+    Taxonomy tax;
+    uint32_t ntargets = 0;
+};
+
+void write_shard(const std::string& file, const DbMeta& m, mcg_db* db)
+{
+    uint64_t nk = 0, ne = 0, nl = 0;
+    check(mcg_db_counts(db, &nk, &ne, &nl), "mcg_db_counts");
+    std::vector<uint32_t> keys(ne ? ne : 1), sizes(ne ? ne : 1), tg(nl ? nl : 1), wn(nl ? nl : 1);
+    check(mcg_db_export(db, keys.data(), sizes.data(), tg.data(), wn.data()), "mcg_db_export");
+    std::ofstream os(file, std::ios::binary);
+    if(!os.good()) die("can't open file " + file);
+    wr<uint64_t>(os, 20181001);                                   // MC_DB_VERSION
+    wr<uint8_t>(os, 4); wr<uint8_t>(os, 4); wr<uint8_t>(os, 4); wr<uint8_t>(os, 1); wr<uint8_t>(os, 8); wr<uint8_t>(os, 21);
+    wr<uint64_t>(os, m.tcfg.k); wr<uint64_t>(os, m.tcfg.sketchlen); wr<uint64_t>(os, m.tcfg.winlen); wr<uint64_t>(os, m.tcfg.winstride);
+    wr<uint64_t>(os, m.tcfg.k); wr<uint64_t>(os, m.qsketch); wr<uint64_t>(os, m.qwinlen); wr<uint64_t>(os, m.qstride);
+    wr<uint64_t>(os, m.maxlocs);
+    wr<uint64_t>(os, m.tax.taxa.size());
+    for(auto& kv : m.tax.taxa) {
+        const Taxon& t = kv.second;
+        wr<int64_t>(os, t.id); wr<int64_t>(os, t.parent); wr<uint8_t>(os, t.rank);
+        wr_str(os, t.name); wr_str(os, t.file); wr<uint64_t>(os, t.index); wr<uint64_t>(os, t.windows);
+    }
+    wr<uint32_t>(os, m.ntargets);
+    wr<uint64_t>(os, ne); wr<uint64_t>(os, nl);
+    uint64_t lo = 0;
+    std::string buf;
+    buf.reserve(size_t(ne) * 21 + size_t(nl) * 8);
+    auto put = [&](const void* p, size_t n) { buf.append(static_cast<const char*>(p), n); };
+    for(uint64_t j = 0; j < ne; ++j) {
+        const uint32_t key = keys[j];
+        const uint8_t n8 = uint8_t(sizes[j]);
+        const uint64_t n = sizes[j];
+        put(&key, 4); put(&n8, 1);
+        put(&n, 8); put(&tg[lo], size_t(n) * 4);
+        put(&n, 8); put(&wn[lo], size_t(n) * 4);
+        lo += n;
+        if(buf.size() > (size_t(64) << 20)) { os.write(buf.data(), std::streamsize(buf.size())); buf.clear(); }
+    }
+    os.write(buf.data(), std::streamsize(buf.size()));
+}
+
+// returns the bucket arrays of a shard file written by this program or by the reference
+void read_shard(const std::string& file, DbMeta& m, bool meta_only,
+                std::vector<uint32_t>& keys, std::vector<uint32_t>& sizes, std::vector<uint32_t>& tg, std::vector<uint32_t>& wn)
+{
+    std::ifstream is(file, std::ios::binary);
+    if(!is.good()) die("can't open file " + file);
+    uint64_t ver = 0; rd(is, ver);
+    if(ver != 20181001) die("database " + file + " has incompatible version " + std::to_string(ver));
+    uint8_t w[6]; for(auto& x : w) rd(is, x);
+    if(w[0] != 4 || w[1] != 4 || w[2] != 4 || w[3] != 1 || w[4] != 8 || w[5] != 21) die("database " + file + " uses different data type sizes");
+    uint64_t k, s, wl, ws, qk;
+    rd(is, k); rd(is, s); rd(is, wl); rd(is, ws);
+    m.tcfg.k = int32_t(k); m.tcfg.sketchlen = int32_t(s); m.tcfg.winlen = int64_t(wl); m.tcfg.winstride = int64_t(ws);
+    rd(is, qk); rd(is, m.qsketch); rd(is, m.qwinlen); rd(is, m.qstride);
+    rd(is, m.maxlocs);
+    uint64_t nt = 0; rd(is, nt);
+    m.tax.taxa.clear();
+    for(uint64_t i = 0; i < nt; ++i) {
+        Taxon t;
+        rd(is, t.id); rd(is, t.parent); rd(is, t.rank); rd_str(is, t.name); rd_str(is, t.file); rd(is, t.index); rd(is, t.windows);
+        m.tax.taxa[t.id] = t;
+    }
+    rd(is, m.ntargets);
+    if(meta_only) return;
+    uint64_t nk = 0, nv = 0; rd(is, nk); rd(is, nv);
+    keys.resize(nk); sizes.resize(nk); tg.resize(nv); wn.resize(nv);
+    uint64_t lo = 0;
+    for(uint64_t j = 0; j < nk; ++j) {
+        uint8_t n8 = 0; rd(is, keys[j]); rd(is, n8);
+        sizes[j] = n8;
+        if(n8 > 0) {
+            uint64_t n = 0;
+            rd(is, n); is.read(reinterpret_cast<char*>(&tg[lo]), std::streamsize(n * 4));
+            rd(is, n); is.read(reinterpret_cast<char*>(&wn[lo]), std::streamsize(n * 4));
+            lo += n;
+        }
+    }
+    if(!is.good() || lo != nv) die("database " + file + " is truncated or corrupt");
+}
+
+std::vector<mcg_ctx*> g_ctx;        // one per device
+
+mcg_ctx* ctx_for_shard(int shard)
+{
+    const int ndev = mcg_device_count();
+    if(ndev < 1) die("no CUDA device available; there is no CPU fallback");
+    if(g_ctx.empty()) g_ctx.assign(size_t(ndev), nullptr);
+    const int d = shard % ndev;
+    if(!g_ctx[d]) check(mcg_ctx_create(d, nullptr, &g_ctx[d]), "mcg_ctx_create");
+    return g_ctx[d];
+}
+
+double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+// ------------------------------------------------------------------------------- build
+int mode_build(const Args& a)
+{
+    if(a.pos.size() < 2) die("usage: metacache_b200 build <database> <sequence files / directories ...> [options]");
+    const std::string dbfile = db_name(a.pos[0]);
+    int P = int(a.geti({"gpus", "np"}, std::max(1, mcg_device_count())));
+    if(P < 1) P = 1;
+    DbMeta m;
+    m.tcfg.k = int32_t(a.geti({"kmerlen"}, 16));
+    m.tcfg.sketchlen = int32_t(a.geti({"sketchlen"}, 16));
+    m.tcfg.winlen = a.geti({"winlen"}, 128);
+    m.tcfg.winstride = a.geti({"winstride"}, m.tcfg.winlen - m.tcfg.k + 1);       // mode_build.cpp:108-112
+    if(m.tcfg.winstride < 1) m.tcfg.winstride = 1;
+    m.qsketch = uint64_t(m.tcfg.sketchlen); m.qwinlen = uint64_t(m.tcfg.winlen); m.qstride = uint64_t(m.tcfg.winstride);
+    int maxlocs_arg = int(a.geti({"max-locations-per-feature", "max_locations_per_feature"}, 254));
+    {   // mode_build.cpp:659 narrows to the uint8 bucket size type
+        int v = int(uint8_t(maxlocs_arg));
+        if(v < 1) v = 1;
+        if(v > 254) v = 254;
+        m.maxlocs = uint64_t(v);
+    }
+    const bool remove_over = a.has({"remove-overpopulated-features"});
+    const std::string taxdir = a.get({"taxonomy"}, "");
+    if(!taxdir.empty()) m.tax.load(taxdir);
+
+    std::vector<std::string> files;
+    for(size_t i = 1; i < a.pos.size(); ++i) list_files(a.pos[i], files);
+    std::sort(files.begin(), files.end());                                     // mode_build.cpp:575
+    if(files.empty()) die("no sequence files found");
+
+    std::vector<mcg_db*> dbs(static_cast<size_t>(P), nullptr);
+    for(int r = 0; r < P; ++r) check(mcg_db_create(ctx_for_shard(r), &m.tcfg, maxlocs_arg, r, P, &dbs[size_t(r)]), "mcg_db_create");
+
+    const double t0 = now();
+    // per-shard batches of owned targets
+    struct Batch { std::string bytes; std::vector<int64_t> offs{0}; std::vector<uint32_t> ids; };
+    std::vector<Batch> batch(static_cast<size_t>(P));
+    std::vector<uint64_t> target_windows;
+    auto flush = [&](int r) {
+        Batch& b = batch[size_t(r)];
+        if(b.ids.empty()) return;
+        std::vector<uint32_t> wins(b.ids.size());
+        check(mcg_db_add_targets(dbs[size_t(r)], b.bytes.data(), b.offs.data(), b.ids.data(), int64_t(b.ids.size()), wins.data()),
+              "mcg_db_add_targets");
+        for(size_t i = 0; i < b.ids.size(); ++i) target_windows[b.ids[i]] = wins[i];
+        b.bytes.clear(); b.offs.assign(1, 0); b.ids.clear();
+    };
+    std::set<std::string> names;
+    uint32_t ntargets = 0;
+    uint64_t total_bp = 0;
+    std::string txt;
+    for(const auto& f : files) {
+        if(!read_text_file(f, txt)) continue;
+        std::vector<Record> recs;
+        parse_sequences(txt, recs);
+        uint64_t index = 0;
+        for(auto& rec : recs) {
+            ++index;
+            if(rec.data.empty()) continue;
+            std::string sid = extract_accession(rec.header);
+            if(sid.empty()) sid = rec.header;
+            if(names.count(sid)) continue;                                      // sketch_database.h:534
+            names.insert(sid);
+            int64_t parent = extract_taxid(rec.header);
+            if(parent < 1) parent = 0;
+            const uint32_t tgt = ntargets++;
+            const int r = int(tgt % uint32_t(P));
+            Taxon t;
+            t.id = -int64_t(tgt) - 1; t.parent = parent; t.rank = 0; t.name = sid; t.file = f; t.index = index; t.windows = 0;
+            m.tax.taxa[t.id] = t;
+            target_windows.push_back(0);
+            Batch& b = batch[size_t(r)];
+            b.bytes += rec.data;
+            b.offs.push_back(int64_t(b.bytes.size()));
+            b.ids.push_back(tgt);
+            total_bp += rec.data.size();
+            if(b.bytes.size() > (size_t(512) << 20)) flush(r);
+        }
+    }
+    for(int r = 0; r < P; ++r) flush(r);
+    m.ntargets = ntargets;
+    for(int r = 0; r < P; ++r) check(mcg_db_finalize(dbs[size_t(r)]), "mcg_db_finalize");
+    const double t1 = now();
+    std::cout << "Added " << ntargets << " reference sequences (" << total_bp << " bp) in " << (t1 - t0) << " s" << std::endl;
+    if(remove_over) {
+        uint64_t rem = 0;
+        check(mcg_remove_overpopulated(dbs.data(), P, &rem), "mcg_remove_overpopulated");
+        std::cout << rem << " overpopulated feature lists removed" << std::endl;
+    }
+    for(int r = 0; r < P; ++r) {
+        // source.windows is only known on the owning rank (sketch_database.h:541), 0 elsewhere
+        DbMeta mr = m;
+        for(uint32_t t = 0; t < ntargets; ++t) mr.tax.taxa[-int64_t(t) - 1].windows = (int(t % uint32_t(P)) == r) ? target_windows[t] : 0;
+        const std::string out = dbfile + "_" + std::to_string(r);
+        write_shard(out, mr, dbs[size_t(r)]);
+        uint64_t nk = 0, ne = 0, nl = 0;
+        mcg_db_counts(dbs[size_t(r)], &nk, &ne, &nl);
+        std::cout << "shard " << r << ": features " << ne << " dead " << (nk - ne) << " locations " << nl << " -> " << out << std::endl;
+        mcg_db_destroy(dbs[size_t(r)]);
+    }
+    std::cout << "Total build time: " << (now() - t0) << " s" << std::endl;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------- query
+struct OutOpt {
+    bool queryids = false, tophits = false, lineage = false, show_ranks = true, summary = true, params = true;
+    int mode = 0;               // 0 rank_name, 1 rank_id (taxids-only), 2 rank_name_id (taxids)
+    int map = 0;                // 0 all, 1 mapped only, 2 none
+    int lowest = 0, highest = 19;
+    std::string comment = "# ", none = "--", col = "\t|\t", taxsep = ",", ranksuf = ":", idpre = "(", idsuf = ")";
+};
+
+void show_one_taxon(std::ostream& os, const OutOpt& o, const Taxon* t)
+{
+    if(o.show_ranks) os << RANK_NAMES[t->rank] << o.ranksuf;
+    if(o.mode == 1) os << t->id;
+    else if(o.mode == 2) os << t->name << o.idpre << t->id << o.idsuf;
+    else os << t->name;
+}
+
+void show_no_taxon(std::ostream& os, const OutOpt& o, int r)
+{
+    if(o.show_ranks) os << RANK_NAMES[r] << o.ranksuf;
+    if(o.mode == 1) os << 0;
+    else if(o.mode == 2) os << o.none << o.idpre << 0 << o.idsuf;
+    else os << o.none;
+}
+
+// printing.cpp:305-330 show_taxon (collapseUnclassified = true)
+void show_classification(std::ostream& os, const OutOpt& o, const TaxTables& tt, int32_t best)
+{
+    if(best < 0 || tt.rank[size_t(best)] > o.highest) {
+        if(o.mode == 1) os << 0; else os << o.none;
+        return;
+    }
+    const int rmin = o.lowest < tt.rank[size_t(best)] ? tt.rank[size_t(best)] : o.lowest;
+    const int rmax = o.lineage ? o.highest : rmin;
+    for(int r = rmin; r <= rmax; ++r) {
+        const int32_t x = tt.lineage[size_t(best) * 21 + size_t(r)];
+        if(x >= 0) show_one_taxon(os, o, tt.tax[size_t(x)]); else show_no_taxon(os, o, r);
+        if(r < rmax) os << o.taxsep;
+    }
+}
+
+int mode_query(const Args& a)
+{
+    if(a.pos.size() < 2) die("usage: metacache_b200 query <database> <reads1> [<reads2> -pairfiles] [options]");
+    const std::string dbfile = db_name(a.pos[0]);
+    int P = int(a.geti({"gpus", "np"}, 0));
+    if(P < 1) { P = 0; struct stat st; while(stat((dbfile + "_" + std::to_string(P)).c_str(), &st) == 0) ++P; }
+    if(P < 1) die("no shard files " + dbfile + "_<r> found");
+    const bool paired = a.has({"pairfiles", "pair-files"}) && a.pos.size() >= 3;
+
+    // shards
+    std::vector<DbMeta> metas(static_cast<size_t>(P));
+    std::vector<mcg_db*> dbs(static_cast<size_t>(P), nullptr);
+    for(int r = 0; r < P; ++r) {
+        std::vector<uint32_t> keys, sizes, tg, wn;
+        read_shard(dbfile + "_" + std::to_string(r), metas[size_t(r)], false, keys, sizes, tg, wn);
+        const DbMeta& m = metas[size_t(r)];
+        check(mcg_db_create(ctx_for_shard(r), &m.tcfg, int(m.maxlocs), r, P, &dbs[size_t(r)]), "mcg_db_create");
+        check(mcg_db_import(dbs[size_t(r)], keys.data(), sizes.data(), tg.data(), wn.data(), keys.size(), tg.size()), "mcg_db_import");
+    }
+    const DbMeta& m0 = metas[0];
+    TaxTables tt;
+    tt.build(m0.tax, m0.ntargets);
+    for(mcg_ctx* c : g_ctx) if(c) check(mcg_tax_upload(c, tt.lineage.data(), tt.rank.data(), int64_t(tt.rank.size()), tt.ntargets), "mcg_tax_upload");
+
+    // options (query_options.cpp)
+    mcg_query_opts q{};
+    q.sketchlen = int32_t(a.geti({"sketchlen"}, int64_t(m0.qsketch)));
+    q.winlen = a.geti({"winlen"}, int64_t(m0.qwinlen));
+    q.winstride = a.has({"winstride"}) ? a.geti({"winstride"}, 0) : (a.has({"winlen"}) ? q.winlen : int64_t(m0.qstride));   // quirk Q9
+    q.lowest = 0; q.highest = 19;
+    { const std::string s = a.get({"lowest"}, ""); if(!s.empty()) { int r = rank_from_name(s); if(r < 21) q.lowest = r; } }
+    { const std::string s = a.get({"highest"}, ""); if(!s.empty()) { int r = rank_from_name(s); if(r <= 20) q.highest = r; } }
+    if(q.lowest > q.highest) q.lowest = q.highest;
+    q.insertsize = a.geti({"insertsize", "insert-size"}, 0);
+    q.hitmin = int32_t(a.geti({"hitmin"}, 0));
+    {
+        float f = float(std::atof(a.get({"hitdiff"}, "1").c_str()));
+        if(f > 1) f = float(double(f) * 0.01);                                  // query_options.cpp:167-169
+        q.hitdiff = f;
+    }
+    q.maxcand = int32_t(a.geti({"max-cand", "maxcand", "max_cand", "max-candidates", "maxcandidates"}, 2));
+    if(q.maxcand < 1 || q.maxcand > MCG_MAX_CAND) die("-maxcand must be 1.." + std::to_string(MCG_MAX_CAND) + " on the device");
+    if(q.hitmin < 1) {                                                          // mode_query.cpp:247-260
+        const int sks = m0.tcfg.sketchlen;
+        q.hitmin = sks >= 6 ? int(sks / 3.0) : (sks >= 4 ? 2 : 1);
+    }
+    OutOpt o;
+    o.queryids = a.has({"queryids", "query-ids", "queryid", "query-id"});
+    o.tophits = a.has({"tophits", "top-hits"});
+    o.lineage = a.has({"lineage"});
+    o.show_ranks = !a.has({"omit-ranks", "omitranks"});
+    if(a.has({"taxidsonly", "taxids-only", "taxidonly", "taxid-only"})) o.mode = 1;
+    else if(a.has({"taxids", "taxid"})) o.mode = 2;
+    if(a.has({"nomap", "no-map"})) o.map = 2; else if(a.has({"mapped-only", "mappedonly"})) o.map = 1;
+    if(o.map == 2 && o.tophits) o.map = 1;
+    o.summary = !a.has({"no-summary", "nosummary"});
+    o.params = !a.has({"no-query-params", "noqueryparams"});
+    o.lowest = q.lowest; o.highest = q.highest;
+
+    std::ofstream fout;
+    const std::string outname = a.get({"out"}, "");
+    if(!outname.empty()) {
+        fout.open(outname);
+        if(!fout.good()) die("Could not write to file " + outname);
+        std::cout << "Per-Read mappings will be written to file: " << outname << std::endl;
+    }
+    std::ostream& os = outname.empty() ? std::cout : fout;
+    const std::string& cm = o.comment;
+    if(o.params) {                                                              // printing.cpp:40-112
+        if(o.map != 2) {
+            os << cm << "Reporting per-read mappings (non-mapping lines start with '" << cm << "').\n";
+            os << cm << (o.lineage ? "The complete lineage will be reported starting with the lowest match.\n"
+                                   : "Only the lowest matching rank will be reported.\n");
+        } else {
+            os << cm << "Per-Read mappings will not be shown.\n";
+        }
+        os << cm << "Classification will be constrained to ranks from '" << RANK_NAMES[q.lowest] << "' to '" << RANK_NAMES[q.highest] << "'.\n";
+        os << cm << "Classification hit threshold is " << q.hitmin << " per query\n";
+        os << cm << "At maximum " << q.maxcand << " classification candidates will be considered per query.\n";
+        if(paired) {
+            os << cm << "File based paired-end mode:\n" << cm << "  Reads from two consecutive files will be interleaved.\n"
+               << cm << "  Max insert size considered " << q.insertsize << ".\n";
+        }
+        os << cm << "Using " << a.geti({"threads"}, 1) << " threads\n";
+    }
+    if(o.map != 2) {                                                            // classification.cpp:486-511
+        os << cm << "TABLE_LAYOUT: ";
+        if(o.queryids) os << "query_id" << o.col;
+        os << "query_header" << o.col;
+        if(o.tophits) os << "top_hits" << o.col;
+        const int rmax = o.lineage ? o.highest : o.lowest;
+        for(int r = o.lowest; r <= rmax; ++r) {
+            if(o.show_ranks) os << (o.lowest == rmax ? "rank" : RANK_NAMES[r]) << o.ranksuf;
+            if(o.mode == 1) os << "taxid"; else if(o.mode == 2) os << "taxname" << o.idpre << "taxid" << o.idsuf; else os << "taxname";
+            if(r < rmax) os << o.taxsep;
+        }
+        os << '\n';
+    }
+    os << cm << a.pos[1];
+    if(paired) os << " + " << a.pos[2];
+    os << '\n';
+
+    // reads
+    const double t0 = now();
+    std::vector<Record> r1, r2;
+    { std::string txt; if(!read_text_file(a.pos[1], txt)) die("can't open file " + a.pos[1]); parse_sequences(txt, r1); }
+    if(paired) { std::string txt; if(!read_text_file(a.pos[2], txt)) die("can't open file " + a.pos[2]); parse_sequences(txt, r2); }
+    const size_t nreads = paired ? std::min(r1.size(), r2.size()) : r1.size();
+    const int K = q.maxcand;
+    uint64_t stats[22] = {0};
+    const size_t BATCH = size_t(1) << 20;
+    std::string b1, b2;
+    std::vector<int64_t> o1, o2;
+    std::vector<int32_t> ctax, cn, mtax, mn, best, brank;
+    std::vector<uint32_t> chits, mhits;
+    for(size_t lo = 0; lo < nreads; lo += BATCH) {
+        const size_t n = std::min(BATCH, nreads - lo);
+        b1.clear(); b2.clear(); o1.assign(1, 0); o2.assign(1, 0);
+        for(size_t i = 0; i < n; ++i) {
+            b1 += r1[lo + i].data; o1.push_back(int64_t(b1.size()));
+            if(paired) { b2 += r2[lo + i].data; o2.push_back(int64_t(b2.size())); }
+        }
+        ctax.resize(size_t(P) * n * K); chits.resize(size_t(P) * n * K); cn.resize(size_t(P) * n);
+        for(int r = 0; r < P; ++r) {
+            check(mcg_query_batch(dbs[size_t(r)], &q, b1.data(), o1.data(), paired ? b2.data() : nullptr, paired ? o2.data() : nullptr,
+                                  int64_t(n), ctax.data() + size_t(r) * n * K, chits.data() + size_t(r) * n * K, cn.data() + size_t(r) * n),
+                  "mcg_query_batch");
+        }
+        mtax.resize(n * K); mhits.resize(n * K); mn.resize(n); best.resize(n); brank.resize(n);
+        check(mcg_merge_classify(ctx_for_shard(0), &q, ctax.data(), chits.data(), cn.data(), P, int64_t(n), mtax.data(), mhits.data(),
+                                 mn.data(), best.data(), brank.data(), stats), "mcg_merge_classify");
+        if(o.map == 2) continue;
+        std::string line;
+        for(size_t i = 0; i < n; ++i) {
+            if(o.map == 1 && best[i] < 0) continue;
+            std::ostringstream ls;
+            if(o.queryids) ls << (lo + i + 1) << o.col;
+            const std::string& h = r1[lo + i].header;
+            ls << h.substr(0, h.find(' ')) << o.col;
+            if(o.tophits) {                                                     // printing.cpp:333-360
+                for(int c = 0; c < mn[i] && mhits[i * K + c] > 0; ++c) {
+                    if(c > 0) ls << ',';
+                    const int32_t tx = mtax[i * K + c];
+                    const Taxon* t = tt.tax[size_t(tx)];
+                    if(q.lowest == 0) ls << t->name;
+                    else {
+                        const int32_t an = (t->rank < q.lowest) ? tt.lineage[size_t(tx) * 21 + size_t(q.lowest)] : tx;
+                        if(an >= 0) ls << tt.taxid[size_t(an)]; else ls << t->name;
+                    }
+                    ls << ':' << mhits[i * K + c];
+                }
+                ls << o.col;
+            }
+            show_classification(ls, o, tt, best[i]);
+            ls << '\n';
+            os << ls.str();
+        }
+    }
+    const double t1 = now();
+    if(o.summary) {                                                             // printing.cpp:522-641
+        const uint64_t total = stats[20] + stats[21];
+        const uint64_t nq = paired ? 2 * total : total;
+        const double minutes = (t1 - t0) / 60.0;
+        os << cm << "queries: " << nq << '\n' << cm << "time:    " << int64_t((t1 - t0) * 1000) << " ms\n"
+           << cm << "speed:   " << (double(nq) / minutes) << " queries/min\n";
+        if(total > 0) {
+            if(stats[20] < 1) os << "None of the input sequences could be classified.\n";
+            else {
+                if(stats[21] > 0) os << cm << "unclassified: " << (100 * (double(stats[21]) / double(total))) << "% (" << stats[21] << ")\n";
+                os << cm << "classified:\n";
+                const int ranks[] = {0, 3, 4, 6, 10, 12, 14, 16, 18, 19, 20};
+                for(int r : ranks) {
+                    if(stats[r] > 0) {
+                        std::string rn = RANK_NAMES[r];
+                        rn.resize(11, ' ');
+                        os << cm << "  " << rn << (100 * (double(stats[r]) / double(total))) << "% (" << stats[r] << ")\n";
+                    }
+                }
+            }
+        } else {
+            std::cerr << cm << "No valid query sequences found.\n";
+        }
+    }
+    for(mcg_db* d : dbs) mcg_db_destroy(d);
+    return 0;
+}
+
+}  // namespace
+
+int main(int argc, char** argv)
+{
+    if(argc < 2) {
+        std::cerr << "usage: metacache_b200 build|query ... (see the header of host/metacache_b200.cpp)" << std::endl;
+        return 1;
+    }
+    const std::string mode = argv[1];
+    const Args a = parse_args(argc, argv, 2);
+    int rc = 1;
+    if(mode == "build") rc = mode_build(a);
+    else if(mode == "query") rc = mode_query(a);
+    else die("unknown mode '" + mode + "' (build and query are implemented, like in the reference: README.md:37)");
+    for(mcg_ctx* c : g_ctx) if(c) mcg_ctx_destroy(c);
+    return rc;
+}

@@ -1,0 +1,144 @@
+"""Drop-in check of the C++ host driver (metacache-mpi_b200/metacache_b200) against the REAL
+reference binary (oracle/_ref/metacache_mpi_ref under the MPI shim) on the same files:
+  * shard files `<db>.db_<r>`: same header, taxonomy records and bucket contents; each side can
+    load the other's shards and produces the same query output;
+  * query output (`-tophits -queryids`): identical per-read lines, TABLE_LAYOUT, parameter header
+    and classification summary (only the time / speed lines differ).
+Without oracle/_ref the committed golden output of the reference is used."""
+import os
+import struct
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from metacache_mpi_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "metacache-mpi_b200", "metacache_b200")
+REF = os.path.join(ROOT, "oracle", "_ref", "metacache_mpi_ref")
+SHIM = os.path.join(ROOT, "oracle", "mpirun_shim.py")
+GOLDEN = os.path.join(ROOT, "tests", "golden", "cli_np2_species_maxcand4.txt")
+QFLAGS = ["-pairfiles", "-lowest", "species", "-maxcand", "4", "-hitmin", "4", "-hitdiff", "80", "-tophits", "-queryids"]
+
+
+def make_files(d):
+    G, L = 6, 30000
+    genomes = synth.make_genomes(G, L)
+    ids, par, rk, species = synth.make_taxonomy(G)
+    synth.write_genome_files(os.path.join(d, "genomes"), genomes, species)
+    synth.write_taxonomy_files(os.path.join(d, "tax"), ids, par, rk)
+    b1, o1, b2, o2, t = synth.make_read_pairs(genomes, 300, seed=5)
+    synth.write_fastq_pair(os.path.join(d, "r1.fq"), os.path.join(d, "r2.fq"), b1, o1, b2, o2, t)
+
+
+def parse_shard(path):
+    d = open(path, "rb").read()
+    o = 0
+
+    def rd(fmt):
+        nonlocal o
+        v = struct.unpack_from("<" + fmt, d, o)
+        o += struct.calcsize("<" + fmt)
+        return v
+
+    def rds():
+        nonlocal o
+        n, = rd("Q")
+        s = d[o:o + n]
+        o += n
+        return s
+
+    head = rd("Q") + rd("6B") + rd("QQQQ") + rd("QQQQ") + rd("Q")
+    nt, = rd("Q")
+    taxa = []
+    for _ in range(nt):
+        tid, par, rank = rd("qqB")
+        name, fn = rds(), rds()
+        idx, win = rd("QQ")
+        taxa.append((tid, par, rank, name, os.path.basename(fn), idx, win))
+    ntgt, = rd("I")
+    nk, nv = rd("QQ")
+    buckets = {}
+    for _ in range(nk):
+        key, n = rd("IB")
+        n1, = rd("Q")
+        tg = rd("%dI" % n1)
+        n2, = rd("Q")
+        wn = rd("%dI" % n2)
+        assert n == n1 == n2
+        buckets[key] = (tg, wn)
+    assert o == len(d), "trailing bytes in shard file"
+    return head, taxa, ntgt, nv, buckets
+
+
+def stable_lines(path):
+    out = []
+    for l in open(path).read().splitlines():
+        if l.startswith("# time:") or l.startswith("# speed:"):
+            continue
+        out.append(l)
+    return out
+
+
+def run(cmd, cwd):
+    r = subprocess.run(cmd, cwd=cwd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=600)
+    assert r.returncode == 0, r.stdout.decode()[-2000:]
+    return r.stdout.decode()
+
+
+def test_cli_build_query_dropin(tmp_path):
+    d = str(tmp_path)
+    make_files(d)
+    assert os.path.exists(EXE), "host driver not built (python __graft_entry__.py)"
+    run([EXE, "build", "gdb", "genomes", "-taxonomy", "tax", "-gpus", "2"], d)
+    run([EXE, "query", "gdb", "r1.fq", "r2.fq"] + QFLAGS + ["-out", "res_gpu.txt"], d)
+    mine = stable_lines(os.path.join(d, "res_gpu.txt"))
+    if os.path.exists(GOLDEN):
+        assert mine == open(GOLDEN).read().splitlines()
+    if not os.path.exists(REF):
+        assert os.path.exists(GOLDEN), "neither oracle/_ref nor the golden output is available"
+        return
+    # the reference itself, np = 2
+    run([sys.executable, SHIM, "-np", "2", "--", REF, "build", "rdb", "genomes", "-taxonomy", "tax"], d)
+    run([sys.executable, SHIM, "-np", "2", "--", REF, "query", "rdb", "r1.fq", "r2.fq"] + QFLAGS +
+        ["-threads", "1", "-query-limit", "300", "-out", "res_ref.txt"], d)
+    ref = stable_lines(os.path.join(d, "res_ref.txt"))
+    assert mine == ref
+    # shard files: same content
+    for r in range(2):
+        a = parse_shard(os.path.join(d, "gdb.db_%d" % r))
+        b = parse_shard(os.path.join(d, "rdb.db_%d" % r))
+        assert a[0] == b[0] and a[1] == b[1] and a[2] == b[2] and a[3] == b[3]
+        assert a[4] == b[4]
+    # cross-loading: the reference reads GPU-built shards, the GPU driver reads reference-built shards
+    run([sys.executable, SHIM, "-np", "2", "--", REF, "query", "gdb", "r1.fq", "r2.fq"] + QFLAGS +
+        ["-threads", "1", "-query-limit", "300", "-out", "res_ref_on_gpu_db.txt"], d)
+    assert stable_lines(os.path.join(d, "res_ref_on_gpu_db.txt")) == ref
+    run([EXE, "query", "rdb", "r1.fq", "r2.fq"] + QFLAGS + ["-out", "res_gpu_on_ref_db.txt"], d)
+    assert stable_lines(os.path.join(d, "res_gpu_on_ref_db.txt")) == ref
+
+
+def test_cli_defaults_and_overpopulated(tmp_path):
+    """reference defaults (-maxcand 2, hitmin 5, hitdiff 1.0) at -lowest genus with lineage + taxids,
+    and a capped database with -remove-overpopulated-features"""
+    d = str(tmp_path)
+    make_files(d)
+    run([EXE, "build", "gdb", "genomes", "-taxonomy", "tax", "-gpus", "2", "-max-locations-per-feature", "2",
+         "-remove-overpopulated-features"], d)
+    flags = ["-pairfiles", "-lowest", "genus", "-tophits", "-queryids", "-lineage", "-taxids"]
+    run([EXE, "query", "gdb", "r1.fq", "r2.fq"] + flags + ["-out", "res_gpu.txt"], d)
+    if not os.path.exists(REF):
+        return
+    run([sys.executable, SHIM, "-np", "2", "--", REF, "build", "rdb", "genomes", "-taxonomy", "tax",
+         "-max-locations-per-feature", "2", "-remove-overpopulated-features"], d)
+    run([sys.executable, SHIM, "-np", "2", "--", REF, "query", "rdb", "r1.fq", "r2.fq"] + flags +
+        ["-threads", "1", "-query-limit", "300", "-out", "res_ref.txt"], d)
+    assert stable_lines(os.path.join(d, "res_gpu.txt")) == stable_lines(os.path.join(d, "res_ref.txt"))
+    for r in range(2):
+        a = parse_shard(os.path.join(d, "gdb.db_%d" % r))
+        b = parse_shard(os.path.join(d, "rdb.db_%d" % r))
+        assert a[4] == b[4] and a[3] == b[3]
