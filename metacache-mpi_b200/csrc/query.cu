@@ -88,12 +88,22 @@ __global__ void q_bin_reads_kernel(const uint64_t* fpos, const uint32_t* W, int 
                                    int32_t* out_n)
 {
     const int64_t r = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
-    if(r >= n) return;
-    const uint64_t m = fpos[uint64_t(W[r + 1]) * s] - fpos[uint64_t(W[r]) * s];
-    if(m == 0) { out_n[r] = 0; return; }
-    const int cls = m <= Q_SMALL ? 0 : (m <= Q_MED ? 1 : (m <= Q_LARGE ? 2 : 3));
-    const uint32_t p = atomicAdd(&counters[cls], 1u);
-    lists[uint64_t(cls) * n + p] = uint32_t(r);
+    int cls = 4;                                          // 4 = nothing to do
+    if(r < n) {
+        const uint64_t m = fpos[uint64_t(W[r + 1]) * s] - fpos[uint64_t(W[r]) * s];
+        if(m == 0) out_n[r] = 0;
+        else cls = m <= Q_SMALL ? 0 : (m <= Q_MED ? 1 : (m <= Q_LARGE ? 2 : 3));
+    }
+    // one atomic per class per warp
+    const int lane = threadIdx.x & 31;
+    const uint32_t peers = __match_any_sync(0xFFFFFFFFu, cls);
+    if(cls < 4) {
+        const int leader = __ffs(peers) - 1;
+        uint32_t base = 0;
+        if(lane == leader) base = atomicAdd(&counters[cls], uint32_t(__popc(peers)));
+        base = __shfl_sync(peers, base, leader);
+        lists[uint64_t(cls) * n + base + __popc(peers & ((1u << lane) - 1u))] = uint32_t(r);
+    }
 }
 
 // ------------------------------------------------------------------ gather
@@ -198,23 +208,24 @@ __device__ __forceinline__ void gsync()
 template<bool WARP>
 __device__ __forceinline__ void bitonic_sort(uint64_t* A, uint32_t m, int tid, int nt)
 {
-    uint32_t P = 1;
-    while(P < m) P <<= 1;
-    const uint32_t half = P >> 1;
-    for(uint32_t k = 2; k <= P; k <<= 1) {
-        const uint32_t hk = k >> 1;
+    if(m < 2) return;
+    const uint32_t lgP = 32u - uint32_t(__clz(int(m - 1)));      // P = 2^lgP >= m
+    const uint32_t half = 1u << (lgP - 1);
+    for(uint32_t lk = 1; lk <= lgP; ++lk) {                       // merge size k = 2^lk
+        const uint32_t k = 1u << lk, hk = k >> 1;
         for(uint32_t t = tid; t < half; t += nt) {
-            const uint32_t blk = t / hk, o = t % hk;
-            const uint32_t lo = blk * k + o, hi = blk * k + k - 1 - o;
+            const uint32_t blk = t >> (lk - 1), o = t & (hk - 1);
+            const uint32_t lo = (blk << lk) + o, hi = (blk << lk) + k - 1 - o;
             if(hi < m) {
                 const uint64_t a = A[lo], b = A[hi];
                 if(a > b) { A[lo] = b; A[hi] = a; }
             }
         }
         gsync<WARP>();
-        for(uint32_t j = hk >> 1; j > 0; j >>= 1) {
+        for(uint32_t lj = lk - 1; lj-- > 0;) {                    // j = 2^lj
+            const uint32_t j = 1u << lj;
             for(uint32_t t = tid; t < half; t += nt) {
-                const uint32_t lo = (t / j) * (j << 1) + (t % j), hi = lo + j;
+                const uint32_t lo = ((t >> lj) << (lj + 1)) + (t & (j - 1)), hi = lo + j;
                 if(hi < m) {
                     const uint64_t a = A[lo], b = A[hi];
                     if(a > b) { A[lo] = b; A[hi] = a; }
