@@ -267,6 +267,12 @@ int db_finalize(mcg_db* db)
     MCG_CUDA(cudaStreamSynchronize(c->stream));
     db->feat.release();
     c->tmp0.release(); c->tmp1.release(); c->tmp2.release();
+    {
+        uint64_t maxwin = 0;
+        for(size_t t = 0; t + 1 < db->h_tgt_firstwin.size(); ++t) maxwin = std::max<uint64_t>(maxwin, db->h_tgt_firstwin[t + 1] - db->h_tgt_firstwin[t]);
+        db->set_key_layout(db->h_tgt_id.empty() ? 0 : db->h_tgt_id.back(), maxwin);
+        if(getenv("MCG_FORCE_KEY64")) { db->wbits = 32; db->key32 = false; }
+    }
     db->finalized = true;
     return MCG_OK;
 }
@@ -493,7 +499,10 @@ int mcg_db_import(mcg_db* db, const uint32_t* keys, const uint32_t* sizes,
     if(!std::is_sorted(keys, keys + nkeys))
         std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return keys[a] < keys[b]; });
     std::vector<uint32_t> k(nkeys); std::vector<uint8_t> sz(nkeys); std::vector<uint64_t> of(nkeys + 1, 0), locs(nlocs);
-    uint64_t lo = 0;
+    uint64_t lo = 0, max_tgt = 0, max_win = 0;
+    for(uint64_t i = 0; i < nlocs; ++i) { max_tgt = std::max<uint64_t>(max_tgt, tgts[i]); max_win = std::max<uint64_t>(max_win, wins[i]); }
+    db->set_key_layout(max_tgt, max_win);
+    if(getenv("MCG_FORCE_KEY64")) { db->wbits = 32; db->key32 = false; }
     for(uint64_t j = 0; j < nkeys; ++j) {
         const uint32_t o = order[j];
         if(j > 0) MCG_REQUIRE(keys[o] != k[j - 1], "duplicate key %u", keys[o]);

@@ -93,6 +93,16 @@ struct mcg_db {
     mcg::DevBuf locs;                 // uint64 (tgt << 32 | win)
     mcg::DevBuf table;                // uint4 slots {key, size, off_lo, off_hi}
     uint64_t nkeys = 0, nlocs = 0, table_cap = 0;
+    // per-read match keys: (tgt << wbits) | win; 32-bit when target and window ids fit together
+    int wbits = 32;
+    bool key32 = false;
+    void set_key_layout(uint64_t max_tgt, uint64_t max_win)
+    {
+        int wb = 1, tb = 1;
+        while((max_win >> wb) != 0) ++wb;
+        while((max_tgt >> tb) != 0) ++tb;
+        if(wb + tb <= 32) { wbits = wb; key32 = true; } else { wbits = 32; key32 = false; }
+    }
 };
 
 namespace mcg {

@@ -107,9 +107,16 @@ __global__ void q_bin_reads_kernel(const uint64_t* fpos, const uint32_t* W, int 
 }
 
 // ------------------------------------------------------------------ gather
+template<class KeyT>
+__device__ __forceinline__ KeyT make_key(uint64_t loc, int wbits)
+{
+    return KeyT((KeyT(loc >> 32) << wbits) | KeyT(uint32_t(loc)));
+}
+
+template<class KeyT>
 __global__ void __launch_bounds__(256)
 q_gather_kernel(const uint8_t* __restrict__ flen, const uint64_t* __restrict__ foff, const uint64_t* __restrict__ fpos,
-                uint64_t nslots, const uint64_t* __restrict__ locs, uint64_t* __restrict__ out)
+                uint64_t nslots, const uint64_t* __restrict__ locs, KeyT* __restrict__ out, int wbits)
 {
     const int lane = threadIdx.x & 31;
     const uint64_t slot = (blockIdx.x * uint64_t(blockDim.x) + threadIdx.x);
@@ -120,8 +127,8 @@ q_gather_kernel(const uint8_t* __restrict__ flen, const uint64_t* __restrict__ f
         if(len) { off = foff[slot]; pos = fpos[slot]; }
     }
     if(len > 0 && len <= 2) {
-        out[pos] = locs[off];
-        if(len == 2) out[pos + 1] = locs[off + 1];
+        out[pos] = make_key<KeyT>(locs[off], wbits);
+        if(len == 2) out[pos + 1] = make_key<KeyT>(locs[off + 1], wbits);
     }
     uint32_t big = __ballot_sync(0xFFFFFFFFu, len > 2);
     while(big) {
@@ -130,7 +137,7 @@ q_gather_kernel(const uint8_t* __restrict__ flen, const uint64_t* __restrict__ f
         const uint32_t L = __shfl_sync(0xFFFFFFFFu, len, src);
         const uint64_t O = __shfl_sync(0xFFFFFFFFu, off, src);
         const uint64_t P = __shfl_sync(0xFFFFFFFFu, pos, src);
-        for(uint32_t t = lane; t < L; t += 32) out[P + t] = locs[O + t];
+        for(uint32_t t = lane; t < L; t += 32) out[P + t] = make_key<KeyT>(locs[O + t], wbits);
     }
 }
 
@@ -175,6 +182,9 @@ __device__ __forceinline__ void topk_insert(TopK& L, int K, int32_t tax, uint32_
 }
 
 // ------------------------------------------------------------------ K4 + K5
+// Match keys: (tgt << wbits) | win.  When target and window ids of the shard fit 32 bits together
+// (e.g. 5000 targets x 35k windows) the whole per-read stage runs on 32-bit keys, which halves the
+// sorting work and the gathered bytes; otherwise wbits = 32 and keys are the stored 64-bit locations.
 struct CandParams {
     const uint64_t* fpos;
     const uint32_t* W;
@@ -183,7 +193,8 @@ struct CandParams {
     const int64_t* offs2;
     int64_t insertsize;
     int64_t tstride;
-    uint64_t* loc;
+    void* loc;
+    int wbits;
     uint32_t* hits_scratch;      // only for the global-memory class
     const uint32_t* list;
     const uint32_t* list_count;
@@ -203,10 +214,47 @@ __device__ __forceinline__ void gsync()
     if(WARP) __syncwarp(); else __syncthreads();
 }
 
+template<class KeyT> __device__ __forceinline__ uint32_t tgt_of(KeyT k, int wbits) { return uint32_t(k >> wbits); }
+
+// window-range width of a read (classification.cpp:217-219)
+__device__ __forceinline__ uint32_t num_windows_in_range(const CandParams& p, uint32_t r)
+{
+    int64_t span = p.offs1[r + 1] - p.offs1[r];
+    if(p.offs2) span += p.offs2[r + 1] - p.offs2[r];
+    if(p.insertsize > span) span = p.insertsize;
+    return uint32_t(2 + span / p.tstride);
+}
+
+// hits of the best window range ENDING at element i (candidates.h:141-152): number of
+// elements of the same target with win > win_i - numwin, found by binary search in [0, i]
+template<class KeyT>
+__device__ __forceinline__ uint32_t hits_ending_at(const KeyT* A, uint32_t i, uint32_t numwin, int wbits)
+{
+    const KeyT key = A[i];
+    const KeyT wmask = (KeyT(1) << wbits) - 1;
+    const KeyT win = key & wmask;
+    const KeyT lowkey = (key & ~wmask) | (win >= KeyT(numwin - 1) ? win - KeyT(numwin - 1) : KeyT(0));
+    uint32_t lo = 0, hi = i;
+    while(lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if(A[mid] < lowkey) lo = mid + 1; else hi = mid;
+    }
+    return i - lo + 1;
+}
+
+__device__ __forceinline__ void write_toplist(const CandParams& p, uint32_t r, const TopK& L)
+{
+    for(int c = 0; c < p.K; ++c) {
+        p.out_tax[uint64_t(r) * p.K + c] = c < L.n ? L.tax[c] : -1;
+        p.out_hits[uint64_t(r) * p.K + c] = c < L.n ? L.hits[c] : 0u;
+    }
+    p.out_n[r] = L.n;
+}
+
 // ascending bitonic network in the "flip" formulation: every comparator is (lo < hi,
 // ascending), so elements beyond m behave as +infinity without being stored
-template<bool WARP>
-__device__ __forceinline__ void bitonic_sort(uint64_t* A, uint32_t m, int tid, int nt)
+template<bool WARP, class KeyT>
+__device__ __forceinline__ void bitonic_sort(KeyT* A, uint32_t m, int tid, int nt)
 {
     if(m < 2) return;
     const uint32_t lgP = 32u - uint32_t(__clz(int(m - 1)));      // P = 2^lgP >= m
@@ -217,7 +265,7 @@ __device__ __forceinline__ void bitonic_sort(uint64_t* A, uint32_t m, int tid, i
             const uint32_t blk = t >> (lk - 1), o = t & (hk - 1);
             const uint32_t lo = (blk << lk) + o, hi = (blk << lk) + k - 1 - o;
             if(hi < m) {
-                const uint64_t a = A[lo], b = A[hi];
+                const KeyT a = A[lo], b = A[hi];
                 if(a > b) { A[lo] = b; A[hi] = a; }
             }
         }
@@ -227,7 +275,7 @@ __device__ __forceinline__ void bitonic_sort(uint64_t* A, uint32_t m, int tid, i
             for(uint32_t t = tid; t < half; t += nt) {
                 const uint32_t lo = ((t >> lj) << (lj + 1)) + (t & (j - 1)), hi = lo + j;
                 if(hi < m) {
-                    const uint64_t a = A[lo], b = A[hi];
+                    const KeyT a = A[lo], b = A[hi];
                     if(a > b) { A[lo] = b; A[hi] = a; }
                 }
             }
@@ -236,96 +284,180 @@ __device__ __forceinline__ void bitonic_sort(uint64_t* A, uint32_t m, int tid, i
     }
 }
 
-// one read: A = its matches (shared or global memory), Hh = scratch of m uint32
-template<bool WARP>
-__device__ __forceinline__ void process_read(const CandParams& p, uint32_t r, uint64_t* A, uint32_t* Hh, uint32_t m,
-                                             uint64_t* gsrc, bool staged, int tid, int nt)
+// ---- register sorting networks of one warp (flip formulation, ascending)
+template<class KeyT>
+__device__ __forceinline__ KeyT wsort32(KeyT v, int lane)
+{
+#pragma unroll
+    for(int k = 2; k <= 32; k <<= 1) {
+        {
+            const KeyT o = __shfl_xor_sync(0xFFFFFFFFu, v, k - 1);
+            v = (lane & (k >> 1)) ? max(v, o) : min(v, o);
+        }
+#pragma unroll
+        for(int j = k >> 2; j > 0; j >>= 1) {
+            const KeyT o = __shfl_xor_sync(0xFFFFFFFFu, v, j);
+            v = (lane & j) ? max(v, o) : min(v, o);
+        }
+    }
+    return v;
+}
+
+// 64 keys: element e = lane (a) and lane + 32 (b)
+template<class KeyT>
+__device__ __forceinline__ void wsort64(KeyT& a, KeyT& b, int lane)
+{
+    a = wsort32(a, lane);
+    b = wsort32(b, lane);
+    // merge of size 64: flip step pairs e with 63 - e, i.e. a of lane L with b of lane 31 - L
+    {
+        const KeyT ob = __shfl_sync(0xFFFFFFFFu, b, 31 - lane);
+        const KeyT oa = __shfl_sync(0xFFFFFFFFu, a, 31 - lane);
+        a = min(a, ob);
+        b = max(b, oa);
+    }
+    // distance 32 is inside the flip step's halves already sorted apart; remaining distances < 32
+#pragma unroll
+    for(int j = 16; j > 0; j >>= 1) {
+        const KeyT oa = __shfl_xor_sync(0xFFFFFFFFu, a, j);
+        const KeyT ob = __shfl_xor_sync(0xFFFFFFFFu, b, j);
+        a = (lane & j) ? max(a, oa) : min(a, oa);
+        b = (lane & j) ? max(b, ob) : min(b, ob);
+    }
+}
+
+// one read handled by one warp (<= Q_SMALL matches)
+template<class KeyT>
+__device__ __forceinline__ void process_read_warp(const CandParams& p, uint32_t r, KeyT* A, uint32_t* Hh, uint32_t m,
+                                                  KeyT* gsrc, int lane)
+{
+    const KeyT KMAX = ~KeyT(0);
+    if(m <= 32) {
+        KeyT a = lane < int(m) ? gsrc[lane] : KMAX;
+        a = wsort32(a, lane);
+        A[lane] = a;
+    } else if(m <= 64) {
+        KeyT a = gsrc[lane];
+        KeyT b = lane + 32 < int(m) ? gsrc[lane + 32] : KMAX;
+        wsort64(a, b, lane);
+        A[lane] = a;
+        A[lane + 32] = b;
+    } else {
+        for(uint32_t i = lane; i < m; i += 32) A[i] = gsrc[i];
+        __syncwarp();
+        bitonic_sort<true>(A, m, lane, 32);
+    }
+    __syncwarp();
+    if(p.write_sorted) for(uint32_t i = lane; i < m; i += 32) gsrc[i] = A[i];
+    const uint32_t numwin = num_windows_in_range(p, r);
+    for(uint32_t i = lane; i < m; i += 32) Hh[i] = hits_ending_at(A, i, numwin, p.wbits);
+    __syncwarp();
+    // walk the target runs (ascending target = insertion order of candidates.h:207-219)
+    TopK L;
+    L.n = 0;
+    uint32_t i = 0;
+    while(i < m) {
+        const uint32_t tgt = tgt_of(A[i], p.wbits);
+        uint32_t e = i;
+        for(;;) {                                    // end of the run, 32 elements per probe
+            const uint32_t idx = e + lane;
+            const bool same = idx < m && tgt_of(A[idx], p.wbits) == tgt;
+            const uint32_t b = __ballot_sync(0xFFFFFFFFu, same);
+            if(b == 0xFFFFFFFFu) { e += 32; continue; }
+            e += uint32_t(__ffs(int(~b))) - 1u;
+            break;
+        }
+        uint32_t mx = 0;
+        for(uint32_t j = i + lane; j < e; j += 32) mx = max(mx, Hh[j]);
+        mx = __reduce_max_sync(0xFFFFFFFFu, mx);
+        if(lane == 0) topk_insert(L, p.K, int32_t(tgt), mx, p.lowest, p.lineage, p.rank);
+        i = e;
+    }
+    if(lane == 0) write_toplist(p, r, L);
+    __syncwarp();
+}
+
+// one read handled by a whole CTA: A = its matches (shared or global memory), Hh = m uint32
+template<class KeyT>
+__device__ __forceinline__ void process_read_cta(const CandParams& p, uint32_t r, KeyT* A, uint32_t* Hh, uint32_t m,
+                                                 KeyT* gsrc, bool staged, int tid, int nt)
 {
     if(staged) {
         for(uint32_t i = tid; i < m; i += nt) A[i] = gsrc[i];
-        gsync<WARP>();
+        __syncthreads();
     }
-    bitonic_sort<WARP>(A, m, tid, nt);
-    if(staged && p.write_sorted) {
-        for(uint32_t i = tid; i < m; i += nt) gsrc[i] = A[i];
-    }
-    // window-range width of this read (classification.cpp:217-219)
-    int64_t span = p.offs1[r + 1] - p.offs1[r];
-    if(p.offs2) span += p.offs2[r + 1] - p.offs2[r];
-    if(p.insertsize > span) span = p.insertsize;
-    const uint32_t numwin = uint32_t(2 + span / p.tstride);
-    // hits of the best range ENDING at each element
-    for(uint32_t i = tid; i < m; i += nt) {
-        const uint64_t key = A[i];
-        const uint32_t win = uint32_t(key);
-        const uint64_t lowkey = (key & 0xFFFFFFFF00000000ull) | (win >= numwin - 1 ? win - (numwin - 1) : 0u);
-        uint32_t lo = 0, hi = i;                 // first index with A[idx] >= lowkey, in [0, i]
-        while(lo < hi) {
-            const uint32_t mid = (lo + hi) >> 1;
-            if(A[mid] < lowkey) lo = mid + 1; else hi = mid;
-        }
-        Hh[i] = i - lo + 1;
-    }
-    gsync<WARP>();
+    bitonic_sort<false>(A, m, tid, nt);
+    if(staged && p.write_sorted) for(uint32_t i = tid; i < m; i += nt) gsrc[i] = A[i];
+    const uint32_t numwin = num_windows_in_range(p, r);
+    for(uint32_t i = tid; i < m; i += nt) Hh[i] = hits_ending_at(A, i, numwin, p.wbits);
+    __syncthreads();
     // the last element of each target run collects the run's maximum
     for(uint32_t i = tid; i < m; i += nt) {
-        const uint32_t tgt = uint32_t(A[i] >> 32);
-        if(i + 1 < m && uint32_t(A[i + 1] >> 32) == tgt) continue;
-        uint32_t best = Hh[i];
-        for(uint32_t j = i; j > 0 && uint32_t(A[j - 1] >> 32) == tgt; --j) best = max(best, Hh[j - 1]);
-        Hh[i] = best;
+        const uint32_t tgt = tgt_of(A[i], p.wbits);
+        uint32_t lo = i, hi = m;                     // first index whose target is larger
+        while(lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if(tgt_of(A[mid], p.wbits) <= tgt) lo = mid + 1; else hi = mid;
+        }
+        const uint32_t tail = lo - 1;
+        if(tail != i) atomicMax(&Hh[tail], Hh[i]);
     }
-    gsync<WARP>();
+    __syncthreads();
     if(tid == 0) {
         TopK L;
         L.n = 0;
-        for(uint32_t i = 0; i < m; ++i) {
-            const uint32_t tgt = uint32_t(A[i] >> 32);
-            if(i + 1 < m && uint32_t(A[i + 1] >> 32) == tgt) continue;
-            topk_insert(L, p.K, int32_t(tgt), Hh[i], p.lowest, p.lineage, p.rank);
+        uint32_t i = 0;
+        while(i < m) {
+            const uint32_t tgt = tgt_of(A[i], p.wbits);
+            uint32_t lo = i, hi = m;
+            while(lo < hi) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if(tgt_of(A[mid], p.wbits) <= tgt) lo = mid + 1; else hi = mid;
+            }
+            topk_insert(L, p.K, int32_t(tgt), Hh[lo - 1], p.lowest, p.lineage, p.rank);
+            i = lo;
         }
-        for(int c = 0; c < p.K; ++c) {
-            p.out_tax[uint64_t(r) * p.K + c] = c < L.n ? L.tax[c] : -1;
-            p.out_hits[uint64_t(r) * p.K + c] = c < L.n ? L.hits[c] : 0u;
-        }
-        p.out_n[r] = L.n;
+        write_toplist(p, r, L);
     }
-    gsync<WARP>();
+    __syncthreads();
 }
 
 // small reads: one warp per read
+template<class KeyT>
 __global__ void __launch_bounds__(256)
 q_cand_warp_kernel(const CandParams p)
 {
     extern __shared__ __align__(16) unsigned char sm[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint64_t* A = reinterpret_cast<uint64_t*>(sm) + size_t(warp) * Q_SMALL;
-    uint32_t* Hh = reinterpret_cast<uint32_t*>(sm + size_t(8) * Q_SMALL * 8) + size_t(warp) * Q_SMALL;
+    KeyT* A = reinterpret_cast<KeyT*>(sm) + size_t(warp) * Q_SMALL;
+    uint32_t* Hh = reinterpret_cast<uint32_t*>(sm + size_t(8) * Q_SMALL * sizeof(KeyT)) + size_t(warp) * Q_SMALL;
     const uint32_t cnt = *p.list_count;
     for(uint32_t it = blockIdx.x * 8 + warp; it < cnt; it += gridDim.x * 8) {
         const uint32_t r = p.list[it];
         const uint64_t beg = p.fpos[uint64_t(p.W[r]) * p.s];
         const uint32_t m = uint32_t(p.fpos[uint64_t(p.W[r + 1]) * p.s] - beg);
-        process_read<true>(p, r, A, Hh, m, p.loc + beg, true, lane, 32);
+        process_read_warp<KeyT>(p, r, A, Hh, m, static_cast<KeyT*>(p.loc) + beg, lane);
     }
 }
 
 // medium / large reads: one CTA per read, capacity fixed by the launch
+template<class KeyT>
 __global__ void q_cand_cta_kernel(const CandParams p, uint32_t capacity)
 {
     extern __shared__ __align__(16) unsigned char sm[];
-    uint64_t* A = reinterpret_cast<uint64_t*>(sm);
-    uint32_t* Hh = reinterpret_cast<uint32_t*>(sm + size_t(capacity) * 8);
+    KeyT* A = reinterpret_cast<KeyT*>(sm);
+    uint32_t* Hh = reinterpret_cast<uint32_t*>(sm + size_t(capacity) * sizeof(KeyT));
     const uint32_t cnt = *p.list_count;
     for(uint32_t it = blockIdx.x; it < cnt; it += gridDim.x) {
         const uint32_t r = p.list[it];
         const uint64_t beg = p.fpos[uint64_t(p.W[r]) * p.s];
         const uint32_t m = uint32_t(p.fpos[uint64_t(p.W[r + 1]) * p.s] - beg);
-        process_read<false>(p, r, A, Hh, m, p.loc + beg, true, threadIdx.x, blockDim.x);
+        process_read_cta<KeyT>(p, r, A, Hh, m, static_cast<KeyT*>(p.loc) + beg, true, threadIdx.x, blockDim.x);
     }
 }
 
 // oversized reads: sorted in place in global memory by one CTA (correctness fallback)
+template<class KeyT>
 __global__ void __launch_bounds__(1024)
 q_cand_global_kernel(const CandParams p)
 {
@@ -334,14 +466,16 @@ q_cand_global_kernel(const CandParams p)
         const uint32_t r = p.list[it];
         const uint64_t beg = p.fpos[uint64_t(p.W[r]) * p.s];
         const uint64_t m64 = p.fpos[uint64_t(p.W[r + 1]) * p.s] - beg;
-        process_read<false>(p, r, p.loc + beg, p.hits_scratch + beg, uint32_t(m64), p.loc + beg, false, threadIdx.x, blockDim.x);
+        KeyT* A = static_cast<KeyT*>(p.loc) + beg;
+        process_read_cta<KeyT>(p, r, A, p.hits_scratch + beg, uint32_t(m64), A, false, threadIdx.x, blockDim.x);
     }
 }
 
-__global__ void q_split_locs_kernel(const uint64_t* loc, uint64_t n, uint32_t* tg, uint32_t* wn)
+template<class KeyT>
+__global__ void q_split_locs_kernel(const KeyT* loc, uint64_t n, int wbits, uint32_t* tg, uint32_t* wn)
 {
     const uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
-    if(i < n) { tg[i] = uint32_t(loc[i] >> 32); wn[i] = uint32_t(loc[i]); }
+    if(i < n) { tg[i] = uint32_t(loc[i] >> wbits); wn[i] = uint32_t(loc[i] & ((KeyT(1) << wbits) - 1)); }
 }
 
 __global__ void q_read_counts_kernel(const uint64_t* fpos, const uint32_t* W, int s, int64_t n, int64_t* out)
@@ -503,8 +637,12 @@ static int query_front(mcg_db* db, const mcg_query_opts* o,
     // gather
     MCG_TRY(c->q_loc.reserve((total + 2) * 8));
     if(nslots > 0 && total > 0) {
-        q_gather_kernel<<<grid_for(nslots), 256, 0, c->stream>>>(c->q_flen.as<uint8_t>(), c->q_foff.as<uint64_t>(), c->q_fpos.as<uint64_t>(),
-                                                                nslots, db->locs.as<uint64_t>(), c->q_loc.as<uint64_t>());
+        if(db->key32)
+            q_gather_kernel<uint32_t><<<grid_for(nslots), 256, 0, c->stream>>>(c->q_flen.as<uint8_t>(), c->q_foff.as<uint64_t>(), c->q_fpos.as<uint64_t>(),
+                                                                              nslots, db->locs.as<uint64_t>(), c->q_loc.as<uint32_t>(), db->wbits);
+        else
+            q_gather_kernel<uint64_t><<<grid_for(nslots), 256, 0, c->stream>>>(c->q_flen.as<uint8_t>(), c->q_foff.as<uint64_t>(), c->q_fpos.as<uint64_t>(),
+                                                                              nslots, db->locs.as<uint64_t>(), c->q_loc.as<uint64_t>(), db->wbits);
         c->launches++;
     }
     MCG_CUDA(cudaGetLastError());
@@ -523,7 +661,7 @@ static int query_back(mcg_db* db, const mcg_query_opts* o, const int64_t* doffs1
     p.offs2 = doffs2;
     p.insertsize = o->insertsize;
     p.tstride = db->cfg.winstride;
-    p.loc = c->q_loc.as<uint64_t>();
+    p.loc = c->q_loc.p;
     p.hits_scratch = nullptr;
     p.K = o->maxcand;
     p.lowest = o->lowest;
@@ -535,28 +673,35 @@ static int query_back(mcg_db* db, const mcg_query_opts* o, const int64_t* doffs1
     p.write_sorted = write_sorted;
     const uint32_t* lists = c->q_cls.as<uint32_t>();
     const uint32_t* counters = c->q_rinfo.as<uint32_t>();
+    p.wbits = db->wbits;
+    const bool k32 = db->key32;
+    const int ksz = k32 ? 4 : 8;
     static bool configured = false;
     if(!configured) {
-        MCG_CUDA(cudaFuncSetAttribute(q_cand_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * Q_SMALL * 12));
-        MCG_CUDA(cudaFuncSetAttribute(q_cand_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Q_LARGE * 12));
+        MCG_CUDA(cudaFuncSetAttribute(q_cand_warp_kernel<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * Q_SMALL * 12));
+        MCG_CUDA(cudaFuncSetAttribute(q_cand_cta_kernel<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, Q_LARGE * 12));
+        MCG_CUDA(cudaFuncSetAttribute(q_cand_cta_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, Q_LARGE * 8));
         configured = true;
     }
     if(run.cls[0] > 0) {
         p.list = lists; p.list_count = counters;
         const unsigned g = unsigned(std::min<uint64_t>((run.cls[0] + 7) / 8, uint64_t(kNumSMs) * 16));
-        q_cand_warp_kernel<<<g, 256, 8 * Q_SMALL * 12, c->stream>>>(p);
+        if(k32) q_cand_warp_kernel<uint32_t><<<g, 256, 8 * Q_SMALL * (ksz + 4), c->stream>>>(p);
+        else    q_cand_warp_kernel<uint64_t><<<g, 256, 8 * Q_SMALL * (ksz + 4), c->stream>>>(p);
         c->launches++;
     }
     if(run.cls[1] > 0) {
         p.list = lists + uint64_t(n); p.list_count = counters + 1;
         const unsigned g = unsigned(std::min<uint64_t>(run.cls[1], uint64_t(kNumSMs) * 8));
-        q_cand_cta_kernel<<<g, 256, Q_MED * 12, c->stream>>>(p, Q_MED);
+        if(k32) q_cand_cta_kernel<uint32_t><<<g, 256, Q_MED * (ksz + 4), c->stream>>>(p, Q_MED);
+        else    q_cand_cta_kernel<uint64_t><<<g, 256, Q_MED * (ksz + 4), c->stream>>>(p, Q_MED);
         c->launches++;
     }
     if(run.cls[2] > 0) {
         p.list = lists + uint64_t(2) * n; p.list_count = counters + 2;
         const unsigned g = unsigned(std::min<uint64_t>(run.cls[2], uint64_t(kNumSMs) * 2));
-        q_cand_cta_kernel<<<g, 512, Q_LARGE * 12, c->stream>>>(p, Q_LARGE);
+        if(k32) q_cand_cta_kernel<uint32_t><<<g, 512, Q_LARGE * (ksz + 4), c->stream>>>(p, Q_LARGE);
+        else    q_cand_cta_kernel<uint64_t><<<g, 512, Q_LARGE * (ksz + 4), c->stream>>>(p, Q_LARGE);
         c->launches++;
     }
     if(run.cls[3] > 0) {
@@ -564,7 +709,8 @@ static int query_back(mcg_db* db, const mcg_query_opts* o, const int64_t* doffs1
         p.hits_scratch = c->tmp4.as<uint32_t>();
         p.list = lists + uint64_t(3) * n; p.list_count = counters + 3;
         const unsigned g = unsigned(std::min<uint64_t>(run.cls[3], uint64_t(kNumSMs) * 2));
-        q_cand_global_kernel<<<g, 1024, 0, c->stream>>>(p);
+        if(k32) q_cand_global_kernel<uint32_t><<<g, 1024, 0, c->stream>>>(p);
+        else    q_cand_global_kernel<uint64_t><<<g, 1024, 0, c->stream>>>(p);
         c->launches++;
     }
     MCG_CUDA(cudaGetLastError());
@@ -719,8 +865,12 @@ int mcg_query_matches(mcg_db* db, const mcg_query_opts* o,
     if(out_tgts != nullptr && out_wins != nullptr && run.total > 0) {
         MCG_TRY(c->m_hits.reserve(run.total * 4));
         MCG_TRY(c->m_n.reserve(run.total * 4));
-        q_split_locs_kernel<<<grid_for(run.total), 256, 0, c->stream>>>(c->q_loc.as<uint64_t>(), run.total,
-                                                                       c->m_hits.as<uint32_t>(), c->m_n.as<uint32_t>());
+        if(db->key32)
+            q_split_locs_kernel<uint32_t><<<grid_for(run.total), 256, 0, c->stream>>>(c->q_loc.as<uint32_t>(), run.total, db->wbits,
+                                                                                     c->m_hits.as<uint32_t>(), c->m_n.as<uint32_t>());
+        else
+            q_split_locs_kernel<uint64_t><<<grid_for(run.total), 256, 0, c->stream>>>(c->q_loc.as<uint64_t>(), run.total, db->wbits,
+                                                                                     c->m_hits.as<uint32_t>(), c->m_n.as<uint32_t>());
         c->launches++;
         MCG_TRY(copy_out(c, out_tgts, c->m_hits.p, run.total * 4));
         MCG_TRY(copy_out(c, out_wins, c->m_n.p, run.total * 4));
