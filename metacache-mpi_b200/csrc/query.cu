@@ -222,6 +222,8 @@ __device__ __forceinline__ uint32_t num_windows_in_range(const CandParams& p, ui
     int64_t span = p.offs1[r + 1] - p.offs1[r];
     if(p.offs2) span += p.offs2[r + 1] - p.offs2[r];
     if(p.insertsize > span) span = p.insertsize;
+    // 32-bit division when possible (the 64-bit one is emulated with ~150 instructions)
+    if(span < (int64_t(1) << 31) && p.tstride < (int64_t(1) << 31)) return 2u + uint32_t(span) / uint32_t(p.tstride);
     return uint32_t(2 + span / p.tstride);
 }
 
