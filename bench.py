@@ -36,6 +36,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+print_json = None
 
 K, S, WINLEN, STRIDE = 16, 16, 128, 113
 GENOME_LEN = 5_000_000
@@ -182,7 +183,7 @@ def run_reference(args):
         "e2e": {"value": val, "unit": "bp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    print_json(line)
 
 
 # ----------------------------------------------------------------------------- our arm
@@ -199,6 +200,9 @@ def run_mcgpu(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # NCCL prints its version banner on stdout at INFO/VERSION level: keep stdout to the one JSON line
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE"):
+            os.environ["NCCL_DEBUG_FILE"] = os.environ.get("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
@@ -327,7 +331,7 @@ def run_mcgpu(args):
             line["cpu_baseline"] = {"value": None, "unit": "bp/s", "cores": 0, "kind": "port", "sample": "failed: %r" % (e,)}
 
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        print_json(line)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
@@ -385,22 +389,52 @@ def run_extras(args, ctx, api, synth, taxonomy, torch, dist, dev, stream, world,
     lt = torch.empty((npairs, Kc), dtype=torch.int32, device=dev)
     lh = torch.empty((npairs, Kc), dtype=torch.int32, device=dev)
     ln = torch.empty(npairs, dtype=torch.int32, device=dev)
-    gt = torch.empty((world, npairs, Kc), dtype=torch.int32, device=dev)
-    gh = torch.empty((world, npairs, Kc), dtype=torch.int32, device=dev)
-    gn = torch.empty((world, npairs), dtype=torch.int32, device=dev)
+    # cross-shard exchange of the per-read top lists.  Preferred: every rank's candidate kernel stores its
+    # lists straight into rank 0's [P][n][K] buffers through NVLink peer memory (torch symmetric memory),
+    # followed by one barrier -- compute and "gather" are the same kernel.  Fallback: NCCL all-gather.
+    gather_mode = "local"
+    hdl_t = hdl_h = hdl_n = None
+    if world > 1:
+        gather_mode = "nccl-all-gather"
+        if os.environ.get("MCG_BENCH_NO_P2P", "") == "":
+            try:
+                import torch.distributed._symmetric_memory as symm
+                gt = symm.empty((world, npairs, Kc), dtype=torch.int32, device=dev)
+                gh = symm.empty((world, npairs, Kc), dtype=torch.int32, device=dev)
+                gn = symm.empty((world, npairs), dtype=torch.int32, device=dev)
+                hdl_t = symm.rendezvous(gt, dist.group.WORLD)
+                hdl_h = symm.rendezvous(gh, dist.group.WORLD)
+                hdl_n = symm.rendezvous(gn, dist.group.WORLD)
+                gather_mode = "p2p-store into rank 0 (symmetric memory) + barrier"
+            except Exception as e:          # pragma: no cover
+                gather_mode = "nccl-all-gather (symmetric memory unavailable: %s)" % type(e).__name__
+                hdl_t = None
+    if hdl_t is None:
+        gt = torch.empty((world, npairs, Kc), dtype=torch.int32, device=dev)
+        gh = torch.empty((world, npairs, Kc), dtype=torch.int32, device=dev)
+        gn = torch.empty((world, npairs), dtype=torch.int32, device=dev)
     mt = torch.empty((npairs, Kc), dtype=torch.int32, device=dev)
     mh = torch.empty((npairs, Kc), dtype=torch.int32, device=dev)
     mn = torch.empty(npairs, dtype=torch.int32, device=dev)
     best = torch.empty(npairs, dtype=torch.int32, device=dev)
     brank = torch.empty(npairs, dtype=torch.int32, device=dev)
     stats = torch.zeros(22, dtype=torch.int64, device=dev)
+    if hdl_t is not None:
+        out_t = hdl_t.buffer_ptrs[0] + rank * npairs * Kc * 4
+        out_h = hdl_h.buffer_ptrs[0] + rank * npairs * Kc * 4
+        out_n = hdl_n.buffer_ptrs[0] + rank * npairs * 4
+    else:
+        out_t, out_h, out_n = lt.data_ptr(), lh.data_ptr(), ln.data_ptr()
 
     def qstep():
         rc = L.mcg_query_batch_dev(db.h, C.byref(q), d1.data_ptr(), do1.data_ptr(), len(b1), d2.data_ptr(), do2.data_ptr(), len(b2),
-                                   npairs, 150, lt.data_ptr(), lh.data_ptr(), ln.data_ptr())
+                                   npairs, 150, out_t, out_h, out_n)
         if rc != 0:
             raise RuntimeError(L.mcg_last_error().decode())
-        if world > 1:
+        if hdl_t is not None:
+            hdl_t.barrier(channel=0)            # all shards' lists have landed in rank 0's memory
+            ct, ch, cn = gt, gh, gn
+        elif world > 1:
             dist.all_gather_into_tensor(gt.view(world * npairs, Kc), lt)
             dist.all_gather_into_tensor(gh.view(world * npairs, Kc), lh)
             dist.all_gather_into_tensor(gn.view(world * npairs), ln)
@@ -414,6 +448,8 @@ def run_extras(args, ctx, api, synth, taxonomy, torch, dist, dev, stream, world,
                                           stats.data_ptr())
             if rc != 0:
                 raise RuntimeError(L.mcg_last_error().decode())
+        if hdl_t is not None:
+            hdl_t.barrier(channel=1)            # rank 0 is done reading before the next batch overwrites
 
     for _ in range(3):
         qstep()
@@ -441,8 +477,8 @@ def run_extras(args, ctx, api, synth, taxonomy, torch, dist, dev, stream, world,
     out["query"] = {"metric": "query_reads_per_s", "value": 2 * npairs / (qms * 1e-3), "unit": "reads/s",
                     "pairs_per_s": npairs / (qms * 1e-3), "ms_per_batch": qms,
                     "workload": "%d pairs 2x150 bp per batch vs %d x 5 Mbp database sharded over %d GPU(s); -lowest species "
-                                "-maxcand 4 -hitmin 4 -hitdiff 80; reads resident, per-rank top lists %s, merge+classify on rank 0"
-                                % (npairs, QG, world, "all-gathered over NCCL" if world > 1 else "local"),
+                                "-maxcand 4 -hitmin 4 -hitdiff 80; reads resident, per-rank top lists: %s, merge+classify on rank 0"
+                                % (npairs, QG, world, gather_mode),
                     "classified": int(st[20]), "unclassified": int(st[21]),
                     "mean_locations_per_pair_shard0": mloc, "gpu_launches_per_batch": int((ctx.launches() - l0) / qsteps),
                     "roofline": {"bound": "hbm", "achieved": algq / (qms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
@@ -453,6 +489,16 @@ def run_extras(args, ctx, api, synth, taxonomy, torch, dist, dev, stream, world,
 
 def main():
     args = parse_args()
+    # keep stdout for the ONE JSON line: anything libraries write to fd 1 meanwhile (e.g. NCCL's
+    # version banner) goes to stderr
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    real_stdout = os.fdopen(saved, "w")
+    global print_json
+    def print_json(obj):
+        real_stdout.write(json.dumps(obj) + "\n")
+        real_stdout.flush()
     if args.impl == "reference":
         run_reference(args)
     else:
