@@ -17,6 +17,7 @@
 
 #include <algorithm>
 #include <numeric>
+#include <ctime>
 
 namespace mcg {
 
@@ -188,9 +189,14 @@ static int build_table(mcg_db* db)
     return MCG_OK;
 }
 
+static double wall() { timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec + 1e-9 * t.tv_nsec; }
+#define TRACE(msg) do { if(trace) { cudaStreamSynchronize(c->stream); const double t = wall(); fprintf(stderr, "[mcg finalize] %-22s %8.2f ms\n", msg, 1e3 * (t - t_prev)); t_prev = t; } } while(0)
+
 int db_finalize(mcg_db* db)
 {
     mcg_ctx* c = db->ctx;
+    const bool trace = getenv("MCG_TRACE") != nullptr;
+    double t_prev = wall();
     MCG_CUDA(cudaSetDevice(c->device));
     const uint32_t s = uint32_t(db->cfg.sketchlen);
     const uint64_t nslots = db->nwin * s;
@@ -211,7 +217,9 @@ int db_finalize(mcg_db* db)
     MCG_TRY(c->tmp2.reserve(nslots * 4));     // vals alt
     uint32_t* skeys = db->feat.as<uint32_t>();
     uint32_t* svals = c->tmp0.as<uint32_t>();
+    TRACE("alloc sort buffers");
     MCG_TRY(radix_sort_pairs(c, skeys, svals, c->tmp1.as<uint32_t>(), c->tmp2.as<uint32_t>(), nslots, 32, true));
+    TRACE("radix sort");
     // (2) drop the padding tail
     MCG_TRY(c->tmp3.reserve(64));
     uint64_t* d_scalar = c->tmp3.as<uint64_t>();
@@ -232,6 +240,7 @@ int db_finalize(mcg_db* db)
         MCG_CUDA(cudaMemcpyAsync(&nkeys, hs + nvalid, 4, cudaMemcpyDeviceToHost, c->stream));
         MCG_CUDA(cudaStreamSynchronize(c->stream));
     }
+    TRACE("runs");
     db->nkeys = nkeys;
     MCG_TRY(db->keys.reserve((uint64_t(nkeys) + 1) * 4));
     MCG_TRY(db->sizes.reserve(uint64_t(nkeys) + 16));
@@ -247,6 +256,7 @@ int db_finalize(mcg_db* db)
     uint64_t nlocs = 0;
     MCG_CUDA(cudaMemcpyAsync(&nlocs, db->offs.as<uint64_t>() + nkeys, 8, cudaMemcpyDeviceToHost, c->stream));
     MCG_CUDA(cudaStreamSynchronize(c->stream));
+    TRACE("sizes + offsets");
     db->nlocs = nlocs;
     MCG_TRY(db->locs.reserve((nlocs + 2) * 8));
     // (4) locations
@@ -262,11 +272,16 @@ int db_finalize(mcg_db* db)
         c->launches++;
         MCG_CUDA(cudaStreamSynchronize(c->stream));     // host vectors were the copy source
     }
-    // (5) open-addressing table over the unique keys
-    MCG_TRY(build_table(db));
+    TRACE("locations");
+    // the sort scratch goes back before the table is allocated (peak memory)
     MCG_CUDA(cudaStreamSynchronize(c->stream));
     db->feat.release();
     c->tmp0.release(); c->tmp1.release(); c->tmp2.release();
+    TRACE("free scratch");
+    // (5) open-addressing table over the unique keys
+    MCG_TRY(build_table(db));
+    MCG_CUDA(cudaStreamSynchronize(c->stream));
+    TRACE("table");
     {
         uint64_t maxwin = 0;
         for(size_t t = 0; t + 1 < db->h_tgt_firstwin.size(); ++t) maxwin = std::max<uint64_t>(maxwin, db->h_tgt_firstwin[t + 1] - db->h_tgt_firstwin[t]);

@@ -4,6 +4,7 @@
 
 #include <cstdarg>
 #include <algorithm>
+#include <mutex>
 
 namespace mcg {
 
@@ -17,20 +18,75 @@ void set_error(const char* fmt, ...)
     va_end(ap);
 }
 
+// ---- caching device allocator -------------------------------------------------------------
+// cudaFree of multi-GB blocks costs up to hundreds of milliseconds (and synchronises the device);
+// released blocks are therefore parked in a per-device cache and handed out again (best fit).
+// The cache is flushed when an allocation fails.
+namespace {
+struct Block { void* p; size_t cap; int dev; };
+std::vector<Block> g_cache;
+std::mutex g_cache_mtx;
+
+void* cache_take(size_t bytes, size_t* cap)
+{
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lk(g_cache_mtx);
+    int best = -1;
+    for(size_t i = 0; i < g_cache.size(); ++i) {
+        const Block& b = g_cache[i];
+        if(b.dev != dev || b.cap < bytes || b.cap > 2 * bytes + (size_t(1) << 20)) continue;
+        if(best < 0 || b.cap < g_cache[size_t(best)].cap) best = int(i);
+    }
+    if(best < 0) return nullptr;
+    void* p = g_cache[size_t(best)].p;
+    *cap = g_cache[size_t(best)].cap;
+    g_cache.erase(g_cache.begin() + best);
+    return p;
+}
+
+void cache_flush()
+{
+    std::lock_guard<std::mutex> lk(g_cache_mtx);
+    int cur = 0;
+    cudaGetDevice(&cur);
+    for(const Block& b : g_cache) { cudaSetDevice(b.dev); cudaFree(b.p); }
+    cudaSetDevice(cur);
+    g_cache.clear();
+}
+
+cudaError_t cached_malloc(void** p, size_t bytes, size_t* cap)
+{
+    void* q = cache_take(bytes, cap);
+    if(q != nullptr) { *p = q; return cudaSuccess; }
+    cudaError_t e = cudaMalloc(p, bytes);
+    if(e != cudaSuccess) {
+        cudaGetLastError();
+        cache_flush();
+        e = cudaMalloc(p, bytes);
+    }
+    *cap = bytes;
+    return e;
+}
+}  // namespace
+
+void release_cached_device_memory() { cache_flush(); }
+
 int DevBuf::reserve(size_t bytes)
 {
     if(bytes <= cap && p != nullptr) return MCG_OK;
-    if(p != nullptr) { cudaFree(p); p = nullptr; cap = 0; }
+    release();
     size_t want = bytes + bytes / 8 + 256;       // slack against repeated growth
     want = (want + 255) & ~size_t(255);
-    cudaError_t e = cudaMalloc(&p, want);
+    size_t got = 0;
+    cudaError_t e = cached_malloc(&p, want, &got);
     if(e != cudaSuccess) {
         p = nullptr;
         set_error("cudaMalloc(%zu bytes) failed: %s", want, cudaGetErrorString(e));
         cudaGetLastError();
         return MCG_ERR_NOMEM;
     }
-    cap = want;
+    cap = got;
     return MCG_OK;
 }
 
@@ -40,12 +96,13 @@ int DevBuf::reserve_keep(size_t bytes, size_t used, cudaStream_t st)
     size_t want = bytes + bytes / 2 + 256;
     want = (want + 255) & ~size_t(255);
     void* np = nullptr;
-    cudaError_t e = cudaMalloc(&np, want);
+    size_t got = 0;
+    cudaError_t e = cached_malloc(&np, want, &got);
     if(e != cudaSuccess) {
         // retry without slack before giving up
         want = (bytes + 255) & ~size_t(255);
         cudaGetLastError();
-        e = cudaMalloc(&np, want);
+        e = cached_malloc(&np, want, &got);
     }
     if(e != cudaSuccess) {
         set_error("cudaMalloc(%zu bytes) failed: %s", want, cudaGetErrorString(e));
@@ -56,15 +113,23 @@ int DevBuf::reserve_keep(size_t bytes, size_t used, cudaStream_t st)
         MCG_CUDA(cudaMemcpyAsync(np, p, used, cudaMemcpyDeviceToDevice, st));
         MCG_CUDA(cudaStreamSynchronize(st));
     }
-    if(p != nullptr) cudaFree(p);
+    release();
     p = np;
-    cap = want;
+    cap = got;
     return MCG_OK;
 }
 
 void DevBuf::release()
 {
-    if(p != nullptr) cudaFree(p);
+    if(p == nullptr) return;
+    // in-flight work may still use the block: wait (cudaFree did so implicitly), then park it
+    cudaDeviceSynchronize();
+    int dev = 0;
+    cudaGetDevice(&dev);
+    {
+        std::lock_guard<std::mutex> lk(g_cache_mtx);
+        g_cache.push_back(Block{p, cap, dev});
+    }
     p = nullptr;
     cap = 0;
 }
@@ -152,6 +217,7 @@ int mcg_ctx_destroy(mcg_ctx* c)
     if(c->ev_misc) cudaEventDestroy(c->ev_misc);
     if(c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
+    release_cached_device_memory();
     return MCG_OK;
 }
 

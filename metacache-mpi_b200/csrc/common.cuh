@@ -53,6 +53,8 @@ struct DevBuf {
     template<class T> T* as() const { return static_cast<T*>(p); }
 };
 
+void release_cached_device_memory();
+
 }  // namespace mcg
 
 // ------------------------------------------------------------------ context / db
