@@ -42,6 +42,8 @@ struct SketchParams {
     int k, s;
     int64_t winlen, stride;
     int wpc;                     // windows per warp tile
+    int nk_full;                 // k-mer starts of a full window and its precomputed threshold
+    uint32_t thr_full;
     int warp_smem;               // bytes of shared memory per warp
     int ngroups;                 // 16-base groups of span capacity
     int pitch;                   // row pitch of the transposed hash array (words)
@@ -221,7 +223,9 @@ __device__ __forceinline__ int filter_compact(const uint32_t* hp, int rel0, int 
     return cnt;
 }
 
-__device__ __noinline__ uint32_t chunked_select(const uint32_t* cb, int cnt, int sp, int lane, uint32_t* tmp, int& nout)
+struct SelOut { uint32_t kept; int nout; };
+
+__device__ __noinline__ SelOut chunked_select(const uint32_t* cb, int cnt, int sp, int lane, uint32_t* tmp)
 {
     const bool wide = sp > 16;
     uint32_t kept = NOF;
@@ -231,13 +235,15 @@ __device__ __noinline__ uint32_t chunked_select(const uint32_t* cb, int cnt, int
         kept = merge_chunk(kept, v, first, wide, lane, tmp);
         first = false;
     }
-    nout = __popc(__ballot_sync(0xFFFFFFFFu, kept != NOF));
-    return kept;
+    SelOut o;
+    o.kept = kept;
+    o.nout = __popc(__ballot_sync(0xFFFFFFFFu, kept != NOF));
+    return o;
 }
 
 // exact selection over all k-mer hashes of a window, 32 at a time (any window length)
-__device__ __noinline__ uint32_t exact_select(const uint32_t* hp, int rel0, int nk, int span, int sp, int lane,
-                                              uint32_t* tmp, int& nout)
+__device__ __noinline__ SelOut exact_select(const uint32_t* hp, int rel0, int nk, int span, int sp, int lane,
+                                            uint32_t* tmp)
 {
     const bool wide = sp > 16;
     uint32_t kept = NOF;
@@ -250,8 +256,10 @@ __device__ __noinline__ uint32_t exact_select(const uint32_t* hp, int rel0, int 
         kept = merge_chunk(kept, h, first, wide, lane, tmp);
         first = false;
     }
-    nout = __popc(__ballot_sync(0xFFFFFFFFu, kept != NOF));
-    return kept;
+    SelOut o;
+    o.kept = kept;
+    o.nout = __popc(__ballot_sync(0xFFFFFFFFu, kept != NOF));
+    return o;
 }
 
 // threshold with ~1.5 s expected survivors among nk hashes; a multiple of 65536 (see NOH);
@@ -370,10 +378,16 @@ __device__ __forceinline__ uint32_t finish_window(const Win& w, int cnt, uint32_
         }
         done = (nout >= w.sp) || (w.T == 0u);
     } else if(cnt > 32) {                            // only without threshold
-        kept = chunked_select(cb, cnt, w.sp, lane, tmp, nout);
+        const SelOut o = chunked_select(cb, cnt, w.sp, lane, tmp);
+        kept = o.kept;
+        nout = o.nout;
         done = true;
     }
-    if(!done) kept = exact_select(w.hp, w.rel0, w.nk, w.span, w.sp, lane, tmp, nout);
+    if(!done) {
+        const SelOut o = exact_select(w.hp, w.rel0, w.nk, w.span, w.sp, lane, tmp);
+        kept = o.kept;
+        nout = o.nout;
+    }
     if(nout > w.sp) nout = w.sp;
     return kept;
 }
@@ -415,40 +429,62 @@ sketch_kernel(const SketchParams p)
     // resolve tile `tile` into table `stage` and start the TMA copy of its bytes
     auto prefetch = [&](uint64_t tile, int stage) {
         int32_t* tb = tabs + stage * tabsz;
+        uint32_t* tbu = reinterpret_cast<uint32_t*>(tb);
         const uint64_t g0 = p.win_lo + tile * uint64_t(wpt);
         const int nw = int(min(uint64_t(wpt), p.nwin - g0));
         int64_t first_abs = 0, last_end = 0;
-        for(int i0 = 0; i0 < nw; i0 += 32) {
-            const int i = i0 + lane;
-            int64_t abs_i = 0, end_i = 0;
-            if(i < nw) {
-                const uint32_t g = uint32_t(g0 + i);
-                int64_t q = p.cta_seq[tile];
-                while(p.win_first[q + 1] <= g) ++q;          // few steps: tiles are short
-                const int64_t w = g - p.win_first[q];
-                const int64_t so = p.seq_off[q];
-                const int64_t len = p.seq_off[q + 1] - so;
-                int64_t b = 0, e = len;
-                if(len > p.winlen) { b = w * p.stride; e = min(b + p.winlen, len); }
-                abs_i = so + b;
-                end_i = so + e;
-                const int nk = int(e - b) - p.k + 1;
-                const int sp = nk < p.s ? (nk < 0 ? 0 : nk) : p.s;
-                tb[wpt + i] = nk;
-                reinterpret_cast<uint32_t*>(tb)[2 * wpt + i] = p.out_first[q] + uint32_t(w);
-                reinterpret_cast<uint32_t*>(tb)[3 * wpt + i] = select_threshold(nk, sp);
-            }
-            if(i0 == 0) first_abs = __shfl_sync(0xFFFFFFFFu, abs_i, 0);
+        const uint32_t q0 = p.cta_seq[tile];
+        const uint32_t wf0 = p.win_first[q0], wf1 = p.win_first[q0 + 1];
+        if(g0 + uint64_t(nw) <= uint64_t(wf1) && nw <= 32) {
+            // common case: the whole tile lies in one sequence
+            const int64_t so = p.seq_off[q0];
+            const int64_t len = p.seq_off[q0 + 1] - so;
+            const uint32_t of = p.out_first[q0];
+            const uint32_t w = uint32_t(g0 - wf0) + uint32_t(lane);
+            int64_t b = 0, e = len;
+            if(len > p.winlen) { b = int64_t(w) * p.stride; e = min(b + p.winlen, len); }
+            const int nk = int(e - b) - p.k + 1;
+            first_abs = __shfl_sync(0xFFFFFFFFu, so + b, 0);
+            last_end = __shfl_sync(0xFFFFFFFFu, so + e, nw - 1);
             const int sb_lo = int((reinterpret_cast<uintptr_t>(p.seq) + uint64_t(first_abs)) & 15u);
-            if(i < nw) tb[i] = int32_t(abs_i - first_abs) + sb_lo;
-            if(i0 + 32 >= nw) last_end = __shfl_sync(0xFFFFFFFFu, end_i, (nw - 1) & 31);
+            if(lane < nw) {
+                tb[lane] = int32_t(so + b - first_abs) + sb_lo;
+                tb[wpt + lane] = nk;
+                tbu[2 * wpt + lane] = of + w;
+                tbu[3 * wpt + lane] = (nk == p.nk_full) ? p.thr_full : select_threshold(nk, min(p.s, max(nk, 0)));
+            }
+        } else {
+            for(int i0 = 0; i0 < nw; i0 += 32) {
+                const int i = i0 + lane;
+                int64_t abs_i = 0, end_i = 0;
+                if(i < nw) {
+                    const uint32_t g = uint32_t(g0 + i);
+                    int64_t q = q0;
+                    while(p.win_first[q + 1] <= g) ++q;          // few steps: tiles are short
+                    const int64_t w = g - p.win_first[q];
+                    const int64_t so = p.seq_off[q];
+                    const int64_t len = p.seq_off[q + 1] - so;
+                    int64_t b = 0, e = len;
+                    if(len > p.winlen) { b = w * p.stride; e = min(b + p.winlen, len); }
+                    abs_i = so + b;
+                    end_i = so + e;
+                    const int nk = int(e - b) - p.k + 1;
+                    tb[wpt + i] = nk;
+                    tbu[2 * wpt + i] = p.out_first[q] + uint32_t(w);
+                    tbu[3 * wpt + i] = select_threshold(nk, min(p.s, max(nk, 0)));
+                }
+                if(i0 == 0) first_abs = __shfl_sync(0xFFFFFFFFu, abs_i, 0);
+                const int sb_lo = int((reinterpret_cast<uintptr_t>(p.seq) + uint64_t(first_abs)) & 15u);
+                if(i < nw) tb[i] = int32_t(abs_i - first_abs) + sb_lo;
+                if(i0 + 32 >= nw) last_end = __shfl_sync(0xFFFFFFFFu, end_i, (nw - 1) & 31);
+            }
         }
         const int64_t sb = first_abs - int64_t((reinterpret_cast<uintptr_t>(p.seq) + uint64_t(first_abs)) & 15u);
         const int span_len = int(last_end - sb);
         if(lane == 0) {
             tb[4 * wpt] = nw;
             tb[4 * wpt + 1] = span_len;
-            const uint32_t bytes = uint32_t(((span_len + 15) >> 4) + 2) * 16u;
+            const uint32_t bytes = uint32_t(((span_len + 15) >> 4) + 1) * 16u;
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_expect_tx(&bars[stage], bytes);
             tma_load_1d(stage ? raw1 : raw0, p.seq + sb, bytes, &bars[stage]);
@@ -480,7 +516,7 @@ sketch_kernel(const SketchParams p)
 
         // ---- (1) pack: raw ASCII (shared) -> 2-bit words + ambiguity bits
         const uint4* rawv = reinterpret_cast<const uint4*>(stage ? raw1 : raw0);
-        for(int j = lane; j < ng + 2; j += 32) {
+        for(int j = lane; j < ng + 1; j += 32) {
             const uint4 v = rawv[j];
             uint32_t c0, c1, c2, c3, d0, d1, d2, d3;
             pack4(v.x, c0, d0);
@@ -636,6 +672,16 @@ int sketch_launch(mcg_ctx* c, const mcg_sketch_cfg& cfg, int sketchlen, int64_t 
     p.out_first = d_out_first;
     p.nwin = nwin;
     p.win_lo = win_lo;
+    {
+        const int nk = int(winlen) - cfg.k + 1;
+        const int sp = std::min(sketchlen, std::max(nk, 0));
+        p.nk_full = nk;
+        p.thr_full = 0u;
+        if(nk > 32) {
+            const float pr = 1.5f * float(sp) / float(nk);
+            if(pr < 0.999f) p.thr_full = uint32_t(pr * 65536.0f) << 16;
+        }
+    }
     p.out_feat = d_out_feat;
     p.out_cnt = d_out_cnt;
     p.k = cfg.k;
