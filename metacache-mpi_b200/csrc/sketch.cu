@@ -25,7 +25,7 @@ constexpr int SK_THREADS = 256;
 constexpr int SK_WARPS = SK_THREADS / 32;
 constexpr int SK_CBUF = 128;              // per-warp compaction buffer (hashes)
 constexpr uint32_t NOF = 0xFFFFFFFFu;
-constexpr int SK_PITCH_DEFAULT = 42;        // pitch of the default shape (k=16, winlen=128, stride=113)
+constexpr int SK_PITCH_DEFAULT = 74;        // pitch of the default shape (k=16, winlen=128, stride=113)
 
 struct SketchParams {
     const uint8_t* seq;
@@ -637,8 +637,10 @@ int sketch_config(const mcg_sketch_cfg& cfg, int sketchlen, int64_t winlen, int6
     const int64_t adv = winlen > stride ? winlen : stride;
     MCG_REQUIRE(adv <= 8192, "window length / stride above 8192 are not supported on the device");
     // windows per warp tile: a typical span (same sequence) fits one 16-base group per lane
-    int64_t w = (512 - 30 - winlen) / stride + 1;
-    if(winlen > 512 - 30) w = 1;
+    static int span_target = -1;
+    if(span_target < 0) { const char* e = getenv("MCG_SK_SPAN"); span_target = e ? atoi(e) : 1024; }
+    int64_t w = (span_target - 30 - winlen) / stride + 1;
+    if(winlen > span_target - 30) w = 1;
     if(w > 16) w = 16;
     if(w < 1) w = 1;
     // capacity for the worst case (every window in a different sequence)
