@@ -81,3 +81,17 @@ def test_full_size_properties(ctx):
     f2, _ = ctx.sketch_windows(*po.concat([synth.revcomp_ascii(seg)]))
     # 1000 full windows + one 15-base tail window (empty sketch) on both strands
     assert len(f1) == 1001 and (f1[:1000] == f2[:1000][::-1]).all()
+
+
+def test_pipelined_host_path_many_chunks(ctx, oracle):
+    """> 32 MB of sequence: the host entry point cuts the input into chunks of windows that are copied,
+    sketched and copied back on three streams; chunk seams fall inside sequences"""
+    rng = np.random.default_rng(11)
+    seqs = [synth.genome(0, 30_000_000), synth.random_bases(rng, 100), synth.genome(2, 41_000_003), b"", synth.genome(4, 7_000_001)]
+    buf, offs = po.concat(seqs)
+    fg, cg = ctx.sketch_windows(buf, offs)
+    fo, co = oracle.sketch_sequences(buf, offs)
+    assert fg.shape == fo.shape
+    bad = np.nonzero((fg != fo).any(axis=1))[0]
+    assert len(bad) == 0, "first differing window %d" % bad[0]
+    assert (cg == co).all()
