@@ -85,11 +85,11 @@ q_find_kernel(const uint32_t* __restrict__ feat, uint64_t nslots, const uint4* _
 // counters: [0] small [1] medium [2] large [3] xl
 __global__ void q_bin_reads_kernel(const uint64_t* fpos, const uint32_t* W, int s, int64_t n,
                                    uint32_t* lists /* [4][n] */, uint32_t* counters,
-                                   int32_t* out_n)
+                                   int32_t* out_n, const uint8_t* done)
 {
     const int64_t r = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
     int cls = 4;                                          // 4 = nothing to do
-    if(r < n) {
+    if(r < n && !(done != nullptr && done[r])) {
         const uint64_t m = fpos[uint64_t(W[r + 1]) * s] - fpos[uint64_t(W[r]) * s];
         if(m == 0) out_n[r] = 0;
         else cls = m <= Q_SMALL ? 0 : (m <= Q_MED ? 1 : (m <= Q_LARGE ? 2 : 3));
@@ -488,6 +488,118 @@ q_cand_warp_kernel(const CandParams p)
     }
 }
 
+// Short reads, fully fused: one warp probes the read's features, gathers the location lists straight
+// into its shared-memory slice, sorts them and derives the top list -- the match list never touches
+// HBM.  Reads with more than 128 feature slots or more than Q_SMALL matches are left to the staged
+// path (their features stay in `feat`; finished reads overwrite theirs with NO_FEATURE so that the
+// staged path skips them).
+struct FusedParams {
+    uint32_t* feat;
+    const uint4* table;
+    uint64_t cap;
+    const uint64_t* locs;
+    int64_t n;
+    uint8_t* done;
+    uint32_t* left_over;        // number of reads left to the staged path
+};
+
+template<class KeyT>
+__global__ void __launch_bounds__(256)
+q_fused_warp_kernel(const CandParams p, const FusedParams f)
+{
+    extern __shared__ __align__(16) unsigned char sm[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    KeyT* A = reinterpret_cast<KeyT*>(sm) + size_t(warp) * Q_SMALL;
+    uint32_t* Hh = reinterpret_cast<uint32_t*>(sm + size_t(8) * Q_SMALL * sizeof(KeyT)) + size_t(warp) * Q_SMALL;
+    const int64_t nwarps = int64_t(gridDim.x) * 8;
+    for(int64_t r = int64_t(blockIdx.x) * 8 + warp; r < f.n; r += nwarps) {
+        const uint64_t s0 = uint64_t(p.W[r]) * p.s, s1 = uint64_t(p.W[r + 1]) * p.s;
+        const uint32_t ns = uint32_t(s1 - s0);
+        if(ns > 128) {
+            if(lane == 0) { atomicAdd(f.left_over, 1u); f.done[r] = 0; }
+            continue;
+        }
+        // (1) probe: up to 4 independent probes per lane in flight
+        uint32_t len[4];
+        uint64_t off[4];
+        uint32_t key[4];
+#pragma unroll
+        for(int c = 0; c < 4; ++c) {
+            const uint32_t sl = uint32_t(c) * 32u + uint32_t(lane);
+            key[c] = sl < ns ? f.feat[s0 + sl] : EMPTY_KEY;
+        }
+        // first probe of all four slots in flight together; collisions continue in a (rare) loop
+        uint64_t slot[4];
+        uint4 ent[4];
+#pragma unroll
+        for(int c = 0; c < 4; ++c) {
+            slot[c] = table_slot(key[c], f.cap);
+            ent[c] = key[c] != EMPTY_KEY ? __ldg(&f.table[slot[c]]) : make_uint4(EMPTY_KEY, 0u, 0u, 0u);
+        }
+#pragma unroll
+        for(int c = 0; c < 4; ++c) {
+            len[c] = 0; off[c] = 0;
+            uint4 e = ent[c];
+            uint64_t s = slot[c];
+            while(e.x != key[c] && e.x != EMPTY_KEY) {
+                if(++s == f.cap) s = 0;
+                e = __ldg(&f.table[s]);
+            }
+            if(e.x == key[c] && key[c] != EMPTY_KEY) { len[c] = e.y; off[c] = uint64_t(e.z) | (uint64_t(e.w) << 32); }
+        }
+        // (2) positions: exclusive scan of the per-lane totals
+        const uint32_t tot = len[0] + len[1] + len[2] + len[3];
+        uint32_t inc = tot;
+#pragma unroll
+        for(int d = 1; d < 32; d <<= 1) {
+            const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+            if(lane >= d) inc += o;
+        }
+        const uint32_t m = __shfl_sync(0xFFFFFFFFu, inc, 31);
+        if(m > Q_SMALL) {
+            if(lane == 0) { atomicAdd(f.left_over, 1u); f.done[r] = 0; }
+            continue;
+        }
+        // this read is finished here: hide its features from the staged path
+#pragma unroll
+        for(int c = 0; c < 4; ++c) {
+            const uint32_t sl = uint32_t(c) * 32u + uint32_t(lane);
+            if(sl < ns) f.feat[s0 + sl] = EMPTY_KEY;
+        }
+        if(lane == 0) f.done[r] = 1;
+        if(m == 0) {
+            if(lane == 0) p.out_n[r] = 0;
+            continue;
+        }
+        // (3) gather into shared memory: short lists by their own lane, long ones by the whole warp
+        uint32_t pos = inc - tot;
+        uint64_t first[4];
+#pragma unroll
+        for(int c = 0; c < 4; ++c) first[c] = len[c] > 0 ? f.locs[off[c]] : 0ull;
+#pragma unroll
+        for(int c = 0; c < 4; ++c) {
+            const uint32_t L = len[c];
+            if(L > 0 && L <= 4) {
+                A[pos] = make_key<KeyT>(first[c], p.wbits);
+                for(uint32_t t = 1; t < L; ++t) A[pos + t] = make_key<KeyT>(f.locs[off[c] + t], p.wbits);
+            }
+            uint32_t big = __ballot_sync(0xFFFFFFFFu, L > 4);
+            while(big) {
+                const int src = __ffs(int(big)) - 1;
+                big &= big - 1;
+                const uint32_t Ls = __shfl_sync(0xFFFFFFFFu, L, src);
+                const uint64_t Os = __shfl_sync(0xFFFFFFFFu, off[c], src);
+                const uint32_t Ps = __shfl_sync(0xFFFFFFFFu, pos, src);
+                for(uint32_t t = lane; t < Ls; t += 32) A[Ps + t] = make_key<KeyT>(f.locs[Os + t], p.wbits);
+            }
+            pos += L;
+        }
+        __syncwarp();
+        // (4) sort + window ranges + top list
+        process_read_warp<KeyT>(p, uint32_t(r), A, Hh, m, A, lane);
+    }
+}
+
 // medium / large reads: one CTA per read, capacity fixed by the launch
 template<class KeyT>
 __global__ void q_cand_cta_kernel(const CandParams p, uint32_t capacity)
@@ -623,10 +735,10 @@ static int check_opts(const mcg_db* db, const mcg_query_opts* o)
 }
 
 // stages a..g: everything up to (and including) the gather.  Reads are on the device.
-static int query_front(mcg_db* db, const mcg_query_opts* o,
-                       const char* d1, const int64_t* doffs1, int64_t bytes1,
-                       const char* d2, const int64_t* doffs2, int64_t bytes2, int64_t n,
-                       int32_t* d_out_n, QueryRun* run)
+// window bookkeeping + K1 on both mates: read-major sketches in c->q_feat, window prefix W in c->tmp2
+static int query_sketch(mcg_db* db, const mcg_query_opts* o,
+                        const char* d1, const int64_t* doffs1, int64_t bytes1,
+                        const char* d2, const int64_t* doffs2, int64_t bytes2, int64_t n, QueryRun* run)
 {
     mcg_ctx* c = db->ctx;
     const int s = o->sketchlen;
@@ -660,6 +772,16 @@ static int query_front(mcg_db* db, const mcg_query_opts* o,
     mcg_sketch_cfg cfg = db->cfg;
     MCG_TRY(sketch_launch(c, cfg, s, o->winlen, o->winstride, d1, bytes1, doffs1, n, wf1, W, h_tot[0], c->q_feat.as<uint32_t>(), nullptr));
     if(d2) MCG_TRY(sketch_launch(c, cfg, s, o->winlen, o->winstride, d2, bytes2, doffs2, n, wf2, of2, h_tot[1], c->q_feat.as<uint32_t>(), nullptr));
+    return MCG_OK;
+}
+
+// staged path: find -> scan -> binning -> gather (reads marked done are skipped)
+static int query_find_gather(mcg_db* db, const mcg_query_opts* o, int64_t n, int32_t* d_out_n, const uint8_t* d_done, QueryRun* run)
+{
+    mcg_ctx* c = db->ctx;
+    const int s = o->sketchlen;
+    const uint64_t nslots = run->nslots;
+    uint32_t* W = c->tmp2.as<uint32_t>();
     // K3: find
     MCG_TRY(c->q_flen.reserve(nslots + 16));
     MCG_TRY(c->q_foff.reserve((nslots + 1) * 8));
@@ -675,7 +797,7 @@ static int query_front(mcg_db* db, const mcg_query_opts* o,
     MCG_TRY(c->q_rinfo.reserve(64));
     uint32_t* counters = c->q_rinfo.as<uint32_t>();
     MCG_CUDA(cudaMemsetAsync(counters, 0, 16, c->stream));
-    q_bin_reads_kernel<<<grid_for(n), 256, 0, c->stream>>>(c->q_fpos.as<uint64_t>(), W, s, n, c->q_cls.as<uint32_t>(), counters, d_out_n);
+    q_bin_reads_kernel<<<grid_for(n), 256, 0, c->stream>>>(c->q_fpos.as<uint64_t>(), W, s, n, c->q_cls.as<uint32_t>(), counters, d_out_n, d_done);
     c->launches++;
     uint64_t total = 0;
     MCG_CUDA(cudaMemcpyAsync(&total, c->q_fpos.as<uint64_t>() + nslots, 8, cudaMemcpyDeviceToHost, c->stream));
@@ -697,11 +819,11 @@ static int query_front(mcg_db* db, const mcg_query_opts* o,
     return MCG_OK;
 }
 
-static int query_back(mcg_db* db, const mcg_query_opts* o, const int64_t* doffs1, const int64_t* doffs2, int64_t n,
-                      const QueryRun& run, int32_t* d_out_tax, uint32_t* d_out_hits, int32_t* d_out_n, int write_sorted)
+static void fill_cand_params(mcg_db* db, const mcg_query_opts* o, const int64_t* doffs1, const int64_t* doffs2,
+                             int32_t* d_out_tax, uint32_t* d_out_hits, int32_t* d_out_n, int write_sorted, CandParams* pp)
 {
     mcg_ctx* c = db->ctx;
-    CandParams p;
+    CandParams& p = *pp;
     p.fpos = c->q_fpos.as<uint64_t>();
     p.W = c->tmp2.as<uint32_t>();
     p.s = o->sketchlen;
@@ -710,7 +832,10 @@ static int query_back(mcg_db* db, const mcg_query_opts* o, const int64_t* doffs1
     p.insertsize = o->insertsize;
     p.tstride = db->cfg.winstride;
     p.loc = c->q_loc.p;
+    p.wbits = db->wbits;
     p.hits_scratch = nullptr;
+    p.list = nullptr;
+    p.list_count = nullptr;
     p.K = o->maxcand;
     p.lowest = o->lowest;
     p.lineage = c->lineage.as<int32_t>();
@@ -719,6 +844,14 @@ static int query_back(mcg_db* db, const mcg_query_opts* o, const int64_t* doffs1
     p.out_hits = d_out_hits;
     p.out_n = d_out_n;
     p.write_sorted = write_sorted;
+}
+
+static int query_back(mcg_db* db, const mcg_query_opts* o, const int64_t* doffs1, const int64_t* doffs2, int64_t n,
+                      const QueryRun& run, int32_t* d_out_tax, uint32_t* d_out_hits, int32_t* d_out_n, int write_sorted)
+{
+    mcg_ctx* c = db->ctx;
+    CandParams p;
+    fill_cand_params(db, o, doffs1, doffs2, d_out_tax, d_out_hits, d_out_n, write_sorted, &p);
     const uint32_t* lists = c->q_cls.as<uint32_t>();
     const uint32_t* counters = c->q_rinfo.as<uint32_t>();
     p.wbits = db->wbits;
@@ -782,7 +915,38 @@ int query_batch_dev(mcg_db* db, const mcg_query_opts* o,
     MCG_CUDA(cudaMemsetAsync(d_out_tax, 0xFF, size_t(n) * K * 4, c->stream));
     MCG_CUDA(cudaMemsetAsync(d_out_hits, 0, size_t(n) * K * 4, c->stream));
     QueryRun run;
-    MCG_TRY(query_front(db, o, d1, doffs1, bytes1, d2, doffs2, bytes2, n, d_out_n, &run));
+    MCG_TRY(query_sketch(db, o, d1, doffs1, bytes1, d2, doffs2, bytes2, n, &run));
+    const uint8_t* d_done = nullptr;
+    static const bool fused_off = getenv("MCG_QUERY_NO_FUSION") != nullptr;
+    if(!write_sorted && !fused_off && run.nslots > 0) {
+        // short reads end to end in one kernel; what it leaves over goes through the staged path
+        MCG_TRY(c->q_cls.reserve(size_t(4) * size_t(n) * 4 + 64));
+        MCG_TRY(c->q_rinfo.reserve(64));
+        MCG_TRY(c->q_done.reserve(size_t(n) + 16));
+        uint32_t* left = c->q_rinfo.as<uint32_t>() + 8;
+        MCG_CUDA(cudaMemsetAsync(left, 0, 4, c->stream));
+        CandParams p;
+        fill_cand_params(db, o, doffs1, d2 ? doffs2 : nullptr, d_out_tax, d_out_hits, d_out_n, 0, &p);
+        FusedParams f;
+        f.feat = c->q_feat.as<uint32_t>(); f.table = db->table.as<uint4>(); f.cap = db->table_cap;
+        f.locs = db->locs.as<uint64_t>(); f.n = n; f.done = c->q_done.as<uint8_t>(); f.left_over = left;
+        const unsigned g = unsigned(std::min<uint64_t>(uint64_t(n + 7) / 8, uint64_t(kNumSMs) * 8));
+        const int ksz = db->key32 ? 4 : 8;
+        static bool configured = false;
+        if(!configured) {
+            MCG_CUDA(cudaFuncSetAttribute(q_fused_warp_kernel<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * Q_SMALL * 12));
+            configured = true;
+        }
+        if(db->key32) q_fused_warp_kernel<uint32_t><<<g, 256, 8 * Q_SMALL * (ksz + 4), c->stream>>>(p, f);
+        else          q_fused_warp_kernel<uint64_t><<<g, 256, 8 * Q_SMALL * (ksz + 4), c->stream>>>(p, f);
+        c->launches++;
+        uint32_t h_left = 0;
+        MCG_CUDA(cudaMemcpyAsync(&h_left, left, 4, cudaMemcpyDeviceToHost, c->stream));
+        MCG_CUDA(cudaStreamSynchronize(c->stream));
+        if(h_left == 0) { if(run_out) *run_out = run; return MCG_OK; }
+        d_done = c->q_done.as<uint8_t>();
+    }
+    MCG_TRY(query_find_gather(db, o, n, d_out_n, d_done, &run));
     MCG_TRY(query_back(db, o, doffs1, d2 ? doffs2 : nullptr, n, run, d_out_tax, d_out_hits, d_out_n, write_sorted));
     if(run_out) *run_out = run;
     return MCG_OK;
