@@ -30,6 +30,7 @@ struct SketchParams {
     int warp_smem;               // bytes of shared memory per warp
     int ngroups;                 // 16-base groups of span capacity
     int pitch;                   // row pitch of the transposed hash array (words)
+    uint32_t c65536;             // the constant 65536, opaque to the compiler (keeps x >> 16 as a multiply-high)
 };
 
 // The hash array holds the hash BEFORE its last xor-shift: y = ((x1>>16)^x1)*C, h = y ^ (y>>16).

@@ -27,7 +27,6 @@ constexpr int TW_WARPS = TW_THREADS / 32;
 constexpr int TW_WPT = 32;               // windows per warp tile (one per lane)
 constexpr int TW_LCAP = 64;              // candidate slots per window in shared memory
 constexpr int TW_SEL = 48;               // candidates the register network takes
-constexpr int TW_TABSZ = 4 * TW_WPT + 2;
 
 // threshold on the hash head (multiple of 65536, see NOH) with sp+15 expected survivors among
 // nk k-mers; 0 = keep everything (short windows)
@@ -50,25 +49,6 @@ __device__ __forceinline__ void tw_pack4(uint32_t x, uint32_t& prod, uint32_t& d
     prod = b * 0x40100401u;
 }
 
-// 16 k-mers of one lane's window: starts 0..15 of the aligned word pair (A0,A1); R = rc16(A)
-template<bool K16, bool CHECK>
-__device__ __forceinline__ void tw_group(uint32_t A0, uint32_t A1, uint32_t R0, uint32_t R1, uint32_t a32, int k,
-                                         uint32_t T, uint32_t*& lp)
-{
-    const int fsh = 32 - 2 * k;
-    const uint32_t kmask = 0xFFFFFFFFu >> fsh;
-    const int ash = 32 - k;
-#pragma unroll
-    for(int r = 0; r < 16; ++r) {
-        uint32_t f = r ? __funnelshift_l(A1, A0, 2 * r) : A0;
-        uint32_t c = r ? __funnelshift_r(R0, R1, 2 * r) : R0;
-        if(!K16) { f >>= fsh; c &= kmask; }
-        uint32_t y = tmh_head(min(f, c));
-        if(CHECK) { if(((a32 << r) >> ash) != 0u) y = NOH; }
-        if(y < T) { *lp = y; lp += 32; }
-    }
-}
-
 #define SN_CE(i, j)                                       \
     {                                                     \
         const uint32_t lo__ = min(v[SN_B + (i)], v[SN_B + (j)]); \
@@ -76,21 +56,66 @@ __device__ __forceinline__ void tw_group(uint32_t A0, uint32_t A1, uint32_t R0, 
         v[SN_B + (i)] = lo__;                             \
     }
 
-// v[0..15] <- the 16 smallest of v[0..15] (sorted) and v[OFF..OFF+15] (sorted), ascending
-template<int OFF>
-__device__ __forceinline__ void tw_merge_low(uint32_t (&v)[TW_SEL])
+__device__ __forceinline__ void st_shared_u32(uint32_t addr, uint32_t v)
 {
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
+// x >> 16 as a multiply-high by 65536 held in a register: IMAD.HI runs on the FMA pipe, which
+// idles while the ALU pipe (shifts, logic, min/max, compares) limits this kernel
+__device__ __forceinline__ uint32_t shr16_fma(uint32_t x, uint32_t c65536)
+{
+    uint32_t h;
+    asm("mul.hi.u32 %0, %1, %2;" : "=r"(h) : "r"(x), "r"(c65536));
+    return h;
+}
+
+template<int MH>
+__device__ __forceinline__ uint32_t tw_head(uint32_t x, uint32_t c65536)
+{
+    x = ((MH >= 1 ? shr16_fma(x, c65536) : (x >> 16)) ^ x) * 0x45d9f3bu;
+    x = ((MH >= 2 ? shr16_fma(x, c65536) : (x >> 16)) ^ x) * 0x45d9f3bu;
+    return x;
+}
+
+// 16 unambiguous k-mers of one lane's window: starts 0..15 of the aligned word pair (A0,A1);
+// R = rc16(A).  Survivors of the threshold go to the lane's column at shared address la.
+template<bool K16, int MH>
+__device__ __forceinline__ void tw_group_fast(uint32_t A0, uint32_t A1, uint32_t R0, uint32_t R1, int k, uint32_t T,
+                                              uint32_t c65536, uint32_t& la)
+{
+    const int fsh = 32 - 2 * k;
+    const uint32_t kmask = 0xFFFFFFFFu >> fsh;
 #pragma unroll
-    for(int i = 0; i < 16; ++i) v[i] = min(v[i], v[OFF + 15 - i]);      // bitonic
-#pragma unroll
-    for(int d = 8; d > 0; d >>= 1) {
-#pragma unroll
-        for(int i = 0; i < 16; ++i) {
-            if((i & d) == 0) {
-                const uint32_t lo = min(v[i], v[i + d]);
-                v[i + d] = max(v[i], v[i + d]);
-                v[i] = lo;
-            }
+    for(int r = 0; r < 16; ++r) {
+        uint32_t f = r ? __funnelshift_l(A1, A0, 2 * r) : A0;
+        uint32_t c = r ? __funnelshift_r(R0, R1, 2 * r) : R0;
+        if(!K16) { f >>= fsh; c &= kmask; }
+        const uint32_t y = tw_head<MH>(min(f, c), c65536);
+        if(y < T) { st_shared_u32(la, y); la += 128u; }
+    }
+}
+
+// the first nr (<= 16) k-mers of a group, any content: ambiguity check, threshold or keep-all
+// mode, capacity check (rolled: rare and small)
+template<bool K16>
+__device__ __forceinline__ void tw_group_any(uint32_t A0, uint32_t A1, uint32_t R0, uint32_t R1, uint32_t a32, int nr, int k,
+                                             bool thr, uint32_t T, uint32_t& la, uint32_t lend, bool& ovf)
+{
+    const int fsh = 32 - 2 * k;
+    const uint32_t kmask = 0xFFFFFFFFu >> fsh;
+    const int ash = 32 - k;
+#pragma unroll 1
+    for(int r = 0; r < nr; ++r) {
+        uint32_t f = __funnelshift_l(A1, A0, 2 * r);
+        uint32_t c = __funnelshift_r(R0, R1, 2 * r);
+        if(!K16) { f >>= fsh; c &= kmask; }
+        uint32_t y = tmh_head(min(f, c));
+        if(((a32 << r) >> ash) != 0u) y = NOH;
+        const bool pass = thr ? (y < T) : (y != NOH);
+        if(pass) {
+            if(la < lend) { st_shared_u32(la, y); la += 128u; }
+            else ovf = true;
         }
     }
 }
@@ -124,88 +149,118 @@ __device__ __noinline__ void tw_slow_window(const uint2* pk2, int pos, int nk, i
     if(out_cnt != nullptr && lane == 0) *out_cnt = uint32_t(nout);
 }
 
-template<bool K16>
-__global__ void __launch_bounds__(TW_THREADS, 3)
+// what a lane knows about its window of the tile (+ warp-uniform span data)
+struct TwTile {
+    int pos, nk;            // first base of the window inside the packed span, k-mer count
+    uint32_t oidx, T;       // output row, threshold
+    int nw, span_len;       // uniform: windows in the tile, bytes from the aligned span start
+    int64_t sb;             // uniform: 16-byte aligned offset of the span in the sequence buffer
+};
+struct TwSeq { uint32_t q0, wf0, wf1, of; int64_t so, so1; };
+
+__device__ __forceinline__ TwSeq tw_load_seq(const SketchParams& p, uint32_t q0)
+{
+    TwSeq q;
+    q.q0 = q0;
+    q.wf0 = __ldg(p.win_first + q0);
+    q.wf1 = __ldg(p.win_first + q0 + 1);
+    q.of = __ldg(p.out_first + q0);
+    q.so = __ldg(p.seq_off + q0);
+    q.so1 = __ldg(p.seq_off + q0 + 1);
+    return q;
+}
+
+__device__ __forceinline__ TwTile tw_resolve(const SketchParams& p, uint64_t tile, const TwSeq& q, int lane)
+{
+    TwTile t;
+    const uint64_t g0 = p.win_lo + tile * uint64_t(TW_WPT);
+    const int nw = int(min(uint64_t(TW_WPT), p.nwin - g0));
+    const int winlen = int(p.winlen), stride = int(p.stride);
+    int64_t first_abs, last_end;
+    if(g0 + uint64_t(nw) <= uint64_t(q.wf1)) {
+        // common case: the whole tile lies in one sequence
+        const int64_t len = q.so1 - q.so;
+        const uint32_t w0 = uint32_t(g0 - q.wf0);
+        int64_t b0 = 0;
+        int off = 0, off_last = 0, wl = int(min(len, int64_t(winlen)));
+        if(len > winlen) {
+            b0 = int64_t(w0) * stride;
+            off = lane * stride;
+            off_last = (nw - 1) * stride;
+            const int rem = int(min(len - b0, int64_t(1) << 30)) - off;      // bases from this window's start to the end
+            wl = min(winlen, rem);
+        }
+        first_abs = q.so + b0;
+        t.pos = off;
+        t.nk = wl - p.k + 1;
+        t.oidx = q.of + w0 + uint32_t(lane);
+        last_end = first_abs + off_last + __shfl_sync(0xFFFFFFFFu, wl, nw - 1);
+    } else {
+        int64_t abs_i = 0;
+        int wl = 0;
+        t.nk = 0;
+        t.oidx = 0;
+        if(lane < nw) {
+            const uint32_t g = uint32_t(g0) + uint32_t(lane);
+            // every sequence has >= 1 window: the sequence of window g0+lane is in [q0, q0+lane]
+            uint32_t lo = q.q0, hi = uint32_t(min(int64_t(q.q0) + lane + 1, p.nseq));
+            while(hi - lo > 1) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if(__ldg(p.win_first + mid) <= g) lo = mid; else hi = mid;
+            }
+            const uint32_t w = g - __ldg(p.win_first + lo);
+            const int64_t so = __ldg(p.seq_off + lo);
+            const int64_t len = __ldg(p.seq_off + lo + 1) - so;
+            int64_t b = 0, e = len;
+            if(len > winlen) { b = int64_t(w) * stride; e = min(b + winlen, len); }
+            abs_i = so + b;
+            wl = int(e - b);
+            t.nk = wl - p.k + 1;
+            t.oidx = __ldg(p.out_first + lo) + w;
+        }
+        first_abs = __shfl_sync(0xFFFFFFFFu, abs_i, 0);
+        t.pos = int(abs_i - first_abs);
+        last_end = __shfl_sync(0xFFFFFFFFu, abs_i + wl, nw - 1);
+    }
+    const int sb_lo = int((reinterpret_cast<uintptr_t>(p.seq) + uint64_t(first_abs)) & 15u);
+    t.pos += sb_lo;
+    t.sb = first_abs - sb_lo;
+    t.span_len = int(last_end - t.sb);
+    t.nw = nw;
+    if(lane >= nw) t.nk = 0;
+    t.T = (t.nk == p.nk_full) ? p.thr_full : tw_threshold(t.nk, min(p.s, max(t.nk, 0)));
+    return t;
+}
+
+template<bool K16, int MH>
+__global__ void __launch_bounds__(TW_THREADS)
 sketch_tpw_kernel(const SketchParams p)
 {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int ngc = p.ngroups;
-    const int rawcap = (ngc + 2) * 16;
+    const int rawcap = max((ngc + 2) * 16, TW_LCAP * 128);
     uint8_t*  base = smem_raw + size_t(warp) * p.warp_smem;
     uint64_t* bar  = reinterpret_cast<uint64_t*>(base);
-    uint8_t*  raw  = base + 16;
+    uint8_t*  raw  = base + 16;                                              // TMA destination ...
+    uint32_t* list = reinterpret_cast<uint32_t*>(raw);                       // ... reused as [TW_LCAP][32] candidate columns
     uint2*    pk2  = reinterpret_cast<uint2*>(raw + rawcap);                 // [ngc + 2] {packed, ambiguity}
-    uint32_t* list = reinterpret_cast<uint32_t*>(pk2 + ngc + 2);             // [TW_LCAP][32]
-    uint32_t* tmp  = list + TW_LCAP * 32;                                    // [32]
-    int32_t*  tabs = reinterpret_cast<int32_t*>(tmp + 32);                   // 2 x TW_TABSZ
-    constexpr int wpt = TW_WPT;
-    const uint64_t ntiles = (p.nwin - p.win_lo + wpt - 1) / wpt;
+    uint32_t* tmp  = reinterpret_cast<uint32_t*>(pk2 + ngc + 2);             // [32]
+    const uint64_t ntiles = (p.nwin - p.win_lo + TW_WPT - 1) / TW_WPT;
     const uint64_t nwarps = uint64_t(gridDim.x) * TW_WARPS;
     const uint64_t gw = uint64_t(blockIdx.x) * TW_WARPS + warp;
+    const int k = p.k;
+    const uint32_t c65536 = p.c65536;
 
-    // resolve tile `tile` into table `stage` and start the TMA copy of its bytes into raw
-    auto prefetch = [&](uint64_t tile, int stage) {
-        int32_t* tb = tabs + stage * TW_TABSZ;
-        uint32_t* tbu = reinterpret_cast<uint32_t*>(tb);
-        const uint64_t g0 = p.win_lo + tile * uint64_t(wpt);
-        const int nw = int(min(uint64_t(wpt), p.nwin - g0));
-        int64_t first_abs = 0, last_end = 0;
-        const uint32_t q0 = p.cta_seq[tile];
-        const uint32_t wf0 = p.win_first[q0], wf1 = p.win_first[q0 + 1];
-        if(g0 + uint64_t(nw) <= uint64_t(wf1)) {
-            // common case: the whole tile lies in one sequence
-            const int64_t so = p.seq_off[q0];
-            const int64_t len = p.seq_off[q0 + 1] - so;
-            const uint32_t of = p.out_first[q0];
-            const uint32_t w = uint32_t(g0 - wf0) + uint32_t(lane);
-            int64_t b = 0, e = len;
-            if(len > p.winlen) { b = int64_t(w) * p.stride; e = min(b + p.winlen, len); }
-            const int nk = int(e - b) - p.k + 1;
-            first_abs = __shfl_sync(0xFFFFFFFFu, so + b, 0);
-            last_end = __shfl_sync(0xFFFFFFFFu, so + e, nw - 1);
-            const int sb_lo = int((reinterpret_cast<uintptr_t>(p.seq) + uint64_t(first_abs)) & 15u);
-            if(lane < nw) {
-                tb[lane] = int32_t(so + b - first_abs) + sb_lo;
-                tb[wpt + lane] = nk;
-                tbu[2 * wpt + lane] = of + w;
-                tbu[3 * wpt + lane] = (nk == p.nk_full) ? p.thr_full : tw_threshold(nk, min(p.s, max(nk, 0)));
-            }
-        } else {
-            int64_t abs_i = 0, end_i = 0;
-            if(lane < nw) {
-                const uint32_t g = uint32_t(g0 + lane);
-                int64_t q = q0;
-                while(p.win_first[q + 1] <= g) ++q;          // few steps: tiles are short
-                const int64_t w = g - p.win_first[q];
-                const int64_t so = p.seq_off[q];
-                const int64_t len = p.seq_off[q + 1] - so;
-                int64_t b = 0, e = len;
-                if(len > p.winlen) { b = w * p.stride; e = min(b + p.winlen, len); }
-                abs_i = so + b;
-                end_i = so + e;
-                const int nk = int(e - b) - p.k + 1;
-                tb[wpt + lane] = nk;
-                tbu[2 * wpt + lane] = p.out_first[q] + uint32_t(w);
-                tbu[3 * wpt + lane] = tw_threshold(nk, min(p.s, max(nk, 0)));
-            }
-            first_abs = __shfl_sync(0xFFFFFFFFu, abs_i, 0);
-            const int sb_lo = int((reinterpret_cast<uintptr_t>(p.seq) + uint64_t(first_abs)) & 15u);
-            if(lane < nw) tb[lane] = int32_t(abs_i - first_abs) + sb_lo;
-            last_end = __shfl_sync(0xFFFFFFFFu, end_i, nw - 1);
-        }
-        const int64_t sb = first_abs - int64_t((reinterpret_cast<uintptr_t>(p.seq) + uint64_t(first_abs)) & 15u);
-        const int span_len = int(last_end - sb);
+    // starts the TMA copy of a tile's bytes (the candidate columns of the previous tile must be consumed)
+    auto tma_issue = [&](const TwTile& t) {
         if(lane == 0) {
-            tb[4 * wpt] = nw;
-            tb[4 * wpt + 1] = span_len;
-            const uint32_t bytes = uint32_t(((span_len + 15) >> 4) + 1) * 16u;
+            const uint32_t bytes = uint32_t(((t.span_len + 15) >> 4) + 1) * 16u;
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_expect_tx(bar, bytes);
-            tma_load_1d(raw, p.seq + sb, bytes, bar);
+            tma_load_1d(raw, p.seq + t.sb, bytes, bar);
         }
-        __syncwarp();
     };
 
     if(lane == 0) {
@@ -213,18 +268,22 @@ sketch_tpw_kernel(const SketchParams p)
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
-    if(gw < ntiles) prefetch(gw, 0);
+    if(gw >= ntiles) return;
+    TwTile cur = tw_resolve(p, gw, tw_load_seq(p, __ldg(p.cta_seq + gw)), lane);
+    tma_issue(cur);
 
-    uint32_t* const lbase = list + lane;
-    const int k = p.k;
-    const int fsh = 32 - 2 * k;
+    const uint32_t la0 = smem_u32(list) + uint32_t(lane) * 4u;
+    const uint32_t lguard = la0 + uint32_t(TW_LCAP - 16) * 128u;
+    const uint32_t lend = la0 + uint32_t(TW_LCAP) * 128u;
 
     int it = 0;
     for(uint64_t tile = gw; tile < ntiles; tile += nwarps, ++it) {
-        const int stage = it & 1;
-        const int32_t* tb = tabs + stage * TW_TABSZ;
-        const int nw = tb[4 * wpt];
-        const int ng = (tb[4 * wpt + 1] + 15) >> 4;
+        const uint64_t nt = tile + nwarps;
+        const bool more = nt < ntiles;
+        // the descriptor of the warp's next tile is resolved in three steps spread over this
+        // tile's work, so that no global-memory latency is ever waited for
+        const uint32_t q0n = more ? __ldg(p.cta_seq + nt) : 0u;             // step A
+        const int ng = (cur.span_len + 15) >> 4;
         mbar_wait(bar, uint32_t(it & 1));
 
         // ---- (1) pack: raw ASCII -> {2-bit word, ambiguity bits} per 16-base group
@@ -246,102 +305,109 @@ sketch_tpw_kernel(const SketchParams p)
             pk2[j] = make_uint2(w, a);
         }
         __syncwarp();
-        // raw is consumed: the copy of the next tile overlaps everything below
-        if(tile + nwarps < ntiles) prefetch(tile + nwarps, stage ^ 1);
+        TwSeq sn;
+        if(more) sn = tw_load_seq(p, q0n);                                   // step B
 
         // ---- (2) this lane's window: hash + threshold filter into the lane's column
-        const bool have = lane < nw;
-        const int pos = have ? tb[lane] : 0;
-        const int nk = have ? tb[wpt + lane] : 0;
-        const uint32_t oidx = reinterpret_cast<const uint32_t*>(tb)[2 * wpt + lane];
-        uint32_t T = reinterpret_cast<const uint32_t*>(tb)[3 * wpt + lane];
+        const int nk = cur.nk;
         const int sp = min(p.s, max(nk, 0));
+        uint32_t T = cur.T;
         const bool thr = T != 0u;
 #pragma unroll
-        for(int i = 0; i < TW_SEL; ++i) lbase[i * 32] = NOH;
-        uint32_t* lp = lbase;
-        uint32_t* const lguard = lbase + (TW_LCAP - 16) * 32;
-        uint32_t* const lend = lbase + TW_LCAP * 32;
+        for(int i = 0; i < TW_LCAP; ++i) st_shared_u32(la0 + uint32_t(i) * 128u, NOH);
+        uint32_t la = la0;
         bool ovf = false;
-        int done = 0;
-        if(thr && nk >= 16) {
-            const int j0 = pos >> 4, sh = 2 * (pos & 15), sa = pos & 15;
-            uint2 w0 = pk2[j0], w1 = pk2[j0 + 1];
+        if(nk > 0) {
+            const int j0 = cur.pos >> 4, sa = cur.pos & 15, sh = 2 * sa;
+            const uint2 w0 = pk2[j0];
+            uint2 w1 = pk2[j0 + 1];
             uint32_t A0 = __funnelshift_l(w1.x, w0.x, sh);
             uint32_t B0 = (((w0.y << 16) | w1.y) << sa) >> 16;
             uint32_t R0 = rc16(A0);
-            const int nfull = nk >> 4;
-            for(int g = 0; g < nfull; ++g) {
+            const int ngr = (nk + 15) >> 4;
+            for(int g = 0; g < ngr; ++g) {
                 const uint2 w2 = pk2[j0 + g + 2];
                 const uint32_t A1 = __funnelshift_l(w2.x, w1.x, sh);
                 const uint32_t B1 = (((w1.y << 16) | w2.y) << sa) >> 16;
                 const uint32_t R1 = rc16(A1);
-                if(lp > lguard) { ovf = true; T = 0u; }
                 const uint32_t a32 = (B0 << 16) | B1;
-                if(a32 == 0u) tw_group<K16, false>(A0, A1, R0, R1, a32, k, T, lp);
-                else          tw_group<K16, true>(A0, A1, R0, R1, a32, k, T, lp);
+                const int nr = min(16, nk - 16 * g);
+                if(thr && nr == 16 && a32 == 0u) {
+                    if(la > lguard) { ovf = true; T = 0u; }
+                    tw_group_fast<K16, MH>(A0, A1, R0, R1, k, T, c65536, la);
+                } else {
+                    tw_group_any<K16>(A0, A1, R0, R1, a32, nr, k, thr, T, la, lend, ovf);
+                }
                 A0 = A1; B0 = B1; R0 = R1; w1 = w2;
             }
-            done = nfull << 4;
         }
-        for(int i = done; i < nk; ++i) {
-            const int b = pos + i, j = b >> 4, r = b & 15;
-            const uint2 w0 = pk2[j], w1 = pk2[j + 1];
-            const uint32_t f = __funnelshift_l(w1.x, w0.x, 2 * r) >> fsh;
-            const uint32_t c = rc16(f) >> fsh;
-            const uint32_t a = (w0.y << 16) | w1.y;
-            uint32_t y = tmh_head(min(f, c));
-            if(((a << r) >> (32 - k)) != 0u) y = NOH;
-            const bool pass = thr ? (y < T) : (y != NOH);
-            if(pass) {
-                if(lp < lend) { *lp = y; lp += 32; }
-                else ovf = true;
-            }
-        }
-        const int cnt = int(lp - lbase) >> 5;
+        const int cnt = int(la - la0) >> 7;
 
-        // ---- (3) register network: 16 smallest of the <= 48 survivors
-        uint32_t v[TW_SEL];
+        // ---- (3) register network, 16 survivors at a time: 16-input sort, then the 16 smallest
+        //      of (best, block) by one min layer + a bitonic merge
+        uint32_t best[16];
 #pragma unroll
-        for(int i = 0; i < TW_SEL; ++i) v[i] = tmh_tail(lbase[i * 32]);
+        for(int i = 0; i < 16; ++i) best[i] = NOF;
+        const int nb = (cnt + 15) >> 4;
+#pragma unroll 1
+        for(int b = 0; b < nb; ++b) {
+            uint32_t v[16];
+            const uint32_t* src = list + lane + b * 512;
+#pragma unroll
+            for(int i = 0; i < 16; ++i) v[i] = tmh_tail(src[i * 32]);
 #define SN_B 0
 #include "sortnet16.inc"
 #undef SN_B
-#define SN_B 16
-#include "sortnet16.inc"
-#undef SN_B
-#define SN_B 32
-#include "sortnet16.inc"
-#undef SN_B
-        tw_merge_low<16>(v);
-        tw_merge_low<32>(v);
+#pragma unroll
+            for(int i = 0; i < 16; ++i) best[i] = min(best[i], v[15 - i]);
+#pragma unroll
+            for(int d = 8; d > 0; d >>= 1) {
+#pragma unroll
+                for(int i = 0; i < 16; ++i) {
+                    if((i & d) == 0) {
+                        const uint32_t lo = min(best[i], best[i + d]);
+                        best[i + d] = max(best[i], best[i + d]);
+                        best[i] = lo;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        // the columns are consumed: resolve the next tile and start its copy         (step C)
+        TwTile nxt = cur;
+        if(more) {
+            nxt = tw_resolve(p, nt, sn, lane);
+            tma_issue(nxt);
+        }
+
         bool dup = false;
 #pragma unroll
-        for(int i = 0; i < 15; ++i) dup |= (v[i] == v[i + 1]);
+        for(int i = 0; i < 15; ++i) dup |= (best[i] == best[i + 1]);
         if(dup) {                                   // equal padding does not count
             dup = false;
 #pragma unroll
-            for(int i = 0; i < 15; ++i) dup |= (v[i] == v[i + 1]) && (v[i] != NOF);
+            for(int i = 0; i < 15; ++i) dup |= (best[i] == best[i + 1]) && (best[i] != NOF);
         }
-        const bool bad = (sp > 0) && (ovf || cnt > TW_SEL || dup || (thr && cnt < sp));
+        const bool have = lane < cur.nw;
+        const bool bad = (sp > 0) && (ovf || dup || (thr && cnt < sp));
         if(have && !bad) {
-            uint32_t* o = p.out_feat + uint64_t(oidx) * uint32_t(p.s);
+            uint32_t* o = p.out_feat + uint64_t(cur.oidx) * uint32_t(p.s);
             if(p.s == 16) {
                 uint4* o4 = reinterpret_cast<uint4*>(o);
-                o4[0] = make_uint4(v[0], v[1], v[2], v[3]);
-                o4[1] = make_uint4(v[4], v[5], v[6], v[7]);
-                o4[2] = make_uint4(v[8], v[9], v[10], v[11]);
-                o4[3] = make_uint4(v[12], v[13], v[14], v[15]);
+                o4[0] = make_uint4(best[0], best[1], best[2], best[3]);
+                o4[1] = make_uint4(best[4], best[5], best[6], best[7]);
+                o4[2] = make_uint4(best[8], best[9], best[10], best[11]);
+                o4[3] = make_uint4(best[12], best[13], best[14], best[15]);
             } else {
 #pragma unroll
                 for(int i = 0; i < 16; ++i)
-                    if(i < p.s) o[i] = v[i];
+                    if(i < p.s) o[i] = best[i];
             }
             if(p.out_cnt != nullptr) {
                 int n = 0;
 #pragma unroll
-                for(int i = 0; i < 16; ++i) n += (i < p.s && v[i] != NOF) ? 1 : 0;
-                p.out_cnt[oidx] = uint32_t(min(n, sp));
+                for(int i = 0; i < 16; ++i) n += (i < p.s && best[i] != NOF) ? 1 : 0;
+                p.out_cnt[cur.oidx] = uint32_t(min(n, sp));
             }
         }
         // ---- (4) rare: exact redo of flagged windows by the whole warp
@@ -349,13 +415,14 @@ sketch_tpw_kernel(const SketchParams p)
         while(bm != 0u) {
             const int src = __ffs(bm) - 1;
             bm &= bm - 1u;
-            const int pos_s = __shfl_sync(0xFFFFFFFFu, pos, src);
+            const int pos_s = __shfl_sync(0xFFFFFFFFu, cur.pos, src);
             const int nk_s = __shfl_sync(0xFFFFFFFFu, nk, src);
-            const uint32_t o_s = __shfl_sync(0xFFFFFFFFu, oidx, src);
+            const uint32_t o_s = __shfl_sync(0xFFFFFFFFu, cur.oidx, src);
             tw_slow_window(pk2, pos_s, nk_s, min(p.s, max(nk_s, 0)), k, p.s, p.out_feat + uint64_t(o_s) * uint32_t(p.s),
                            p.out_cnt ? p.out_cnt + o_s : nullptr, lane, tmp);
         }
         __syncwarp();
+        cur = nxt;
     }
 }
 #undef SN_CE
@@ -373,7 +440,8 @@ void tpw_config(int64_t winlen, int64_t stride, int* ngroups, size_t* warp_smem)
 {
     const int64_t adv = winlen > stride ? winlen : stride;
     const int ng = int((TW_WPT * adv + 30 + 15) / 16) + 1;      // worst case: every window in another sequence
-    size_t bytes = 16 + size_t(ng + 2) * 16 + size_t(ng + 2) * 8 + size_t(TW_LCAP) * 32 * 4 + 32 * 4 + 2 * TW_TABSZ * 4;
+    const size_t region = std::max(size_t(ng + 2) * 16, size_t(TW_LCAP) * 32 * 4);     // raw bytes, then candidate columns
+    size_t bytes = 16 + region + size_t(ng + 2) * 8 + 32 * 4;
     bytes = (bytes + 127) & ~size_t(127);
     *ngroups = ng;
     *warp_smem = bytes;
@@ -389,9 +457,12 @@ int tpw_launch(mcg_ctx* c, SketchParams& p, const mcg_sketch_cfg& cfg, uint64_t 
         p.nk_full = nk;
         p.thr_full = tw_threshold(nk, sp);
     }
-#define TW_LAUNCH(K16)                                                                                              \
+    static int mh = -1;
+    if(mh < 0) { const char* e = getenv("MCG_SK_MH"); mh = e ? atoi(e) : 0; }
+    p.c65536 = 65536u;
+#define TW_LAUNCH(K16, MH)                                                                                          \
     do {                                                                                                            \
-        auto kern = sketch_tpw_kernel<K16>;                                                                         \
+        auto kern = sketch_tpw_kernel<K16, MH>;                                                                       \
         if(smem > 48 * 1024) MCG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))); \
         int per_sm = 1;                                                                                             \
         MCG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TW_THREADS, smem));                   \
@@ -399,8 +470,10 @@ int tpw_launch(mcg_ctx* c, SketchParams& p, const mcg_sketch_cfg& cfg, uint64_t 
         const uint64_t grid = std::min<uint64_t>((nblocks + TW_WARPS - 1) / TW_WARPS, uint64_t(kNumSMs) * uint64_t(per_sm)); \
         kern<<<unsigned(grid), TW_THREADS, smem, stream>>>(p);                                                      \
     } while(0)
-    if(cfg.k == 16) TW_LAUNCH(true);
-    else            TW_LAUNCH(false);
+    if(cfg.k != 16)   TW_LAUNCH(false, 0);
+    else if(mh == 1)  TW_LAUNCH(true, 1);
+    else if(mh == 2)  TW_LAUNCH(true, 2);
+    else              TW_LAUNCH(true, 0);
 #undef TW_LAUNCH
     c->launches++;
     MCG_CUDA(cudaGetLastError());
