@@ -208,7 +208,7 @@ int mcg_ctx_destroy(mcg_ctx* c)
                       &c->tmp2, &c->tmp3, &c->tmp4, &c->tmp5, &c->scan_tmp, &c->q_feat, &c->q_flen, &c->q_foff,
                       &c->q_fpos, &c->q_loc, &c->q_rinfo, &c->q_cls, &c->q_out_tax, &c->q_out_hits, &c->q_out_n, &c->q_done,
                       &c->m_tax, &c->m_hits, &c->m_n, &c->m_o_tax, &c->m_o_hits, &c->m_o_n, &c->m_best,
-                      &c->m_brank, &c->m_stats};
+                      &c->m_brank, &c->m_stats, &c->tilectr};
     for(DevBuf* b : bufs) b->release();
     if(c->pinned != nullptr) cudaFreeHost(c->pinned);
     if(c->s_h2d) cudaStreamDestroy(c->s_h2d);

@@ -67,7 +67,7 @@ struct mcg_ctx {
     mcg::DevBuf lineage, rank;
     int64_t ntaxa = 0, ntargets = 0;
     // scratch
-    mcg::DevBuf seq, seqoff, winfirst, outfirst, tmp0, tmp1, tmp2, tmp3, tmp4, tmp5, scan_tmp;
+    mcg::DevBuf seq, seqoff, winfirst, outfirst, tmp0, tmp1, tmp2, tmp3, tmp4, tmp5, scan_tmp, tilectr;
     mcg::DevBuf q_feat, q_flen, q_foff, q_fpos, q_loc, q_rinfo, q_cls, q_out_tax, q_out_hits, q_out_n, q_done;
     mcg::DevBuf m_tax, m_hits, m_n, m_o_tax, m_o_hits, m_o_n, m_best, m_brank, m_stats;
     void* pinned = nullptr;           // small pinned staging area for scalars

@@ -407,9 +407,11 @@ sketch_kernel(const SketchParams p)
 
 // sequence that holds the first window of every CTA (one binary search per CTA, done up front
 // so that the main kernel starts with one load instead of a chain of dependent ones)
-__global__ void cta_seq_kernel(const uint32_t* win_first, int64_t nseq, int wpc, uint32_t nblocks, uint64_t win_lo, uint32_t* cta_seq)
+__global__ void cta_seq_kernel(const uint32_t* win_first, int64_t nseq, int wpc, uint32_t nblocks, uint64_t win_lo, uint32_t* cta_seq,
+                               uint32_t* tile_ctr)
 {
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if(b == 0 && tile_ctr != nullptr) *tile_ctr = 0u;
     if(b > nblocks) return;
     if(b == nblocks) { cta_seq[b] = uint32_t(nseq - 1); return; }
     const uint32_t g = uint32_t(win_lo + uint64_t(b) * uint32_t(wpc));
@@ -529,7 +531,10 @@ int sketch_launch(mcg_ctx* c, const mcg_sketch_cfg& cfg, int sketchlen, int64_t 
         MCG_TRY(c->outfirst.reserve((nblocks + 4) * sizeof(uint32_t)));
         tile_seq = c->outfirst.as<uint32_t>();
     }
-    cta_seq_kernel<<<unsigned((nblocks + 256) / 256), 256, 0, stream>>>(d_win_first, nseq, p.wpc, uint32_t(nblocks), win_lo, tile_seq);
+    MCG_TRY(c->tilectr.reserve(64));
+    p.tile_ctr = c->tilectr.as<uint32_t>();
+    cta_seq_kernel<<<unsigned((nblocks + 256) / 256), 256, 0, stream>>>(d_win_first, nseq, p.wpc, uint32_t(nblocks), win_lo, tile_seq,
+                                                                         p.tile_ctr);
     c->launches++;
     p.cta_seq = tile_seq;
     if(tpw_eligible(sketchlen, winlen, stride)) return tpw_launch(c, p, cfg, nblocks, stream);

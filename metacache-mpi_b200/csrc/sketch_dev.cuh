@@ -30,6 +30,7 @@ struct SketchParams {
     int warp_smem;               // bytes of shared memory per warp
     int ngroups;                 // 16-base groups of span capacity
     int pitch;                   // row pitch of the transposed hash array (words)
+    uint32_t* tile_ctr;          // dynamic tile counter of the thread-per-window kernel (zeroed by cta_seq_kernel)
     uint32_t c65536;             // the constant 65536, opaque to the compiler (keeps x >> 16 as a multiply-high)
 };
 

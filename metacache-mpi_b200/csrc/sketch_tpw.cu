@@ -247,9 +247,7 @@ sketch_tpw_kernel(const SketchParams p)
     uint32_t* list = reinterpret_cast<uint32_t*>(raw);                       // ... reused as [TW_LCAP][32] candidate columns
     uint2*    pk2  = reinterpret_cast<uint2*>(raw + rawcap);                 // [ngc + 2] {packed, ambiguity}
     uint32_t* tmp  = reinterpret_cast<uint32_t*>(pk2 + ngc + 2);             // [32]
-    const uint64_t ntiles = (p.nwin - p.win_lo + TW_WPT - 1) / TW_WPT;
-    const uint64_t nwarps = uint64_t(gridDim.x) * TW_WARPS;
-    const uint64_t gw = uint64_t(blockIdx.x) * TW_WARPS + warp;
+    const uint32_t ntiles = uint32_t((p.nwin - p.win_lo + TW_WPT - 1) / TW_WPT);
     const int k = p.k;
     const uint32_t c65536 = p.c65536;
 
@@ -268,17 +266,24 @@ sketch_tpw_kernel(const SketchParams p)
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
-    if(gw >= ntiles) return;
-    TwTile cur = tw_resolve(p, gw, tw_load_seq(p, __ldg(p.cta_seq + gw)), lane);
+    // tiles are handed out by an atomic counter: warps that the scheduler favours simply take
+    // more tiles, and every warp stays busy until the last tile is gone
+    auto next_tile = [&]() -> uint32_t {
+        uint32_t t = 0;
+        if(lane == 0) t = atomicAdd(p.tile_ctr, 1u);
+        return __shfl_sync(0xFFFFFFFFu, t, 0);
+    };
+    uint32_t tile = next_tile();
+    if(tile >= ntiles) return;
+    TwTile cur = tw_resolve(p, tile, tw_load_seq(p, __ldg(p.cta_seq + tile)), lane);
     tma_issue(cur);
 
     const uint32_t la0 = smem_u32(list) + uint32_t(lane) * 4u;
     const uint32_t lguard = la0 + uint32_t(TW_LCAP - 16) * 128u;
     const uint32_t lend = la0 + uint32_t(TW_LCAP) * 128u;
 
-    int it = 0;
-    for(uint64_t tile = gw; tile < ntiles; tile += nwarps, ++it) {
-        const uint64_t nt = tile + nwarps;
+    for(int it = 0;; ++it) {
+        const uint32_t nt = next_tile();
         const bool more = nt < ntiles;
         // the descriptor of the warp's next tile is resolved in three steps spread over this
         // tile's work, so that no global-memory latency is ever waited for
@@ -346,11 +351,18 @@ sketch_tpw_kernel(const SketchParams p)
         // ---- (3) register network, 16 survivors at a time: 16-input sort, then the 16 smallest
         //      of (best, block) by one min layer + a bitonic merge
         uint32_t best[16];
+        {
+            uint32_t (&v)[16] = best;
+            const uint32_t* src = list + lane;
 #pragma unroll
-        for(int i = 0; i < 16; ++i) best[i] = NOF;
+            for(int i = 0; i < 16; ++i) v[i] = tmh_tail(src[i * 32]);
+#define SN_B 0
+#include "sortnet16.inc"
+#undef SN_B
+        }
         const int nb = (cnt + 15) >> 4;
 #pragma unroll 1
-        for(int b = 0; b < nb; ++b) {
+        for(int b = 1; b < nb; ++b) {
             uint32_t v[16];
             const uint32_t* src = list + lane + b * 512;
 #pragma unroll
@@ -422,7 +434,9 @@ sketch_tpw_kernel(const SketchParams p)
                            p.out_cnt ? p.out_cnt + o_s : nullptr, lane, tmp);
         }
         __syncwarp();
+        if(!more) break;
         cur = nxt;
+        tile = nt;
     }
 }
 #undef SN_CE
