@@ -25,7 +25,7 @@ namespace mcg {
 constexpr int TW_THREADS = 128;
 constexpr int TW_WARPS = TW_THREADS / 32;
 constexpr int TW_WPT = 32;               // windows per warp tile (one per lane)
-constexpr int TW_LCAP = 64;              // candidate slots per window in shared memory
+constexpr int TW_LCAP = 64;              // candidate slots per window in shared memory 
 constexpr int TW_SEL = 48;               // candidates the register network takes
 
 // threshold on the hash head (multiple of 65536, see NOH) with sp+15 expected survivors among
@@ -49,12 +49,23 @@ __device__ __forceinline__ void tw_pack4(uint32_t x, uint32_t& prod, uint32_t& d
     prod = b * 0x40100401u;
 }
 
-#define SN_CE(i, j)                                       \
-    {                                                     \
-        const uint32_t lo__ = min(v[SN_B + (i)], v[SN_B + (j)]); \
-        v[SN_B + (j)] = max(v[SN_B + (i)], v[SN_B + (j)]);       \
-        v[SN_B + (i)] = lo__;                             \
+// compare-exchange.  FMA form: hi = a + b - min(a, b) as two multiply-adds by registers holding
+// 1 and -1 (IMAD, FMA pipe) instead of a second min/max on the ALU pipe that limits this kernel
+template<bool FMA>
+__device__ __forceinline__ void tw_ce(uint32_t& a, uint32_t& b, uint32_t one, uint32_t m1)
+{
+    const uint32_t lo = min(a, b);
+    if(FMA) {
+        uint32_t s, hi;
+        asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(s) : "r"(a), "r"(one), "r"(b));
+        asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(hi) : "r"(lo), "r"(m1), "r"(s));
+        b = hi;
+    } else {
+        b = max(a, b);
     }
+    a = lo;
+}
+#define SN_CE(i, j) tw_ce<(CEF & 1) != 0>(v[SN_B + (i)], v[SN_B + (j)], one, m1);
 
 __device__ __forceinline__ void st_shared_u32(uint32_t addr, uint32_t v)
 {
@@ -80,18 +91,20 @@ __device__ __forceinline__ uint32_t tw_head(uint32_t x, uint32_t c65536)
 
 // 16 unambiguous k-mers of one lane's window: starts 0..15 of the aligned word pair (A0,A1);
 // R = rc16(A).  Survivors of the threshold go to the lane's column at shared address la.
-template<bool K16, int MH>
-__device__ __forceinline__ void tw_group_fast(uint32_t A0, uint32_t A1, uint32_t R0, uint32_t R1, int k, uint32_t T,
+template<bool K16, int MH, bool CHECK>
+__device__ __forceinline__ void tw_group_fast(uint32_t A0, uint32_t A1, uint32_t R0, uint32_t R1, uint32_t a32, int k, uint32_t T,
                                               uint32_t c65536, uint32_t& la)
 {
     const int fsh = 32 - 2 * k;
     const uint32_t kmask = 0xFFFFFFFFu >> fsh;
+    const int ash = 32 - k;
 #pragma unroll
     for(int r = 0; r < 16; ++r) {
         uint32_t f = r ? __funnelshift_l(A1, A0, 2 * r) : A0;
         uint32_t c = r ? __funnelshift_r(R0, R1, 2 * r) : R0;
         if(!K16) { f >>= fsh; c &= kmask; }
-        const uint32_t y = tw_head<MH>(min(f, c), c65536);
+        uint32_t y = tw_head<MH>(min(f, c), c65536);
+        if(CHECK) { if(((a32 << r) >> ash) != 0u) y = NOH; }     // NOH >= every threshold
         if(y < T) { st_shared_u32(la, y); la += 128u; }
     }
 }
@@ -232,8 +245,8 @@ __device__ __forceinline__ TwTile tw_resolve(const SketchParams& p, uint64_t til
     return t;
 }
 
-template<bool K16, int MH>
-__global__ void __launch_bounds__(TW_THREADS)
+template<bool K16, int MH, int CEF>
+__global__ void __launch_bounds__(TW_THREADS, 5)
 sketch_tpw_kernel(const SketchParams p)
 {
     extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -250,6 +263,7 @@ sketch_tpw_kernel(const SketchParams p)
     const uint32_t ntiles = uint32_t((p.nwin - p.win_lo + TW_WPT - 1) / TW_WPT);
     const int k = p.k;
     const uint32_t c65536 = p.c65536;
+    const uint32_t one = c65536 >> 16, m1 = 0u - one;      // opaque 1 and -1
 
     // starts the TMA copy of a tile's bytes (the candidate columns of the previous tile must be consumed)
     auto tma_issue = [&](const TwTile& t) {
@@ -329,21 +343,29 @@ sketch_tpw_kernel(const SketchParams p)
             uint32_t A0 = __funnelshift_l(w1.x, w0.x, sh);
             uint32_t B0 = (((w0.y << 16) | w1.y) << sa) >> 16;
             uint32_t R0 = rc16(A0);
-            const int ngr = (nk + 15) >> 4;
-            for(int g = 0; g < ngr; ++g) {
-                const uint2 w2 = pk2[j0 + g + 2];
+            const uint2* pw = pk2 + j0 + 2;
+            const int nfull = thr ? (nk >> 4) : 0;              // full groups of the threshold mode
+            int left = nk;
+            for(int g = 0; g < nfull; ++g) {
+                const uint2 w2 = *pw++;
                 const uint32_t A1 = __funnelshift_l(w2.x, w1.x, sh);
                 const uint32_t B1 = (((w1.y << 16) | w2.y) << sa) >> 16;
                 const uint32_t R1 = rc16(A1);
                 const uint32_t a32 = (B0 << 16) | B1;
-                const int nr = min(16, nk - 16 * g);
-                if(thr && nr == 16 && a32 == 0u) {
-                    if(la > lguard) { ovf = true; T = 0u; }
-                    tw_group_fast<K16, MH>(A0, A1, R0, R1, k, T, c65536, la);
-                } else {
-                    tw_group_any<K16>(A0, A1, R0, R1, a32, nr, k, thr, T, la, lend, ovf);
-                }
+                if(la > lguard) { ovf = true; T = 0u; }
+                if(a32 == 0u) tw_group_fast<K16, MH, false>(A0, A1, R0, R1, a32, k, T, c65536, la);
+                else          tw_group_fast<K16, MH, true>(A0, A1, R0, R1, a32, k, T, c65536, la);
                 A0 = A1; B0 = B1; R0 = R1; w1 = w2;
+            }
+            left -= nfull << 4;
+            while(left > 0) {                                   // last partial group / keep-everything mode
+                const uint2 w2 = *pw++;
+                const uint32_t A1 = __funnelshift_l(w2.x, w1.x, sh);
+                const uint32_t B1 = (((w1.y << 16) | w2.y) << sa) >> 16;
+                const uint32_t R1 = rc16(A1);
+                tw_group_any<K16>(A0, A1, R0, R1, (B0 << 16) | B1, min(16, left), k, thr, T, la, lend, ovf);
+                A0 = A1; B0 = B1; R0 = R1; w1 = w2;
+                left -= 16;
             }
         }
         const int cnt = int(la - la0) >> 7;
@@ -376,11 +398,7 @@ sketch_tpw_kernel(const SketchParams p)
             for(int d = 8; d > 0; d >>= 1) {
 #pragma unroll
                 for(int i = 0; i < 16; ++i) {
-                    if((i & d) == 0) {
-                        const uint32_t lo = min(best[i], best[i + d]);
-                        best[i + d] = max(best[i], best[i + d]);
-                        best[i] = lo;
-                    }
+                    if((i & d) == 0) tw_ce<(CEF & 2) != 0>(best[i], best[i + d], one, m1);
                 }
             }
         }
@@ -474,9 +492,11 @@ int tpw_launch(mcg_ctx* c, SketchParams& p, const mcg_sketch_cfg& cfg, uint64_t 
     static int mh = -1;
     if(mh < 0) { const char* e = getenv("MCG_SK_MH"); mh = e ? atoi(e) : 0; }
     p.c65536 = 65536u;
-#define TW_LAUNCH(K16, MH)                                                                                          \
+    static int cef = -1;
+    if(cef < 0) { const char* e = getenv("MCG_SK_CEF"); cef = e ? atoi(e) : 3; }
+#define TW_LAUNCH(K16, MH, CEF)                                                                                     \
     do {                                                                                                            \
-        auto kern = sketch_tpw_kernel<K16, MH>;                                                                       \
+        auto kern = sketch_tpw_kernel<K16, MH, CEF>;                                                                       \
         if(smem > 48 * 1024) MCG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))); \
         int per_sm = 1;                                                                                             \
         MCG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TW_THREADS, smem));                   \
@@ -484,10 +504,12 @@ int tpw_launch(mcg_ctx* c, SketchParams& p, const mcg_sketch_cfg& cfg, uint64_t 
         const uint64_t grid = std::min<uint64_t>((nblocks + TW_WARPS - 1) / TW_WARPS, uint64_t(kNumSMs) * uint64_t(per_sm)); \
         kern<<<unsigned(grid), TW_THREADS, smem, stream>>>(p);                                                      \
     } while(0)
-    if(cfg.k != 16)   TW_LAUNCH(false, 0);
-    else if(mh == 1)  TW_LAUNCH(true, 1);
-    else if(mh == 2)  TW_LAUNCH(true, 2);
-    else              TW_LAUNCH(true, 0);
+    (void)mh;
+    if(cfg.k != 16)   TW_LAUNCH(false, 0, 0);
+    else if(cef == 1) TW_LAUNCH(true, 0, 1);
+    else if(cef == 2) TW_LAUNCH(true, 0, 2);
+    else if(cef == 0) TW_LAUNCH(true, 0, 0);
+    else              TW_LAUNCH(true, 0, 3);
 #undef TW_LAUNCH
     c->launches++;
     MCG_CUDA(cudaGetLastError());

@@ -53,6 +53,31 @@ __global__ void __launch_bounds__(256) probe(uint32_t* out, uint32_t seed, uint3
                 v = (v | x[(i + 3) % ILP]) ^ (x[(i + 5) % ILP] & 0x33u);
             } else if(V == 8) {     // mixed: 1 LOP3 + 1 IMAD
                 v = (v ^ x[(i + 1) % ILP]) * 0x45d9f3bu + x[(i + 2) % ILP];
+            } else if(V >= 10 && V <= 13) {   // 6 independent-ish LOP3 + FMA-pipe candidates
+                uint32_t a = x[(i + 1) % ILP], b = x[(i + 2) % ILP], c = x[(i + 3) % ILP];
+                uint32_t l = (v ^ a) & (b | 0x55u);
+                l = (l | c) ^ (a & 0x33u);
+                l = (l ^ b) | (c & 0x0Fu);
+                uint32_t h = 0;
+                if(V == 10) {
+                    uint32_t h1, h2;
+                    asm("mul.hi.u32 %0, %1, %2;" : "=r"(h1) : "r"(a), "r"(c65536));
+                    asm("mul.hi.u32 %0, %1, %2;" : "=r"(h2) : "r"(b), "r"(c65536));
+                    h = h1 + h2;
+                } else if(V == 12) {
+                    unsigned long long d1, d2;
+                    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(d1) : "r"(a), "r"(one), "l"((unsigned long long)c << 7));
+                    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(d2) : "r"(b), "r"(one), "l"((unsigned long long)a << 9));
+                    h = uint32_t(d1 >> 32) + uint32_t(d2 >> 32);
+                } else if(V == 13) {
+                    uint32_t h1, h2, h3, h4;
+                    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(h1) : "r"(a), "r"(c65536), "r"(b));
+                    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(h2) : "r"(b), "r"(m1), "r"(c));
+                    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(h3) : "r"(c), "r"(c65536), "r"(a));
+                    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(h4) : "r"(h1), "r"(m1), "r"(h2));
+                    h = h3 + h4;
+                }
+                v = l + h;
             } else if(V == 9) {     // funnel via IMAD.HI + IMAD: f = A0*4^r + hi(A1*4^r)
                 uint32_t h;
                 asm("mul.hi.u32 %0, %1, %2;" : "=r"(h) : "r"(x[(i + 1) % ILP]), "r"(c65536));
@@ -98,6 +123,10 @@ int main()
     run<7>("LOP3 x2", 2, d);
     run<8>("LOP3 + IMAD", 2, d);
     run<9>("funnel via IMAD.HI + IMAD", 2, d);
+    run<11>("6 LOP3 (+add)", 7, d);
+    run<10>("6 LOP3 + 2 IMAD.HI (+2 add)", 10, d);
+    run<12>("6 LOP3 + 2 IMAD.WIDE (+adds)", 10, d);
+    run<13>("6 LOP3 + 4 IMAD (+2 add)", 12, d);
     cudaError_t e = cudaDeviceSynchronize();
     printf("%s\n", cudaGetErrorString(e));
     return 0;
