@@ -304,10 +304,10 @@ def run_mcgpu(args):
                 "steps": args.e2e_steps, "api": "mcg_sketch_windows (pinned host buffers)"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "peak_source": peak_src, "kernel": "mcg::sketch_kernel",
+                     "traffic": traffic, "peak_source": peak_src, "kernel": "mcg::sketch_tpw_kernel",
                      "algorithmic_bytes_per_bp": ALG_BYTES_PER_BP,
-                     "note": "integer-issue bound kernel (see profiles/): HBM fraction is reported as required, "
-                             "issue-slot utilisation is the binding roofline"},
+                     "note": "instruction-throughput bound kernel (ncu: ALU pipe 86 %, issue slots 79 % busy, see profiles/): "
+                             "the HBM fraction is reported as required, integer issue is the binding limit"},
     }
 
     # ---- extras: build + query of the same path

@@ -2,20 +2,24 @@
 // Same contract as sketch.cu (bit-exact with dna_encoding.h:261-348,114-121,189-197,
 // hash_int.h:40-45, hash_dna.h:115-152).
 //
-// A warp owns tiles of 32 consecutive windows, one window per lane:
+// A warp owns tiles of 32 consecutive windows, one window per lane.  Tiles are handed out by
+// an atomic counter (warps the scheduler favours take more tiles).  Per tile:
 //   (1) the tile's contiguous byte span arrives through TMA (cp.async.bulk + mbarrier) and is
 //       packed by the whole warp to 2 bits/base + 1 ambiguity bit/base (shared memory);
-//       the TMA copy of the warp's next tile is issued as soon as the raw bytes are consumed;
 //   (2) every lane walks the k-mers of ITS window: 16 k-mers per step out of two aligned
 //       packed words (compile-time funnel shifts), canonical k-mer, hash, and keeps the hashes
 //       below a threshold with ~sketchlen+15 expected survivors in its own shared-memory column
-//       (slot i of lane l lives at word i*32+l: conflict-free, no ballots, no shuffles);
-//   (3) every lane sorts its <= 48 survivors in REGISTERS with a fixed compare-exchange
-//       network (three 16-input networks + two bottom-half bitonic merges) and stores its
-//       16 smallest.  A window whose survivors are too few / too many / not distinct is redone
-//       exactly by the whole warp (rare).
-// Against the warp-per-window kernel this removes the 15-stage shuffle network per window:
-// ~75 instead of ~325 warp instructions per 128-base window.
+//       (slot i of lane l lives at word i*32+l: conflict-free, no ballots, no shuffles; the
+//       columns reuse the raw-byte buffer, which is dead after packing);
+//   (3) every lane reduces its column in REGISTERS, 16 survivors at a time: a 60-comparator
+//       16-input sorting network, then "16 smallest of two sorted 16s" (one min layer + a
+//       bitonic merge).  The max of each compare-exchange is a + b - min(a, b) as two IMADs:
+//       the FMA pipe idles while the ALU pipe (shifts, logic, min, compares) is the limit;
+//   (4) the warp's next tile was resolved in three steps spread over (1)-(3) so that no
+//       global-memory latency is waited for; its TMA copy starts as soon as the columns are
+//       consumed and overlaps the stores and the other warps.
+// A window whose survivors are too few / too many / not distinct is redone exactly by the whole
+// warp (rare).  ~105 warp instructions per 128-base window (warp-per-window kernel: ~325).
 #include "sketch_dev.cuh"
 
 #include <algorithm>
@@ -65,35 +69,19 @@ __device__ __forceinline__ void tw_ce(uint32_t& a, uint32_t& b, uint32_t one, ui
     }
     a = lo;
 }
-#define SN_CE(i, j) tw_ce<(CEF & 1) != 0>(v[SN_B + (i)], v[SN_B + (j)], one, m1);
+#define SN_CE(i, j) tw_ce<CEF>(v[SN_B + (i)], v[SN_B + (j)], one, m1);
 
 __device__ __forceinline__ void st_shared_u32(uint32_t addr, uint32_t v)
 {
     asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
 
-// x >> 16 as a multiply-high by 65536 held in a register: IMAD.HI runs on the FMA pipe, which
-// idles while the ALU pipe (shifts, logic, min/max, compares) limits this kernel
-__device__ __forceinline__ uint32_t shr16_fma(uint32_t x, uint32_t c65536)
-{
-    uint32_t h;
-    asm("mul.hi.u32 %0, %1, %2;" : "=r"(h) : "r"(x), "r"(c65536));
-    return h;
-}
-
-template<int MH>
-__device__ __forceinline__ uint32_t tw_head(uint32_t x, uint32_t c65536)
-{
-    x = ((MH >= 1 ? shr16_fma(x, c65536) : (x >> 16)) ^ x) * 0x45d9f3bu;
-    x = ((MH >= 2 ? shr16_fma(x, c65536) : (x >> 16)) ^ x) * 0x45d9f3bu;
-    return x;
-}
-
-// 16 unambiguous k-mers of one lane's window: starts 0..15 of the aligned word pair (A0,A1);
-// R = rc16(A).  Survivors of the threshold go to the lane's column at shared address la.
-template<bool K16, int MH, bool CHECK>
+// 16 k-mers of one lane's window: starts 0..15 of the aligned word pair (A0,A1); R = rc16(A);
+// a32 = ambiguity bits of the 32 bases (CHECK).  Survivors of the threshold go to the lane's
+// column at shared address la.
+template<bool K16, bool CHECK>
 __device__ __forceinline__ void tw_group_fast(uint32_t A0, uint32_t A1, uint32_t R0, uint32_t R1, uint32_t a32, int k, uint32_t T,
-                                              uint32_t c65536, uint32_t& la)
+                                              uint32_t& la)
 {
     const int fsh = 32 - 2 * k;
     const uint32_t kmask = 0xFFFFFFFFu >> fsh;
@@ -103,7 +91,7 @@ __device__ __forceinline__ void tw_group_fast(uint32_t A0, uint32_t A1, uint32_t
         uint32_t f = r ? __funnelshift_l(A1, A0, 2 * r) : A0;
         uint32_t c = r ? __funnelshift_r(R0, R1, 2 * r) : R0;
         if(!K16) { f >>= fsh; c &= kmask; }
-        uint32_t y = tw_head<MH>(min(f, c), c65536);
+        uint32_t y = tmh_head(min(f, c));
         if(CHECK) { if(((a32 << r) >> ash) != 0u) y = NOH; }     // NOH >= every threshold
         if(y < T) { st_shared_u32(la, y); la += 128u; }
     }
@@ -245,7 +233,7 @@ __device__ __forceinline__ TwTile tw_resolve(const SketchParams& p, uint64_t til
     return t;
 }
 
-template<bool K16, int MH, int CEF>
+template<bool K16, bool CEF>
 __global__ void __launch_bounds__(TW_THREADS, 5)
 sketch_tpw_kernel(const SketchParams p)
 {
@@ -262,8 +250,7 @@ sketch_tpw_kernel(const SketchParams p)
     uint32_t* tmp  = reinterpret_cast<uint32_t*>(pk2 + ngc + 2);             // [32]
     const uint32_t ntiles = uint32_t((p.nwin - p.win_lo + TW_WPT - 1) / TW_WPT);
     const int k = p.k;
-    const uint32_t c65536 = p.c65536;
-    const uint32_t one = c65536 >> 16, m1 = 0u - one;      // opaque 1 and -1
+    const uint32_t one = p.c65536 >> 16, m1 = 0u - one;      // 1 and -1, opaque to the compiler
 
     // starts the TMA copy of a tile's bytes (the candidate columns of the previous tile must be consumed)
     auto tma_issue = [&](const TwTile& t) {
@@ -332,8 +319,6 @@ sketch_tpw_kernel(const SketchParams p)
         const int sp = min(p.s, max(nk, 0));
         uint32_t T = cur.T;
         const bool thr = T != 0u;
-#pragma unroll
-        for(int i = 0; i < TW_LCAP; ++i) st_shared_u32(la0 + uint32_t(i) * 128u, NOH);
         uint32_t la = la0;
         bool ovf = false;
         if(nk > 0) {
@@ -353,8 +338,8 @@ sketch_tpw_kernel(const SketchParams p)
                 const uint32_t R1 = rc16(A1);
                 const uint32_t a32 = (B0 << 16) | B1;
                 if(la > lguard) { ovf = true; T = 0u; }
-                if(a32 == 0u) tw_group_fast<K16, MH, false>(A0, A1, R0, R1, a32, k, T, c65536, la);
-                else          tw_group_fast<K16, MH, true>(A0, A1, R0, R1, a32, k, T, c65536, la);
+                if(a32 == 0u) tw_group_fast<K16, false>(A0, A1, R0, R1, a32, k, T, la);
+                else          tw_group_fast<K16, true>(A0, A1, R0, R1, a32, k, T, la);
                 A0 = A1; B0 = B1; R0 = R1; w1 = w2;
             }
             left -= nfull << 4;
@@ -369,6 +354,13 @@ sketch_tpw_kernel(const SketchParams p)
             }
         }
         const int cnt = int(la - la0) >> 7;
+        // pad the column with the sentinel up to the next multiple of 16 (the sorter reads blocks of 16)
+        if(la <= lguard) {
+#pragma unroll
+            for(int i = 0; i < 16; ++i) st_shared_u32(la + uint32_t(i) * 128u, NOH);
+        } else {
+            for(uint32_t a = la; a < lend; a += 128u) st_shared_u32(a, NOH);
+        }
 
         // ---- (3) register network, 16 survivors at a time: 16-input sort, then the 16 smallest
         //      of (best, block) by one min layer + a bitonic merge
@@ -398,7 +390,7 @@ sketch_tpw_kernel(const SketchParams p)
             for(int d = 8; d > 0; d >>= 1) {
 #pragma unroll
                 for(int i = 0; i < 16; ++i) {
-                    if((i & d) == 0) tw_ce<(CEF & 2) != 0>(best[i], best[i + d], one, m1);
+                    if((i & d) == 0) tw_ce<CEF>(best[i], best[i + d], one, m1);
                 }
             }
         }
@@ -489,14 +481,12 @@ int tpw_launch(mcg_ctx* c, SketchParams& p, const mcg_sketch_cfg& cfg, uint64_t 
         p.nk_full = nk;
         p.thr_full = tw_threshold(nk, sp);
     }
-    static int mh = -1;
-    if(mh < 0) { const char* e = getenv("MCG_SK_MH"); mh = e ? atoi(e) : 0; }
-    p.c65536 = 65536u;
     static int cef = -1;
-    if(cef < 0) { const char* e = getenv("MCG_SK_CEF"); cef = e ? atoi(e) : 3; }
-#define TW_LAUNCH(K16, MH, CEF)                                                                                     \
+    if(cef < 0) { const char* e = getenv("MCG_SK_CEF"); cef = e ? atoi(e) : 1; }
+    p.c65536 = 65536u;
+#define TW_LAUNCH(K16, CEF)                                                                                         \
     do {                                                                                                            \
-        auto kern = sketch_tpw_kernel<K16, MH, CEF>;                                                                       \
+        auto kern = sketch_tpw_kernel<K16, CEF>;                                                                    \
         if(smem > 48 * 1024) MCG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))); \
         int per_sm = 1;                                                                                             \
         MCG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TW_THREADS, smem));                   \
@@ -504,12 +494,9 @@ int tpw_launch(mcg_ctx* c, SketchParams& p, const mcg_sketch_cfg& cfg, uint64_t 
         const uint64_t grid = std::min<uint64_t>((nblocks + TW_WARPS - 1) / TW_WARPS, uint64_t(kNumSMs) * uint64_t(per_sm)); \
         kern<<<unsigned(grid), TW_THREADS, smem, stream>>>(p);                                                      \
     } while(0)
-    (void)mh;
-    if(cfg.k != 16)   TW_LAUNCH(false, 0, 0);
-    else if(cef == 1) TW_LAUNCH(true, 0, 1);
-    else if(cef == 2) TW_LAUNCH(true, 0, 2);
-    else if(cef == 0) TW_LAUNCH(true, 0, 0);
-    else              TW_LAUNCH(true, 0, 3);
+    if(cfg.k != 16)   TW_LAUNCH(false, true);
+    else if(cef == 0) TW_LAUNCH(true, false);
+    else              TW_LAUNCH(true, true);
 #undef TW_LAUNCH
     c->launches++;
     MCG_CUDA(cudaGetLastError());
