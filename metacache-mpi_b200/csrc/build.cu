@@ -11,8 +11,10 @@
 // HBM layout of a finalized shard:
 //   keys [nkeys]  uint32 ascending        sizes[nkeys] uint8 (0 = emptied "dead" key)
 //   offs [nkeys+1] uint64 (CSR)           locs [nlocs] uint64 = tgt << 32 | win
-//   table[cap]    uint4 {key, size, off_lo, off_hi}: open addressing, linear probing,
-//                 slot = umulhi(slot_mix(key), cap), empty key = 0xFFFFFFFF
+//   table[cap]    32-byte slots = one DRAM sector {key, size, off:u64, loc0:u64, loc1:u64}: open
+//                 addressing, linear probing, slot = umulhi(slot_mix(key), cap), empty key =
+//                 0xFFFFFFFF.  The first two locations of a list sit in the slot itself, so a
+//                 probe of the (dominant) lists of length <= 2 needs no second memory access.
 #include "common.cuh"
 
 #include <algorithm>
@@ -26,7 +28,7 @@ int copy_out(mcg_ctx* c, void* h, const void* d, size_t bytes);
 int exclusive_scan_u32_to_u32(mcg_ctx* c, const uint32_t* d_in, uint32_t* d_out, uint64_t n);
 
 constexpr uint32_t EMPTY_KEY = 0xFFFFFFFFu;
-constexpr double TABLE_LOAD = 0.6;
+constexpr double TABLE_LOAD = 0.5;
 
 // first index with sorted_keys[i] == 0xFFFFFFFF (padding slots sort to the end)
 __global__ void count_valid_kernel(const uint32_t* keys, uint64_t n, uint64_t* out)
@@ -95,8 +97,8 @@ __global__ void emit_locations_kernel(const uint32_t* keys, const uint32_t* slot
 
 __global__ void table_clear_kernel(uint4* table, uint64_t cap)
 {
-    const uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
-    if(i < cap) table[i] = make_uint4(EMPTY_KEY, 0u, 0u, 0u);
+    const uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;      // one uint4 = half a slot
+    if(i < 2 * cap) table[i] = (i & 1) ? make_uint4(0u, 0u, 0u, 0u) : make_uint4(EMPTY_KEY, 0u, 0u, 0u);
 }
 
 __device__ __forceinline__ uint64_t table_slot(uint32_t key, uint64_t cap)
@@ -106,19 +108,22 @@ __device__ __forceinline__ uint64_t table_slot(uint32_t key, uint64_t cap)
 }
 
 __global__ void table_insert_kernel(uint4* table, uint64_t cap, const uint32_t* ukeys, const uint8_t* sizes,
-                                    const uint64_t* offs, uint32_t nkeys)
+                                    const uint64_t* offs, const uint64_t* locs, uint32_t nkeys)
 {
     const uint64_t j = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
     if(j >= nkeys) return;
     const uint32_t key = ukeys[j];
+    const uint32_t size = sizes[j];
+    const uint64_t o = offs[j];
+    const uint64_t l0 = size > 0 ? locs[o] : 0ull, l1 = size > 1 ? locs[o + 1] : 0ull;
     uint64_t s = table_slot(key, cap);
     for(;;) {
-        const uint32_t old = atomicCAS(&table[s].x, EMPTY_KEY, key);
+        const uint32_t old = atomicCAS(&table[2 * s].x, EMPTY_KEY, key);
         if(old == EMPTY_KEY) {
-            const uint64_t o = offs[j];
-            table[s].y = sizes[j];
-            table[s].z = uint32_t(o);
-            table[s].w = uint32_t(o >> 32);
+            table[2 * s].y = size;
+            table[2 * s].z = uint32_t(o);
+            table[2 * s].w = uint32_t(o >> 32);
+            table[2 * s + 1] = make_uint4(uint32_t(l0), uint32_t(l0 >> 32), uint32_t(l1), uint32_t(l1 >> 32));
             return;
         }
         if(++s == cap) s = 0;
@@ -142,8 +147,8 @@ __global__ void remove_keys_kernel(uint4* table, uint64_t cap, const uint32_t* u
     sizes[lo] = 0;
     uint64_t s = table_slot(key, cap);
     for(;;) {
-        const uint32_t k = table[s].x;
-        if(k == key) { table[s].y = 0; return; }
+        const uint32_t k = table[2 * s].x;
+        if(k == key) { table[2 * s].y = 0; return; }
         if(k == EMPTY_KEY) return;
         if(++s == cap) s = 0;
     }
@@ -175,14 +180,14 @@ static int build_table(mcg_db* db)
 {
     mcg_ctx* c = db->ctx;
     uint64_t cap = uint64_t(double(db->nkeys) / TABLE_LOAD) + 64;
-    MCG_TRY(db->table.reserve(cap * sizeof(uint4)));
+    MCG_TRY(db->table.reserve(cap * 2 * sizeof(uint4)));
     db->table_cap = cap;
-    table_clear_kernel<<<grid_for(cap), 256, 0, c->stream>>>(db->table.as<uint4>(), cap);
+    table_clear_kernel<<<grid_for(2 * cap), 256, 0, c->stream>>>(db->table.as<uint4>(), cap);
     c->launches++;
     if(db->nkeys > 0) {
         table_insert_kernel<<<grid_for(db->nkeys), 256, 0, c->stream>>>(
             db->table.as<uint4>(), cap, db->keys.as<uint32_t>(), db->sizes.as<uint8_t>(), db->offs.as<uint64_t>(),
-            uint32_t(db->nkeys));
+            db->locs.as<uint64_t>(), uint32_t(db->nkeys));
         c->launches++;
     }
     MCG_CUDA(cudaGetLastError());

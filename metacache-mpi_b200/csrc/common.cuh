@@ -93,7 +93,7 @@ struct mcg_db {
     // finalized: CSR + open-addressing table
     mcg::DevBuf keys, offs, sizes;    // unique keys ascending, uint64 offsets, uint8 sizes
     mcg::DevBuf locs;                 // uint64 (tgt << 32 | win)
-    mcg::DevBuf table;                // uint4 slots {key, size, off_lo, off_hi}
+    mcg::DevBuf table;                // 32-byte slots {key, size, off:u64, loc0:u64, loc1:u64} (build.cu)
     uint64_t nkeys = 0, nlocs = 0, table_cap = 0;
     // per-read match keys: (tgt << wbits) | win; 32-bit when target and window ids fit together
     int wbits = 32;

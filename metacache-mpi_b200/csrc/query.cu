@@ -71,7 +71,7 @@ q_find_kernel(const uint32_t* __restrict__ feat, uint64_t nslots, const uint4* _
     if(f != EMPTY_KEY) {
         uint64_t s = table_slot(f, cap);
         for(;;) {
-            const uint4 e = __ldg(&table[s]);
+            const uint4 e = __ldg(&table[2 * s]);
             if(e.x == f) { len = e.y; off = uint64_t(e.z) | (uint64_t(e.w) << 32); break; }
             if(e.x == EMPTY_KEY) break;
             if(++s == cap) s = 0;
@@ -488,20 +488,110 @@ q_cand_warp_kernel(const CandParams p)
     }
 }
 
-// Short reads, fully fused: one warp probes the read's features, gathers the location lists straight
-// into its shared-memory slice, sorts them and derives the top list -- the match list never touches
-// HBM.  Reads with more than 128 feature slots or more than Q_SMALL matches are left to the staged
-// path (their features stay in `feat`; finished reads overwrite theirs with NO_FEATURE so that the
+// Short reads, fully fused: one warp probes the read's features, takes the locations out of the
+// 32-byte table slots themselves (lists of length <= 2) or gathers longer lists, sorts them in
+// registers / shared memory and derives the top list -- the match list never touches HBM.  Reads
+// with more than 128 feature slots or more than Q_FUSED matches are left to the staged path
+// (their features stay in `feat`; finished reads overwrite theirs with NO_FEATURE so that the
 // staged path skips them).
 struct FusedParams {
     uint32_t* feat;
-    const uint4* table;
+    const uint4* table;         // 32-byte slots: [2s] = {key, size, off_lo, off_hi}, [2s+1] = {loc0, loc1}
     uint64_t cap;
     const uint64_t* locs;
     int64_t n;
     uint8_t* done;
-    uint32_t* left_over;        // number of reads left to the staged path
+    uint32_t* left_over;        // [0] number of reads left to the staged path, [1] read counter (dynamic scheduling)
 };
+
+constexpr int Q_FUSED = 256;    // matches per read of the fused path
+
+// candidates.h:236-285 with the taxon already lifted to -lowest and its rank known (seq = the
+// taxon is of sequence rank: such taxa are never merged); entry i of the list lives in lane i
+__device__ __forceinline__ void warp_topk_insert_lifted(WarpTopK& L, int K, int32_t tax, uint32_t hits, bool seq, int lane)
+{
+    const bool live = lane < L.n;
+    int pos = -1;
+    if(!seq) {
+        const uint32_t hit = __ballot_sync(0xFFFFFFFFu, live && L.tax == tax);
+        if(hit) pos = __ffs(int(hit)) - 1;
+    }
+    const int32_t up_tax = __shfl_up_sync(0xFFFFFFFFu, L.tax, 1);
+    const uint32_t up_hits = __shfl_up_sync(0xFFFFFFFFu, L.hits, 1);
+    if(pos >= 0) {
+        const uint32_t old = __shfl_sync(0xFFFFFFFFu, L.hits, pos);
+        const uint32_t h = hits > old ? hits : old;
+        const int j = __popc(__ballot_sync(0xFFFFFFFFu, lane < pos && L.hits >= h));
+        if(lane > j && lane <= pos) { L.tax = up_tax; L.hits = up_hits; }
+        if(lane == j) { L.tax = tax; L.hits = h; }
+        return;
+    }
+    const int i0 = __popc(__ballot_sync(0xFFFFFFFFu, live && L.hits >= hits));      // upper bound, descending list
+    if(i0 < L.n || L.n < K) {
+        const int last = L.n < K ? L.n : K - 1;
+        if(lane > i0 && lane <= last) { L.tax = up_tax; L.hits = up_hits; }
+        if(lane == i0) { L.tax = tax; L.hits = hits; }
+        if(L.n < K) L.n++;
+    }
+}
+
+// sorted matches A[0..m) + per-element range hits Hh -> top list.  The target runs are found, their
+// maxima taken (segmented warp scan) and their taxa lifted by all lanes at once (the lineage
+// loads of all candidates are in flight together); only the order-dependent list insertion
+// (candidates.h:236-285) runs one candidate after the other, out of shared memory.
+template<class KeyT>
+__device__ __forceinline__ void toplist_from_sorted(const CandParams& p, uint32_t r, const KeyT* A, const uint32_t* Hh,
+                                                    uint32_t m, int32_t* Ct, uint32_t* Ch, int lane)
+{
+    const uint32_t ltmask = (1u << lane) - 1u;
+    uint32_t ncand = 0, carry = 0;
+    for(uint32_t b = 0; b < m; b += 32) {
+        const uint32_t i = b + lane;
+        const bool valid = i < m;
+        const uint32_t tgt = valid ? tgt_of(A[i], p.wbits) : 0xFFFFFFFFu;
+        uint32_t prev = __shfl_up_sync(0xFFFFFFFFu, tgt, 1);
+        if(lane == 0) prev = b > 0 ? tgt_of(A[b - 1], p.wbits) : 0xFFFFFFFFu;
+        const bool head = valid && (i == 0 || prev != tgt);
+        const bool tail = valid && (i + 1 == m || tgt_of(A[i + 1], p.wbits) != tgt);
+        uint32_t v = valid ? Hh[i] : 0u;
+        if(lane == 0 && !head) v = max(v, carry);
+        const uint32_t hm = __ballot_sync(0xFFFFFFFFu, head);
+        // inclusive segmented max scan: take the value d lanes down unless a run starts in between
+#pragma unroll
+        for(int d = 1; d < 32; d <<= 1) {
+            const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, v, d);
+            const uint32_t between = (hm >> (lane >= d ? lane - d + 1 : 0)) & ((1u << d) - 1u);    // heads in (lane-d, lane]
+            if(lane >= d && between == 0u) v = max(v, o);
+        }
+        carry = __shfl_sync(0xFFFFFFFFu, v, 31);
+        const uint32_t tm = __ballot_sync(0xFFFFFFFFu, tail);
+        if(tail) {
+            int32_t tax = int32_t(tgt);
+            if(p.lowest > MCG_RANK_SEQUENCE) {
+                const int32_t anc = __ldg(p.lineage + int64_t(tax) * MCG_NUM_RANKS + p.lowest);
+                if(anc >= 0) tax = anc;
+            }
+            const bool seq = __ldg(p.rank + tax) == MCG_RANK_SEQUENCE;
+            const uint32_t j = ncand + __popc(tm & ltmask);
+            Ct[j] = tax | (seq ? int32_t(0x80000000u) : 0);
+            Ch[j] = v;
+        }
+        ncand += __popc(tm);
+    }
+    __syncwarp();
+    WarpTopK L;
+    L.tax = -1; L.hits = 0; L.n = 0;
+    for(uint32_t j = 0; j < ncand; ++j) {
+        const int32_t t = Ct[j];
+        warp_topk_insert_lifted(L, p.K, t & 0x7FFFFFFF, Ch[j], t < 0, lane);
+    }
+    if(lane < p.K) {
+        p.out_tax[uint64_t(r) * p.K + lane] = lane < L.n ? L.tax : -1;
+        p.out_hits[uint64_t(r) * p.K + lane] = lane < L.n ? L.hits : 0u;
+    }
+    if(lane == 0) p.out_n[r] = L.n;
+    __syncwarp();
+}
 
 template<class KeyT>
 __global__ void __launch_bounds__(256)
@@ -509,46 +599,67 @@ q_fused_warp_kernel(const CandParams p, const FusedParams f)
 {
     extern __shared__ __align__(16) unsigned char sm[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    KeyT* A = reinterpret_cast<KeyT*>(sm) + size_t(warp) * Q_SMALL;
-    uint32_t* Hh = reinterpret_cast<uint32_t*>(sm + size_t(8) * Q_SMALL * sizeof(KeyT)) + size_t(warp) * Q_SMALL;
-    const int64_t nwarps = int64_t(gridDim.x) * 8;
-    for(int64_t r = int64_t(blockIdx.x) * 8 + warp; r < f.n; r += nwarps) {
+    // per warp: A[Q_FUSED] keys, Hh[Q_FUSED], Ct[Q_FUSED], Ch[Q_FUSED]
+    unsigned char* wbase = sm + size_t(warp) * Q_FUSED * (sizeof(KeyT) + 12);
+    KeyT* A = reinterpret_cast<KeyT*>(wbase);
+    uint32_t* Hh = reinterpret_cast<uint32_t*>(wbase + size_t(Q_FUSED) * sizeof(KeyT));
+    int32_t* Ct = reinterpret_cast<int32_t*>(Hh + Q_FUSED);
+    uint32_t* Ch = reinterpret_cast<uint32_t*>(Ct + Q_FUSED);
+    const KeyT KMAX = ~KeyT(0);
+    // reads are handed out 8 at a time by an atomic counter (their cost varies with their matches)
+    for(int64_t rr = 0;; ++rr) {
+        if((rr & 7) == 0) {
+            uint32_t b0 = 0;
+            if(lane == 0) b0 = atomicAdd(f.left_over + 1, 8u);
+            rr = int64_t(__shfl_sync(0xFFFFFFFFu, b0, 0));
+        }
+        const int64_t r = rr;
+        if((r & ~int64_t(7)) >= f.n) break;
+        if(r >= f.n) continue;
         const uint64_t s0 = uint64_t(p.W[r]) * p.s, s1 = uint64_t(p.W[r + 1]) * p.s;
         const uint32_t ns = uint32_t(s1 - s0);
         if(ns > 128) {
             if(lane == 0) { atomicAdd(f.left_over, 1u); f.done[r] = 0; }
             continue;
         }
-        // (1) probe: up to 4 independent probes per lane in flight
-        uint32_t len[4];
-        uint64_t off[4];
-        uint32_t key[4];
-#pragma unroll
-        for(int c = 0; c < 4; ++c) {
-            const uint32_t sl = uint32_t(c) * 32u + uint32_t(lane);
-            key[c] = sl < ns ? f.feat[s0 + sl] : EMPTY_KEY;
-        }
-        // first probe of all four slots in flight together; collisions continue in a (rare) loop
+        const int nc = int(ns + 31) >> 5;                 // feature slots per lane (uniform)
+        // (1) probe: every slot's sector (two 16-byte halves) in flight at once
+        uint32_t key[4], len[4];
         uint64_t slot[4];
-        uint4 ent[4];
+        uint4 q0[4], q1[4];
 #pragma unroll
         for(int c = 0; c < 4; ++c) {
-            slot[c] = table_slot(key[c], f.cap);
-            ent[c] = key[c] != EMPTY_KEY ? __ldg(&f.table[slot[c]]) : make_uint4(EMPTY_KEY, 0u, 0u, 0u);
+            key[c] = EMPTY_KEY;
+            if(c < nc) {
+                const uint32_t sl = uint32_t(c) * 32u + uint32_t(lane);
+                if(sl < ns) key[c] = f.feat[s0 + sl];
+            }
         }
 #pragma unroll
         for(int c = 0; c < 4; ++c) {
-            len[c] = 0; off[c] = 0;
-            uint4 e = ent[c];
-            uint64_t s = slot[c];
-            while(e.x != key[c] && e.x != EMPTY_KEY) {
-                if(++s == f.cap) s = 0;
-                e = __ldg(&f.table[s]);
+            q0[c] = make_uint4(EMPTY_KEY, 0u, 0u, 0u);
+            q1[c] = make_uint4(0u, 0u, 0u, 0u);
+            if(c < nc && key[c] != EMPTY_KEY) {
+                slot[c] = table_slot(key[c], f.cap);
+                q0[c] = __ldg(&f.table[2 * slot[c]]);
+                q1[c] = __ldg(&f.table[2 * slot[c] + 1]);
             }
-            if(e.x == key[c] && key[c] != EMPTY_KEY) { len[c] = e.y; off[c] = uint64_t(e.z) | (uint64_t(e.w) << 32); }
+        }
+        uint32_t tot = 0;
+#pragma unroll
+        for(int c = 0; c < 4; ++c) {
+            len[c] = 0;
+            if(c < nc) {
+                while(q0[c].x != key[c] && q0[c].x != EMPTY_KEY) {          // collision: next slot
+                    if(++slot[c] == f.cap) slot[c] = 0;
+                    q0[c] = __ldg(&f.table[2 * slot[c]]);
+                    q1[c] = __ldg(&f.table[2 * slot[c] + 1]);
+                }
+                if(q0[c].x == key[c] && key[c] != EMPTY_KEY) len[c] = q0[c].y;
+                tot += len[c];
+            }
         }
         // (2) positions: exclusive scan of the per-lane totals
-        const uint32_t tot = len[0] + len[1] + len[2] + len[3];
         uint32_t inc = tot;
 #pragma unroll
         for(int d = 1; d < 32; d <<= 1) {
@@ -556,7 +667,7 @@ q_fused_warp_kernel(const CandParams p, const FusedParams f)
             if(lane >= d) inc += o;
         }
         const uint32_t m = __shfl_sync(0xFFFFFFFFu, inc, 31);
-        if(m > Q_SMALL) {
+        if(m > Q_FUSED) {
             if(lane == 0) { atomicAdd(f.left_over, 1u); f.done[r] = 0; }
             continue;
         }
@@ -564,39 +675,58 @@ q_fused_warp_kernel(const CandParams p, const FusedParams f)
 #pragma unroll
         for(int c = 0; c < 4; ++c) {
             const uint32_t sl = uint32_t(c) * 32u + uint32_t(lane);
-            if(sl < ns) f.feat[s0 + sl] = EMPTY_KEY;
+            if(c < nc && sl < ns) f.feat[s0 + sl] = EMPTY_KEY;
         }
         if(lane == 0) f.done[r] = 1;
         if(m == 0) {
             if(lane == 0) p.out_n[r] = 0;
             continue;
         }
-        // (3) gather into shared memory: short lists by their own lane, long ones by the whole warp
+        // (3) matches into shared memory: lists of <= 2 straight from the slot, longer ones gathered
         uint32_t pos = inc - tot;
-        uint64_t first[4];
-#pragma unroll
-        for(int c = 0; c < 4; ++c) first[c] = len[c] > 0 ? f.locs[off[c]] : 0ull;
 #pragma unroll
         for(int c = 0; c < 4; ++c) {
-            const uint32_t L = len[c];
-            if(L > 0 && L <= 4) {
-                A[pos] = make_key<KeyT>(first[c], p.wbits);
-                for(uint32_t t = 1; t < L; ++t) A[pos + t] = make_key<KeyT>(f.locs[off[c] + t], p.wbits);
+            if(c < nc) {
+                const uint32_t L = len[c];
+                if(L >= 1 && L <= 2) {
+                    A[pos] = make_key<KeyT>(uint64_t(q1[c].x) | (uint64_t(q1[c].y) << 32), p.wbits);
+                    if(L == 2) A[pos + 1] = make_key<KeyT>(uint64_t(q1[c].z) | (uint64_t(q1[c].w) << 32), p.wbits);
+                }
+                uint32_t big = __ballot_sync(0xFFFFFFFFu, L > 2);
+                while(big) {
+                    const int src = __ffs(int(big)) - 1;
+                    big &= big - 1;
+                    const uint32_t Ls = __shfl_sync(0xFFFFFFFFu, L, src);
+                    const uint64_t Os = __shfl_sync(0xFFFFFFFFu, uint64_t(q0[c].z) | (uint64_t(q0[c].w) << 32), src);
+                    const uint32_t Ps = __shfl_sync(0xFFFFFFFFu, pos, src);
+                    for(uint32_t t = lane; t < Ls; t += 32) A[Ps + t] = make_key<KeyT>(f.locs[Os + t], p.wbits);
+                }
+                pos += L;
             }
-            uint32_t big = __ballot_sync(0xFFFFFFFFu, L > 4);
-            while(big) {
-                const int src = __ffs(int(big)) - 1;
-                big &= big - 1;
-                const uint32_t Ls = __shfl_sync(0xFFFFFFFFu, L, src);
-                const uint64_t Os = __shfl_sync(0xFFFFFFFFu, off[c], src);
-                const uint32_t Ps = __shfl_sync(0xFFFFFFFFu, pos, src);
-                for(uint32_t t = lane; t < Ls; t += 32) A[Ps + t] = make_key<KeyT>(f.locs[Os + t], p.wbits);
-            }
-            pos += L;
         }
         __syncwarp();
-        // (4) sort + window ranges + top list
-        process_read_warp<KeyT>(p, uint32_t(r), A, Hh, m, A, lane);
+        // (4) sort by (tgt, win)
+        if(m <= 32) {
+            KeyT a = lane < int(m) ? A[lane] : KMAX;
+            __syncwarp();
+            a = wsort32(a, lane);
+            A[lane] = a;
+        } else if(m <= 64) {
+            KeyT a = A[lane];
+            KeyT b2 = lane + 32 < int(m) ? A[lane + 32] : KMAX;
+            __syncwarp();
+            wsort64(a, b2, lane);
+            A[lane] = a;
+            A[lane + 32] = b2;
+        } else {
+            bitonic_sort<true>(A, m, lane, 32);
+        }
+        __syncwarp();
+        // (5) window ranges + top list
+        const uint32_t numwin = num_windows_in_range(p, uint32_t(r));
+        for(uint32_t i = lane; i < m; i += 32) Hh[i] = hits_ending_at(A, i, numwin, p.wbits);
+        __syncwarp();
+        toplist_from_sorted<KeyT>(p, uint32_t(r), A, Hh, m, Ct, Ch, lane);
     }
 }
 
@@ -924,21 +1054,25 @@ int query_batch_dev(mcg_db* db, const mcg_query_opts* o,
         MCG_TRY(c->q_rinfo.reserve(64));
         MCG_TRY(c->q_done.reserve(size_t(n) + 16));
         uint32_t* left = c->q_rinfo.as<uint32_t>() + 8;
-        MCG_CUDA(cudaMemsetAsync(left, 0, 4, c->stream));
+        MCG_CUDA(cudaMemsetAsync(left, 0, 8, c->stream));
         CandParams p;
         fill_cand_params(db, o, doffs1, d2 ? doffs2 : nullptr, d_out_tax, d_out_hits, d_out_n, 0, &p);
         FusedParams f;
         f.feat = c->q_feat.as<uint32_t>(); f.table = db->table.as<uint4>(); f.cap = db->table_cap;
         f.locs = db->locs.as<uint64_t>(); f.n = n; f.done = c->q_done.as<uint8_t>(); f.left_over = left;
-        const unsigned g = unsigned(std::min<uint64_t>(uint64_t(n + 7) / 8, uint64_t(kNumSMs) * 8));
         const int ksz = db->key32 ? 4 : 8;
         static bool configured = false;
+        static int per_sm32 = 1, per_sm64 = 1;
         if(!configured) {
-            MCG_CUDA(cudaFuncSetAttribute(q_fused_warp_kernel<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * Q_SMALL * 12));
+            MCG_CUDA(cudaFuncSetAttribute(q_fused_warp_kernel<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * Q_FUSED * 20));
+            MCG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm32, q_fused_warp_kernel<uint32_t>, 256, 8 * Q_FUSED * 16));
+            MCG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm64, q_fused_warp_kernel<uint64_t>, 256, 8 * Q_FUSED * 20));
             configured = true;
         }
-        if(db->key32) q_fused_warp_kernel<uint32_t><<<g, 256, 8 * Q_SMALL * (ksz + 4), c->stream>>>(p, f);
-        else          q_fused_warp_kernel<uint64_t><<<g, 256, 8 * Q_SMALL * (ksz + 4), c->stream>>>(p, f);
+        const int per_sm = std::max(1, db->key32 ? per_sm32 : per_sm64);
+        const unsigned g = unsigned(std::min<uint64_t>(uint64_t(n + 63) / 64, uint64_t(kNumSMs) * uint64_t(per_sm)));
+        if(db->key32) q_fused_warp_kernel<uint32_t><<<g, 256, 8 * Q_FUSED * (ksz + 12), c->stream>>>(p, f);
+        else          q_fused_warp_kernel<uint64_t><<<g, 256, 8 * Q_FUSED * (ksz + 12), c->stream>>>(p, f);
         c->launches++;
         uint32_t h_left = 0;
         MCG_CUDA(cudaMemcpyAsync(&h_left, left, 4, cudaMemcpyDeviceToHost, c->stream));
