@@ -11,10 +11,10 @@
 // HBM layout of a finalized shard:
 //   keys [nkeys]  uint32 ascending        sizes[nkeys] uint8 (0 = emptied "dead" key)
 //   offs [nkeys+1] uint64 (CSR)           locs [nlocs] uint64 = tgt << 32 | win
-//   table[cap]    32-byte slots = one DRAM sector {key, size, off:u64, loc0:u64, loc1:u64}: open
-//                 addressing, linear probing, slot = umulhi(slot_mix(key), cap), empty key =
-//                 0xFFFFFFFF.  The first two locations of a list sit in the slot itself, so a
-//                 probe of the (dominant) lists of length <= 2 needs no second memory access.
+//   table[nbuckets] 128-byte buckets of 4 slots {key, size, off, loc0, loc1} (layout and probe
+//                 rule: common.cuh, "feature table"); the first two locations of a list sit in
+//                 the bucket line itself, so the (dominant) lists of length <= 2 need no second
+//                 memory access at query time.
 #include "common.cuh"
 
 #include <algorithm>
@@ -28,7 +28,7 @@ int copy_out(mcg_ctx* c, void* h, const void* d, size_t bytes);
 int exclusive_scan_u32_to_u32(mcg_ctx* c, const uint32_t* d_in, uint32_t* d_out, uint64_t n);
 
 constexpr uint32_t EMPTY_KEY = 0xFFFFFFFFu;
-constexpr double TABLE_LOAD = 0.5;
+constexpr double TABLE_LOAD = 0.5;       // keys per slot
 
 // first index with sorted_keys[i] == 0xFFFFFFFF (padding slots sort to the end)
 __global__ void count_valid_kernel(const uint32_t* keys, uint64_t n, uint64_t* out)
@@ -95,19 +95,13 @@ __global__ void emit_locations_kernel(const uint32_t* keys, const uint32_t* slot
     locs[offs[j] + r] = (uint64_t(tgt_id[lo]) << 32) | win;
 }
 
-__global__ void table_clear_kernel(uint4* table, uint64_t cap)
+__global__ void table_clear_kernel(uint4* table, uint64_t nbuckets)
 {
-    const uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;      // one uint4 = half a slot
-    if(i < 2 * cap) table[i] = (i & 1) ? make_uint4(0u, 0u, 0u, 0u) : make_uint4(EMPTY_KEY, 0u, 0u, 0u);
+    const uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;      // one uint4 = an eighth of a bucket
+    if(i < 8 * nbuckets) table[i] = (i & 7) ? make_uint4(0u, 0u, 0u, 0u) : make_uint4(EMPTY_KEY, EMPTY_KEY, EMPTY_KEY, EMPTY_KEY);
 }
 
-__device__ __forceinline__ uint64_t table_slot(uint32_t key, uint64_t cap)
-{
-    // cap < 2^40: two-step multiply-high keeps all 32 hash bits in play
-    return (uint64_t(slot_mix(key)) * cap) >> 32;
-}
-
-__global__ void table_insert_kernel(uint4* table, uint64_t cap, const uint32_t* ukeys, const uint8_t* sizes,
+__global__ void table_insert_kernel(uint32_t* table, uint32_t nbuckets, const uint32_t* ukeys, const uint8_t* sizes,
                                     const uint64_t* offs, const uint64_t* locs, uint32_t nkeys)
 {
     const uint64_t j = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
@@ -116,22 +110,23 @@ __global__ void table_insert_kernel(uint4* table, uint64_t cap, const uint32_t* 
     const uint32_t size = sizes[j];
     const uint64_t o = offs[j];
     const uint64_t l0 = size > 0 ? locs[o] : 0ull, l1 = size > 1 ? locs[o + 1] : 0ull;
-    uint64_t s = table_slot(key, cap);
+    uint32_t b = table_bucket(key, nbuckets);
     for(;;) {
-        const uint32_t old = atomicCAS(&table[2 * s].x, EMPTY_KEY, key);
-        if(old == EMPTY_KEY) {
-            table[2 * s].y = size;
-            table[2 * s].z = uint32_t(o);
-            table[2 * s].w = uint32_t(o >> 32);
-            table[2 * s + 1] = make_uint4(uint32_t(l0), uint32_t(l0 >> 32), uint32_t(l1), uint32_t(l1 >> 32));
-            return;
+        uint32_t* line = table + uint64_t(b) * TABLE_BUCKET_WORDS;
+        for(int t = 0; t < 4; ++t) {
+            if(atomicCAS(line + t, EMPTY_KEY, key) == EMPTY_KEY) {
+                atomicOr(line + 4, size << (8 * t));
+                uint64_t* pay = reinterpret_cast<uint64_t*>(line + 8 + 6 * t);
+                pay[0] = o; pay[1] = l0; pay[2] = l1;
+                return;
+            }
         }
-        if(++s == cap) s = 0;
+        if(++b == nbuckets) b = 0;
     }
 }
 
 // clear(bucket) for a list of keys: hash_multimap.h:720 -- the key stays, its list is emptied
-__global__ void remove_keys_kernel(uint4* table, uint64_t cap, const uint32_t* ukeys, uint8_t* sizes, uint32_t nkeys,
+__global__ void remove_keys_kernel(uint32_t* table, uint32_t nbuckets, const uint32_t* ukeys, uint8_t* sizes, uint32_t nkeys,
                                    const uint32_t* rem, uint64_t nrem, unsigned long long* removed)
 {
     const uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
@@ -145,12 +140,14 @@ __global__ void remove_keys_kernel(uint4* table, uint64_t cap, const uint32_t* u
     if(lo >= nkeys || ukeys[lo] != key) return;
     atomicAdd(removed, 1ull);                       // found (reference counts found keys, :410-413)
     sizes[lo] = 0;
-    uint64_t s = table_slot(key, cap);
+    uint32_t b = table_bucket(key, nbuckets);
     for(;;) {
-        const uint32_t k = table[2 * s].x;
-        if(k == key) { table[2 * s].y = 0; return; }
-        if(k == EMPTY_KEY) return;
-        if(++s == cap) s = 0;
+        uint32_t* line = table + uint64_t(b) * TABLE_BUCKET_WORDS;
+        const uint4 k4 = *reinterpret_cast<const uint4*>(line);
+        const int t = table_match(k4, key);
+        if(t >= 0) { atomicAnd(line + 4, ~(0xFFu << (8 * t))); return; }
+        if(t == -1) return;
+        if(++b == nbuckets) b = 0;
     }
 }
 
@@ -179,14 +176,15 @@ static inline unsigned grid_for(uint64_t n, int threads = 256) { return unsigned
 static int build_table(mcg_db* db)
 {
     mcg_ctx* c = db->ctx;
-    uint64_t cap = uint64_t(double(db->nkeys) / TABLE_LOAD) + 64;
-    MCG_TRY(db->table.reserve(cap * 2 * sizeof(uint4)));
+    const uint64_t cap = uint64_t(double(db->nkeys) / TABLE_LOAD / 4.0) + 16;      // buckets
+    MCG_REQUIRE(cap < (1ull << 32), "feature table too large");
+    MCG_TRY(db->table.reserve(cap * 128));
     db->table_cap = cap;
-    table_clear_kernel<<<grid_for(2 * cap), 256, 0, c->stream>>>(db->table.as<uint4>(), cap);
+    table_clear_kernel<<<grid_for(8 * cap), 256, 0, c->stream>>>(db->table.as<uint4>(), cap);
     c->launches++;
     if(db->nkeys > 0) {
         table_insert_kernel<<<grid_for(db->nkeys), 256, 0, c->stream>>>(
-            db->table.as<uint4>(), cap, db->keys.as<uint32_t>(), db->sizes.as<uint8_t>(), db->offs.as<uint64_t>(),
+            db->table.as<uint32_t>(), uint32_t(cap), db->keys.as<uint32_t>(), db->sizes.as<uint8_t>(), db->offs.as<uint64_t>(),
             db->locs.as<uint64_t>(), uint32_t(db->nkeys));
         c->launches++;
     }
@@ -324,7 +322,7 @@ int db_remove_keys_dev(mcg_db* db, const uint32_t* d_keys, uint64_t n, uint64_t*
     if(n > 0 && db->nkeys > 0) {
         MCG_TRY(c->tmp3.reserve(64));
         MCG_CUDA(cudaMemsetAsync(c->tmp3.p, 0, 8, c->stream));
-        remove_keys_kernel<<<grid_for(n), 256, 0, c->stream>>>(db->table.as<uint4>(), db->table_cap, db->keys.as<uint32_t>(),
+        remove_keys_kernel<<<grid_for(n), 256, 0, c->stream>>>(db->table.as<uint32_t>(), uint32_t(db->table_cap), db->keys.as<uint32_t>(),
                                                               db->sizes.as<uint8_t>(), uint32_t(db->nkeys), d_keys, n,
                                                               c->tmp3.as<unsigned long long>());
         c->launches++;

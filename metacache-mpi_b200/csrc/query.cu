@@ -53,14 +53,10 @@ __global__ void q_out_first2_kernel(const uint32_t* W, const uint32_t* wf1, int6
 }
 
 // ------------------------------------------------------------------ K3: find
-__device__ __forceinline__ uint64_t table_slot(uint32_t key, uint64_t cap)
-{
-    return (uint64_t(slot_mix(key)) * cap) >> 32;
-}
-
-// hash_multimap.h:779-789 / 1034-1047 find: probe until key or unused slot
+// hash_multimap.h:779-789 / 1034-1047 find, on the bucketized table (common.cuh): walk the buckets
+// from the key's home bucket until the key or a free slot shows up
 __global__ void __launch_bounds__(256)
-q_find_kernel(const uint32_t* __restrict__ feat, uint64_t nslots, const uint4* __restrict__ table, uint64_t cap,
+q_find_kernel(const uint32_t* __restrict__ feat, uint64_t nslots, const uint32_t* __restrict__ table, uint32_t nbuckets,
               uint8_t* __restrict__ flen, uint64_t* __restrict__ foff)
 {
     const uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
@@ -69,12 +65,18 @@ q_find_kernel(const uint32_t* __restrict__ feat, uint64_t nslots, const uint4* _
     uint32_t len = 0;
     uint64_t off = 0;
     if(f != EMPTY_KEY) {
-        uint64_t s = table_slot(f, cap);
+        uint32_t b = table_bucket(f, nbuckets);
         for(;;) {
-            const uint4 e = __ldg(&table[2 * s]);
-            if(e.x == f) { len = e.y; off = uint64_t(e.z) | (uint64_t(e.w) << 32); break; }
-            if(e.x == EMPTY_KEY) break;
-            if(++s == cap) s = 0;
+            const uint32_t* line = table + uint64_t(b) * TABLE_BUCKET_WORDS;
+            const uint4 k4 = __ldg(reinterpret_cast<const uint4*>(line));
+            const int t = table_match(k4, f);
+            if(t >= 0) {
+                len = (__ldg(line + 4) >> (8 * t)) & 0xFFu;
+                off = __ldg(reinterpret_cast<const uint64_t*>(line + 8 + 6 * t));
+                break;
+            }
+            if(t == -1) break;
+            if(++b == nbuckets) b = 0;
         }
     }
     flen[i] = uint8_t(len);
@@ -496,8 +498,8 @@ q_cand_warp_kernel(const CandParams p)
 // staged path skips them).
 struct FusedParams {
     uint32_t* feat;
-    const uint4* table;         // 32-byte slots: [2s] = {key, size, off_lo, off_hi}, [2s+1] = {loc0, loc1}
-    uint64_t cap;
+    const uint32_t* table;      // 128-byte buckets of 4 slots (common.cuh)
+    uint32_t nbuckets;
     const uint64_t* locs;
     int64_t n;
     uint8_t* done;
@@ -593,7 +595,7 @@ __device__ __forceinline__ void toplist_from_sorted(const CandParams& p, uint32_
     __syncwarp();
 }
 
-template<class KeyT>
+template<class KeyT, int NC>           // NC: feature slots per lane (reads with more than 32*NC slots are left over)
 __global__ void __launch_bounds__(256)
 q_fused_warp_kernel(const CandParams p, const FusedParams f)
 {
@@ -618,47 +620,65 @@ q_fused_warp_kernel(const CandParams p, const FusedParams f)
         if(r >= f.n) continue;
         const uint64_t s0 = uint64_t(p.W[r]) * p.s, s1 = uint64_t(p.W[r + 1]) * p.s;
         const uint32_t ns = uint32_t(s1 - s0);
-        if(ns > 128) {
+        if(ns > 32u * NC) {
             if(lane == 0) { atomicAdd(f.left_over, 1u); f.done[r] = 0; }
             continue;
         }
         const int nc = int(ns + 31) >> 5;                 // feature slots per lane (uniform)
-        // (1) probe: every slot's sector (two 16-byte halves) in flight at once
-        uint32_t key[4], len[4];
-        uint64_t slot[4];
-        uint4 q0[4], q1[4];
+        // (1) probe.  A pass loads the bucket line (keys + sizes) of every unresolved feature of the
+        //     lane at once; a feature leaves when its key or a free slot is found.  Passes repeat
+        //     while any lane still has a feature whose bucket was full (few: <= 2 in most reads).
+        uint32_t key[NC], len[NC], bkt[NC];
+        uint64_t off[NC], loc0[NC], loc1[NC];
+        bool pend[NC];
 #pragma unroll
-        for(int c = 0; c < 4; ++c) {
+        for(int c = 0; c < NC; ++c) {
             key[c] = EMPTY_KEY;
             if(c < nc) {
                 const uint32_t sl = uint32_t(c) * 32u + uint32_t(lane);
                 if(sl < ns) key[c] = f.feat[s0 + sl];
             }
+            pend[c] = key[c] != EMPTY_KEY;
+            bkt[c] = table_bucket(key[c], f.nbuckets);
+            len[c] = 0; off[c] = 0; loc0[c] = 0; loc1[c] = 0;
         }
+        for(;;) {
+            uint4 k4[NC];
+            uint32_t sz[NC];
 #pragma unroll
-        for(int c = 0; c < 4; ++c) {
-            q0[c] = make_uint4(EMPTY_KEY, 0u, 0u, 0u);
-            q1[c] = make_uint4(0u, 0u, 0u, 0u);
-            if(c < nc && key[c] != EMPTY_KEY) {
-                slot[c] = table_slot(key[c], f.cap);
-                q0[c] = __ldg(&f.table[2 * slot[c]]);
-                q1[c] = __ldg(&f.table[2 * slot[c] + 1]);
+            for(int c = 0; c < NC; ++c) {
+                if(c < nc && pend[c]) {
+                    const uint32_t* line = f.table + uint64_t(bkt[c]) * TABLE_BUCKET_WORDS;
+                    k4[c] = __ldg(reinterpret_cast<const uint4*>(line));
+                    sz[c] = __ldg(line + 4);
+                }
             }
+            bool again = false;
+#pragma unroll
+            for(int c = 0; c < NC; ++c) {
+                if(c < nc && pend[c]) {
+                    const int t = table_match(k4[c], key[c]);
+                    if(t >= 0) {
+                        const uint32_t L = (sz[c] >> (8 * t)) & 0xFFu;
+                        const uint64_t* pay = reinterpret_cast<const uint64_t*>(f.table + uint64_t(bkt[c]) * TABLE_BUCKET_WORDS + 8 + 6 * t);
+                        len[c] = L;
+                        if(L > 0) loc0[c] = __ldg(pay + 1);               // same line: L1 hits
+                        if(L > 1) loc1[c] = __ldg(pay + 2);
+                        if(L > 2) off[c] = __ldg(pay);
+                        pend[c] = false;
+                    } else if(t == -1) {
+                        pend[c] = false;
+                    } else {
+                        if(++bkt[c] == f.nbuckets) bkt[c] = 0;
+                        again = true;
+                    }
+                }
+            }
+            if(!__any_sync(0xFFFFFFFFu, again)) break;
         }
         uint32_t tot = 0;
 #pragma unroll
-        for(int c = 0; c < 4; ++c) {
-            len[c] = 0;
-            if(c < nc) {
-                while(q0[c].x != key[c] && q0[c].x != EMPTY_KEY) {          // collision: next slot
-                    if(++slot[c] == f.cap) slot[c] = 0;
-                    q0[c] = __ldg(&f.table[2 * slot[c]]);
-                    q1[c] = __ldg(&f.table[2 * slot[c] + 1]);
-                }
-                if(q0[c].x == key[c] && key[c] != EMPTY_KEY) len[c] = q0[c].y;
-                tot += len[c];
-            }
-        }
+        for(int c = 0; c < NC; ++c) tot += len[c];
         // (2) positions: exclusive scan of the per-lane totals
         uint32_t inc = tot;
 #pragma unroll
@@ -673,7 +693,7 @@ q_fused_warp_kernel(const CandParams p, const FusedParams f)
         }
         // this read is finished here: hide its features from the staged path
 #pragma unroll
-        for(int c = 0; c < 4; ++c) {
+        for(int c = 0; c < NC; ++c) {
             const uint32_t sl = uint32_t(c) * 32u + uint32_t(lane);
             if(c < nc && sl < ns) f.feat[s0 + sl] = EMPTY_KEY;
         }
@@ -685,19 +705,19 @@ q_fused_warp_kernel(const CandParams p, const FusedParams f)
         // (3) matches into shared memory: lists of <= 2 straight from the slot, longer ones gathered
         uint32_t pos = inc - tot;
 #pragma unroll
-        for(int c = 0; c < 4; ++c) {
+        for(int c = 0; c < NC; ++c) {
             if(c < nc) {
                 const uint32_t L = len[c];
                 if(L >= 1 && L <= 2) {
-                    A[pos] = make_key<KeyT>(uint64_t(q1[c].x) | (uint64_t(q1[c].y) << 32), p.wbits);
-                    if(L == 2) A[pos + 1] = make_key<KeyT>(uint64_t(q1[c].z) | (uint64_t(q1[c].w) << 32), p.wbits);
+                    A[pos] = make_key<KeyT>(loc0[c], p.wbits);
+                    if(L == 2) A[pos + 1] = make_key<KeyT>(loc1[c], p.wbits);
                 }
                 uint32_t big = __ballot_sync(0xFFFFFFFFu, L > 2);
                 while(big) {
                     const int src = __ffs(int(big)) - 1;
                     big &= big - 1;
                     const uint32_t Ls = __shfl_sync(0xFFFFFFFFu, L, src);
-                    const uint64_t Os = __shfl_sync(0xFFFFFFFFu, uint64_t(q0[c].z) | (uint64_t(q0[c].w) << 32), src);
+                    const uint64_t Os = __shfl_sync(0xFFFFFFFFu, off[c], src);
                     const uint32_t Ps = __shfl_sync(0xFFFFFFFFu, pos, src);
                     for(uint32_t t = lane; t < Ls; t += 32) A[Ps + t] = make_key<KeyT>(f.locs[Os + t], p.wbits);
                 }
@@ -917,7 +937,7 @@ static int query_find_gather(mcg_db* db, const mcg_query_opts* o, int64_t n, int
     MCG_TRY(c->q_foff.reserve((nslots + 1) * 8));
     MCG_TRY(c->q_fpos.reserve((nslots + 2) * 8));
     if(nslots > 0) {
-        q_find_kernel<<<grid_for(nslots), 256, 0, c->stream>>>(c->q_feat.as<uint32_t>(), nslots, db->table.as<uint4>(), db->table_cap,
+        q_find_kernel<<<grid_for(nslots), 256, 0, c->stream>>>(c->q_feat.as<uint32_t>(), nslots, db->table.as<uint32_t>(), uint32_t(db->table_cap),
                                                               c->q_flen.as<uint8_t>(), c->q_foff.as<uint64_t>());
         c->launches++;
     }
@@ -1058,21 +1078,25 @@ int query_batch_dev(mcg_db* db, const mcg_query_opts* o,
         CandParams p;
         fill_cand_params(db, o, doffs1, d2 ? doffs2 : nullptr, d_out_tax, d_out_hits, d_out_n, 0, &p);
         FusedParams f;
-        f.feat = c->q_feat.as<uint32_t>(); f.table = db->table.as<uint4>(); f.cap = db->table_cap;
+        f.feat = c->q_feat.as<uint32_t>(); f.table = db->table.as<uint32_t>(); f.nbuckets = uint32_t(db->table_cap);
         f.locs = db->locs.as<uint64_t>(); f.n = n; f.done = c->q_done.as<uint8_t>(); f.left_over = left;
-        const int ksz = db->key32 ? 4 : 8;
-        static bool configured = false;
-        static int per_sm32 = 1, per_sm64 = 1;
-        if(!configured) {
-            MCG_CUDA(cudaFuncSetAttribute(q_fused_warp_kernel<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * Q_FUSED * 20));
-            MCG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm32, q_fused_warp_kernel<uint32_t>, 256, 8 * Q_FUSED * 16));
-            MCG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm64, q_fused_warp_kernel<uint64_t>, 256, 8 * Q_FUSED * 20));
-            configured = true;
-        }
-        const int per_sm = std::max(1, db->key32 ? per_sm32 : per_sm64);
-        const unsigned g = unsigned(std::min<uint64_t>(uint64_t(n + 63) / 64, uint64_t(kNumSMs) * uint64_t(per_sm)));
-        if(db->key32) q_fused_warp_kernel<uint32_t><<<g, 256, 8 * Q_FUSED * (ksz + 12), c->stream>>>(p, f);
-        else          q_fused_warp_kernel<uint64_t><<<g, 256, 8 * Q_FUSED * (ksz + 12), c->stream>>>(p, f);
+        // feature slots per lane: 2 (reads of <= 64 slots, e.g. 2 x 150 bp at sketchlen 16) keeps the
+        // registers at the level of 6 resident CTAs; longer reads take the 4-slot variant
+        const bool nc2 = run.nslots <= uint64_t(n) * 64;
+        unsigned g = 1;
+        int per_sm = 1;
+#define QF_LAUNCH(KT, NC)                                                                                            \
+    do {                                                                                                             \
+        auto kern = q_fused_warp_kernel<KT, NC>;                                                                     \
+        const int smem = 8 * Q_FUSED * (int(sizeof(KT)) + 12);                                                       \
+        MCG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));                     \
+        MCG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem));                           \
+        g = unsigned(std::min<uint64_t>(uint64_t(n + 63) / 64, uint64_t(kNumSMs) * uint64_t(std::max(1, per_sm)))); \
+        kern<<<g, 256, smem, c->stream>>>(p, f);                                                                     \
+    } while(0)
+        if(db->key32) { if(nc2) QF_LAUNCH(uint32_t, 2); else QF_LAUNCH(uint32_t, 4); }
+        else          { if(nc2) QF_LAUNCH(uint64_t, 2); else QF_LAUNCH(uint64_t, 4); }
+#undef QF_LAUNCH
         c->launches++;
         uint32_t h_left = 0;
         MCG_CUDA(cudaMemcpyAsync(&h_left, left, 4, cudaMemcpyDeviceToHost, c->stream));
