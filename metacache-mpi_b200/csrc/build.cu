@@ -113,11 +113,13 @@ __global__ void table_insert_kernel(uint32_t* table, uint32_t nbuckets, const ui
     uint32_t b = table_bucket(key, nbuckets);
     for(;;) {
         uint32_t* line = table + uint64_t(b) * TABLE_BUCKET_WORDS;
-        for(int t = 0; t < 4; ++t) {
+        // look first, then claim: one compare-and-swap per key unless another thread was faster
+        const uint4 k4 = __ldcg(reinterpret_cast<const uint4*>(line));
+        int t = k4.x == EMPTY_KEY ? 0 : (k4.y == EMPTY_KEY ? 1 : (k4.z == EMPTY_KEY ? 2 : (k4.w == EMPTY_KEY ? 3 : 4)));
+        for(; t < 4; ++t) {
             if(atomicCAS(line + t, EMPTY_KEY, key) == EMPTY_KEY) {
-                atomicOr(line + 4, size << (8 * t));
                 uint64_t* pay = reinterpret_cast<uint64_t*>(line + 8 + 6 * t);
-                pay[0] = o; pay[1] = l0; pay[2] = l1;
+                pay[0] = (uint64_t(size) << 56) | o; pay[1] = l0; pay[2] = l1;
                 return;
             }
         }
@@ -145,7 +147,7 @@ __global__ void remove_keys_kernel(uint32_t* table, uint32_t nbuckets, const uin
         uint32_t* line = table + uint64_t(b) * TABLE_BUCKET_WORDS;
         const uint4 k4 = *reinterpret_cast<const uint4*>(line);
         const int t = table_match(k4, key);
-        if(t >= 0) { atomicAnd(line + 4, ~(0xFFu << (8 * t))); return; }
+        if(t >= 0) { atomicAnd(reinterpret_cast<unsigned long long*>(line + 8 + 6 * t), 0x00FFFFFFFFFFFFFFull); return; }
         if(t == -1) return;
         if(++b == nbuckets) b = 0;
     }

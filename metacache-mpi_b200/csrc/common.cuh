@@ -130,8 +130,8 @@ __host__ __device__ __forceinline__ uint32_t slot_mix(uint32_t x)
 
 // ------------------------------------------------------------------ feature table (build.cu / query.cu)
 // Buckets of one 128-byte line = 4 slots, structure of arrays inside the line (uint32 words):
-//   [0..3] keys   [4] the 4 list sizes, one byte each   [5..7] unused
-//   [8 + 6j ..] payload of slot j: off (u64, index into locs), loc0 (u64), loc1 (u64)
+//   [0..3] keys   [4..7] unused
+//   [8 + 6j ..] payload of slot j: size << 56 | off (u64, off = index into locs), loc0 (u64), loc1 (u64)
 // bucket = umulhi(slot_mix(key), nbuckets); a key lives in the first bucket at or after its home
 // bucket that had a free slot (linear probing over buckets).  A probe is ONE line -- what an L1
 // miss fetches anyway -- and the first two locations of a list come with it.

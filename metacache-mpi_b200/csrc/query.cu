@@ -71,8 +71,9 @@ q_find_kernel(const uint32_t* __restrict__ feat, uint64_t nslots, const uint32_t
             const uint4 k4 = __ldg(reinterpret_cast<const uint4*>(line));
             const int t = table_match(k4, f);
             if(t >= 0) {
-                len = (__ldg(line + 4) >> (8 * t)) & 0xFFu;
-                off = __ldg(reinterpret_cast<const uint64_t*>(line + 8 + 6 * t));
+                const uint64_t so = __ldg(reinterpret_cast<const uint64_t*>(line + 8 + 6 * t));
+                len = uint32_t(so >> 56);
+                off = so & 0x00FFFFFFFFFFFFFFull;
                 break;
             }
             if(t == -1) break;
@@ -644,14 +645,9 @@ q_fused_warp_kernel(const CandParams p, const FusedParams f)
         }
         for(;;) {
             uint4 k4[NC];
-            uint32_t sz[NC];
 #pragma unroll
             for(int c = 0; c < NC; ++c) {
-                if(c < nc && pend[c]) {
-                    const uint32_t* line = f.table + uint64_t(bkt[c]) * TABLE_BUCKET_WORDS;
-                    k4[c] = __ldg(reinterpret_cast<const uint4*>(line));
-                    sz[c] = __ldg(line + 4);
-                }
+                if(c < nc && pend[c]) k4[c] = __ldg(reinterpret_cast<const uint4*>(f.table + uint64_t(bkt[c]) * TABLE_BUCKET_WORDS));
             }
             bool again = false;
 #pragma unroll
@@ -659,12 +655,13 @@ q_fused_warp_kernel(const CandParams p, const FusedParams f)
                 if(c < nc && pend[c]) {
                     const int t = table_match(k4[c], key[c]);
                     if(t >= 0) {
-                        const uint32_t L = (sz[c] >> (8 * t)) & 0xFFu;
+                        // payload of the slot: same line, L1 hits, all three words in flight at once
                         const uint64_t* pay = reinterpret_cast<const uint64_t*>(f.table + uint64_t(bkt[c]) * TABLE_BUCKET_WORDS + 8 + 6 * t);
-                        len[c] = L;
-                        if(L > 0) loc0[c] = __ldg(pay + 1);               // same line: L1 hits
-                        if(L > 1) loc1[c] = __ldg(pay + 2);
-                        if(L > 2) off[c] = __ldg(pay);
+                        const uint64_t so = __ldg(pay);
+                        loc0[c] = __ldg(pay + 1);
+                        loc1[c] = __ldg(pay + 2);
+                        len[c] = uint32_t(so >> 56);
+                        off[c] = so & 0x00FFFFFFFFFFFFFFull;
                         pend[c] = false;
                     } else if(t == -1) {
                         pend[c] = false;
