@@ -27,6 +27,7 @@ struct SketchParams {
     int wpc;                     // windows per warp tile
     int nk_full;                 // k-mer starts of a full window and its precomputed threshold
     uint32_t thr_full;
+    int thr_extra;               // thread-per-window kernel: expected filter survivors = sketchlen + thr_extra
     int warp_smem;               // bytes of shared memory per warp
     int ngroups;                 // 16-base groups of span capacity
     int pitch;                   // row pitch of the transposed hash array (words)

@@ -34,11 +34,11 @@ constexpr int TW_SEL = 48;               // candidates the register network take
 
 // threshold on the hash head (multiple of 65536, see NOH) with sp+15 expected survivors among
 // nk k-mers; 0 = keep everything (short windows)
-__host__ __device__ __forceinline__ uint32_t tw_threshold(int nk, int sp)
+__host__ __device__ __forceinline__ uint32_t tw_threshold(int nk, int sp, int extra)
 {
     if(nk <= TW_SEL) return 0u;
-    const float pr = float(sp + 15) / float(nk);
-    return uint32_t(pr * 65536.0f) << 16;
+    const float pr = float(sp + extra) / float(nk);
+    return pr < 0.999f ? uint32_t(pr * 65536.0f) << 16 : 0u;
 }
 
 // 4 ASCII bases -> product whose top byte holds four 2-bit codes in the order A0 C1 T2 G3
@@ -229,7 +229,7 @@ __device__ __forceinline__ TwTile tw_resolve(const SketchParams& p, uint64_t til
     t.span_len = int(last_end - t.sb);
     t.nw = nw;
     if(lane >= nw) t.nk = 0;
-    t.T = (t.nk == p.nk_full) ? p.thr_full : tw_threshold(t.nk, min(p.s, max(t.nk, 0)));
+    t.T = (t.nk == p.nk_full) ? p.thr_full : tw_threshold(t.nk, min(p.s, max(t.nk, 0)), p.thr_extra);
     return t;
 }
 
@@ -479,7 +479,11 @@ int tpw_launch(mcg_ctx* c, SketchParams& p, const mcg_sketch_cfg& cfg, uint64_t 
         const int nk = int(p.winlen) - cfg.k + 1;
         const int sp = std::min(p.s, std::max(nk, 0));
         p.nk_full = nk;
-        p.thr_full = tw_threshold(nk, sp);
+        // expected survivors = sketchlen + 15; MCG_SK_EXTRA (tests) moves the filter to force the rare paths
+        static int extra = -1000;
+        if(extra == -1000) { const char* e = getenv("MCG_SK_EXTRA"); extra = e ? atoi(e) : 15; }
+        p.thr_extra = extra;
+        p.thr_full = tw_threshold(nk, sp, extra);
     }
     static int cef = -1;
     if(cef < 0) { const char* e = getenv("MCG_SK_CEF"); cef = e ? atoi(e) : 1; }

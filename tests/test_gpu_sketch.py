@@ -95,3 +95,33 @@ def test_pipelined_host_path_many_chunks(ctx, oracle):
     bad = np.nonzero((fg != fo).any(axis=1))[0]
     assert len(bad) == 0, "first differing window %d" % bad[0]
     assert (cg == co).all()
+
+
+@pytest.mark.parametrize("extra", ["-6", "40", "200"])
+def test_rare_selection_paths(extra):
+    """thread-per-window kernel with its filter moved (MCG_SK_EXTRA): too few survivors (exact
+    warp redo), 49..64 survivors (fourth sort block), column overflow, keep-everything -- all
+    must still equal the oracle.  Own process: the knob is read once per process."""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import sys, numpy as np\n"
+        "sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "from __graft_entry__ import load_package; load_package()\n"
+        "from metacache_mpi_b200 import api, synth\n"
+        "from oracle import pyoracle as po\n"
+        "ctx = api.Context(0); orc = po.Oracle()\n"
+        "rng = np.random.default_rng(11)\n"
+        "seqs = [synth.genome(1, 60000), synth.genome(2, 777), b'ACGT' * 200, b'A' * 300, b'N' * 200 + synth.genome(3, 500).tobytes()]\n"
+        "seqs += [synth.random_bases(rng, int(n)) for n in rng.integers(0, 400, size=200)]\n"
+        "buf, offs = po.concat(seqs)\n"
+        "for (k, s, wl, st) in [(16, 16, 128, 113), (12, 8, 64, 50), (16, 16, 256, 241), (16, 5, 128, 113)]:\n"
+        "    fo, co = orc.sketch_sequences(buf, offs, k=k, sketchlen=s, winlen=wl, stride=st)\n"
+        "    fg, cg = ctx.sketch_windows(buf, offs, k=k, sketchlen=s, winlen=wl, winstride=st)\n"
+        "    assert fg.shape == fo.shape and (fg == fo).all() and (cg == co).all(), (k, s, wl, st)\n"
+        "print('OK')\n"
+    ) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, MCG_SK_EXTRA=extra)
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "OK" in out.stdout, out.stderr[-2000:]
