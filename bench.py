@@ -486,6 +486,40 @@ def run_extras(args, ctx, api, synth, taxonomy, torch, dist, dev, stream, world,
                     "mean_locations_per_pair_shard0": mloc, "gpu_launches_per_batch": int((ctx.launches() - l0) / qsteps),
                     "roofline": {"bound": "hbm", "achieved": algq / (qms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                                  "frac": algq / (qms * 1e-3) / 1e9 / peak, "traffic": None}}
+    # long reads (BASELINE.json configs[4] shape): 10 kbp reads, ~89 windows / ~1400 features per read, staged path
+    try:
+        nlong = 20_000
+        src = [synth.genome(g, GENOME_LEN) for g in range(0, QG, max(QG // 8, 1))]
+        lb, lo, _ = synth.make_long_reads(src, nlong, readlen=10_000)
+        del src
+        dl = torch.from_numpy(np.concatenate([lb, np.zeros(64, np.uint8)])).to(dev)
+        dlo = torch.from_numpy(lo).to(dev)
+        llt = torch.empty((nlong, Kc), dtype=torch.int32, device=dev)
+        llh = torch.empty((nlong, Kc), dtype=torch.int32, device=dev)
+        lln = torch.empty(nlong, dtype=torch.int32, device=dev)
+
+        def lstep():
+            rc = L.mcg_query_batch_dev(db.h, C.byref(q), dl.data_ptr(), dlo.data_ptr(), len(lb), None, None, 0,
+                                       nlong, 10_000, llt.data_ptr(), llh.data_ptr(), lln.data_ptr())
+            if rc != 0:
+                raise RuntimeError(L.mcg_last_error().decode())
+        for _ in range(2):
+            lstep()
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record(stream)
+        for _ in range(5):
+            lstep()
+        f1.record(stream)
+        barrier()
+        lms = max_over_ranks(f0.elapsed_time(f1)) / 5
+        out["query_long"] = {"metric": "query_reads_per_s", "value": nlong / (lms * 1e-3), "unit": "reads/s",
+                             "bp_per_s": nlong * 10_000 / (lms * 1e-3), "ms_per_batch": lms,
+                             "workload": "%d single-end reads x 10 kbp (10 %% substitutions) per batch vs the shard of this rank "
+                                         "(%d x 5 Mbp over %d GPU(s)); per-shard top lists only" % (nlong, QG, world),
+                             "mean_candidates": float(lln.float().mean().item())}
+    except Exception as e:
+        out["query_long"] = {"error": repr(e)}
     db.close()
     return out
 

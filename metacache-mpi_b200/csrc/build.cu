@@ -11,7 +11,7 @@
 // HBM layout of a finalized shard:
 //   keys [nkeys]  uint32 ascending        sizes[nkeys] uint8 (0 = emptied "dead" key)
 //   offs [nkeys+1] uint64 (CSR)           locs [nlocs] uint64 = tgt << 32 | win
-//   table[nbuckets] 128-byte buckets of 4 slots {key, size, off, loc0, loc1} (layout and probe
+//   table[nbuckets] 128-byte buckets of 3 slots {key | size, off, loc0, loc1} (layout and probe
 //                 rule: common.cuh, "feature table"); the first two locations of a list sit in
 //                 the bucket line itself, so the (dominant) lists of length <= 2 need no second
 //                 memory access at query time.
@@ -28,7 +28,7 @@ int copy_out(mcg_ctx* c, void* h, const void* d, size_t bytes);
 int exclusive_scan_u32_to_u32(mcg_ctx* c, const uint32_t* d_in, uint32_t* d_out, uint64_t n);
 
 constexpr uint32_t EMPTY_KEY = 0xFFFFFFFFu;
-constexpr double TABLE_LOAD = 0.5;       // keys per slot
+constexpr double TABLE_LOAD = 0.45;      // keys per slot
 
 // first index with sorted_keys[i] == 0xFFFFFFFF (padding slots sort to the end)
 __global__ void count_valid_kernel(const uint32_t* keys, uint64_t n, uint64_t* out)
@@ -98,7 +98,7 @@ __global__ void emit_locations_kernel(const uint32_t* keys, const uint32_t* slot
 __global__ void table_clear_kernel(uint4* table, uint64_t nbuckets)
 {
     const uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;      // one uint4 = an eighth of a bucket
-    if(i < 8 * nbuckets) table[i] = (i & 7) ? make_uint4(0u, 0u, 0u, 0u) : make_uint4(EMPTY_KEY, EMPTY_KEY, EMPTY_KEY, EMPTY_KEY);
+    if(i < 8 * nbuckets) table[i] = (i & 7) ? make_uint4(0u, 0u, 0u, 0u) : make_uint4(EMPTY_KEY, EMPTY_KEY, EMPTY_KEY, 0u);
 }
 
 __global__ void table_insert_kernel(uint32_t* table, uint32_t nbuckets, const uint32_t* ukeys, const uint8_t* sizes,
@@ -115,11 +115,13 @@ __global__ void table_insert_kernel(uint32_t* table, uint32_t nbuckets, const ui
         uint32_t* line = table + uint64_t(b) * TABLE_BUCKET_WORDS;
         // look first, then claim: one compare-and-swap per key unless another thread was faster
         const uint4 k4 = __ldcg(reinterpret_cast<const uint4*>(line));
-        int t = k4.x == EMPTY_KEY ? 0 : (k4.y == EMPTY_KEY ? 1 : (k4.z == EMPTY_KEY ? 2 : (k4.w == EMPTY_KEY ? 3 : 4)));
-        for(; t < 4; ++t) {
+        int t = k4.x == EMPTY_KEY ? 0 : (k4.y == EMPTY_KEY ? 1 : (k4.z == EMPTY_KEY ? 2 : 3));
+        for(; t < TABLE_BUCKET_SLOTS; ++t) {
             if(atomicCAS(line + t, EMPTY_KEY, key) == EMPTY_KEY) {
-                uint64_t* pay = reinterpret_cast<uint64_t*>(line + 8 + 6 * t);
-                pay[0] = (uint64_t(size) << 56) | o; pay[1] = l0; pay[2] = l1;
+                // the slot's payload is one whole 32-byte sector: no fill from DRAM
+                uint4* pay = reinterpret_cast<uint4*>(line + 8 + 8 * t);
+                pay[0] = make_uint4(size, 0u, uint32_t(o), uint32_t(o >> 32));
+                pay[1] = make_uint4(uint32_t(l0), uint32_t(l0 >> 32), uint32_t(l1), uint32_t(l1 >> 32));
                 return;
             }
         }
@@ -147,7 +149,7 @@ __global__ void remove_keys_kernel(uint32_t* table, uint32_t nbuckets, const uin
         uint32_t* line = table + uint64_t(b) * TABLE_BUCKET_WORDS;
         const uint4 k4 = *reinterpret_cast<const uint4*>(line);
         const int t = table_match(k4, key);
-        if(t >= 0) { atomicAnd(reinterpret_cast<unsigned long long*>(line + 8 + 6 * t), 0x00FFFFFFFFFFFFFFull); return; }
+        if(t >= 0) { line[8 + 8 * t] = 0u; return; }
         if(t == -1) return;
         if(++b == nbuckets) b = 0;
     }
@@ -178,7 +180,7 @@ static inline unsigned grid_for(uint64_t n, int threads = 256) { return unsigned
 static int build_table(mcg_db* db)
 {
     mcg_ctx* c = db->ctx;
-    const uint64_t cap = uint64_t(double(db->nkeys) / TABLE_LOAD / 4.0) + 16;      // buckets
+    const uint64_t cap = uint64_t(double(db->nkeys) / TABLE_LOAD / double(TABLE_BUCKET_SLOTS)) + 16;      // buckets
     MCG_REQUIRE(cap < (1ull << 32), "feature table too large");
     MCG_TRY(db->table.reserve(cap * 128));
     db->table_cap = cap;

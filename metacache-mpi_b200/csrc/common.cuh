@@ -93,7 +93,7 @@ struct mcg_db {
     // finalized: CSR + open-addressing table
     mcg::DevBuf keys, offs, sizes;    // unique keys ascending, uint64 offsets, uint8 sizes
     mcg::DevBuf locs;                 // uint64 (tgt << 32 | win)
-    mcg::DevBuf table;                // 128-byte buckets of 4 slots (layout: table_bucket below); table_cap = buckets
+    mcg::DevBuf table;                // 128-byte buckets of 3 slots (layout: table_bucket below); table_cap = buckets
     uint64_t nkeys = 0, nlocs = 0, table_cap = 0;
     // per-read match keys: (tgt << wbits) | win; 32-bit when target and window ids fit together
     int wbits = 32;
@@ -129,29 +129,31 @@ __host__ __device__ __forceinline__ uint32_t slot_mix(uint32_t x)
 }
 
 // ------------------------------------------------------------------ feature table (build.cu / query.cu)
-// Buckets of one 128-byte line = 4 slots, structure of arrays inside the line (uint32 words):
-//   [0..3] keys   [4..7] unused
-//   [8 + 6j ..] payload of slot j: size << 56 | off (u64, off = index into locs), loc0 (u64), loc1 (u64)
+// Buckets of one 128-byte line = 3 slots, one 32-byte DRAM sector each for the keys and for
+// every slot's payload (uint32 words of the line):
+//   [0..2] keys   [3..7] unused
+//   [8 + 8t ..] payload of slot t: size (u32), pad, off (u64 index into locs), loc0 (u64), loc1 (u64)
 // bucket = umulhi(slot_mix(key), nbuckets); a key lives in the first bucket at or after its home
 // bucket that had a free slot (linear probing over buckets).  A probe is ONE line -- what an L1
-// miss fetches anyway -- and the first two locations of a list come with it.
+// miss fetches anyway -- and the first two locations of a list come with it.  An insert is one
+// compare-and-swap in the key sector plus ONE full-sector payload store (no read-modify-write).
 constexpr uint32_t TABLE_EMPTY = 0xFFFFFFFFu;
 constexpr int TABLE_BUCKET_WORDS = 32;
+constexpr int TABLE_BUCKET_SLOTS = 3;
 
 __host__ __device__ __forceinline__ uint32_t table_bucket(uint32_t key, uint32_t nbuckets)
 {
     return uint32_t((uint64_t(slot_mix(key)) * nbuckets) >> 32);
 }
 
-// slot of `key` in bucket line k4 (the 4 keys): 0..3, -1 = absent but the bucket has a free slot
-// (the key is not in the table), -2 = absent and the bucket is full (look in the next bucket)
+// slot of `key` in a bucket whose key sector starts with k4: 0..2, -1 = absent but the bucket
+// has a free slot (the key is not in the table), -2 = absent and the bucket is full (next bucket)
 __device__ __forceinline__ int table_match(const uint4& k4, uint32_t key)
 {
     if(k4.x == key) return 0;
     if(k4.y == key) return 1;
     if(k4.z == key) return 2;
-    if(k4.w == key) return 3;
-    return (k4.x == TABLE_EMPTY || k4.y == TABLE_EMPTY || k4.z == TABLE_EMPTY || k4.w == TABLE_EMPTY) ? -1 : -2;
+    return (k4.x == TABLE_EMPTY || k4.y == TABLE_EMPTY || k4.z == TABLE_EMPTY) ? -1 : -2;
 }
 
 __host__ __device__ __forceinline__ int64_t num_windows(int64_t len, int64_t winlen, int64_t stride)

@@ -71,9 +71,9 @@ q_find_kernel(const uint32_t* __restrict__ feat, uint64_t nslots, const uint32_t
             const uint4 k4 = __ldg(reinterpret_cast<const uint4*>(line));
             const int t = table_match(k4, f);
             if(t >= 0) {
-                const uint64_t so = __ldg(reinterpret_cast<const uint64_t*>(line + 8 + 6 * t));
-                len = uint32_t(so >> 56);
-                off = so & 0x00FFFFFFFFFFFFFFull;
+                const uint4 q0 = __ldg(reinterpret_cast<const uint4*>(line + 8 + 8 * t));
+                len = q0.x;
+                off = uint64_t(q0.z) | (uint64_t(q0.w) << 32);
                 break;
             }
             if(t == -1) break;
@@ -499,7 +499,7 @@ q_cand_warp_kernel(const CandParams p)
 // staged path skips them).
 struct FusedParams {
     uint32_t* feat;
-    const uint32_t* table;      // 128-byte buckets of 4 slots (common.cuh)
+    const uint32_t* table;      // 128-byte buckets of 3 slots (common.cuh)
     uint32_t nbuckets;
     const uint64_t* locs;
     int64_t n;
@@ -655,13 +655,13 @@ q_fused_warp_kernel(const CandParams p, const FusedParams f)
                 if(c < nc && pend[c]) {
                     const int t = table_match(k4[c], key[c]);
                     if(t >= 0) {
-                        // payload of the slot: same line, L1 hits, all three words in flight at once
-                        const uint64_t* pay = reinterpret_cast<const uint64_t*>(f.table + uint64_t(bkt[c]) * TABLE_BUCKET_WORDS + 8 + 6 * t);
-                        const uint64_t so = __ldg(pay);
-                        loc0[c] = __ldg(pay + 1);
-                        loc1[c] = __ldg(pay + 2);
-                        len[c] = uint32_t(so >> 56);
-                        off[c] = so & 0x00FFFFFFFFFFFFFFull;
+                        // payload of the slot: one sector of the same line (L1 hits)
+                        const uint4* pay = reinterpret_cast<const uint4*>(f.table + uint64_t(bkt[c]) * TABLE_BUCKET_WORDS + 8 + 8 * t);
+                        const uint4 q0 = __ldg(pay), q1 = __ldg(pay + 1);
+                        len[c] = q0.x;
+                        off[c] = uint64_t(q0.z) | (uint64_t(q0.w) << 32);
+                        loc0[c] = uint64_t(q1.x) | (uint64_t(q1.y) << 32);
+                        loc1[c] = uint64_t(q1.z) | (uint64_t(q1.w) << 32);
                         pend[c] = false;
                     } else if(t == -1) {
                         pend[c] = false;
