@@ -446,7 +446,7 @@ int window_prefix(mcg_ctx* c, int64_t winlen, int64_t stride, const int64_t* d_s
 
 // sketch_tpw.cu
 bool tpw_eligible(int sketchlen, int64_t winlen, int64_t stride);
-void tpw_config(int64_t winlen, int64_t stride, int* ngroups, size_t* warp_smem);
+void tpw_config(int64_t winlen, int64_t stride, int rounds, int* ngroups, size_t* warp_smem);
 int tpw_launch(mcg_ctx* c, SketchParams& p, const mcg_sketch_cfg& cfg, uint64_t nblocks, cudaStream_t stream);
 
 int sketch_config(const mcg_sketch_cfg& cfg, int sketchlen, int64_t winlen, int64_t stride,
@@ -465,7 +465,7 @@ int sketch_config(const mcg_sketch_cfg& cfg, int sketchlen, int64_t winlen, int6
         // thread-per-window kernel: 32 windows per warp tile
         *wpt = 32;
         *pitch = 0;
-        tpw_config(winlen, stride, ngroups, warp_smem);
+        tpw_config(winlen, stride, 1, ngroups, warp_smem);
         return MCG_OK;
     }
     // windows per warp tile: a typical span (same sequence) fits one 16-base group per lane
@@ -522,6 +522,16 @@ int sketch_launch(mcg_ctx* c, const mcg_sketch_cfg& cfg, int sketchlen, int64_t 
     p.s = sketchlen;
     p.winlen = winlen;
     p.stride = stride;
+    const bool tpw = tpw_eligible(sketchlen, winlen, stride);
+    if(tpw && nseq > 0 && total_bytes / nseq < 4 * winlen) {
+        // read-like input (long and short windows alternate): 64-window tiles handled in two
+        // interleaved rounds, so that the lanes of a round have windows of one kind
+        int ng2 = 0;
+        size_t ws2 = 0;
+        tpw_config(winlen, stride, 2, &ng2, &ws2);
+        static const bool no_rounds = getenv("MCG_SK_NO_ROUNDS") != nullptr;
+        if(ws2 * 4 <= 56 * 1024 && !no_rounds) { p.wpc = 64; p.ngroups = ng2; p.warp_smem = int(ws2); }
+    }
     const uint64_t nblocks = (nwin - win_lo + p.wpc - 1) / p.wpc;
     MCG_REQUIRE(nblocks < (1ull << 31), "too many windows in one launch");
     MCG_REQUIRE(nseq < (1ll << 32), "too many sequences in one launch");
@@ -537,7 +547,7 @@ int sketch_launch(mcg_ctx* c, const mcg_sketch_cfg& cfg, int sketchlen, int64_t 
                                                                          p.tile_ctr);
     c->launches++;
     p.cta_seq = tile_seq;
-    if(tpw_eligible(sketchlen, winlen, stride)) return tpw_launch(c, p, cfg, nblocks, stream);
+    if(tpw) return tpw_launch(c, p, cfg, nblocks, stream);
 #define SK_LAUNCH(K16, PT)                                                                                        \
     do {                                                                                                          \
         auto kern = sketch_kernel<K16, PT>;                                                                       \

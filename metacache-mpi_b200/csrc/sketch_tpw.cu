@@ -150,10 +150,18 @@ __device__ __noinline__ void tw_slow_window(const uint2* pk2, int pos, int nk, i
     if(out_cnt != nullptr && lane == 0) *out_cnt = uint32_t(nout);
 }
 
-// what a lane knows about its window of the tile (+ warp-uniform span data)
-struct TwTile {
+// what a lane knows about one of its windows
+struct TwWin {
     int pos, nk;            // first base of the window inside the packed span, k-mer count
     uint32_t oidx, T;       // output row, threshold
+    bool have;              // the window exists (tiles at the end of a launch are short)
+};
+// a tile = 32 * R consecutive windows; lane l owns windows R*l .. R*l + R-1 and handles them in R
+// rounds.  R = 2 is for read-like input (long and short windows alternate: interleaving gives
+// every round windows of one kind); + warp-uniform span data
+template<int R>
+struct TwTile {
+    TwWin w[R];
     int nw, span_len;       // uniform: windows in the tile, bytes from the aligned span start
     int64_t sb;             // uniform: 16-byte aligned offset of the span in the sequence buffer
 };
@@ -171,70 +179,86 @@ __device__ __forceinline__ TwSeq tw_load_seq(const SketchParams& p, uint32_t q0)
     return q;
 }
 
-__device__ __forceinline__ TwTile tw_resolve(const SketchParams& p, uint64_t tile, const TwSeq& q, int lane)
+template<int R>
+__device__ __forceinline__ TwTile<R> tw_resolve(const SketchParams& p, uint64_t tile, const TwSeq& q, int lane)
 {
-    TwTile t;
-    const uint64_t g0 = p.win_lo + tile * uint64_t(TW_WPT);
-    const int nw = int(min(uint64_t(TW_WPT), p.nwin - g0));
+    TwTile<R> t;
+    constexpr int WPT = TW_WPT * R;
+    const uint64_t g0 = p.win_lo + tile * uint64_t(WPT);
+    const int nw = int(min(uint64_t(WPT), p.nwin - g0));
     const int winlen = int(p.winlen), stride = int(p.stride);
+    const int last_lane = (nw - 1) / R, last_round = (nw - 1) % R;
     int64_t first_abs, last_end;
     if(g0 + uint64_t(nw) <= uint64_t(q.wf1)) {
         // common case: the whole tile lies in one sequence
         const int64_t len = q.so1 - q.so;
         const uint32_t w0 = uint32_t(g0 - q.wf0);
-        int64_t b0 = 0;
-        int off = 0, off_last = 0, wl = int(min(len, int64_t(winlen)));
-        if(len > winlen) {
-            b0 = int64_t(w0) * stride;
-            off = lane * stride;
-            off_last = (nw - 1) * stride;
-            const int rem = int(min(len - b0, int64_t(1) << 30)) - off;      // bases from this window's start to the end
-            wl = min(winlen, rem);
+        const bool multi = len > winlen;
+        const int64_t b0 = multi ? int64_t(w0) * stride : 0;
+        const int rem0 = int(min(len - b0, int64_t(1) << 30));       // bases from the tile's first window to the end
+        int wl_sel = 0;
+#pragma unroll
+        for(int r = 0; r < R; ++r) {
+            const int j = R * lane + r;
+            int off = 0, wl = int(min(len, int64_t(winlen)));
+            if(multi) { off = j * stride; wl = min(winlen, rem0 - off); }
+            t.w[r].pos = off;
+            t.w[r].nk = wl - p.k + 1;
+            t.w[r].oidx = q.of + w0 + uint32_t(j);
+            if(r == last_round) wl_sel = wl;
         }
         first_abs = q.so + b0;
-        t.pos = off;
-        t.nk = wl - p.k + 1;
-        t.oidx = q.of + w0 + uint32_t(lane);
-        last_end = first_abs + off_last + __shfl_sync(0xFFFFFFFFu, wl, nw - 1);
+        last_end = first_abs + (multi ? (nw - 1) * stride : 0) + __shfl_sync(0xFFFFFFFFu, wl_sel, last_lane);
     } else {
-        int64_t abs_i = 0;
-        int wl = 0;
-        t.nk = 0;
-        t.oidx = 0;
-        if(lane < nw) {
-            const uint32_t g = uint32_t(g0) + uint32_t(lane);
-            // every sequence has >= 1 window: the sequence of window g0+lane is in [q0, q0+lane]
-            uint32_t lo = q.q0, hi = uint32_t(min(int64_t(q.q0) + lane + 1, p.nseq));
-            while(hi - lo > 1) {
-                const uint32_t mid = (lo + hi) >> 1;
-                if(__ldg(p.win_first + mid) <= g) lo = mid; else hi = mid;
+        int64_t abs0 = 0, end_sel = 0;
+#pragma unroll
+        for(int r = 0; r < R; ++r) {
+            const int j = R * lane + r;
+            int64_t abs_i = 0;
+            int wl = 0;
+            t.w[r].nk = 0;
+            t.w[r].oidx = 0;
+            if(j < nw) {
+                const uint32_t g = uint32_t(g0) + uint32_t(j);
+                // every sequence has >= 1 window: the sequence of window g0+j is in [q0, q0+j]
+                uint32_t lo = q.q0, hi = uint32_t(min(int64_t(q.q0) + j + 1, p.nseq));
+                while(hi - lo > 1) {
+                    const uint32_t mid = (lo + hi) >> 1;
+                    if(__ldg(p.win_first + mid) <= g) lo = mid; else hi = mid;
+                }
+                const uint32_t w = g - __ldg(p.win_first + lo);
+                const int64_t so = __ldg(p.seq_off + lo);
+                const int64_t len = __ldg(p.seq_off + lo + 1) - so;
+                int64_t b = 0, e = len;
+                if(len > winlen) { b = int64_t(w) * stride; e = min(b + winlen, len); }
+                abs_i = so + b;
+                wl = int(e - b);
+                t.w[r].nk = wl - p.k + 1;
+                t.w[r].oidx = __ldg(p.out_first + lo) + w;
             }
-            const uint32_t w = g - __ldg(p.win_first + lo);
-            const int64_t so = __ldg(p.seq_off + lo);
-            const int64_t len = __ldg(p.seq_off + lo + 1) - so;
-            int64_t b = 0, e = len;
-            if(len > winlen) { b = int64_t(w) * stride; e = min(b + winlen, len); }
-            abs_i = so + b;
-            wl = int(e - b);
-            t.nk = wl - p.k + 1;
-            t.oidx = __ldg(p.out_first + lo) + w;
+            if(r == 0) abs0 = abs_i;
+            if(r == last_round) end_sel = abs_i + wl;
+            if(r == 0) first_abs = __shfl_sync(0xFFFFFFFFu, abs0, 0);
+            t.w[r].pos = int(abs_i - first_abs);
         }
-        first_abs = __shfl_sync(0xFFFFFFFFu, abs_i, 0);
-        t.pos = int(abs_i - first_abs);
-        last_end = __shfl_sync(0xFFFFFFFFu, abs_i + wl, nw - 1);
+        last_end = __shfl_sync(0xFFFFFFFFu, end_sel, last_lane);
     }
     const int sb_lo = int((reinterpret_cast<uintptr_t>(p.seq) + uint64_t(first_abs)) & 15u);
-    t.pos += sb_lo;
     t.sb = first_abs - sb_lo;
     t.span_len = int(last_end - t.sb);
     t.nw = nw;
-    if(lane >= nw) t.nk = 0;
-    t.T = (t.nk == p.nk_full) ? p.thr_full : tw_threshold(t.nk, min(p.s, max(t.nk, 0)), p.thr_extra);
+#pragma unroll
+    for(int r = 0; r < R; ++r) {
+        t.w[r].have = R * lane + r < nw;
+        t.w[r].pos += sb_lo;
+        if(!t.w[r].have) t.w[r].nk = 0;
+        t.w[r].T = (t.w[r].nk == p.nk_full) ? p.thr_full : tw_threshold(t.w[r].nk, min(p.s, max(t.w[r].nk, 0)), p.thr_extra);
+    }
     return t;
 }
 
-template<bool K16, bool CEF>
-__global__ void __launch_bounds__(TW_THREADS, 5)
+template<bool K16, bool CEF, int R>
+__global__ void __launch_bounds__(TW_THREADS, R == 1 ? 5 : 4)
 sketch_tpw_kernel(const SketchParams p)
 {
     extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -248,12 +272,12 @@ sketch_tpw_kernel(const SketchParams p)
     uint32_t* list = reinterpret_cast<uint32_t*>(raw);                       // ... reused as [TW_LCAP][32] candidate columns
     uint2*    pk2  = reinterpret_cast<uint2*>(raw + rawcap);                 // [ngc + 2] {packed, ambiguity}
     uint32_t* tmp  = reinterpret_cast<uint32_t*>(pk2 + ngc + 2);             // [32]
-    const uint32_t ntiles = uint32_t((p.nwin - p.win_lo + TW_WPT - 1) / TW_WPT);
+    const uint32_t ntiles = uint32_t((p.nwin - p.win_lo + TW_WPT * R - 1) / (TW_WPT * R));
     const int k = p.k;
     const uint32_t one = p.c65536 >> 16, m1 = 0u - one;      // 1 and -1, opaque to the compiler
 
     // starts the TMA copy of a tile's bytes (the candidate columns of the previous tile must be consumed)
-    auto tma_issue = [&](const TwTile& t) {
+    auto tma_issue = [&](const TwTile<R>& t) {
         if(lane == 0) {
             const uint32_t bytes = uint32_t(((t.span_len + 15) >> 4) + 1) * 16u;
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -276,7 +300,7 @@ sketch_tpw_kernel(const SketchParams p)
     };
     uint32_t tile = next_tile();
     if(tile >= ntiles) return;
-    TwTile cur = tw_resolve(p, tile, tw_load_seq(p, __ldg(p.cta_seq + tile)), lane);
+    TwTile<R> cur = tw_resolve<R>(p, tile, tw_load_seq(p, __ldg(p.cta_seq + tile)), lane);
     tma_issue(cur);
 
     const uint32_t la0 = smem_u32(list) + uint32_t(lane) * 4u;
@@ -314,15 +338,19 @@ sketch_tpw_kernel(const SketchParams p)
         TwSeq sn;
         if(more) sn = tw_load_seq(p, q0n);                                   // step B
 
-        // ---- (2) this lane's window: hash + threshold filter into the lane's column
-        const int nk = cur.nk;
+        TwTile<R> nxt = cur;
+        TwWin d = cur.w[0];
+#pragma unroll 1
+        for(int rd = 0; rd < R; ++rd) {
+        // ---- (2) this lane's window of the round: hash + threshold filter into the lane's column
+        const int nk = d.nk;
         const int sp = min(p.s, max(nk, 0));
-        uint32_t T = cur.T;
+        uint32_t T = d.T;
         const bool thr = T != 0u;
         uint32_t la = la0;
         bool ovf = false;
         if(nk > 0) {
-            const int j0 = cur.pos >> 4, sa = cur.pos & 15, sh = 2 * sa;
+            const int j0 = d.pos >> 4, sa = d.pos & 15, sh = 2 * sa;
             const uint2 w0 = pk2[j0];
             uint2 w1 = pk2[j0 + 1];
             uint32_t A0 = __funnelshift_l(w1.x, w0.x, sh);
@@ -395,10 +423,9 @@ sketch_tpw_kernel(const SketchParams p)
             }
         }
         __syncwarp();
-        // the columns are consumed: resolve the next tile and start its copy         (step C)
-        TwTile nxt = cur;
-        if(more) {
-            nxt = tw_resolve(p, nt, sn, lane);
+        // the columns of the last round are consumed: resolve the next tile and start its copy   (step C)
+        if(rd == R - 1 && more) {
+            nxt = tw_resolve<R>(p, nt, sn, lane);
             tma_issue(nxt);
         }
 
@@ -410,10 +437,10 @@ sketch_tpw_kernel(const SketchParams p)
 #pragma unroll
             for(int i = 0; i < 15; ++i) dup |= (best[i] == best[i + 1]) && (best[i] != NOF);
         }
-        const bool have = lane < cur.nw;
+        const bool have = d.have;
         const bool bad = (sp > 0) && (ovf || dup || (thr && cnt < sp));
         if(have && !bad) {
-            uint32_t* o = p.out_feat + uint64_t(cur.oidx) * uint32_t(p.s);
+            uint32_t* o = p.out_feat + uint64_t(d.oidx) * uint32_t(p.s);
             if(p.s == 16) {
                 uint4* o4 = reinterpret_cast<uint4*>(o);
                 o4[0] = make_uint4(best[0], best[1], best[2], best[3]);
@@ -429,7 +456,7 @@ sketch_tpw_kernel(const SketchParams p)
                 int n = 0;
 #pragma unroll
                 for(int i = 0; i < 16; ++i) n += (i < p.s && best[i] != NOF) ? 1 : 0;
-                p.out_cnt[cur.oidx] = uint32_t(min(n, sp));
+                p.out_cnt[d.oidx] = uint32_t(min(n, sp));
             }
         }
         // ---- (4) rare: exact redo of flagged windows by the whole warp
@@ -437,13 +464,15 @@ sketch_tpw_kernel(const SketchParams p)
         while(bm != 0u) {
             const int src = __ffs(bm) - 1;
             bm &= bm - 1u;
-            const int pos_s = __shfl_sync(0xFFFFFFFFu, cur.pos, src);
+            const int pos_s = __shfl_sync(0xFFFFFFFFu, d.pos, src);
             const int nk_s = __shfl_sync(0xFFFFFFFFu, nk, src);
-            const uint32_t o_s = __shfl_sync(0xFFFFFFFFu, cur.oidx, src);
+            const uint32_t o_s = __shfl_sync(0xFFFFFFFFu, d.oidx, src);
             tw_slow_window(pk2, pos_s, nk_s, min(p.s, max(nk_s, 0)), k, p.s, p.out_feat + uint64_t(o_s) * uint32_t(p.s),
                            p.out_cnt ? p.out_cnt + o_s : nullptr, lane, tmp);
         }
         __syncwarp();
+        if(R > 1) d = cur.w[R - 1];                 // R <= 2
+        }   // rounds
         if(!more) break;
         cur = nxt;
         tile = nt;
@@ -460,10 +489,10 @@ bool tpw_eligible(int sketchlen, int64_t winlen, int64_t stride)
 }
 
 // shared-memory geometry of the thread-per-window kernel
-void tpw_config(int64_t winlen, int64_t stride, int* ngroups, size_t* warp_smem)
+void tpw_config(int64_t winlen, int64_t stride, int rounds, int* ngroups, size_t* warp_smem)
 {
     const int64_t adv = winlen > stride ? winlen : stride;
-    const int ng = int((TW_WPT * adv + 30 + 15) / 16) + 1;      // worst case: every window in another sequence
+    const int ng = int((TW_WPT * rounds * adv + 30 + 15) / 16) + 1;      // worst case: every window in another sequence
     const size_t region = std::max(size_t(ng + 2) * 16, size_t(TW_LCAP) * 32 * 4);     // raw bytes, then candidate columns
     size_t bytes = 16 + region + size_t(ng + 2) * 8 + 32 * 4;
     bytes = (bytes + 127) & ~size_t(127);
@@ -488,9 +517,10 @@ int tpw_launch(mcg_ctx* c, SketchParams& p, const mcg_sketch_cfg& cfg, uint64_t 
     static int cef = -1;
     if(cef < 0) { const char* e = getenv("MCG_SK_CEF"); cef = e ? atoi(e) : 1; }
     p.c65536 = 65536u;
-#define TW_LAUNCH(K16, CEF)                                                                                         \
+    const int rounds = p.wpc / TW_WPT;
+#define TW_LAUNCH(K16, CEF, R)                                                                                      \
     do {                                                                                                            \
-        auto kern = sketch_tpw_kernel<K16, CEF>;                                                                    \
+        auto kern = sketch_tpw_kernel<K16, CEF, R>;                                                                 \
         if(smem > 48 * 1024) MCG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))); \
         int per_sm = 1;                                                                                             \
         MCG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TW_THREADS, smem));                   \
@@ -498,9 +528,14 @@ int tpw_launch(mcg_ctx* c, SketchParams& p, const mcg_sketch_cfg& cfg, uint64_t 
         const uint64_t grid = std::min<uint64_t>((nblocks + TW_WARPS - 1) / TW_WARPS, uint64_t(kNumSMs) * uint64_t(per_sm)); \
         kern<<<unsigned(grid), TW_THREADS, smem, stream>>>(p);                                                      \
     } while(0)
-    if(cfg.k != 16)   TW_LAUNCH(false, true);
-    else if(cef == 0) TW_LAUNCH(true, false);
-    else              TW_LAUNCH(true, true);
+    if(rounds == 2) {
+        if(cfg.k != 16)   TW_LAUNCH(false, true, 2);
+        else              TW_LAUNCH(true, true, 2);
+    } else {
+        if(cfg.k != 16)   TW_LAUNCH(false, true, 1);
+        else if(cef == 0) TW_LAUNCH(true, false, 1);
+        else              TW_LAUNCH(true, true, 1);
+    }
 #undef TW_LAUNCH
     c->launches++;
     MCG_CUDA(cudaGetLastError());
