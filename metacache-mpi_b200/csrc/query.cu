@@ -507,7 +507,7 @@ struct FusedParams {
     uint32_t* left_over;        // [0] number of reads left to the staged path, [1] read counter (dynamic scheduling)
 };
 
-constexpr int Q_FUSED = 256;    // matches per read of the fused path
+constexpr int Q_FUSED = 128;    // matches per read of the fused path (small: shared memory is taken from L1, which the probes need)
 
 // candidates.h:236-285 with the taxon already lifted to -lowest and its rank known (seq = the
 // taxon is of sequence rank: such taxa are never merged); entry i of the list lives in lane i
@@ -594,6 +594,16 @@ __device__ __forceinline__ void toplist_from_sorted(const CandParams& p, uint32_
     }
     if(lane == 0) p.out_n[r] = L.n;
     __syncwarp();
+}
+
+// features of the reads the fused kernel finished -> NO_FEATURE: the staged path skips them
+__global__ void q_hide_done_kernel(uint32_t* feat, const uint32_t* W, int s, const uint8_t* done, int64_t n)
+{
+    const int64_t r = (blockIdx.x * int64_t(blockDim.x) + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if(r >= n || !done[r]) return;
+    const uint64_t s0 = uint64_t(W[r]) * s, s1 = uint64_t(W[r + 1]) * s;
+    for(uint64_t i = s0 + lane; i < s1; i += 32) feat[i] = EMPTY_KEY;
 }
 
 template<class KeyT, int NC>           // NC: feature slots per lane (reads with more than 32*NC slots are left over)
@@ -688,12 +698,8 @@ q_fused_warp_kernel(const CandParams p, const FusedParams f)
             if(lane == 0) { atomicAdd(f.left_over, 1u); f.done[r] = 0; }
             continue;
         }
-        // this read is finished here: hide its features from the staged path
-#pragma unroll
-        for(int c = 0; c < NC; ++c) {
-            const uint32_t sl = uint32_t(c) * 32u + uint32_t(lane);
-            if(c < nc && sl < ns) f.feat[s0 + sl] = EMPTY_KEY;
-        }
+        // this read is finished here (q_hide_done_kernel hides its features from the staged path,
+        // should any read of the batch be left over)
         if(lane == 0) f.done[r] = 1;
         if(m == 0) {
             if(lane == 0) p.out_n[r] = 0;
@@ -1082,11 +1088,14 @@ int query_batch_dev(mcg_db* db, const mcg_query_opts* o,
         const bool nc2 = run.nslots <= uint64_t(n) * 64;
         unsigned g = 1;
         int per_sm = 1;
+        // shared memory comes out of L1, which the probes live on: ask for no more than the 5 CTAs need
+        const int carve = 38;
 #define QF_LAUNCH(KT, NC)                                                                                            \
     do {                                                                                                             \
         auto kern = q_fused_warp_kernel<KT, NC>;                                                                     \
         const int smem = 8 * Q_FUSED * (int(sizeof(KT)) + 12);                                                       \
         MCG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));                     \
+        if(carve >= 0) MCG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve));    \
         MCG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem));                           \
         g = unsigned(std::min<uint64_t>(uint64_t(n + 63) / 64, uint64_t(kNumSMs) * uint64_t(std::max(1, per_sm)))); \
         kern<<<g, 256, smem, c->stream>>>(p, f);                                                                     \
@@ -1100,6 +1109,9 @@ int query_batch_dev(mcg_db* db, const mcg_query_opts* o,
         MCG_CUDA(cudaStreamSynchronize(c->stream));
         if(h_left == 0) { if(run_out) *run_out = run; return MCG_OK; }
         d_done = c->q_done.as<uint8_t>();
+        q_hide_done_kernel<<<grid_for(uint64_t(n) * 32), 256, 0, c->stream>>>(c->q_feat.as<uint32_t>(), c->tmp2.as<uint32_t>(), o->sketchlen,
+                                                                               d_done, n);
+        c->launches++;
     }
     MCG_TRY(query_find_gather(db, o, n, d_out_n, d_done, &run));
     MCG_TRY(query_back(db, o, doffs1, d2 ? doffs2 : nullptr, n, run, d_out_tax, d_out_hits, d_out_n, write_sorted));
