@@ -240,7 +240,8 @@ struct CandParams {
     int64_t tstride;
     void* loc;
     int wbits;
-    uint32_t* hits_scratch;      // only for the global-memory class
+    uint32_t* hits_scratch;      // only for the global-memory class: range hits, candidate scratch
+    uint32_t* hits_scratch2;
     const uint32_t* list;
     const uint32_t* list_count;
     int K;
@@ -373,10 +374,14 @@ __device__ __forceinline__ void wsort64(KeyT& a, KeyT& b, int lane)
     }
 }
 
-// one read handled by one warp (<= Q_SMALL matches)
+template<class KeyT>
+__device__ __forceinline__ void toplist_from_sorted(const CandParams& p, uint32_t r, const KeyT* A, const uint32_t* Hh,
+                                                    uint32_t m, int32_t* Ct, uint32_t* Ch, int lane);
+
+// one read handled by one warp (<= Q_SMALL matches); Ct, Ch: candidate scratch of Q_SMALL entries
 template<class KeyT>
 __device__ __forceinline__ void process_read_warp(const CandParams& p, uint32_t r, KeyT* A, uint32_t* Hh, uint32_t m,
-                                                  KeyT* gsrc, int lane)
+                                                  KeyT* gsrc, int lane, int32_t* Ct, uint32_t* Ch)
 {
     const KeyT KMAX = ~KeyT(0);
     if(m <= 32) {
@@ -399,39 +404,16 @@ __device__ __forceinline__ void process_read_warp(const CandParams& p, uint32_t 
     const uint32_t numwin = num_windows_in_range(p, r);
     for(uint32_t i = lane; i < m; i += 32) Hh[i] = hits_ending_at(A, i, numwin, p.wbits);
     __syncwarp();
-    // walk the target runs (ascending target = insertion order of candidates.h:207-219)
-    WarpTopK L;
-    L.tax = -1; L.hits = 0; L.n = 0;
-    uint32_t i = 0;
-    while(i < m) {
-        const uint32_t tgt = tgt_of(A[i], p.wbits);
-        uint32_t e = i;
-        for(;;) {                                    // end of the run, 32 elements per probe
-            const uint32_t idx = e + lane;
-            const bool same = idx < m && tgt_of(A[idx], p.wbits) == tgt;
-            const uint32_t b = __ballot_sync(0xFFFFFFFFu, same);
-            if(b == 0xFFFFFFFFu) { e += 32; continue; }
-            e += uint32_t(__ffs(int(~b))) - 1u;
-            break;
-        }
-        uint32_t mx = 0;
-        for(uint32_t j = i + lane; j < e; j += 32) mx = max(mx, Hh[j]);
-        mx = __reduce_max_sync(0xFFFFFFFFu, mx);
-        warp_topk_insert(L, p.K, int32_t(tgt), mx, p.lowest, lane, p.lineage, p.rank);
-        i = e;
-    }
-    if(lane < p.K) {
-        p.out_tax[uint64_t(r) * p.K + lane] = lane < L.n ? L.tax : -1;
-        p.out_hits[uint64_t(r) * p.K + lane] = lane < L.n ? L.hits : 0u;
-    }
-    if(lane == 0) p.out_n[r] = L.n;
-    __syncwarp();
+    toplist_from_sorted<KeyT>(p, r, A, Hh, m, Ct, Ch, lane);
 }
 
-// one read handled by a whole CTA: A = its matches (shared or global memory), Hh = m uint32
+__device__ __forceinline__ void warp_topk_insert_lifted(WarpTopK& L, int K, int32_t tax, uint32_t hits, bool seq, int lane);
+
+// one read handled by a whole CTA: A = its matches (shared or global memory), Hh = m uint32,
+// Ct = m int32 of candidate scratch (may alias A: candidate j is written after element j was read)
 template<class KeyT>
 __device__ __forceinline__ void process_read_cta(const CandParams& p, uint32_t r, KeyT* A, uint32_t* Hh, uint32_t m,
-                                                 KeyT* gsrc, bool staged, int tid, int nt)
+                                                 KeyT* gsrc, bool staged, int tid, int nt, int32_t* Ct)
 {
     if(staged) {
         for(uint32_t i = tid; i < m; i += nt) A[i] = gsrc[i];
@@ -454,21 +436,55 @@ __device__ __forceinline__ void process_read_cta(const CandParams& p, uint32_t r
         if(tail != i) atomicMax(&Hh[tail], Hh[i]);
     }
     __syncthreads();
-    if(tid == 0) {
-        TopK L;
-        L.n = 0;
-        uint32_t i = 0;
-        while(i < m) {
-            const uint32_t tgt = tgt_of(A[i], p.wbits);
-            uint32_t lo = i, hi = m;
-            while(lo < hi) {
-                const uint32_t mid = (lo + hi) >> 1;
-                if(tgt_of(A[mid], p.wbits) <= tgt) lo = mid + 1; else hi = mid;
+    // the run tails are the candidates, in ascending target order (candidates.h:207-219).  Their
+    // taxa are lifted by all threads at once (the lineage loads are in flight together) and they
+    // are compacted in order, nt elements at a time; only the order-dependent list insertion is
+    // sequential (warp 0, out of the compacted arrays, no memory latency).
+    __shared__ uint32_t s_wcount[32];
+    const int lane = tid & 31, warp = tid >> 5, nwarp = (nt + 31) >> 5;
+    uint32_t* Ch = Hh;
+    uint32_t ncand = 0;
+    for(uint32_t base = 0; base < m; base += nt) {
+        const uint32_t i = base + tid;
+        const bool valid = i < m;
+        const uint32_t tgt = valid ? tgt_of(A[i], p.wbits) : 0xFFFFFFFFu;
+        const bool tail = valid && (i + 1 == m || tgt_of(A[i + 1], p.wbits) != tgt);
+        uint32_t v = 0;
+        int32_t tax = 0;
+        if(tail) {
+            v = Hh[i];
+            tax = int32_t(tgt);
+            if(p.lowest > MCG_RANK_SEQUENCE) {
+                const int32_t anc = __ldg(p.lineage + int64_t(tax) * MCG_NUM_RANKS + p.lowest);
+                if(anc >= 0) tax = anc;
             }
-            topk_insert(L, p.K, int32_t(tgt), Hh[lo - 1], p.lowest, p.lineage, p.rank);
-            i = lo;
+            if(__ldg(p.rank + tax) == MCG_RANK_SEQUENCE) tax |= int32_t(0x80000000u);
         }
-        write_toplist(p, r, L);
+        const uint32_t bal = __ballot_sync(0xFFFFFFFFu, tail);
+        if(lane == 0) s_wcount[warp] = __popc(bal);
+        __syncthreads();
+        uint32_t pre = 0, tot = 0;
+        for(int w = 0; w < nwarp; ++w) { const uint32_t cw = s_wcount[w]; if(w < warp) pre += cw; tot += cw; }
+        if(tail) {
+            const uint32_t j = ncand + pre + __popc(bal & ((1u << lane) - 1u));
+            Ct[j] = tax;
+            Ch[j] = v;
+        }
+        ncand += tot;
+        __syncthreads();
+    }
+    if(warp == 0) {
+        WarpTopK L;
+        L.tax = -1; L.hits = 0; L.n = 0;
+        for(uint32_t j = 0; j < ncand; ++j) {
+            const int32_t t = Ct[j];
+            warp_topk_insert_lifted(L, p.K, t & 0x7FFFFFFF, Ch[j], t < 0, lane);
+        }
+        if(lane < p.K) {
+            p.out_tax[uint64_t(r) * p.K + lane] = lane < L.n ? L.tax : -1;
+            p.out_hits[uint64_t(r) * p.K + lane] = lane < L.n ? L.hits : 0u;
+        }
+        if(lane == 0) p.out_n[r] = L.n;
     }
     __syncthreads();
 }
@@ -480,14 +496,17 @@ q_cand_warp_kernel(const CandParams p)
 {
     extern __shared__ __align__(16) unsigned char sm[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    KeyT* A = reinterpret_cast<KeyT*>(sm) + size_t(warp) * Q_SMALL;
-    uint32_t* Hh = reinterpret_cast<uint32_t*>(sm + size_t(8) * Q_SMALL * sizeof(KeyT)) + size_t(warp) * Q_SMALL;
+    unsigned char* wbase = sm + size_t(warp) * Q_SMALL * (sizeof(KeyT) + 12);
+    KeyT* A = reinterpret_cast<KeyT*>(wbase);
+    uint32_t* Hh = reinterpret_cast<uint32_t*>(wbase + size_t(Q_SMALL) * sizeof(KeyT));
+    int32_t* Ct = reinterpret_cast<int32_t*>(Hh + Q_SMALL);
+    uint32_t* Ch = reinterpret_cast<uint32_t*>(Ct + Q_SMALL);
     const uint32_t cnt = *p.list_count;
     for(uint32_t it = blockIdx.x * 8 + warp; it < cnt; it += gridDim.x * 8) {
         const uint32_t r = p.list[it];
         const uint64_t beg = p.fpos[uint64_t(p.W[r]) * p.s];
         const uint32_t m = uint32_t(p.fpos[uint64_t(p.W[r + 1]) * p.s] - beg);
-        process_read_warp<KeyT>(p, r, A, Hh, m, static_cast<KeyT*>(p.loc) + beg, lane);
+        process_read_warp<KeyT>(p, r, A, Hh, m, static_cast<KeyT*>(p.loc) + beg, lane, Ct, Ch);
     }
 }
 
@@ -547,13 +566,14 @@ __device__ __forceinline__ void toplist_from_sorted(const CandParams& p, uint32_
                                                     uint32_t m, int32_t* Ct, uint32_t* Ch, int lane)
 {
     const uint32_t ltmask = (1u << lane) - 1u;
-    uint32_t ncand = 0, carry = 0;
+    uint32_t ncand = 0, carry = 0, last_tgt = 0xFFFFFFFFu;
     for(uint32_t b = 0; b < m; b += 32) {
         const uint32_t i = b + lane;
         const bool valid = i < m;
         const uint32_t tgt = valid ? tgt_of(A[i], p.wbits) : 0xFFFFFFFFu;
         uint32_t prev = __shfl_up_sync(0xFFFFFFFFu, tgt, 1);
-        if(lane == 0) prev = b > 0 ? tgt_of(A[b - 1], p.wbits) : 0xFFFFFFFFu;
+        if(lane == 0) prev = last_tgt;
+        last_tgt = __shfl_sync(0xFFFFFFFFu, tgt, 31);
         const bool head = valid && (i == 0 || prev != tgt);
         const bool tail = valid && (i + 1 == m || tgt_of(A[i + 1], p.wbits) != tgt);
         uint32_t v = valid ? Hh[i] : 0u;
@@ -765,7 +785,7 @@ __global__ void q_cand_cta_kernel(const CandParams p, uint32_t capacity)
         const uint32_t r = p.list[it];
         const uint64_t beg = p.fpos[uint64_t(p.W[r]) * p.s];
         const uint32_t m = uint32_t(p.fpos[uint64_t(p.W[r + 1]) * p.s] - beg);
-        process_read_cta<KeyT>(p, r, A, Hh, m, static_cast<KeyT*>(p.loc) + beg, true, threadIdx.x, blockDim.x);
+        process_read_cta<KeyT>(p, r, A, Hh, m, static_cast<KeyT*>(p.loc) + beg, true, threadIdx.x, blockDim.x, reinterpret_cast<int32_t*>(A));
     }
 }
 
@@ -780,7 +800,8 @@ q_cand_global_kernel(const CandParams p)
         const uint64_t beg = p.fpos[uint64_t(p.W[r]) * p.s];
         const uint64_t m64 = p.fpos[uint64_t(p.W[r + 1]) * p.s] - beg;
         KeyT* A = static_cast<KeyT*>(p.loc) + beg;
-        process_read_cta<KeyT>(p, r, A, p.hits_scratch + beg, uint32_t(m64), A, false, threadIdx.x, blockDim.x);
+        process_read_cta<KeyT>(p, r, A, p.hits_scratch + beg, uint32_t(m64), A, false, threadIdx.x, blockDim.x,
+                               reinterpret_cast<int32_t*>(p.hits_scratch2 + beg));
     }
 }
 
@@ -987,6 +1008,7 @@ static void fill_cand_params(mcg_db* db, const mcg_query_opts* o, const int64_t*
     p.loc = c->q_loc.p;
     p.wbits = db->wbits;
     p.hits_scratch = nullptr;
+    p.hits_scratch2 = nullptr;
     p.list = nullptr;
     p.list_count = nullptr;
     p.K = o->maxcand;
@@ -1012,7 +1034,8 @@ static int query_back(mcg_db* db, const mcg_query_opts* o, const int64_t* doffs1
     const int ksz = k32 ? 4 : 8;
     static bool configured = false;
     if(!configured) {
-        MCG_CUDA(cudaFuncSetAttribute(q_cand_warp_kernel<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * Q_SMALL * 12));
+        MCG_CUDA(cudaFuncSetAttribute(q_cand_warp_kernel<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * Q_SMALL * 20));
+        MCG_CUDA(cudaFuncSetAttribute(q_cand_warp_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * Q_SMALL * 16));
         MCG_CUDA(cudaFuncSetAttribute(q_cand_cta_kernel<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, Q_LARGE * 12));
         MCG_CUDA(cudaFuncSetAttribute(q_cand_cta_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, Q_LARGE * 8));
         configured = true;
@@ -1020,8 +1043,8 @@ static int query_back(mcg_db* db, const mcg_query_opts* o, const int64_t* doffs1
     if(run.cls[0] > 0) {
         p.list = lists; p.list_count = counters;
         const unsigned g = unsigned(std::min<uint64_t>((run.cls[0] + 7) / 8, uint64_t(kNumSMs) * 16));
-        if(k32) q_cand_warp_kernel<uint32_t><<<g, 256, 8 * Q_SMALL * (ksz + 4), c->stream>>>(p);
-        else    q_cand_warp_kernel<uint64_t><<<g, 256, 8 * Q_SMALL * (ksz + 4), c->stream>>>(p);
+        if(k32) q_cand_warp_kernel<uint32_t><<<g, 256, 8 * Q_SMALL * (ksz + 12), c->stream>>>(p);
+        else    q_cand_warp_kernel<uint64_t><<<g, 256, 8 * Q_SMALL * (ksz + 12), c->stream>>>(p);
         c->launches++;
     }
     if(run.cls[1] > 0) {
@@ -1039,8 +1062,9 @@ static int query_back(mcg_db* db, const mcg_query_opts* o, const int64_t* doffs1
         c->launches++;
     }
     if(run.cls[3] > 0) {
-        MCG_TRY(c->tmp4.reserve((run.total + 2) * 4));
+        MCG_TRY(c->tmp4.reserve((run.total + 2) * 8));
         p.hits_scratch = c->tmp4.as<uint32_t>();
+        p.hits_scratch2 = c->tmp4.as<uint32_t>() + run.total + 2;
         p.list = lists + uint64_t(3) * n; p.list_count = counters + 3;
         const unsigned g = unsigned(std::min<uint64_t>(run.cls[3], uint64_t(kNumSMs) * 2));
         if(k32) q_cand_global_kernel<uint32_t><<<g, 1024, 0, c->stream>>>(p);
