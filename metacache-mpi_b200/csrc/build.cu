@@ -95,42 +95,135 @@ __global__ void emit_locations_kernel(const uint32_t* keys, const uint32_t* slot
     locs[offs[j] + r] = (uint64_t(tgt_id[lo]) << 32) | win;
 }
 
+// ---- ordered table construction (layout and rule: common.cuh, "feature table")
 __global__ void table_clear_kernel(uint4* table, uint64_t nbuckets)
 {
-    const uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;      // one uint4 = an eighth of a bucket
-    if(i < 8 * nbuckets) table[i] = (i & 7) ? make_uint4(0u, 0u, 0u, 0u) : make_uint4(EMPTY_KEY, EMPTY_KEY, EMPTY_KEY, 0u);
+    const uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;      // key sector of bucket i (payloads are
+    if(i < nbuckets) table[8 * i] = make_uint4(EMPTY_KEY, EMPTY_KEY, EMPTY_KEY, 0u);   // only read after a key match)
 }
 
-__global__ void table_insert_kernel(uint32_t* table, uint32_t nbuckets, const uint32_t* ukeys, const uint8_t* sizes,
-                                    const uint64_t* offs, const uint64_t* locs, uint32_t nkeys)
+// cdf[c] = number of keys below c << (32 - TABLE_CDF_BITS)
+__global__ void table_cdf_kernel(const uint32_t* ukeys, uint32_t nkeys, uint32_t* cdf)
 {
-    const uint64_t j = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
-    if(j >= nkeys) return;
-    const uint32_t key = ukeys[j];
-    const uint32_t size = sizes[j];
-    const uint64_t o = offs[j];
-    const uint64_t l0 = size > 0 ? locs[o] : 0ull, l1 = size > 1 ? locs[o + 1] : 0ull;
-    uint32_t b = table_bucket(key, nbuckets);
-    for(;;) {
-        uint32_t* line = table + uint64_t(b) * TABLE_BUCKET_WORDS;
-        // look first, then claim: one compare-and-swap per key unless another thread was faster
-        const uint4 k4 = __ldcg(reinterpret_cast<const uint4*>(line));
-        int t = k4.x == EMPTY_KEY ? 0 : (k4.y == EMPTY_KEY ? 1 : (k4.z == EMPTY_KEY ? 2 : 3));
-        for(; t < TABLE_BUCKET_SLOTS; ++t) {
-            if(atomicCAS(line + t, EMPTY_KEY, key) == EMPTY_KEY) {
-                // the slot's payload is one whole 32-byte sector: no fill from DRAM
-                uint4* pay = reinterpret_cast<uint4*>(line + 8 + 8 * t);
-                pay[0] = make_uint4(size, 0u, uint32_t(o), uint32_t(o >> 32));
-                pay[1] = make_uint4(uint32_t(l0), uint32_t(l0 >> 32), uint32_t(l1), uint32_t(l1 >> 32));
-                return;
-            }
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if(c > (1u << TABLE_CDF_BITS)) return;
+    if(c == (1u << TABLE_CDF_BITS)) { cdf[c] = nkeys; return; }
+    const uint32_t bound = c << (32 - TABLE_CDF_BITS);
+    uint32_t lo = 0, hi = nkeys;
+    while(lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if(ukeys[mid] < bound) lo = mid + 1; else hi = mid;
+    }
+    cdf[c] = lo;
+}
+
+constexpr int TB_THREADS = 256, TB_ITEMS = 8, TB_TILE = TB_THREADS * TB_ITEMS;
+
+// d_j = 3 * home_j - j; slot_j = j + max_{i <= j} d_i.  Pass 1: maximum of d per tile.
+__global__ void __launch_bounds__(TB_THREADS)
+table_tilemax_kernel(const uint32_t* ukeys, uint32_t nkeys, TableGeom g, int64_t* tmax)
+{
+    __shared__ int64_t s[TB_THREADS / 32];
+    const uint64_t base = uint64_t(blockIdx.x) * TB_TILE + uint64_t(threadIdx.x) * TB_ITEMS;
+    int64_t m = INT64_MIN;
+    for(int t = 0; t < TB_ITEMS; ++t) {
+        const uint64_t j = base + t;
+        if(j < nkeys) m = max(m, int64_t(TABLE_BUCKET_SLOTS) * table_bucket(ukeys[j], g) - int64_t(j));
+    }
+    for(int d = 16; d > 0; d >>= 1) m = max(m, __shfl_down_sync(0xFFFFFFFFu, m, d));
+    if((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if(threadIdx.x == 0) {
+        for(int w = 1; w < TB_THREADS / 32; ++w) m = max(m, s[w]);
+        tmax[blockIdx.x] = m;
+    }
+}
+
+// pass 2 (one block): exclusive running maximum over the tiles; out[ntiles] = overall maximum
+__global__ void __launch_bounds__(1024)
+table_tilescan_kernel(int64_t* tmax, uint32_t ntiles)
+{
+    __shared__ int64_t s[32];
+    __shared__ int64_t s_carry;
+    if(threadIdx.x == 0) s_carry = INT64_MIN;
+    __syncthreads();
+    for(uint32_t b0 = 0; b0 < ntiles; b0 += 1024) {
+        const uint32_t i = b0 + threadIdx.x;
+        const int64_t own = i < ntiles ? tmax[i] : INT64_MIN;
+        int64_t v = own;
+        for(int d = 1; d < 32; d <<= 1) {
+            const int64_t o = __shfl_up_sync(0xFFFFFFFFu, v, d);
+            if(int(threadIdx.x & 31) >= d) v = max(v, o);
         }
-        if(++b == nbuckets) b = 0;
+        if((threadIdx.x & 31) == 31) s[threadIdx.x >> 5] = v;
+        __syncthreads();
+        int64_t pre = s_carry;
+        for(uint32_t w = 0; w < (threadIdx.x >> 5); ++w) pre = max(pre, s[w]);
+        const int64_t incl = max(pre, v);
+        // exclusive value of element i = max(carry, everything before i)
+        int64_t excl = __shfl_up_sync(0xFFFFFFFFu, incl, 1);
+        if((threadIdx.x & 31) == 0) {
+            excl = s_carry;
+            for(uint32_t w = 0; w < (threadIdx.x >> 5); ++w) excl = max(excl, s[w]);
+        }
+        __syncthreads();
+        if(i < ntiles) tmax[i] = excl;
+        if(threadIdx.x == 1023) s_carry = incl;
+        __syncthreads();
+    }
+    if(threadIdx.x == 0) tmax[ntiles] = s_carry;
+}
+
+// pass 3: running maximum inside the tile (+ carry of pass 2) -> slot of every key; keys and
+// payloads are written front to back
+__global__ void __launch_bounds__(TB_THREADS)
+table_place_kernel(uint32_t* table, const uint32_t* ukeys, const uint8_t* sizes, const uint64_t* offs, const uint64_t* locs,
+                   uint32_t nkeys, TableGeom g, const int64_t* tcarry)
+{
+    __shared__ int64_t s[TB_THREADS / 32];
+    const uint64_t base = uint64_t(blockIdx.x) * TB_TILE + uint64_t(threadIdx.x) * TB_ITEMS;
+    int64_t d[TB_ITEMS];
+    int64_t m = INT64_MIN;
+#pragma unroll
+    for(int t = 0; t < TB_ITEMS; ++t) {
+        const uint64_t j = base + t;
+        d[t] = j < nkeys ? int64_t(TABLE_BUCKET_SLOTS) * table_bucket(ukeys[j], g) - int64_t(j) : INT64_MIN;
+        m = max(m, d[t]);
+        d[t] = m;                                   // inclusive running maximum inside the thread
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int64_t v = m;
+    for(int dd = 1; dd < 32; dd <<= 1) {
+        const int64_t o = __shfl_up_sync(0xFFFFFFFFu, v, dd);
+        if(lane >= dd) v = max(v, o);
+    }
+    if(lane == 31) s[warp] = v;
+    __syncthreads();
+    int64_t pre = tcarry[blockIdx.x];
+    for(int w = 0; w < warp; ++w) pre = max(pre, s[w]);
+    int64_t before = __shfl_up_sync(0xFFFFFFFFu, v, 1);     // maximum of the lanes before this one
+    if(lane == 0) before = INT64_MIN;
+    pre = max(pre, before);
+#pragma unroll
+    for(int t = 0; t < TB_ITEMS; ++t) {
+        const uint64_t j = base + t;
+        if(j >= nkeys) break;
+        const uint64_t slot = uint64_t(int64_t(j) + max(pre, d[t]));
+        const uint64_t bkt = slot / TABLE_BUCKET_SLOTS;
+        const uint32_t st = uint32_t(slot - bkt * TABLE_BUCKET_SLOTS);
+        const uint32_t size = sizes[j];
+        const uint64_t o = offs[j];
+        const uint64_t l0 = size > 0 ? locs[o] : 0ull, l1 = size > 1 ? locs[o + 1] : 0ull;
+        uint32_t* line = table + bkt * TABLE_BUCKET_WORDS;
+        line[st] = ukeys[j];
+        uint4* pay = reinterpret_cast<uint4*>(line + 8 + 8 * st);
+        pay[0] = make_uint4(size, 0u, uint32_t(o), uint32_t(o >> 32));
+        pay[1] = make_uint4(uint32_t(l0), uint32_t(l0 >> 32), uint32_t(l1), uint32_t(l1 >> 32));
     }
 }
 
 // clear(bucket) for a list of keys: hash_multimap.h:720 -- the key stays, its list is emptied
-__global__ void remove_keys_kernel(uint32_t* table, uint32_t nbuckets, const uint32_t* ukeys, uint8_t* sizes, uint32_t nkeys,
+__global__ void remove_keys_kernel(uint32_t* table, TableGeom g, const uint32_t* ukeys, uint8_t* sizes, uint32_t nkeys,
                                    const uint32_t* rem, uint64_t nrem, unsigned long long* removed)
 {
     const uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
@@ -144,14 +237,14 @@ __global__ void remove_keys_kernel(uint32_t* table, uint32_t nbuckets, const uin
     if(lo >= nkeys || ukeys[lo] != key) return;
     atomicAdd(removed, 1ull);                       // found (reference counts found keys, :410-413)
     sizes[lo] = 0;
-    uint32_t b = table_bucket(key, nbuckets);
+    uint32_t b = table_bucket(key, g);
     for(;;) {
         uint32_t* line = table + uint64_t(b) * TABLE_BUCKET_WORDS;
         const uint4 k4 = *reinterpret_cast<const uint4*>(line);
         const int t = table_match(k4, key);
         if(t >= 0) { line[8 + 8 * t] = 0u; return; }
         if(t == -1) return;
-        if(++b == nbuckets) b = 0;
+        ++b;
     }
 }
 
@@ -180,16 +273,37 @@ static inline unsigned grid_for(uint64_t n, int threads = 256) { return unsigned
 static int build_table(mcg_db* db)
 {
     mcg_ctx* c = db->ctx;
-    const uint64_t cap = uint64_t(double(db->nkeys) / TABLE_LOAD / double(TABLE_BUCKET_SLOTS)) + 16;      // buckets
+    const uint64_t nkeys = db->nkeys;
+    MCG_REQUIRE(nkeys < (1ull << 32), "too many keys in one shard");
+    const uint64_t home = uint64_t(double(nkeys) / TABLE_LOAD / double(TABLE_BUCKET_SLOTS)) + 1;      // home buckets
+    MCG_REQUIRE(home < (1ull << 31), "feature table too large");
+    db->table_scale = nkeys > 0 ? uint32_t(std::min<uint64_t>((home << 32) / nkeys, 0xFFFFFFFFull)) : 0u;
+    MCG_TRY(db->cdf.reserve(((1u << TABLE_CDF_BITS) + 2) * sizeof(uint32_t)));
+    table_cdf_kernel<<<((1u << TABLE_CDF_BITS) + 256) / 256, 256, 0, c->stream>>>(db->keys.as<uint32_t>(), uint32_t(nkeys), db->cdf.as<uint32_t>());
+    c->launches++;
+    const TableGeom g = db->geom();
+    // slot of the last key = nkeys - 1 + max_j (3 * home_j - j): the table ends right after it
+    uint64_t last_slot = 0;
+    const uint32_t ntiles = uint32_t((nkeys + TB_TILE - 1) / TB_TILE);
+    if(nkeys > 0) {
+        MCG_TRY(c->tmp5.reserve((size_t(ntiles) + 2) * sizeof(int64_t)));
+        table_tilemax_kernel<<<ntiles, TB_THREADS, 0, c->stream>>>(db->keys.as<uint32_t>(), uint32_t(nkeys), g, c->tmp5.as<int64_t>());
+        table_tilescan_kernel<<<1, 1024, 0, c->stream>>>(c->tmp5.as<int64_t>(), ntiles);
+        c->launches += 2;
+        int64_t dmax = 0;
+        MCG_TRY(copy_out(c, &dmax, c->tmp5.as<int64_t>() + ntiles, sizeof(int64_t)));
+        last_slot = uint64_t(int64_t(nkeys) - 1 + dmax);
+    }
+    const uint64_t cap = last_slot / TABLE_BUCKET_SLOTS + 2;        // + an empty bucket that ends every walk
     MCG_REQUIRE(cap < (1ull << 32), "feature table too large");
     MCG_TRY(db->table.reserve(cap * 128));
     db->table_cap = cap;
-    table_clear_kernel<<<grid_for(8 * cap), 256, 0, c->stream>>>(db->table.as<uint4>(), cap);
+    table_clear_kernel<<<grid_for(cap), 256, 0, c->stream>>>(db->table.as<uint4>(), cap);
     c->launches++;
-    if(db->nkeys > 0) {
-        table_insert_kernel<<<grid_for(db->nkeys), 256, 0, c->stream>>>(
-            db->table.as<uint32_t>(), uint32_t(cap), db->keys.as<uint32_t>(), db->sizes.as<uint8_t>(), db->offs.as<uint64_t>(),
-            db->locs.as<uint64_t>(), uint32_t(db->nkeys));
+    if(nkeys > 0) {
+        table_place_kernel<<<ntiles, TB_THREADS, 0, c->stream>>>(db->table.as<uint32_t>(), db->keys.as<uint32_t>(), db->sizes.as<uint8_t>(),
+                                                                db->offs.as<uint64_t>(), db->locs.as<uint64_t>(), uint32_t(nkeys), g,
+                                                                c->tmp5.as<int64_t>());
         c->launches++;
     }
     MCG_CUDA(cudaGetLastError());
@@ -326,7 +440,7 @@ int db_remove_keys_dev(mcg_db* db, const uint32_t* d_keys, uint64_t n, uint64_t*
     if(n > 0 && db->nkeys > 0) {
         MCG_TRY(c->tmp3.reserve(64));
         MCG_CUDA(cudaMemsetAsync(c->tmp3.p, 0, 8, c->stream));
-        remove_keys_kernel<<<grid_for(n), 256, 0, c->stream>>>(db->table.as<uint32_t>(), uint32_t(db->table_cap), db->keys.as<uint32_t>(),
+        remove_keys_kernel<<<grid_for(n), 256, 0, c->stream>>>(db->table.as<uint32_t>(), db->geom(), db->keys.as<uint32_t>(),
                                                               db->sizes.as<uint8_t>(), uint32_t(db->nkeys), d_keys, n,
                                                               c->tmp3.as<unsigned long long>());
         c->launches++;
@@ -371,7 +485,7 @@ int mcg_db_destroy(mcg_db* db)
     if(db == nullptr) return MCG_OK;
     cudaSetDevice(db->ctx->device);
     cudaStreamSynchronize(db->ctx->stream);
-    db->feat.release(); db->keys.release(); db->offs.release(); db->sizes.release(); db->locs.release(); db->table.release();
+    db->feat.release(); db->keys.release(); db->offs.release(); db->sizes.release(); db->locs.release(); db->table.release(); db->cdf.release();
     delete db;
     return MCG_OK;
 }

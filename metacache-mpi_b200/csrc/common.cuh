@@ -55,6 +55,12 @@ struct DevBuf {
 
 void release_cached_device_memory();
 
+// parameters of the feature table's bucket function (see "feature table" below)
+struct TableGeom {
+    const uint32_t* cdf;      // [2^TABLE_CDF_BITS + 1] keys below each cell boundary
+    uint32_t scale;           // floor(home buckets * 2^32 / nkeys)
+};
+
 }  // namespace mcg
 
 // ------------------------------------------------------------------ context / db
@@ -94,6 +100,9 @@ struct mcg_db {
     mcg::DevBuf keys, offs, sizes;    // unique keys ascending, uint64 offsets, uint8 sizes
     mcg::DevBuf locs;                 // uint64 (tgt << 32 | win)
     mcg::DevBuf table;                // 128-byte buckets of 3 slots (layout: table_bucket below); table_cap = buckets
+    mcg::DevBuf cdf;                  // cumulative key histogram of the bucket function
+    uint32_t table_scale = 0;
+    mcg::TableGeom geom() const { mcg::TableGeom g; g.cdf = cdf.as<uint32_t>(); g.scale = table_scale; return g; }
     uint64_t nkeys = 0, nlocs = 0, table_cap = 0;
     // per-read match keys: (tgt << wbits) | win; 32-bit when target and window ids fit together
     int wbits = 32;
@@ -133,17 +142,27 @@ __host__ __device__ __forceinline__ uint32_t slot_mix(uint32_t x)
 // every slot's payload (uint32 words of the line):
 //   [0..2] keys   [3..7] unused
 //   [8 + 8t ..] payload of slot t: size (u32), pad, off (u64 index into locs), loc0 (u64), loc1 (u64)
-// bucket = umulhi(slot_mix(key), nbuckets); a key lives in the first bucket at or after its home
-// bucket that had a free slot (linear probing over buckets).  A probe is ONE line -- what an L1
-// miss fetches anyway -- and the first two locations of a list come with it.  An insert is one
-// compare-and-swap in the key sector plus ONE full-sector payload store (no read-modify-write).
+// The home bucket of a key is MONOTONE in the key: bucket = rank_estimate(key) * nbuckets / nkeys,
+// where rank_estimate interpolates a 4096-cell cumulative histogram of the shard's keys (16 KB,
+// stays in L1).  Keys are bottom-s hashes, i.e. far from uniform, but locally uniform inside a
+// cell, so bucket loads are as even as with a random hash -- and because the unique keys leave
+// the radix sort ascending, the whole table is written front to back by a max-scan
+// (slot_j = max(3 * home_j, slot_{j-1} + 1)): no atomics, no random writes.  A key lives in the
+// first bucket at or after its home bucket that had a free slot when it was placed; lookups walk
+// forward until the key or a free slot shows up (the table ends with an empty bucket: no wrap).
+// A probe is ONE line -- what an L1 miss fetches anyway -- with the first two locations of the list.
 constexpr uint32_t TABLE_EMPTY = 0xFFFFFFFFu;
 constexpr int TABLE_BUCKET_WORDS = 32;
 constexpr int TABLE_BUCKET_SLOTS = 3;
+constexpr int TABLE_CDF_BITS = 12;
 
-__host__ __device__ __forceinline__ uint32_t table_bucket(uint32_t key, uint32_t nbuckets)
+__device__ __forceinline__ uint32_t table_bucket(uint32_t key, const TableGeom& g)
 {
-    return uint32_t((uint64_t(slot_mix(key)) * nbuckets) >> 32);
+    constexpr int SH = 32 - TABLE_CDF_BITS;
+    const uint32_t c = key >> SH;
+    const uint32_t lo = __ldg(g.cdf + c), hi = __ldg(g.cdf + c + 1);
+    const uint32_t rank = lo + uint32_t((uint64_t(hi - lo) * (key & ((1u << SH) - 1u))) >> SH);
+    return uint32_t((uint64_t(rank) * g.scale) >> 32);
 }
 
 // slot of `key` in a bucket whose key sector starts with k4: 0..2, -1 = absent but the bucket

@@ -56,7 +56,7 @@ __global__ void q_out_first2_kernel(const uint32_t* W, const uint32_t* wf1, int6
 // hash_multimap.h:779-789 / 1034-1047 find, on the bucketized table (common.cuh): walk the buckets
 // from the key's home bucket until the key or a free slot shows up
 __global__ void __launch_bounds__(256)
-q_find_kernel(const uint32_t* __restrict__ feat, uint64_t nslots, const uint32_t* __restrict__ table, uint32_t nbuckets,
+q_find_kernel(const uint32_t* __restrict__ feat, uint64_t nslots, const uint32_t* __restrict__ table, const TableGeom g,
               uint8_t* __restrict__ flen, uint64_t* __restrict__ foff)
 {
     const uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
@@ -65,7 +65,7 @@ q_find_kernel(const uint32_t* __restrict__ feat, uint64_t nslots, const uint32_t
     uint32_t len = 0;
     uint64_t off = 0;
     if(f != EMPTY_KEY) {
-        uint32_t b = table_bucket(f, nbuckets);
+        uint32_t b = table_bucket(f, g);
         for(;;) {
             const uint32_t* line = table + uint64_t(b) * TABLE_BUCKET_WORDS;
             const uint4 k4 = __ldg(reinterpret_cast<const uint4*>(line));
@@ -77,7 +77,7 @@ q_find_kernel(const uint32_t* __restrict__ feat, uint64_t nslots, const uint32_t
                 break;
             }
             if(t == -1) break;
-            if(++b == nbuckets) b = 0;
+            ++b;
         }
     }
     flen[i] = uint8_t(len);
@@ -519,7 +519,7 @@ q_cand_warp_kernel(const CandParams p)
 struct FusedParams {
     uint32_t* feat;
     const uint32_t* table;      // 128-byte buckets of 3 slots (common.cuh)
-    uint32_t nbuckets;
+    TableGeom geom;
     const uint64_t* locs;
     int64_t n;
     uint8_t* done;
@@ -670,7 +670,7 @@ q_fused_warp_kernel(const CandParams p, const FusedParams f)
                 if(sl < ns) key[c] = f.feat[s0 + sl];
             }
             pend[c] = key[c] != EMPTY_KEY;
-            bkt[c] = table_bucket(key[c], f.nbuckets);
+            bkt[c] = pend[c] ? table_bucket(key[c], f.geom) : 0u;
             len[c] = 0; off[c] = 0; loc0[c] = 0; loc1[c] = 0;
         }
         for(;;) {
@@ -696,7 +696,7 @@ q_fused_warp_kernel(const CandParams p, const FusedParams f)
                     } else if(t == -1) {
                         pend[c] = false;
                     } else {
-                        if(++bkt[c] == f.nbuckets) bkt[c] = 0;
+                        ++bkt[c];
                         again = true;
                     }
                 }
@@ -961,7 +961,7 @@ static int query_find_gather(mcg_db* db, const mcg_query_opts* o, int64_t n, int
     MCG_TRY(c->q_foff.reserve((nslots + 1) * 8));
     MCG_TRY(c->q_fpos.reserve((nslots + 2) * 8));
     if(nslots > 0) {
-        q_find_kernel<<<grid_for(nslots), 256, 0, c->stream>>>(c->q_feat.as<uint32_t>(), nslots, db->table.as<uint32_t>(), uint32_t(db->table_cap),
+        q_find_kernel<<<grid_for(nslots), 256, 0, c->stream>>>(c->q_feat.as<uint32_t>(), nslots, db->table.as<uint32_t>(), db->geom(),
                                                               c->q_flen.as<uint8_t>(), c->q_foff.as<uint64_t>());
         c->launches++;
     }
@@ -1105,7 +1105,7 @@ int query_batch_dev(mcg_db* db, const mcg_query_opts* o,
         CandParams p;
         fill_cand_params(db, o, doffs1, d2 ? doffs2 : nullptr, d_out_tax, d_out_hits, d_out_n, 0, &p);
         FusedParams f;
-        f.feat = c->q_feat.as<uint32_t>(); f.table = db->table.as<uint32_t>(); f.nbuckets = uint32_t(db->table_cap);
+        f.feat = c->q_feat.as<uint32_t>(); f.table = db->table.as<uint32_t>(); f.geom = db->geom();
         f.locs = db->locs.as<uint64_t>(); f.n = n; f.done = c->q_done.as<uint8_t>(); f.left_over = left;
         // feature slots per lane: 2 (reads of <= 64 slots, e.g. 2 x 150 bp at sketchlen 16) keeps the
         // registers at the level of 6 resident CTAs; longer reads take the 4-slot variant
