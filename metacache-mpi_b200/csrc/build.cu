@@ -98,8 +98,10 @@ __global__ void emit_locations_kernel(const uint32_t* keys, const uint32_t* slot
 // ---- ordered table construction (layout and rule: common.cuh, "feature table")
 __global__ void table_clear_kernel(uint4* table, uint64_t nbuckets)
 {
-    const uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;      // key sector of bucket i (payloads are
-    if(i < nbuckets) table[8 * i] = make_uint4(EMPTY_KEY, EMPTY_KEY, EMPTY_KEY, 0u);   // only read after a key match)
+    // the 32-byte key sector of every bucket, as a whole sector (no fill from DRAM); payload
+    // sectors are only ever read after a key match
+    const uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
+    if(i < 2 * nbuckets) table[8 * (i >> 1) + (i & 1)] = (i & 1) ? make_uint4(0u, 0u, 0u, 0u) : make_uint4(EMPTY_KEY, EMPTY_KEY, EMPTY_KEY, 0u);
 }
 
 // cdf[c] = number of keys below c << (32 - TABLE_CDF_BITS)
@@ -298,7 +300,7 @@ static int build_table(mcg_db* db)
     MCG_REQUIRE(cap < (1ull << 32), "feature table too large");
     MCG_TRY(db->table.reserve(cap * 128));
     db->table_cap = cap;
-    table_clear_kernel<<<grid_for(cap), 256, 0, c->stream>>>(db->table.as<uint4>(), cap);
+    table_clear_kernel<<<grid_for(2 * cap), 256, 0, c->stream>>>(db->table.as<uint4>(), cap);
     c->launches++;
     if(nkeys > 0) {
         table_place_kernel<<<ntiles, TB_THREADS, 0, c->stream>>>(db->table.as<uint32_t>(), db->keys.as<uint32_t>(), db->sizes.as<uint8_t>(),
