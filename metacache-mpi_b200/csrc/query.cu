@@ -185,46 +185,12 @@ __device__ __forceinline__ void topk_insert(TopK& L, int K, int32_t tax, uint32_
 }
 
 // the same list held one entry per lane (entry i in lane i): insertion is a handful of ballots and
-// one shuffle instead of loops over a local-memory array.  All 32 lanes call it with uniform arguments.
+// one shuffle instead of loops over a local-memory array (warp_topk_insert_lifted below).
 struct WarpTopK {
     int32_t tax;        // lane i: entry i (valid for i < n)
     uint32_t hits;
     int n;              // uniform
 };
-
-__device__ __forceinline__ void warp_topk_insert(WarpTopK& L, int K, int32_t tax, uint32_t hits, int lowest, int lane,
-                                                 const int32_t* __restrict__ lineage, const uint8_t* __restrict__ rank)
-{
-    if(tax < 0) return;
-    if(lowest > MCG_RANK_SEQUENCE) {
-        const int32_t anc = lineage[int64_t(tax) * MCG_NUM_RANKS + lowest];
-        if(anc >= 0) tax = anc;
-    }
-    const bool live = lane < L.n;
-    int pos = -1;
-    if(rank[tax] != MCG_RANK_SEQUENCE) {
-        const uint32_t hit = __ballot_sync(0xFFFFFFFFu, live && L.tax == tax);
-        if(hit) pos = __ffs(int(hit)) - 1;
-    }
-    const int32_t up_tax = __shfl_up_sync(0xFFFFFFFFu, L.tax, 1);
-    const uint32_t up_hits = __shfl_up_sync(0xFFFFFFFFu, L.hits, 1);
-    if(pos >= 0) {
-        // taxon already listed: keep the larger hit count and move it left past strictly smaller ones
-        const uint32_t old = __shfl_sync(0xFFFFFFFFu, L.hits, pos);
-        const uint32_t h = hits > old ? hits : old;
-        const int j = __popc(__ballot_sync(0xFFFFFFFFu, lane < pos && L.hits >= h));
-        if(lane > j && lane <= pos) { L.tax = up_tax; L.hits = up_hits; }
-        if(lane == j) { L.tax = tax; L.hits = h; }
-        return;
-    }
-    const int i0 = __popc(__ballot_sync(0xFFFFFFFFu, live && L.hits >= hits));      // upper bound, descending list
-    if(i0 < L.n || L.n < K) {
-        const int last = L.n < K ? L.n : K - 1;
-        if(lane > i0 && lane <= last) { L.tax = up_tax; L.hits = up_hits; }
-        if(lane == i0) { L.tax = tax; L.hits = hits; }
-        if(L.n < K) L.n++;
-    }
-}
 
 // ------------------------------------------------------------------ K4 + K5
 // Match keys: (tgt << wbits) | win.  When target and window ids of the shard fit 32 bits together
@@ -288,15 +254,6 @@ __device__ __forceinline__ uint32_t hits_ending_at(const KeyT* A, uint32_t i, ui
         if(A[mid] < lowkey) lo = mid + 1; else hi = mid;
     }
     return i - lo + 1;
-}
-
-__device__ __forceinline__ void write_toplist(const CandParams& p, uint32_t r, const TopK& L)
-{
-    for(int c = 0; c < p.K; ++c) {
-        p.out_tax[uint64_t(r) * p.K + c] = c < L.n ? L.tax[c] : -1;
-        p.out_hits[uint64_t(r) * p.K + c] = c < L.n ? L.hits[c] : 0u;
-    }
-    p.out_n[r] = L.n;
 }
 
 // ascending bitonic network in the "flip" formulation: every comparator is (lo < hi,
