@@ -466,7 +466,34 @@ def run_extras(args, ctx, api, synth, taxonomy, torch, dist, dev, stream, world,
     e1.record(stream)
     barrier()
     qms = max_over_ranks(e0.elapsed_time(e1)) / qsteps
+    launches_q = int((ctx.launches() - l0) / qsteps)
     st = stats.cpu().numpy()
+    # the same batch through the host entry point: pinned host reads in, top lists out (H2D / query / D2H pipelined)
+    qe2e = None
+    try:
+        hb1 = torch.from_numpy(b1).pin_memory(); hb2 = torch.from_numpy(b2).pin_memory()
+        hot = torch.empty((npairs, Kc), dtype=torch.int32, pin_memory=True)
+        hoh = torch.empty((npairs, Kc), dtype=torch.int32, pin_memory=True)
+        hon = torch.empty(npairs, dtype=torch.int32, pin_memory=True)
+
+        def qhost():
+            rc = L.mcg_query_batch(db.h, C.byref(q), hb1.data_ptr(), o1.ctypes.data, hb2.data_ptr(), o2.ctypes.data, npairs,
+                                   hot.data_ptr(), hoh.data_ptr(), hon.data_ptr())
+            if rc != 0:
+                raise RuntimeError(L.mcg_last_error().decode())
+        qhost()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            qhost()
+        barrier()
+        qe = max_over_ranks(time.perf_counter() - t0) / 3
+        same_q = bool((hon.numpy() == ln.cpu().numpy()).all()) if world == 1 else None
+        qe2e = {"value": 2 * npairs / qe, "unit": "reads/s", "ms_per_batch": 1e3 * qe,
+                "h2d_bytes_per_step": int(len(b1) + len(b2) + 16 * (npairs + 1)), "d2h_bytes_per_step": int(npairs * (8 * Kc + 4)),
+                "api": "mcg_query_batch (pinned host buffers, per-shard top lists)", "same_as_device_path": same_q}
+    except Exception as e:
+        qe2e = {"error": repr(e)}
     # byte accounting per pair on this shard: 300 B reads + 32 B per probed feature + 8 B per location + 8K
     nfeat = 4 * 16
     mloc = None
@@ -483,7 +510,7 @@ def run_extras(args, ctx, api, synth, taxonomy, torch, dist, dev, stream, world,
                                 "-maxcand 4 -hitmin 4 -hitdiff 80; reads resident, per-rank top lists: %s, merge+classify on rank 0"
                                 % (npairs, QG, world, gather_mode),
                     "classified": int(st[20]), "unclassified": int(st[21]),
-                    "mean_locations_per_pair_shard0": mloc, "gpu_launches_per_batch": int((ctx.launches() - l0) / qsteps),
+                    "mean_locations_per_pair_shard0": mloc, "gpu_launches_per_batch": launches_q, "e2e": qe2e,
                     "roofline": {"bound": "hbm", "achieved": algq / (qms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                                  "frac": algq / (qms * 1e-3) / 1e9 / peak, "traffic": None}}
     # long reads (BASELINE.json configs[4] shape): 10 kbp reads, ~89 windows / ~1400 features per read, staged path

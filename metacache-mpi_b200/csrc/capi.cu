@@ -297,7 +297,9 @@ int mcg_sketch_windows_dev(mcg_ctx* c, const mcg_sketch_cfg* cfg,
                          d_out_features, d_out_counts);
 }
 
-static int ensure_pipeline(mcg_ctx* c)
+}  // extern "C"
+namespace mcg {
+int ensure_pipeline(mcg_ctx* c)
 {
     if(c->s_h2d != nullptr) return MCG_OK;
     MCG_CUDA(cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
@@ -309,6 +311,8 @@ static int ensure_pipeline(mcg_ctx* c)
     MCG_CUDA(cudaEventCreateWithFlags(&c->ev_misc, cudaEventDisableTiming));
     return MCG_OK;
 }
+}  // namespace mcg
+extern "C" {
 
 // Host path: the input is cut into chunks of windows; chunk i+1 is copied to the device
 // (H2D stream) while chunk i is sketched (ctx stream) and the sketches of chunk i-1 travel

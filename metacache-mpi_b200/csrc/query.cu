@@ -24,6 +24,7 @@ namespace mcg {
 int copy_in(mcg_ctx* c, void* d, const void* h, size_t bytes);
 int copy_out(mcg_ctx* c, void* h, const void* d, size_t bytes);
 int exclusive_scan_u32_to_u32(mcg_ctx* c, const uint32_t* d_in, uint32_t* d_out, uint64_t n);
+int ensure_pipeline(mcg_ctx* c);
 
 constexpr uint32_t EMPTY_KEY = 0xFFFFFFFFu;
 constexpr int Q_SMALL = 512;       // matches per read handled by one warp
@@ -1170,6 +1171,10 @@ int mcg_query_batch_dev(mcg_db* db, const mcg_query_opts* o,
                            d_out_tax, d_out_hits, d_out_ncand, 0, nullptr);
 }
 
+// Host path.  The batch is cut into sub-batches: while sub-batch i is queried (ctx stream), the
+// reads of sub-batch i+1 are copied in (H2D stream, second staging buffer) and the top lists of
+// sub-batch i-1 travel back (D2H stream) -- PCIe is full duplex, so the call costs about the H2D
+// copy of the reads instead of H2D + query + D2H.
 int mcg_query_batch(mcg_db* db, const mcg_query_opts* o,
                     const char* reads1, const int64_t* offs1,
                     const char* reads2, const int64_t* offs2, int64_t n,
@@ -1179,20 +1184,70 @@ int mcg_query_batch(mcg_db* db, const mcg_query_opts* o,
     MCG_REQUIRE(n >= 0, "n < 0");
     if(n == 0) return MCG_OK;
     MCG_REQUIRE(out_tax && out_hits && out_ncand, "output buffers are NULL");
+    MCG_REQUIRE(offs1[0] == 0, "offs1[0] must be 0");
+    if(reads2 != nullptr) MCG_REQUIRE(offs2 != nullptr && offs2[0] == 0, "offs2[0] must be 0");
     mcg_ctx* c = db->ctx;
     MCG_CUDA(cudaSetDevice(c->device));
     MCG_TRY(check_opts(db, o));
-    const char *d1, *d2; const int64_t *do1, *do2; int64_t b1, b2;
-    MCG_TRY(stage_reads(c, reads1, offs1, reads2, offs2, n, &d1, &do1, &b1, &d2, &do2, &b2));
+    MCG_TRY(ensure_pipeline(c));
     const int K = o->maxcand;
+    static int64_t sub_reads = -1;
+    if(sub_reads < 0) { const char* e = getenv("MCG_QUERY_SUB"); sub_reads = e ? atoll(e) : 262144; if(sub_reads < 1) sub_reads = 1; }
+    const int64_t nsub = (n + sub_reads - 1) / sub_reads;
+    // staging: two buffers, each [reads1 | pad | reads2 | slack]; offsets [2 buffers][2 mates][sub+1]
+    int64_t maxb1 = 0, maxb2 = 0;
+    for(int64_t i = 0; i < nsub; ++i) {
+        const int64_t a = i * sub_reads, b = std::min(n, a + sub_reads);
+        maxb1 = std::max(maxb1, offs1[b] - offs1[a]);
+        if(reads2) maxb2 = std::max(maxb2, offs2[b] - offs2[a]);
+    }
+    const size_t pad1 = (size_t(maxb1) + 127) & ~size_t(63);
+    const size_t bufsz = pad1 + ((size_t(maxb2) + 127) & ~size_t(63));
+    const size_t offsz = size_t(std::min(n, sub_reads) + 1);
+    MCG_TRY(c->seq.reserve(2 * bufsz + 64));
+    MCG_TRY(c->seqoff.reserve(4 * offsz * 8));
     MCG_TRY(c->q_out_tax.reserve(size_t(n) * K * 4));
     MCG_TRY(c->q_out_hits.reserve(size_t(n) * K * 4));
     MCG_TRY(c->q_out_n.reserve(size_t(n) * 4));
-    MCG_TRY(query_batch_dev(db, o, d1, do1, b1, d2, do2, b2, n, c->q_out_tax.as<int32_t>(), c->q_out_hits.as<uint32_t>(),
-                            c->q_out_n.as<int32_t>(), 0, nullptr));
-    MCG_TRY(copy_out(c, out_tax, c->q_out_tax.p, size_t(n) * K * 4));
-    MCG_TRY(copy_out(c, out_hits, c->q_out_hits.p, size_t(n) * K * 4));
-    MCG_TRY(copy_out(c, out_ncand, c->q_out_n.p, size_t(n) * 4));
+    MCG_CUDA(cudaEventRecord(c->ev_misc, c->stream));
+    MCG_CUDA(cudaStreamWaitEvent(c->s_h2d, c->ev_misc, 0));     // staging buffers are ours from here on
+    MCG_CUDA(cudaStreamWaitEvent(c->s_d2h, c->ev_misc, 0));
+    auto stage = [&](int64_t i) -> int {
+        const int slot = int(i & 1);
+        const int64_t a = i * sub_reads, b = std::min(n, a + sub_reads);
+        char* dbuf = c->seq.as<char>() + size_t(slot) * bufsz;
+        int64_t* doff = c->seqoff.as<int64_t>() + size_t(slot) * 2 * offsz;
+        if(i >= 2) MCG_CUDA(cudaStreamWaitEvent(c->s_h2d, c->ev_k[slot], 0));      // the buffer's previous user is done
+        // the (small) offset arrays first: they usually come from pageable memory, whose copy blocks the
+        // host until everything queued before it on the stream is done
+        MCG_CUDA(cudaMemcpyAsync(doff, offs1 + a, size_t(b - a + 1) * 8, cudaMemcpyHostToDevice, c->s_h2d));
+        if(reads2) MCG_CUDA(cudaMemcpyAsync(doff + offsz, offs2 + a, size_t(b - a + 1) * 8, cudaMemcpyHostToDevice, c->s_h2d));
+        MCG_CUDA(cudaMemcpyAsync(dbuf, reads1 + offs1[a], size_t(offs1[b] - offs1[a]), cudaMemcpyHostToDevice, c->s_h2d));
+        if(reads2) MCG_CUDA(cudaMemcpyAsync(dbuf + pad1, reads2 + offs2[a], size_t(offs2[b] - offs2[a]), cudaMemcpyHostToDevice, c->s_h2d));
+        MCG_CUDA(cudaEventRecord(c->ev_h2d[slot], c->s_h2d));
+        return MCG_OK;
+    };
+    MCG_TRY(stage(0));
+    for(int64_t i = 0; i < nsub; ++i) {
+        const int slot = int(i & 1);
+        const int64_t a = i * sub_reads, b = std::min(n, a + sub_reads);
+        if(i + 1 < nsub) MCG_TRY(stage(i + 1));
+        MCG_CUDA(cudaStreamWaitEvent(c->stream, c->ev_h2d[slot], 0));
+        // the offsets keep their values of the whole batch: the base pointers are moved instead
+        const char* d1 = c->seq.as<char>() + size_t(slot) * bufsz - offs1[a];
+        const int64_t* do1 = c->seqoff.as<int64_t>() + size_t(slot) * 2 * offsz;
+        const char* d2 = reads2 ? c->seq.as<char>() + size_t(slot) * bufsz + pad1 - offs2[a] : nullptr;
+        const int64_t* do2 = reads2 ? do1 + offsz : nullptr;
+        MCG_TRY(query_batch_dev(db, o, d1, do1, offs1[b] - offs1[a], d2, do2, reads2 ? offs2[b] - offs2[a] : 0, b - a,
+                                c->q_out_tax.as<int32_t>() + a * K, c->q_out_hits.as<uint32_t>() + a * K,
+                                c->q_out_n.as<int32_t>() + a, 0, nullptr));
+        MCG_CUDA(cudaEventRecord(c->ev_k[slot], c->stream));
+        MCG_CUDA(cudaStreamWaitEvent(c->s_d2h, c->ev_k[slot], 0));
+        MCG_CUDA(cudaMemcpyAsync(out_tax + a * K, c->q_out_tax.as<int32_t>() + a * K, size_t(b - a) * K * 4, cudaMemcpyDeviceToHost, c->s_d2h));
+        MCG_CUDA(cudaMemcpyAsync(out_hits + a * K, c->q_out_hits.as<uint32_t>() + a * K, size_t(b - a) * K * 4, cudaMemcpyDeviceToHost, c->s_d2h));
+        MCG_CUDA(cudaMemcpyAsync(out_ncand + a, c->q_out_n.as<int32_t>() + a, size_t(b - a) * 4, cudaMemcpyDeviceToHost, c->s_d2h));
+    }
+    MCG_CUDA(cudaStreamSynchronize(c->s_d2h));
     MCG_CUDA(cudaStreamSynchronize(c->stream));
     return MCG_OK;
 }

@@ -130,3 +130,40 @@ def test_query_window_overrides(ctx, oracle):
         ct, ch, cn, mt, mh, mn, best, brank, stats = _gpu_full(ctx, gd, q, w.b1, w.o1, w.b2, w.o2)
         et, eh, en, eb, er, es = oracle.query_batch(od, w.tax, oq, w.b1, w.o1, w.b2, w.o2)
         assert (mn == en).all() and (mt == et).all() and (mh == eh).all() and (best == eb).all() and (stats == es).all()
+
+
+def test_host_path_sub_batches(tmp_path):
+    """mcg_query_batch cuts a batch into pipelined sub-batches (MCG_QUERY_SUB reads each): the
+    results must not depend on the cut.  Own processes: the knob is read once per process."""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import sys, numpy as np\n"
+        "sys.path.insert(0, %r)\n"
+        "from __graft_entry__ import load_package; load_package()\n"
+        "from metacache_mpi_b200 import api, synth, taxonomy\n"
+        "ctx = api.Context(0)\n"
+        "G = 6\n"
+        "genomes = [synth.genome(g, 60000) for g in range(G)]\n"
+        "ids, par, rk, species = synth.make_taxonomy(G)\n"
+        "tabs = taxonomy.TaxonomyTables(ids, par, rk, species)\n"
+        "ctx.upload_taxonomy(tabs.lineage, tabs.rank, G)\n"
+        "db = api.Database(ctx)\n"
+        "db.add_targets(np.concatenate(genomes), np.arange(G + 1, dtype=np.int64) * 60000, np.arange(G, dtype=np.uint32))\n"
+        "db.finalize()\n"
+        "b1, o1, b2, o2, truth = synth.make_read_pairs(genomes, 1000, seed=3)\n"
+        "q = api.make_query_opts(maxcand=4, lowest=4, hitmin=4, hitdiff=0.8)\n"
+        "ct, ch, cn = db.query_batch(q, b1, o1, b2, o2)\n"
+        "st, sh, sn = db.query_batch(q, b1, o1, None, None)\n"
+        "np.savez(sys.argv[1], ct=ct, ch=ch, cn=cn, st=st, sh=sh, sn=sn)\n"
+    ) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))),)
+    outs = []
+    for sub in ("37", "1000000"):
+        f = str(tmp_path / ("q%s.npz" % sub))
+        r = subprocess.run([sys.executable, "-c", code, f], env=dict(os.environ, MCG_QUERY_SUB=sub), capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append(np.load(f))
+    for k in ("ct", "ch", "cn", "st", "sh", "sn"):
+        assert (outs[0][k] == outs[1][k]).all(), k
+    assert (outs[0]["cn"] > 0).sum() > 900
