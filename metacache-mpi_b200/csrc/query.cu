@@ -13,10 +13,13 @@
 //   classification_statistics.h:70-78 assign
 //
 // Pipeline per batch (all on the ctx stream):
-//   window counts -> 3 scans -> K1 (mate 1, mate 2) -> find (one 16-byte slot probe per
-//   feature) -> scan of list lengths -> read binning -> gather -> per-read bitonic sort
-//   in shared memory + window-range scan + top list (size-binned: warp / CTA / big CTA /
-//   global-memory fallback).
+//   window counts -> 3 scans -> K1 (mate 1, mate 2) -> q_fused_warp_kernel: one warp per read
+//   (pair) probes the bucket table (one 128-byte line per probe, common.cuh "feature table"),
+//   gathers, sorts, scans the window ranges and builds the top list, all in shared memory.
+//   Reads it cannot hold (> 128 matches or > 32 * NC feature slots, i.e. long reads) take the
+//   staged path: find -> scan of list lengths -> read binning -> gather -> size-binned sorters
+//   (warp / CTA / big CTA / global-memory fallback) with the same window-range + top-list logic.
+//   The host entry point mcg_query_batch cuts a batch into sub-batches and overlaps H2D, query and D2H.
 #include "common.cuh"
 
 namespace mcg {

@@ -1,5 +1,7 @@
-// sketch.cu -- K1: 2-bit encode + canonical k-mer + thomas_mueller_hash +
-// per-window bottom-s unique selection, fused.  Must equal
+// sketch.cu -- K1, warp-per-window formulation (the path for sketchlen > 16 or windows > 512
+// bases; everything else runs sketch_tpw.cu) + the host side of both: window prefix, tile table,
+// launch.  2-bit encode + canonical k-mer + thomas_mueller_hash + per-window bottom-s unique
+// selection, fused.  Must equal
 //   dna_encoding.h:261-276 (windows), :305-348 (2-bit k-mers + ambiguity),
 //   :114-121,189-197 (reverse complement, canonical), hash_int.h:40-45 (hash),
 //   hash_dna.h:115-152 (bottom-s unique, ascending, 0xFFFFFFFF never a feature).
