@@ -19,6 +19,7 @@
 // FASTA/FASTQ reading, NCBI taxonomy files, text output.  They are written from the formats the
 // reference reads and writes, not from its code.
 #include <algorithm>
+#include <charconv>
 #include <chrono>
 #include <cstdint>
 #include <cstdio>
@@ -30,10 +31,12 @@
 #include <set>
 #include <sstream>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
 #include <dirent.h>
+#include <unistd.h>
 #include <sys/stat.h>
 
 #include "../../include/mcgpu.h"
@@ -44,7 +47,8 @@ namespace {
 [[noreturn]] void die(const std::string& msg)
 {
     std::cerr << "metacache_b200: " << msg << std::endl;
-    std::exit(1);
+    std::fflush(nullptr);
+    _exit(1);                 // no static destructors: a background thread may still be running
 }
 
 void check(int rc, const char* what)
@@ -123,14 +127,31 @@ std::string db_name(std::string n)            // args_handling.cpp:34-45
     return n;
 }
 
-template<class T> void wr(std::ostream& os, T x) { os.write(reinterpret_cast<const char*>(&x), sizeof(x)); }
-template<class T> void rd(std::istream& is, T& x) { is.read(reinterpret_cast<char*>(&x), sizeof(x)); }
-void wr_str(std::ostream& os, const std::string& s) { wr<uint64_t>(os, s.size()); os.write(s.data(), std::streamsize(s.size())); }
-void rd_str(std::istream& is, std::string& s)
+// minimal ostream-like sink over a std::string: the per-read output is formatted by several threads
+// into their own buffers and written in order (decimal integers print like operator<< of ostream)
+struct StrOut {
+    std::string s;
+    StrOut& operator<<(const std::string& x) { s += x; return *this; }
+    StrOut& operator<<(const char* x) { s += x; return *this; }
+    StrOut& operator<<(char x) { s += x; return *this; }
+    template<class I, class = typename std::enable_if<std::is_integral<I>::value>::type>
+    StrOut& operator<<(I x)
+    {
+        char b[24];
+        auto r = std::to_chars(b, b + sizeof(b), x);
+        s.append(b, size_t(r.ptr - b));
+        return *this;
+    }
+};
+
+unsigned host_threads()
 {
-    uint64_t n = 0; rd(is, n); s.assign(size_t(n), '\0');
-    if(n) is.read(&s[0], std::streamsize(n));
+    unsigned t = std::thread::hardware_concurrency();
+    return t < 1 ? 1 : (t > 32 ? 32 : t);
 }
+
+template<class T> void wr(std::ostream& os, T x) { os.write(reinterpret_cast<const char*>(&x), sizeof(x)); }
+void wr_str(std::ostream& os, const std::string& s) { wr<uint64_t>(os, s.size()); os.write(s.data(), std::streamsize(s.size())); }
 
 // ------------------------------------------------------------------------------- taxonomy
 struct Taxon {
@@ -306,6 +327,51 @@ void parse_sequences(const std::string& txt, std::vector<Record>& out)
     }
 }
 
+// query reads: positions inside the file text instead of copies.  FASTQ records are 4 lines
+// (sequence_io.cpp:253-284); FASTA sequences may span lines and are then copied into `extra`.
+struct ReadRec { size_t hpos, hlen, spos, slen; bool in_extra; };
+
+void index_reads(const std::string& txt, std::vector<ReadRec>& out, std::string& extra)
+{
+    size_t p = 0;
+    const size_t n = txt.size();
+    const char* base = txt.data();
+    auto line_end = [&](size_t s) { const void* e = std::memchr(base + s, '\n', n - s); return e ? size_t(static_cast<const char*>(e) - base) : n; };
+    while(p < n && (txt[p] == '\n' || txt[p] == '\r')) ++p;
+    if(p >= n) return;
+    if(txt[p] == '@') {
+        while(p < n && txt[p] == '@') {
+            size_t e = line_end(p);
+            ReadRec r;
+            r.hpos = p + 1; r.hlen = e - p - 1; r.in_extra = false;
+            if(r.hlen && txt[r.hpos + r.hlen - 1] == '\r') --r.hlen;
+            p = e + 1;
+            if(p > n) break;
+            e = line_end(p);
+            r.spos = p; r.slen = e - p;
+            if(r.slen && txt[r.spos + r.slen - 1] == '\r') --r.slen;
+            p = e + 1;
+            if(p >= n || txt[p] != '+') break;
+            p = line_end(p) + 1;               // quality header
+            p = line_end(p) + 1;               // qualities
+            out.push_back(r);
+        }
+    } else if(txt[p] == '>') {
+        std::vector<Record> recs;
+        parse_sequences(txt, recs);
+        size_t total = 0;
+        for(auto& r : recs) total += r.header.size() + r.data.size();
+        extra.reserve(total);
+        for(auto& r : recs) {
+            ReadRec x;
+            x.in_extra = true;
+            x.hpos = extra.size(); x.hlen = r.header.size(); extra += r.header;
+            x.spos = extra.size(); x.slen = r.data.size(); extra += r.data;
+            out.push_back(x);
+        }
+    }
+}
+
 std::string trimmed(const std::string& s)
 {
     size_t a = s.find_first_not_of(" \t\r\n"), b = s.find_last_not_of(" \t\r\n");
@@ -389,12 +455,21 @@ struct DbMeta {
     uint32_t ntargets = 0;
 };
 
-void write_shard(const std::string& file, const DbMeta& m, mcg_db* db)
+// device -> host bucket arrays of one shard
+struct ShardData { std::vector<uint32_t> keys, sizes, tg, wn; uint64_t ne = 0, nl = 0; };
+
+void export_shard(mcg_db* db, ShardData& d)
 {
-    uint64_t nk = 0, ne = 0, nl = 0;
-    check(mcg_db_counts(db, &nk, &ne, &nl), "mcg_db_counts");
-    std::vector<uint32_t> keys(ne ? ne : 1), sizes(ne ? ne : 1), tg(nl ? nl : 1), wn(nl ? nl : 1);
-    check(mcg_db_export(db, keys.data(), sizes.data(), tg.data(), wn.data()), "mcg_db_export");
+    uint64_t nk = 0;
+    check(mcg_db_counts(db, &nk, &d.ne, &d.nl), "mcg_db_counts");
+    d.keys.resize(d.ne ? d.ne : 1); d.sizes.resize(d.ne ? d.ne : 1); d.tg.resize(d.nl ? d.nl : 1); d.wn.resize(d.nl ? d.nl : 1);
+    check(mcg_db_export(db, d.keys.data(), d.sizes.data(), d.tg.data(), d.wn.data()), "mcg_db_export");
+}
+
+// host only (runs in one thread per shard): the reference's file layout, sketch_database.h:959-999
+void write_shard(const std::string& file, const DbMeta& m, const ShardData& d)
+{
+    const uint64_t ne = d.ne, nl = d.nl;
     std::ofstream os(file, std::ios::binary);
     if(!os.good()) die("can't open file " + file);
     wr<uint64_t>(os, 20181001);                                   // MC_DB_VERSION
@@ -410,61 +485,71 @@ void write_shard(const std::string& file, const DbMeta& m, mcg_db* db)
     }
     wr<uint32_t>(os, m.ntargets);
     wr<uint64_t>(os, ne); wr<uint64_t>(os, nl);
+    // per bucket: key u32, n u8, (n u64, n x tgt u32), (n u64, n x win u32)
+    std::string buf(size_t(ne) * 21 + size_t(nl) * 8, '\0');
+    char* q = &buf[0];
     uint64_t lo = 0;
-    std::string buf;
-    buf.reserve(size_t(ne) * 21 + size_t(nl) * 8);
-    auto put = [&](const void* p, size_t n) { buf.append(static_cast<const char*>(p), n); };
     for(uint64_t j = 0; j < ne; ++j) {
-        const uint32_t key = keys[j];
-        const uint8_t n8 = uint8_t(sizes[j]);
-        const uint64_t n = sizes[j];
-        put(&key, 4); put(&n8, 1);
-        put(&n, 8); put(&tg[lo], size_t(n) * 4);
-        put(&n, 8); put(&wn[lo], size_t(n) * 4);
+        const uint32_t key = d.keys[j];
+        const uint64_t n = d.sizes[j];
+        const uint8_t n8 = uint8_t(n);
+        std::memcpy(q, &key, 4); q += 4;
+        *q++ = char(n8);
+        std::memcpy(q, &n, 8); q += 8;
+        std::memcpy(q, &d.tg[lo], size_t(n) * 4); q += n * 4;
+        std::memcpy(q, &n, 8); q += 8;
+        std::memcpy(q, &d.wn[lo], size_t(n) * 4); q += n * 4;
         lo += n;
-        if(buf.size() > (size_t(64) << 20)) { os.write(buf.data(), std::streamsize(buf.size())); buf.clear(); }
     }
-    os.write(buf.data(), std::streamsize(buf.size()));
+    os.write(buf.data(), std::streamsize(q - buf.data()));
+    if(!os.good()) die("could not write " + file);
 }
 
 // returns the bucket arrays of a shard file written by this program or by the reference
 void read_shard(const std::string& file, DbMeta& m, bool meta_only,
                 std::vector<uint32_t>& keys, std::vector<uint32_t>& sizes, std::vector<uint32_t>& tg, std::vector<uint32_t>& wn)
 {
-    std::ifstream is(file, std::ios::binary);
-    if(!is.good()) die("can't open file " + file);
-    uint64_t ver = 0; rd(is, ver);
+    std::string txt;
+    if(!read_text_file(file, txt)) die("can't open file " + file);
+    const char* p = txt.data();
+    const char* const end = p + txt.size();
+    auto need = [&](size_t n) { if(size_t(end - p) < n) die("database " + file + " is truncated or corrupt"); };
+    auto get = [&](auto& x) { need(sizeof(x)); std::memcpy(&x, p, sizeof(x)); p += sizeof(x); };
+    auto get_str = [&](std::string& x) { uint64_t n = 0; get(n); need(size_t(n)); x.assign(p, size_t(n)); p += n; };
+    uint64_t ver = 0; get(ver);
     if(ver != 20181001) die("database " + file + " has incompatible version " + std::to_string(ver));
-    uint8_t w[6]; for(auto& x : w) rd(is, x);
+    uint8_t w[6]; for(auto& x : w) get(x);
     if(w[0] != 4 || w[1] != 4 || w[2] != 4 || w[3] != 1 || w[4] != 8 || w[5] != 21) die("database " + file + " uses different data type sizes");
-    uint64_t k, s, wl, ws, qk;
-    rd(is, k); rd(is, s); rd(is, wl); rd(is, ws);
-    m.tcfg.k = int32_t(k); m.tcfg.sketchlen = int32_t(s); m.tcfg.winlen = int64_t(wl); m.tcfg.winstride = int64_t(ws);
-    rd(is, qk); rd(is, m.qsketch); rd(is, m.qwinlen); rd(is, m.qstride);
-    rd(is, m.maxlocs);
-    uint64_t nt = 0; rd(is, nt);
+    uint64_t k, sk, wl, ws, qk;
+    get(k); get(sk); get(wl); get(ws);
+    m.tcfg.k = int32_t(k); m.tcfg.sketchlen = int32_t(sk); m.tcfg.winlen = int64_t(wl); m.tcfg.winstride = int64_t(ws);
+    get(qk); get(m.qsketch); get(m.qwinlen); get(m.qstride);
+    get(m.maxlocs);
+    uint64_t nt = 0; get(nt);
     m.tax.taxa.clear();
     for(uint64_t i = 0; i < nt; ++i) {
         Taxon t;
-        rd(is, t.id); rd(is, t.parent); rd(is, t.rank); rd_str(is, t.name); rd_str(is, t.file); rd(is, t.index); rd(is, t.windows);
+        get(t.id); get(t.parent); get(t.rank); get_str(t.name); get_str(t.file); get(t.index); get(t.windows);
         m.tax.taxa[t.id] = t;
     }
-    rd(is, m.ntargets);
+    get(m.ntargets);
     if(meta_only) return;
-    uint64_t nk = 0, nv = 0; rd(is, nk); rd(is, nv);
+    uint64_t nk = 0, nv = 0; get(nk); get(nv);
     keys.resize(nk); sizes.resize(nk); tg.resize(nv); wn.resize(nv);
     uint64_t lo = 0;
     for(uint64_t j = 0; j < nk; ++j) {
-        uint8_t n8 = 0; rd(is, keys[j]); rd(is, n8);
+        uint8_t n8 = 0; get(keys[j]); get(n8);
         sizes[j] = n8;
         if(n8 > 0) {
             uint64_t n = 0;
-            rd(is, n); is.read(reinterpret_cast<char*>(&tg[lo]), std::streamsize(n * 4));
-            rd(is, n); is.read(reinterpret_cast<char*>(&wn[lo]), std::streamsize(n * 4));
+            get(n); if(lo + n > nv) die("database " + file + " is truncated or corrupt");
+            need(size_t(n) * 4); std::memcpy(&tg[lo], p, size_t(n) * 4); p += n * 4;
+            get(n);
+            need(size_t(n) * 4); std::memcpy(&wn[lo], p, size_t(n) * 4); p += n * 4;
             lo += n;
         }
     }
-    if(!is.good() || lo != nv) die("database " + file + " is truncated or corrupt");
+    if(lo != nv) die("database " + file + " is truncated or corrupt");
 }
 
 std::vector<mcg_ctx*> g_ctx;        // one per device
@@ -479,15 +564,33 @@ mcg_ctx* ctx_for_shard(int shard)
     return g_ctx[d];
 }
 
+// CUDA start-up (driver initialisation + context creation: 1-2 s on an 8-GPU box) runs in the
+// background while the main thread reads and parses files
+std::thread g_gpu_init;
+void start_gpu_init(int nshards)
+{
+    g_gpu_init = std::thread([nshards] { for(int r = 0; r < nshards && r < mcg_device_count(); ++r) ctx_for_shard(r); });
+}
+void wait_gpu_init() { if(g_gpu_init.joinable()) g_gpu_init.join(); }
+
 double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+// phase timer on stderr (MCG_TRACE=1)
+struct Lap {
+    bool on = getenv("MCG_TRACE") != nullptr;
+    double t = now();
+    void operator()(const char* what) { if(on) { const double n = now(); std::fprintf(stderr, "[metacache_b200] %-28s %8.1f ms\n", what, 1e3 * (n - t)); t = n; } }
+};
 
 // ------------------------------------------------------------------------------- build
 int mode_build(const Args& a)
 {
     if(a.pos.size() < 2) die("usage: metacache_b200 build <database> <sequence files / directories ...> [options]");
+    Lap lap;
     const std::string dbfile = db_name(a.pos[0]);
-    int P = int(a.geti({"gpus", "np"}, std::max(1, mcg_device_count())));
-    if(P < 1) P = 1;
+    int P = int(a.geti({"gpus", "np"}, 0));
+    if(P < 1) P = std::max(1, mcg_device_count());          // one shard per GPU unless told otherwise
+    start_gpu_init(P);
     DbMeta m;
     m.tcfg.k = int32_t(a.geti({"kmerlen"}, 16));
     m.tcfg.sketchlen = int32_t(a.geti({"sketchlen"}, 16));
@@ -511,8 +614,13 @@ int mode_build(const Args& a)
     std::sort(files.begin(), files.end());                                     // mode_build.cpp:575
     if(files.empty()) die("no sequence files found");
 
+    lap("taxonomy + file list");
     std::vector<mcg_db*> dbs(static_cast<size_t>(P), nullptr);
-    for(int r = 0; r < P; ++r) check(mcg_db_create(ctx_for_shard(r), &m.tcfg, maxlocs_arg, r, P, &dbs[size_t(r)]), "mcg_db_create");
+    auto ensure_dbs = [&]() {          // first use of the GPUs: their start-up ran beside the file parsing
+        if(dbs[0] != nullptr) return;
+        wait_gpu_init();
+        for(int r = 0; r < P; ++r) check(mcg_db_create(ctx_for_shard(r), &m.tcfg, maxlocs_arg, r, P, &dbs[size_t(r)]), "mcg_db_create");
+    };
 
     const double t0 = now();
     // per-shard batches of owned targets
@@ -522,6 +630,7 @@ int mode_build(const Args& a)
     auto flush = [&](int r) {
         Batch& b = batch[size_t(r)];
         if(b.ids.empty()) return;
+        ensure_dbs();
         std::vector<uint32_t> wins(b.ids.size());
         check(mcg_db_add_targets(dbs[size_t(r)], b.bytes.data(), b.offs.data(), b.ids.data(), int64_t(b.ids.size()), wins.data()),
               "mcg_db_add_targets");
@@ -560,9 +669,14 @@ int mode_build(const Args& a)
             if(b.bytes.size() > (size_t(512) << 20)) flush(r);
         }
     }
+    lap("parse sequence files");
+    ensure_dbs();
+    lap("wait for CUDA start-up");
     for(int r = 0; r < P; ++r) flush(r);
+    lap("add_targets");
     m.ntargets = ntargets;
     for(int r = 0; r < P; ++r) check(mcg_db_finalize(dbs[size_t(r)]), "mcg_db_finalize");
+    lap("finalize");
     const double t1 = now();
     std::cout << "Added " << ntargets << " reference sequences (" << total_bp << " bp) in " << (t1 - t0) << " s" << std::endl;
     if(remove_over) {
@@ -570,17 +684,26 @@ int mode_build(const Args& a)
         check(mcg_remove_overpopulated(dbs.data(), P, &rem), "mcg_remove_overpopulated");
         std::cout << rem << " overpopulated feature lists removed" << std::endl;
     }
-    for(int r = 0; r < P; ++r) {
-        // source.windows is only known on the owning rank (sketch_database.h:541), 0 elsewhere
-        DbMeta mr = m;
-        for(uint32_t t = 0; t < ntargets; ++t) mr.tax.taxa[-int64_t(t) - 1].windows = (int(t % uint32_t(P)) == r) ? target_windows[t] : 0;
-        const std::string out = dbfile + "_" + std::to_string(r);
-        write_shard(out, mr, dbs[size_t(r)]);
-        uint64_t nk = 0, ne = 0, nl = 0;
-        mcg_db_counts(dbs[size_t(r)], &nk, &ne, &nl);
-        std::cout << "shard " << r << ": features " << ne << " dead " << (nk - ne) << " locations " << nl << " -> " << out << std::endl;
-        mcg_db_destroy(dbs[size_t(r)]);
+    {
+        // device -> host per shard, then one writer thread per shard
+        std::vector<ShardData> data(static_cast<size_t>(P));
+        std::vector<DbMeta> metas(static_cast<size_t>(P), m);
+        std::vector<std::thread> writers;
+        for(int r = 0; r < P; ++r) {
+            // source.windows is only known on the owning rank (sketch_database.h:541), 0 elsewhere
+            DbMeta& mr = metas[size_t(r)];
+            for(uint32_t t = 0; t < ntargets; ++t) mr.tax.taxa[-int64_t(t) - 1].windows = (int(t % uint32_t(P)) == r) ? target_windows[t] : 0;
+            export_shard(dbs[size_t(r)], data[size_t(r)]);
+            const std::string out = dbfile + "_" + std::to_string(r);
+            uint64_t nk = 0, ne = 0, nl = 0;
+            mcg_db_counts(dbs[size_t(r)], &nk, &ne, &nl);
+            std::cout << "shard " << r << ": features " << ne << " dead " << (nk - ne) << " locations " << nl << " -> " << out << std::endl;
+            mcg_db_destroy(dbs[size_t(r)]);
+            writers.emplace_back([&metas, &data, out, r] { write_shard(out, metas[size_t(r)], data[size_t(r)]); });
+        }
+        for(auto& w : writers) w.join();
     }
+    lap("write shards");
     std::cout << "Total build time: " << (now() - t0) << " s" << std::endl;
     return 0;
 }
@@ -594,7 +717,8 @@ struct OutOpt {
     std::string comment = "# ", none = "--", col = "\t|\t", taxsep = ",", ranksuf = ":", idpre = "(", idsuf = ")";
 };
 
-void show_one_taxon(std::ostream& os, const OutOpt& o, const Taxon* t)
+template<class OS>
+void show_one_taxon(OS& os, const OutOpt& o, const Taxon* t)
 {
     if(o.show_ranks) os << RANK_NAMES[t->rank] << o.ranksuf;
     if(o.mode == 1) os << t->id;
@@ -602,7 +726,8 @@ void show_one_taxon(std::ostream& os, const OutOpt& o, const Taxon* t)
     else os << t->name;
 }
 
-void show_no_taxon(std::ostream& os, const OutOpt& o, int r)
+template<class OS>
+void show_no_taxon(OS& os, const OutOpt& o, int r)
 {
     if(o.show_ranks) os << RANK_NAMES[r] << o.ranksuf;
     if(o.mode == 1) os << 0;
@@ -611,7 +736,8 @@ void show_no_taxon(std::ostream& os, const OutOpt& o, int r)
 }
 
 // printing.cpp:305-330 show_taxon (collapseUnclassified = true)
-void show_classification(std::ostream& os, const OutOpt& o, const TaxTables& tt, int32_t best)
+template<class OS>
+void show_classification(OS& os, const OutOpt& o, const TaxTables& tt, int32_t best)
 {
     if(best < 0 || tt.rank[size_t(best)] > o.highest) {
         if(o.mode == 1) os << 0; else os << o.none;
@@ -635,15 +761,27 @@ int mode_query(const Args& a)
     if(P < 1) die("no shard files " + dbfile + "_<r> found");
     const bool paired = a.has({"pairfiles", "pair-files"}) && a.pos.size() >= 3;
 
-    // shards
+    // shards: CUDA starts up in the background while one thread per shard reads and parses its file
+    Lap lap;
+    start_gpu_init(P);
     std::vector<DbMeta> metas(static_cast<size_t>(P));
     std::vector<mcg_db*> dbs(static_cast<size_t>(P), nullptr);
-    for(int r = 0; r < P; ++r) {
-        std::vector<uint32_t> keys, sizes, tg, wn;
-        read_shard(dbfile + "_" + std::to_string(r), metas[size_t(r)], false, keys, sizes, tg, wn);
-        const DbMeta& m = metas[size_t(r)];
-        check(mcg_db_create(ctx_for_shard(r), &m.tcfg, int(m.maxlocs), r, P, &dbs[size_t(r)]), "mcg_db_create");
-        check(mcg_db_import(dbs[size_t(r)], keys.data(), sizes.data(), tg.data(), wn.data(), keys.size(), tg.size()), "mcg_db_import");
+    {
+        std::vector<ShardData> data(static_cast<size_t>(P));
+        std::vector<std::thread> readers;
+        for(int r = 0; r < P; ++r)
+            readers.emplace_back([&, r] { ShardData& d = data[size_t(r)]; read_shard(dbfile + "_" + std::to_string(r), metas[size_t(r)], false, d.keys, d.sizes, d.tg, d.wn); });
+        for(auto& t : readers) t.join();
+        lap("read shard files");
+        wait_gpu_init();
+        lap("wait for CUDA start-up");
+        for(int r = 0; r < P; ++r) {
+            const DbMeta& m = metas[size_t(r)];
+            const ShardData& d = data[size_t(r)];
+            check(mcg_db_create(ctx_for_shard(r), &m.tcfg, int(m.maxlocs), r, P, &dbs[size_t(r)]), "mcg_db_create");
+            check(mcg_db_import(dbs[size_t(r)], d.keys.data(), d.sizes.data(), d.tg.data(), d.wn.data(), d.keys.size(), d.tg.size()), "mcg_db_import");
+        }
+        lap("import shards to device");
     }
     const DbMeta& m0 = metas[0];
     TaxTables tt;
@@ -730,10 +868,19 @@ int mode_query(const Args& a)
 
     // reads
     const double t0 = now();
-    std::vector<Record> r1, r2;
-    { std::string txt; if(!read_text_file(a.pos[1], txt)) die("can't open file " + a.pos[1]); parse_sequences(txt, r1); }
-    if(paired) { std::string txt; if(!read_text_file(a.pos[2], txt)) die("can't open file " + a.pos[2]); parse_sequences(txt, r2); }
+    std::string txt1, txt2, extra1, extra2;
+    std::vector<ReadRec> r1, r2;
+    {
+        // the two read files are read and indexed by two threads
+        std::thread th2;
+        if(paired) th2 = std::thread([&] { if(!read_text_file(a.pos[2], txt2)) die("can't open file " + a.pos[2]); index_reads(txt2, r2, extra2); });
+        if(!read_text_file(a.pos[1], txt1)) die("can't open file " + a.pos[1]);
+        index_reads(txt1, r1, extra1);
+        if(th2.joinable()) th2.join();
+    }
+    auto seq_of = [](const ReadRec& r, const std::string& txt, const std::string& extra) { return (r.in_extra ? extra.data() : txt.data()) + r.spos; };
     const size_t nreads = paired ? std::min(r1.size(), r2.size()) : r1.size();
+    lap("read + index read files");
     const int K = q.maxcand;
     uint64_t stats[22] = {0};
     const size_t BATCH = size_t(1) << 20;
@@ -741,13 +888,28 @@ int mode_query(const Args& a)
     std::vector<int64_t> o1, o2;
     std::vector<int32_t> ctax, cn, mtax, mn, best, brank;
     std::vector<uint32_t> chits, mhits;
+    const unsigned NT = host_threads();
     for(size_t lo = 0; lo < nreads; lo += BATCH) {
         const size_t n = std::min(BATCH, nreads - lo);
-        b1.clear(); b2.clear(); o1.assign(1, 0); o2.assign(1, 0);
+        // batch buffers: offsets first, then the bases are copied by all threads
+        o1.assign(n + 1, 0); o2.assign(paired ? n + 1 : 1, 0);
         for(size_t i = 0; i < n; ++i) {
-            b1 += r1[lo + i].data; o1.push_back(int64_t(b1.size()));
-            if(paired) { b2 += r2[lo + i].data; o2.push_back(int64_t(b2.size())); }
+            o1[i + 1] = o1[i] + int64_t(r1[lo + i].slen);
+            if(paired) o2[i + 1] = o2[i] + int64_t(r2[lo + i].slen);
         }
+        b1.resize(size_t(o1[n])); b2.resize(paired ? size_t(o2[n]) : 0);
+        {
+            std::vector<std::thread> th;
+            for(unsigned t = 0; t < NT; ++t) th.emplace_back([&, t] {
+                const size_t ia = n * t / NT, ib = n * (t + 1) / NT;
+                for(size_t i = ia; i < ib; ++i) {
+                    std::memcpy(&b1[size_t(o1[i])], seq_of(r1[lo + i], txt1, extra1), r1[lo + i].slen);
+                    if(paired) std::memcpy(&b2[size_t(o2[i])], seq_of(r2[lo + i], txt2, extra2), r2[lo + i].slen);
+                }
+            });
+            for(auto& x : th) x.join();
+        }
+        lap("assemble batch");
         ctax.resize(size_t(P) * n * K); chits.resize(size_t(P) * n * K); cn.resize(size_t(P) * n);
         for(int r = 0; r < P; ++r) {
             check(mcg_query_batch(dbs[size_t(r)], &q, b1.data(), o1.data(), paired ? b2.data() : nullptr, paired ? o2.data() : nullptr,
@@ -757,32 +919,46 @@ int mode_query(const Args& a)
         mtax.resize(n * K); mhits.resize(n * K); mn.resize(n); best.resize(n); brank.resize(n);
         check(mcg_merge_classify(ctx_for_shard(0), &q, ctax.data(), chits.data(), cn.data(), P, int64_t(n), mtax.data(), mhits.data(),
                                  mn.data(), best.data(), brank.data(), stats), "mcg_merge_classify");
+        lap("query batch (device)");
         if(o.map == 2) continue;
-        std::string line;
-        for(size_t i = 0; i < n; ++i) {
-            if(o.map == 1 && best[i] < 0) continue;
-            std::ostringstream ls;
-            if(o.queryids) ls << (lo + i + 1) << o.col;
-            const std::string& h = r1[lo + i].header;
-            ls << h.substr(0, h.find(' ')) << o.col;
-            if(o.tophits) {                                                     // printing.cpp:333-360
-                for(int c = 0; c < mn[i] && mhits[i * K + c] > 0; ++c) {
-                    if(c > 0) ls << ',';
-                    const int32_t tx = mtax[i * K + c];
-                    const Taxon* t = tt.tax[size_t(tx)];
-                    if(q.lowest == 0) ls << t->name;
-                    else {
-                        const int32_t an = (t->rank < q.lowest) ? tt.lineage[size_t(tx) * 21 + size_t(q.lowest)] : tx;
-                        if(an >= 0) ls << tt.taxid[size_t(an)]; else ls << t->name;
+        // per-read lines: formatted by all threads into their own buffers, written in order
+        std::vector<StrOut> parts(NT);
+        {
+            std::vector<std::thread> th;
+            for(unsigned t = 0; t < NT; ++t) th.emplace_back([&, t] {
+                StrOut& ls = parts[t];
+                const size_t ia = n * t / NT, ib = n * (t + 1) / NT;
+                ls.s.reserve((ib - ia) * 96);
+                for(size_t i = ia; i < ib; ++i) {
+                    if(o.map == 1 && best[i] < 0) continue;
+                    if(o.queryids) ls << (lo + i + 1) << o.col;
+                    const ReadRec& rr = r1[lo + i];
+                    const char* h = (rr.in_extra ? extra1.data() : txt1.data()) + rr.hpos;
+                    const void* sp = std::memchr(h, ' ', rr.hlen);
+                    ls.s.append(h, sp ? size_t(static_cast<const char*>(sp) - h) : rr.hlen);
+                    ls << o.col;
+                    if(o.tophits) {                                                     // printing.cpp:333-360
+                        for(int c = 0; c < mn[i] && mhits[i * K + c] > 0; ++c) {
+                            if(c > 0) ls << ',';
+                            const int32_t tx = mtax[i * K + c];
+                            const Taxon* t2 = tt.tax[size_t(tx)];
+                            if(q.lowest == 0) ls << t2->name;
+                            else {
+                                const int32_t an = (t2->rank < q.lowest) ? tt.lineage[size_t(tx) * 21 + size_t(q.lowest)] : tx;
+                                if(an >= 0) ls << tt.taxid[size_t(an)]; else ls << t2->name;
+                            }
+                            ls << ':' << mhits[i * K + c];
+                        }
+                        ls << o.col;
                     }
-                    ls << ':' << mhits[i * K + c];
+                    show_classification(ls, o, tt, best[i]);
+                    ls << '\n';
                 }
-                ls << o.col;
-            }
-            show_classification(ls, o, tt, best[i]);
-            ls << '\n';
-            os << ls.str();
+            });
+            for(auto& x : th) x.join();
         }
+        for(auto& part : parts) os.write(part.s.data(), std::streamsize(part.s.size()));
+        lap("format + write output");
     }
     const double t1 = now();
     if(o.summary) {                                                             // printing.cpp:522-641
@@ -817,6 +993,7 @@ int mode_query(const Args& a)
 
 int main(int argc, char** argv)
 {
+    Lap total;
     if(argc < 2) {
         std::cerr << "usage: metacache_b200 build|query ... (see the header of host/metacache_b200.cpp)" << std::endl;
         return 1;
@@ -827,6 +1004,12 @@ int main(int argc, char** argv)
     if(mode == "build") rc = mode_build(a);
     else if(mode == "query") rc = mode_query(a);
     else die("unknown mode '" + mode + "' (build and query are implemented, like in the reference: README.md:37)");
+    wait_gpu_init();
+    total("whole run before teardown");
+    std::cout.flush();
+    std::fflush(nullptr);
+    if(getenv("MCG_SLOW_EXIT") == nullptr) _exit(rc);        // the driver reclaims the contexts faster than an orderly teardown
     for(mcg_ctx* c : g_ctx) if(c) mcg_ctx_destroy(c);
+    total("context teardown");
     return rc;
 }
