@@ -569,9 +569,29 @@ mcg_ctx* ctx_for_shard(int shard)
 std::thread g_gpu_init;
 void start_gpu_init(int nshards)
 {
-    g_gpu_init = std::thread([nshards] { for(int r = 0; r < nshards && r < mcg_device_count(); ++r) ctx_for_shard(r); });
+    g_gpu_init = std::thread([nshards] {
+        const int ndev = mcg_device_count();                      // driver initialisation
+        if(ndev < 1) die("no CUDA device available; there is no CPU fallback");
+        g_ctx.assign(size_t(ndev), nullptr);
+        std::vector<std::thread> th;                              // one context per GPU in use, created side by side
+        for(int d = 0; d < ndev && d < nshards; ++d)
+            th.emplace_back([d] { check(mcg_ctx_create(d, nullptr, &g_ctx[size_t(d)]), "mcg_ctx_create"); });
+        for(auto& t : th) t.join();
+    });
 }
 void wait_gpu_init() { if(g_gpu_init.joinable()) g_gpu_init.join(); }
+
+// f(shard) for every shard: one thread per GPU, the shards of a GPU one after the other (a context
+// is not re-entrant)
+template<class F>
+void for_each_shard_parallel(int P, F f)
+{
+    const int ndev = std::max(1, mcg_device_count());
+    if(ndev == 1 || P == 1) { for(int r = 0; r < P; ++r) f(r); return; }
+    std::vector<std::thread> th;
+    for(int d = 0; d < ndev && d < P; ++d) th.emplace_back([=] { for(int r = d; r < P; r += ndev) f(r); });
+    for(auto& t : th) t.join();
+}
 
 double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
@@ -672,10 +692,10 @@ int mode_build(const Args& a)
     lap("parse sequence files");
     ensure_dbs();
     lap("wait for CUDA start-up");
-    for(int r = 0; r < P; ++r) flush(r);
+    for_each_shard_parallel(P, [&](int r) { flush(r); });
     lap("add_targets");
     m.ntargets = ntargets;
-    for(int r = 0; r < P; ++r) check(mcg_db_finalize(dbs[size_t(r)]), "mcg_db_finalize");
+    for_each_shard_parallel(P, [&](int r) { check(mcg_db_finalize(dbs[size_t(r)]), "mcg_db_finalize"); });
     lap("finalize");
     const double t1 = now();
     std::cout << "Added " << ntargets << " reference sequences (" << total_bp << " bp) in " << (t1 - t0) << " s" << std::endl;
@@ -911,11 +931,11 @@ int mode_query(const Args& a)
         }
         lap("assemble batch");
         ctax.resize(size_t(P) * n * K); chits.resize(size_t(P) * n * K); cn.resize(size_t(P) * n);
-        for(int r = 0; r < P; ++r) {
+        for_each_shard_parallel(P, [&](int r) {          // every GPU queries its shard(s) with all reads of the batch
             check(mcg_query_batch(dbs[size_t(r)], &q, b1.data(), o1.data(), paired ? b2.data() : nullptr, paired ? o2.data() : nullptr,
                                   int64_t(n), ctax.data() + size_t(r) * n * K, chits.data() + size_t(r) * n * K, cn.data() + size_t(r) * n),
                   "mcg_query_batch");
-        }
+        });
         mtax.resize(n * K); mhits.resize(n * K); mn.resize(n); best.resize(n); brank.resize(n);
         check(mcg_merge_classify(ctx_for_shard(0), &q, ctax.data(), chits.data(), cn.data(), P, int64_t(n), mtax.data(), mhits.data(),
                                  mn.data(), best.data(), brank.data(), stats), "mcg_merge_classify");
