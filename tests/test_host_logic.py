@@ -40,3 +40,21 @@ def test_option_defaults_follow_reference():
     assert api.default_hitmin(16) == 5 and api.default_hitmin(5) == 2 and api.default_hitmin(3) == 1   # mode_query.cpp:247
     q = api.make_query_opts(hitdiff=float(np.float32(np.float64(np.float32(80.0)) * 0.01)))       # query_options.cpp:167
     assert abs(q.hitdiff - 0.8) < 1e-6
+
+
+def test_sorting_network_include_is_valid():
+    """csrc/sortnet16.inc (the register network of the thread-per-window sketch kernel) must be a
+    sorting network: 0-1 principle over all 2^16 inputs, checked on the committed file itself"""
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    txt = open(os.path.join(root, "metacache-mpi_b200", "csrc", "sortnet16.inc")).read()
+    ces = [(int(a), int(b)) for a, b in re.findall(r"SN_CE\((\d+), (\d+)\)", txt)]
+    assert 55 <= len(ces) <= 63 and all(0 <= a < b < 16 for a, b in ces)
+    import numpy as np
+    v = ((np.arange(1 << 16)[:, None] >> np.arange(16)[None, :]) & 1).astype(np.uint8)
+    for a, b in ces:
+        lo = np.minimum(v[:, a], v[:, b])
+        hi = np.maximum(v[:, a], v[:, b])
+        v[:, a], v[:, b] = lo, hi
+    assert (v[:, :-1] <= v[:, 1:]).all()
