@@ -277,7 +277,9 @@ static int build_table(mcg_db* db)
     mcg_ctx* c = db->ctx;
     const uint64_t nkeys = db->nkeys;
     MCG_REQUIRE(nkeys < (1ull << 32), "too many keys in one shard");
-    const uint64_t home = uint64_t(double(nkeys) / TABLE_LOAD / double(TABLE_BUCKET_SLOTS)) + 1;      // home buckets
+    static double load = -1.0;
+    if(load < 0) { const char* e = getenv("MCG_TABLE_LOAD"); load = e ? atof(e) : TABLE_LOAD; if(load < 0.05 || load > 0.95) load = TABLE_LOAD; }
+    const uint64_t home = uint64_t(double(nkeys) / load / double(TABLE_BUCKET_SLOTS)) + 1;      // home buckets
     MCG_REQUIRE(home < (1ull << 31), "feature table too large");
     db->table_scale = nkeys > 0 ? uint32_t(std::min<uint64_t>((home << 32) / nkeys, 0xFFFFFFFFull)) : 0u;
     MCG_TRY(db->cdf.reserve(((1u << TABLE_CDF_BITS) + 2) * sizeof(uint32_t)));
