@@ -158,11 +158,14 @@ int  mcg_tax_upload(mcg_ctx*, const int32_t* lineage, const uint8_t* rank,
  * make_classification_candidates (classification.cpp:210, candidates.h:119,236).
  * reads2/offs2 may be NULL (single-end).  Outputs [n][maxcand]: taxon index
  * (-1 = unused slot), hits; out_ncand[n]. */
+/* (host buffers: the batch is cut into sub-batches of 256 k reads and H2D copy, query and D2H copy of
+ * consecutive sub-batches overlap; pinned buffers make the copies asynchronous) */
 int  mcg_query_batch(mcg_db*, const mcg_query_opts*,
                      const char* reads1, const int64_t* offs1,
                      const char* reads2, const int64_t* offs2, int64_t n,
                      int32_t* out_tax, uint32_t* out_hits, int32_t* out_ncand);
-/* same with device-resident reads and outputs; offsets on the device */
+/* same with device-resident reads and outputs; offsets on the device; d_reads1 / d_reads2 must be
+ * readable up to bytes + 64 (the TMA span copies of the sketch kernel are 16-byte granular) */
 int  mcg_query_batch_dev(mcg_db*, const mcg_query_opts*,
                          const char* d_reads1, const int64_t* d_offs1, int64_t bytes1,
                          const char* d_reads2, const int64_t* d_offs2, int64_t bytes2,
