@@ -1092,6 +1092,9 @@ int query_batch_dev(mcg_db* db, const mcg_query_opts* o,
         uint32_t h_left = 0;
         MCG_CUDA(cudaMemcpyAsync(&h_left, left, 4, cudaMemcpyDeviceToHost, c->stream));
         MCG_CUDA(cudaStreamSynchronize(c->stream));
+        static const bool trace = getenv("MCG_TRACE") != nullptr;
+        if(trace) fprintf(stderr, "[mcg query] %lld reads, %llu feature slots, left over by the fused kernel: %u\n",
+                          (long long)n, (unsigned long long)run.nslots, h_left);
         if(h_left == 0) { if(run_out) *run_out = run; return MCG_OK; }
         d_done = c->q_done.as<uint8_t>();
         q_hide_done_kernel<<<grid_for(uint64_t(n) * 32), 256, 0, c->stream>>>(c->q_feat.as<uint32_t>(), c->tmp2.as<uint32_t>(), o->sketchlen,

@@ -34,7 +34,11 @@ rs_hist_kernel(const uint32_t* __restrict__ keys, uint64_t n, int shift, uint32_
     hist[uint64_t(threadIdx.x) * ntiles + blockIdx.x] = h[threadIdx.x];
 }
 
-__global__ void __launch_bounds__(RS_THREADS)
+// Ranking as in the "match" scheme of one-sweep sorts: a warp owns RS_ROUNDS x 32 CONSECUTIVE
+// elements of the tile and ranks them round by round against its own 256 digit counters
+// (__match_any_sync, no block barrier inside the loop); one pass over [warp][digit] turns the
+// counters into tile positions.  Stable: tile order = (warp, round, lane).
+__global__ void __launch_bounds__(RS_THREADS, 4)
 rs_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                   uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
                   uint64_t n, int shift, const uint32_t* __restrict__ offsets, uint32_t ntiles, int iota)
@@ -42,29 +46,49 @@ rs_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restri
     __shared__ uint32_t s_key[RS_TILE];
     __shared__ uint32_t s_val[RS_TILE];
     __shared__ uint32_t s_start[256];            // tile-local start of each digit
-    __shared__ uint32_t s_run[256];              // running count of each digit (over rounds)
-    __shared__ uint32_t s_gbase[256];            // global base of each digit for this tile
-    __shared__ uint32_t s_wcnt[RS_WARPS][256];
+    __shared__ uint32_t s_gbase[256];            // global base of each digit for this tile - s_start
+    __shared__ uint32_t s_wcnt[RS_WARPS][256];   // per warp: running count, then exclusive prefix over warps
     __shared__ uint32_t s_wsum[RS_WARPS];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint64_t base = uint64_t(blockIdx.x) * RS_TILE;
     const int tile_n = int(min(uint64_t(RS_TILE), n - base));
+    const int wbase = warp * (RS_ROUNDS * 32);
+    const uint32_t lt = (1u << lane) - 1u;
 
-    // tile histogram (order-free) -> exclusive scan over the 256 digits
-    s_run[tid] = 0;
-    __syncthreads();
+#pragma unroll
+    for(int w = 0; w < RS_WARPS; ++w) s_wcnt[w][tid] = 0;
     uint32_t mykey[RS_ROUNDS];
 #pragma unroll
     for(int r = 0; r < RS_ROUNDS; ++r) {
-        const int li = r * RS_THREADS + tid;
-        mykey[r] = li < tile_n ? keys_in[base + li] : 0u;
-        if(li < tile_n) atomicAdd(&s_run[(mykey[r] >> shift) & 255u], 1u);
+        const int li = wbase + r * 32 + lane;
+        mykey[r] = li < tile_n ? keys_in[base + li] : 0xFFFFFFFFu;
+    }
+    __syncthreads();
+    uint32_t* wc = s_wcnt[warp];
+    uint32_t myrank[RS_ROUNDS / 2];                         // two 16-bit ranks per register
+#pragma unroll
+    for(int r = 0; r < RS_ROUNDS; ++r) {
+        const uint32_t d = (mykey[r] >> shift) & 255u;      // padding elements rank as digit 255 behind all real ones
+        const uint32_t peers = __match_any_sync(0xFFFFFFFFu, d);
+        const uint32_t before = wc[d];
+        __syncwarp();
+        if((peers & lt) == 0) wc[d] = before + __popc(peers);
+        __syncwarp();
+        const uint32_t rk = before + __popc(peers & lt);
+        if(r & 1) myrank[r >> 1] |= rk << 16; else myrank[r >> 1] = rk;
     }
     __syncthreads();
     {
-        const uint32_t cnt = s_run[tid];
-        uint32_t inc = cnt;
+        // thread tid owns digit tid: exclusive prefix over the warps, then over the digits
+        uint32_t run = 0;
+#pragma unroll
+        for(int w = 0; w < RS_WARPS; ++w) {
+            const uint32_t cnt = s_wcnt[w][tid];
+            s_wcnt[w][tid] = run;
+            run += cnt;
+        }
+        uint32_t inc = run;
 #pragma unroll
         for(int d = 1; d < 32; d <<= 1) {
             const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, inc, d);
@@ -74,52 +98,28 @@ rs_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restri
         __syncthreads();
         uint32_t wb = 0;
         for(int w = 0; w < warp; ++w) wb += s_wsum[w];
-        s_start[tid] = wb + inc - cnt;
-        s_gbase[tid] = offsets[uint64_t(tid) * ntiles + blockIdx.x];
-        s_run[tid] = 0;
+        const uint32_t start = wb + inc - run;
+        s_start[tid] = start;
+        s_gbase[tid] = offsets[uint64_t(tid) * ntiles + blockIdx.x] - start;
     }
     __syncthreads();
-
-    // stable ranking, one round of 256 elements at a time
 #pragma unroll
     for(int r = 0; r < RS_ROUNDS; ++r) {
-        const int li = r * RS_THREADS + tid;
-        if(r * RS_THREADS >= tile_n) break;
-        const bool valid = li < tile_n;
-        const uint32_t key = mykey[r];
-        const uint32_t d = valid ? ((key >> shift) & 255u) : 256u;
-#pragma unroll
-        for(int w = 0; w < RS_WARPS; ++w) s_wcnt[w][tid] = 0;
-        __syncthreads();
-        const uint32_t peers = __match_any_sync(0xFFFFFFFFu, d);
-        const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
-        if(valid && rank == 0) s_wcnt[warp][d] = __popc(peers);
-        __syncthreads();
-        {
-            // thread tid owns digit tid: prefix over warps + running offset
-            uint32_t run = s_run[tid];
-#pragma unroll
-            for(int w = 0; w < RS_WARPS; ++w) {
-                const uint32_t cnt = s_wcnt[w][tid];
-                s_wcnt[w][tid] = run;
-                run += cnt;
-            }
-            s_run[tid] = run;
-        }
-        __syncthreads();
-        if(valid) {
-            const uint32_t pos = s_start[d] + s_wcnt[warp][d] + rank;
-            s_key[pos] = key;
+        const int li = wbase + r * 32 + lane;
+        const uint32_t d = (mykey[r] >> shift) & 255u;
+        if(li < tile_n) {
+            const uint32_t pos = s_start[d] + wc[d] + ((r & 1) ? (myrank[r >> 1] >> 16) : (myrank[r >> 1] & 0xFFFFu));
+            s_key[pos] = mykey[r];
             s_val[pos] = iota ? uint32_t(base + li) : vals_in[base + li];
         }
-        __syncthreads();
     }
-
+    __syncthreads();
     // coalesced stores: consecutive tile positions of one digit are consecutive globally
+#pragma unroll 4
     for(int i = tid; i < tile_n; i += RS_THREADS) {
         const uint32_t key = s_key[i];
         const uint32_t d = (key >> shift) & 255u;
-        const uint64_t g = uint64_t(s_gbase[d]) + uint32_t(i - s_start[d]);
+        const uint64_t g = uint64_t(s_gbase[d] + uint32_t(i));
         keys_out[g] = key;
         vals_out[g] = s_val[i];
     }
