@@ -335,6 +335,31 @@ __device__ __forceinline__ void wsort64(KeyT& a, KeyT& b, int lane)
     }
 }
 
+// 128 keys: element e = 32 * i + lane lives in v[i]
+template<class KeyT>
+__device__ __forceinline__ void wsort128(KeyT (&v)[4], int lane)
+{
+    wsort64(v[0], v[1], lane);
+    wsort64(v[2], v[3], lane);
+    {   // flip step of merge size 128: e with 127 - e, i.e. v[i] of lane L with v[3 - i] of lane 31 - L
+        const KeyT o0 = __shfl_sync(0xFFFFFFFFu, v[0], 31 - lane), o1 = __shfl_sync(0xFFFFFFFFu, v[1], 31 - lane);
+        const KeyT o2 = __shfl_sync(0xFFFFFFFFu, v[2], 31 - lane), o3 = __shfl_sync(0xFFFFFFFFu, v[3], 31 - lane);
+        v[0] = min(v[0], o3); v[1] = min(v[1], o2); v[2] = max(v[2], o1); v[3] = max(v[3], o0);
+    }
+    {   // distance 32: inside the lane
+        const KeyT a = min(v[0], v[1]), b = max(v[0], v[1]), c = min(v[2], v[3]), d = max(v[2], v[3]);
+        v[0] = a; v[1] = b; v[2] = c; v[3] = d;
+    }
+#pragma unroll
+    for(int j = 16; j > 0; j >>= 1) {
+#pragma unroll
+        for(int i = 0; i < 4; ++i) {
+            const KeyT o = __shfl_xor_sync(0xFFFFFFFFu, v[i], j);
+            v[i] = (lane & j) ? max(v[i], o) : min(v[i], o);
+        }
+    }
+}
+
 template<class KeyT>
 __device__ __forceinline__ void toplist_from_sorted(const CandParams& p, uint32_t r, const KeyT* A, const uint32_t* Hh,
                                                     uint32_t m, int32_t* Ct, uint32_t* Ch, int lane);
@@ -369,6 +394,32 @@ __device__ __forceinline__ void process_read_warp(const CandParams& p, uint32_t 
 }
 
 __device__ __forceinline__ void warp_topk_insert_lifted(WarpTopK& L, int K, int32_t tax, uint32_t hits, bool seq, int lane);
+
+// All candidates of a read (Ct: lifted taxon | sequence-rank flag in bit 31, Ch: hits; ascending
+// target order) -> top list.  The insertion itself is order-dependent (candidates.h:236-285) and
+// runs one candidate at a time, but a candidate with hits <= the hits of entry K-1 of a FULL list
+// changes nothing in any branch of insert() (a new taxon would land behind the list, a known one
+// only replaces on MORE hits), and that bound never decreases: such candidates are skipped, 32 at a
+// time, by a ballot.  In a large database most candidates are chance hits of 1..2 and never get in.
+__device__ __forceinline__ void warp_toplist_insert_all(WarpTopK& L, int K, const int32_t* Ct, const uint32_t* Ch, uint32_t ncand, int lane)
+{
+    for(uint32_t base = 0; base < ncand; base += 32) {
+        const uint32_t j = base + uint32_t(lane);
+        const int32_t myt = j < ncand ? Ct[j] : 0;
+        const uint32_t myh = j < ncand ? Ch[j] : 0u;          // hits of a real candidate are >= 1
+        uint32_t rest = 0xFFFFFFFFu;
+        for(;;) {
+            const uint32_t bound = L.n == K ? __shfl_sync(0xFFFFFFFFu, L.hits, K - 1) : 0u;
+            const uint32_t pass = __ballot_sync(0xFFFFFFFFu, myh > bound) & rest;
+            if(pass == 0u) break;
+            const int src = __ffs(int(pass)) - 1;
+            const int32_t t = __shfl_sync(0xFFFFFFFFu, myt, src);
+            const uint32_t h = __shfl_sync(0xFFFFFFFFu, myh, src);
+            warp_topk_insert_lifted(L, K, t & 0x7FFFFFFF, h, t < 0, lane);
+            rest = src == 31 ? 0u : ~((2u << src) - 1u);
+        }
+    }
+}
 
 // one read handled by a whole CTA: A = its matches (shared or global memory), Hh = m uint32,
 // Ct = m int32 of candidate scratch (may alias A: candidate j is written after element j was read)
@@ -437,10 +488,7 @@ __device__ __forceinline__ void process_read_cta(const CandParams& p, uint32_t r
     if(warp == 0) {
         WarpTopK L;
         L.tax = -1; L.hits = 0; L.n = 0;
-        for(uint32_t j = 0; j < ncand; ++j) {
-            const int32_t t = Ct[j];
-            warp_topk_insert_lifted(L, p.K, t & 0x7FFFFFFF, Ch[j], t < 0, lane);
-        }
+        warp_toplist_insert_all(L, p.K, Ct, Ch, ncand, lane);
         if(lane < p.K) {
             p.out_tax[uint64_t(r) * p.K + lane] = lane < L.n ? L.tax : -1;
             p.out_hits[uint64_t(r) * p.K + lane] = lane < L.n ? L.hits : 0u;
@@ -487,7 +535,8 @@ struct FusedParams {
     uint32_t* left_over;        // [0] number of reads left to the staged path, [1] read counter (dynamic scheduling)
 };
 
-constexpr int Q_FUSED = 128;    // matches per read of the fused path (small: shared memory is taken from L1, which the probes need)
+constexpr int Q_FUSED = 128;
+constexpr uint32_t Q_LANE_GATHER = 12;   // lists up to this length are copied by their own lane    // matches per read of the fused path (small: shared memory is taken from L1, which the probes need)
 
 // candidates.h:236-285 with the taxon already lifted to -lowest and its rank known (seq = the
 // taxon is of sequence rank: such taxa are never merged); entry i of the list lives in lane i
@@ -565,10 +614,7 @@ __device__ __forceinline__ void toplist_from_sorted(const CandParams& p, uint32_
     __syncwarp();
     WarpTopK L;
     L.tax = -1; L.hits = 0; L.n = 0;
-    for(uint32_t j = 0; j < ncand; ++j) {
-        const int32_t t = Ct[j];
-        warp_topk_insert_lifted(L, p.K, t & 0x7FFFFFFF, Ch[j], t < 0, lane);
-    }
+    warp_toplist_insert_all(L, p.K, Ct, Ch, ncand, lane);
     if(lane < p.K) {
         p.out_tax[uint64_t(r) * p.K + lane] = lane < L.n ? L.tax : -1;
         p.out_hits[uint64_t(r) * p.K + lane] = lane < L.n ? L.hits : 0u;
@@ -696,7 +742,22 @@ q_fused_warp_kernel(const CandParams p, const FusedParams f)
                     A[pos] = make_key<KeyT>(loc0[c], p.wbits);
                     if(L == 2) A[pos + 1] = make_key<KeyT>(loc1[c], p.wbits);
                 }
-                uint32_t big = __ballot_sync(0xFFFFFFFFu, L > 2);
+                if(L > 2 && L <= Q_LANE_GATHER) {
+                    // short lists: every lane copies its own (a whole-warp copy per list costs more
+                    // instructions than the list has elements)
+                    const uint64_t* src = f.locs + off[c];
+                    for(uint32_t t = 0; t < L; t += 4) {
+                        uint64_t x0 = __ldg(src + t), x1 = 0, x2 = 0, x3 = 0;
+                        if(t + 1 < L) x1 = __ldg(src + t + 1);
+                        if(t + 2 < L) x2 = __ldg(src + t + 2);
+                        if(t + 3 < L) x3 = __ldg(src + t + 3);
+                        A[pos + t] = make_key<KeyT>(x0, p.wbits);
+                        if(t + 1 < L) A[pos + t + 1] = make_key<KeyT>(x1, p.wbits);
+                        if(t + 2 < L) A[pos + t + 2] = make_key<KeyT>(x2, p.wbits);
+                        if(t + 3 < L) A[pos + t + 3] = make_key<KeyT>(x3, p.wbits);
+                    }
+                }
+                uint32_t big = __ballot_sync(0xFFFFFFFFu, L > Q_LANE_GATHER);
                 while(big) {
                     const int src = __ffs(int(big)) - 1;
                     big &= big - 1;
@@ -722,6 +783,14 @@ q_fused_warp_kernel(const CandParams p, const FusedParams f)
             wsort64(a, b2, lane);
             A[lane] = a;
             A[lane + 32] = b2;
+        } else if(m <= 128) {
+            KeyT v[4];
+#pragma unroll
+            for(int i = 0; i < 4; ++i) v[i] = 32 * i + lane < int(m) ? A[32 * i + lane] : KMAX;
+            __syncwarp();
+            wsort128(v, lane);
+#pragma unroll
+            for(int i = 0; i < 4; ++i) A[32 * i + lane] = v[i];
         } else {
             bitonic_sort<true>(A, m, lane, 32);
         }
