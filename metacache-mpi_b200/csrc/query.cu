@@ -92,13 +92,13 @@ q_find_kernel(const uint32_t* __restrict__ feat, uint64_t nslots, const uint32_t
 // counters: [0] small [1] medium [2] large [3] xl
 __global__ void q_bin_reads_kernel(const uint64_t* fpos, const uint32_t* W, int s, int64_t n,
                                    uint32_t* lists /* [4][n] */, uint32_t* counters,
-                                   int32_t* out_n, const uint8_t* done)
+                                   int32_t* out_n, const uint8_t* done, const uint32_t* rmap)
 {
     const int64_t r = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
     int cls = 4;                                          // 4 = nothing to do
     if(r < n && !(done != nullptr && done[r])) {
         const uint64_t m = fpos[uint64_t(W[r + 1]) * s] - fpos[uint64_t(W[r]) * s];
-        if(m == 0) out_n[r] = 0;
+        if(m == 0) out_n[rmap ? rmap[r] : uint32_t(r)] = 0;
         else cls = m <= Q_SMALL ? 0 : (m <= Q_MED ? 1 : (m <= Q_LARGE ? 2 : 3));
     }
     // one atomic per class per warp
@@ -214,6 +214,7 @@ struct CandParams {
     uint32_t* hits_scratch2;
     const uint32_t* list;
     const uint32_t* list_count;
+    const uint32_t* rmap;        // staged path over a compacted sub-batch: position -> read of the batch (nullptr: identity)
     int K;
     int lowest;
     const int32_t* lineage;
@@ -515,7 +516,7 @@ q_cand_warp_kernel(const CandParams p)
         const uint32_t r = p.list[it];
         const uint64_t beg = p.fpos[uint64_t(p.W[r]) * p.s];
         const uint32_t m = uint32_t(p.fpos[uint64_t(p.W[r + 1]) * p.s] - beg);
-        process_read_warp<KeyT>(p, r, A, Hh, m, static_cast<KeyT*>(p.loc) + beg, lane, Ct, Ch);
+        process_read_warp<KeyT>(p, p.rmap ? p.rmap[r] : r, A, Hh, m, static_cast<KeyT*>(p.loc) + beg, lane, Ct, Ch);
     }
 }
 
@@ -533,6 +534,7 @@ struct FusedParams {
     int64_t n;
     uint8_t* done;
     uint32_t* left_over;        // [0] number of reads left to the staged path, [1] read counter (dynamic scheduling)
+    uint32_t* left_list;        // the reads left over, in no particular order
 };
 
 constexpr int Q_FUSED = 128;
@@ -623,6 +625,24 @@ __device__ __forceinline__ void toplist_from_sorted(const CandParams& p, uint32_
     __syncwarp();
 }
 
+// few reads left over: their windows / features are compacted into a sub-batch of their own
+__global__ void q_left_counts_kernel(const uint32_t* W, const uint32_t* left_list, uint32_t nleft, uint32_t* Wc)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i < nleft) { const uint32_t r = left_list[i]; Wc[i] = W[r + 1] - W[r]; }
+}
+
+__global__ void q_left_copy_kernel(const uint32_t* feat, const uint32_t* W, const uint32_t* left_list, uint32_t nleft, const uint32_t* Wc,
+                                   int s, uint32_t* featc)
+{
+    const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if(i >= nleft) return;
+    const uint32_t r = left_list[i];
+    const uint64_t src = uint64_t(W[r]) * s, dst = uint64_t(Wc[i]) * s, cnt = uint64_t(Wc[i + 1] - Wc[i]) * s;
+    for(uint64_t t = lane; t < cnt; t += 32) featc[dst + t] = feat[src + t];
+}
+
 // features of the reads the fused kernel finished -> NO_FEATURE: the staged path skips them
 __global__ void q_hide_done_kernel(uint32_t* feat, const uint32_t* W, int s, const uint8_t* done, int64_t n)
 {
@@ -659,7 +679,7 @@ q_fused_warp_kernel(const CandParams p, const FusedParams f)
         const uint64_t s0 = uint64_t(p.W[r]) * p.s, s1 = uint64_t(p.W[r + 1]) * p.s;
         const uint32_t ns = uint32_t(s1 - s0);
         if(ns > 32u * NC) {
-            if(lane == 0) { atomicAdd(f.left_over, 1u); f.done[r] = 0; }
+            if(lane == 0) { f.left_list[atomicAdd(f.left_over, 1u)] = uint32_t(r); f.done[r] = 0; }
             continue;
         }
         const int nc = int(ns + 31) >> 5;                 // feature slots per lane (uniform)
@@ -722,7 +742,7 @@ q_fused_warp_kernel(const CandParams p, const FusedParams f)
         }
         const uint32_t m = __shfl_sync(0xFFFFFFFFu, inc, 31);
         if(m > Q_FUSED) {
-            if(lane == 0) { atomicAdd(f.left_over, 1u); f.done[r] = 0; }
+            if(lane == 0) { f.left_list[atomicAdd(f.left_over, 1u)] = uint32_t(r); f.done[r] = 0; }
             continue;
         }
         // this read is finished here (q_hide_done_kernel hides its features from the staged path,
@@ -815,7 +835,7 @@ __global__ void q_cand_cta_kernel(const CandParams p, uint32_t capacity)
         const uint32_t r = p.list[it];
         const uint64_t beg = p.fpos[uint64_t(p.W[r]) * p.s];
         const uint32_t m = uint32_t(p.fpos[uint64_t(p.W[r + 1]) * p.s] - beg);
-        process_read_cta<KeyT>(p, r, A, Hh, m, static_cast<KeyT*>(p.loc) + beg, true, threadIdx.x, blockDim.x, reinterpret_cast<int32_t*>(A));
+        process_read_cta<KeyT>(p, p.rmap ? p.rmap[r] : r, A, Hh, m, static_cast<KeyT*>(p.loc) + beg, true, threadIdx.x, blockDim.x, reinterpret_cast<int32_t*>(A));
     }
 }
 
@@ -830,7 +850,7 @@ q_cand_global_kernel(const CandParams p)
         const uint64_t beg = p.fpos[uint64_t(p.W[r]) * p.s];
         const uint64_t m64 = p.fpos[uint64_t(p.W[r + 1]) * p.s] - beg;
         KeyT* A = static_cast<KeyT*>(p.loc) + beg;
-        process_read_cta<KeyT>(p, r, A, p.hits_scratch + beg, uint32_t(m64), A, false, threadIdx.x, blockDim.x,
+        process_read_cta<KeyT>(p, p.rmap ? p.rmap[r] : r, A, p.hits_scratch + beg, uint32_t(m64), A, false, threadIdx.x, blockDim.x,
                                reinterpret_cast<int32_t*>(p.hits_scratch2 + beg));
     }
 }
@@ -926,6 +946,10 @@ q_merge_classify_kernel(const MergeParams p)
 struct QueryRun {
     uint64_t nwin = 0, nslots = 0, total = 0;
     uint32_t cls[4] = {0, 0, 0, 0};
+    // what the staged path works on: the whole batch, or the compacted reads the fused kernel left over
+    const uint32_t* feat = nullptr;     // [nslots]
+    const uint32_t* W = nullptr;        // [n + 1] window prefix
+    const uint32_t* rmap = nullptr;     // position -> read of the batch (nullptr: identity)
 };
 
 static int check_opts(const mcg_db* db, const mcg_query_opts* o)
@@ -976,6 +1000,9 @@ static int query_sketch(mcg_db* db, const mcg_query_opts* o,
     mcg_sketch_cfg cfg = db->cfg;
     MCG_TRY(sketch_launch(c, cfg, s, o->winlen, o->winstride, d1, bytes1, doffs1, n, wf1, W, h_tot[0], c->q_feat.as<uint32_t>(), nullptr));
     if(d2) MCG_TRY(sketch_launch(c, cfg, s, o->winlen, o->winstride, d2, bytes2, doffs2, n, wf2, of2, h_tot[1], c->q_feat.as<uint32_t>(), nullptr));
+    run->feat = c->q_feat.as<uint32_t>();
+    run->W = W;
+    run->rmap = nullptr;
     return MCG_OK;
 }
 
@@ -985,13 +1012,13 @@ static int query_find_gather(mcg_db* db, const mcg_query_opts* o, int64_t n, int
     mcg_ctx* c = db->ctx;
     const int s = o->sketchlen;
     const uint64_t nslots = run->nslots;
-    uint32_t* W = c->tmp2.as<uint32_t>();
+    const uint32_t* W = run->W;
     // K3: find
     MCG_TRY(c->q_flen.reserve(nslots + 16));
     MCG_TRY(c->q_foff.reserve((nslots + 1) * 8));
     MCG_TRY(c->q_fpos.reserve((nslots + 2) * 8));
     if(nslots > 0) {
-        q_find_kernel<<<grid_for(nslots), 256, 0, c->stream>>>(c->q_feat.as<uint32_t>(), nslots, db->table.as<uint32_t>(), db->geom(),
+        q_find_kernel<<<grid_for(nslots), 256, 0, c->stream>>>(run->feat, nslots, db->table.as<uint32_t>(), db->geom(),
                                                               c->q_flen.as<uint8_t>(), c->q_foff.as<uint64_t>());
         c->launches++;
     }
@@ -1001,7 +1028,7 @@ static int query_find_gather(mcg_db* db, const mcg_query_opts* o, int64_t n, int
     MCG_TRY(c->q_rinfo.reserve(64));
     uint32_t* counters = c->q_rinfo.as<uint32_t>();
     MCG_CUDA(cudaMemsetAsync(counters, 0, 16, c->stream));
-    q_bin_reads_kernel<<<grid_for(n), 256, 0, c->stream>>>(c->q_fpos.as<uint64_t>(), W, s, n, c->q_cls.as<uint32_t>(), counters, d_out_n, d_done);
+    q_bin_reads_kernel<<<grid_for(n), 256, 0, c->stream>>>(c->q_fpos.as<uint64_t>(), W, s, n, c->q_cls.as<uint32_t>(), counters, d_out_n, d_done, run->rmap);
     c->launches++;
     uint64_t total = 0;
     MCG_CUDA(cudaMemcpyAsync(&total, c->q_fpos.as<uint64_t>() + nslots, 8, cudaMemcpyDeviceToHost, c->stream));
@@ -1030,6 +1057,7 @@ static void fill_cand_params(mcg_db* db, const mcg_query_opts* o, const int64_t*
     CandParams& p = *pp;
     p.fpos = c->q_fpos.as<uint64_t>();
     p.W = c->tmp2.as<uint32_t>();
+    p.rmap = nullptr;
     p.s = o->sketchlen;
     p.offs1 = doffs1;
     p.offs2 = doffs2;
@@ -1060,6 +1088,8 @@ static int query_back(mcg_db* db, const mcg_query_opts* o, const int64_t* doffs1
     const uint32_t* lists = c->q_cls.as<uint32_t>();
     const uint32_t* counters = c->q_rinfo.as<uint32_t>();
     p.wbits = db->wbits;
+    p.W = run.W;
+    p.rmap = run.rmap;
     const bool k32 = db->key32;
     const int ksz = k32 ? 4 : 8;
     static bool configured = false;
@@ -1124,6 +1154,7 @@ int query_batch_dev(mcg_db* db, const mcg_query_opts* o,
     QueryRun run;
     MCG_TRY(query_sketch(db, o, d1, doffs1, bytes1, d2, doffs2, bytes2, n, &run));
     const uint8_t* d_done = nullptr;
+    int64_t n_staged = n;
     static const bool fused_off = getenv("MCG_QUERY_NO_FUSION") != nullptr;
     if(!write_sorted && !fused_off && run.nslots > 0) {
         // short reads end to end in one kernel; what it leaves over goes through the staged path
@@ -1137,6 +1168,7 @@ int query_batch_dev(mcg_db* db, const mcg_query_opts* o,
         FusedParams f;
         f.feat = c->q_feat.as<uint32_t>(); f.table = db->table.as<uint32_t>(); f.geom = db->geom();
         f.locs = db->locs.as<uint64_t>(); f.n = n; f.done = c->q_done.as<uint8_t>(); f.left_over = left;
+        f.left_list = c->tmp1.as<uint32_t>();          // (the mate-2 window prefix is dead once K1 has run)
         // feature slots per lane: 2 (reads of <= 64 slots, e.g. 2 x 150 bp at sketchlen 16) keeps the
         // registers at the level of 6 resident CTAs; longer reads take the 4-slot variant
         const bool nc2 = run.nslots <= uint64_t(n) * 64;
@@ -1165,13 +1197,38 @@ int query_batch_dev(mcg_db* db, const mcg_query_opts* o,
         if(trace) fprintf(stderr, "[mcg query] %lld reads, %llu feature slots, left over by the fused kernel: %u\n",
                           (long long)n, (unsigned long long)run.nslots, h_left);
         if(h_left == 0) { if(run_out) *run_out = run; return MCG_OK; }
-        d_done = c->q_done.as<uint8_t>();
-        q_hide_done_kernel<<<grid_for(uint64_t(n) * 32), 256, 0, c->stream>>>(c->q_feat.as<uint32_t>(), c->tmp2.as<uint32_t>(), o->sketchlen,
-                                                                               d_done, n);
-        c->launches++;
+        static const bool compact_off = getenv("MCG_QUERY_NO_COMPACT") != nullptr;
+        if(uint64_t(h_left) * 8 <= uint64_t(n) && !compact_off) {
+            // few reads left: the staged path runs over a sub-batch of just these reads (its kernels
+            // are per feature slot of the batch they are given)
+            uint32_t* Wc = c->tmp0.as<uint32_t>();
+            const uint32_t* left_list = c->tmp1.as<uint32_t>();
+            q_left_counts_kernel<<<grid_for(h_left), 256, 0, c->stream>>>(c->tmp2.as<uint32_t>(), left_list, h_left, Wc);
+            c->launches++;
+            MCG_TRY(exclusive_scan_u32_to_u32(c, Wc, Wc, h_left));
+            uint32_t wtot = 0;
+            MCG_CUDA(cudaMemcpyAsync(&wtot, Wc + h_left, 4, cudaMemcpyDeviceToHost, c->stream));
+            MCG_CUDA(cudaStreamSynchronize(c->stream));
+            const uint64_t nsl = uint64_t(wtot) * uint64_t(o->sketchlen);
+            MCG_TRY(c->tmp3.reserve((nsl + 1) * 4));
+            q_left_copy_kernel<<<grid_for(uint64_t(h_left) * 32), 256, 0, c->stream>>>(c->q_feat.as<uint32_t>(), c->tmp2.as<uint32_t>(), left_list,
+                                                                                     h_left, Wc, o->sketchlen, c->tmp3.as<uint32_t>());
+            c->launches++;
+            run.feat = c->tmp3.as<uint32_t>();
+            run.W = Wc;
+            run.rmap = left_list;
+            run.nwin = wtot;
+            run.nslots = nsl;
+            n_staged = int64_t(h_left);
+        } else {
+            d_done = c->q_done.as<uint8_t>();
+            q_hide_done_kernel<<<grid_for(uint64_t(n) * 32), 256, 0, c->stream>>>(c->q_feat.as<uint32_t>(), c->tmp2.as<uint32_t>(), o->sketchlen,
+                                                                                   d_done, n);
+            c->launches++;
+        }
     }
-    MCG_TRY(query_find_gather(db, o, n, d_out_n, d_done, &run));
-    MCG_TRY(query_back(db, o, doffs1, d2 ? doffs2 : nullptr, n, run, d_out_tax, d_out_hits, d_out_n, write_sorted));
+    MCG_TRY(query_find_gather(db, o, n_staged, d_out_n, d_done, &run));
+    MCG_TRY(query_back(db, o, doffs1, d2 ? doffs2 : nullptr, n_staged, run, d_out_tax, d_out_hits, d_out_n, write_sorted));
     if(run_out) *run_out = run;
     return MCG_OK;
 }

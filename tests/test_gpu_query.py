@@ -71,6 +71,29 @@ def test_pairs_all_stages(ctx, oracle, P):
         assert stats[20] + stats[21] == len(w.o1) - 1
 
 
+def test_many_targets_per_read(ctx, oracle):
+    """a block shared by 38 of 40 genomes: location lists of every gather class (inline, per-lane,
+    whole-warp), reads with 65..128 matches (register sort of 128), reads with more than 32
+    candidates (chunked, filtered top-list insertion) and reads left over to the staged path"""
+    w = World(G=40, L=12000, npairs=1500, seed=11)
+    ctx.upload_taxonomy(w.tabs.lineage, w.tabs.rank, w.G)
+    for P in (1, 2):
+        od = w.oracle_shards(oracle, P)
+        gd = w.gpu_shards(api, ctx, P)
+        for maxcand, lowest, hitmin, hitdiff in CONFIGS:
+            q = api.make_query_opts(maxcand=maxcand, lowest=lowest, hitmin=hitmin, hitdiff=hitdiff)
+            oq = po.make_qopt(maxcand=maxcand, lowest=lowest, hitmin=hitmin, hitdiff=hitdiff)
+            ct, ch, cn, mt, mh, mn, best, brank, stats = _gpu_full(ctx, gd, q, w.b1, w.o1, w.b2, w.o2)
+            ot, oh, on = _oracle_local(od, w.tax, oq, w.b1, w.o1, w.b2, w.o2, maxcand)
+            assert (cn == on).all() and (ct == ot).all() and (ch == oh).all()
+            et, eh, en, eb, er, es = oracle.query_batch(od, w.tax, oq, w.b1, w.o1, w.b2, w.o2)
+            assert (mn == en).all() and (mt == et).all() and (mh == eh).all()
+            assert (best == eb).all() and (brank == er).all() and (stats == es).all()
+        q0 = api.make_query_opts()
+        cnt, _, _ = gd[0].query_matches(q0, w.b1, w.o1, w.b2, w.o2)
+        assert ((cnt > 64) & (cnt <= 128)).any() and (cnt > 128).any() and (cnt <= 64).any()
+
+
 def test_single_end_and_ragged_reads(ctx, oracle):
     w = World(G=6, L=20000, npairs=10)
     ctx.upload_taxonomy(w.tabs.lineage, w.tabs.rank, w.G)
