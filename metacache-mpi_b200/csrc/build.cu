@@ -30,70 +30,141 @@ int exclusive_scan_u32_to_u32(mcg_ctx* c, const uint32_t* d_in, uint32_t* d_out,
 constexpr uint32_t EMPTY_KEY = 0xFFFFFFFFu;
 constexpr double TABLE_LOAD = 0.45;      // keys per slot
 
-// first index with sorted_keys[i] == 0xFFFFFFFF (padding slots sort to the end)
-__global__ void count_valid_kernel(const uint32_t* keys, uint64_t n, uint64_t* out)
+// ---- runs of equal feature in the sorted slot list -> keys, sizes, offsets, locations
+//
+// Everything a slot needs is a prefix quantity of slot-local values: its key index is the number
+// of run heads up to it, its position in the run is its index minus the last head index (a
+// max-scan), and -- because exactly the first maxlocs slots of a run are kept
+// (sketch_database.h:1089-1092, hash_multimap.h:706-713) -- its location index is the number of
+// kept slots before it.  Two passes over tiles of the sorted keys: COUNT (heads and kept slots
+// per tile), a scan of the tile counts, EMIT (keys, sizes, offsets and locations written in
+// place).  The run a tile starts in is found by galloping backwards from the tile boundary.
+// Padding slots (0xFFFFFFFF) sort to the end and are neither heads nor kept.
+constexpr int RN_THREADS = 256, RN_ITEMS = 8, RN_TILE = RN_THREADS * RN_ITEMS;
+
+__device__ __forceinline__ void rn_load8(const uint32_t* a, uint64_t e0, uint64_t n, uint32_t fill, uint32_t (&v)[RN_ITEMS])
 {
-    uint64_t lo = 0, hi = n;
-    while(lo < hi) {
-        const uint64_t mid = (lo + hi) >> 1;
-        if(keys[mid] == EMPTY_KEY) hi = mid; else lo = mid + 1;
+    if(e0 + RN_ITEMS <= n) {
+        const uint4 x = __ldg(reinterpret_cast<const uint4*>(a + e0)), y = __ldg(reinterpret_cast<const uint4*>(a + e0) + 1);
+        v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w; v[4] = y.x; v[5] = y.y; v[6] = y.z; v[7] = y.w;
+    } else {
+#pragma unroll
+        for(int i = 0; i < RN_ITEMS; ++i) v[i] = e0 + i < n ? a[e0 + i] : fill;
     }
-    *out = lo;
 }
 
-__global__ void head_flags_kernel(const uint32_t* keys, uint64_t n, uint32_t* head)
+template<bool EMIT>
+__global__ void __launch_bounds__(RN_THREADS)
+runs_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ slots, uint64_t n, uint32_t maxlocs,
+            uint32_t* __restrict__ tile_heads, uint32_t* __restrict__ tile_kept,      // COUNT: per-tile counts out; EMIT: their exclusive prefixes
+            uint32_t* __restrict__ ukeys, uint8_t* __restrict__ sizes, uint64_t* __restrict__ offs, uint64_t* __restrict__ locs,
+            uint32_t sketchlen, const uint64_t* __restrict__ tgt_firstwin, const uint32_t* __restrict__ tgt_id, uint32_t ntgt)
 {
-    const uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
-    if(i < n) head[i] = (i == 0 || keys[i] != keys[i - 1]) ? 1u : 0u;
-}
-
-// hs = exclusive scan of head flags.  For every run head: record key and run start.
-__global__ void run_starts_kernel(const uint32_t* keys, const uint32_t* hs, uint64_t n,
-                                  uint32_t* ukeys, uint32_t* ustart, uint32_t nkeys)
-{
-    const uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
-    if(i < n) {
-        const bool head = (i == 0 || keys[i] != keys[i - 1]);
-        if(head) {
-            const uint32_t j = hs[i];
-            ukeys[j] = keys[i];
-            ustart[j] = uint32_t(i);
+    __shared__ long long s_max[RN_THREADS / 32];
+    __shared__ unsigned long long s_sum[RN_THREADS / 32];
+    __shared__ long long s_first;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint64_t tbase = uint64_t(blockIdx.x) * RN_TILE;
+    const uint64_t e0 = tbase + uint64_t(tid) * RN_ITEMS;
+    uint32_t k[RN_ITEMS];
+    rn_load8(keys, e0, n, EMPTY_KEY, k);
+    const uint32_t prev = (e0 > 0 && e0 <= n) ? keys[e0 - 1] : ~k[0];
+    if(tid == 0) {
+        long long st = (long long)tbase;
+        if(tbase > 0 && k[0] != EMPTY_KEY && prev == k[0]) {
+            // keys[hi] == k[0]; step back 1, 2, 4, ... until a different key (or the front), then bisect
+            long long hi = (long long)tbase - 1, lo = -1, step = 1;
+            while(hi - step >= 0) {
+                if(keys[hi - step] != k[0]) { lo = hi - step; break; }
+                hi -= step;
+                step <<= 1;
+            }
+            while(hi - lo > 1) {
+                const long long mid = (lo + hi) >> 1;
+                if(keys[mid] == k[0]) hi = mid; else lo = mid;
+            }
+            st = hi;
+        }
+        s_first = st;
+    }
+    // heads of this thread; index of its last head
+    uint32_t hmask = 0;
+    long long last = -1;
+#pragma unroll
+    for(int i = 0; i < RN_ITEMS; ++i) {
+        const uint32_t p = i == 0 ? prev : k[i - 1];
+        if(k[i] != EMPTY_KEY && p != k[i]) { hmask |= 1u << i; last = (long long)(e0 + i); }
+    }
+    // exclusive max-scan of `last` over the block: start of the run this thread begins in
+    long long inc = last;
+#pragma unroll
+    for(int d = 1; d < 32; d <<= 1) {
+        const long long o = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+        if(lane >= d) inc = max(inc, o);
+    }
+    if(lane == 31) s_max[warp] = inc;
+    long long start = __shfl_up_sync(0xFFFFFFFFu, inc, 1);
+    if(lane == 0) start = -1;
+    __syncthreads();
+    for(int w = 0; w < warp; ++w) start = max(start, s_max[w]);
+    if(start < 0) start = s_first;
+    // positions in the run, kept slots
+    uint32_t kmask = 0;
+    uint32_t pos[RN_ITEMS];
+#pragma unroll
+    for(int i = 0; i < RN_ITEMS; ++i) {
+        if(hmask >> i & 1u) start = (long long)(e0 + i);
+        pos[i] = uint32_t((long long)(e0 + i) - start);
+        if(k[i] != EMPTY_KEY && pos[i] < maxlocs) kmask |= 1u << i;
+    }
+    // block sums / exclusive prefixes of (heads, kept), packed
+    const unsigned long long mine = (unsigned long long)(__popc(hmask)) << 32 | (unsigned long long)(__popc(kmask));
+    unsigned long long sinc = mine;
+#pragma unroll
+    for(int d = 1; d < 32; d <<= 1) {
+        const unsigned long long o = __shfl_up_sync(0xFFFFFFFFu, sinc, d);
+        if(lane >= d) sinc += o;
+    }
+    if(lane == 31) s_sum[warp] = sinc;
+    __syncthreads();
+    if(!EMIT) {
+        if(tid == 0) {
+            unsigned long long tot = 0;
+            for(int w = 0; w < RN_THREADS / 32; ++w) tot += s_sum[w];
+            tile_heads[blockIdx.x] = uint32_t(tot >> 32);
+            tile_kept[blockIdx.x] = uint32_t(tot);
+        }
+        return;
+    }
+    unsigned long long ex = sinc - mine;
+    for(int w = 0; w < warp; ++w) ex += s_sum[w];
+    uint32_t kidx = tile_heads[blockIdx.x] + uint32_t(ex >> 32) - 1u;      // run this thread begins in (may have started in an earlier tile)
+    uint64_t lidx = uint64_t(tile_kept[blockIdx.x]) + uint32_t(ex);
+    uint32_t sl[RN_ITEMS];
+    if(kmask) rn_load8(slots, e0, n, 0u, sl);
+    const uint32_t next = e0 + RN_ITEMS < n ? keys[e0 + RN_ITEMS] : EMPTY_KEY;
+#pragma unroll
+    for(int i = 0; i < RN_ITEMS; ++i) {
+        if(hmask >> i & 1u) {
+            ++kidx;
+            ukeys[kidx] = k[i];
+            offs[kidx] = lidx;
+        }
+        const uint32_t nk = i + 1 < RN_ITEMS ? k[i + 1] : next;
+        if(k[i] != EMPTY_KEY && nk != k[i]) sizes[kidx] = uint8_t(min(pos[i] + 1u, maxlocs));
+        if(kmask >> i & 1u) {
+            const uint64_t gw = sl[i] / sketchlen;             // global window of the shard
+            uint32_t lo = 0, hi = ntgt;                        // largest t with firstwin[t] <= gw
+            while(hi - lo > 1) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if(__ldg(tgt_firstwin + mid) <= gw) lo = mid; else hi = mid;
+            }
+            locs[lidx++] = (uint64_t(__ldg(tgt_id + lo)) << 32) | (gw - __ldg(tgt_firstwin + lo));
         }
     }
-    if(i == 0) ustart[nkeys] = uint32_t(n);
 }
 
-__global__ void run_sizes_kernel(const uint32_t* ustart, uint32_t nkeys, uint32_t maxlocs, uint8_t* sizes)
-{
-    const uint64_t j = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
-    if(j < nkeys) {
-        const uint32_t len = ustart[j + 1] - ustart[j];
-        sizes[j] = uint8_t(len < maxlocs ? len : maxlocs);
-    }
-}
-
-// element i of the sorted slot list -> location, if it is among the first maxlocs of its run
-__global__ void emit_locations_kernel(const uint32_t* keys, const uint32_t* slots, const uint32_t* hs,
-                                      const uint32_t* ustart, const uint64_t* offs, uint64_t n,
-                                      uint32_t maxlocs, uint32_t sketchlen,
-                                      const uint64_t* tgt_firstwin, const uint32_t* tgt_id, uint32_t ntgt,
-                                      uint64_t* locs)
-{
-    const uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
-    if(i >= n) return;
-    const bool head = (i == 0 || keys[i] != keys[i - 1]);
-    const uint32_t j = hs[i] + (head ? 1u : 0u) - 1u;
-    const uint32_t r = uint32_t(i) - ustart[j];
-    if(r >= maxlocs) return;
-    const uint64_t gw = slots[i] / sketchlen;          // global window of the shard
-    uint32_t lo = 0, hi = ntgt;                        // largest t with firstwin[t] <= gw
-    while(hi - lo > 1) {
-        const uint32_t mid = (lo + hi) >> 1;
-        if(tgt_firstwin[mid] <= gw) lo = mid; else hi = mid;
-    }
-    const uint64_t win = gw - tgt_firstwin[lo];
-    locs[offs[j] + r] = (uint64_t(tgt_id[lo]) << 32) | win;
-}
+__global__ void set_u64_kernel(uint64_t* p, uint64_t v) { *p = v; }
 
 // ---- ordered table construction (layout and rule: common.cuh, "feature table")
 __global__ void table_clear_kernel(uint4* table, uint64_t nbuckets)
@@ -345,59 +416,41 @@ int db_finalize(mcg_db* db)
     TRACE("alloc sort buffers");
     MCG_TRY(radix_sort_pairs(c, skeys, svals, c->tmp1.as<uint32_t>(), c->tmp2.as<uint32_t>(), nslots, 32, true));
     TRACE("radix sort");
-    // (2) drop the padding tail
-    MCG_TRY(c->tmp3.reserve(64));
-    uint64_t* d_scalar = c->tmp3.as<uint64_t>();
-    count_valid_kernel<<<1, 1, 0, c->stream>>>(skeys, nslots, d_scalar);
+    // (2) runs of equal feature: counts per tile, scan, then keys / sizes / offsets / locations in one pass
+    const uint32_t ntiles = uint32_t((nslots + RN_TILE - 1) / RN_TILE);
+    MCG_TRY(c->tmp1.reserve((size_t(ntiles) + 2) * 4));
+    MCG_TRY(c->tmp2.reserve((size_t(ntiles) + 2) * 4));
+    uint32_t* th = c->tmp1.as<uint32_t>();
+    uint32_t* tk = c->tmp2.as<uint32_t>();
+    const uint32_t ntgt = uint32_t(db->h_tgt_id.size());
+    MCG_TRY(c->tmp3.reserve((size_t(ntgt) + 2) * 8 + 64));
+    MCG_TRY(c->tmp4.reserve((size_t(ntgt) + 2) * 4 + 64));
+    MCG_CUDA(cudaMemcpyAsync(c->tmp3.p, db->h_tgt_firstwin.data(), (size_t(ntgt) + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+    MCG_CUDA(cudaMemcpyAsync(c->tmp4.p, db->h_tgt_id.data(), size_t(ntgt) * 4, cudaMemcpyHostToDevice, c->stream));
+    runs_kernel<false><<<ntiles, RN_THREADS, 0, c->stream>>>(skeys, svals, nslots, uint32_t(db->maxlocs), th, tk, nullptr, nullptr, nullptr, nullptr,
+                                                             s, nullptr, nullptr, 0);
     c->launches++;
-    uint64_t nvalid = 0;
-    MCG_CUDA(cudaMemcpyAsync(&nvalid, d_scalar, 8, cudaMemcpyDeviceToHost, c->stream));
-    MCG_CUDA(cudaStreamSynchronize(c->stream));
-    // (3) runs of equal feature
-    uint32_t* hs = c->tmp1.as<uint32_t>();    // reuse (needs nvalid+1 <= nslots+... entries)
-    MCG_TRY(c->tmp1.reserve((nslots + 2) * 4));
-    hs = c->tmp1.as<uint32_t>();
-    uint32_t nkeys = 0;
-    if(nvalid > 0) {
-        head_flags_kernel<<<grid_for(nvalid), 256, 0, c->stream>>>(skeys, nvalid, hs);
-        c->launches++;
-        MCG_TRY(exclusive_scan_u32_to_u32(c, hs, hs, nvalid));
-        MCG_CUDA(cudaMemcpyAsync(&nkeys, hs + nvalid, 4, cudaMemcpyDeviceToHost, c->stream));
-        MCG_CUDA(cudaStreamSynchronize(c->stream));
-    }
-    TRACE("runs");
+    MCG_TRY(exclusive_scan_u32_to_u32(c, th, th, ntiles));
+    MCG_TRY(exclusive_scan_u32_to_u32(c, tk, tk, ntiles));
+    uint32_t nkeys = 0, nlocs32 = 0;
+    MCG_CUDA(cudaMemcpyAsync(&nkeys, th + ntiles, 4, cudaMemcpyDeviceToHost, c->stream));
+    MCG_CUDA(cudaMemcpyAsync(&nlocs32, tk + ntiles, 4, cudaMemcpyDeviceToHost, c->stream));
+    MCG_CUDA(cudaStreamSynchronize(c->stream));       // (also: the host vectors were the copy source)
+    TRACE("runs: count");
+    const uint64_t nlocs = nlocs32;
     db->nkeys = nkeys;
+    db->nlocs = nlocs;
     MCG_TRY(db->keys.reserve((uint64_t(nkeys) + 1) * 4));
     MCG_TRY(db->sizes.reserve(uint64_t(nkeys) + 16));
     MCG_TRY(db->offs.reserve((uint64_t(nkeys) + 2) * 8));
-    MCG_TRY(c->tmp2.reserve((uint64_t(nkeys) + 2) * 4));
-    uint32_t* ustart = c->tmp2.as<uint32_t>();
-    if(nkeys > 0) {
-        run_starts_kernel<<<grid_for(nvalid), 256, 0, c->stream>>>(skeys, hs, nvalid, db->keys.as<uint32_t>(), ustart, nkeys);
-        run_sizes_kernel<<<grid_for(nkeys), 256, 0, c->stream>>>(ustart, nkeys, uint32_t(db->maxlocs), db->sizes.as<uint8_t>());
-        c->launches += 2;
-    }
-    MCG_TRY(exclusive_scan_u8_to_u64(c, db->sizes.as<uint8_t>(), db->offs.as<uint64_t>(), nkeys));
-    uint64_t nlocs = 0;
-    MCG_CUDA(cudaMemcpyAsync(&nlocs, db->offs.as<uint64_t>() + nkeys, 8, cudaMemcpyDeviceToHost, c->stream));
-    MCG_CUDA(cudaStreamSynchronize(c->stream));
-    TRACE("sizes + offsets");
-    db->nlocs = nlocs;
     MCG_TRY(db->locs.reserve((nlocs + 2) * 8));
-    // (4) locations
-    if(nvalid > 0) {
-        const uint32_t ntgt = uint32_t(db->h_tgt_id.size());
-        MCG_TRY(c->tmp3.reserve((size_t(ntgt) + 2) * 8 + 64));
-        MCG_TRY(c->tmp4.reserve((size_t(ntgt) + 2) * 4 + 64));
-        MCG_CUDA(cudaMemcpyAsync(c->tmp3.p, db->h_tgt_firstwin.data(), (size_t(ntgt) + 1) * 8, cudaMemcpyHostToDevice, c->stream));
-        MCG_CUDA(cudaMemcpyAsync(c->tmp4.p, db->h_tgt_id.data(), size_t(ntgt) * 4, cudaMemcpyHostToDevice, c->stream));
-        emit_locations_kernel<<<grid_for(nvalid), 256, 0, c->stream>>>(
-            skeys, svals, hs, ustart, db->offs.as<uint64_t>(), nvalid, uint32_t(db->maxlocs), s,
-            c->tmp3.as<uint64_t>(), c->tmp4.as<uint32_t>(), ntgt, db->locs.as<uint64_t>());
-        c->launches++;
-        MCG_CUDA(cudaStreamSynchronize(c->stream));     // host vectors were the copy source
-    }
-    TRACE("locations");
+    runs_kernel<true><<<ntiles, RN_THREADS, 0, c->stream>>>(skeys, svals, nslots, uint32_t(db->maxlocs), th, tk, db->keys.as<uint32_t>(),
+                                                            db->sizes.as<uint8_t>(), db->offs.as<uint64_t>(), db->locs.as<uint64_t>(),
+                                                            s, c->tmp3.as<uint64_t>(), c->tmp4.as<uint32_t>(), ntgt);
+    set_u64_kernel<<<1, 1, 0, c->stream>>>(db->offs.as<uint64_t>() + nkeys, nlocs);
+    c->launches += 2;
+    MCG_CUDA(cudaGetLastError());
+    TRACE("runs: emit");
     // the sort scratch goes back before the table is allocated (peak memory)
     MCG_CUDA(cudaStreamSynchronize(c->stream));
     db->feat.release();
