@@ -247,14 +247,29 @@ table_tilescan_kernel(int64_t* tmax, uint32_t ntiles)
     if(threadIdx.x == 0) tmax[ntiles] = s_carry;
 }
 
-// pass 3: running maximum inside the tile (+ carry of pass 2) -> slot of every key; keys and
-// payloads are written front to back
+// pass 3: running maximum inside the tile (+ carry of pass 2) -> slot of every key.  The table is
+// written BUCKET-centric: tile t owns the buckets (E(t-1), E(t)], E(t) = bucket of its last key (the
+// last tile: up to the end of the table), assembles them -- empty ones included -- in shared memory,
+// TBL_CH buckets at a time, and streams them out as whole 128-byte lines: every byte of the table is
+// written exactly once, front to back, no clearing pass, no partial-sector writes.  Bucket E(t) can
+// also hold the first one or two keys of tile t+1: tile t places them (their slots follow from its
+// own running maximum), tile t+1 skips them.
+constexpr int TBL_CH = 256;
+
 __global__ void __launch_bounds__(TB_THREADS)
-table_place_kernel(uint32_t* table, const uint32_t* ukeys, const uint8_t* sizes, const uint64_t* offs, const uint64_t* locs,
-                   uint32_t nkeys, TableGeom g, const int64_t* tcarry)
+table_build_kernel(uint4* __restrict__ table4, const uint32_t* __restrict__ ukeys, const uint8_t* __restrict__ sizes,
+                   const uint64_t* __restrict__ offs, const uint64_t* __restrict__ locs,
+                   uint32_t nkeys, TableGeom g, const int64_t* __restrict__ tcarry, uint64_t cap, uint32_t ntiles)
 {
+    extern __shared__ __align__(16) uint4 lines[];              // [TBL_CH][8]
     __shared__ int64_t s[TB_THREADS / 32];
-    const uint64_t base = uint64_t(blockIdx.x) * TB_TILE + uint64_t(threadIdx.x) * TB_ITEMS;
+    __shared__ int32_t s_slot[TB_TILE + 2];                     // slot - 3 * B0 of the tile's keys (+ <= 2 keys of the next tile)
+    __shared__ int64_t s_end[2];                                // running maximum / slot at the last key of the tile
+    __shared__ int s_extra;
+    const int tid = threadIdx.x;
+    const uint64_t j0 = uint64_t(blockIdx.x) * TB_TILE;
+    const uint64_t j1 = min(j0 + uint64_t(TB_TILE), uint64_t(nkeys));
+    const uint64_t base = j0 + uint64_t(tid) * TB_ITEMS;
     int64_t d[TB_ITEMS];
     int64_t m = INT64_MIN;
 #pragma unroll
@@ -264,34 +279,83 @@ table_place_kernel(uint32_t* table, const uint32_t* ukeys, const uint8_t* sizes,
         m = max(m, d[t]);
         d[t] = m;                                   // inclusive running maximum inside the thread
     }
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = tid & 31, warp = tid >> 5;
     int64_t v = m;
     for(int dd = 1; dd < 32; dd <<= 1) {
         const int64_t o = __shfl_up_sync(0xFFFFFFFFu, v, dd);
         if(lane >= dd) v = max(v, o);
     }
     if(lane == 31) s[warp] = v;
+    if(tid == 0) s_extra = 0;
     __syncthreads();
-    int64_t pre = tcarry[blockIdx.x];
+    const int64_t mprev = tcarry[blockIdx.x];
+    int64_t pre = mprev;
     for(int w = 0; w < warp; ++w) pre = max(pre, s[w]);
     int64_t before = __shfl_up_sync(0xFFFFFFFFu, v, 1);     // maximum of the lanes before this one
     if(lane == 0) before = INT64_MIN;
     pre = max(pre, before);
+    const uint64_t B0 = blockIdx.x == 0 ? 0ull : uint64_t(int64_t(j0) - 1 + mprev) / TABLE_BUCKET_SLOTS + 1ull;
 #pragma unroll
     for(int t = 0; t < TB_ITEMS; ++t) {
         const uint64_t j = base + t;
-        if(j >= nkeys) break;
-        const uint64_t slot = uint64_t(int64_t(j) + max(pre, d[t]));
-        const uint64_t bkt = slot / TABLE_BUCKET_SLOTS;
-        const uint32_t st = uint32_t(slot - bkt * TABLE_BUCKET_SLOTS);
-        const uint32_t size = sizes[j];
-        const uint64_t o = offs[j];
-        const uint64_t l0 = size > 0 ? locs[o] : 0ull, l1 = size > 1 ? locs[o + 1] : 0ull;
-        uint32_t* line = table + bkt * TABLE_BUCKET_WORDS;
-        line[st] = ukeys[j];
-        uint4* pay = reinterpret_cast<uint4*>(line + 8 + 8 * st);
-        pay[0] = make_uint4(size, 0u, uint32_t(o), uint32_t(o >> 32));
-        pay[1] = make_uint4(uint32_t(l0), uint32_t(l0 >> 32), uint32_t(l1), uint32_t(l1 >> 32));
+        if(j < j1) {
+            const int64_t mx = max(pre, d[t]);
+            const int64_t slot = int64_t(j) + mx;
+            s_slot[j - j0] = int32_t(slot - int64_t(TABLE_BUCKET_SLOTS * B0));      // negative: placed by the previous tile
+            if(j + 1 == j1) { s_end[0] = mx; s_end[1] = slot; }
+        }
+    }
+    __syncthreads();
+    const bool last_tile = blockIdx.x + 1 == ntiles;
+    const uint64_t B1 = last_tile ? cap - 1 : uint64_t(s_end[1]) / TABLE_BUCKET_SLOTS;
+    if(tid == 0 && !last_tile) {
+        int64_t mx = s_end[0];
+        int extra = 0;
+        for(int q = 0; q < 2; ++q) {
+            const uint64_t jn = j1 + q;
+            if(jn >= nkeys) break;
+            mx = max(mx, int64_t(TABLE_BUCKET_SLOTS) * table_bucket(ukeys[jn], g) - int64_t(jn));
+            const int64_t slot = int64_t(jn) + mx;
+            if(uint64_t(slot) / TABLE_BUCKET_SLOTS != B1) break;
+            s_slot[TB_TILE + q] = int32_t(slot - int64_t(TABLE_BUCKET_SLOTS * B0));
+            ++extra;
+        }
+        s_extra = extra;
+    }
+    __syncthreads();
+    // items 0 .. nitems-1 are the keys j0 + i (a full tile whenever there is a next one)
+    const int nitems = int(j1 - j0) + s_extra;
+    int ia = 0;
+    while(ia < nitems && s_slot[ia] < 0) ++ia;              // <= 2 keys
+    uint32_t* words = reinterpret_cast<uint32_t*>(lines);
+    for(uint64_t cb = B0; cb <= B1; cb += TBL_CH) {
+        const int nb = int(min(uint64_t(TBL_CH), B1 - cb + 1));
+        for(int i = tid; i < nb * 8; i += TB_THREADS)
+            lines[i] = (i & 7) == 0 ? make_uint4(TABLE_EMPTY, TABLE_EMPTY, TABLE_EMPTY, 0u) : make_uint4(0u, 0u, 0u, 0u);
+        const int64_t lo_rel = int64_t(TABLE_BUCKET_SLOTS) * int64_t(cb - B0), hi_rel = lo_rel + int64_t(TABLE_BUCKET_SLOTS) * nb;
+        int lo = ia, hi = nitems;                           // first item at or beyond the end of the chunk
+        while(lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if(int64_t(s_slot[mid]) < hi_rel) lo = mid + 1; else hi = mid;
+        }
+        const int ib = lo;
+        __syncthreads();
+        for(int i = ia + tid; i < ib; i += TB_THREADS) {
+            const uint64_t j = j0 + uint64_t(i);
+            const uint32_t rel = uint32_t(int64_t(s_slot[i]) - lo_rel);
+            const uint32_t b = rel / TABLE_BUCKET_SLOTS, st = rel - b * TABLE_BUCKET_SLOTS;
+            const uint32_t size = sizes[j];
+            const uint64_t o = offs[j];
+            const uint64_t l0 = size > 0 ? locs[o] : 0ull, l1 = size > 1 ? locs[o + 1] : 0ull;
+            words[b * TABLE_BUCKET_WORDS + st] = ukeys[j];
+            lines[b * 8 + 2 + 2 * st] = make_uint4(size, 0u, uint32_t(o), uint32_t(o >> 32));
+            lines[b * 8 + 3 + 2 * st] = make_uint4(uint32_t(l0), uint32_t(l0 >> 32), uint32_t(l1), uint32_t(l1 >> 32));
+        }
+        __syncthreads();
+        uint4* out = table4 + cb * 8;
+        for(int i = tid; i < nb * 8; i += TB_THREADS) out[i] = lines[i];
+        __syncthreads();
+        ia = ib;
     }
 }
 
@@ -373,14 +437,19 @@ static int build_table(mcg_db* db)
     MCG_REQUIRE(cap < (1ull << 32), "feature table too large");
     MCG_TRY(db->table.reserve(cap * 128));
     db->table_cap = cap;
-    table_clear_kernel<<<grid_for(2 * cap), 256, 0, c->stream>>>(db->table.as<uint4>(), cap);
-    c->launches++;
     if(nkeys > 0) {
-        table_place_kernel<<<ntiles, TB_THREADS, 0, c->stream>>>(db->table.as<uint32_t>(), db->keys.as<uint32_t>(), db->sizes.as<uint8_t>(),
-                                                                db->offs.as<uint64_t>(), db->locs.as<uint64_t>(), uint32_t(nkeys), g,
-                                                                c->tmp5.as<int64_t>());
-        c->launches++;
+        static bool configured = false;
+        if(!configured) {
+            MCG_CUDA(cudaFuncSetAttribute(table_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TBL_CH * 128));
+            configured = true;
+        }
+        table_build_kernel<<<ntiles, TB_THREADS, TBL_CH * 128, c->stream>>>(db->table.as<uint4>(), db->keys.as<uint32_t>(), db->sizes.as<uint8_t>(),
+                                                                          db->offs.as<uint64_t>(), db->locs.as<uint64_t>(), uint32_t(nkeys), g,
+                                                                          c->tmp5.as<int64_t>(), cap, ntiles);
+    } else {
+        table_clear_kernel<<<grid_for(2 * cap), 256, 0, c->stream>>>(db->table.as<uint4>(), cap);
     }
+    c->launches++;
     MCG_CUDA(cudaGetLastError());
     return MCG_OK;
 }
