@@ -8,7 +8,7 @@
 //   metacache_b200 query <db> <r1.fq> <r2.fq> -pairfiles [-gpus P] [-lowest rank] [-highest rank]
 //       [-hitmin n] [-hitdiff f] [-maxcand n] [-insertsize n] [-winlen n] [-winstride n]
 //       [-sketchlen n] [-out file] [-tophits] [-queryids] [-taxids|-taxids-only] [-lineage]
-//       [-mapped-only|-nomap] [-no-summary] [-no-query-params]            (query_options.cpp)
+//       [-mapped-only|-nomap] [-no-summary] [-no-query-params] [-abundances [file]] [-abundance-per rank]   (query_options.cpp)
 //
 // `-gpus P` replaces `mpirun -np P`: the database has P shards (shard = target_id % P,
 // sketch_database.h:540), shard r is written to / read from `<db>.db_<r>` in the reference's own
@@ -772,6 +772,71 @@ void show_classification(OS& os, const OutOpt& o, const TaxTables& tt, int32_t b
     }
 }
 
+// ---- per-taxon read counts and abundance estimates (classification.h:107-115, classification.cpp:362-428,
+// printing.cpp:474-516).  Counts are floats in the reference; its arithmetic is kept expression by expression.
+struct TaxaByRank {                                   // root first, then by id (classification.h:107-114)
+    bool operator()(const Taxon* l, const Taxon* r) const
+    {
+        if(l->rank > r->rank) return true;
+        if(l->rank < r->rank) return false;
+        return l->id < r->id;
+    }
+};
+using TaxCountMap = std::map<const Taxon*, float, TaxaByRank>;
+
+void estimate_abundance(const TaxTables& tt, TaxCountMap& all, int rank)
+{
+    auto lineage_at = [&](const Taxon* t, unsigned r) -> const Taxon* {
+        const int32_t x = tt.lineage[size_t(tt.index_of.at(t->id)) * 21 + r];
+        return x >= 0 ? tt.tax[size_t(x)] : nullptr;
+    };
+    if(rank != 0) {
+        // taxa below the estimation rank are added to their ancestor at (or above) it
+        Taxon probe;
+        probe.id = 0; probe.rank = uint8_t(rank - 1);
+        for(auto tc = all.lower_bound(&probe); tc != all.end();) {
+            const Taxon* anc = nullptr;
+            unsigned index = unsigned(rank);
+            while(!anc && index < 21) anc = lineage_at(tc->first, index++);
+            if(anc) { all[anc] += tc->second; tc = all.erase(tc); } else ++tc;
+        }
+    }
+    std::unordered_map<const Taxon*, std::vector<const Taxon*>> children;
+    std::unordered_map<const Taxon*, uint64_t> weights;
+    for(const auto& tc : all) weights[tc.first] = 0;
+    // leaves to root: every taxon adds its count to the closest ancestor that has a count itself
+    for(auto tc = all.rbegin(); tc != all.rend(); ++tc) {
+        uint8_t index = uint8_t(tc->first->rank + 1);
+        while(index < 21) {
+            const Taxon* parent = lineage_at(tc->first, index++);
+            if(parent && weights.count(parent)) {
+                weights[parent] += weights[tc->first] + tc->second;
+                children[parent].emplace_back(tc->first);
+                break;
+            }
+        }
+    }
+    // root to leaves: counts of inner taxa are distributed proportionally, inner taxa disappear
+    for(auto tc = all.begin(); tc != all.end();) {
+        auto ch = children.find(tc->first);
+        if(ch != children.end()) {
+            const uint64_t sum_children = weights[tc->first];
+            for(const Taxon* child : ch->second)
+                all[child] += tc->second * (all[child] + weights[child]) / sum_children;
+            tc = all.erase(tc);
+        } else {
+            ++tc;
+        }
+    }
+}
+
+void show_abundance_table(std::ostream& os, const TaxCountMap& all, uint64_t total, const std::string& ranksuf, const std::string& col)
+{
+    for(const auto& tc : all)
+        os << RANK_NAMES[tc.first->rank] << ranksuf << tc.first->name << col << tc.second << col
+           << (tc.second / double(total) * 100) << "%\n";
+}
+
 int mode_query(const Args& a)
 {
     if(a.pos.size() < 2) die("usage: metacache_b200 query <database> <reads1> [<reads2> -pairfiles] [options]");
@@ -842,6 +907,14 @@ int mode_query(const Args& a)
     o.summary = !a.has({"no-summary", "nosummary"});
     o.params = !a.has({"no-query-params", "noqueryparams"});
     o.lowest = q.lowest; o.highest = q.highest;
+    const bool show_abund = a.has({"abundances"});                              // query_options.cpp:310-320
+    std::string abund_name = a.get({"abundances"}, "");
+    int est_rank = 21;
+    {
+        const std::string s = a.get({"abundance-per", "abundances-per", "abundance_per", "abundances_per"}, "");
+        if(!s.empty()) { const int r = rank_from_name(s); if(r < 20) est_rank = r; }
+    }
+    const bool tax_counts = show_abund || est_rank != 21;
 
     std::ofstream fout;
     const std::string outname = a.get({"out"}, "");
@@ -851,6 +924,14 @@ int mode_query(const Args& a)
         std::cout << "Per-Read mappings will be written to file: " << outname << std::endl;
     }
     std::ostream& os = outname.empty() ? std::cout : fout;
+    if(abund_name == outname) abund_name.clear();                               // query_options.cpp:355
+    std::ofstream fabund;
+    if(!abund_name.empty()) {                                                   // mode_query.cpp:104-115
+        fabund.open(abund_name);
+        if(!fabund.good()) die("Could not write to file " + abund_name);
+        std::cout << "Per-Taxon mappings will be written to file: " << abund_name << std::endl;
+    }
+    std::ostream& os_tax = abund_name.empty() ? os : fabund;
     const std::string& cm = o.comment;
     if(o.params) {                                                              // printing.cpp:40-112
         if(o.map != 2) {
@@ -867,6 +948,9 @@ int mode_query(const Args& a)
             os << cm << "File based paired-end mode:\n" << cm << "  Reads from two consecutive files will be interleaved.\n"
                << cm << "  Max insert size considered " << q.insertsize << ".\n";
         }
+        if(est_rank != 21)
+            os << cm << "A list of absolute and relative abundances for each '" << RANK_NAMES[est_rank]
+               << "' will be generated after the read mapping.\n";
         os << cm << "Using " << a.geti({"threads"}, 1) << " threads\n";
     }
     if(o.map != 2) {                                                            // classification.cpp:486-511
@@ -903,6 +987,7 @@ int mode_query(const Args& a)
     lap("read + index read files");
     const int K = q.maxcand;
     uint64_t stats[22] = {0};
+    std::vector<uint64_t> tax_reads(tax_counts ? tt.tax.size() : 0, 0);      // reads per assigned taxon
     const size_t BATCH = size_t(1) << 20;
     std::string b1, b2;
     std::vector<int64_t> o1, o2;
@@ -940,6 +1025,7 @@ int mode_query(const Args& a)
         check(mcg_merge_classify(ctx_for_shard(0), &q, ctax.data(), chits.data(), cn.data(), P, int64_t(n), mtax.data(), mhits.data(),
                                  mn.data(), best.data(), brank.data(), stats), "mcg_merge_classify");
         lap("query batch (device)");
+        if(tax_counts) for(size_t i = 0; i < n; ++i) if(best[i] >= 0) ++tax_reads[size_t(best[i])];
         if(o.map == 2) continue;
         // per-read lines: formatted by all threads into their own buffers, written in order
         std::vector<StrOut> parts(NT);
@@ -979,6 +1065,20 @@ int mode_query(const Args& a)
         }
         for(auto& part : parts) os.write(part.s.data(), std::streamsize(part.s.size()));
         lap("format + write output");
+    }
+    if(tax_counts) {                                                            // classification.cpp:753-764
+        TaxCountMap all;
+        for(size_t t = 0; t < tax_reads.size(); ++t) if(tax_reads[t] > 0) all[tt.tax[t]] = float(tax_reads[t]);
+        const uint64_t total = stats[20] + stats[21];
+        if(show_abund) {
+            os_tax << cm << "query summary: number of queries mapped per taxon\n";
+            show_abundance_table(os_tax, all, total, o.ranksuf, o.col);
+        }
+        if(est_rank != 21) {
+            estimate_abundance(tt, all, est_rank);
+            os_tax << cm << "estimated abundance (number of queries) per " << RANK_NAMES[est_rank] << "\n";
+            show_abundance_table(os_tax, all, total, o.ranksuf, o.col);
+        }
     }
     const double t1 = now();
     if(o.summary) {                                                             // printing.cpp:522-641

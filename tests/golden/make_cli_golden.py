@@ -1,0 +1,32 @@
+"""Regenerates the golden command-line outputs of tests/test_gpu_cli_dropin.py from the REFERENCE
+binary (oracle/_ref/metacache_mpi_ref, built from /root/reference by oracle/Makefile, run as
+`mpirun -np 2` through oracle/mpirun_shim.py).  Needs no GPU.  Usage: python tests/golden/make_cli_golden.py"""
+import os
+import sys
+import tempfile
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from __graft_entry__ import load_package  # noqa: E402
+
+load_package()
+import test_gpu_cli_dropin as t  # noqa: E402
+
+CASES = {
+    "cli_np2_species_maxcand4.txt": t.QFLAGS,
+    "cli_np2_abundances.txt": ["-pairfiles", "-lowest", "species", "-maxcand", "4", "-hitmin", "4", "-hitdiff", "30",
+                               "-abundances", "-abundance-per", "species"],
+}
+
+if __name__ == "__main__":
+    assert os.path.exists(t.REF), "build the reference first: make -C oracle"
+    with tempfile.TemporaryDirectory() as d:
+        t.make_files(d)
+        t.run([sys.executable, t.SHIM, "-np", "2", "--", t.REF, "build", "rdb", "genomes", "-taxonomy", "tax"], d)
+        for name, flags in CASES.items():
+            t.run([sys.executable, t.SHIM, "-np", "2", "--", t.REF, "query", "rdb", "r1.fq", "r2.fq"] + flags +
+                  ["-threads", "1", "-query-limit", "300", "-out", "res.txt"], d)
+            with open(os.path.join(ROOT, "tests", "golden", name), "w") as f:
+                f.write("\n".join(t.stable_lines(os.path.join(d, "res.txt"))) + "\n")
+            print("wrote", name)

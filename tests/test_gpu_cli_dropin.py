@@ -142,3 +142,36 @@ def test_cli_defaults_and_overpopulated(tmp_path):
         a = parse_shard(os.path.join(d, "gdb.db_%d" % r))
         b = parse_shard(os.path.join(d, "rdb.db_%d" % r))
         assert a[4] == b[4] and a[3] == b[3]
+
+
+def test_cli_abundances(tmp_path):
+    """-abundances / -abundance-per (classification.cpp:362-428, printing.cpp:474-516): per-taxon read
+    counts and the estimate at species level, in the mapping output and in a file of their own.
+    -hitdiff 30 leaves most reads at genus level, so the estimate has counts to distribute."""
+    d = str(tmp_path)
+    make_files(d)
+    run([EXE, "build", "gdb", "genomes", "-taxonomy", "tax", "-gpus", "2"], d)
+    base = ["-pairfiles", "-lowest", "species", "-maxcand", "4", "-hitmin", "4", "-hitdiff", "30"]
+    inline = base + ["-abundances", "-abundance-per", "species"]
+    tofile = base + ["-abundance-per", "species", "-abundances"]
+    run([EXE, "query", "gdb", "r1.fq", "r2.fq"] + inline + ["-out", "res_gpu.txt"], d)
+    run([EXE, "query", "gdb", "r1.fq", "r2.fq"] + tofile + ["ab_gpu.txt", "-out", "res_gpu2.txt"], d)
+    mine = stable_lines(os.path.join(d, "res_gpu.txt"))
+    golden = os.path.join(ROOT, "tests", "golden", "cli_np2_abundances.txt")
+    if os.path.exists(golden):
+        assert mine == open(golden).read().splitlines()
+    assert any(l.startswith("# estimated abundance") for l in mine)
+    tail = mine[[i for i, l in enumerate(mine) if l.startswith("# query summary")][0]:]
+    tail = tail[:[i for i, l in enumerate(tail) if l.startswith("# queries:")][0]]
+    assert open(os.path.join(d, "ab_gpu.txt")).read().splitlines() == tail
+    if not os.path.exists(REF):
+        assert os.path.exists(golden), "neither oracle/_ref nor the golden output is available"
+        return
+    run([sys.executable, SHIM, "-np", "2", "--", REF, "build", "rdb", "genomes", "-taxonomy", "tax"], d)
+    ref_tail = ["-threads", "1", "-query-limit", "300"]
+    run([sys.executable, SHIM, "-np", "2", "--", REF, "query", "rdb", "r1.fq", "r2.fq"] + inline + ref_tail + ["-out", "res_ref.txt"], d)
+    run([sys.executable, SHIM, "-np", "2", "--", REF, "query", "rdb", "r1.fq", "r2.fq"] + tofile + ["ab_ref.txt"] + ref_tail +
+        ["-out", "res_ref2.txt"], d)
+    assert mine == stable_lines(os.path.join(d, "res_ref.txt"))
+    assert stable_lines(os.path.join(d, "res_gpu2.txt")) == stable_lines(os.path.join(d, "res_ref2.txt"))
+    assert open(os.path.join(d, "ab_gpu.txt")).read() == open(os.path.join(d, "ab_ref.txt")).read()
