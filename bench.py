@@ -548,6 +548,36 @@ def run_extras(args, ctx, api, synth, taxonomy, torch, dist, dev, stream, world,
     except Exception as e:
         out["query_long"] = {"error": repr(e)}
     db.close()
+    # the reference's own build / query code (oracle/_ref, one MPI rank = one thread, as in the reference: build is
+    # single-threaded per rank, querying.h runs T such workers per rank) on a bounded sample of the same data
+    if world == 1 and not args.no_cpu:
+        try:
+            sys.path.insert(0, ROOT)
+            from oracle import pyoracle as po
+            if po.have_reference():
+                ref = po.Reference()
+                rdb = ref.db_create()
+                rdb.set_taxonomy(ids, par, rk)
+                ng = 4
+                t0 = time.perf_counter()
+                for g in range(ng):
+                    rdb.add_target(genomes[g], "SYN%06d.1" % g, int(species[g]), 1, 0)
+                tb = time.perf_counter() - t0
+                out["build"]["cpu_baseline"] = {"value": ng * GENOME_LEN / tb, "unit": "bp/s", "cores": 1, "kind": "reference",
+                                                "sample": "database::add_target_distributed on %d of the %d genomes (%d Mbp), one rank = "
+                                                          "one thread, %.1f s; the reference scales with the number of MPI ranks"
+                                                          % (ng, QG, ng * GENOME_LEN // 1_000_000, tb)}
+                sub = [genomes[g] for g in range(ng)]
+                sb1, so1, sb2, so2, _ = synth.make_read_pairs(sub, 20_000, seed=7)
+                t0 = time.perf_counter()
+                for i in range(20_000):
+                    rdb.query_local(sb1[so1[i]:so1[i + 1]], sb2[so2[i]:so2[i + 1]], 4, 4)
+                tq = time.perf_counter() - t0
+                out["query"]["cpu_baseline"] = {"value": 2 * 20_000 / tq, "unit": "reads/s", "cores": 1, "kind": "reference",
+                                                "sample": "accumulate_matches + candidate generation for 20000 pairs against the %d-genome "
+                                                          "database above, one worker thread, %.1f s (ctypes call per read included)" % (ng, tq)}
+        except Exception as e:      # pragma: no cover
+            out["build"]["cpu_baseline"] = {"error": repr(e)}
     return out
 
 
