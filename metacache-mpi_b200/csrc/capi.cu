@@ -186,19 +186,6 @@ int mcg_ctx_create(int device, void* stream, mcg_ctx** out)
         set_error("device %d is sm_%d%d; libmcgpu is built for sm_100a only", device, prop.major, prop.minor);
         return MCG_ERR_CUDA;
     }
-    {
-        // experiment knob: granularity of L2 fills from DRAM (the table probes are random 32..64-byte accesses)
-        const char* e2 = getenv("MCG_L2_FETCH");
-        size_t cur = 0;
-        cudaDeviceGetLimit(&cur, cudaLimitMaxL2FetchGranularity);
-        if(e2 != nullptr) {
-            const cudaError_t r = cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, size_t(atoi(e2)));
-            size_t now = 0;
-            cudaDeviceGetLimit(&now, cudaLimitMaxL2FetchGranularity);
-            fprintf(stderr, "[mcg] L2 fetch granularity %zu -> %zu (%s)\n", cur, now, cudaGetErrorString(r));
-            cudaGetLastError();
-        }
-    }
     mcg_ctx* c = new mcg_ctx;
     c->device = device;
     if(stream != nullptr) {
