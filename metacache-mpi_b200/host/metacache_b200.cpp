@@ -8,7 +8,8 @@
 //   metacache_b200 query <db> <r1.fq> <r2.fq> -pairfiles [-gpus P] [-lowest rank] [-highest rank]
 //       [-hitmin n] [-hitdiff f] [-maxcand n] [-insertsize n] [-winlen n] [-winstride n]
 //       [-sketchlen n] [-out file] [-tophits] [-queryids] [-taxids|-taxids-only] [-lineage]
-//       [-mapped-only|-nomap] [-no-summary] [-no-query-params] [-abundances [file]] [-abundance-per rank]   (query_options.cpp)
+//       [-mapped-only|-nomap] [-no-summary] [-no-query-params] [-abundances [file]] [-abundance-per rank]
+//       [-hits-per-seq [file]]                                            (query_options.cpp)
 //
 // `-gpus P` replaces `mpirun -np P`: the database has P shards (shard = target_id % P,
 // sketch_database.h:540), shard r is written to / read from `<db>.db_<r>` in the reference's own
@@ -915,6 +916,13 @@ int mode_query(const Args& a)
         if(!s.empty()) { const int r = rank_from_name(s); if(r < 20) est_rank = r; }
     }
     const bool tax_counts = show_abund || est_rank != 21;
+    // -hits-per-seq: the per-target match lists are dead code in this fork (classification.cpp:694-699 is commented
+    // out): the reference prints the table header only, and so does this driver
+    const std::initializer_list<const char*> HPS = {"hits-per-seq", "hitsperseq", "hits_per_seq", "hits-per-sequence",
+                                                    "hitspersequence", "hits_per_sequence"};
+    const bool hits_per_seq = a.has(HPS);
+    std::string targets_name = a.get(HPS, "");
+    if(hits_per_seq) o.queryids = true;                                         // query_options.cpp:308
 
     std::ofstream fout;
     const std::string outname = a.get({"out"}, "");
@@ -924,6 +932,14 @@ int mode_query(const Args& a)
         std::cout << "Per-Read mappings will be written to file: " << outname << std::endl;
     }
     std::ostream& os = outname.empty() ? std::cout : fout;
+    if(targets_name == outname) targets_name.clear();                           // query_options.cpp:353
+    std::ofstream ftargets;
+    if(!targets_name.empty()) {                                                 // mode_query.cpp:91-102
+        ftargets.open(targets_name);
+        if(!ftargets.good()) die("Could not write to file " + targets_name);
+        std::cout << "Per-Target mappings will be written to file: " << targets_name << std::endl;
+    }
+    std::ostream& os_tgt = targets_name.empty() ? os : ftargets;
     if(abund_name == outname) abund_name.clear();                               // query_options.cpp:355
     std::ofstream fabund;
     if(!abund_name.empty()) {                                                   // mode_query.cpp:104-115
@@ -948,6 +964,9 @@ int mode_query(const Args& a)
             os << cm << "File based paired-end mode:\n" << cm << "  Reads from two consecutive files will be interleaved.\n"
                << cm << "  Max insert size considered " << q.insertsize << ".\n";
         }
+        if(hits_per_seq)                                                        // printing.cpp:95-103 (both lines hang on this switch)
+            os << cm << "A list of hits per reference sequence will be generated after the read mapping.\n"
+               << cm << "A list of absolute and relative abundances per taxon will be generated after the read mapping.\n";
         if(est_rank != 21)
             os << cm << "A list of absolute and relative abundances for each '" << RANK_NAMES[est_rank]
                << "' will be generated after the read mapping.\n";
@@ -1066,6 +1085,11 @@ int mode_query(const Args& a)
         for(auto& part : parts) os.write(part.s.data(), std::streamsize(part.s.size()));
         lap("format + write output");
     }
+    if(hits_per_seq)                                                            // printing.cpp:437-451, no rows (see above)
+        os_tgt << cm << "--- list of hits for each reference sequence ---\n"
+               << cm << "window start position within sequence = window_index * window_stride(=" << q.winstride << ")\n"
+               << cm << "TABLE_LAYOUT: " << " sequence " << o.col << " windows_in_sequence " << o.col
+               << "queryid/window_index:hits/window_index:hits/...,queryid/...\n";
     if(tax_counts) {                                                            // classification.cpp:753-764
         TaxCountMap all;
         for(size_t t = 0; t < tax_reads.size(); ++t) if(tax_reads[t] > 0) all[tt.tax[t]] = float(tax_reads[t]);

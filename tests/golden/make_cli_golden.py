@@ -17,6 +17,7 @@ CASES = {
     "cli_np2_species_maxcand4.txt": t.QFLAGS,
     "cli_np2_abundances.txt": ["-pairfiles", "-lowest", "species", "-maxcand", "4", "-hitmin", "4", "-hitdiff", "30",
                                "-abundances", "-abundance-per", "species"],
+    "cli_np2_hits_per_seq.txt": ["-pairfiles", "-lowest", "species", "-maxcand", "4", "-hitmin", "4", "-hitdiff", "80", "-hits-per-seq"],
 }
 
 if __name__ == "__main__":

@@ -175,3 +175,28 @@ def test_cli_abundances(tmp_path):
     assert mine == stable_lines(os.path.join(d, "res_ref.txt"))
     assert stable_lines(os.path.join(d, "res_gpu2.txt")) == stable_lines(os.path.join(d, "res_ref2.txt"))
     assert open(os.path.join(d, "ab_gpu.txt")).read() == open(os.path.join(d, "ab_ref.txt")).read()
+
+
+def test_cli_hits_per_seq(tmp_path):
+    """-hits-per-seq: the per-target lists are dead code in this fork of the reference:
+    query ids are forced on, two parameter lines appear and the table header is printed without rows --
+    in the mapping output or in a file of its own"""
+    d = str(tmp_path)
+    make_files(d)
+    run([EXE, "build", "gdb", "genomes", "-taxonomy", "tax", "-gpus", "2"], d)
+    flags = ["-pairfiles", "-lowest", "species", "-maxcand", "4", "-hitmin", "4", "-hitdiff", "80", "-hits-per-seq"]
+    run([EXE, "query", "gdb", "r1.fq", "r2.fq"] + flags + ["-out", "res_gpu.txt"], d)
+    run([EXE, "query", "gdb", "r1.fq", "r2.fq"] + flags + ["hps_gpu.txt", "-out", "res_gpu2.txt"], d)
+    mine = stable_lines(os.path.join(d, "res_gpu.txt"))
+    golden = os.path.join(ROOT, "tests", "golden", "cli_np2_hits_per_seq.txt")
+    assert mine == open(golden).read().splitlines()
+    hdr = [l for l in mine if "list of hits for each reference sequence" in l or "window start position" in l or
+           l.startswith("# TABLE_LAYOUT:  sequence")]
+    assert len(hdr) == 3 and open(os.path.join(d, "hps_gpu.txt")).read().splitlines() == hdr
+    assert [l for l in stable_lines(os.path.join(d, "res_gpu2.txt")) if l not in hdr] == [l for l in mine if l not in hdr]
+    if not os.path.exists(REF):
+        return
+    run([sys.executable, SHIM, "-np", "2", "--", REF, "build", "rdb", "genomes", "-taxonomy", "tax"], d)
+    run([sys.executable, SHIM, "-np", "2", "--", REF, "query", "rdb", "r1.fq", "r2.fq"] + flags +
+        ["-threads", "1", "-query-limit", "300", "-out", "res_ref.txt"], d)
+    assert mine == stable_lines(os.path.join(d, "res_ref.txt"))
