@@ -494,6 +494,90 @@ def run_extras(args, ctx, api, synth, taxonomy, torch, dist, dev, stream, world,
                 "api": "mcg_query_batch (pinned host buffers, per-shard top lists)", "same_as_device_path": same_q}
     except Exception as e:
         qe2e = {"error": repr(e)}
+    # N > 1: every rank copying all reads over PCIe itself (above) is bounded by the host.  The reads of a batch
+    # cross PCIe ONCE (rank 0), travel to the other GPUs by an NCCL broadcast over NVLink, every GPU queries its
+    # shard, the per-shard top lists land in rank 0 (P2P stores / all-gather), rank 0 merges, classifies and
+    # copies the result to the host.
+    if world > 1 and isinstance(qe2e, dict) and "error" not in qe2e:
+        try:
+            hdo1 = torch.from_numpy(o1).pin_memory(); hdo2 = torch.from_numpy(o2).pin_memory()
+            hbest = torch.empty(npairs, dtype=torch.int32, pin_memory=True)
+            hmt = torch.empty((npairs, Kc), dtype=torch.int32, pin_memory=True)
+            hmh = torch.empty((npairs, Kc), dtype=torch.int32, pin_memory=True)
+            n1, n2 = len(b1), len(b2)
+
+            # sub-batches: while sub-batch j is broadcast and queried, rank 0 copies sub-batch j + 1 over PCIe
+            NSUB = 4
+            assert npairs % NSUB == 0
+            ns = npairs // NSUB
+            rel = torch.from_numpy(np.arange(ns + 1, dtype=np.int64) * 150).pin_memory()     # offsets of a sub-batch
+            drel = torch.empty(ns + 1, dtype=torch.int64, device=dev)
+            copy_stream = torch.cuda.Stream(device=dev)
+            ev_in = [torch.cuda.Event() for _ in range(NSUB)]
+            ev_free = torch.cuda.Event()
+
+            def qbcast():
+                cur = torch.cuda.current_stream()
+                if rank == 0:
+                    ev_free.record(cur)                       # the previous batch no longer reads d1 / d2
+                    with torch.cuda.stream(copy_stream):
+                        copy_stream.wait_event(ev_free)
+                        drel.copy_(rel, non_blocking=True)
+                        for j in range(NSUB):
+                            d1[j * ns * 150:(j + 1) * ns * 150].copy_(hb1[j * ns * 150:(j + 1) * ns * 150], non_blocking=True)
+                            d2[j * ns * 150:(j + 1) * ns * 150].copy_(hb2[j * ns * 150:(j + 1) * ns * 150], non_blocking=True)
+                            ev_in[j].record(copy_stream)
+                for j in range(NSUB):
+                    if rank == 0:
+                        cur.wait_event(ev_in[j])
+                    if j == 0:
+                        dist.broadcast(drel, src=0)
+                    s1 = d1[j * ns * 150:(j + 1) * ns * 150 + (64 if j == NSUB - 1 else 0)]
+                    s2 = d2[j * ns * 150:(j + 1) * ns * 150 + (64 if j == NSUB - 1 else 0)]
+                    dist.broadcast(s1, src=0)
+                    dist.broadcast(s2, src=0)
+                    rc = L.mcg_query_batch_dev(db.h, C.byref(q), d1.data_ptr() + j * ns * 150, drel.data_ptr(), ns * 150,
+                                               d2.data_ptr() + j * ns * 150, drel.data_ptr(), ns * 150, ns, 150,
+                                               out_t + j * ns * Kc * 4, out_h + j * ns * Kc * 4, out_n + j * ns * 4)
+                    if rc != 0:
+                        raise RuntimeError(L.mcg_last_error().decode())
+                if hdl_t is not None:
+                    hdl_t.barrier(channel=0)
+                    ct, ch, cn = gt, gh, gn
+                else:
+                    dist.all_gather_into_tensor(gt.view(world * npairs, Kc), lt)
+                    dist.all_gather_into_tensor(gh.view(world * npairs, Kc), lh)
+                    dist.all_gather_into_tensor(gn.view(world * npairs), ln)
+                    ct, ch, cn = gt, gh, gn
+                if rank == 0:
+                    stats.zero_()
+                    rc = L.mcg_merge_classify_dev(ctx.h, C.byref(q), ct.data_ptr(), ch.data_ptr(), cn.data_ptr(), world, npairs,
+                                                  mt.data_ptr(), mh.data_ptr(), mn.data_ptr(), best.data_ptr(), brank.data_ptr(),
+                                                  stats.data_ptr())
+                    if rc != 0:
+                        raise RuntimeError(L.mcg_last_error().decode())
+                    hbest.copy_(best, non_blocking=True); hmt.copy_(mt, non_blocking=True); hmh.copy_(mh, non_blocking=True)
+                if hdl_t is not None:
+                    hdl_t.barrier(channel=1)
+                torch.cuda.synchronize()
+            st_before = stats.clone()
+            qbcast()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(3):
+                qbcast()
+            barrier()
+            qb = max_over_ranks(time.perf_counter() - t0) / 3
+            same_b = bool((stats == st_before).all().item()) if rank == 0 else None
+            qe2e = {"value": 2 * npairs / qb, "unit": "reads/s", "ms_per_batch": 1e3 * qb,
+                    "h2d_bytes_per_step": int(n1 + n2 + 16 * (npairs + 1)), "d2h_bytes_per_step": int(npairs * (8 * Kc + 4)),
+                    "api": "rank 0: pinned host reads -> H2D once -> NCCL broadcast over NVLink -> mcg_query_batch_dev on every "
+                           "shard -> top lists into rank 0 -> mcg_merge_classify_dev -> D2H of taxa and merged lists; "
+                           "%d sub-batches, the PCIe copy of one overlaps the broadcast and query of the previous" % NSUB,
+                    "same_statistics_as_device_path": same_b,
+                    "every_rank_copies_all_reads_itself": qe2e}
+        except Exception as e:      # pragma: no cover
+            qe2e["broadcast_error"] = repr(e)
     # byte accounting per pair on this shard: 300 B reads + 32 B per probed feature + 8 B per location + 8K
     nfeat = 4 * 16
     mloc = None

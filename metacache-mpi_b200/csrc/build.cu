@@ -708,35 +708,119 @@ static int fetch_csr(mcg_db* db, std::vector<uint32_t>& keys, std::vector<uint8_
     return MCG_OK;
 }
 
+// ---- export / import on the device (the host loops over tens of millions of buckets were the
+// longest phases of the command-line driver)
+struct TmpBuf : DevBuf {                         // scratch that goes back to the allocator on every return path
+    ~TmpBuf() { if(p != nullptr) release(); }
+};
+
+__global__ void exp_flags_kernel(const uint8_t* sizes, uint32_t nkeys, uint32_t* live)
+{
+    const uint64_t j = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
+    if(j < nkeys) live[j] = sizes[j] != 0;
+}
+
+// non-empty keys, compacted: key, size, and the list split into targets / windows
+__global__ void exp_emit_kernel(const uint32_t* ukeys, const uint8_t* sizes, const uint64_t* offs, const uint64_t* locs, uint32_t nkeys,
+                                const uint32_t* kpos, const uint64_t* lpos, uint32_t* okeys, uint32_t* osizes, uint32_t* otg, uint32_t* own)
+{
+    const uint64_t j = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
+    if(j >= nkeys) return;
+    const uint32_t sz = sizes[j];
+    if(sz == 0) return;
+    if(okeys) okeys[kpos[j]] = ukeys[j];
+    if(osizes) osizes[kpos[j]] = sz;
+    if(otg == nullptr) return;
+    const uint64_t src = offs[j], dst = lpos[j];
+    for(uint32_t t = 0; t < sz; ++t) {
+        const uint64_t l = locs[src + t];
+        otg[dst + t] = uint32_t(l >> 32);
+        own[dst + t] = uint32_t(l);
+    }
+}
+
 int mcg_db_export(mcg_db* db, uint32_t* keys, uint32_t* sizes, uint32_t* tgts, uint32_t* wins)
 {
     MCG_REQUIRE(db != nullptr, "db is NULL");
     if(!db->finalized) { set_error("database not finalized"); return MCG_ERR_STATE; }
     mcg_ctx* c = db->ctx;
     MCG_CUDA(cudaSetDevice(c->device));
-    std::vector<uint32_t> k; std::vector<uint8_t> sz; std::vector<uint64_t> of;
-    MCG_TRY(fetch_csr(db, k, sz, of));
-    std::vector<uint64_t> locs(db->nlocs);
-    MCG_TRY(copy_out(c, locs.data(), db->locs.p, db->nlocs * 8));
+    const uint32_t nkeys = uint32_t(db->nkeys);
+    if(nkeys == 0) return MCG_OK;
+    const bool want_locs = tgts != nullptr && wins != nullptr;
+    uint32_t* kpos = nullptr; uint64_t* lpos = nullptr;
+    MCG_TRY(c->tmp0.reserve((size_t(nkeys) + 2) * 4));
+    MCG_TRY(c->tmp4.reserve((size_t(nkeys) + 2) * 8));
+    kpos = c->tmp0.as<uint32_t>();
+    lpos = c->tmp4.as<uint64_t>();
+    exp_flags_kernel<<<grid_for(nkeys), 256, 0, c->stream>>>(db->sizes.as<uint8_t>(), nkeys, kpos);
+    c->launches++;
+    MCG_TRY(exclusive_scan_u32_to_u32(c, kpos, kpos, nkeys));
+    MCG_TRY(exclusive_scan_u8_to_u64(c, db->sizes.as<uint8_t>(), lpos, nkeys));
+    uint32_t nlive = 0; uint64_t nl = 0;
+    MCG_TRY(copy_out(c, &nlive, kpos + nkeys, 4));
+    MCG_TRY(copy_out(c, &nl, lpos + nkeys, 8));
     MCG_CUDA(cudaStreamSynchronize(c->stream));
-    uint64_t ko = 0, lo = 0;
-    for(uint64_t j = 0; j < db->nkeys; ++j) {
-        if(sz[j] == 0) continue;
-        if(keys) keys[ko] = k[j];
-        if(sizes) sizes[ko] = sz[j];
-        ++ko;
-        for(uint32_t t = 0; t < sz[j]; ++t, ++lo) {
-            const uint64_t l = locs[of[j] + t];
-            if(tgts) tgts[lo] = uint32_t(l >> 32);
-            if(wins) wins[lo] = uint32_t(l);
-        }
-    }
+    MCG_TRY(c->tmp1.reserve((size_t(nlive) + 1) * 4));
+    MCG_TRY(c->tmp2.reserve((size_t(nlive) + 1) * 4));
+    TmpBuf otg, own;
+    if(want_locs) { MCG_TRY(otg.reserve((nl + 1) * 4)); MCG_TRY(own.reserve((nl + 1) * 4)); }
+    exp_emit_kernel<<<grid_for(nkeys), 256, 0, c->stream>>>(db->keys.as<uint32_t>(), db->sizes.as<uint8_t>(), db->offs.as<uint64_t>(),
+                                                           db->locs.as<uint64_t>(), nkeys, kpos, lpos, c->tmp1.as<uint32_t>(),
+                                                           c->tmp2.as<uint32_t>(), want_locs ? otg.as<uint32_t>() : nullptr,
+                                                           want_locs ? own.as<uint32_t>() : nullptr);
+    c->launches++;
+    MCG_CUDA(cudaGetLastError());
+    if(keys) MCG_TRY(copy_out(c, keys, c->tmp1.p, size_t(nlive) * 4));
+    if(sizes) MCG_TRY(copy_out(c, sizes, c->tmp2.p, size_t(nlive) * 4));
+    if(want_locs) { MCG_TRY(copy_out(c, tgts, otg.p, nl * 4)); MCG_TRY(copy_out(c, wins, own.p, nl * 4)); }
+    MCG_CUDA(cudaStreamSynchronize(c->stream));
     return MCG_OK;
 }
 
 int mcg_db_key_sizes(mcg_db* db, uint32_t* keys, uint32_t* sizes)
 {
     return mcg_db_export(db, keys, sizes, nullptr, nullptr);
+}
+
+// err: bit 0 size > 255, bit 1 key 0xFFFFFFFF; mx: [0] largest target, [1] largest window
+__global__ void imp_check_kernel(const uint32_t* keys, const uint32_t* sizes, uint64_t nkeys, const uint32_t* tgts, const uint32_t* wins,
+                                 uint64_t nlocs, uint32_t* err, uint32_t* mx)
+{
+    const uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
+    uint32_t e = 0, mt = 0, mw = 0;
+    if(i < nkeys) { if(sizes[i] > 255u) e |= 1u; if(keys[i] == EMPTY_KEY) e |= 2u; }
+    if(i < nlocs) { mt = tgts[i]; mw = wins[i]; }
+    for(int d = 16; d > 0; d >>= 1) {
+        e |= __shfl_down_sync(0xFFFFFFFFu, e, d);
+        mt = max(mt, __shfl_down_sync(0xFFFFFFFFu, mt, d));
+        mw = max(mw, __shfl_down_sync(0xFFFFFFFFu, mw, d));
+    }
+    if((threadIdx.x & 31) == 0) {
+        if(e) atomicOr(err, e);
+        if(mt) atomicMax(mx, mt);
+        if(mw) atomicMax(mx + 1, mw);
+    }
+}
+
+// sorted position j <- bucket order[j] of the file: size cut to maxlocs (sketch_database.h:361-364), duplicate keys flagged
+__global__ void imp_sizes_kernel(const uint32_t* skeys, const uint32_t* order, const uint32_t* sizes, uint32_t nkeys, uint32_t maxlocs,
+                                 uint8_t* osz, uint32_t* err)
+{
+    const uint64_t j = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
+    if(j >= nkeys) return;
+    if(j > 0 && skeys[j] == skeys[j - 1]) atomicOr(err, 4u);
+    osz[j] = uint8_t(min(sizes[order[j]], maxlocs));
+}
+
+__global__ void imp_locs_kernel(const uint32_t* order, const uint64_t* start, const uint8_t* osz, const uint64_t* offs, uint32_t nkeys,
+                                const uint32_t* tgts, const uint32_t* wins, uint64_t* locs)
+{
+    const uint64_t j = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
+    if(j >= nkeys) return;
+    const uint64_t src = start[order[j]], dst = offs[j];
+    const uint32_t sz = osz[j];
+    for(uint32_t t = 0; t < sz; ++t) locs[dst + t] = (uint64_t(tgts[src + t]) << 32) | wins[src + t];
 }
 
 int mcg_db_import(mcg_db* db, const uint32_t* keys, const uint32_t* sizes,
@@ -749,40 +833,58 @@ int mcg_db_import(mcg_db* db, const uint32_t* keys, const uint32_t* sizes,
     if(db->finalized || db->nwin > 0) { set_error("import needs an empty database"); return MCG_ERR_STATE; }
     mcg_ctx* c = db->ctx;
     MCG_CUDA(cudaSetDevice(c->device));
-    // bucket order of a reference-written file is table order: sort by key on the host
-    std::vector<uint64_t> start(nkeys + 1, 0);
-    for(uint64_t j = 0; j < nkeys; ++j) {
-        MCG_REQUIRE(sizes[j] <= 255, "bucket larger than 255");
-        start[j + 1] = start[j] + sizes[j];
+    // the buckets of a reference-written file come in table order: everything is sorted by key on the device
+    TmpBuf d_sizes, d_tg, d_wn, d_start;
+    MCG_TRY(db->keys.reserve((nkeys + 1) * 4)); MCG_TRY(db->sizes.reserve(nkeys + 16)); MCG_TRY(db->offs.reserve((nkeys + 2) * 8));
+    MCG_TRY(d_sizes.reserve((nkeys + 1) * 4)); MCG_TRY(d_start.reserve((nkeys + 2) * 8));
+    MCG_TRY(d_tg.reserve((nlocs + 1) * 4)); MCG_TRY(d_wn.reserve((nlocs + 1) * 4));
+    MCG_TRY(c->tmp0.reserve((nkeys + 1) * 4)); MCG_TRY(c->tmp1.reserve((nkeys + 1) * 4)); MCG_TRY(c->tmp2.reserve((nkeys + 1) * 4));
+    MCG_TRY(c->tmp3.reserve(64));
+    uint32_t* skeys = db->keys.as<uint32_t>();
+    uint32_t* order = c->tmp0.as<uint32_t>();
+    uint32_t* flags = c->tmp3.as<uint32_t>();                  // [0] error bits, [1] max target, [2] max window
+    MCG_CUDA(cudaMemsetAsync(flags, 0, 16, c->stream));
+    MCG_TRY(copy_in(c, skeys, keys, nkeys * 4));
+    MCG_TRY(copy_in(c, d_sizes.p, sizes, nkeys * 4));
+    MCG_TRY(copy_in(c, d_tg.p, tgts, nlocs * 4));
+    MCG_TRY(copy_in(c, d_wn.p, wins, nlocs * 4));
+    uint64_t total = 0, lo = 0;
+    uint32_t h_flags[3] = {0, 0, 0};
+    if(nkeys > 0) {
+        imp_check_kernel<<<grid_for(std::max(nkeys, nlocs)), 256, 0, c->stream>>>(skeys, d_sizes.as<uint32_t>(), nkeys, d_tg.as<uint32_t>(),
+                                                                                 d_wn.as<uint32_t>(), nlocs, flags, flags + 1);
+        c->launches++;
+        MCG_TRY(exclusive_scan_u32_to_u64(c, d_sizes.as<uint32_t>(), d_start.as<uint64_t>(), nkeys));
+        MCG_TRY(copy_out(c, &total, d_start.as<uint64_t>() + nkeys, 8));
+        MCG_TRY(copy_out(c, h_flags, flags, 12));
+        MCG_CUDA(cudaStreamSynchronize(c->stream));
+        MCG_REQUIRE((h_flags[0] & 1u) == 0, "bucket larger than 255");
+        MCG_REQUIRE((h_flags[0] & 2u) == 0, "0xFFFFFFFF is not a valid feature");
+        MCG_REQUIRE(total == nlocs, "sizes do not add up to nlocs");
+        MCG_TRY(radix_sort_pairs(c, skeys, order, c->tmp1.as<uint32_t>(), c->tmp2.as<uint32_t>(), nkeys, 32, true));
+        imp_sizes_kernel<<<grid_for(nkeys), 256, 0, c->stream>>>(skeys, order, d_sizes.as<uint32_t>(), uint32_t(nkeys), uint32_t(db->maxlocs),
+                                                                db->sizes.as<uint8_t>(), flags);
+        c->launches++;
+        MCG_TRY(exclusive_scan_u8_to_u64(c, db->sizes.as<uint8_t>(), db->offs.as<uint64_t>(), nkeys));
+        MCG_TRY(copy_out(c, &lo, db->offs.as<uint64_t>() + nkeys, 8));
+        MCG_TRY(copy_out(c, h_flags, flags, 4));
+        MCG_CUDA(cudaStreamSynchronize(c->stream));
+        MCG_REQUIRE((h_flags[0] & 4u) == 0, "duplicate key in the imported buckets");
+    } else {
+        MCG_REQUIRE(nlocs == 0, "sizes do not add up to nlocs");
+        MCG_CUDA(cudaMemsetAsync(db->offs.p, 0, 16, c->stream));
     }
-    MCG_REQUIRE(start[nkeys] == nlocs, "sizes do not add up to nlocs");
-    std::vector<uint32_t> order(nkeys);
-    std::iota(order.begin(), order.end(), 0u);
-    if(!std::is_sorted(keys, keys + nkeys))
-        std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return keys[a] < keys[b]; });
-    std::vector<uint32_t> k(nkeys); std::vector<uint8_t> sz(nkeys); std::vector<uint64_t> of(nkeys + 1, 0), locs(nlocs);
-    uint64_t lo = 0, max_tgt = 0, max_win = 0;
-    for(uint64_t i = 0; i < nlocs; ++i) { max_tgt = std::max<uint64_t>(max_tgt, tgts[i]); max_win = std::max<uint64_t>(max_win, wins[i]); }
-    db->set_key_layout(max_tgt, max_win);
+    db->set_key_layout(h_flags[1], h_flags[2]);
     if(getenv("MCG_FORCE_KEY64")) { db->wbits = 32; db->key32 = false; }
-    for(uint64_t j = 0; j < nkeys; ++j) {
-        const uint32_t o = order[j];
-        if(j > 0) MCG_REQUIRE(keys[o] != k[j - 1], "duplicate key %u", keys[o]);
-        MCG_REQUIRE(keys[o] != EMPTY_KEY, "0xFFFFFFFF is not a valid feature");
-        k[j] = keys[o];
-        sz[j] = uint8_t(sizes[o] > uint32_t(db->maxlocs) ? uint32_t(db->maxlocs) : sizes[o]);   // sketch_database.h:361-364
-        of[j] = lo;
-        for(uint32_t t = 0; t < sz[j]; ++t) locs[lo++] = (uint64_t(tgts[start[o] + t]) << 32) | wins[start[o] + t];
-    }
-    of[nkeys] = lo;
     db->nkeys = nkeys;
     db->nlocs = lo;
-    MCG_TRY(db->keys.reserve((nkeys + 1) * 4)); MCG_TRY(db->sizes.reserve(nkeys + 16));
-    MCG_TRY(db->offs.reserve((nkeys + 2) * 8)); MCG_TRY(db->locs.reserve((lo + 2) * 8));
-    MCG_TRY(copy_in(c, db->keys.p, k.data(), nkeys * 4));
-    MCG_TRY(copy_in(c, db->sizes.p, sz.data(), nkeys));
-    MCG_TRY(copy_in(c, db->offs.p, of.data(), (nkeys + 1) * 8));
-    MCG_TRY(copy_in(c, db->locs.p, locs.data(), lo * 8));
+    MCG_TRY(db->locs.reserve((lo + 2) * 8));
+    if(nkeys > 0) {
+        imp_locs_kernel<<<grid_for(nkeys), 256, 0, c->stream>>>(order, d_start.as<uint64_t>(), db->sizes.as<uint8_t>(), db->offs.as<uint64_t>(),
+                                                               uint32_t(nkeys), d_tg.as<uint32_t>(), d_wn.as<uint32_t>(), db->locs.as<uint64_t>());
+        c->launches++;
+        MCG_CUDA(cudaGetLastError());
+    }
     MCG_TRY(build_table(db));
     MCG_CUDA(cudaStreamSynchronize(c->stream));
     db->finalized = true;
