@@ -20,6 +20,11 @@
 // FASTA/FASTQ reading, NCBI taxonomy files, text output.  They are written from the formats the
 // reference reads and writes, not from its code.
 #include <algorithm>
+#include <atomic>
+#include <fcntl.h>
+#include <memory>
+#include <sys/mman.h>
+#include <unistd.h>
 #include <charconv>
 #include <chrono>
 #include <cstdint>
@@ -487,22 +492,32 @@ void write_shard(const std::string& file, const DbMeta& m, const ShardData& d)
     wr<uint32_t>(os, m.ntargets);
     wr<uint64_t>(os, ne); wr<uint64_t>(os, nl);
     // per bucket: key u32, n u8, (n u64, n x tgt u32), (n u64, n x win u32)
-    std::string buf(size_t(ne) * 21 + size_t(nl) * 8, '\0');
-    char* q = &buf[0];
-    uint64_t lo = 0;
-    for(uint64_t j = 0; j < ne; ++j) {
-        const uint32_t key = d.keys[j];
-        const uint64_t n = d.sizes[j];
-        const uint8_t n8 = uint8_t(n);
-        std::memcpy(q, &key, 4); q += 4;
-        *q++ = char(n8);
-        std::memcpy(q, &n, 8); q += 8;
-        std::memcpy(q, &d.tg[lo], size_t(n) * 4); q += n * 4;
-        std::memcpy(q, &n, 8); q += 8;
-        std::memcpy(q, &d.wn[lo], size_t(n) * 4); q += n * 4;
-        lo += n;
+    // bucket j starts at byte 21 j + 8 start[j] of the bucket stream: the stream is filled by all host threads
+    std::vector<uint64_t> start(size_t(ne) + 1, 0);
+    for(uint64_t j = 0; j < ne; ++j) start[j + 1] = start[j] + d.sizes[j];
+    if(start[ne] != nl) die("internal error: bucket sizes of " + file + " do not add up");
+    std::unique_ptr<char[]> buf(new char[size_t(ne) * 21 + size_t(nl) * 8 + 1]);
+    const unsigned NT = host_threads();
+    {
+        std::vector<std::thread> th;
+        for(unsigned t = 0; t < NT; ++t) th.emplace_back([&, t] {
+            const uint64_t ja = ne * t / NT, jb = ne * (t + 1) / NT;
+            char* q = buf.get() + 21 * ja + 8 * start[ja];
+            for(uint64_t j = ja; j < jb; ++j) {
+                const uint32_t key = d.keys[j];
+                const uint64_t n = d.sizes[j], lo = start[j];
+                const uint8_t n8 = uint8_t(n);
+                std::memcpy(q, &key, 4); q += 4;
+                *q++ = char(n8);
+                std::memcpy(q, &n, 8); q += 8;
+                std::memcpy(q, &d.tg[lo], size_t(n) * 4); q += n * 4;
+                std::memcpy(q, &n, 8); q += 8;
+                std::memcpy(q, &d.wn[lo], size_t(n) * 4); q += n * 4;
+            }
+        });
+        for(auto& x : th) x.join();
     }
-    os.write(buf.data(), std::streamsize(q - buf.data()));
+    os.write(buf.get(), std::streamsize(size_t(ne) * 21 + size_t(nl) * 8));
     if(!os.good()) die("could not write " + file);
 }
 
@@ -510,10 +525,19 @@ void write_shard(const std::string& file, const DbMeta& m, const ShardData& d)
 void read_shard(const std::string& file, DbMeta& m, bool meta_only,
                 std::vector<uint32_t>& keys, std::vector<uint32_t>& sizes, std::vector<uint32_t>& tg, std::vector<uint32_t>& wn)
 {
-    std::string txt;
-    if(!read_text_file(file, txt)) die("can't open file " + file);
-    const char* p = txt.data();
-    const char* const end = p + txt.size();
+    // the file is mapped, not copied; the bucket stream is indexed by one thread and copied out by all
+    const int fd = ::open(file.c_str(), O_RDONLY);
+    if(fd < 0) die("can't open file " + file);
+    struct stat fst;
+    if(::fstat(fd, &fst) != 0 || fst.st_size <= 0) die("can't open file " + file);
+    const size_t fsize = size_t(fst.st_size);
+    void* mapping = ::mmap(nullptr, fsize, PROT_READ, MAP_PRIVATE, fd, 0);
+    ::close(fd);
+    if(mapping == MAP_FAILED) die("can't map file " + file);
+    struct Unmap { void* p; size_t n; ~Unmap() { ::munmap(p, n); } } unmap{mapping, fsize};
+    ::madvise(mapping, fsize, MADV_WILLNEED);
+    const char* p = static_cast<const char*>(mapping);
+    const char* const end = p + fsize;
     auto need = [&](size_t n) { if(size_t(end - p) < n) die("database " + file + " is truncated or corrupt"); };
     auto get = [&](auto& x) { need(sizeof(x)); std::memcpy(&x, p, sizeof(x)); p += sizeof(x); };
     auto get_str = [&](std::string& x) { uint64_t n = 0; get(n); need(size_t(n)); x.assign(p, size_t(n)); p += n; };
@@ -537,20 +561,60 @@ void read_shard(const std::string& file, DbMeta& m, bool meta_only,
     if(meta_only) return;
     uint64_t nk = 0, nv = 0; get(nk); get(nv);
     keys.resize(nk); sizes.resize(nk); tg.resize(nv); wn.resize(nv);
-    uint64_t lo = 0;
-    for(uint64_t j = 0; j < nk; ++j) {
-        uint8_t n8 = 0; get(keys[j]); get(n8);
-        sizes[j] = n8;
-        if(n8 > 0) {
-            uint64_t n = 0;
-            get(n); if(lo + n > nv) die("database " + file + " is truncated or corrupt");
-            need(size_t(n) * 4); std::memcpy(&tg[lo], p, size_t(n) * 4); p += n * 4;
-            get(n);
-            need(size_t(n) * 4); std::memcpy(&wn[lo], p, size_t(n) * 4); p += n * 4;
-            lo += n;
+    // pass 1 (one thread): only the size byte of every bucket is read; every CHUNK buckets the byte position
+    // and the location count so far are noted.  Pass 2 (all threads): chunks are parsed independently.
+    const uint64_t CHUNK = 1u << 16;
+    const uint64_t nchunks = (nk + CHUNK - 1) / CHUNK;
+    std::vector<const char*> cpos(size_t(nchunks) + 1);
+    std::vector<uint64_t> cloc(size_t(nchunks) + 1);
+    {
+        uint64_t lo = 0;
+        for(uint64_t j = 0; j < nk; ++j) {
+            if(j % CHUNK == 0) { cpos[j / CHUNK] = p; cloc[j / CHUNK] = lo; }
+            need(5);
+            const uint8_t n8 = uint8_t(p[4]);
+            p += 5;
+            if(n8 > 0) {
+                // both counts repeat the size byte (hash_multimap.h:975-1029); checked in pass 2
+                const size_t len = 16 + size_t(n8) * 8;
+                need(len);
+                p += len;
+                lo += n8;
+            }
         }
+        cpos[nchunks] = p; cloc[nchunks] = lo;
+        if(lo != nv) die("database " + file + " is truncated or corrupt");
     }
-    if(lo != nv) die("database " + file + " is truncated or corrupt");
+    {
+        const unsigned NT = host_threads();
+        std::atomic<bool> bad{false};
+        std::vector<std::thread> th;
+        for(unsigned t = 0; t < NT; ++t) th.emplace_back([&, t] {
+            for(uint64_t c = t; c < nchunks; c += NT) {
+                const char* q = cpos[c];
+                uint64_t lo = cloc[c];
+                const uint64_t jb = std::min(nk, (c + 1) * CHUNK);
+                for(uint64_t j = c * CHUNK; j < jb; ++j) {
+                    std::memcpy(&keys[j], q, 4);
+                    const uint8_t n8 = uint8_t(q[4]);
+                    q += 5;
+                    sizes[j] = n8;
+                    if(n8 > 0) {
+                        uint64_t n1 = 0, n2 = 0;
+                        std::memcpy(&n1, q, 8); q += 8;
+                        std::memcpy(&tg[lo], q, size_t(n8) * 4); q += size_t(n8) * 4;
+                        std::memcpy(&n2, q, 8); q += 8;
+                        std::memcpy(&wn[lo], q, size_t(n8) * 4); q += size_t(n8) * 4;
+                        if(n1 != n8 || n2 != n8) bad = true;
+                        lo += n8;
+                    }
+                }
+                if(q != cpos[c + 1] || lo != cloc[c + 1]) bad = true;
+            }
+        });
+        for(auto& x : th) x.join();
+        if(bad) die("database " + file + " is truncated or corrupt");
+    }
 }
 
 std::vector<mcg_ctx*> g_ctx;        // one per device
