@@ -19,6 +19,9 @@
 //   Reads it cannot hold (> 128 matches or > 32 * NC feature slots, i.e. long reads) take the
 //   staged path: find -> scan of list lengths -> read binning -> gather -> size-binned sorters
 //   (warp / CTA / big CTA / global-memory fallback) with the same window-range + top-list logic.
+//   When only a few reads are left over (< 1/8 of the batch) their windows and features are first
+//   compacted into a sub-batch of their own (q_left_*), so that the staged kernels, which run per
+//   feature slot of the batch they are given, do not pass over the whole batch.
 //   The host entry point mcg_query_batch cuts a batch into sub-batches and overlaps H2D, query and D2H.
 #include "common.cuh"
 
@@ -523,9 +526,9 @@ q_cand_warp_kernel(const CandParams p)
 // Short reads, fully fused: one warp probes the read's features, takes the locations out of the
 // 32-byte table slots themselves (lists of length <= 2) or gathers longer lists, sorts them in
 // registers / shared memory and derives the top list -- the match list never touches HBM.  Reads
-// with more than 128 feature slots or more than Q_FUSED matches are left to the staged path
-// (their features stay in `feat`; finished reads overwrite theirs with NO_FEATURE so that the
-// staged path skips them).
+// with more than 32 * NC feature slots or more than Q_FUSED matches are left to the staged path:
+// they are listed in `left_list` (few left: compacted sub-batch) and flagged in `done` (many left:
+// the features of the finished reads are overwritten with NO_FEATURE so that the staged path skips them).
 struct FusedParams {
     uint32_t* feat;
     const uint32_t* table;      // 128-byte buckets of 3 slots (common.cuh)
