@@ -376,7 +376,8 @@ def run_extras(args, ctx, api, synth, taxonomy, torch, dist, dev, stream, world,
                     "workload": "%d genomes x 5 Mbp sharded over %d GPU(s), host buffers -> finalized HBM multimap" % (QG, world),
                     "shard0_keys": int(nk), "shard0_locations": int(nl),
                     "roofline": {"bound": "hbm", "achieved": alg_build / bt / 1e9, "peak": peak, "unit": "GB/s",
-                                 "frac": alg_build / bt / 1e9 / peak, "traffic": None,
+                                 "frac": alg_build / bt / 1e9 / peak,
+                                 "traffic": (load_traffic().get("build_kernels_1gbp", {}).get("dram_bytes_per_bp") or 0) * len(buf) or None,
                                  "note": "wall time of mcg_db_add_targets + mcg_db_finalize incl. the H2D copy of the sequences from pinned host memory"}}
     # query
     npairs = 1_000_000
@@ -596,7 +597,10 @@ def run_extras(args, ctx, api, synth, taxonomy, torch, dist, dev, stream, world,
                     "classified": int(st[20]), "unclassified": int(st[21]),
                     "mean_locations_per_pair_shard0": mloc, "gpu_launches_per_batch": launches_q, "e2e": qe2e,
                     "roofline": {"bound": "hbm", "achieved": algq / (qms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                                 "frac": algq / (qms * 1e-3) / 1e9 / peak, "traffic": None}}
+                                 "frac": algq / (qms * 1e-3) / 1e9 / peak,
+                                 "traffic": (load_traffic().get("query_fused_kernel", {}).get("dram_bytes_per_pair") or 0) * npairs or None,
+                                 "note": "traffic: DRAM bytes of the fused kernel per batch from the committed ncu capture (1-GPU database); "
+                                         "a probe fills a 128-byte line for 64 useful bytes"}}
     # long reads (BASELINE.json configs[4] shape): 10 kbp reads, ~89 windows / ~1400 features per read, staged path
     try:
         nlong = 20_000
