@@ -107,12 +107,13 @@ struct mcg_db {
     // per-read match keys: (tgt << wbits) | win; 32-bit when target and window ids fit together
     int wbits = 32;
     bool key32 = false;
+    int kbits = 64;                   // significant bits of a match key (target bits + window bits)
     void set_key_layout(uint64_t max_tgt, uint64_t max_win)
     {
         int wb = 1, tb = 1;
         while((max_win >> wb) != 0) ++wb;
         while((max_tgt >> tb) != 0) ++tb;
-        if(wb + tb <= 32) { wbits = wb; key32 = true; } else { wbits = 32; key32 = false; }
+        if(wb + tb <= 32) { wbits = wb; key32 = true; kbits = wb + tb; } else { wbits = 32; key32 = false; kbits = 64; }
     }
 };
 
