@@ -1,5 +1,5 @@
-// scan.cu -- device-wide exclusive prefix sums (three-phase: tile scan, scan of
-// tile sums, add).  HBM-bound helper of the build and query paths.
+// scan.cu -- device-wide exclusive prefix sums (three-phase: tile sums, scan of
+// tile sums, tile scans with their base).  HBM-bound helper of the build and query paths.
 #include "common.cuh"
 
 namespace mcg {
@@ -60,6 +60,31 @@ tile_scan_kernel(const TIn* in, TOut* out, uint64_t n, TOut* tile_sum, const TOu
     if(tile_sum != nullptr && threadIdx.x == 0) tile_sum[blockIdx.x] = total;
 }
 
+// tile_sum[block] = sum of the tile (items beyond n count as 0): the first phase of a scan that
+// reads its input twice instead of writing, re-reading and re-writing its output
+template<class TIn, class TOut>
+__global__ void __launch_bounds__(SC_THREADS)
+tile_reduce_kernel(const TIn* in, uint64_t n, TOut* tile_sum)
+{
+    __shared__ TOut sh[SC_THREADS / 32];
+    const uint64_t base = uint64_t(blockIdx.x) * SC_TILE;
+    TOut s = 0;
+#pragma unroll 4
+    for(int i = 0; i < SC_ITEMS; ++i) {
+        const uint64_t idx = base + uint64_t(i) * SC_THREADS + threadIdx.x;      // coalesced
+        if(idx < n) s += TOut(in[idx]);
+    }
+#pragma unroll
+    for(int d = 16; d > 0; d >>= 1) s += __shfl_down_sync(0xFFFFFFFFu, s, d);
+    if((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if(threadIdx.x == 0) {
+        TOut t = 0;
+        for(int w = 0; w < SC_THREADS / 32; ++w) t += sh[w];
+        tile_sum[blockIdx.x] = t;
+    }
+}
+
 template<class T>
 __global__ void set_value_kernel(T* p, T v) { *p = v; }
 
@@ -90,11 +115,13 @@ static int scan_rec(mcg_ctx* c, const TIn* in, TOut* out, uint64_t n, TOut* lvl_
         c->launches++;
         return MCG_OK;
     }
+    // reduce -> scan of the tile sums -> tile scans with their base: the input is read twice, the output
+    // written once (tile scan + add-base pass: output written, re-read and re-written)
     TOut* sums = lvl_mem;                  // [nb]
-    tile_scan_kernel<TIn, TOut><<<unsigned(nb), SC_THREADS, 0, c->stream>>>(in, out, n, sums, nullptr);
+    tile_reduce_kernel<TIn, TOut><<<unsigned(nb), SC_THREADS, 0, c->stream>>>(in, n, sums);
     c->launches++;
     MCG_TRY((scan_rec<TOut, TOut>(c, sums, sums, nb, lvl_mem + nb, d_total)));
-    add_base_kernel<TOut><<<unsigned(nb), SC_THREADS, 0, c->stream>>>(out, n, sums);
+    tile_scan_kernel<TIn, TOut><<<unsigned(nb), SC_THREADS, 0, c->stream>>>(in, out, n, nullptr, sums);
     c->launches++;
     return MCG_OK;
 }
