@@ -88,18 +88,6 @@ tile_reduce_kernel(const TIn* in, uint64_t n, TOut* tile_sum)
 template<class T>
 __global__ void set_value_kernel(T* p, T v) { *p = v; }
 
-template<class T>
-__global__ void __launch_bounds__(SC_THREADS)
-add_base_kernel(T* data, uint64_t n, const T* base)
-{
-    const uint64_t b0 = uint64_t(blockIdx.x) * SC_TILE;
-    const T add = base[blockIdx.x];
-    for(int i = threadIdx.x; i < SC_TILE; i += SC_THREADS) {
-        const uint64_t idx = b0 + i;
-        if(idx < n) data[idx] += add;
-    }
-}
-
 // exclusive scan of `in` (n items) -> out (n items); returns grand total in *d_total (device)
 template<class TIn, class TOut>
 static int scan_rec(mcg_ctx* c, const TIn* in, TOut* out, uint64_t n, TOut* lvl_mem, TOut* d_total)
