@@ -1197,6 +1197,76 @@ int mode_query(const Args& a)
     return 0;
 }
 
+// ------------------------------------------------------------------------------- host-only self tests
+// (no CUDA call: they run in the CPU test suite)
+
+// selftest-shard <file> <nkeys>: pseudo-random buckets -> write_shard -> read_shard -> compare
+int mode_selftest_shard(const Args& a)
+{
+    if(a.pos.size() < 2) die("usage: metacache_b200 selftest-shard <file> <nkeys>");
+    const uint64_t nk = uint64_t(std::atoll(a.pos[1].c_str()));
+    DbMeta m;
+    m.ntargets = 3;
+    for(int t = 0; t < 3; ++t) {
+        Taxon x; x.id = -t - 1; x.parent = 100 + t; x.rank = 0; x.name = "SEQ" + std::to_string(t); x.file = "dir/g" + std::to_string(t) + ".fna";
+        x.index = 0; x.windows = 1000 + uint64_t(t);
+        m.tax.taxa[x.id] = x;
+    }
+    { Taxon x; x.id = 1; x.parent = 1; x.rank = 20; x.name = "root"; m.tax.taxa[1] = x; }
+    ShardData d;
+    uint64_t st = 88172645463325252ull;
+    auto rnd = [&] { st ^= st << 13; st ^= st >> 7; st ^= st << 17; return st; };
+    d.keys.resize(nk); d.sizes.resize(nk);
+    for(uint64_t j = 0; j < nk; ++j) {
+        d.keys[j] = uint32_t(j * 7919u + 13u);
+        const uint64_t r = rnd() % 100;
+        d.sizes[j] = r < 70 ? 1 : (r < 90 ? 2 : (r < 99 ? uint32_t(3 + rnd() % 20) : 254));
+        d.nl += d.sizes[j];
+    }
+    d.ne = nk;
+    d.tg.resize(d.nl); d.wn.resize(d.nl);
+    for(uint64_t i = 0; i < d.nl; ++i) { d.tg[i] = uint32_t(rnd() % 3); d.wn[i] = uint32_t(rnd() % 1000); }
+    write_shard(a.pos[0], m, d);
+    DbMeta m2;
+    std::vector<uint32_t> k2, s2, t2, w2;
+    read_shard(a.pos[0], m2, false, k2, s2, t2, w2);
+    bool ok = k2 == d.keys && s2 == d.sizes && t2 == d.tg && w2 == d.wn && m2.ntargets == 3 && m2.tax.taxa.size() == 4 &&
+              m2.tax.taxa[-2].file == "dir/g1.fna" && m2.tax.taxa[-3].windows == 1002 && m2.maxlocs == m.maxlocs &&
+              m2.tcfg.k == 16 && m2.qstride == 113;
+    std::cout << (ok ? "selftest-shard ok" : "selftest-shard MISMATCH") << ": " << nk << " keys, " << d.nl << " locations" << std::endl;
+    return ok ? 0 : 1;
+}
+
+// selftest-abundance <taxonomy dir> <rank> <taxid:count> ...: the two tables of -abundances / -abundance-per
+int mode_selftest_abundance(const Args& a)
+{
+    if(a.pos.size() < 3) die("usage: metacache_b200 selftest-abundance <taxonomy dir> <rank> <taxid:count> ...");
+    Taxonomy tax;
+    tax.load(a.pos[0]);
+    TaxTables tt;
+    tt.build(tax, 0);
+    const int rank = rank_from_name(a.pos[1]);
+    TaxCountMap all;
+    uint64_t total = 0;
+    for(size_t i = 2; i < a.pos.size(); ++i) {
+        const size_t c = a.pos[i].find(':');
+        if(c == std::string::npos) die("expected taxid:count");
+        const int64_t id = std::atoll(a.pos[i].substr(0, c).c_str());
+        const uint64_t n = uint64_t(std::atoll(a.pos[i].substr(c + 1).c_str()));
+        auto it = tt.index_of.find(id);
+        if(it == tt.index_of.end()) die("unknown taxon " + std::to_string(id));
+        all[tt.tax[size_t(it->second)]] = float(n);
+        total += n;
+    }
+    if(a.has({"total"})) total = uint64_t(a.geti({"total"}, 0));
+    std::cout << "# query summary: number of queries mapped per taxon\n";
+    show_abundance_table(std::cout, all, total, ":", "\t|\t");
+    estimate_abundance(tt, all, rank);
+    std::cout << "# estimated abundance (number of queries) per " << RANK_NAMES[rank] << "\n";
+    show_abundance_table(std::cout, all, total, ":", "\t|\t");
+    return 0;
+}
+
 }  // namespace
 
 int main(int argc, char** argv)
@@ -1211,6 +1281,8 @@ int main(int argc, char** argv)
     int rc = 1;
     if(mode == "build") rc = mode_build(a);
     else if(mode == "query") rc = mode_query(a);
+    else if(mode == "selftest-shard") return mode_selftest_shard(a);
+    else if(mode == "selftest-abundance") return mode_selftest_abundance(a);
     else die("unknown mode '" + mode + "' (build and query are implemented, like in the reference: README.md:37)");
     wait_gpu_init();
     total("whole run before teardown");

@@ -17,6 +17,10 @@ CASES = {
     "cli_np2_species_maxcand4.txt": t.QFLAGS,
     "cli_np2_abundances.txt": ["-pairfiles", "-lowest", "species", "-maxcand", "4", "-hitmin", "4", "-hitdiff", "30",
                                "-abundances", "-abundance-per", "species"],
+    "cli_np2_abundance_per_genus.txt": ["-pairfiles", "-lowest", "species", "-maxcand", "4", "-hitmin", "4", "-hitdiff", "30",
+                                        "-highest", "family", "-abundances", "-abundance-per", "genus"],
+    "cli_np2_abundance_two_levels.txt": ["-pairfiles", "-lowest", "species", "-maxcand", "8", "-hitmin", "2", "-hitdiff", "3",
+                                         "-abundances", "-abundance-per", "species"],
     "cli_np2_hits_per_seq.txt": ["-pairfiles", "-lowest", "species", "-maxcand", "4", "-hitmin", "4", "-hitdiff", "80", "-hits-per-seq"],
 }
 
