@@ -155,6 +155,28 @@ def test_query_window_overrides(ctx, oracle):
         assert (mn == en).all() and (mt == et).all() and (mh == eh).all() and (best == eb).all() and (stats == es).all()
 
 
+@pytest.mark.parametrize("k,s,wl,st,maxlocs", [(12, 32, 256, 241, 10), (16, 8, 64, 49, 254), (9, 16, 128, 120, 3)])
+def test_nondefault_database_parameters(ctx, oracle, k, s, wl, st, maxlocs):
+    """databases built with other k / sketchlen / window parameters and a small location cap, queried with the
+    database's own parameters (mode_build.cpp:93-138): wide-sketch K1, 2 and 4 feature slots per lane in the
+    fused kernel, short k-mers (many chance hits, long lists, capping)"""
+    w = World(G=8, L=30000, npairs=300, seed=13)
+    ctx.upload_taxonomy(w.tabs.lineage, w.tabs.rank, w.G)
+    kw = dict(k=k, sketchlen=s, winlen=wl, maxlocs=maxlocs)
+    od = w.oracle_shards(oracle, 2, stride=st, **kw)
+    gd = w.gpu_shards(api, ctx, 2, winstride=st, **kw)
+    from test_gpu_build import _same
+    for r in range(2):
+        _same(gd[r].export(), od[r].export())
+    q = api.make_query_opts(sketchlen=s, winlen=wl, winstride=st, maxcand=4, lowest=4, hitmin=2, hitdiff=0.8)
+    oq = po.make_qopt(sketchlen=s, winlen=wl, stride=st, maxcand=4, lowest=4, hitmin=2, hitdiff=0.8)
+    ct, ch, cn, mt, mh, mn, best, brank, stats = _gpu_full(ctx, gd, q, w.b1, w.o1, w.b2, w.o2)
+    ot, oh, on = _oracle_local(od, w.tax, oq, w.b1, w.o1, w.b2, w.o2, 4)
+    assert (cn == on).all() and (ct == ot).all() and (ch == oh).all()
+    et, eh, en, eb, er, es = oracle.query_batch(od, w.tax, oq, w.b1, w.o1, w.b2, w.o2)
+    assert (mn == en).all() and (mt == et).all() and (mh == eh).all() and (best == eb).all() and (stats == es).all()
+
+
 def test_host_path_sub_batches(tmp_path):
     """mcg_query_batch cuts a batch into pipelined sub-batches (MCG_QUERY_SUB reads each): the
     results must not depend on the cut.  Own processes: the knob is read once per process."""
