@@ -176,8 +176,10 @@ def run_reference(args):
         "impl": "reference", "metric": "sketch_bp_per_s", "value": val, "unit": "bp/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / len(times),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-        "config": {"workload": "sketching-only: synthetic reference genomes, k=16 sketchlen=16 winlen=128 winstride=113",
-                   "sample": "%d Mbp per step (bounded sample of the 1 Gbp workload)" % (bp // 1_000_000)},
+        "config": {"workload": "sketching-only: %d Mbp of synthetic reference genomes per GPU (%d x 5 Mbp), k=16 sketchlen=16 "
+                               "winlen=128 winstride=113 (BASELINE.json configs[1])" % (args.mbp, max(args.mbp // 5, 1)),
+                   "sample": "%d Mbp per step: the first %d genomes of that workload (bounded sample, same generator and seeds)"
+                             % (bp // 1_000_000, G)},
         "cpu_baseline": {"value": val, "unit": "bp/s", "cores": cores, "kind": kind,
                          "sample": "%d genomes x 5 Mbp, %d threads over sequences, hash_dna.h sketcher" % (G, cores)},
         "e2e": {"value": val, "unit": "bp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
