@@ -596,7 +596,7 @@ q_cand_warp_kernel(const CandParams p)
 // Short reads, fully fused: one warp probes the read's features, takes the locations out of the
 // 32-byte table slots themselves (lists of length <= 2) or gathers longer lists, sorts them in
 // registers / shared memory and derives the top list -- the match list never touches HBM.  Reads
-// with more than 32 * NC feature slots or more than Q_FUSED matches are left to the staged path:
+// with more than 32 * NC feature slots or more than CAP matches are left to the staged path:
 // they are listed in `left_list` (few left: compacted sub-batch) and flagged in `done` (many left:
 // the features of the finished reads are overwritten with NO_FEATURE so that the staged path skips them).
 struct FusedParams {
@@ -610,7 +610,7 @@ struct FusedParams {
     uint32_t* left_list;        // the reads left over, in no particular order
 };
 
-constexpr int Q_FUSED = 128;
+constexpr int Q_FUSED = 128;      // default; databases with long lists (nlocs > 2.1 nkeys) use 256
 constexpr uint32_t Q_LANE_GATHER = 12;   // lists up to this length are copied by their own lane    // matches per read of the fused path (small: shared memory is taken from L1, which the probes need)
 
 // candidates.h:236-285 with the taxon already lifted to -lowest and its rank known (seq = the
@@ -726,18 +726,18 @@ __global__ void q_hide_done_kernel(uint32_t* feat, const uint32_t* W, int s, con
     for(uint64_t i = s0 + lane; i < s1; i += 32) feat[i] = EMPTY_KEY;
 }
 
-template<class KeyT, int NC>           // NC: feature slots per lane (reads with more than 32*NC slots are left over)
+template<class KeyT, int NC, int CAP>  // NC: feature slots per lane (reads with more than 32*NC slots are left over); CAP: matches per read
 __global__ void __launch_bounds__(256)
 q_fused_warp_kernel(const CandParams p, const FusedParams f)
 {
     extern __shared__ __align__(16) unsigned char sm[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // per warp: A[Q_FUSED] keys, Hh[Q_FUSED], Ct[Q_FUSED], Ch[Q_FUSED]
-    unsigned char* wbase = sm + size_t(warp) * Q_FUSED * (sizeof(KeyT) + 12);
+    // per warp: A[CAP] keys, Hh[CAP], Ct[CAP], Ch[CAP]
+    unsigned char* wbase = sm + size_t(warp) * CAP * (sizeof(KeyT) + 12);
     KeyT* A = reinterpret_cast<KeyT*>(wbase);
-    uint32_t* Hh = reinterpret_cast<uint32_t*>(wbase + size_t(Q_FUSED) * sizeof(KeyT));
-    int32_t* Ct = reinterpret_cast<int32_t*>(Hh + Q_FUSED);
-    uint32_t* Ch = reinterpret_cast<uint32_t*>(Ct + Q_FUSED);
+    uint32_t* Hh = reinterpret_cast<uint32_t*>(wbase + size_t(CAP) * sizeof(KeyT));
+    int32_t* Ct = reinterpret_cast<int32_t*>(Hh + CAP);
+    uint32_t* Ch = reinterpret_cast<uint32_t*>(Ct + CAP);
     const KeyT KMAX = ~KeyT(0);
     // reads are handed out 8 at a time by an atomic counter (their cost varies with their matches)
     for(int64_t rr = 0;; ++rr) {
@@ -814,7 +814,7 @@ q_fused_warp_kernel(const CandParams p, const FusedParams f)
             if(lane >= d) inc += o;
         }
         const uint32_t m = __shfl_sync(0xFFFFFFFFu, inc, 31);
-        if(m > Q_FUSED) {
+        if(m > uint32_t(CAP)) {
             if(lane == 0) { f.left_list[atomicAdd(f.left_over, 1u)] = uint32_t(r); f.done[r] = 0; }
             continue;
         }
@@ -1249,12 +1249,17 @@ int query_batch_dev(mcg_db* db, const mcg_query_opts* o,
         const bool nc2 = run.nslots <= uint64_t(n) * 64;
         unsigned g = 1;
         int per_sm = 1;
+        // matches per read: 128 unless the lists of this database are long (a read pair of 64 features then gathers
+        // more than 128 locations as a rule and the staged path would take over the batch)
+        static const int cap_env = getenv("MCG_FUSED_CAP") ? atoi(getenv("MCG_FUSED_CAP")) : 0;
+        const bool cap256 = cap_env ? cap_env >= 256 : (double(db->nlocs) > 2.1 * double(db->nkeys));
         // shared memory comes out of L1, which the probes live on: ask for no more than the 5 CTAs need
-        const int carve = 38;
-#define QF_LAUNCH(KT, NC)                                                                                            \
+        const int carve = cap256 ? 70 : 38;
+#define QF_LAUNCH(KT, NC) do { if(cap256) QF_LAUNCH_CAP(KT, NC, 256); else QF_LAUNCH_CAP(KT, NC, Q_FUSED); } while(0)
+#define QF_LAUNCH_CAP(KT, NC, CAP)                                                                                   \
     do {                                                                                                             \
-        auto kern = q_fused_warp_kernel<KT, NC>;                                                                     \
-        const int smem = 8 * Q_FUSED * (int(sizeof(KT)) + 12);                                                       \
+        auto kern = q_fused_warp_kernel<KT, NC, CAP>;                                                                \
+        const int smem = 8 * CAP * (int(sizeof(KT)) + 12);                                                           \
         MCG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));                     \
         if(carve >= 0) MCG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve));    \
         MCG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem));                           \
@@ -1264,6 +1269,7 @@ int query_batch_dev(mcg_db* db, const mcg_query_opts* o,
         if(db->key32) { if(nc2) QF_LAUNCH(uint32_t, 2); else QF_LAUNCH(uint32_t, 4); }
         else          { if(nc2) QF_LAUNCH(uint64_t, 2); else QF_LAUNCH(uint64_t, 4); }
 #undef QF_LAUNCH
+#undef QF_LAUNCH_CAP
         c->launches++;
         uint32_t h_left = 0;
         MCG_CUDA(cudaMemcpyAsync(&h_left, left, 4, cudaMemcpyDeviceToHost, c->stream));
