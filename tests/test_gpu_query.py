@@ -9,6 +9,9 @@ from util import World
 
 pytestmark = pytest.mark.gpu
 
+import os as _os
+ROOT_DIR = _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__)))
+
 CONFIGS = [  # maxcand, lowest, hitmin, hitdiff
     (4, 4, 4, 0.8),      # the authors' script settings: -lowest species -maxcand 4 -hitmin 4 -hitdiff 80
     (2, 0, 5, 1.0),      # reference defaults
@@ -212,3 +215,38 @@ def test_host_path_sub_batches(tmp_path):
     for k in ("ct", "ch", "cn", "st", "sh", "sn"):
         assert (outs[0][k] == outs[1][k]).all(), k
     assert (outs[0]["cn"] > 0).sum() > 900
+
+
+def test_fused_kernel_variants_agree(tmp_path):
+    """the per-read top lists must not depend on which path a read takes: fused kernel holding 128 matches,
+    holding 256 (databases with long lists), no fusion at all (staged path for every read), left-over reads
+    not compacted.  40 genomes sharing a block put reads into every class.  Own processes: the knobs are
+    read once per process."""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import sys, numpy as np\n"
+        "sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "from __graft_entry__ import load_package; load_package()\n"
+        "from metacache_mpi_b200 import api\n"
+        "from util import World\n"
+        "ctx = api.Context(0)\n"
+        "w = World(G=40, L=12000, npairs=1500, seed=11)\n"
+        "ctx.upload_taxonomy(w.tabs.lineage, w.tabs.rank, w.G)\n"
+        "db = w.gpu_shards(api, ctx, 1)[0]\n"
+        "q = api.make_query_opts(maxcand=4, lowest=4, hitmin=4, hitdiff=0.8)\n"
+        "ct, ch, cn = db.query_batch(q, w.b1, w.o1, w.b2, w.o2)\n"
+        "np.savez(sys.argv[1], ct=ct, ch=ch, cn=cn)\n"
+    ) % (ROOT_DIR, os.path.join(ROOT_DIR, "tests"))
+    outs = []
+    for i, env in enumerate(({"MCG_FUSED_CAP": "128"}, {"MCG_FUSED_CAP": "256"}, {"MCG_QUERY_NO_FUSION": "1"},
+                             {"MCG_FUSED_CAP": "128", "MCG_QUERY_NO_COMPACT": "1"})):
+        f = str(tmp_path / ("v%d.npz" % i))
+        r = subprocess.run([sys.executable, "-c", code, f], env=dict(os.environ, **env), capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append(np.load(f))
+    for o in outs[1:]:
+        for k in ("ct", "ch", "cn"):
+            assert (outs[0][k] == o[k]).all(), k
+    assert (outs[0]["cn"] > 0).sum() > 1400
