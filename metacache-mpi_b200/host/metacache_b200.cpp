@@ -11,6 +11,10 @@
 //       [-mapped-only|-nomap] [-no-summary] [-no-query-params] [-abundances [file]] [-abundance-per rank]
 //       [-hits-per-seq [file]]                                            (query_options.cpp)
 //
+// `-threads T` and `-query-limit n` are accepted and have no effect: in the reference they only set the size of the
+// blocks its workers take (querying.h:764-765, 1321); every read is classified either way (checked with the reference:
+// `-threads 2 -query-limit 100` on 300 pairs prints 300 lines).
+//
 // `-gpus P` replaces `mpirun -np P`: the database has P shards (shard = target_id % P,
 // sketch_database.h:540), shard r is written to / read from `<db>.db_<r>` in the reference's own
 // binary format (sketch_database.h:858-999, hash_multimap.h:923-1029) and lives on GPU
