@@ -41,7 +41,9 @@ extern "C" {
 #define MCG_RANK_NONE 21
 #define MCG_MAX_K 16          /* kmer_type = uint32_t, config.h:44-48 */
 #define MCG_MAX_SKETCH 32     /* device bottom-s network width */
-#define MCG_MAX_CAND 16       /* top-list width (std::sort stability bound, candidates.h:270) */
+#define MCG_MAX_CAND 32       /* top-list width: one list entry per lane of a warp.  Beyond 16 entries the reference's
+                               * std::sort (candidates.h:270) leaves the order of equal-hit taxa unspecified; here it
+                               * stays stable. */
 #define MCG_MAX_LOCS 254      /* sketch_database.h:375-378 */
 
 typedef enum {
@@ -71,12 +73,17 @@ typedef struct {
     int32_t sketchlen;        /* query sketch size (default: database's) */
     int64_t winlen;           /* query window size */
     int64_t winstride;
-    int32_t maxcand;          /* -maxcand 1..MCG_MAX_CAND */
+    int32_t maxcand;          /* -maxcand 1..MCG_MAX_CAND (the host driver maps "unlimited", i.e. < 1, to MCG_MAX_CAND) */
     int32_t lowest;           /* -lowest  (rank index) */
     int32_t highest;          /* -highest (rank index) */
     int32_t hitmin;           /* -hitmin  (already defaulted, mode_query.cpp:247) */
     float   hitdiff;          /* -hitdiff as a fraction (query_options.cpp:167-169) */
     int64_t insertsize;       /* -insertsize */
+    int32_t reference_compat; /* 0: every shard's candidates take part in the cross-shard merge (restated semantics).
+                               * 1: reproduce the reference's merge bit for bit, including its defect Q1: candidate taxon
+                               *    ids travel as uint32 (querying.h:984,1001) and are widened unsigned on receipt
+                               *    (:958), so sequence-level taxa (ids -(tgt)-1) of every rank but the receiver itself
+                               *    are dropped -- along the reduction tree of querying.h:892-1066, P a power of two */
 } mcg_query_opts;
 
 /* ---------------------------------------------------------------- context */

@@ -33,7 +33,8 @@ class SketchCfg(C.Structure):
 class QueryOpts(C.Structure):
     _fields_ = [("sketchlen", C.c_int32), ("winlen", C.c_int64), ("winstride", C.c_int64),
                 ("maxcand", C.c_int32), ("lowest", C.c_int32), ("highest", C.c_int32),
-                ("hitmin", C.c_int32), ("hitdiff", C.c_float), ("insertsize", C.c_int64)]
+                ("hitmin", C.c_int32), ("hitdiff", C.c_float), ("insertsize", C.c_int64),
+                ("reference_compat", C.c_int32)]
 
 
 def declared_symbols():
@@ -108,9 +109,9 @@ def _u8(a):
 
 
 def make_query_opts(sketchlen=16, winlen=128, winstride=113, maxcand=2, lowest=0, highest=19,
-                    hitmin=5, hitdiff=1.0, insertsize=0):
+                    hitmin=5, hitdiff=1.0, insertsize=0, reference_compat=0):
     return QueryOpts(sketchlen, winlen, winstride, maxcand, lowest, highest, hitmin,
-                     float(np.float32(hitdiff)), insertsize)
+                     float(np.float32(hitdiff)), insertsize, reference_compat)
 
 
 def default_hitmin(sketchlen):

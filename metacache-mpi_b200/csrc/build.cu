@@ -438,11 +438,8 @@ static int build_table(mcg_db* db)
     MCG_TRY(db->table.reserve(cap * 128));
     db->table_cap = cap;
     if(nkeys > 0) {
-        static bool configured = false;
-        if(!configured) {
-            MCG_CUDA(cudaFuncSetAttribute(table_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TBL_CH * 128));
-            configured = true;
-        }
+        // (function attributes are per device: set on every call, not once per process)
+        MCG_CUDA(cudaFuncSetAttribute(table_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TBL_CH * 128));
         table_build_kernel<<<ntiles, TB_THREADS, TBL_CH * 128, c->stream>>>(db->table.as<uint4>(), db->keys.as<uint32_t>(), db->sizes.as<uint8_t>(),
                                                                           db->offs.as<uint64_t>(), db->locs.as<uint64_t>(), uint32_t(nkeys), g,
                                                                           c->tmp5.as<int64_t>(), cap, ntiles);
@@ -529,6 +526,7 @@ int db_finalize(mcg_db* db)
     MCG_TRY(build_table(db));
     MCG_CUDA(cudaStreamSynchronize(c->stream));
     TRACE("table");
+    trim_cached_device_memory(size_t(1) << 30);      // the sort scratch does not stay parked
     {
         uint64_t maxwin = 0;
         for(size_t t = 0; t + 1 < db->h_tgt_firstwin.size(); ++t) maxwin = std::max<uint64_t>(maxwin, db->h_tgt_firstwin[t + 1] - db->h_tgt_firstwin[t]);
@@ -547,7 +545,7 @@ int db_counts(mcg_db* db, uint64_t* nkeys, uint64_t* nonempty, uint64_t* nlocs)
     if(db->nkeys > 0) {
         MCG_TRY(c->tmp3.reserve(64));
         MCG_CUDA(cudaMemsetAsync(c->tmp3.p, 0, 16, c->stream));
-        count_sizes_kernel<<<kNumSMs * 4, 256, 0, c->stream>>>(db->sizes.as<uint8_t>(), uint32_t(db->nkeys),
+        count_sizes_kernel<<<c->num_sms * 4, 256, 0, c->stream>>>(db->sizes.as<uint8_t>(), uint32_t(db->nkeys),
                                                               c->tmp3.as<unsigned long long>());
         c->launches++;
         MCG_CUDA(cudaMemcpyAsync(h, c->tmp3.p, 16, cudaMemcpyDeviceToHost, c->stream));

@@ -72,6 +72,27 @@ cudaError_t cached_malloc(void** p, size_t bytes, size_t* cap)
 
 void release_cached_device_memory() { cache_flush(); }
 
+// frees parked blocks of the current device, largest first, until at most keep_bytes stay parked:
+// multi-GB scratch (the sort buffers of finalize) must not sit in the cache while other allocators of
+// the process (torch, NCCL) run out of memory
+void trim_cached_device_memory(size_t keep_bytes)
+{
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lk(g_cache_mtx);
+    size_t total = 0;
+    for(const Block& b : g_cache) if(b.dev == dev) total += b.cap;
+    while(total > keep_bytes) {
+        int big = -1;
+        for(size_t i = 0; i < g_cache.size(); ++i)
+            if(g_cache[i].dev == dev && (big < 0 || g_cache[i].cap > g_cache[size_t(big)].cap)) big = int(i);
+        if(big < 0) break;
+        total -= g_cache[size_t(big)].cap;
+        cudaFree(g_cache[size_t(big)].p);
+        g_cache.erase(g_cache.begin() + big);
+    }
+}
+
 int DevBuf::reserve(size_t bytes)
 {
     if(bytes <= cap && p != nullptr) return MCG_OK;
@@ -188,6 +209,7 @@ int mcg_ctx_create(int device, void* stream, mcg_ctx** out)
     }
     mcg_ctx* c = new mcg_ctx;
     c->device = device;
+    c->num_sms = prop.multiProcessorCount;
     if(stream != nullptr) {
         c->stream = static_cast<cudaStream_t>(stream);
         c->own_stream = false;
@@ -208,7 +230,7 @@ int mcg_ctx_destroy(mcg_ctx* c)
                       &c->tmp2, &c->tmp3, &c->tmp4, &c->tmp5, &c->scan_tmp, &c->q_feat, &c->q_flen, &c->q_foff,
                       &c->q_fpos, &c->q_loc, &c->q_rinfo, &c->q_cls, &c->q_out_tax, &c->q_out_hits, &c->q_out_n, &c->q_done,
                       &c->m_tax, &c->m_hits, &c->m_n, &c->m_o_tax, &c->m_o_hits, &c->m_o_n, &c->m_best,
-                      &c->m_brank, &c->m_stats, &c->tilectr};
+                      &c->m_brank, &c->m_stats, &c->m_bad, &c->tilectr};
     for(DevBuf* b : bufs) b->release();
     if(c->pinned != nullptr) cudaFreeHost(c->pinned);
     if(c->s_h2d) cudaStreamDestroy(c->s_h2d);

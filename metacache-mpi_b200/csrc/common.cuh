@@ -40,7 +40,6 @@ void set_error(const char* fmt, ...);
         }                                                                           \
     } while(0)
 
-constexpr int kNumSMs = 148;          // B200: 2 dies x 74 SMs
 
 // ------------------------------------------------------------------ device memory
 // grow-only device buffer (cudaMalloc is synchronising; buffers are reused across calls)
@@ -54,6 +53,7 @@ struct DevBuf {
 };
 
 void release_cached_device_memory();
+void trim_cached_device_memory(size_t keep_bytes);
 
 // parameters of the feature table's bucket function (see "feature table" below)
 struct TableGeom {
@@ -66,6 +66,7 @@ struct TableGeom {
 // ------------------------------------------------------------------ context / db
 struct mcg_ctx {
     int device = 0;
+    int num_sms = 148;                // multiProcessorCount of the device (B200: 2 dies x 74 SMs): persistent grids are sized from it
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     int64_t launches = 0;
@@ -75,7 +76,8 @@ struct mcg_ctx {
     // scratch
     mcg::DevBuf seq, seqoff, winfirst, outfirst, tmp0, tmp1, tmp2, tmp3, tmp4, tmp5, scan_tmp, tilectr;
     mcg::DevBuf q_feat, q_flen, q_foff, q_fpos, q_loc, q_rinfo, q_cls, q_out_tax, q_out_hits, q_out_n, q_done;
-    mcg::DevBuf m_tax, m_hits, m_n, m_o_tax, m_o_hits, m_o_n, m_best, m_brank, m_stats;
+    mcg::DevBuf m_tax, m_hits, m_n, m_o_tax, m_o_hits, m_o_n, m_best, m_brank, m_stats, m_bad;
+    bool m_bad_clear = false;         // m_bad (flags of the merge kernel's input checks) is zero
     void* pinned = nullptr;           // small pinned staging area for scalars
     size_t pinned_cap = 0;
     // copy streams + events of the pipelined host entry points
@@ -104,12 +106,15 @@ struct mcg_db {
     uint32_t table_scale = 0;
     mcg::TableGeom geom() const { mcg::TableGeom g; g.cdf = cdf.as<uint32_t>(); g.scale = table_scale; return g; }
     uint64_t nkeys = 0, nlocs = 0, table_cap = 0;
+    uint64_t max_tgt = 0;             // largest target id stored in the shard (checked against the taxonomy at query time)
     // per-read match keys: (tgt << wbits) | win; 32-bit when target and window ids fit together
     int wbits = 32;
     bool key32 = false;
     int kbits = 64;                   // significant bits of a match key (target bits + window bits)
-    void set_key_layout(uint64_t max_tgt, uint64_t max_win)
+    void set_key_layout(uint64_t max_tgt_, uint64_t max_win)
     {
+        const uint64_t max_tgt = max_tgt_;
+        this->max_tgt = max_tgt_;
         int wb = 1, tb = 1;
         while((max_win >> wb) != 0) ++wb;
         while((max_tgt >> tb) != 0) ++tb;

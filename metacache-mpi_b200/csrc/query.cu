@@ -952,6 +952,8 @@ struct MergeParams {
     int K;
     int lowest, highest, hitmin;
     float hitdiff;
+    int compat;                  // reproduce quirk Q1 along the reference's reduction tree
+    int32_t ntaxa, ntargets;
     const int32_t* lineage;
     const uint8_t* rank;
     int32_t* out_tax;
@@ -960,7 +962,34 @@ struct MergeParams {
     int32_t* out_best;
     int32_t* out_brank;
     unsigned long long* stats;
+    uint32_t* bad;               // set when a candidate taxon lies outside [-1, ntaxa)
 };
+
+// inserts the entries of `src` into `dst` in list order (querying.h:944-971); with `drop_seq` the
+// entries whose taxon is a target's own sequence-level taxon are skipped: their ids are negative
+// (sketch_database.h:150), travel as uint32 (querying.h:984,1001) and no longer name a taxon once
+// widened on the receiving rank (:958) -- quirk Q1
+__device__ __forceinline__ void merge_lists(TopK& dst, const TopK& src, const MergeParams& p, bool drop_seq)
+{
+    for(int c = 0; c < src.n; ++c) {
+        if(drop_seq && src.tax[c] < p.ntargets) continue;
+        topk_insert(dst, p.K, src.tax[c], src.hits[c], p.lowest, p.lineage, p.rank);
+    }
+}
+
+__device__ __forceinline__ void load_list(TopK& L, const MergeParams& p, int q, int64_t r)
+{
+    const int64_t row = int64_t(q) * p.n + r;
+    int cnt = p.cand_n[row];
+    if(cnt < 0 || cnt > p.K) { atomicOr(p.bad, 2u); cnt = cnt < 0 ? 0 : p.K; }
+    L.n = 0;
+    for(int c = 0; c < cnt; ++c) {
+        const int32_t t = p.cand_tax[row * p.K + c];
+        if(t < 0 || t >= p.ntaxa) { if(t != -1) atomicOr(p.bad, 1u); continue; }
+        // a per-shard list is a valid top list already: re-inserting it (querying.h:910-940) reproduces it
+        topk_insert(L, p.K, t, p.cand_hits[row * p.K + c], p.lowest, p.lineage, p.rank);
+    }
+}
 
 __global__ void __launch_bounds__(128)
 q_merge_classify_kernel(const MergeParams p)
@@ -972,11 +1001,44 @@ q_merge_classify_kernel(const MergeParams p)
     if(r < p.n) {
         TopK L;
         L.n = 0;
-        for(int q = 0; q < p.P; ++q) {                       // rank order (querying.h:905-971)
-            const int64_t row = int64_t(q) * p.n + r;
-            const int cnt = p.cand_n[row];
-            for(int c = 0; c < cnt; ++c)
-                topk_insert(L, p.K, p.cand_tax[row * p.K + c], p.cand_hits[row * p.K + c], p.lowest, p.lineage, p.rank);
+        if(!p.compat) {
+            for(int q = 0; q < p.P; ++q) {                   // rank order (querying.h:905-971)
+                const int64_t row = int64_t(q) * p.n + r;
+                int cnt = p.cand_n[row];
+                if(cnt < 0 || cnt > p.K) { atomicOr(p.bad, 2u); cnt = cnt < 0 ? 0 : p.K; }
+                for(int c = 0; c < cnt; ++c) {
+                    const int32_t t = p.cand_tax[row * p.K + c];
+                    if(t < 0 || t >= p.ntaxa) { if(t != -1) atomicOr(p.bad, 1u); continue; }
+                    topk_insert(L, p.K, t, p.cand_hits[row * p.K + c], p.lowest, p.lineage, p.rank);
+                }
+            }
+        } else if((p.P & (p.P - 1)) == 0) {
+            // the reduction tree of querying.h:892-1066 for P = 2^d: round 1 pairs (1->0), (3->2), ...,
+            // round 2 (2->0), (6->4), ...: a receiver keeps its own list whole and takes from the
+            // sender's (already merged and truncated) list only what survives the uint32 round trip.
+            // Evaluated like a binary counter over the ranks in order; the stack never holds more
+            // than log2(P) + 1 lists.
+            TopK st[7];
+            int lvl[7];
+            int sp = 0;
+            for(int q = 0; q < p.P; ++q) {
+                load_list(st[sp], p, q, r);
+                lvl[sp] = 0;
+                ++sp;
+                while(sp >= 2 && lvl[sp - 1] == lvl[sp - 2]) {
+                    merge_lists(st[sp - 2], st[sp - 1], p, true);
+                    ++lvl[sp - 2];
+                    --sp;
+                }
+            }
+            L = st[0];
+        } else {
+            // no reduction tree exists for other P in the reference (quirk Q12): rank order, rank 0 whole
+            TopK S;
+            for(int q = 0; q < p.P; ++q) {
+                load_list(S, p, q, r);
+                merge_lists(L, S, p, q > 0);
+            }
         }
         for(int c = 0; c < p.K; ++c) {
             p.out_tax[r * p.K + c] = c < L.n ? L.tax[c] : -1;
@@ -1032,7 +1094,12 @@ static int check_opts(const mcg_db* db, const mcg_query_opts* o)
     MCG_REQUIRE(o->winlen >= 1 && o->winstride >= 1, "query window length / stride must be >= 1");
     MCG_REQUIRE(o->maxcand >= 1 && o->maxcand <= MCG_MAX_CAND, "maxcand %d outside 1..%d (unlimited lists are not supported on the device)", o->maxcand, MCG_MAX_CAND);
     MCG_REQUIRE(o->lowest >= 0 && o->lowest < MCG_NUM_RANKS && o->highest >= 0 && o->highest < MCG_NUM_RANKS, "rank out of range");
-    (void)db;
+    MCG_REQUIRE(o->hitmin >= 0, "hitmin %d is negative", o->hitmin);
+    MCG_REQUIRE(o->insertsize >= 0, "insertsize %lld is negative", (long long)o->insertsize);
+    // every target id stored in the shard indexes the taxonomy tables (lineage[tgt], rank[tgt])
+    if(db != nullptr && db->nlocs > 0)
+        MCG_REQUIRE(int64_t(db->max_tgt) < db->ctx->ntargets, "shard holds target id %llu but the uploaded taxonomy has %lld targets",
+                    (unsigned long long)db->max_tgt, (long long)db->ctx->ntargets);
     return MCG_OK;
 }
 
@@ -1167,33 +1234,27 @@ static int query_back(mcg_db* db, const mcg_query_opts* o, const int64_t* doffs1
     p.rmap = run.rmap;
     const bool k32 = db->key32;
     const int ksz = k32 ? 4 : 8;
-    static bool configured = false;
-    if(!configured) {
-        MCG_CUDA(cudaFuncSetAttribute(q_cand_warp_kernel<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * Q_SMALL * 20));
-        MCG_CUDA(cudaFuncSetAttribute(q_cand_warp_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * Q_SMALL * 16));
-        MCG_CUDA(cudaFuncSetAttribute(q_cand_cta_kernel<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, Q_LARGE * 12));
-        MCG_CUDA(cudaFuncSetAttribute(q_cand_cta_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, Q_LARGE * 8 + 16 * 1024));
-        configured = true;
-    }
+    // function attributes are per DEVICE (one process may drive several GPUs): set before every launch
+#define QC_SMEM(kern, bytes) MCG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes)))
     if(run.cls[0] > 0) {
         p.list = lists; p.list_count = counters;
-        const unsigned g = unsigned(std::min<uint64_t>((run.cls[0] + 7) / 8, uint64_t(kNumSMs) * 16));
-        if(k32) q_cand_warp_kernel<uint32_t><<<g, 256, 8 * Q_SMALL * (ksz + 12), c->stream>>>(p);
-        else    q_cand_warp_kernel<uint64_t><<<g, 256, 8 * Q_SMALL * (ksz + 12), c->stream>>>(p);
+        const unsigned g = unsigned(std::min<uint64_t>((run.cls[0] + 7) / 8, uint64_t(c->num_sms) * 16));
+        if(k32) { QC_SMEM(q_cand_warp_kernel<uint32_t>, 8 * Q_SMALL * 16); q_cand_warp_kernel<uint32_t><<<g, 256, 8 * Q_SMALL * (ksz + 12), c->stream>>>(p); }
+        else    { QC_SMEM(q_cand_warp_kernel<uint64_t>, 8 * Q_SMALL * 20); q_cand_warp_kernel<uint64_t><<<g, 256, 8 * Q_SMALL * (ksz + 12), c->stream>>>(p); }
         c->launches++;
     }
     if(run.cls[1] > 0) {
         p.list = lists + uint64_t(n); p.list_count = counters + 1;
-        const unsigned g = unsigned(std::min<uint64_t>(run.cls[1], uint64_t(kNumSMs) * 8));
-        if(k32) q_cand_cta_kernel<uint32_t><<<g, 256, Q_MED * (ksz + 4) + 8 * 1024, c->stream>>>(p, Q_MED);        // + digit counters of the radix sort
-        else    q_cand_cta_kernel<uint64_t><<<g, 256, Q_MED * (ksz + 4), c->stream>>>(p, Q_MED);
+        const unsigned g = unsigned(std::min<uint64_t>(run.cls[1], uint64_t(c->num_sms) * 8));
+        if(k32) { QC_SMEM(q_cand_cta_kernel<uint32_t>, Q_LARGE * 8 + 16 * 1024); q_cand_cta_kernel<uint32_t><<<g, 256, Q_MED * (ksz + 4) + 8 * 1024, c->stream>>>(p, Q_MED); }        // + digit counters of the radix sort
+        else    { QC_SMEM(q_cand_cta_kernel<uint64_t>, Q_LARGE * 12); q_cand_cta_kernel<uint64_t><<<g, 256, Q_MED * (ksz + 4), c->stream>>>(p, Q_MED); }
         c->launches++;
     }
     if(run.cls[2] > 0) {
         p.list = lists + uint64_t(2) * n; p.list_count = counters + 2;
-        const unsigned g = unsigned(std::min<uint64_t>(run.cls[2], uint64_t(kNumSMs) * 2));
-        if(k32) q_cand_cta_kernel<uint32_t><<<g, 512, Q_LARGE * (ksz + 4) + 16 * 1024, c->stream>>>(p, Q_LARGE);
-        else    q_cand_cta_kernel<uint64_t><<<g, 512, Q_LARGE * (ksz + 4), c->stream>>>(p, Q_LARGE);
+        const unsigned g = unsigned(std::min<uint64_t>(run.cls[2], uint64_t(c->num_sms) * 2));
+        if(k32) { QC_SMEM(q_cand_cta_kernel<uint32_t>, Q_LARGE * 8 + 16 * 1024); q_cand_cta_kernel<uint32_t><<<g, 512, Q_LARGE * (ksz + 4) + 16 * 1024, c->stream>>>(p, Q_LARGE); }
+        else    { QC_SMEM(q_cand_cta_kernel<uint64_t>, Q_LARGE * 12); q_cand_cta_kernel<uint64_t><<<g, 512, Q_LARGE * (ksz + 4), c->stream>>>(p, Q_LARGE); }
         c->launches++;
     }
     if(run.cls[3] > 0) {
@@ -1201,11 +1262,12 @@ static int query_back(mcg_db* db, const mcg_query_opts* o, const int64_t* doffs1
         p.hits_scratch = c->tmp4.as<uint32_t>();
         p.hits_scratch2 = c->tmp4.as<uint32_t>() + run.total + 2;
         p.list = lists + uint64_t(3) * n; p.list_count = counters + 3;
-        const unsigned g = unsigned(std::min<uint64_t>(run.cls[3], uint64_t(kNumSMs) * 2));
+        const unsigned g = unsigned(std::min<uint64_t>(run.cls[3], uint64_t(c->num_sms) * 2));
         if(k32) q_cand_global_kernel<uint32_t><<<g, 1024, 0, c->stream>>>(p);
         else    q_cand_global_kernel<uint64_t><<<g, 1024, 0, c->stream>>>(p);
         c->launches++;
     }
+#undef QC_SMEM
     MCG_CUDA(cudaGetLastError());
     return MCG_OK;
 }
@@ -1263,7 +1325,7 @@ int query_batch_dev(mcg_db* db, const mcg_query_opts* o,
         MCG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));                     \
         if(carve >= 0) MCG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve));    \
         MCG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem));                           \
-        g = unsigned(std::min<uint64_t>(uint64_t(n + 63) / 64, uint64_t(kNumSMs) * uint64_t(std::max(1, per_sm)))); \
+        g = unsigned(std::min<uint64_t>(uint64_t(n + 63) / 64, uint64_t(c->num_sms) * uint64_t(std::max(1, per_sm)))); \
         kern<<<g, 256, smem, c->stream>>>(p, f);                                                                     \
     } while(0)
         if(db->key32) { if(nc2) QF_LAUNCH(uint32_t, 2); else QF_LAUNCH(uint32_t, 4); }
@@ -1517,10 +1579,15 @@ int mcg_merge_classify_dev(mcg_ctx* c, const mcg_query_opts* o,
     MCG_REQUIRE(nshards >= 1 && n >= 0, "bad shard / read count");
     MCG_REQUIRE(o->maxcand >= 1 && o->maxcand <= MCG_MAX_CAND, "maxcand %d outside 1..%d", o->maxcand, MCG_MAX_CAND);
     MCG_REQUIRE(o->lowest >= 0 && o->lowest < MCG_NUM_RANKS && o->highest >= 0 && o->highest < MCG_NUM_RANKS, "rank out of range");
+    MCG_REQUIRE(o->hitmin >= 0, "hitmin %d is negative", o->hitmin);
+    MCG_REQUIRE(!o->reference_compat || nshards <= 64, "reference-compatible merge supports up to 64 shards");
     if(c->lineage.p == nullptr) { set_error("taxonomy not uploaded (mcg_tax_upload)"); return MCG_ERR_STATE; }
     if(n == 0) return MCG_OK;
     MCG_CUDA(cudaSetDevice(c->device));
+    MCG_TRY(c->m_bad.reserve(64));
+    if(!c->m_bad_clear) { MCG_CUDA(cudaMemsetAsync(c->m_bad.p, 0, 4, c->stream)); c->m_bad_clear = true; }
     MergeParams p;
+    p.compat = o->reference_compat; p.ntaxa = int32_t(c->ntaxa); p.ntargets = int32_t(c->ntargets); p.bad = c->m_bad.as<uint32_t>();
     p.cand_tax = d_cand_tax; p.cand_hits = d_cand_hits; p.cand_n = d_cand_n;
     p.P = nshards; p.n = n; p.K = o->maxcand;
     p.lowest = o->lowest; p.highest = o->highest; p.hitmin = o->hitmin; p.hitdiff = o->hitdiff;
@@ -1562,8 +1629,15 @@ int mcg_merge_classify(mcg_ctx* c, const mcg_query_opts* o,
     if(out_best) MCG_TRY(copy_out(c, out_best, c->m_best.p, size_t(n) * 4));
     if(out_best_rank) MCG_TRY(copy_out(c, out_best_rank, c->m_brank.p, size_t(n) * 4));
     uint64_t st[22];
+    uint32_t bad = 0;
     MCG_TRY(copy_out(c, st, c->m_stats.p, 22 * 8));
+    MCG_TRY(copy_out(c, &bad, c->m_bad.p, 4));
     MCG_CUDA(cudaStreamSynchronize(c->stream));
+    if(bad != 0) {
+        c->m_bad_clear = false;
+        set_error("mcg_merge_classify: %s", (bad & 1u) ? "candidate taxon outside [-1, ntaxa)" : "candidate count outside [0, maxcand]");
+        return MCG_ERR_ARG;
+    }
     if(out_stats22) for(int i = 0; i < 22; ++i) out_stats22[i] += st[i];
     return MCG_OK;
 }

@@ -181,13 +181,10 @@ int radix_sort_pairs(mcg_ctx* c, uint32_t* keys, uint32_t* vals, uint32_t* keys_
 {
     if(n == 0) return MCG_OK;
     MCG_REQUIRE(n < (1ull << 32), "radix_sort_pairs: more than 2^32-1 elements");
-    static int threads = 0;
-    if(threads == 0) {
-        const char* e = getenv("MCG_RS_THREADS");
-        threads = (e && atoi(e) == 512) ? 512 : 256;
-        MCG_CUDA(cudaFuncSetAttribute(rs_scatter_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (2 * 256 * RS_ROUNDS + 8 * 256) * 4));
-        MCG_CUDA(cudaFuncSetAttribute(rs_scatter_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (2 * 512 * RS_ROUNDS + 16 * 256) * 4));
-    }
+    static const int threads = [] { const char* e = getenv("MCG_RS_THREADS"); return (e && atoi(e) == 512) ? 512 : 256; }();
+    // function attributes are per device: set on every call
+    if(threads == 256) MCG_CUDA(cudaFuncSetAttribute(rs_scatter_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (2 * 256 * RS_ROUNDS + 8 * 256) * 4));
+    else               MCG_CUDA(cudaFuncSetAttribute(rs_scatter_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (2 * 512 * RS_ROUNDS + 16 * 256) * 4));
     const int tile = threads * RS_ROUNDS;
     const size_t smem = size_t(2 * tile + (threads / 32) * 256) * 4;
     const uint32_t ntiles = uint32_t((n + tile - 1) / tile);

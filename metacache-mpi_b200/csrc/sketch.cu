@@ -557,7 +557,7 @@ int sketch_launch(mcg_ctx* c, const mcg_sketch_cfg& cfg, int sketchlen, int64_t 
         int per_sm = 1;                                                                                           \
         MCG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, SK_THREADS, smem));                 \
         if(per_sm < 1) per_sm = 1;                                                                                \
-        const uint64_t grid = std::min<uint64_t>((nblocks + SK_WARPS - 1) / SK_WARPS, uint64_t(kNumSMs) * uint64_t(per_sm));                   \
+        const uint64_t grid = std::min<uint64_t>((nblocks + SK_WARPS - 1) / SK_WARPS, uint64_t(c->num_sms) * uint64_t(per_sm));                   \
         kern<<<unsigned(grid), SK_THREADS, smem, stream>>>(p);                                                 \
     } while(0)
     if(cfg.k == 16 && p.pitch == SK_PITCH_DEFAULT) SK_LAUNCH(true, SK_PITCH_DEFAULT);

@@ -525,7 +525,7 @@ int tpw_launch(mcg_ctx* c, SketchParams& p, const mcg_sketch_cfg& cfg, uint64_t 
         int per_sm = 1;                                                                                             \
         MCG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TW_THREADS, smem));                   \
         if(per_sm < 1) per_sm = 1;                                                                                  \
-        const uint64_t grid = std::min<uint64_t>((nblocks + TW_WARPS - 1) / TW_WARPS, uint64_t(kNumSMs) * uint64_t(per_sm)); \
+        const uint64_t grid = std::min<uint64_t>((nblocks + TW_WARPS - 1) / TW_WARPS, uint64_t(c->num_sms) * uint64_t(per_sm)); \
         kern<<<unsigned(grid), TW_THREADS, smem, stream>>>(p);                                                      \
     } while(0)
     if(rounds == 2) {

@@ -9,7 +9,7 @@
 //       [-hitmin n] [-hitdiff f] [-maxcand n] [-insertsize n] [-winlen n] [-winstride n]
 //       [-sketchlen n] [-out file] [-tophits] [-queryids] [-taxids|-taxids-only] [-lineage]
 //       [-mapped-only|-nomap] [-no-summary] [-no-query-params] [-abundances [file]] [-abundance-per rank]
-//       [-hits-per-seq [file]]                                            (query_options.cpp)
+//       [-hits-per-seq [file]] [-reference-compat]                       (query_options.cpp)
 //
 // `-threads T` and `-query-limit n` are accepted and have no effect: in the reference they only set the size of the
 // blocks its workers take (querying.h:764-765, 1321); every read is classified either way (checked with the reference:
@@ -37,6 +37,7 @@
 #include <cstring>
 #include <fstream>
 #include <iostream>
+#include <limits>
 #include <map>
 #include <set>
 #include <sstream>
@@ -120,7 +121,7 @@ Args parse_args(int argc, char** argv, int first)
                     "pairfiles", "pair-files", "pairseq", "tophits", "top-hits", "queryids", "query-ids", "taxids",
                     "taxid", "taxids-only", "taxidsonly", "lineage", "mapped-only", "mappedonly", "nomap", "no-map",
                     "no-summary", "nosummary", "no-query-params", "noqueryparams", "remove-overpopulated-features",
-                    "silent", "verbose", "omit-ranks", "separate-cols"};
+                    "silent", "verbose", "omit-ranks", "separate-cols", "reference-compat", "reference_compat", "refcompat"};
                 if(flags.count(name)) val.clear(); else ++i;
             }
             a.opt[name] = val;
@@ -959,7 +960,16 @@ int mode_query(const Args& a)
         q.hitdiff = f;
     }
     q.maxcand = int32_t(a.geti({"max-cand", "maxcand", "max_cand", "max-candidates", "maxcandidates"}, 2));
-    if(q.maxcand < 1 || q.maxcand > MCG_MAX_CAND) die("-maxcand must be 1.." + std::to_string(MCG_MAX_CAND) + " on the device");
+    const int maxcand_shown = q.maxcand;
+    if(q.maxcand < 1 || q.maxcand > MCG_MAX_CAND) {
+        // query_options.cpp:176-178: < 1 means "unlimited"; the device keeps MCG_MAX_CAND (one list entry per lane)
+        std::cerr << "metacache_b200: -maxcand " << q.maxcand << (q.maxcand < 1 ? " (unlimited)" : "") << " is limited to "
+                  << MCG_MAX_CAND << " candidates per query on the device\n";
+        q.maxcand = MCG_MAX_CAND;
+    }
+    // -reference-compat: the cross-shard merge drops what the reference's uint32 wire format loses (quirk Q1,
+    // querying.h:958,984,1001): with the default -lowest sequence only shard 0's candidates survive
+    q.reference_compat = a.has({"reference-compat", "reference_compat", "refcompat"}) ? 1 : 0;
     if(q.hitmin < 1) {                                                          // mode_query.cpp:247-260
         const int sks = m0.tcfg.sketchlen;
         q.hitmin = sks >= 6 ? int(sks / 3.0) : (sks >= 4 ? 2 : 1);
@@ -1027,7 +1037,9 @@ int mode_query(const Args& a)
         }
         os << cm << "Classification will be constrained to ranks from '" << RANK_NAMES[q.lowest] << "' to '" << RANK_NAMES[q.highest] << "'.\n";
         os << cm << "Classification hit threshold is " << q.hitmin << " per query\n";
-        os << cm << "At maximum " << q.maxcand << " classification candidates will be considered per query.\n";
+        os << cm << "At maximum ";
+        if(maxcand_shown < 1) os << std::numeric_limits<std::size_t>::max(); else os << maxcand_shown;      // query_options.cpp:176-178
+        os << " classification candidates will be considered per query.\n";
         if(paired) {
             os << cm << "File based paired-end mode:\n" << cm << "  Reads from two consecutive files will be interleaved.\n"
                << cm << "  Max insert size considered " << q.insertsize << ".\n";

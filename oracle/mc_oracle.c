@@ -573,6 +573,55 @@ int mco_merge_classify(const mco_tax* tx, const mco_qopt* o,
     return n;
 }
 
+/* The same with the reference's wire format reproduced: taxon ids travel as
+ * uint32 (querying.h:984,1001) and are widened unsigned on receipt (:958), so a sequence-level taxon
+ * (id -(tgt)-1, dense index < ntargets here) received from another rank names no taxon and is dropped
+ * (candidates.h:240).  Lists move along the reduction tree of querying.h:892-1066 (P a power of two):
+ * round 1 (1->0), (3->2), ...; round 2 (2->0), (6->4), ...; a receiver keeps its own list whole
+ * (:910-940), a sender ships its merged, truncated list (:994-1009).  in_n[r] = length of rank r's list. */
+static void compat_reduce(const mco_tax* tx, const mco_qopt* o, candlist* lists, int lo, int hi)
+{
+    /* result of ranks [lo, hi) ends in lists[lo] */
+    if(hi - lo <= 1) return;
+    const int mid = lo + (hi - lo) / 2;
+    compat_reduce(tx, o, lists, lo, mid);
+    compat_reduce(tx, o, lists, mid, hi);
+    for(int c = 0; c < lists[mid].n; ++c) {
+        if((int64_t)lists[mid].c[c].tax < tx->ntargets) continue;          /* negative id: lost on the wire */
+        cand_insert(&lists[lo], tx, lists[mid].c[c].tax, lists[mid].c[c].hits, eff_maxcand(o->maxcand), o->lowest);
+    }
+}
+
+int mco_merge_classify_compat(const mco_tax* tx, const mco_qopt* o, int P,
+                              const int32_t* in_tax, const uint32_t* in_hits, const int* in_n,
+                              int32_t* out_tax, uint32_t* out_hits, int cap,
+                              int32_t* best_tax, int* best_rank)
+{
+    candlist* lists = (candlist*)calloc((size_t)P, sizeof(candlist));
+    int at = 0;
+    for(int r = 0; r < P; ++r) {
+        for(int c = 0; c < in_n[r]; ++c) cand_insert(&lists[r], tx, in_tax[at + c], in_hits[at + c], eff_maxcand(o->maxcand), o->lowest);
+        at += in_n[r];
+    }
+    if((P & (P - 1)) == 0) compat_reduce(tx, o, lists, 0, P);
+    else                                                    /* no tree exists in the reference (Q12): rank order */
+        for(int r = 1; r < P; ++r)
+            for(int c = 0; c < lists[r].n; ++c) {
+                if((int64_t)lists[r].c[c].tax < tx->ntargets) continue;
+                cand_insert(&lists[0], tx, lists[r].c[c].tax, lists[r].c[c].hits, eff_maxcand(o->maxcand), o->lowest);
+            }
+    /* decision on the merged list: same code as mco_merge_classify (re-inserting a valid list reproduces it) */
+    int nin = lists[0].n;
+    int32_t* t = (int32_t*)malloc((size_t)(nin > 0 ? nin : 1) * sizeof(int32_t));
+    uint32_t* h = (uint32_t*)malloc((size_t)(nin > 0 ? nin : 1) * sizeof(uint32_t));
+    for(int c = 0; c < nin; ++c) { t[c] = lists[0].c[c].tax; h[c] = lists[0].c[c].hits; }
+    const int n = mco_merge_classify(tx, o, t, h, nin, out_tax, out_hits, cap, best_tax, best_rank);
+    free(t); free(h);
+    for(int r = 0; r < P; ++r) free(lists[r].c);
+    free(lists);
+    return n;
+}
+
 /* classification_statistics.h:70-78 assign */
 void mco_statistics(const int* ranks, int64_t n, uint64_t* out22)
 {
@@ -599,10 +648,16 @@ void mco_query_batch(mco_db* const* shards, int P, const mco_tax* tx, const mco_
         const char* s2 = buf2 ? buf2 + offs2[q] : "";
         const int64_t n2 = buf2 ? offs2[q + 1] - offs2[q] : 0;
         int nin = 0;
-        for(int r = 0; r < P; ++r)
-            nin += mco_query_local(shards[r], tx, o, s1, n1, s2, n2, lt + nin, lh + nin, K);
+        int per_rank[256];
+        for(int r = 0; r < P; ++r) {
+            const int c = mco_query_local(shards[r], tx, o, s1, n1, s2, n2, lt + nin, lh + nin, K);
+            if(r < 256) per_rank[r] = c;
+            nin += c;
+        }
         int32_t best; int brank;
-        const int n = mco_merge_classify(tx, o, lt, lh, nin, out_tax + q * K, out_hits + q * K, K, &best, &brank);
+        const int n = (o->reference_compat && P <= 256)
+                    ? mco_merge_classify_compat(tx, o, P, lt, lh, per_rank, out_tax + q * K, out_hits + q * K, K, &best, &brank)
+                    : mco_merge_classify(tx, o, lt, lh, nin, out_tax + q * K, out_hits + q * K, K, &best, &brank);
         for(int c = n; c < K; ++c) { out_tax[q * K + c] = -1; out_hits[q * K + c] = 0; }
         out_ncand[q] = n;
         out_best[q] = best;

@@ -61,7 +61,8 @@ def concat(seqs):
 class QOpt(C.Structure):
     _fields_ = [("sketchlen", C.c_int), ("winlen", C.c_int64), ("stride", C.c_int64),
                 ("maxcand", C.c_int), ("lowest", C.c_int), ("highest", C.c_int),
-                ("hitmin", C.c_int), ("hitdiff", C.c_float), ("insertsize", C.c_int64)]
+                ("hitmin", C.c_int), ("hitdiff", C.c_float), ("insertsize", C.c_int64),
+                ("reference_compat", C.c_int)]
 
 
 class Tax(C.Structure):
@@ -70,9 +71,9 @@ class Tax(C.Structure):
 
 
 def make_qopt(sketchlen=16, winlen=128, stride=113, maxcand=2, lowest=0, highest=19,
-              hitmin=5, hitdiff=1.0, insertsize=0):
+              hitmin=5, hitdiff=1.0, insertsize=0, reference_compat=0):
     return QOpt(sketchlen, winlen, stride, maxcand, lowest, highest, hitmin,
-                float(np.float32(hitdiff)), insertsize)
+                float(np.float32(hitdiff)), insertsize, reference_compat)
 
 
 class Oracle:

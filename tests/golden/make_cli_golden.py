@@ -24,8 +24,27 @@ CASES = {
     "cli_np2_hits_per_seq.txt": ["-pairfiles", "-lowest", "species", "-maxcand", "4", "-hitmin", "4", "-hitdiff", "80", "-hits-per-seq"],
 }
 
+# the reference's DEFAULT flags (-lowest sequence, -maxcand 2, hitmin 5, hitdiff 1.0): at np >= 2 its uint32 wire format
+# loses the sequence-level taxa of every rank but the receiver; np = 4 adds the reduction tree.
+# "mixed": genomes 1 and 4 carry no taxid, so at -lowest species their candidates stay sequence-level while the others are lifted.
+COMPAT_CASES = {
+    ("cli_np2_default_flags.txt", 2, False): ["-pairfiles", "-tophits", "-queryids"],
+    ("cli_np4_default_flags.txt", 4, False): ["-pairfiles", "-tophits", "-queryids"],
+    ("cli_np4_mixed_lowest_species.txt", 4, True): t.QFLAGS,
+    ("cli_np2_mixed_lowest_species.txt", 2, True): t.QFLAGS,
+}
+
 if __name__ == "__main__":
     assert os.path.exists(t.REF), "build the reference first: make -C oracle"
+    for (name, np_, mixed), flags in COMPAT_CASES.items():
+        with tempfile.TemporaryDirectory() as d:
+            t.make_files(d, no_taxid=(1, 4) if mixed else ())
+            t.run([sys.executable, t.SHIM, "-np", str(np_), "--", t.REF, "build", "rdb", "genomes", "-taxonomy", "tax"], d)
+            t.run([sys.executable, t.SHIM, "-np", str(np_), "--", t.REF, "query", "rdb", "r1.fq", "r2.fq"] + flags +
+                  ["-threads", "1", "-query-limit", "300", "-out", "res.txt"], d)
+            with open(os.path.join(ROOT, "tests", "golden", name), "w") as f:
+                f.write("\n".join(t.stable_lines(os.path.join(d, "res.txt"))) + "\n")
+            print("wrote", name)
     with tempfile.TemporaryDirectory() as d:
         t.make_files(d)
         t.run([sys.executable, t.SHIM, "-np", "2", "--", t.REF, "build", "rdb", "genomes", "-taxonomy", "tax"], d)

@@ -25,10 +25,13 @@ GOLDEN = os.path.join(ROOT, "tests", "golden", "cli_np2_species_maxcand4.txt")
 QFLAGS = ["-pairfiles", "-lowest", "species", "-maxcand", "4", "-hitmin", "4", "-hitdiff", "80", "-tophits", "-queryids"]
 
 
-def make_files(d):
+def make_files(d, no_taxid=()):
     G, L = 6, 30000
     genomes = synth.make_genomes(G, L)
     ids, par, rk, species = synth.make_taxonomy(G)
+    species = species.copy()
+    for g in no_taxid:                 # header without a usable taxid: the target hangs below no species
+        species[g] = 0
     synth.write_genome_files(os.path.join(d, "genomes"), genomes, species)
     synth.write_taxonomy_files(os.path.join(d, "tax"), ids, par, rk)
     b1, o1, b2, o2, t = synth.make_read_pairs(genomes, 300, seed=5)
