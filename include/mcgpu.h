@@ -15,8 +15,12 @@
  *     database shard (= reference MPI rank, shard = target_id % nshards).
  *     Calls on one ctx / db are not re-entrant.
  *   - "host" entry points take caller-owned host buffers (pinned memory is
- *     detected and copied asynchronously); "_dev" entry points take device
- *     pointers and never synchronise (they enqueue on the ctx stream).
+ *     detected and copied asynchronously) and return when the results are
+ *     there; "_dev" entry points take device pointers and enqueue on the ctx
+ *     stream.  Sketching, build-side kernels and the merge never wait for the
+ *     device; the query "_dev" calls wait once, for one 4-byte count (how many
+ *     reads the fused kernel left to the staged path), and -- only when that
+ *     count is not zero -- for the sizes the staged path allocates from.
  *   - sequences: one byte buffer + offsets[n+1] (int64).  Sketches:
  *     uint32[nwin][sketchlen], ascending, padded with MCG_NO_FEATURE.
  *   - taxa are dense indices: index t < ntargets is the sequence-level taxon
@@ -86,6 +90,9 @@ typedef struct {
                                *    are dropped -- along the reduction tree of querying.h:892-1066, P a power of two */
 } mcg_query_opts;
 
+typedef struct mcg_comm mcg_comm;
+#define MCG_COMM_ID_BYTES 128
+
 /* ---------------------------------------------------------------- context */
 const char* mcg_last_error(void);
 int  mcg_version(void);
@@ -154,6 +161,28 @@ int  mcg_db_remove_keys(mcg_db*, const uint32_t* keys, uint64_t n, uint64_t* rem
  * for shards living in this process (single-process multi-GPU or tests) */
 int  mcg_remove_overpopulated(mcg_db** shards, int32_t nshards, uint64_t* removed);
 
+/* same as mcg_db_key_sizes with device output arrays (sized by mcg_db_counts: nkeys_nonempty) */
+int  mcg_db_key_sizes_dev(mcg_db*, uint32_t* d_keys, uint32_t* d_sizes);
+
+/* ---------------------------------------------------------- communicator */
+/* One rank = one GPU = one mcg_ctx; ranks are processes (torchrun / mpirun) or threads of one process.
+ * Replaces MPI_Init / MPI_COMM_WORLD of main.cpp:41 for this path: NCCL over NVLink / NVSwitch.
+ * mcg_comm_get_id on one rank, the 128 bytes travel to the others by whatever the launcher offers
+ * (torch.distributed store, MPI_Bcast, shared memory of the process), then every rank calls
+ * mcg_comm_create at the same time (collective). */
+int  mcg_comm_get_id(uint8_t* id /* [MCG_COMM_ID_BYTES] */);
+int  mcg_comm_create(mcg_ctx*, const uint8_t* id, int32_t rank, int32_t nranks, mcg_comm** out);
+int  mcg_comm_destroy(mcg_comm*);
+int  mcg_comm_rank(const mcg_comm*);
+int  mcg_comm_size(const mcg_comm*);
+
+/* the -remove-overpopulated-features reduction across ranks (mode_build.cpp:847-1074: tree reduce of
+ * (key, bucket size) pairs to rank 0, MPI_Bcast of the removal list, sketch_database.h:398-417 clear):
+ * (key, size) pairs go to rank key % P (all-to-all), the owner sums them, keys whose summed size exceeds
+ * maxlocs - 1 are all-gathered and cleared on every rank.  Collective over the communicator; the shard
+ * must be finalized.  removed_here: buckets cleared in this shard; removal_list_len: keys removed overall. */
+int  mcg_db_remove_overpopulated_dist(mcg_db*, mcg_comm*, uint64_t* removed_here, uint64_t* removal_list_len);
+
 /* -------------------------------------------------------------- taxonomy */
 /* flattened ranked_lineages_cache (taxonomy.h:702-806, :576-597) */
 int  mcg_tax_upload(mcg_ctx*, const int32_t* lineage, const uint8_t* rank,
@@ -176,7 +205,7 @@ int  mcg_query_batch(mcg_db*, const mcg_query_opts*,
 int  mcg_query_batch_dev(mcg_db*, const mcg_query_opts*,
                          const char* d_reads1, const int64_t* d_offs1, int64_t bytes1,
                          const char* d_reads2, const int64_t* d_offs2, int64_t bytes2,
-                         int64_t n, int64_t max_read_len,
+                         int64_t n, int64_t max_read_len /* 0 = unknown: tightens the scratch bounds only */,
                          int32_t* d_out_tax, uint32_t* d_out_hits, int32_t* d_out_ncand);
 /* debugging / parity seam: the sorted match list of every read
  * (querying.h:798-811); out arrays sized by a first call with NULL arrays that
@@ -185,6 +214,31 @@ int  mcg_query_matches(mcg_db*, const mcg_query_opts*,
                        const char* reads1, const int64_t* offs1,
                        const char* reads2, const int64_t* offs2, int64_t n,
                        int64_t* out_counts, uint32_t* out_tgts, uint32_t* out_wins);
+
+/* query_batched_parallel2 (querying.h:721-1173) as ONE collective call over all shards: every rank passes
+ * ITS slice of the batch (slices in rank order form the batch) and receives the merged top lists, the
+ * decision and the statistics counters of that slice.  Per part of the call:
+ *   H2D of the slice over the rank's own PCIe link -> K1 on the slice only -> all-gather of the sketches
+ *   (64 B per window) over NVLink -> every rank probes ALL reads against its shard (rows 10-15) ->
+ *   all-to-all of the per-read top lists (rank r receives the lists of its slice from every shard) ->
+ *   merge in rank order + classify + statistics of the slice (rows 16-19) -> D2H of the slice's results.
+ * Replaces the reference's replicated sketching of every read on every rank and its blocking tree reduce
+ * to rank 0 (querying.h:867-1071).  comm may be NULL or of size 1 (single shard: no exchange).
+ * out_tax/out_hits [n_local][maxcand], out_ncand/out_best/out_best_rank [n_local]; any of them may be
+ * NULL; out_stats22 (may be NULL): the slice's counters are ADDED. */
+int  mcg_query_batch_sharded(mcg_db*, mcg_comm*, const mcg_query_opts*,
+                             const char* reads1, const int64_t* offs1,
+                             const char* reads2, const int64_t* offs2, int64_t n_local,
+                             int32_t* out_tax, uint32_t* out_hits, int32_t* out_ncand,
+                             int32_t* out_best, int32_t* out_best_rank, uint64_t* out_stats22);
+/* same with the slice and the outputs resident on the device (one part; enqueues on the ctx stream and
+ * waits for the fused kernel's left-over count only); d_stats22: counters are ADDED on the device */
+int  mcg_query_batch_sharded_dev(mcg_db*, mcg_comm*, const mcg_query_opts*,
+                                 const char* d_reads1, const int64_t* d_offs1, int64_t bytes1,
+                                 const char* d_reads2, const int64_t* d_offs2, int64_t bytes2,
+                                 int64_t n_local, int64_t max_read_len,
+                                 int32_t* d_out_tax, uint32_t* d_out_hits, int32_t* d_out_ncand,
+                                 int32_t* d_out_best, int32_t* d_out_best_rank, uint64_t* d_stats22);
 
 /* cross-shard merge + decision + statistics on rank 0: querying.h:905-971
  * (insert in rank order), classification.cpp:236-265 (classify),

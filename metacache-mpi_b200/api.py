@@ -88,6 +88,16 @@ def load_library():
     L.mcg_query_matches.argtypes = [vp, C.POINTER(QueryOpts), vp, vp, vp, vp, i64, vp, vp, vp]
     L.mcg_merge_classify.argtypes = [vp, C.POINTER(QueryOpts), vp, vp, vp, i32, i64, vp, vp, vp, vp, vp, vp]
     L.mcg_merge_classify_dev.argtypes = [vp, C.POINTER(QueryOpts), vp, vp, vp, i32, i64, vp, vp, vp, vp, vp, vp]
+    L.mcg_db_key_sizes_dev.argtypes = [vp, vp, vp]
+    L.mcg_comm_get_id.argtypes = [vp]
+    L.mcg_comm_create.argtypes = [vp, vp, i32, i32, C.POINTER(vp)]
+    L.mcg_comm_destroy.argtypes = [vp]
+    L.mcg_comm_rank.argtypes = [vp]
+    L.mcg_comm_size.argtypes = [vp]
+    L.mcg_db_remove_overpopulated_dist.argtypes = [vp, vp, u64p, u64p]
+    L.mcg_query_batch_sharded.argtypes = [vp, vp, C.POINTER(QueryOpts), vp, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp]
+    L.mcg_query_batch_sharded_dev.argtypes = [vp, vp, C.POINTER(QueryOpts), vp, vp, i64, vp, vp, i64, i64, i64,
+                                              vp, vp, vp, vp, vp, vp]
     _lib = L
     return L
 
@@ -194,6 +204,30 @@ class Context:
         return ot[:n], oh[:n], on[:n], best[:n], brank[:n], stats
 
 
+class Comm:
+    """one rank of the NCCL communicator inside libmcgpu (mcg_comm).  `comm_id`: the 128 bytes of
+    mcg_comm_get_id() from rank 0, carried to the other ranks by the launcher (see distributed.make_comm)"""
+
+    def __init__(self, ctx, comm_id, rank, nranks):
+        self.ctx, self.L = ctx, ctx.L
+        h = C.c_void_p()
+        buf = (C.c_uint8 * 128).from_buffer_copy(bytes(comm_id)) if nranks > 1 else None
+        _check(self.L.mcg_comm_create(ctx.h, buf, rank, nranks, C.byref(h)))
+        self.h = h
+        self.rank, self.nranks = rank, nranks
+
+    @staticmethod
+    def new_id():
+        buf = (C.c_uint8 * 128)()
+        _check(load_library().mcg_comm_get_id(buf))
+        return bytes(buf)
+
+    def close(self):
+        if self.h:
+            self.L.mcg_comm_destroy(self.h)
+            self.h = None
+
+
 class Database:
     """one shard (mcg_db): the sketch_database seams of the reference"""
 
@@ -281,6 +315,31 @@ class Database:
         _check(self.L.mcg_query_batch(self.h, C.byref(qopt), _ptr(buf1), _ptr(offs1), _ptr(buf2), _ptr(offs2), n,
                                       _ptr(ot), _ptr(oh), _ptr(on)))
         return ot[:n], oh[:n], on[:n]
+
+    def query_batch_sharded(self, comm, qopt, buf1, offs1, buf2=None, offs2=None):
+        """collective: this rank's slice of the batch in, merged lists + decision + statistics of the slice out"""
+        buf1 = _u8(buf1)
+        offs1 = np.ascontiguousarray(offs1, np.int64)
+        n = len(offs1) - 1
+        if buf2 is not None:
+            buf2 = _u8(buf2)
+            offs2 = np.ascontiguousarray(offs2, np.int64)
+        K = qopt.maxcand
+        ot = np.empty((max(n, 1), K), np.int32)
+        oh = np.empty((max(n, 1), K), np.uint32)
+        on = np.empty(max(n, 1), np.int32)
+        best = np.empty(max(n, 1), np.int32)
+        brank = np.empty(max(n, 1), np.int32)
+        stats = np.zeros(22, np.uint64)
+        _check(self.L.mcg_query_batch_sharded(self.h, comm.h if comm is not None else None, C.byref(qopt), _ptr(buf1), _ptr(offs1),
+                                              _ptr(buf2), _ptr(offs2), n, _ptr(ot), _ptr(oh), _ptr(on), _ptr(best), _ptr(brank),
+                                              _ptr(stats)))
+        return ot[:n], oh[:n], on[:n], best[:n], brank[:n], stats
+
+    def remove_overpopulated_dist(self, comm):
+        a, b = C.c_uint64(), C.c_uint64()
+        _check(self.L.mcg_db_remove_overpopulated_dist(self.h, comm.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def query_matches(self, qopt, buf1, offs1, buf2=None, offs2=None):
         buf1 = _u8(buf1)

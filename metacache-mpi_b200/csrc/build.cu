@@ -781,6 +781,26 @@ int mcg_db_key_sizes(mcg_db* db, uint32_t* keys, uint32_t* sizes)
     return mcg_db_export(db, keys, sizes, nullptr, nullptr);
 }
 
+int mcg_db_key_sizes_dev(mcg_db* db, uint32_t* d_keys, uint32_t* d_sizes)
+{
+    MCG_REQUIRE(db != nullptr, "db is NULL");
+    if(!db->finalized) { set_error("database not finalized"); return MCG_ERR_STATE; }
+    mcg_ctx* c = db->ctx;
+    MCG_CUDA(cudaSetDevice(c->device));
+    const uint32_t nkeys = uint32_t(db->nkeys);
+    if(nkeys == 0) return MCG_OK;
+    MCG_TRY(c->tmp0.reserve((size_t(nkeys) + 2) * 4));
+    uint32_t* kpos = c->tmp0.as<uint32_t>();
+    exp_flags_kernel<<<grid_for(nkeys), 256, 0, c->stream>>>(db->sizes.as<uint8_t>(), nkeys, kpos);
+    c->launches++;
+    MCG_TRY(exclusive_scan_u32_to_u32(c, kpos, kpos, nkeys));
+    exp_emit_kernel<<<grid_for(nkeys), 256, 0, c->stream>>>(db->keys.as<uint32_t>(), db->sizes.as<uint8_t>(), db->offs.as<uint64_t>(),
+                                                           db->locs.as<uint64_t>(), nkeys, kpos, nullptr, d_keys, d_sizes, nullptr, nullptr);
+    c->launches++;
+    MCG_CUDA(cudaGetLastError());
+    return MCG_OK;
+}
+
 // err: bit 0 size > 255, bit 1 key 0xFFFFFFFF; mx: [0] largest target, [1] largest window
 __global__ void imp_check_kernel(const uint32_t* keys, const uint32_t* sizes, uint64_t nkeys, const uint32_t* tgts, const uint32_t* wins,
                                  uint64_t nlocs, uint32_t* err, uint32_t* mx)

@@ -232,6 +232,9 @@ int mcg_ctx_destroy(mcg_ctx* c)
                       &c->m_tax, &c->m_hits, &c->m_n, &c->m_o_tax, &c->m_o_hits, &c->m_o_n, &c->m_best,
                       &c->m_brank, &c->m_stats, &c->m_bad, &c->tilectr};
     for(DevBuf* b : bufs) b->release();
+    c->qp[0].release_all(); c->qp[1].release_all();
+    c->s_wc.release(); c->s_featc.release(); c->plan.release();
+    if(c->h_left != nullptr) cudaFreeHost(c->h_left);
     if(c->pinned != nullptr) cudaFreeHost(c->pinned);
     if(c->s_h2d) cudaStreamDestroy(c->s_h2d);
     if(c->s_d2h) cudaStreamDestroy(c->s_d2h);
@@ -331,6 +334,11 @@ int ensure_pipeline(mcg_ctx* c)
         MCG_CUDA(cudaEventCreateWithFlags(&c->ev_k[i], cudaEventDisableTiming));
     }
     MCG_CUDA(cudaEventCreateWithFlags(&c->ev_misc, cudaEventDisableTiming));
+    for(int i = 0; i < 2; ++i) {
+        MCG_CUDA(cudaEventCreateWithFlags(&c->qp[i].evA, cudaEventDisableTiming));
+        MCG_CUDA(cudaEventCreateWithFlags(&c->qp[i].evB, cudaEventDisableTiming));
+    }
+    MCG_CUDA(cudaMallocHost(reinterpret_cast<void**>(&c->h_left), 64));
     return MCG_OK;
 }
 }  // namespace mcg

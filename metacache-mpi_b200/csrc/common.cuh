@@ -64,6 +64,29 @@ struct TableGeom {
 }  // namespace mcg
 
 // ------------------------------------------------------------------ context / db
+struct mcg_comm;
+
+namespace mcg {
+// Buffers of one query part in flight.  Stage A of a part (sketch, feature exchange, fused kernel) is
+// enqueued before the host looks at the previous part's left-over count, so what stage A writes and the
+// later stages (left-over reads, list exchange, merge, copy-out) read exists twice.
+struct QPart {
+    DevBuf W, feat, meta, left_list, done, ctr;        // window prefix, features, per-read meta; fused kernel bookkeeping
+    DevBuf lt, lh, ln;                                 // per-read top lists of every read of the part
+    DevBuf ct, ch, cn;                                 // lists received from the other shards for the own block [P][n][K]
+    DevBuf mt, mh, mn, mbest, mbrank;                  // merged lists + decision of the own block
+    cudaEvent_t evA = nullptr, evB = nullptr;
+    void release_all()
+    {
+        DevBuf* b[] = {&W, &feat, &meta, &left_list, &done, &ctr, &lt, &lh, &ln, &ct, &ch, &cn, &mt, &mh, &mn, &mbest, &mbrank};
+        for(DevBuf* x : b) x->release();
+        if(evA) cudaEventDestroy(evA);
+        if(evB) cudaEventDestroy(evB);
+        evA = evB = nullptr;
+    }
+};
+}  // namespace mcg
+
 struct mcg_ctx {
     int device = 0;
     int num_sms = 148;                // multiProcessorCount of the device (B200: 2 dies x 74 SMs): persistent grids are sized from it
@@ -80,6 +103,9 @@ struct mcg_ctx {
     bool m_bad_clear = false;         // m_bad (flags of the merge kernel's input checks) is zero
     void* pinned = nullptr;           // small pinned staging area for scalars
     size_t pinned_cap = 0;
+    mcg::QPart qp[2];                 // query parts in flight (see QPart)
+    uint32_t* h_left = nullptr;       // pinned: left-over counts of the two parts
+    mcg::DevBuf s_wc, s_featc, plan;  // left-over path: compacted window prefix / features; sharded query: part sizes
     // copy streams + events of the pipelined host entry points
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
     cudaEvent_t ev_h2d[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -205,7 +231,7 @@ int sketch_launch(mcg_ctx* c, const mcg_sketch_cfg& cfg, int sketchlen, int64_t 
                   const char* d_seq, int64_t total_bytes, const int64_t* d_seq_off, int64_t nseq,
                   const uint32_t* d_win_first, const uint32_t* d_out_first, uint64_t nwin,
                   uint32_t* d_out_feat, uint32_t* d_out_cnt, uint64_t win_lo = 0, cudaStream_t stream = nullptr,
-                  uint32_t* d_tile_scratch = nullptr);
+                  uint32_t* d_tile_scratch = nullptr, const uint32_t* d_nwin = nullptr);   // d_nwin: exact window count on the device when `nwin` is only a bound
 int sketch_config(const mcg_sketch_cfg& cfg, int sketchlen, int64_t winlen, int64_t stride,
                   int* wpt, int* ngroups, int* pitch, size_t* warp_smem);
 int window_prefix(mcg_ctx* c, int64_t winlen, int64_t stride, const int64_t* d_seq_off, int64_t nseq,

@@ -31,6 +31,13 @@ int copy_in(mcg_ctx* c, void* d, const void* h, size_t bytes);
 int copy_out(mcg_ctx* c, void* h, const void* d, size_t bytes);
 int exclusive_scan_u32_to_u32(mcg_ctx* c, const uint32_t* d_in, uint32_t* d_out, uint64_t n);
 int ensure_pipeline(mcg_ctx* c);
+// comm.cu
+int comm_rank(const mcg_comm* m);
+int comm_size(const mcg_comm* m);
+int comm_allgather_dev_u64(mcg_comm* m, const uint64_t* d_mine, int count, uint64_t* out);
+int comm_allgatherv_inplace(mcg_comm* m, void* buf, const uint64_t* off, const uint64_t* len, cudaStream_t st);
+int comm_alltoallv(mcg_comm* m, const void* send, const uint64_t* soff, const uint64_t* slen,
+                   void* recv, const uint64_t* roff, const uint64_t* rlen, cudaStream_t st);
 
 constexpr uint32_t EMPTY_KEY = 0xFFFFFFFFu;
 constexpr int Q_SMALL = 512;       // matches per read handled by one warp
@@ -40,17 +47,32 @@ constexpr int Q_LARGE = 16384;     // by one 512-thread CTA with 192 KB of share
 static inline unsigned grid_for(uint64_t n, int threads = 256) { return unsigned((n + threads - 1) / threads); }
 
 // ------------------------------------------------------------------ window bookkeeping
+// per read: windows of mate 1 / mate 2 (dna_encoding.h:261-276) and meta = {windows of the read (pair),
+// window-range width numWindows = 2 + max(len1 + len2, insertsize) / target stride (classification.cpp:217-219)}
 __global__ void q_window_counts_kernel(const int64_t* offs1, const int64_t* offs2, int64_t n,
-                                       int64_t winlen, int64_t stride,
-                                       uint32_t* nw1, uint32_t* nw2, uint32_t* nws)
+                                       int64_t winlen, int64_t stride, int64_t insertsize, int64_t tstride,
+                                       uint32_t* nw1, uint32_t* nw2, uint32_t* nws, uint2* meta)
 {
     const int64_t r = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
     if(r >= n) return;
-    const uint32_t a = uint32_t(num_windows(offs1[r + 1] - offs1[r], winlen, stride));
-    const uint32_t b = offs2 ? uint32_t(num_windows(offs2[r + 1] - offs2[r], winlen, stride)) : 0u;
+    const int64_t l1 = offs1[r + 1] - offs1[r], l2 = offs2 ? offs2[r + 1] - offs2[r] : 0;
+    const uint32_t a = uint32_t(num_windows(l1, winlen, stride));
+    const uint32_t b = offs2 ? uint32_t(num_windows(l2, winlen, stride)) : 0u;
     nw1[r] = a;
     nw2[r] = b;
     nws[r] = a + b;
+    int64_t span = l1 + l2;
+    if(insertsize > span) span = insertsize;
+    // 32-bit division when possible (the 64-bit one is emulated with ~150 instructions)
+    const uint64_t nwr = (span < (int64_t(1) << 31) && tstride < (int64_t(1) << 31)) ? 2u + uint32_t(span) / uint32_t(tstride)
+                                                                                      : uint64_t(2 + span / tstride);
+    meta[r] = make_uint2(a + b, uint32_t(nwr < 0xFFFFFFFFull ? nwr : 0xFFFFFFFFull));
+}
+
+__global__ void q_meta_windows_kernel(const uint2* meta, int64_t n, uint32_t* nws)
+{
+    const int64_t r = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+    if(r < n) nws[r] = meta[r].x;
 }
 
 __global__ void q_out_first2_kernel(const uint32_t* W, const uint32_t* wf1, int64_t n, uint32_t* of2)
@@ -207,10 +229,7 @@ struct CandParams {
     const uint64_t* fpos;
     const uint32_t* W;
     int s;
-    const int64_t* offs1;
-    const int64_t* offs2;
-    int64_t insertsize;
-    int64_t tstride;
+    const uint2* meta;           // per read {windows, numWindows of the candidate ranges}
     void* loc;
     int wbits;
     int kbits;                   // significant bits of a match key
@@ -237,15 +256,10 @@ __device__ __forceinline__ void gsync()
 
 template<class KeyT> __device__ __forceinline__ uint32_t tgt_of(KeyT k, int wbits) { return uint32_t(k >> wbits); }
 
-// window-range width of a read (classification.cpp:217-219)
+// window-range width of a read (classification.cpp:217-219), precomputed by q_window_counts_kernel
 __device__ __forceinline__ uint32_t num_windows_in_range(const CandParams& p, uint32_t r)
 {
-    int64_t span = p.offs1[r + 1] - p.offs1[r];
-    if(p.offs2) span += p.offs2[r + 1] - p.offs2[r];
-    if(p.insertsize > span) span = p.insertsize;
-    // 32-bit division when possible (the 64-bit one is emulated with ~150 instructions)
-    if(span < (int64_t(1) << 31) && p.tstride < (int64_t(1) << 31)) return 2u + uint32_t(span) / uint32_t(p.tstride);
-    return uint32_t(2 + span / p.tstride);
+    return __ldg(&p.meta[r].y);
 }
 
 // hits of the best window range ENDING at element i (candidates.h:141-152): number of
@@ -1079,6 +1093,15 @@ q_merge_classify_kernel(const MergeParams p)
 }
 
 // ------------------------------------------------------------------ host orchestration
+//
+// A query call is cut into PARTS.  Stage A of a part is enqueued without any host round trip:
+//   window counts + per-read meta -> 3 scans -> K1 on both mates (launches sized from upper bounds, the
+//   kernels read the exact window counts from the device) -> [sharded: all-gather of features + meta over
+//   NVLink] -> q_fused_warp_kernel over all reads of the part -> left-over count into pinned memory.
+// Before the host looks at that count (the only decision it has to take: reads the fused kernel could
+// not hold take the staged path), stage A of the NEXT part is already enqueued, so the GPU never waits
+// for the host.  Stage B: left-over reads (rare), [sharded: all-to-all of the per-read top lists, merge +
+// decision of the own block], copy-out.
 struct QueryRun {
     uint64_t nwin = 0, nslots = 0, total = 0;
     uint32_t cls[4] = {0, 0, 0, 0};
@@ -1103,47 +1126,54 @@ static int check_opts(const mcg_db* db, const mcg_query_opts* o)
     return MCG_OK;
 }
 
-// stages a..g: everything up to (and including) the gather.  Reads are on the device.
-// window bookkeeping + K1 on both mates: read-major sketches in c->q_feat, window prefix W in c->tmp2
-static int query_sketch(mcg_db* db, const mcg_query_opts* o,
-                        const char* d1, const int64_t* doffs1, int64_t bytes1,
-                        const char* d2, const int64_t* doffs2, int64_t bytes2, int64_t n, QueryRun* run)
+static int check_ready(mcg_db* db, const mcg_query_opts* o)
+{
+    MCG_TRY(check_opts(db, o));
+    if(!db->finalized) { set_error("database not finalized"); return MCG_ERR_STATE; }
+    if(db->ctx->lineage.p == nullptr) { set_error("taxonomy not uploaded (mcg_tax_upload)"); return MCG_ERR_STATE; }
+    return MCG_OK;
+}
+
+// upper bound of the windows of n sequences with `bytes` bases in total: a sequence has at most len / stride + 2
+static uint64_t windows_bound(int64_t bytes, int64_t n, int64_t stride, int64_t winlen, int64_t max_len)
+{
+    if(n <= 0) return 0;
+    uint64_t b = uint64_t(bytes / stride) + 2ull * uint64_t(n);
+    if(max_len > 0) b = std::min<uint64_t>(b, uint64_t(n) * uint64_t(num_windows(max_len, winlen, stride)));
+    return b;
+}
+
+// stage A, local part: window bookkeeping + K1 of both mates of n device-resident reads.  Sketches land
+// read-major at feat_out[W[r] * s ...], W (exclusive prefix, total at [n]) and meta are written; nothing
+// returns to the host.  feat_out must hold *wbound * s features.
+static int qa_sketch(mcg_db* db, const mcg_query_opts* o,
+                     const char* d1, const int64_t* doffs1, int64_t bytes1,
+                     const char* d2, const int64_t* doffs2, int64_t bytes2, int64_t n, int64_t max_len,
+                     uint32_t* W, uint2* meta, uint32_t* feat_out, uint64_t wb1, uint64_t wb2)
 {
     mcg_ctx* c = db->ctx;
     const int s = o->sketchlen;
-    // window bookkeeping: wf1, wf2 (processing-order prefixes), W (output prefix), of2
     MCG_TRY(c->tmp0.reserve(size_t(n + 2) * 4));
     MCG_TRY(c->tmp1.reserve(size_t(n + 2) * 4));
-    MCG_TRY(c->tmp2.reserve(size_t(n + 2) * 4));
     MCG_TRY(c->tmp3.reserve(size_t(n + 2) * 4));
     uint32_t* wf1 = c->tmp0.as<uint32_t>();
     uint32_t* wf2 = c->tmp1.as<uint32_t>();
-    uint32_t* W = c->tmp2.as<uint32_t>();
     uint32_t* of2 = c->tmp3.as<uint32_t>();
-    q_window_counts_kernel<<<grid_for(n), 256, 0, c->stream>>>(doffs1, d2 ? doffs2 : nullptr, n, o->winlen, o->winstride, wf1, wf2, W);
+    q_window_counts_kernel<<<grid_for(n), 256, 0, c->stream>>>(doffs1, d2 ? doffs2 : nullptr, n, o->winlen, o->winstride, o->insertsize,
+                                                              db->cfg.winstride, wf1, wf2, W, meta);
     c->launches++;
     MCG_TRY(exclusive_scan_u32_to_u32(c, wf1, wf1, n));
-    MCG_TRY(exclusive_scan_u32_to_u32(c, wf2, wf2, n));
+    if(d2) MCG_TRY(exclusive_scan_u32_to_u32(c, wf2, wf2, n));
     MCG_TRY(exclusive_scan_u32_to_u32(c, W, W, n));
-    q_out_first2_kernel<<<grid_for(n), 256, 0, c->stream>>>(W, wf1, n, of2);
-    c->launches++;
-    uint32_t h_tot[3] = {0, 0, 0};
-    MCG_CUDA(cudaMemcpyAsync(&h_tot[0], wf1 + n, 4, cudaMemcpyDeviceToHost, c->stream));
-    MCG_CUDA(cudaMemcpyAsync(&h_tot[1], wf2 + n, 4, cudaMemcpyDeviceToHost, c->stream));
-    MCG_CUDA(cudaMemcpyAsync(&h_tot[2], W + n, 4, cudaMemcpyDeviceToHost, c->stream));
-    MCG_CUDA(cudaStreamSynchronize(c->stream));
-    const uint64_t nwin = h_tot[2];
-    const uint64_t nslots = nwin * uint64_t(s);
-    run->nwin = nwin;
-    run->nslots = nslots;
-    // K1 on both mates, sketches land read-major
-    MCG_TRY(c->q_feat.reserve((nslots + 1) * 4));
     mcg_sketch_cfg cfg = db->cfg;
-    MCG_TRY(sketch_launch(c, cfg, s, o->winlen, o->winstride, d1, bytes1, doffs1, n, wf1, W, h_tot[0], c->q_feat.as<uint32_t>(), nullptr));
-    if(d2) MCG_TRY(sketch_launch(c, cfg, s, o->winlen, o->winstride, d2, bytes2, doffs2, n, wf2, of2, h_tot[1], c->q_feat.as<uint32_t>(), nullptr));
-    run->feat = c->q_feat.as<uint32_t>();
-    run->W = W;
-    run->rmap = nullptr;
+    (void)max_len;
+    MCG_TRY(sketch_launch(c, cfg, s, o->winlen, o->winstride, d1, bytes1, doffs1, n, wf1, W, wb1, feat_out, nullptr, 0, nullptr, nullptr, wf1 + n));
+    if(d2) {
+        q_out_first2_kernel<<<grid_for(n), 256, 0, c->stream>>>(W, wf1, n, of2);
+        c->launches++;
+        MCG_TRY(sketch_launch(c, cfg, s, o->winlen, o->winstride, d2, bytes2, doffs2, n, wf2, of2, wb2, feat_out, nullptr, 0, nullptr, nullptr, wf2 + n));
+    }
+    MCG_CUDA(cudaGetLastError());
     return MCG_OK;
 }
 
@@ -1191,19 +1221,16 @@ static int query_find_gather(mcg_db* db, const mcg_query_opts* o, int64_t n, int
     return MCG_OK;
 }
 
-static void fill_cand_params(mcg_db* db, const mcg_query_opts* o, const int64_t* doffs1, const int64_t* doffs2,
+static void fill_cand_params(mcg_db* db, const mcg_query_opts* o, const uint32_t* W, const uint2* meta,
                              int32_t* d_out_tax, uint32_t* d_out_hits, int32_t* d_out_n, int write_sorted, CandParams* pp)
 {
     mcg_ctx* c = db->ctx;
     CandParams& p = *pp;
     p.fpos = c->q_fpos.as<uint64_t>();
-    p.W = c->tmp2.as<uint32_t>();
+    p.W = W;
     p.rmap = nullptr;
     p.s = o->sketchlen;
-    p.offs1 = doffs1;
-    p.offs2 = doffs2;
-    p.insertsize = o->insertsize;
-    p.tstride = db->cfg.winstride;
+    p.meta = meta;
     p.loc = c->q_loc.p;
     p.wbits = db->wbits;
     p.kbits = db->kbits;
@@ -1221,16 +1248,14 @@ static void fill_cand_params(mcg_db* db, const mcg_query_opts* o, const int64_t*
     p.write_sorted = write_sorted;
 }
 
-static int query_back(mcg_db* db, const mcg_query_opts* o, const int64_t* doffs1, const int64_t* doffs2, int64_t n,
+static int query_back(mcg_db* db, const mcg_query_opts* o, const uint2* meta, int64_t n,
                       const QueryRun& run, int32_t* d_out_tax, uint32_t* d_out_hits, int32_t* d_out_n, int write_sorted)
 {
     mcg_ctx* c = db->ctx;
     CandParams p;
-    fill_cand_params(db, o, doffs1, doffs2, d_out_tax, d_out_hits, d_out_n, write_sorted, &p);
+    fill_cand_params(db, o, run.W, meta, d_out_tax, d_out_hits, d_out_n, write_sorted, &p);
     const uint32_t* lists = c->q_cls.as<uint32_t>();
     const uint32_t* counters = c->q_rinfo.as<uint32_t>();
-    p.wbits = db->wbits;
-    p.W = run.W;
     p.rmap = run.rmap;
     const bool k32 = db->key32;
     const int ksz = k32 ? 4 : 8;
@@ -1272,51 +1297,39 @@ static int query_back(mcg_db* db, const mcg_query_opts* o, const int64_t* doffs1
     return MCG_OK;
 }
 
-int query_batch_dev(mcg_db* db, const mcg_query_opts* o,
-                    const char* d1, const int64_t* doffs1, int64_t bytes1,
-                    const char* d2, const int64_t* doffs2, int64_t bytes2, int64_t n,
-                    int32_t* d_out_tax, uint32_t* d_out_hits, int32_t* d_out_n, int write_sorted, QueryRun* run_out)
+// stage A, fused kernel: all reads of the part (features / W / meta in `part`) -> per-read top lists; the
+// number of reads it could not hold goes to pinned memory (h_left), followed by part.evA
+static int qa_fused(mcg_db* db, const mcg_query_opts* o, QPart& part, int slot, int64_t n, double slots_per_read,
+                    int32_t* d_out_tax, uint32_t* d_out_hits, int32_t* d_out_n)
 {
     mcg_ctx* c = db->ctx;
-    MCG_CUDA(cudaSetDevice(c->device));
-    MCG_TRY(check_opts(db, o));
-    if(!db->finalized) { set_error("database not finalized"); return MCG_ERR_STATE; }
-    if(c->lineage.p == nullptr) { set_error("taxonomy not uploaded (mcg_tax_upload)"); return MCG_ERR_STATE; }
-    if(n == 0) return MCG_OK;
-    MCG_REQUIRE(n < (1ll << 31), "more than 2^31-1 reads in one batch");
     const int K = o->maxcand;
     // unused slots: taxon -1, hits 0
     MCG_CUDA(cudaMemsetAsync(d_out_tax, 0xFF, size_t(n) * K * 4, c->stream));
     MCG_CUDA(cudaMemsetAsync(d_out_hits, 0, size_t(n) * K * 4, c->stream));
-    QueryRun run;
-    MCG_TRY(query_sketch(db, o, d1, doffs1, bytes1, d2, doffs2, bytes2, n, &run));
-    const uint8_t* d_done = nullptr;
-    int64_t n_staged = n;
-    static const bool fused_off = getenv("MCG_QUERY_NO_FUSION") != nullptr;
-    if(!write_sorted && !fused_off && run.nslots > 0) {
-        // short reads end to end in one kernel; what it leaves over goes through the staged path
-        MCG_TRY(c->q_cls.reserve(size_t(4) * size_t(n) * 4 + 64));
-        MCG_TRY(c->q_rinfo.reserve(64));
-        MCG_TRY(c->q_done.reserve(size_t(n) + 16));
-        uint32_t* left = c->q_rinfo.as<uint32_t>() + 8;
-        MCG_CUDA(cudaMemsetAsync(left, 0, 8, c->stream));
-        CandParams p;
-        fill_cand_params(db, o, doffs1, d2 ? doffs2 : nullptr, d_out_tax, d_out_hits, d_out_n, 0, &p);
-        FusedParams f;
-        f.feat = c->q_feat.as<uint32_t>(); f.table = db->table.as<uint32_t>(); f.geom = db->geom();
-        f.locs = db->locs.as<uint64_t>(); f.n = n; f.done = c->q_done.as<uint8_t>(); f.left_over = left;
-        f.left_list = c->tmp1.as<uint32_t>();          // (the mate-2 window prefix is dead once K1 has run)
-        // feature slots per lane: 2 (reads of <= 64 slots, e.g. 2 x 150 bp at sketchlen 16) keeps the
-        // registers at the level of 6 resident CTAs; longer reads take the 4-slot variant
-        const bool nc2 = run.nslots <= uint64_t(n) * 64;
-        unsigned g = 1;
-        int per_sm = 1;
-        // matches per read: 128 unless the lists of this database are long (a read pair of 64 features then gathers
-        // more than 128 locations as a rule and the staged path would take over the batch)
-        static const int cap_env = getenv("MCG_FUSED_CAP") ? atoi(getenv("MCG_FUSED_CAP")) : 0;
-        const bool cap256 = cap_env ? cap_env >= 256 : (double(db->nlocs) > 2.1 * double(db->nkeys));
-        // shared memory comes out of L1, which the probes live on: ask for no more than the 5 CTAs need
-        const int carve = cap256 ? 70 : 38;
+    MCG_TRY(part.ctr.reserve(64));
+    MCG_TRY(part.done.reserve(size_t(n) + 16));
+    MCG_TRY(part.left_list.reserve(size_t(n + 2) * 4));
+    uint32_t* left = part.ctr.as<uint32_t>();
+    MCG_CUDA(cudaMemsetAsync(left, 0, 8, c->stream));
+    CandParams p;
+    fill_cand_params(db, o, part.W.as<uint32_t>(), part.meta.as<uint2>(), d_out_tax, d_out_hits, d_out_n, 0, &p);
+    FusedParams f;
+    f.feat = part.feat.as<uint32_t>(); f.table = db->table.as<uint32_t>(); f.geom = db->geom();
+    f.locs = db->locs.as<uint64_t>(); f.n = n; f.done = part.done.as<uint8_t>(); f.left_over = left;
+    f.left_list = part.left_list.as<uint32_t>();
+    // feature slots per lane: 2 (reads of <= 64 slots, e.g. 2 x 150 bp at sketchlen 16) keeps the
+    // registers at the level of 6 resident CTAs; longer reads take the 4-slot variant (a read with more
+    // slots than its variant holds is left to the staged path: the choice only affects speed)
+    const bool nc2 = slots_per_read <= 64.0;
+    unsigned g = 1;
+    int per_sm = 1;
+    // matches per read: 128 unless the lists of this database are long (a read pair of 64 features then gathers
+    // more than 128 locations as a rule and the staged path would take over the batch)
+    static const int cap_env = getenv("MCG_FUSED_CAP") ? atoi(getenv("MCG_FUSED_CAP")) : 0;
+    const bool cap256 = cap_env ? cap_env >= 256 : (double(db->nlocs) > 2.1 * double(db->nkeys));
+    // shared memory comes out of L1, which the probes live on: ask for no more than the 5 CTAs need
+    const int carve = cap256 ? 70 : 38;
 #define QF_LAUNCH(KT, NC) do { if(cap256) QF_LAUNCH_CAP(KT, NC, 256); else QF_LAUNCH_CAP(KT, NC, Q_FUSED); } while(0)
 #define QF_LAUNCH_CAP(KT, NC, CAP)                                                                                   \
     do {                                                                                                             \
@@ -1328,50 +1341,133 @@ int query_batch_dev(mcg_db* db, const mcg_query_opts* o,
         g = unsigned(std::min<uint64_t>(uint64_t(n + 63) / 64, uint64_t(c->num_sms) * uint64_t(std::max(1, per_sm)))); \
         kern<<<g, 256, smem, c->stream>>>(p, f);                                                                     \
     } while(0)
-        if(db->key32) { if(nc2) QF_LAUNCH(uint32_t, 2); else QF_LAUNCH(uint32_t, 4); }
-        else          { if(nc2) QF_LAUNCH(uint64_t, 2); else QF_LAUNCH(uint64_t, 4); }
+    if(db->key32) { if(nc2) QF_LAUNCH(uint32_t, 2); else QF_LAUNCH(uint32_t, 4); }
+    else          { if(nc2) QF_LAUNCH(uint64_t, 2); else QF_LAUNCH(uint64_t, 4); }
 #undef QF_LAUNCH
 #undef QF_LAUNCH_CAP
+    c->launches++;
+    MCG_CUDA(cudaGetLastError());
+    MCG_CUDA(cudaMemcpyAsync(c->h_left + slot, left, 4, cudaMemcpyDeviceToHost, c->stream));
+    MCG_CUDA(cudaEventRecord(part.evA, c->stream));
+    return MCG_OK;
+}
+
+// stage B, first half: waits for the part's fused kernel and sends the reads it left over through the
+// staged path (find -> scan -> binning -> gather -> size-binned candidate kernels).  Synchronises.
+static int qb_leftovers(mcg_db* db, const mcg_query_opts* o, QPart& part, int slot, int64_t n,
+                        int32_t* d_out_tax, uint32_t* d_out_hits, int32_t* d_out_n)
+{
+    mcg_ctx* c = db->ctx;
+    MCG_CUDA(cudaEventSynchronize(part.evA));
+    const uint32_t h_left = c->h_left[slot];
+    static const bool trace = getenv("MCG_TRACE") != nullptr;
+    if(trace) fprintf(stderr, "[mcg query] %lld reads, left over by the fused kernel: %u\n", (long long)n, h_left);
+    if(h_left == 0) return MCG_OK;
+    QueryRun run;
+    const uint8_t* d_done = nullptr;
+    int64_t n_staged = n;
+    const uint32_t* W = part.W.as<uint32_t>();
+    static const bool compact_off = getenv("MCG_QUERY_NO_COMPACT") != nullptr;
+    if(uint64_t(h_left) * 8 <= uint64_t(n) && !compact_off) {
+        // few reads left: the staged path runs over a sub-batch of just these reads (its kernels
+        // are per feature slot of the batch they are given)
+        MCG_TRY(c->s_wc.reserve(size_t(h_left + 2) * 4));
+        uint32_t* Wc = c->s_wc.as<uint32_t>();
+        const uint32_t* left_list = part.left_list.as<uint32_t>();
+        q_left_counts_kernel<<<grid_for(h_left), 256, 0, c->stream>>>(W, left_list, h_left, Wc);
         c->launches++;
-        uint32_t h_left = 0;
-        MCG_CUDA(cudaMemcpyAsync(&h_left, left, 4, cudaMemcpyDeviceToHost, c->stream));
+        MCG_TRY(exclusive_scan_u32_to_u32(c, Wc, Wc, h_left));
+        uint32_t wtot = 0;
+        MCG_CUDA(cudaMemcpyAsync(&wtot, Wc + h_left, 4, cudaMemcpyDeviceToHost, c->stream));
         MCG_CUDA(cudaStreamSynchronize(c->stream));
-        static const bool trace = getenv("MCG_TRACE") != nullptr;
-        if(trace) fprintf(stderr, "[mcg query] %lld reads, %llu feature slots, left over by the fused kernel: %u\n",
-                          (long long)n, (unsigned long long)run.nslots, h_left);
-        if(h_left == 0) { if(run_out) *run_out = run; return MCG_OK; }
-        static const bool compact_off = getenv("MCG_QUERY_NO_COMPACT") != nullptr;
-        if(uint64_t(h_left) * 8 <= uint64_t(n) && !compact_off) {
-            // few reads left: the staged path runs over a sub-batch of just these reads (its kernels
-            // are per feature slot of the batch they are given)
-            uint32_t* Wc = c->tmp0.as<uint32_t>();
-            const uint32_t* left_list = c->tmp1.as<uint32_t>();
-            q_left_counts_kernel<<<grid_for(h_left), 256, 0, c->stream>>>(c->tmp2.as<uint32_t>(), left_list, h_left, Wc);
-            c->launches++;
-            MCG_TRY(exclusive_scan_u32_to_u32(c, Wc, Wc, h_left));
-            uint32_t wtot = 0;
-            MCG_CUDA(cudaMemcpyAsync(&wtot, Wc + h_left, 4, cudaMemcpyDeviceToHost, c->stream));
-            MCG_CUDA(cudaStreamSynchronize(c->stream));
-            const uint64_t nsl = uint64_t(wtot) * uint64_t(o->sketchlen);
-            MCG_TRY(c->tmp3.reserve((nsl + 1) * 4));
-            q_left_copy_kernel<<<grid_for(uint64_t(h_left) * 32), 256, 0, c->stream>>>(c->q_feat.as<uint32_t>(), c->tmp2.as<uint32_t>(), left_list,
-                                                                                     h_left, Wc, o->sketchlen, c->tmp3.as<uint32_t>());
-            c->launches++;
-            run.feat = c->tmp3.as<uint32_t>();
-            run.W = Wc;
-            run.rmap = left_list;
-            run.nwin = wtot;
-            run.nslots = nsl;
-            n_staged = int64_t(h_left);
-        } else {
-            d_done = c->q_done.as<uint8_t>();
-            q_hide_done_kernel<<<grid_for(uint64_t(n) * 32), 256, 0, c->stream>>>(c->q_feat.as<uint32_t>(), c->tmp2.as<uint32_t>(), o->sketchlen,
-                                                                                   d_done, n);
-            c->launches++;
-        }
+        const uint64_t nsl = uint64_t(wtot) * uint64_t(o->sketchlen);
+        MCG_TRY(c->s_featc.reserve((nsl + 1) * 4));
+        q_left_copy_kernel<<<grid_for(uint64_t(h_left) * 32), 256, 0, c->stream>>>(part.feat.as<uint32_t>(), W, left_list,
+                                                                                 h_left, Wc, o->sketchlen, c->s_featc.as<uint32_t>());
+        c->launches++;
+        run.feat = c->s_featc.as<uint32_t>();
+        run.W = Wc;
+        run.rmap = left_list;
+        run.nwin = wtot;
+        run.nslots = nsl;
+        n_staged = int64_t(h_left);
+    } else {
+        uint32_t wtot = 0;
+        MCG_CUDA(cudaMemcpyAsync(&wtot, W + n, 4, cudaMemcpyDeviceToHost, c->stream));
+        MCG_CUDA(cudaStreamSynchronize(c->stream));
+        d_done = part.done.as<uint8_t>();
+        q_hide_done_kernel<<<grid_for(uint64_t(n) * 32), 256, 0, c->stream>>>(part.feat.as<uint32_t>(), W, o->sketchlen, d_done, n);
+        c->launches++;
+        run.feat = part.feat.as<uint32_t>();
+        run.W = W;
+        run.rmap = nullptr;
+        run.nwin = wtot;
+        run.nslots = uint64_t(wtot) * uint64_t(o->sketchlen);
     }
     MCG_TRY(query_find_gather(db, o, n_staged, d_out_n, d_done, &run));
-    MCG_TRY(query_back(db, o, doffs1, d2 ? doffs2 : nullptr, n_staged, run, d_out_tax, d_out_hits, d_out_n, write_sorted));
+    MCG_TRY(query_back(db, o, part.meta.as<uint2>(), n_staged, run, d_out_tax, d_out_hits, d_out_n, 0));
+    return MCG_OK;
+}
+
+static double est_slots_per_read(const mcg_query_opts* o, int64_t bytes1, int64_t bytes2, int64_t n, bool paired)
+{
+    if(n <= 0) return 0.0;
+    auto est = [&](int64_t bytes) { const int64_t avg = (bytes + n - 1) / n; return double(num_windows(avg, o->winlen, o->winstride)); };
+    return double(o->sketchlen) * (est(bytes1) + (paired ? est(bytes2) : 0.0));
+}
+
+// one part, device in / device out, per-shard lists (the body of mcg_query_batch_dev)
+int query_batch_dev(mcg_db* db, const mcg_query_opts* o,
+                    const char* d1, const int64_t* doffs1, int64_t bytes1,
+                    const char* d2, const int64_t* doffs2, int64_t bytes2, int64_t n, int64_t max_len,
+                    int32_t* d_out_tax, uint32_t* d_out_hits, int32_t* d_out_n, int slot, bool finish)
+{
+    mcg_ctx* c = db->ctx;
+    QPart& part = c->qp[slot];
+    const int s = o->sketchlen;
+    const uint64_t wb1 = windows_bound(bytes1, n, o->winstride, o->winlen, max_len);
+    const uint64_t wb2 = d2 ? windows_bound(bytes2, n, o->winstride, o->winlen, max_len) : 0;
+    MCG_REQUIRE((wb1 + wb2) * uint64_t(s) < (1ull << 32), "too many feature slots in one query part");
+    MCG_TRY(part.W.reserve(size_t(n + 2) * 4));
+    MCG_TRY(part.meta.reserve(size_t(n + 1) * 8));
+    MCG_TRY(part.feat.reserve(((wb1 + wb2) * s + 1) * 4));
+    MCG_TRY(qa_sketch(db, o, d1, doffs1, bytes1, d2, doffs2, bytes2, n, max_len, part.W.as<uint32_t>(), part.meta.as<uint2>(),
+                      part.feat.as<uint32_t>(), wb1, wb2));
+    MCG_TRY(qa_fused(db, o, part, slot, n, est_slots_per_read(o, bytes1, bytes2, n, d2 != nullptr), d_out_tax, d_out_hits, d_out_n));
+    if(finish) MCG_TRY(qb_leftovers(db, o, part, slot, n, d_out_tax, d_out_hits, d_out_n));
+    return MCG_OK;
+}
+
+// the debugging seam of mcg_query_matches: everything staged, sorted match lists written back
+static int query_staged_sorted(mcg_db* db, const mcg_query_opts* o,
+                               const char* d1, const int64_t* doffs1, int64_t bytes1,
+                               const char* d2, const int64_t* doffs2, int64_t bytes2, int64_t n,
+                               int32_t* d_out_tax, uint32_t* d_out_hits, int32_t* d_out_n, QueryRun* run_out)
+{
+    mcg_ctx* c = db->ctx;
+    QPart& part = c->qp[0];
+    const int s = o->sketchlen, K = o->maxcand;
+    const uint64_t wb1 = windows_bound(bytes1, n, o->winstride, o->winlen, 0);
+    const uint64_t wb2 = d2 ? windows_bound(bytes2, n, o->winstride, o->winlen, 0) : 0;
+    MCG_REQUIRE((wb1 + wb2) * uint64_t(s) < (1ull << 32), "too many feature slots in one query part");
+    MCG_TRY(part.W.reserve(size_t(n + 2) * 4));
+    MCG_TRY(part.meta.reserve(size_t(n + 1) * 8));
+    MCG_TRY(part.feat.reserve(((wb1 + wb2) * s + 1) * 4));
+    MCG_CUDA(cudaMemsetAsync(d_out_tax, 0xFF, size_t(n) * K * 4, c->stream));
+    MCG_CUDA(cudaMemsetAsync(d_out_hits, 0, size_t(n) * K * 4, c->stream));
+    MCG_TRY(qa_sketch(db, o, d1, doffs1, bytes1, d2, doffs2, bytes2, n, 0, part.W.as<uint32_t>(), part.meta.as<uint2>(),
+                      part.feat.as<uint32_t>(), wb1, wb2));
+    uint32_t wtot = 0;
+    MCG_CUDA(cudaMemcpyAsync(&wtot, part.W.as<uint32_t>() + n, 4, cudaMemcpyDeviceToHost, c->stream));
+    MCG_CUDA(cudaStreamSynchronize(c->stream));
+    QueryRun run;
+    run.feat = part.feat.as<uint32_t>();
+    run.W = part.W.as<uint32_t>();
+    run.rmap = nullptr;
+    run.nwin = wtot;
+    run.nslots = uint64_t(wtot) * uint64_t(s);
+    MCG_TRY(query_find_gather(db, o, n, d_out_n, nullptr, &run));
+    MCG_TRY(query_back(db, o, part.meta.as<uint2>(), n, run, d_out_tax, d_out_hits, d_out_n, 1));
     if(run_out) *run_out = run;
     return MCG_OK;
 }
@@ -1402,6 +1498,159 @@ static int stage_reads(mcg_ctx* c, const char* reads1, const int64_t* offs1, con
         *d2 = c->seq.as<char>() + pad1;
         *do2 = c->seqoff.as<int64_t>() + (n + 1);
     }
+    return MCG_OK;
+}
+
+// ------------------------------------------------------------------ sharded query (all ranks, one call)
+// window totals of the np parts a slice of n reads is cut into: part j = reads [n*j/np, n*(j+1)/np)
+__global__ void q_plan_kernel(const uint32_t* W, int64_t n, int np, uint64_t* out)
+{
+    const int j = threadIdx.x;
+    if(j < np) out[1 + j] = uint64_t(W[n * (j + 1) / np] - W[n * j / np]);
+    if(j == 0) out[0] = uint64_t(n);
+}
+
+constexpr int QS_MAX_PARTS = 16;
+
+struct ShardPlan {
+    int P = 1, me = 0, np = 1;                    // ranks, own rank, parts
+    std::vector<uint64_t> n, w;                   // [np][P] reads / windows of part j on rank r
+    uint64_t rn(int j, int r) const { return n[size_t(j) * size_t(P) + size_t(r)]; }
+    uint64_t rw(int j, int r) const { return w[size_t(j) * size_t(P) + size_t(r)]; }
+};
+
+// sizes of every part on every rank (the only thing the ranks have to agree on before they enqueue).
+// P == 1: nothing is exchanged and nothing returns to the host (window counts are bounded instead).
+static int qs_plan(mcg_db* db, mcg_comm* comm, const mcg_query_opts* o, const int64_t* doffs1, const int64_t* doffs2,
+                   int64_t n_loc, int np_want, ShardPlan* pl)
+{
+    mcg_ctx* c = db->ctx;
+    const int P = comm_size(comm), me = comm_rank(comm);
+    pl->P = P; pl->me = me;
+    if(P == 1) {
+        pl->np = np_want;
+        pl->n.assign(size_t(np_want), 0); pl->w.assign(size_t(np_want), 0);
+        for(int j = 0; j < np_want; ++j) pl->n[size_t(j)] = uint64_t(n_loc * (j + 1) / np_want - n_loc * j / np_want);
+        return MCG_OK;                                        // w stays unknown (0): callers use bounds
+    }
+    const int NP = np_want;
+    MCG_TRY(c->tmp0.reserve(size_t(n_loc + 2) * 4)); MCG_TRY(c->tmp1.reserve(size_t(n_loc + 2) * 4));
+    MCG_TRY(c->tmp5.reserve(size_t(n_loc + 2) * 4)); MCG_TRY(c->tmp4.reserve(size_t(n_loc + 2) * 8));
+    MCG_TRY(c->plan.reserve(size_t(QS_MAX_PARTS + 2) * 8));
+    uint32_t* Ww = c->tmp5.as<uint32_t>();
+    if(n_loc > 0) {
+        q_window_counts_kernel<<<grid_for(n_loc), 256, 0, c->stream>>>(doffs1, doffs2, n_loc, o->winlen, o->winstride, o->insertsize,
+                                                                  db->cfg.winstride, c->tmp0.as<uint32_t>(), c->tmp1.as<uint32_t>(), Ww,
+                                                                  c->tmp4.as<uint2>());
+        c->launches++;
+        MCG_TRY(exclusive_scan_u32_to_u32(c, Ww, Ww, n_loc));
+    } else {
+        MCG_CUDA(cudaMemsetAsync(Ww, 0, 8, c->stream));
+    }
+    q_plan_kernel<<<1, 32, 0, c->stream>>>(Ww, n_loc, NP, c->plan.as<uint64_t>());
+    c->launches++;
+    std::vector<uint64_t> all(size_t(P) * size_t(NP + 1), 0);
+    MCG_TRY(comm_allgather_dev_u64(comm, c->plan.as<uint64_t>(), NP + 1, all.data()));
+    uint64_t nmax = 0;
+    for(int r = 0; r < P; ++r) nmax = std::max(nmax, all[size_t(r) * size_t(NP + 1)]);
+    static const uint64_t min_part = getenv("MCG_SHARD_MIN_PART") ? uint64_t(atoll(getenv("MCG_SHARD_MIN_PART"))) : 16384;
+    const bool collapse = nmax < min_part * uint64_t(NP);        // small calls: one part (same decision on every rank)
+    pl->np = collapse ? 1 : NP;
+    pl->n.assign(size_t(pl->np) * size_t(P), 0); pl->w.assign(size_t(pl->np) * size_t(P), 0);
+    for(int r = 0; r < P; ++r) {
+        const uint64_t* a = all.data() + size_t(r) * size_t(NP + 1);
+        const int64_t nr = int64_t(a[0]);
+        for(int j = 0; j < NP; ++j) {
+            const int jj = collapse ? 0 : j;
+            pl->n[size_t(jj) * size_t(P) + size_t(r)] += uint64_t(nr * (j + 1) / NP - nr * j / NP);
+            pl->w[size_t(jj) * size_t(P) + size_t(r)] += a[1 + j];
+        }
+    }
+    return MCG_OK;
+}
+
+// stage A of part j: local K1, feature / meta exchange, fused kernel over all reads of the part
+static int qs_stage_a(mcg_db* db, mcg_comm* comm, const mcg_query_opts* o, const ShardPlan& pl, int j, int slot,
+                      const char* d1, const int64_t* do1, int64_t b1, const char* d2, const int64_t* do2, int64_t b2,
+                      int64_t max_len)
+{
+    mcg_ctx* c = db->ctx;
+    QPart& part = c->qp[slot];
+    const int P = pl.P, me = pl.me, s = o->sketchlen, K = o->maxcand;
+    const int64_t n_loc = int64_t(pl.rn(j, me));
+    uint64_t N = 0, Wt = 0, nb = 0, wb = 0;
+    for(int r = 0; r < P; ++r) { if(r == me) { nb = N; wb = Wt; } N += pl.rn(j, r); Wt += pl.rw(j, r); }
+    const uint64_t wb1 = windows_bound(b1, n_loc, o->winstride, o->winlen, max_len);
+    const uint64_t wb2 = d2 ? windows_bound(b2, n_loc, o->winstride, o->winlen, max_len) : 0;
+    if(P == 1) Wt = wb1 + wb2;                                 // bound instead of an exchanged exact count
+    MCG_REQUIRE((Wt + 1) * uint64_t(s) < (1ull << 32) && N < (1ull << 31), "too many reads / feature slots in one query part");
+    MCG_TRY(part.W.reserve(size_t(N + 2) * 4));
+    MCG_TRY(part.meta.reserve(size_t(N + 1) * 8));
+    MCG_TRY(part.feat.reserve((Wt * s + 1) * 4));
+    MCG_TRY(part.lt.reserve(size_t(N + 1) * K * 4)); MCG_TRY(part.lh.reserve(size_t(N + 1) * K * 4)); MCG_TRY(part.ln.reserve(size_t(N + 1) * 4));
+    uint32_t* Wl = part.W.as<uint32_t>();
+    if(P > 1) { MCG_TRY(c->tmp2.reserve(size_t(n_loc + 2) * 4)); Wl = c->tmp2.as<uint32_t>(); }
+    if(n_loc > 0)
+        MCG_TRY(qa_sketch(db, o, d1, do1, b1, d2, do2, b2, n_loc, max_len, Wl, part.meta.as<uint2>() + nb,
+                          part.feat.as<uint32_t>() + wb * uint64_t(s), wb1, wb2));
+    if(P > 1) {
+        std::vector<uint64_t> off(static_cast<size_t>(P)), len(static_cast<size_t>(P));
+        uint64_t a = 0;
+        for(int r = 0; r < P; ++r) { off[size_t(r)] = a * uint64_t(s) * 4; len[size_t(r)] = pl.rw(j, r) * uint64_t(s) * 4; a += pl.rw(j, r); }
+        MCG_TRY(comm_allgatherv_inplace(comm, part.feat.p, off.data(), len.data(), c->stream));
+        a = 0;
+        for(int r = 0; r < P; ++r) { off[size_t(r)] = a * 8; len[size_t(r)] = pl.rn(j, r) * 8; a += pl.rn(j, r); }
+        MCG_TRY(comm_allgatherv_inplace(comm, part.meta.p, off.data(), len.data(), c->stream));
+        if(N > 0) {
+            q_meta_windows_kernel<<<grid_for(N), 256, 0, c->stream>>>(part.meta.as<uint2>(), int64_t(N), part.W.as<uint32_t>());
+            c->launches++;
+        }
+        MCG_TRY(exclusive_scan_u32_to_u32(c, part.W.as<uint32_t>(), part.W.as<uint32_t>(), N));
+    }
+    if(N == 0) { c->h_left[slot] = 0; MCG_CUDA(cudaEventRecord(part.evA, c->stream)); return MCG_OK; }
+    const double spr = est_slots_per_read(o, b1, b2, std::max<int64_t>(n_loc, 1), d2 != nullptr);
+    return qa_fused(db, o, part, slot, int64_t(N), n_loc > 0 ? spr : 64.0, part.lt.as<int32_t>(), part.lh.as<uint32_t>(), part.ln.as<int32_t>());
+}
+
+// stage B of part j: left-over reads, exchange of the per-read lists, merge + decision of the own block
+static int qs_stage_b(mcg_db* db, mcg_comm* comm, const mcg_query_opts* o, const ShardPlan& pl, int j, int slot,
+                      int32_t* d_out_tax, uint32_t* d_out_hits, int32_t* d_out_n, int32_t* d_out_best, int32_t* d_out_brank,
+                      uint64_t* d_stats)
+{
+    mcg_ctx* c = db->ctx;
+    QPart& part = c->qp[slot];
+    const int P = pl.P, me = pl.me, K = o->maxcand;
+    uint64_t N = 0, nb = 0;
+    for(int r = 0; r < P; ++r) { if(r == me) nb = N; N += pl.rn(j, r); }
+    const uint64_t n_me = pl.rn(j, me);
+    if(N > 0) MCG_TRY(qb_leftovers(db, o, part, slot, int64_t(N), part.lt.as<int32_t>(), part.lh.as<uint32_t>(), part.ln.as<int32_t>()));
+    const int32_t* ct = part.lt.as<int32_t>();
+    const uint32_t* ch = part.lh.as<uint32_t>();
+    const int32_t* cn = part.ln.as<int32_t>();
+    if(P > 1) {
+        MCG_TRY(part.ct.reserve(size_t(P) * (n_me + 1) * K * 4)); MCG_TRY(part.ch.reserve(size_t(P) * (n_me + 1) * K * 4));
+        MCG_TRY(part.cn.reserve(size_t(P) * (n_me + 1) * 4));
+        std::vector<uint64_t> so(static_cast<size_t>(P)), sl(static_cast<size_t>(P)), ro(static_cast<size_t>(P)), rl(static_cast<size_t>(P));
+        for(int pass = 0; pass < 2; ++pass) {
+            const uint64_t row = pass == 0 ? uint64_t(K) * 4 : 4;       // bytes per read: lists, counts
+            uint64_t a = 0;
+            for(int r = 0; r < P; ++r) {
+                so[size_t(r)] = a * row; sl[size_t(r)] = pl.rn(j, r) * row; a += pl.rn(j, r);
+                ro[size_t(r)] = uint64_t(r) * n_me * row; rl[size_t(r)] = n_me * row;
+            }
+            if(pass == 0) {
+                MCG_TRY(comm_alltoallv(comm, part.lt.p, so.data(), sl.data(), part.ct.p, ro.data(), rl.data(), c->stream));
+                MCG_TRY(comm_alltoallv(comm, part.lh.p, so.data(), sl.data(), part.ch.p, ro.data(), rl.data(), c->stream));
+            } else {
+                MCG_TRY(comm_alltoallv(comm, part.ln.p, so.data(), sl.data(), part.cn.p, ro.data(), rl.data(), c->stream));
+            }
+        }
+        ct = part.ct.as<int32_t>(); ch = part.ch.as<uint32_t>(); cn = part.cn.as<int32_t>();
+    }
+    (void)nb;
+    if(n_me > 0)
+        MCG_TRY(mcg_merge_classify_dev(c, o, ct, ch, cn, P, int64_t(n_me), d_out_tax, d_out_hits, d_out_n, d_out_best, d_out_brank, d_stats));
+    MCG_CUDA(cudaEventRecord(part.evB, c->stream));
     return MCG_OK;
 }
 
@@ -1440,16 +1689,19 @@ int mcg_query_batch_dev(mcg_db* db, const mcg_query_opts* o,
                         int32_t* d_out_tax, uint32_t* d_out_hits, int32_t* d_out_ncand)
 {
     MCG_REQUIRE(db != nullptr && o != nullptr && d_reads1 != nullptr && d_offs1 != nullptr, "mcg_query_batch_dev: NULL argument");
-    MCG_REQUIRE(n >= 0, "n < 0");
-    (void)max_read_len;
-    return query_batch_dev(db, o, d_reads1, d_offs1, bytes1, d_reads2, d_offs2, bytes2, n,
-                           d_out_tax, d_out_hits, d_out_ncand, 0, nullptr);
+    MCG_REQUIRE(n >= 0 && n < (1ll << 31), "read count out of range");
+    MCG_CUDA(cudaSetDevice(db->ctx->device));
+    MCG_TRY(check_ready(db, o));
+    if(n == 0) return MCG_OK;
+    MCG_TRY(ensure_pipeline(db->ctx));
+    return query_batch_dev(db, o, d_reads1, d_offs1, bytes1, d_reads2, d_offs2, d_reads2 ? bytes2 : 0, n, max_read_len,
+                           d_out_tax, d_out_hits, d_out_ncand, 0, true);
 }
 
-// Host path.  The batch is cut into sub-batches: while sub-batch i is queried (ctx stream), the
-// reads of sub-batch i+1 are copied in (H2D stream, second staging buffer) and the top lists of
-// sub-batch i-1 travel back (D2H stream) -- PCIe is full duplex, so the call costs about the H2D
-// copy of the reads instead of H2D + query + D2H.
+// Host path.  The batch is cut into parts: while part i is queried (ctx stream), the reads of part
+// i+1 are copied in (H2D stream, second staging buffer) and the top lists of part i-1 travel back
+// (D2H stream) -- PCIe is full duplex, so the call costs about the H2D copy of the reads instead of
+// H2D + query + D2H.  The host looks at the left-over count of part i only after part i+1 is enqueued.
 int mcg_query_batch(mcg_db* db, const mcg_query_opts* o,
                     const char* reads1, const int64_t* offs1,
                     const char* reads2, const int64_t* offs2, int64_t n,
@@ -1463,7 +1715,7 @@ int mcg_query_batch(mcg_db* db, const mcg_query_opts* o,
     if(reads2 != nullptr) MCG_REQUIRE(offs2 != nullptr && offs2[0] == 0, "offs2[0] must be 0");
     mcg_ctx* c = db->ctx;
     MCG_CUDA(cudaSetDevice(c->device));
-    MCG_TRY(check_opts(db, o));
+    MCG_TRY(check_ready(db, o));
     MCG_TRY(ensure_pipeline(c));
     const int K = o->maxcand;
     static int64_t sub_reads = -1;
@@ -1502,10 +1754,25 @@ int mcg_query_batch(mcg_db* db, const mcg_query_opts* o,
         MCG_CUDA(cudaEventRecord(c->ev_h2d[slot], c->s_h2d));
         return MCG_OK;
     };
+    // stage B of part i: left-over reads, then the lists travel back
+    auto finish = [&](int64_t i) -> int {
+        const int slot = int(i & 1);
+        const int64_t a = i * sub_reads, b = std::min(n, a + sub_reads);
+        MCG_TRY(qb_leftovers(db, o, c->qp[slot], slot, b - a, c->q_out_tax.as<int32_t>() + a * K, c->q_out_hits.as<uint32_t>() + a * K,
+                             c->q_out_n.as<int32_t>() + a));
+        MCG_CUDA(cudaEventRecord(c->ev_k[slot], c->stream));
+        MCG_CUDA(cudaStreamWaitEvent(c->s_d2h, c->ev_k[slot], 0));
+        MCG_CUDA(cudaMemcpyAsync(out_tax + a * K, c->q_out_tax.as<int32_t>() + a * K, size_t(b - a) * K * 4, cudaMemcpyDeviceToHost, c->s_d2h));
+        MCG_CUDA(cudaMemcpyAsync(out_hits + a * K, c->q_out_hits.as<uint32_t>() + a * K, size_t(b - a) * K * 4, cudaMemcpyDeviceToHost, c->s_d2h));
+        MCG_CUDA(cudaMemcpyAsync(out_ncand + a, c->q_out_n.as<int32_t>() + a, size_t(b - a) * 4, cudaMemcpyDeviceToHost, c->s_d2h));
+        return MCG_OK;
+    };
     MCG_TRY(stage(0));
     for(int64_t i = 0; i < nsub; ++i) {
         const int slot = int(i & 1);
         const int64_t a = i * sub_reads, b = std::min(n, a + sub_reads);
+        // (the staging buffer of part i+1 is the one part i-1 used: its stage B must be enqueued first)
+        if(i >= 1) MCG_TRY(finish(i - 1));
         if(i + 1 < nsub) MCG_TRY(stage(i + 1));
         MCG_CUDA(cudaStreamWaitEvent(c->stream, c->ev_h2d[slot], 0));
         // the offsets keep their values of the whole batch: the base pointers are moved instead
@@ -1513,15 +1780,11 @@ int mcg_query_batch(mcg_db* db, const mcg_query_opts* o,
         const int64_t* do1 = c->seqoff.as<int64_t>() + size_t(slot) * 2 * offsz;
         const char* d2 = reads2 ? c->seq.as<char>() + size_t(slot) * bufsz + pad1 - offs2[a] : nullptr;
         const int64_t* do2 = reads2 ? do1 + offsz : nullptr;
-        MCG_TRY(query_batch_dev(db, o, d1, do1, offs1[b] - offs1[a], d2, do2, reads2 ? offs2[b] - offs2[a] : 0, b - a,
+        MCG_TRY(query_batch_dev(db, o, d1, do1, offs1[b] - offs1[a], d2, do2, reads2 ? offs2[b] - offs2[a] : 0, b - a, 0,
                                 c->q_out_tax.as<int32_t>() + a * K, c->q_out_hits.as<uint32_t>() + a * K,
-                                c->q_out_n.as<int32_t>() + a, 0, nullptr));
-        MCG_CUDA(cudaEventRecord(c->ev_k[slot], c->stream));
-        MCG_CUDA(cudaStreamWaitEvent(c->s_d2h, c->ev_k[slot], 0));
-        MCG_CUDA(cudaMemcpyAsync(out_tax + a * K, c->q_out_tax.as<int32_t>() + a * K, size_t(b - a) * K * 4, cudaMemcpyDeviceToHost, c->s_d2h));
-        MCG_CUDA(cudaMemcpyAsync(out_hits + a * K, c->q_out_hits.as<uint32_t>() + a * K, size_t(b - a) * K * 4, cudaMemcpyDeviceToHost, c->s_d2h));
-        MCG_CUDA(cudaMemcpyAsync(out_ncand + a, c->q_out_n.as<int32_t>() + a, size_t(b - a) * 4, cudaMemcpyDeviceToHost, c->s_d2h));
+                                c->q_out_n.as<int32_t>() + a, slot, false));
     }
+    MCG_TRY(finish(nsub - 1));
     MCG_CUDA(cudaStreamSynchronize(c->s_d2h));
     MCG_CUDA(cudaStreamSynchronize(c->stream));
     return MCG_OK;
@@ -1537,7 +1800,7 @@ int mcg_query_matches(mcg_db* db, const mcg_query_opts* o,
     if(n == 0) return MCG_OK;
     mcg_ctx* c = db->ctx;
     MCG_CUDA(cudaSetDevice(c->device));
-    MCG_TRY(check_opts(db, o));
+    MCG_TRY(check_ready(db, o));
     const char *d1, *d2; const int64_t *do1, *do2; int64_t b1, b2;
     MCG_TRY(stage_reads(c, reads1, offs1, reads2, offs2, n, &d1, &do1, &b1, &d2, &do2, &b2));
     const int K = o->maxcand;
@@ -1545,10 +1808,10 @@ int mcg_query_matches(mcg_db* db, const mcg_query_opts* o,
     MCG_TRY(c->q_out_hits.reserve(size_t(n) * K * 4));
     MCG_TRY(c->q_out_n.reserve(size_t(n) * 4));
     QueryRun run;
-    MCG_TRY(query_batch_dev(db, o, d1, do1, b1, d2, do2, b2, n, c->q_out_tax.as<int32_t>(), c->q_out_hits.as<uint32_t>(),
-                            c->q_out_n.as<int32_t>(), 1, &run));
+    MCG_TRY(query_staged_sorted(db, o, d1, do1, b1, d2, do2, b2, n, c->q_out_tax.as<int32_t>(), c->q_out_hits.as<uint32_t>(),
+                                c->q_out_n.as<int32_t>(), &run));
     MCG_TRY(c->m_tax.reserve(size_t(n) * 8));
-    q_read_counts_kernel<<<grid_for(n), 256, 0, c->stream>>>(c->q_fpos.as<uint64_t>(), c->tmp2.as<uint32_t>(), o->sketchlen, n,
+    q_read_counts_kernel<<<grid_for(n), 256, 0, c->stream>>>(c->q_fpos.as<uint64_t>(), run.W, o->sketchlen, n,
                                                             c->m_tax.as<int64_t>());
     c->launches++;
     MCG_TRY(copy_out(c, out_counts, c->m_tax.p, size_t(n) * 8));
@@ -1638,6 +1901,140 @@ int mcg_merge_classify(mcg_ctx* c, const mcg_query_opts* o,
         set_error("mcg_merge_classify: %s", (bad & 1u) ? "candidate taxon outside [-1, ntaxa)" : "candidate count outside [0, maxcand]");
         return MCG_ERR_ARG;
     }
+    if(out_stats22) for(int i = 0; i < 22; ++i) out_stats22[i] += st[i];
+    return MCG_OK;
+}
+
+
+int mcg_query_batch_sharded_dev(mcg_db* db, mcg_comm* comm, const mcg_query_opts* o,
+                                const char* d_reads1, const int64_t* d_offs1, int64_t bytes1,
+                                const char* d_reads2, const int64_t* d_offs2, int64_t bytes2,
+                                int64_t n_local, int64_t max_read_len,
+                                int32_t* d_out_tax, uint32_t* d_out_hits, int32_t* d_out_ncand,
+                                int32_t* d_out_best, int32_t* d_out_best_rank, uint64_t* d_stats22)
+{
+    MCG_REQUIRE(db != nullptr && o != nullptr, "mcg_query_batch_sharded_dev: NULL argument");
+    MCG_REQUIRE(n_local >= 0 && n_local < (1ll << 31), "read count out of range");
+    MCG_REQUIRE(n_local == 0 || (d_reads1 != nullptr && d_offs1 != nullptr), "reads are NULL");
+    MCG_REQUIRE(d_out_tax && d_out_hits && d_out_ncand && d_out_best && d_out_best_rank, "device output arrays are NULL");
+    mcg_ctx* c = db->ctx;
+    MCG_CUDA(cudaSetDevice(c->device));
+    MCG_TRY(check_ready(db, o));
+    MCG_TRY(ensure_pipeline(c));
+    if(comm_size(comm) == 1 && n_local == 0) return MCG_OK;
+    ShardPlan pl;
+    MCG_TRY(qs_plan(db, comm, o, d_offs1, d_reads2 ? d_offs2 : nullptr, n_local, 1, &pl));
+    MCG_TRY(qs_stage_a(db, comm, o, pl, 0, 0, d_reads1, d_offs1, bytes1, d_reads2, d_reads2 ? d_offs2 : nullptr, d_reads2 ? bytes2 : 0, max_read_len));
+    return qs_stage_b(db, comm, o, pl, 0, 0, d_out_tax, d_out_hits, d_out_ncand, d_out_best, d_out_best_rank, d_stats22);
+}
+
+int mcg_query_batch_sharded(mcg_db* db, mcg_comm* comm, const mcg_query_opts* o,
+                            const char* reads1, const int64_t* offs1,
+                            const char* reads2, const int64_t* offs2, int64_t n,
+                            int32_t* out_tax, uint32_t* out_hits, int32_t* out_ncand,
+                            int32_t* out_best, int32_t* out_best_rank, uint64_t* out_stats22)
+{
+    MCG_REQUIRE(db != nullptr && o != nullptr, "mcg_query_batch_sharded: NULL argument");
+    MCG_REQUIRE(n >= 0 && n < (1ll << 31), "read count out of range");
+    MCG_REQUIRE(n == 0 || (reads1 != nullptr && offs1 != nullptr && offs1[0] == 0), "reads1 / offs1 (offs1[0] must be 0)");
+    if(reads2 != nullptr) MCG_REQUIRE(offs2 != nullptr && offs2[0] == 0, "offs2[0] must be 0");
+    mcg_ctx* c = db->ctx;
+    MCG_CUDA(cudaSetDevice(c->device));
+    MCG_TRY(check_ready(db, o));
+    MCG_TRY(ensure_pipeline(c));
+    const int P = comm_size(comm);
+    if(P == 1 && n == 0) return MCG_OK;
+    const int K = o->maxcand;
+    static const int64_t sub_reads = [] { const char* e = getenv("MCG_QUERY_SUB"); const int64_t v = e ? atoll(e) : 262144; return v < 1 ? int64_t(1) : v; }();
+    static const int np_env = getenv("MCG_SHARD_PARTS") ? atoi(getenv("MCG_SHARD_PARTS")) : 4;
+    const bool paired = reads2 != nullptr;
+    // the offsets of the whole slice go to the device first (the plan needs them), the bases follow part by part
+    static const int64_t zero_off[1] = {0};
+    if(n == 0) { offs1 = zero_off; offs2 = zero_off; }
+    MCG_TRY(c->seqoff.reserve(2 * size_t(n + 1) * 8));
+    int64_t* do1 = c->seqoff.as<int64_t>();
+    int64_t* do2 = do1 + (n + 1);
+    MCG_CUDA(cudaEventRecord(c->ev_misc, c->stream));
+    MCG_CUDA(cudaStreamWaitEvent(c->s_h2d, c->ev_misc, 0));     // staging buffers are ours from here on
+    MCG_CUDA(cudaStreamWaitEvent(c->s_d2h, c->ev_misc, 0));
+    MCG_CUDA(cudaMemcpyAsync(do1, offs1, size_t(n + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+    if(paired) MCG_CUDA(cudaMemcpyAsync(do2, offs2, size_t(n + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+    int np_want = P == 1 ? int(std::min<int64_t>(QS_MAX_PARTS, std::max<int64_t>(1, (n + sub_reads - 1) / sub_reads)))
+                         : std::max(1, std::min(np_env, QS_MAX_PARTS));
+    ShardPlan pl;
+    MCG_TRY(qs_plan(db, comm, o, do1, paired ? do2 : nullptr, n, np_want, &pl));
+    const int np = pl.np, me = pl.me;
+    // part j of the own slice = reads [lo(j), lo(j + 1))
+    std::vector<int64_t> lo(size_t(np) + 1, 0);
+    for(int j = 0; j < np; ++j) lo[size_t(j) + 1] = lo[size_t(j)] + int64_t(pl.rn(j, me));
+    int64_t maxb1 = 0, maxb2 = 0, maxn = 0;
+    for(int j = 0; j < np; ++j) {
+        maxb1 = std::max(maxb1, offs1[lo[size_t(j) + 1]] - offs1[lo[size_t(j)]]);
+        if(paired) maxb2 = std::max(maxb2, offs2[lo[size_t(j) + 1]] - offs2[lo[size_t(j)]]);
+        maxn = std::max(maxn, lo[size_t(j) + 1] - lo[size_t(j)]);
+    }
+    const size_t pad1 = (size_t(maxb1) + 127) & ~size_t(63);
+    const size_t bufsz = pad1 + ((size_t(maxb2) + 127) & ~size_t(63));
+    MCG_TRY(c->seq.reserve(2 * bufsz + 64));
+    MCG_TRY(c->m_stats.reserve(22 * 8));
+    MCG_CUDA(cudaMemsetAsync(c->m_stats.p, 0, 22 * 8, c->stream));
+    for(int sl = 0; sl < 2; ++sl) {
+        QPart& q = c->qp[sl];
+        MCG_TRY(q.mt.reserve(size_t(maxn + 1) * K * 4)); MCG_TRY(q.mh.reserve(size_t(maxn + 1) * K * 4)); MCG_TRY(q.mn.reserve(size_t(maxn + 1) * 4));
+        MCG_TRY(q.mbest.reserve(size_t(maxn + 1) * 4)); MCG_TRY(q.mbrank.reserve(size_t(maxn + 1) * 4));
+    }
+    MCG_CUDA(cudaEventRecord(c->ev_misc, c->stream));
+    MCG_CUDA(cudaStreamWaitEvent(c->s_h2d, c->ev_misc, 0));     // (allocations above may have recycled blocks)
+    auto stage = [&](int j) -> int {
+        const int slot = j & 1;
+        const int64_t a = lo[size_t(j)], b = lo[size_t(j) + 1];
+        char* dbuf = c->seq.as<char>() + size_t(slot) * bufsz;
+        if(j >= 2) MCG_CUDA(cudaStreamWaitEvent(c->s_h2d, c->ev_k[slot], 0));      // the buffer's previous user is done
+        if(b > a) {
+            MCG_CUDA(cudaMemcpyAsync(dbuf, reads1 + offs1[a], size_t(offs1[b] - offs1[a]), cudaMemcpyHostToDevice, c->s_h2d));
+            if(paired) MCG_CUDA(cudaMemcpyAsync(dbuf + pad1, reads2 + offs2[a], size_t(offs2[b] - offs2[a]), cudaMemcpyHostToDevice, c->s_h2d));
+        }
+        MCG_CUDA(cudaEventRecord(c->ev_h2d[slot], c->s_h2d));
+        return MCG_OK;
+    };
+    auto finish = [&](int j) -> int {
+        const int slot = j & 1;
+        QPart& q = c->qp[slot];
+        const int64_t a = lo[size_t(j)], b = lo[size_t(j) + 1];
+        MCG_TRY(qs_stage_b(db, comm, o, pl, j, slot, q.mt.as<int32_t>(), q.mh.as<uint32_t>(), q.mn.as<int32_t>(), q.mbest.as<int32_t>(),
+                           q.mbrank.as<int32_t>(), c->m_stats.as<uint64_t>()));
+        MCG_CUDA(cudaEventRecord(c->ev_k[slot], c->stream));
+        MCG_CUDA(cudaStreamWaitEvent(c->s_d2h, c->ev_k[slot], 0));
+        const size_t m = size_t(b - a);
+        if(m > 0) {
+            if(out_tax) MCG_CUDA(cudaMemcpyAsync(out_tax + a * K, q.mt.p, m * K * 4, cudaMemcpyDeviceToHost, c->s_d2h));
+            if(out_hits) MCG_CUDA(cudaMemcpyAsync(out_hits + a * K, q.mh.p, m * K * 4, cudaMemcpyDeviceToHost, c->s_d2h));
+            if(out_ncand) MCG_CUDA(cudaMemcpyAsync(out_ncand + a, q.mn.p, m * 4, cudaMemcpyDeviceToHost, c->s_d2h));
+            if(out_best) MCG_CUDA(cudaMemcpyAsync(out_best + a, q.mbest.p, m * 4, cudaMemcpyDeviceToHost, c->s_d2h));
+            if(out_best_rank) MCG_CUDA(cudaMemcpyAsync(out_best_rank + a, q.mbrank.p, m * 4, cudaMemcpyDeviceToHost, c->s_d2h));
+        }
+        MCG_CUDA(cudaEventRecord(c->ev_h2d[2 + slot], c->s_d2h));      // the merged results of this slot have left the device
+        return MCG_OK;
+    };
+    MCG_TRY(stage(0));
+    for(int j = 0; j < np; ++j) {
+        const int slot = j & 1;
+        const int64_t a = lo[size_t(j)], b = lo[size_t(j) + 1];
+        if(j >= 1) MCG_TRY(finish(j - 1));
+        if(j + 1 < np) MCG_TRY(stage(j + 1));
+        MCG_CUDA(cudaStreamWaitEvent(c->stream, c->ev_h2d[slot], 0));
+        if(j >= 2) MCG_CUDA(cudaStreamWaitEvent(c->stream, c->ev_h2d[2 + slot], 0));   // q.m* of this slot are free again
+        // the offsets keep their values of the whole slice: the base pointers are moved instead
+        const char* d1 = c->seq.as<char>() + size_t(slot) * bufsz - offs1[a];
+        const char* d2 = paired ? c->seq.as<char>() + size_t(slot) * bufsz + pad1 - offs2[a] : nullptr;
+        MCG_TRY(qs_stage_a(db, comm, o, pl, j, slot, d1, do1 + a, offs1[b] - offs1[a], d2, paired ? do2 + a : nullptr,
+                           paired ? offs2[b] - offs2[a] : 0, 0));
+    }
+    MCG_TRY(finish(np - 1));
+    uint64_t st[22];
+    MCG_CUDA(cudaMemcpyAsync(st, c->m_stats.p, 22 * 8, cudaMemcpyDeviceToHost, c->stream));
+    MCG_CUDA(cudaStreamSynchronize(c->s_d2h));
+    MCG_CUDA(cudaStreamSynchronize(c->stream));
     if(out_stats22) for(int i = 0; i < 22; ++i) out_stats22[i] += st[i];
     return MCG_OK;
 }

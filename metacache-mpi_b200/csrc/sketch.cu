@@ -242,7 +242,8 @@ sketch_kernel(const SketchParams p)
     int32_t*  tabs = reinterpret_cast<int32_t*>(tmp + 32);   // 2 x (4 * wpt + 2)
     const int wpt = p.wpc;
     const int tabsz = 4 * wpt + 2;
-    const uint64_t ntiles = (p.nwin - p.win_lo + wpt - 1) / wpt;
+    const uint64_t nwin_end = sk_nwin(p);
+    const uint64_t ntiles = nwin_end > p.win_lo ? (nwin_end - p.win_lo + wpt - 1) / wpt : 0;
     const uint64_t nwarps = uint64_t(gridDim.x) * SK_WARPS;
     const uint64_t gw = uint64_t(blockIdx.x) * SK_WARPS + warp;
 
@@ -251,7 +252,7 @@ sketch_kernel(const SketchParams p)
         int32_t* tb = tabs + stage * tabsz;
         uint32_t* tbu = reinterpret_cast<uint32_t*>(tb);
         const uint64_t g0 = p.win_lo + tile * uint64_t(wpt);
-        const int nw = int(min(uint64_t(wpt), p.nwin - g0));
+        const int nw = int(min(uint64_t(wpt), nwin_end - g0));
         int64_t first_abs = 0, last_end = 0;
         const uint32_t q0 = p.cta_seq[tile];
         const uint32_t wf0 = p.win_first[q0], wf1 = p.win_first[q0 + 1];
@@ -491,7 +492,8 @@ int sketch_config(const mcg_sketch_cfg& cfg, int sketchlen, int64_t winlen, int6
 int sketch_launch(mcg_ctx* c, const mcg_sketch_cfg& cfg, int sketchlen, int64_t winlen, int64_t stride,
                   const char* d_seq, int64_t total_bytes, const int64_t* d_seq_off, int64_t nseq,
                   const uint32_t* d_win_first, const uint32_t* d_out_first, uint64_t nwin,
-                  uint32_t* d_out_feat, uint32_t* d_out_cnt, uint64_t win_lo, cudaStream_t stream, uint32_t* d_tile_scratch)
+                  uint32_t* d_out_feat, uint32_t* d_out_cnt, uint64_t win_lo, cudaStream_t stream, uint32_t* d_tile_scratch,
+                  const uint32_t* d_nwin)
 {
     if(nwin <= win_lo) return MCG_OK;
     if(stream == nullptr) stream = c->stream;
@@ -507,6 +509,7 @@ int sketch_launch(mcg_ctx* c, const mcg_sketch_cfg& cfg, int sketchlen, int64_t 
     p.win_first = d_win_first;
     p.out_first = d_out_first;
     p.nwin = nwin;
+    p.nwin_dev = d_nwin;
     p.win_lo = win_lo;
     {
         const int nk = int(winlen) - cfg.k + 1;

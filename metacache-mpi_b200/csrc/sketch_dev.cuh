@@ -18,7 +18,8 @@ struct SketchParams {
     const uint32_t* win_first;   // [nseq+1] window prefix in processing order
     const uint32_t* out_first;   // [nseq]   output index of each sequence's first window
     const uint32_t* cta_seq;     // [ntiles+1] sequence holding the first window of each tile
-    uint64_t nwin;               // end of the window range of this launch (global window index)
+    uint64_t nwin;               // end of the window range of this launch (global window index) -- or an upper bound of it
+    const uint32_t* nwin_dev;    // when non-null: the exact end on the device (callers that only know a bound on the host)
     uint64_t win_lo;             // first window of this launch
     uint32_t* out_feat;
     uint32_t* out_cnt;
@@ -34,6 +35,11 @@ struct SketchParams {
     uint32_t* tile_ctr;          // dynamic tile counter of the thread-per-window kernel (zeroed by cta_seq_kernel)
     uint32_t c65536;             // the constant 65536, opaque to the compiler (keeps x >> 16 as a multiply-high)
 };
+
+__device__ __forceinline__ uint64_t sk_nwin(const SketchParams& p)
+{
+    return p.nwin_dev ? min(p.nwin, uint64_t(__ldg(p.nwin_dev))) : p.nwin;
+}
 
 // The hash array holds the hash BEFORE its last xor-shift: y = ((x1>>16)^x1)*C, h = y ^ (y>>16).
 // h and y share their upper 16 bits, so "h < T" == "y < T" for thresholds that are multiples of

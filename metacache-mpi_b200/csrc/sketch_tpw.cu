@@ -185,7 +185,7 @@ __device__ __forceinline__ TwTile<R> tw_resolve(const SketchParams& p, uint64_t 
     TwTile<R> t;
     constexpr int WPT = TW_WPT * R;
     const uint64_t g0 = p.win_lo + tile * uint64_t(WPT);
-    const int nw = int(min(uint64_t(WPT), p.nwin - g0));
+    const int nw = int(min(uint64_t(WPT), sk_nwin(p) - g0));
     const int winlen = int(p.winlen), stride = int(p.stride);
     const int last_lane = (nw - 1) / R, last_round = (nw - 1) % R;
     int64_t first_abs, last_end;
@@ -272,7 +272,8 @@ sketch_tpw_kernel(const SketchParams p)
     uint32_t* list = reinterpret_cast<uint32_t*>(raw);                       // ... reused as [TW_LCAP][32] candidate columns
     uint2*    pk2  = reinterpret_cast<uint2*>(raw + rawcap);                 // [ngc + 2] {packed, ambiguity}
     uint32_t* tmp  = reinterpret_cast<uint32_t*>(pk2 + ngc + 2);             // [32]
-    const uint32_t ntiles = uint32_t((p.nwin - p.win_lo + TW_WPT * R - 1) / (TW_WPT * R));
+    const uint64_t nwin_end = sk_nwin(p);
+    const uint32_t ntiles = nwin_end > p.win_lo ? uint32_t((nwin_end - p.win_lo + TW_WPT * R - 1) / (TW_WPT * R)) : 0u;
     const int k = p.k;
     const uint32_t one = p.c65536 >> 16, m1 = 0u - one;      // 1 and -1, opaque to the compiler
 

@@ -203,3 +203,46 @@ def test_cli_hits_per_seq(tmp_path):
     run([sys.executable, SHIM, "-np", "2", "--", REF, "query", "rdb", "r1.fq", "r2.fq"] + flags +
         ["-threads", "1", "-query-limit", "300", "-out", "res_ref.txt"], d)
     assert mine == stable_lines(os.path.join(d, "res_ref.txt"))
+
+
+@pytest.mark.parametrize("golden,P,no_taxid,flags", [
+    ("cli_np2_default_flags.txt", 2, (), ["-pairfiles", "-tophits", "-queryids"]),
+    ("cli_np4_default_flags.txt", 4, (), ["-pairfiles", "-tophits", "-queryids"]),
+    ("cli_np2_mixed_lowest_species.txt", 2, (1, 4), QFLAGS),
+    ("cli_np4_mixed_lowest_species.txt", 4, (1, 4), QFLAGS),
+])
+def test_cli_reference_compat(tmp_path, golden, P, no_taxid, flags):
+    """`-reference-compat`: byte-identical output under the reference's DEFAULT flags (-lowest sequence), where
+    its uint32 wire format drops the sequence-level candidates of all ranks but the receiver (quirk Q1), at
+    np = 2 and along the reduction tree at np = 4; goldens printed by the reference binary"""
+    d = str(tmp_path)
+    make_files(d, no_taxid=no_taxid)
+    run([EXE, "build", "gdb", "genomes", "-taxonomy", "tax", "-gpus", str(P)], d)
+    run([EXE, "query", "gdb", "r1.fq", "r2.fq"] + flags + ["-reference-compat", "-out", "res_gpu.txt"], d)
+    mine = stable_lines(os.path.join(d, "res_gpu.txt"))
+    assert mine == open(os.path.join(ROOT, "tests", "golden", golden)).read().splitlines()
+    if os.path.exists(REF):
+        run([sys.executable, SHIM, "-np", str(P), "--", REF, "build", "rdb", "genomes", "-taxonomy", "tax"], d)
+        run([sys.executable, SHIM, "-np", str(P), "--", REF, "query", "rdb", "r1.fq", "r2.fq"] + flags +
+            ["-threads", "1", "-query-limit", "300", "-out", "res_ref.txt"], d)
+        assert mine == stable_lines(os.path.join(d, "res_ref.txt"))
+    # without the switch the restated semantics classify the reads of the other shards' genomes as well
+    run([EXE, "query", "gdb", "r1.fq", "r2.fq"] + flags + ["-out", "res_gpu_plain.txt"], d)
+    assert stable_lines(os.path.join(d, "res_gpu_plain.txt")) != mine
+
+
+def test_cli_unlimited_maxcand(tmp_path):
+    """-maxcand 0 = unlimited (query_options.cpp:176-178): accepted, lists up to 32 entries on the device; with 6
+    genomes no list is longer, so the output equals the reference's"""
+    d = str(tmp_path)
+    make_files(d)
+    run([EXE, "build", "gdb", "genomes", "-taxonomy", "tax", "-gpus", "2"], d)
+    flags = ["-pairfiles", "-lowest", "species", "-maxcand", "0", "-hitmin", "4", "-hitdiff", "80", "-tophits", "-queryids"]
+    run([EXE, "query", "gdb", "r1.fq", "r2.fq"] + flags + ["-out", "res_gpu.txt"], d)
+    mine = stable_lines(os.path.join(d, "res_gpu.txt"))
+    assert any("18446744073709551615 classification candidates" in l for l in mine)
+    if os.path.exists(REF):
+        run([sys.executable, SHIM, "-np", "2", "--", REF, "build", "rdb", "genomes", "-taxonomy", "tax"], d)
+        run([sys.executable, SHIM, "-np", "2", "--", REF, "query", "rdb", "r1.fq", "r2.fq"] + flags +
+            ["-threads", "1", "-query-limit", "300", "-out", "res_ref.txt"], d)
+        assert mine == stable_lines(os.path.join(d, "res_ref.txt"))

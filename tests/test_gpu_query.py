@@ -250,3 +250,54 @@ def test_fused_kernel_variants_agree(tmp_path):
         for k in ("ct", "ch", "cn"):
             assert (outs[0][k] == o[k]).all(), k
     assert (outs[0]["cn"] > 0).sum() > 1400
+
+
+@pytest.mark.parametrize("P", [2, 4, 8, 3])
+def test_reference_compat_merge(ctx, oracle, P):
+    """quirk Q1 (sequence-level taxa of other ranks lost on the uint32 wire, querying.h:958,984,1001) along the
+    reference's reduction tree: merge kernel == oracle, whose compat mode is pinned against the reference binary
+    (tests/test_oracle_cli_golden.py).  Targets 1 and 4 hang below no species, so at -lowest species lifted and
+    sequence-level candidates mix."""
+    w = World(G=8, L=30000, npairs=400, seed=17)
+    species = w.species.copy()
+    species[[1, 4]] = 0
+    from metacache_mpi_b200 import taxonomy
+    tabs = taxonomy.TaxonomyTables(w.ids, w.par, w.rk, species)
+    tax = po.TaxTables(tabs.lineage, tabs.rank, w.G)
+    ctx.upload_taxonomy(tabs.lineage, tabs.rank, w.G)
+    od = w.oracle_shards(oracle, P)
+    gd = w.gpu_shards(api, ctx, P)
+    differs = False
+    for maxcand, lowest, hitmin, hitdiff in CONFIGS + [(32, 4, 2, 0.3)]:
+        res = {}
+        for compat in (0, 1):
+            q = api.make_query_opts(maxcand=maxcand, lowest=lowest, hitmin=hitmin, hitdiff=hitdiff, reference_compat=compat)
+            oq = po.make_qopt(maxcand=maxcand, lowest=lowest, hitmin=hitmin, hitdiff=hitdiff, reference_compat=compat)
+            ct, ch, cn, mt, mh, mn, best, brank, stats = _gpu_full(ctx, gd, q, w.b1, w.o1, w.b2, w.o2)
+            et, eh, en, eb, er, es = oracle.query_batch(od, tax, oq, w.b1, w.o1, w.b2, w.o2)
+            assert (mn == en).all() and (mt == et).all() and (mh == eh).all()
+            assert (best == eb).all() and (brank == er).all() and (stats == es).all()
+            res[compat] = best.copy()
+        differs |= bool((res[0] != res[1]).any())
+    assert differs
+
+
+def test_query_argument_checks(ctx, oracle):
+    """a shard whose target ids exceed the uploaded taxonomy, candidate taxa outside the tables and negative
+    thresholds are refused instead of read out of bounds"""
+    w = World(G=6, L=20000, npairs=20)
+    gd = w.gpu_shards(api, ctx, 1)
+    ctx.upload_taxonomy(w.tabs.lineage[:], w.tabs.rank[:], 3)          # taxonomy knows 3 of the 6 targets
+    q = api.make_query_opts(maxcand=4, lowest=4, hitmin=4, hitdiff=0.8)
+    with pytest.raises(api.McgError, match="target id"):
+        gd[0].query_batch(q, w.b1, w.o1, w.b2, w.o2)
+    ctx.upload_taxonomy(w.tabs.lineage, w.tabs.rank, w.G)
+    with pytest.raises(api.McgError, match="hitmin"):
+        gd[0].query_batch(api.make_query_opts(hitmin=-1), w.b1, w.o1, w.b2, w.o2)
+    ct = np.full((1, 4, 4), -1, np.int32); ch = np.zeros((1, 4, 4), np.uint32); cn = np.ones((1, 4), np.int32)
+    ct[0, :, 0] = 10 ** 6
+    ch[0, :, 0] = 9
+    with pytest.raises(api.McgError, match="taxon"):
+        ctx.merge_classify(q, ct, ch, cn)
+    ct[0, :, 0] = 0
+    ctx.merge_classify(q, ct, ch, cn)                                   # the flag does not stick
