@@ -108,6 +108,10 @@ int64_t mcg_ctx_launches(mcg_ctx*);
 /* device memory helpers for callers that keep data resident (bench, tests) */
 int  mcg_dev_alloc(mcg_ctx*, int64_t bytes, void** dptr);
 int  mcg_dev_free(mcg_ctx*, void* dptr);
+/* page-locked host memory for callers without a CUDA runtime of their own (the host driver's read and result
+ * buffers): copies from / to it run asynchronously and at full PCIe rate */
+int  mcg_host_alloc(int64_t bytes, void** hptr);
+int  mcg_host_free(void* hptr);
 int  mcg_memcpy_h2d(mcg_ctx*, void* dptr, const void* hptr, int64_t bytes);
 int  mcg_memcpy_d2h(mcg_ctx*, void* hptr, const void* dptr, int64_t bytes);
 

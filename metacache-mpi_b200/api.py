@@ -66,6 +66,8 @@ def load_library():
     L.mcg_ctx_launches.argtypes = [vp]
     L.mcg_dev_alloc.argtypes = [vp, i64, C.POINTER(vp)]
     L.mcg_dev_free.argtypes = [vp, vp]
+    L.mcg_host_alloc.argtypes = [i64, C.POINTER(vp)]
+    L.mcg_host_free.argtypes = [vp]
     L.mcg_memcpy_h2d.argtypes = [vp, vp, vp, i64]
     L.mcg_memcpy_d2h.argtypes = [vp, vp, vp, i64]
     L.mcg_count_windows.restype = i64

@@ -279,6 +279,25 @@ int mcg_dev_free(mcg_ctx* c, void* dptr)
     return MCG_OK;
 }
 
+int mcg_host_alloc(int64_t bytes, void** hptr)
+{
+    MCG_REQUIRE(hptr != nullptr && bytes >= 0, "mcg_host_alloc: bad argument");
+    *hptr = nullptr;
+    cudaError_t e = cudaHostAlloc(hptr, size_t(bytes) + 64, cudaHostAllocPortable);
+    if(e != cudaSuccess) {
+        cudaGetLastError();
+        set_error("cudaHostAlloc(%lld) failed: %s", (long long)bytes, cudaGetErrorString(e));
+        return MCG_ERR_NOMEM;
+    }
+    return MCG_OK;
+}
+
+int mcg_host_free(void* hptr)
+{
+    if(hptr != nullptr) MCG_CUDA(cudaFreeHost(hptr));
+    return MCG_OK;
+}
+
 int mcg_memcpy_h2d(mcg_ctx* c, void* dptr, const void* hptr, int64_t bytes)
 {
     MCG_REQUIRE(c != nullptr && bytes >= 0, "mcg_memcpy_h2d: bad argument");

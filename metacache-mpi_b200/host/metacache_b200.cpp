@@ -24,6 +24,7 @@
 // FASTA/FASTQ reading, NCBI taxonomy files, text output.  They are written from the formats the
 // reference reads and writes, not from its code.
 #include <algorithm>
+#include <array>
 #include <atomic>
 #include <fcntl.h>
 #include <memory>
@@ -663,6 +664,37 @@ void for_each_shard_parallel(int P, F f)
     for(auto& t : th) t.join();
 }
 
+// one NCCL rank per shard / GPU inside this process: the id is drawn once, the ranks join side by side
+std::vector<mcg_comm*> make_comms(int P)
+{
+    std::vector<mcg_comm*> comms(static_cast<size_t>(P), nullptr);
+    uint8_t id[MCG_COMM_ID_BYTES];
+    check(mcg_comm_get_id(id), "mcg_comm_get_id");
+    std::vector<std::thread> th;
+    for(int r = 0; r < P; ++r)
+        th.emplace_back([&, r] { check(mcg_comm_create(ctx_for_shard(r), id, r, P, &comms[size_t(r)]), "mcg_comm_create"); });
+    for(auto& t : th) t.join();
+    return comms;
+}
+
+// page-locked buffer (mcg_host_alloc) that grows and is freed with the process
+template<class T>
+struct PinnedBuf {
+    T* p = nullptr;
+    size_t cap = 0;
+    void reserve(size_t n)
+    {
+        if(n <= cap) return;
+        if(p) mcg_host_free(p);
+        cap = n + n / 4 + 64;
+        void* q = nullptr;
+        check(mcg_host_alloc(int64_t(cap * sizeof(T)), &q), "mcg_host_alloc");
+        p = static_cast<T*>(q);
+    }
+    T* data() { return p; }
+    T& operator[](size_t i) { return p[i]; }
+};
+
 double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 // phase timer on stderr (MCG_TRACE=1)
@@ -771,7 +803,18 @@ int mode_build(const Args& a)
     std::cout << "Added " << ntargets << " reference sequences (" << total_bp << " bp) in " << (t1 - t0) << " s" << std::endl;
     if(remove_over) {
         uint64_t rem = 0;
-        check(mcg_remove_overpopulated(dbs.data(), P, &rem), "mcg_remove_overpopulated");
+        if(P > 1 && P <= mcg_device_count()) {
+            // one shard per GPU: the reduction runs on the devices (pairs to their key owner over NVLink, removal list back)
+            std::vector<mcg_comm*> comms = make_comms(P);
+            std::vector<uint64_t> part(static_cast<size_t>(P), 0);
+            for_each_shard_parallel(P, [&](int r) {
+                check(mcg_db_remove_overpopulated_dist(dbs[size_t(r)], comms[size_t(r)], &part[size_t(r)], nullptr), "mcg_db_remove_overpopulated_dist");
+            });
+            for(uint64_t x : part) rem += x;
+            for(mcg_comm* m : comms) mcg_comm_destroy(m);
+        } else {
+            check(mcg_remove_overpopulated(dbs.data(), P, &rem), "mcg_remove_overpopulated");
+        }
         std::cout << rem << " overpopulated feature lists removed" << std::endl;
     }
     {
@@ -1088,44 +1131,81 @@ int mode_query(const Args& a)
     uint64_t stats[22] = {0};
     std::vector<uint64_t> tax_reads(tax_counts ? tt.tax.size() : 0, 0);      // reads per assigned taxon
     const size_t BATCH = size_t(1) << 20;
-    std::string b1, b2;
-    std::vector<int64_t> o1, o2;
-    std::vector<int32_t> ctax, cn, mtax, mn, best, brank;
-    std::vector<uint32_t> chits, mhits;
     const unsigned NT = host_threads();
-    for(size_t lo = 0; lo < nreads; lo += BATCH) {
+    // One shard per GPU (or a single shard): the whole cross-shard pipeline is ONE library call per GPU and batch --
+    // GPU r ingests slice r of the batch over its own PCIe link, the sketches travel by NCCL all-gather, the top
+    // lists by all-to-all, every GPU merges and classifies its slice.  More shards than GPUs (NCCL has one rank per
+    // device): every shard is queried with all reads, the lists are merged on GPU 0 from host arrays.
+    const bool sharded = P == 1 || P <= mcg_device_count();
+    std::vector<mcg_comm*> comms;
+    if(sharded && P > 1) comms = make_comms(P);
+    lap("communicator");
+    // two sets of batch buffers: batch i+1 is assembled and batch i-1 is formatted while batch i is on the GPUs
+    struct BatchBuf {
+        PinnedBuf<char> b1, b2;
+        PinnedBuf<int64_t> o1, o2;
+        PinnedBuf<int32_t> mtax, mn, best, brank;
+        PinnedBuf<uint32_t> mhits;
+        std::vector<int32_t> ctax, cn;          // unsharded path: per-shard lists
+        std::vector<uint32_t> chits;
+        size_t lo = 0, n = 0;
+        uint64_t stats[22] = {0};
+    } bufs[2];
+    auto assemble = [&](BatchBuf& B, size_t lo) {
         const size_t n = std::min(BATCH, nreads - lo);
-        // batch buffers: offsets first, then the bases are copied by all threads
-        o1.assign(n + 1, 0); o2.assign(paired ? n + 1 : 1, 0);
+        B.lo = lo; B.n = n;
+        B.o1.reserve(n + 1); B.o2.reserve(paired ? n + 1 : 1);
+        B.o1[0] = 0; B.o2[0] = 0;
         for(size_t i = 0; i < n; ++i) {
-            o1[i + 1] = o1[i] + int64_t(r1[lo + i].slen);
-            if(paired) o2[i + 1] = o2[i] + int64_t(r2[lo + i].slen);
+            B.o1[i + 1] = B.o1[i] + int64_t(r1[lo + i].slen);
+            if(paired) B.o2[i + 1] = B.o2[i] + int64_t(r2[lo + i].slen);
         }
-        b1.resize(size_t(o1[n])); b2.resize(paired ? size_t(o2[n]) : 0);
-        {
-            std::vector<std::thread> th;
-            for(unsigned t = 0; t < NT; ++t) th.emplace_back([&, t] {
-                const size_t ia = n * t / NT, ib = n * (t + 1) / NT;
-                for(size_t i = ia; i < ib; ++i) {
-                    std::memcpy(&b1[size_t(o1[i])], seq_of(r1[lo + i], txt1, extra1), r1[lo + i].slen);
-                    if(paired) std::memcpy(&b2[size_t(o2[i])], seq_of(r2[lo + i], txt2, extra2), r2[lo + i].slen);
-                }
-            });
-            for(auto& x : th) x.join();
-        }
-        lap("assemble batch");
-        ctax.resize(size_t(P) * n * K); chits.resize(size_t(P) * n * K); cn.resize(size_t(P) * n);
-        for_each_shard_parallel(P, [&](int r) {          // every GPU queries its shard(s) with all reads of the batch
-            check(mcg_query_batch(dbs[size_t(r)], &q, b1.data(), o1.data(), paired ? b2.data() : nullptr, paired ? o2.data() : nullptr,
-                                  int64_t(n), ctax.data() + size_t(r) * n * K, chits.data() + size_t(r) * n * K, cn.data() + size_t(r) * n),
-                  "mcg_query_batch");
+        B.b1.reserve(size_t(B.o1[n]) + 64); B.b2.reserve(paired ? size_t(B.o2[n]) + 64 : 64);
+        std::vector<std::thread> th;
+        for(unsigned t = 0; t < NT; ++t) th.emplace_back([&, t] {
+            const size_t ia = n * t / NT, ib = n * (t + 1) / NT;
+            for(size_t i = ia; i < ib; ++i) {
+                std::memcpy(B.b1.data() + B.o1[i], seq_of(r1[lo + i], txt1, extra1), r1[lo + i].slen);
+                if(paired) std::memcpy(B.b2.data() + B.o2[i], seq_of(r2[lo + i], txt2, extra2), r2[lo + i].slen);
+            }
         });
-        mtax.resize(n * K); mhits.resize(n * K); mn.resize(n); best.resize(n); brank.resize(n);
-        check(mcg_merge_classify(ctx_for_shard(0), &q, ctax.data(), chits.data(), cn.data(), P, int64_t(n), mtax.data(), mhits.data(),
-                                 mn.data(), best.data(), brank.data(), stats), "mcg_merge_classify");
-        lap("query batch (device)");
-        if(tax_counts) for(size_t i = 0; i < n; ++i) if(best[i] >= 0) ++tax_reads[size_t(best[i])];
-        if(o.map == 2) continue;
+        for(auto& x : th) x.join();
+        B.mtax.reserve(n * K); B.mhits.reserve(n * K); B.mn.reserve(n); B.best.reserve(n); B.brank.reserve(n);
+    };
+    auto run_gpu = [&](BatchBuf& B) {
+        const size_t n = B.n;
+        for(auto& x : B.stats) x = 0;
+        if(sharded) {
+            std::vector<std::array<uint64_t, 22>> part(static_cast<size_t>(P));
+            for_each_shard_parallel(P, [&](int r) {
+                const size_t a = n * size_t(r) / size_t(P), b = n * size_t(r + 1) / size_t(P);
+                part[size_t(r)].fill(0);
+                // slice r: offsets re-based to the slice (the library wants offs[0] == 0)
+                std::vector<int64_t> so1(b - a + 1), so2(paired ? b - a + 1 : 1);
+                for(size_t i = a; i <= b; ++i) { so1[i - a] = B.o1[i] - B.o1[a]; if(paired) so2[i - a] = B.o2[i] - B.o2[a]; }
+                check(mcg_query_batch_sharded(dbs[size_t(r)], P > 1 ? comms[size_t(r)] : nullptr, &q,
+                                              B.b1.data() + B.o1[a], so1.data(), paired ? B.b2.data() + B.o2[a] : nullptr,
+                                              paired ? so2.data() : nullptr, int64_t(b - a),
+                                              B.mtax.data() + a * K, B.mhits.data() + a * K, B.mn.data() + a, B.best.data() + a,
+                                              B.brank.data() + a, part[size_t(r)].data()), "mcg_query_batch_sharded");
+            });
+            for(auto& pr : part) for(int i = 0; i < 22; ++i) B.stats[i] += pr[size_t(i)];
+        } else {
+            B.ctax.resize(size_t(P) * n * K); B.chits.resize(size_t(P) * n * K); B.cn.resize(size_t(P) * n);
+            for_each_shard_parallel(P, [&](int r) {          // every GPU queries its shard(s) with all reads of the batch
+                check(mcg_query_batch(dbs[size_t(r)], &q, B.b1.data(), B.o1.data(), paired ? B.b2.data() : nullptr, paired ? B.o2.data() : nullptr,
+                                      int64_t(n), B.ctax.data() + size_t(r) * n * K, B.chits.data() + size_t(r) * n * K, B.cn.data() + size_t(r) * n),
+                      "mcg_query_batch");
+            });
+            check(mcg_merge_classify(ctx_for_shard(0), &q, B.ctax.data(), B.chits.data(), B.cn.data(), P, int64_t(n), B.mtax.data(), B.mhits.data(),
+                                     B.mn.data(), B.best.data(), B.brank.data(), B.stats), "mcg_merge_classify");
+        }
+    };
+    auto emit = [&](BatchBuf& B) {
+        const size_t n = B.n, lo = B.lo;
+        for(int i = 0; i < 22; ++i) stats[i] += B.stats[i];
+        if(tax_counts) for(size_t i = 0; i < n; ++i) if(B.best[i] >= 0) ++tax_reads[size_t(B.best[i])];
+        if(o.map == 2) return;
         // per-read lines: formatted by all threads into their own buffers, written in order
         std::vector<StrOut> parts(NT);
         {
@@ -1135,7 +1215,7 @@ int mode_query(const Args& a)
                 const size_t ia = n * t / NT, ib = n * (t + 1) / NT;
                 ls.s.reserve((ib - ia) * 96);
                 for(size_t i = ia; i < ib; ++i) {
-                    if(o.map == 1 && best[i] < 0) continue;
+                    if(o.map == 1 && B.best[i] < 0) continue;
                     if(o.queryids) ls << (lo + i + 1) << o.col;
                     const ReadRec& rr = r1[lo + i];
                     const char* h = (rr.in_extra ? extra1.data() : txt1.data()) + rr.hpos;
@@ -1143,26 +1223,41 @@ int mode_query(const Args& a)
                     ls.s.append(h, sp ? size_t(static_cast<const char*>(sp) - h) : rr.hlen);
                     ls << o.col;
                     if(o.tophits) {                                                     // printing.cpp:333-360
-                        for(int c = 0; c < mn[i] && mhits[i * K + c] > 0; ++c) {
+                        for(int c = 0; c < B.mn[i] && B.mhits[i * K + c] > 0; ++c) {
                             if(c > 0) ls << ',';
-                            const int32_t tx = mtax[i * K + c];
+                            const int32_t tx = B.mtax[i * K + c];
                             const Taxon* t2 = tt.tax[size_t(tx)];
                             if(q.lowest == 0) ls << t2->name;
                             else {
                                 const int32_t an = (t2->rank < q.lowest) ? tt.lineage[size_t(tx) * 21 + size_t(q.lowest)] : tx;
                                 if(an >= 0) ls << tt.taxid[size_t(an)]; else ls << t2->name;
                             }
-                            ls << ':' << mhits[i * K + c];
+                            ls << ':' << B.mhits[i * K + c];
                         }
                         ls << o.col;
                     }
-                    show_classification(ls, o, tt, best[i]);
+                    show_classification(ls, o, tt, B.best[i]);
                     ls << '\n';
                 }
             });
             for(auto& x : th) x.join();
         }
         for(auto& part : parts) os.write(part.s.data(), std::streamsize(part.s.size()));
+    };
+    {
+        const size_t nbatches = (nreads + BATCH - 1) / BATCH;
+        if(nbatches > 0) assemble(bufs[0], 0);
+        lap("assemble batch");
+        for(size_t bi = 0; bi < nbatches; ++bi) {
+            BatchBuf& B = bufs[bi & 1];
+            std::thread gpu([&] { run_gpu(B); });
+            // meanwhile on the host: the previous batch is written out, the next one assembled
+            if(bi >= 1) emit(bufs[(bi - 1) & 1]);
+            if(bi + 1 < nbatches) assemble(bufs[(bi + 1) & 1], (bi + 1) * BATCH);
+            gpu.join();
+            lap("query batch (device) || format previous / assemble next");
+        }
+        if(nbatches > 0) emit(bufs[(nbatches - 1) & 1]);
         lap("format + write output");
     }
     if(hits_per_seq)                                                            // printing.cpp:437-451, no rows (see above)
@@ -1209,6 +1304,7 @@ int mode_query(const Args& a)
             std::cerr << cm << "No valid query sequences found.\n";
         }
     }
+    for(mcg_comm* m : comms) mcg_comm_destroy(m);
     for(mcg_db* d : dbs) mcg_db_destroy(d);
     return 0;
 }
