@@ -4,31 +4,40 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl mcgpu|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-Headline (BASELINE.json configs[1]): sketching-only throughput of 1 Gbp of synthetic
-reference genomes at k=16 / sketchlen=16 / winlen=128 (stride 113), per GPU.  A "step" is one
-pass of the sketch path (window bookkeeping + K1) over that batch.
+Headline = BASELINE.json's first metric, QUERY reads/s, on configs[3] (paired-end 2 x 150 bp reads against the
+sharded database with the NCCL top-hit merge) over configs[2]'s database: 20 Gbp / 5000 genomes on 8 GPUs, i.e.
+2.5 Gbp (625 genomes x 4 Mbp) per GPU.  With N GPUs the database is N x 2.5 Gbp (weak scaling in database size,
+shard = target_id % N as in the reference); EVERY read is answered by EVERY shard, as in the reference.
+A "step" is one batch of 1 M read pairs (2 M reads) through the whole path: K1 sketch of the reads -> [all-gather
+of the sketches] -> table probe, gather, sort, window ranges, top list on every shard -> [all-to-all of the top
+lists] -> merge in rank order + decision + statistics.  The default 10 steps are 20 % of configs[3]'s 50 M pairs.
 
-  value : bp/s, whole job, inputs resident in HBM, CUDA events on the launching stream,
-          max over ranks.  With N > 1 every rank sketches its own 1 Gbp of genomes (the
-          reference partitions targets by target_id % ranks: no data-path collective) => weak.
-  e2e   : the same metric through the C-ABI call mcg_sketch_windows() with pinned HOST
-          buffers: H2D of the sequence bytes and D2H of the sketches inside the timed region.
-  roofline      : the sketch kernel against the measured HBM copy bandwidth
-                  (MEASURED_PEAKS.json) with 1.566 algorithmic bytes per bp.
-  cpu_baseline  : the reference's own sketcher (oracle/_ref, all host threads) on a bounded
-                  sample; a reported baseline, not the target.
-  build / query : extra objects: device-timed database build (bp/s) and query (reads/s) of
-                  the same path at a smaller synthetic size, with their own byte accounting;
-                  at N > 1 the query shards the database by target_id % N, every GPU queries
-                  all reads and the per-rank top lists are gathered over NCCL before the merge.
+  value : reads/s, whole job.  Every rank holds its 1/N slice of the batch resident in HBM; one step = one
+          mcg_query_batch_sharded_dev call per rank; CUDA events on the library's stream, max over ranks.
+  e2e   : the same through mcg_query_batch_sharded with pinned HOST slices: H2D of the reads and D2H of merged
+          lists / taxa inside the timed region, every rank over its own PCIe link.
+  roofline     : q_fused_warp_kernel (the dominant kernel) against the measured HBM copy bandwidth, its launch
+                 durations taken live with CUDA events around every launch inside the timed region
+                 (mcg_ctx_profile); algorithmic bytes per read pair = SURVEY 8(d): len1 + len2 + 32 F + 8 M + 8 K.
+  cpu_baseline : the reference PROGRAM (oracle/_ref/metacache_mpi_ref, `mpirun -np 2 -threads cores/2` through the
+                 FIFO shim) on a bounded sample: 32 genomes x 4 Mbp, 100 k pairs; its own `# time` line.
+  parity       : after timing, 2000 read pairs of the timed batch are answered by the oracle over the SAME
+                 database content (sketches of every genome of the shard, lists restricted to the sample's features)
+                 and compared with what the GPUs returned: lists, taxa, decision.
+  sketch / build / query_long : the other configs as extra objects with their own roofline / e2e / cpu_baseline.
 
---impl reference times the reference's CPU implementation of the headline path (rank 0 only).
+--impl reference times the reference program on the host cores (rank 0 only) on a bounded sample of the same
+workload and prints the same line with "impl": "reference".
 """
 import argparse
 import ctypes as C
 import json
 import os
+import re
+import shutil
+import subprocess
 import sys
+import tempfile
 import threading
 import time
 
@@ -39,21 +48,30 @@ sys.path.insert(0, ROOT)
 print_json = None
 
 K, S, WINLEN, STRIDE = 16, 16, 128, 113
-GENOME_LEN = 5_000_000
-ALG_BYTES_PER_BP = 1.0 + 4.0 * S / STRIDE        # 1 B in + 64 B per 113 bp out
-FALLBACK_HBM_GBS = 6650.0                         # B200_PROFILING.md fallback
+GLEN = 4_000_000                                    # configs[2]: ~5 k genomes, ~20 Gbp
+READLEN = 150
+KC = 4                                              # -maxcand 4
+QFLAGS = dict(maxcand=KC, lowest=4, hitmin=4, hitdiff=0.8)            # -lowest species -maxcand 4 -hitmin 4 -hitdiff 80
+ALG_SKETCH = 1.0 + 4.0 * S / STRIDE                # 1 B in + 64 B per 113 bp out
+FALLBACK_HBM_GBS = 6650.0                           # B200_PROFILING.md fallback
+REF_EXE = os.path.join(ROOT, "oracle", "_ref", "metacache_mpi_ref")
+SHIM = os.path.join(ROOT, "oracle", "mpirun_shim.py")
 
 
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=40)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="mcgpu", choices=["mcgpu", "reference"])
-    ap.add_argument("--mbp", type=int, default=1000, help="Mbp of reference genomes per GPU (default = configs[1])")
+    ap.add_argument("--db-mbp", type=int, default=2500, help="Mbp of reference genomes per GPU (default = configs[2] / 8)")
+    ap.add_argument("--pairs", type=int, default=1_000_000, help="read pairs per step, whole job")
     ap.add_argument("--e2e-steps", type=int, default=5)
-    ap.add_argument("--no-extras", action="store_true", help="skip the build/query extra objects")
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-extras", action="store_true", help="skip the sketch / build / long-read extra objects")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
+    ap.add_argument("--no-check", action="store_true", help="skip the oracle sample check")
+    ap.add_argument("--ref-genomes", type=int, default=32)
+    ap.add_argument("--ref-pairs", type=int, default=100_000)
     return ap.parse_args()
 
 
@@ -68,14 +86,12 @@ def hbm_peak():
 
 
 def load_traffic():
-    """dram bytes per bp of the sketch kernel from the committed ncu capture (profiles/traffic.json)"""
+    """DRAM bytes of the dominant kernels from the committed ncu captures (profiles/traffic.json)"""
     p = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(p):
-        try:
-            return json.load(open(p))
-        except Exception:
-            return {}
-    return {}
+    try:
+        return json.load(open(p))
+    except Exception:
+        return {}
 
 
 class ClockSampler:
@@ -138,51 +154,100 @@ class ClockSampler:
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
-def make_genome_block(first_genome, count, glen):
+def workload_name(args, world):
+    return ("query: batches of %d read pairs (2 x %d bp, %d reads) vs a %d x %.1f Gbp database (%d genomes x 4 Mbp, shard = "
+            "target_id %% %d, k=16 sketchlen=16 winlen=128; BASELINE.json configs[3] reads over configs[2]'s database: "
+            "20 Gbp / 8 per GPU); -lowest species -maxcand 4 -hitmin 4 -hitdiff 80"
+            % (args.pairs, READLEN, 2 * args.pairs, world, args.db_mbp / 1000.0, world * (args.db_mbp * 1_000_000 // GLEN), world))
+
+
+# ----------------------------------------------------------------------------- the reference program on the host cores
+def reference_program_run(args, steps, warmup, ngenomes, npairs, log=None):
+    """build (once) + `steps` query runs of the UNMODIFIED reference program under the MPI shim on a bounded sample
+    of the workload; returns a dict with its own timers.  Needs oracle/_ref (prebuilt, travels with the repo)."""
     from __graft_entry__ import load_package
     load_package()
     from metacache_mpi_b200 import synth
-    buf = np.empty(count * glen, np.uint8)
-    for i in range(count):
-        buf[i * glen:(i + 1) * glen] = synth.genome(first_genome + i, glen)
-    offs = np.arange(count + 1, dtype=np.int64) * glen
-    return buf, offs
+    import torch
+    if not os.path.exists(REF_EXE):
+        raise RuntimeError("oracle/_ref/metacache_mpi_ref is not built")
+    cores = os.cpu_count() or 1
+    np_ = max(2, args.gpus)                     # the reference classifies nothing at -np 1 (SURVEY 3.4 Q2)
+    T = max(1, cores // np_)
+    gen_dev = "cuda" if torch.cuda.is_available() else "cpu"       # data generation only
+    d = tempfile.mkdtemp(prefix="mcref_")
+    try:
+        genomes = torch.empty(ngenomes * GLEN, dtype=torch.uint8, device=gen_dev)
+        for g in range(ngenomes):
+            synth.genome_fast(g, GLEN, gen_dev, out=genomes[g * GLEN:(g + 1) * GLEN])
+        ids, par, rk, species = synth.make_taxonomy(ngenomes)
+        gh = genomes.cpu().numpy()
+        synth.write_genome_files(os.path.join(d, "genomes"), [gh[g * GLEN:(g + 1) * GLEN] for g in range(ngenomes)], species)
+        synth.write_taxonomy_files(os.path.join(d, "tax"), ids, par, rk)
+        b1, b2, gsel = synth.read_pairs_fast(genomes, GLEN, npairs)
+        offs = np.arange(npairs + 1, dtype=np.int64) * READLEN
+        synth.write_fastq_pair(os.path.join(d, "r1.fq"), os.path.join(d, "r2.fq"), b1.cpu().numpy(), offs, b2.cpu().numpy(), offs,
+                               gsel.cpu().numpy())
+        del genomes, b1, b2
+
+        def run(cmd):
+            r = subprocess.run(cmd, cwd=d, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+            if r.returncode != 0:
+                raise RuntimeError("reference run failed: %s\n%s" % (" ".join(cmd), r.stdout.decode()[-2000:]))
+            return r.stdout.decode()
+        t0 = time.perf_counter()
+        out = run([sys.executable, SHIM, "-np", str(np_), "--", REF_EXE, "build", "rdb", "genomes", "-taxonomy", "tax"])
+        build_wall = time.perf_counter() - t0
+        m = re.search(r"Added (\d+) reference sequences in ([0-9.eE+-]+) s", out)
+        build_added_s = float(m.group(2)) if m else None
+        qcmd = [sys.executable, SHIM, "-np", str(np_), "--", REF_EXE, "query", "rdb", "r1.fq", "r2.fq", "-pairfiles", "-lowest", "species",
+                "-maxcand", "4", "-hitmin", "4", "-hitdiff", "80", "-threads", str(T), "-query-limit", str((npairs + T - 1) // T),
+                "-out", "res.txt"]
+        times, nq = [], 0
+        for it in range(warmup + steps):
+            run(qcmd)
+            txt = open(os.path.join(d, "res.txt")).read()
+            mt = re.search(r"# time:\s+(\d+) ms", txt)
+            mq = re.search(r"# queries:\s+(\d+)", txt)
+            if it >= warmup:
+                times.append(float(mt.group(1)) * 1e-3)
+                nq = int(mq.group(1))
+            if log:
+                log("reference query run %d: %s ms" % (it, mt.group(1)))
+        cls = re.findall(r"#\s+(species|genus)\s+([0-9.]+)%", txt)
+        return {"np": np_, "threads": T, "cores": cores, "query_s": times, "queries": nq, "build_added_s": build_added_s,
+                "build_wall_s": build_wall, "build_bp": ngenomes * GLEN, "classified": dict(cls)}
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
 
 
-# ----------------------------------------------------------------------------- reference arm
+def reference_sample_text(r, ngenomes, npairs):
+    return ("the reference program (oracle/_ref/metacache_mpi_ref, unmodified sources, `mpirun -np %d` through the FIFO shim, "
+            "-threads %d: %d of %d host threads) on a bounded sample of the workload: database %d genomes x 4 Mbp (%d Mbp), "
+            "%d read pairs of the same generator per run; reads/s from its own '# time' line (rank 0, between barriers)"
+            % (r["np"], r["threads"], r["np"] * r["threads"], r["cores"], ngenomes, ngenomes * GLEN // 1_000_000, npairs))
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import pyoracle as po
-    cores = os.cpu_count() or 1
-    if po.have_reference():
-        impl, kind = po.Reference(), "reference"
-    else:
-        impl, kind = po.Oracle(), "port"
-    # bounded sample of the same workload: ~22 Mbp/s/core => a few seconds per step
-    sample_mbp = int(min(args.mbp, max(10, 16 * cores)))
-    G = max(sample_mbp // 5, 1)
-    buf, offs = make_genome_block(0, G, GENOME_LEN)
-    bp = int(offs[-1])
-    times = []
-    for it in range(args.warmup + args.steps):
-        t, cs, nw = impl.sketch_throughput(buf, offs, K, S, WINLEN, STRIDE, threads=cores)
-        if it >= args.warmup:
-            times.append(t)
-    tot = float(np.sum(times))
-    val = bp * len(times) / tot
+    steps, warmup = args.steps, min(args.warmup, 2)
+    r = reference_program_run(args, steps, warmup, args.ref_genomes, args.ref_pairs)
+    tot = float(np.sum(r["query_s"]))
+    val = r["queries"] * len(r["query_s"]) / tot
+    sample = reference_sample_text(r, args.ref_genomes, args.ref_pairs)
     line = {
-        "impl": "reference", "metric": "sketch_bp_per_s", "value": val, "unit": "bp/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / len(times),
+        "impl": "reference", "metric": "query_reads_per_s", "value": val, "unit": "reads/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / len(r["query_s"]),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-        "config": {"workload": "sketching-only: %d Mbp of synthetic reference genomes per GPU (%d x 5 Mbp), k=16 sketchlen=16 "
-                               "winlen=128 winstride=113 (BASELINE.json configs[1])" % (args.mbp, max(args.mbp // 5, 1)),
-                   "sample": "%d Mbp per step: the first %d genomes of that workload (bounded sample, same generator and seeds)"
-                             % (bp // 1_000_000, G)},
-        "cpu_baseline": {"value": val, "unit": "bp/s", "cores": cores, "kind": kind,
-                         "sample": "%d genomes x 5 Mbp, %d threads over sequences, hash_dna.h sketcher" % (G, cores)},
-        "e2e": {"value": val, "unit": "bp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "config": {"workload": workload_name(args, args.gpus), "sample": sample,
+                   "note": "a smaller database means shorter location lists and FEWER chance hits per read: the sample favours the "
+                           "reference; its sketching, table lookups and candidate generation per read are the same code"},
+        "cpu_baseline": {"value": val, "unit": "reads/s", "cores": r["np"] * r["threads"], "kind": "reference", "sample": sample},
+        "e2e": {"value": val, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "build": {"metric": "build_bp_per_s", "value": r["build_bp"] / r["build_added_s"] if r["build_added_s"] else None, "unit": "bp/s",
+                  "seconds": r["build_added_s"], "note": "the reference's own 'Added N reference sequences in X s' (sketch + insert), np=%d" % r["np"]},
         "gpu_launches": 0,
     }
     print_json(line)
@@ -194,7 +259,7 @@ def run_mcgpu(args):
     import torch.distributed as dist
     from __graft_entry__ import load_package
     load_package()
-    from metacache_mpi_b200 import api, synth, taxonomy
+    from metacache_mpi_b200 import api, distributed as D, synth, taxonomy
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -206,12 +271,19 @@ def run_mcgpu(args):
         if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE"):
             os.environ["NCCL_DEBUG_FILE"] = os.environ.get("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
-    stream = torch.cuda.Stream(device=dev)
-    torch.cuda.set_stream(stream)
-    ctx = api.Context(local, stream.cuda_stream)        # raises if libmcgpu.so / the GPU is missing
+    ctx = api.Context(local)                         # raises if libmcgpu.so / the GPU is missing; own (non-blocking) stream
     L = ctx.L
+    comm = D.make_comm(ctx)                          # NCCL inside libmcgpu; torch.distributed only carries the id
+    stream = torch.cuda.ExternalStream(ctx.L.mcg_ctx_stream(ctx.h), device=dev)
+    t_start = time.perf_counter()
+
+    def log(msg):
+        if rank == 0 and os.environ.get("MCG_BENCH_VERBOSE"):
+            sys.stderr.write("[bench %6.1f s] %s\n" % (time.perf_counter() - t_start, msg))
+            sys.stderr.flush()
 
     def barrier():
+        torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -223,451 +295,429 @@ def run_mcgpu(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    # ---- workload: G genomes of 5 Mbp per rank (targets g with g % world == rank)
-    G = max(args.mbp // 5, 1)
-    hbuf_t = torch.empty(G * GENOME_LEN, dtype=torch.uint8, pin_memory=True)
-    hbuf = hbuf_t.numpy()
-    for i in range(G):
-        hbuf[i * GENOME_LEN:(i + 1) * GENOME_LEN] = synth.genome(rank + i * world, GENOME_LEN)
-    offs = np.arange(G + 1, dtype=np.int64) * GENOME_LEN
-    bp = int(offs[-1])
-    cfg = api.SketchCfg(K, S, WINLEN, STRIDE)
-    nwin = ctx.count_windows(cfg, offs)
-    d_seq = torch.empty(bp + 64, dtype=torch.uint8, device=dev)
-    d_seq[:bp].copy_(hbuf_t, non_blocking=True)
-    d_off = torch.from_numpy(offs).to(dev)
-    d_feat = torch.empty(nwin * S, dtype=torch.int32, device=dev)
-    torch.cuda.synchronize()
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
 
-    def step_dev():
-        rc = L.mcg_sketch_windows_dev(ctx.h, C.byref(cfg), d_seq.data_ptr(), bp, d_off.data_ptr(), G, nwin,
-                                      d_feat.data_ptr(), None)
+    def check(rc):
         if rc != 0:
             raise RuntimeError(L.mcg_last_error().decode())
 
-    sampler = ClockSampler(local)
-    for _ in range(args.warmup):
-        step_dev()
+    peak, peak_src = hbm_peak()
+    out_extra = {}
+
+    # ---- database: this rank's shard of configs[2] (genomes g with g % world == rank), generated on the device
+    Gper = max(args.db_mbp * 1_000_000 // GLEN, 1)
+    Gtot = Gper * world
+    own = np.arange(rank, Gtot, world, dtype=np.uint32)
+    ids, par, rk, species = synth.make_taxonomy(Gtot)
+    tabs = taxonomy.TaxonomyTables(ids, par, rk, species)
+    ctx.upload_taxonomy(tabs.lineage, tabs.rank, Gtot)
+    genomes = torch.empty(Gper * GLEN + 64, dtype=torch.uint8, device=dev)
+    for i, g in enumerate(own):
+        synth.genome_fast(int(g), GLEN, dev, out=genomes[i * GLEN:(i + 1) * GLEN])
+    goffs = np.arange(Gper + 1, dtype=np.int64) * GLEN
+    torch.cuda.synchronize()
+    log("genomes generated on the device: %d x %d bp" % (Gper, GLEN))
+    bp_shard = Gper * GLEN
+
+    def build_shard(timed):
+        db_ = api.Database(ctx, shard=rank, nshards=world)
+        ctx.sync()
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        t0 = time.perf_counter()
+        e0.record(stream)
+        CH = 125                                    # genomes per add call (0.5 Gbp): the slot array grows in steps
+        for a in range(0, Gper, CH):
+            b = min(Gper, a + CH)
+            check(L.mcg_db_add_targets_dev(db_.h, genomes.data_ptr(), goffs[a:b + 1].ctypes.data, own[a:b].ctypes.data, b - a, None))
+        e1.record(stream)
+        db_.finalize()
+        e2.record(stream)
+        ctx.sync()
+        return db_, e0.elapsed_time(e1), e1.elapsed_time(e2), time.perf_counter() - t0
+
+    db, _, _, _ = build_shard(False)                 # warm-up build (allocations)
+    db.close()
+    ctx.profile(True)
+    ctx.kernel_times(0); ctx.kernel_times(2)
     barrier()
+    db, ms_add, ms_fin, build_wall = build_shard(True)
+    k1_ms, k1_n = ctx.kernel_times(0)
+    rs_ms, rs_n = ctx.kernel_times(2)
+    ctx.profile(False)
+    nk, ne, nl = db.counts()
+    build_ms = max_over_ranks(ms_add + ms_fin)
+    log("shard built: %.1f ms sketch + %.1f ms finalize; %d keys, %d locations" % (ms_add, ms_fin, nk, nl))
+    alg_build = 1.0 * bp_shard + 8.0 * nl + 12.0 * nk
+    tr = load_traffic()
+    out_extra["build"] = {
+        "metric": "build_bp_per_s", "value": bp_shard * world / (build_ms * 1e-3), "unit": "bp/s", "ms": build_ms,
+        "ms_sketch": ms_add, "ms_finalize": ms_fin,
+        "workload": "database build, BASELINE.json configs[2] share: %d genomes x 4 Mbp (%.1f Gbp) per GPU x %d GPU(s), sequences resident "
+                    "in HBM -> finalized HBM multimap (sketch, stable radix sort by feature, capped lists, bucket table); "
+                    "no data-path collective" % (Gper, bp_shard / 1e9, world),
+        "shard_keys": int(nk), "shard_locations": int(nl),
+        "roofline": {"bound": "hbm", "achieved": alg_build / (ms_add + ms_fin) / 1e6, "peak": peak, "unit": "GB/s",
+                     "frac": alg_build / (ms_add + ms_fin) / 1e6 / peak,
+                     "algorithmic_bytes": "1 B/bp + 8 B/location + 12 B/key (SURVEY 8d) = %.2f B/bp" % (alg_build / bp_shard),
+                     "traffic": (tr.get("build_kernels", {}).get("dram_bytes_per_bp") or 0) * bp_shard or None,
+                     "kernels": {"sketch_tpw_kernel_ms": k1_ms, "rs_scatter_kernel_ms": rs_ms, "rs_scatter_launches": rs_n}},
+    }
+
+    # ---- reads: NB batches; this rank's slice of a batch = pairs sampled from its own genomes (every shard answers them)
+    bnd = D.slice_bounds(args.pairs, world)
+    n_loc = bnd[rank + 1] - bnd[rank]
+    NB = 2
+    gview = genomes[:Gper * GLEN]
+    slices = []
+    for b in range(NB):
+        r1, r2, _ = synth.read_pairs_fast(gview, GLEN, n_loc, first_pair=b * args.pairs + bnd[rank], seed=7 + b)
+        pad = torch.zeros(64, dtype=torch.uint8, device=dev)
+        slices.append((torch.cat([r1, pad]), torch.cat([r2, pad])))
+    offs = np.arange(n_loc + 1, dtype=np.int64) * READLEN
+    d_offs = torch.from_numpy(offs).to(dev)
+    nbytes = n_loc * READLEN
+    q = api.make_query_opts(**QFLAGS)
+    o_t = torch.empty((max(n_loc, 1), KC), dtype=torch.int32, device=dev)
+    o_h = torch.empty((max(n_loc, 1), KC), dtype=torch.int32, device=dev)
+    o_n = torch.empty(max(n_loc, 1), dtype=torch.int32, device=dev)
+    o_b = torch.empty(max(n_loc, 1), dtype=torch.int32, device=dev)
+    o_r = torch.empty(max(n_loc, 1), dtype=torch.int32, device=dev)
+    d_stats = torch.zeros(22, dtype=torch.int64, device=dev)
+    torch.cuda.synchronize()
+    log("read batches generated")
+
+    def step_dev(i):
+        s1, s2 = slices[i % NB]
+        check(L.mcg_query_batch_sharded_dev(db.h, comm.h, C.byref(q), s1.data_ptr(), d_offs.data_ptr(), nbytes,
+                                            s2.data_ptr(), d_offs.data_ptr(), nbytes, n_loc, READLEN,
+                                            o_t.data_ptr(), o_h.data_ptr(), o_n.data_ptr(), o_b.data_ptr(), o_r.data_ptr(),
+                                            d_stats.data_ptr()))
+
+    sampler = ClockSampler(local)
+    for i in range(args.warmup):
+        step_dev(i)
+    barrier()
+    d_stats.zero_()
+    ctx.profile(True)
+    ctx.kernel_times(0); ctx.kernel_times(1)
     l0 = ctx.launches()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler.start()
     e0.record(stream)
-    for _ in range(args.steps):
-        step_dev()
+    for i in range(args.steps):
+        step_dev(i)
     e1.record(stream)
     barrier()
     dev_ms = max_over_ranks(e0.elapsed_time(e1))
     launches = ctx.launches() - l0
-    value = bp * world * args.steps / (dev_ms * 1e-3)
+    fused_ms, fused_n = ctx.kernel_times(1)
+    qk1_ms, qk1_n = ctx.kernel_times(0)
+    ctx.profile(False)
+    stats_dev = d_stats.cpu().numpy().astype(np.int64)
+    value = 2.0 * args.pairs * args.steps / (dev_ms * 1e-3)
+    log("device-resident: %.3f ms per step, fused kernel %.3f ms per launch" % (dev_ms / args.steps, fused_ms / max(fused_n, 1)))
 
-    # ---- e2e: pinned host buffers through the C-ABI host entry point
-    hfeat_t = torch.empty(nwin * S, dtype=torch.int32, pin_memory=True)
-    hfeat = hfeat_t.numpy().view(np.uint32)
-    nw_out = C.c_int64()
+    # ---- e2e: pinned host slices through the host entry point
+    h1 = [s[0][:nbytes].cpu().pin_memory() for s in slices]
+    h2 = [s[1][:nbytes].cpu().pin_memory() for s in slices]
+    hot = torch.empty((max(n_loc, 1), KC), dtype=torch.int32).pin_memory()
+    hoh = torch.empty((max(n_loc, 1), KC), dtype=torch.int32).pin_memory()
+    hon = torch.empty(max(n_loc, 1), dtype=torch.int32).pin_memory()
+    hob = torch.empty(max(n_loc, 1), dtype=torch.int32).pin_memory()
+    hor = torch.empty(max(n_loc, 1), dtype=torch.int32).pin_memory()
+    hstats = np.zeros(22, np.uint64)
 
-    def step_e2e():
-        rc = L.mcg_sketch_windows(ctx.h, C.byref(cfg), hbuf.ctypes.data, offs.ctypes.data, G, hfeat.ctypes.data, None,
-                                  C.byref(nw_out))
-        if rc != 0:
-            raise RuntimeError(L.mcg_last_error().decode())
+    def step_e2e(i):
+        check(L.mcg_query_batch_sharded(db.h, comm.h, C.byref(q), h1[i % NB].data_ptr(), offs.ctypes.data, h2[i % NB].data_ptr(),
+                                        offs.ctypes.data, n_loc, hot.data_ptr(), hoh.data_ptr(), hon.data_ptr(), hob.data_ptr(),
+                                        hor.data_ptr(), hstats.ctypes.data))
 
-    for _ in range(min(args.warmup, 3)):
-        step_e2e()
+    for i in range(2):
+        step_e2e(i)
     barrier()
+    hstats[:] = 0
     t0 = time.perf_counter()
-    for _ in range(args.e2e_steps):
-        step_e2e()
+    for i in range(args.e2e_steps):
+        step_e2e(i)
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     sampler.stop()
-    e2e_value = bp * world * args.e2e_steps / e2e_s
-    # parity spot check of what was just timed: device-resident result == host-path result
-    same = bool((d_feat.cpu().numpy().view(np.uint32) == hfeat).all())
+    e2e_value = 2.0 * args.pairs * args.e2e_steps / e2e_s
+    log("e2e: %.3f ms per step" % (1e3 * e2e_s / args.e2e_steps))
+    # what the e2e call returned for the batch it ran last ((e2e_steps - 1) % NB), kept for the parity sample
+    last_b = (args.e2e_steps - 1) % NB
+    e2e_res = (hot.numpy().copy(), hoh.numpy().view(np.uint32).copy(), hon.numpy().copy(), hob.numpy().copy(), hor.numpy().copy())
+    # device-resident and host path agree on the statistics of the batches both ran
+    same_stats = None
+    if args.steps % NB == 0 and args.e2e_steps % NB == 0:
+        same_stats = bool((stats_dev * args.e2e_steps == hstats.astype(np.int64) * args.steps).all())
 
-    peak, peak_src = hbm_peak()
-    kern_ms = dev_ms / args.steps
-    achieved = ALG_BYTES_PER_BP * bp / (kern_ms * 1e-3) / 1e9
-    tr = load_traffic().get("sketch_kernel")
-    traffic = None
-    if tr:
-        traffic = tr["dram_bytes_per_bp"] * bp
+    # ---- roofline of the dominant kernel: one launch handles all 2 M reads of a step against this shard
+    mloc = None
+    try:
+        ns = min(2000, n_loc)
+        _, tgx, _ = db.query_matches(q, h1[0].numpy()[:ns * READLEN], offs[:ns + 1].copy(), h2[0].numpy()[:ns * READLEN], offs[:ns + 1].copy())
+        mloc = len(tgx) / float(ns)
+    except Exception:
+        pass
+    F = 4 * S
+    alg_pair = 2 * READLEN + 32 * F + 8 * (mloc or 0) + 8 * KC
+    fused_per_launch = fused_ms / max(fused_n, 1)
+    achieved = alg_pair * args.pairs / (fused_per_launch * 1e-3) / 1e9 if fused_n else None
+    trq = tr.get("query_fused_kernel", {})
     line = {
-        "metric": "sketch_bp_per_s", "value": value, "unit": "bp/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": kern_ms, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-        "config": {"workload": "sketching-only: %d Mbp of synthetic reference genomes per GPU (%d x 5 Mbp), k=16 sketchlen=16 "
-                               "winlen=128 winstride=113 (BASELINE.json configs[1])" % (bp // 1_000_000, G),
-                   "l2": "inputs (%.2f GB per step) larger than L2, no flush needed" % (bp / 1e9),
-                   "parallelism": "targets sharded by target_id %% %d, no data-path collective" % world,
-                   "self_check": "device-resident and host-path sketches identical: %s" % same},
+        "metric": "query_reads_per_s", "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
+        "data": "synthetic",
+        "config": {"workload": workload_name(args, world),
+                   "fraction_of_configs3": "%d steps x %d pairs = %.0f %% of configs[3]'s 50 M pairs" % (args.steps, args.pairs, 100.0 * args.steps * args.pairs / 50e6),
+                   "scaling_note": "weak in DATABASE size (2.5 Gbp per GPU: N = 8 is configs[2]'s 20 Gbp); every read is answered by every shard as "
+                                   "in the reference, so reads/s x database size is the quantity that grows with N",
+                   "l2": "every step probes a %.1f GB bucket table at random and reads a fresh 300 MB batch (%d batches alternate): far beyond the 126 MB L2, no flush needed"
+                         % (nk / 0.45 / 3 * 128 / 1e9, NB),
+                   "parallelism": "one process per GPU; shard = target_id %% %d; per step: slice ingest, K1 on the slice, NCCL all-gather of sketches, "
+                                  "shard query of all reads, NCCL all-to-all of top lists, slice-wise merge + decision (libmcgpu: mcg_query_batch_sharded)" % world,
+                   "self_check": "device-resident and host-path runs give the same 22 statistics counters: %s" % same_stats},
+        "classified": int(stats_dev[20] // max(args.steps, 1)) if world == 1 else None,
         "clocks": sampler.summary(),
-        "e2e": {"value": e2e_value, "unit": "bp/s", "h2d_bytes_per_step": bp + 8 * (G + 1), "d2h_bytes_per_step": nwin * S * 4,
-                "steps": args.e2e_steps, "api": "mcg_sketch_windows (pinned host buffers)"},
+        "e2e": {"value": e2e_value, "unit": "reads/s", "ms_per_step": 1e3 * e2e_s / args.e2e_steps,
+                "h2d_bytes_per_step": int(2 * nbytes + 16 * (n_loc + 1)) * world, "d2h_bytes_per_step": int(n_loc * (8 * KC + 12) + 176) * world,
+                "steps": args.e2e_steps, "api": "mcg_query_batch_sharded (pinned host slices; every rank copies its slice over its own PCIe link)"},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "peak_source": peak_src, "kernel": "mcg::sketch_tpw_kernel",
-                     "algorithmic_bytes_per_bp": ALG_BYTES_PER_BP,
-                     "note": "instruction-throughput bound kernel (ncu: ALU pipe 86 %, issue slots 79 % busy, see profiles/): "
-                             "the HBM fraction is reported as required, integer issue is the binding limit"},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
+                     "traffic": (trq.get("dram_bytes_per_pair") or 0) * args.pairs or None, "peak_source": peak_src,
+                     "kernel": "mcg::q_fused_warp_kernel", "ms_per_launch": fused_per_launch, "launches_timed": int(fused_n),
+                     "share_of_step": fused_ms / (dev_ms if world == 1 else e0.elapsed_time(e1)),
+                     "algorithmic_bytes_per_pair": alg_pair, "mean_locations_per_pair": mloc,
+                     "formula": "len1 + len2 + 32 B x F (F = 64 feature probes) + 8 B x M (locations gathered) + 8 B x K (SURVEY 8d), x %d pairs per launch" % args.pairs,
+                     "note": "random 128-byte line fills (one per probe) + dependent location gathers: the kernel is latency / issue bound, see profiles/"},
+        "sketch_in_query": {"ms_per_step": qk1_ms / max(args.steps, 1), "launches": int(qk1_n)},
     }
+    line.update(out_extra)
 
-    # ---- extras: build + query of the same path
+    # ---- parity sample: oracle over the same database content
+    if not args.no_check:
+        try:
+            line["parity"] = parity_sample(args, api, synth, tabs, db, comm, q, world, rank, dist, torch, dev, genomes, goffs, own, Gper, Gtot,
+                                           h1[last_b], h2[last_b], offs, n_loc, e2e_res, log)
+        except Exception as e:
+            line["parity"] = {"error": repr(e)}
+
+    # ---- extras
     if not args.no_extras:
         try:
-            line.update(run_extras(args, ctx, api, synth, taxonomy, torch, dist, dev, stream, world, rank, barrier, max_over_ranks, peak))
+            line.update(run_extras(args, ctx, api, synth, torch, dist, dev, stream, world, rank, barrier, max_over_ranks, check, peak, tr,
+                                   db, comm, q, genomes, goffs, own, Gper, log))
         except Exception as e:       # extras must never hide the headline
             line["extras_error"] = repr(e)
 
-    # ---- CPU baseline on the host cores (rank 0, N = 1 only)
+    # ---- CPU baseline: the reference program on the host cores (rank 0, N = 1 only)
     if world == 1 and not args.no_cpu:
         try:
-            from oracle import pyoracle as po
-            cores = os.cpu_count() or 1
-            impl, kind = (po.Reference(), "reference") if po.have_reference() else (po.Oracle(), "port")
-            sg = int(max(2, min(G, 40 * cores)))          # ~20 core-seconds of the reference's sketcher
-            t, cs, nw = impl.sketch_throughput(hbuf[:sg * GENOME_LEN], offs[:sg + 1].copy(), K, S, WINLEN, STRIDE, threads=cores)
-            line["cpu_baseline"] = {"value": sg * GENOME_LEN / t, "unit": "bp/s", "cores": cores, "kind": kind,
-                                    "sample": "%d of the %d genomes (%d Mbp), %d threads, %.1f s" % (sg, G, sg * 5, cores, t)}
+            del slices
+            torch.cuda.empty_cache()
+            r = reference_program_run(args, 1, 1, args.ref_genomes, args.ref_pairs, log)
+            v = r["queries"] / r["query_s"][0]
+            sample = reference_sample_text(r, args.ref_genomes, args.ref_pairs)
+            line["cpu_baseline"] = {"value": v, "unit": "reads/s", "cores": r["np"] * r["threads"], "kind": "reference", "sample": sample}
+            if "build" in line and r["build_added_s"]:
+                line["build"]["cpu_baseline"] = {"value": r["build_bp"] / r["build_added_s"], "unit": "bp/s", "cores": r["np"], "kind": "reference",
+                                                 "sample": "the reference program's build of that sample database (%d Mbp), its own 'Added N reference "
+                                                           "sequences in X s' timer; build is single-threaded per MPI rank, np=%d"
+                                                           % (r["build_bp"] // 1_000_000, r["np"])}
         except Exception as e:
-            line["cpu_baseline"] = {"value": None, "unit": "bp/s", "cores": 0, "kind": "port", "sample": "failed: %r" % (e,)}
+            line["cpu_baseline"] = {"value": None, "unit": "reads/s", "cores": 0, "kind": "reference", "sample": "failed: %r" % (e,)}
 
     if rank == 0:
         print_json(line)
+    db.close()
+    comm.close()
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
 
 
-def run_extras(args, ctx, api, synth, taxonomy, torch, dist, dev, stream, world, rank, barrier, max_over_ranks, peak):
-    """device-timed build (bp/s) and query (reads/s): 64 genomes x 5 Mbp sharded by target_id % world,
-    1 M read pairs (2 x 150 bp) per batch, the authors' query flags"""
+def parity_sample(args, api, synth, tabs, db, comm, q, world, rank, dist, torch, dev, genomes, goffs, own, Gper, Gtot,
+                  hb1, hb2, offs, n_loc, e2e_res, log):
+    """2000 pairs of rank 0's slice of the timed batch: per-shard lists of every GPU and the merged result of the timed
+    e2e call against the oracle.  The oracle sketches EVERY genome of the shard (all host threads) and keeps the lists
+    of the sample's features: lookups of those features see exactly the lists of the whole database."""
+    from oracle import pyoracle as po
+    O = po.Oracle()
+    NS = 2000
+    ns = min(NS, n_loc) if rank == 0 else 0
+    # rank 0's sample reads go to every rank
+    if world > 1:
+        cnt = torch.tensor([ns], dtype=torch.int64, device=dev)
+        dist.broadcast(cnt, 0)
+        ns = int(cnt.item())
+        s1 = torch.empty(ns * READLEN, dtype=torch.uint8, device=dev)
+        s2 = torch.empty(ns * READLEN, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            s1.copy_(hb1[:ns * READLEN]); s2.copy_(hb2[:ns * READLEN])
+        dist.broadcast(s1, 0); dist.broadcast(s2, 0)
+        b1, b2 = s1.cpu().numpy(), s2.cpu().numpy()
+    else:
+        b1, b2 = hb1.numpy()[:ns * READLEN].copy(), hb2.numpy()[:ns * READLEN].copy()
+    so = offs[:ns + 1].copy()
+    f1, _ = O.sketch_sequences(b1, so)
+    f2, _ = O.sketch_sequences(b2, so)
+    allowed = np.unique(np.concatenate([f1.ravel(), f2.ravel()]))
+    allowed = allowed[allowed != 0xFFFFFFFF]
+    threads = max(1, (os.cpu_count() or 1) // world)
+    t0 = time.perf_counter()
+    odb = O.db_create(shard=rank, nshards=world)
+    gh = genomes[:Gper * GLEN].cpu().numpy()
+    odb.add_targets_restricted(gh, goffs, own, allowed, threads=threads)
+    odb.finalize()
+    del gh
+    t_oracle = time.perf_counter() - t0
+    tax = po.TaxTables(tabs.lineage, tabs.rank, Gtot)
+    oq = po.make_qopt(**QFLAGS)
+    # (1) per-shard lists of this GPU (mcg_query_batch) == oracle shard
+    gt, gh_, gn = db.query_batch(q, b1, so, b2, so)
+    lt = np.full((ns, KC), -1, np.int32); lh = np.zeros((ns, KC), np.uint32); ln = np.zeros(ns, np.int32)
+    for i in range(ns):
+        t, h = odb.query_local(tax, oq, b1[so[i]:so[i + 1]], b2[so[i]:so[i + 1]])
+        ln[i] = len(t); lt[i, :len(t)] = t; lh[i, :len(t)] = h
+    shard_ok = bool((gn == ln).all() and (gt == lt).all() and (gh_ == lh).all())
+    res = {"sample_pairs": ns, "oracle_threads": threads, "oracle_build_s": t_oracle, "features_in_sample": int(len(allowed))}
+    if world > 1:
+        allv = [None] * world if rank == 0 else None
+        dist.gather_object((shard_ok, lt, lh, ln), allv, dst=0)
+    else:
+        allv = [(shard_ok, lt, lh, ln)]
+    if rank != 0:
+        return None
+    res["per_shard_lists_equal_oracle"] = [bool(v[0]) for v in allv]
+    # (2) merged lists + decision of the timed e2e call == oracle merge of the oracle's per-shard lists (rank order)
+    mt, mh, mn, mb, mr = e2e_res
+    ok = True
+    nclass = 0
+    for i in range(ns):
+        it, ih = [], []
+        for r in range(world):
+            c = int(allv[r][3][i])
+            it += allv[r][1][i, :c].tolist(); ih += allv[r][2][i, :c].tolist()
+        et, eh, eb, er = O.merge_classify(tax, oq, it, ih)
+        k = len(et)
+        ok &= bool(mn[i] == k and (mt[i, :k] == et).all() and (mh[i, :k] == eh).all() and mb[i] == eb and mr[i] == er)
+        nclass += eb >= 0
+    res["merged_lists_and_taxa_equal_oracle"] = bool(ok)
+    res["classified_in_sample"] = int(nclass)
+    res["verdict"] = "bit-exact" if ok and all(res["per_shard_lists_equal_oracle"]) else "MISMATCH"
+    return res
+
+
+def run_extras(args, ctx, api, synth, torch, dist, dev, stream, world, rank, barrier, max_over_ranks, check, peak, tr,
+               db, comm, q, genomes, goffs, own, Gper, log):
+    """configs[1] (sketch-only 1 Gbp per GPU) and configs[4] (10 kbp reads) on the data already resident"""
     L = ctx.L
     out = {}
-    QG = 64
-    ids, par, rk, species = synth.make_taxonomy(QG)
-    tabs = taxonomy.TaxonomyTables(ids, par, rk, species)
-    ctx.upload_taxonomy(tabs.lineage, tabs.rank, QG)
-    own = [g for g in range(QG) if g % world == rank]
-    genomes = {g: synth.genome(g, GENOME_LEN) for g in own}
-    buf_t = torch.empty(len(own) * GENOME_LEN, dtype=torch.uint8, pin_memory=True)
-    buf = buf_t.numpy()
-    for i, g in enumerate(own):
-        buf[i * GENOME_LEN:(i + 1) * GENOME_LEN] = genomes[g]
-    offs = np.arange(len(own) + 1, dtype=np.int64) * GENOME_LEN
-    tids = np.array(own, np.uint32)
-    # build: add_targets (H2D + K1) + finalize (sort, CSR, table), timed end to end on the host clock
-    # after a warm-up build (allocations), device work dominates
-    times = []
-    db = None
-    for it in range(4):
-        if db is not None:
-            db.close()
-        db = api.Database(ctx, shard=rank, nshards=world)
-        barrier()
-        t0 = time.perf_counter()
-        db.add_targets(buf, offs, tids)
-        db.finalize()
-        ctx.sync()
-        times.append(time.perf_counter() - t0)
-    bt = max_over_ranks(float(np.median(times[1:])))
-    nk, ne, nl = db.counts()
-    bbp = QG * GENOME_LEN
-    alg_build = 1.0 * len(buf) + 8.0 * nl + 12.0 * nk
-    out["build"] = {"metric": "build_bp_per_s", "value": bbp / bt, "unit": "bp/s", "seconds": bt,
-                    "workload": "%d genomes x 5 Mbp sharded over %d GPU(s), host buffers -> finalized HBM multimap" % (QG, world),
-                    "shard0_keys": int(nk), "shard0_locations": int(nl),
-                    "roofline": {"bound": "hbm", "achieved": alg_build / bt / 1e9, "peak": peak, "unit": "GB/s",
-                                 "frac": alg_build / bt / 1e9 / peak,
-                                 "traffic": (load_traffic().get("build_kernels_1gbp", {}).get("dram_bytes_per_bp") or 0) * len(buf) or None,
-                                 "note": "wall time of mcg_db_add_targets + mcg_db_finalize incl. the H2D copy of the sequences from pinned host memory"}}
-    # query
-    npairs = 1_000_000
-    allg = [synth.genome(g, GENOME_LEN) for g in range(QG)] if world > 1 else [genomes[g] for g in range(QG)]
-    b1, o1, b2, o2, truth = synth.make_read_pairs(allg, npairs, seed=7)
-    del allg
-    q = api.make_query_opts(maxcand=4, lowest=4, hitmin=4, hitdiff=0.8)
-    Kc = 4
-    d1 = torch.from_numpy(np.concatenate([b1, np.zeros(64, np.uint8)])).to(dev)
-    d2 = torch.from_numpy(np.concatenate([b2, np.zeros(64, np.uint8)])).to(dev)
-    do1 = torch.from_numpy(o1).to(dev)
-    do2 = torch.from_numpy(o2).to(dev)
-    lt = torch.empty((npairs, Kc), dtype=torch.int32, device=dev)
-    lh = torch.empty((npairs, Kc), dtype=torch.int32, device=dev)
-    ln = torch.empty(npairs, dtype=torch.int32, device=dev)
-    # cross-shard exchange of the per-read top lists.  Preferred: every rank's candidate kernel stores its
-    # lists straight into rank 0's [P][n][K] buffers through NVLink peer memory (torch symmetric memory),
-    # followed by one barrier -- compute and "gather" are the same kernel.  Fallback: NCCL all-gather.
-    gather_mode = "local"
-    hdl_t = hdl_h = hdl_n = None
-    if world > 1:
-        gather_mode = "nccl-all-gather"
-        if os.environ.get("MCG_BENCH_NO_P2P", "") == "":
-            try:
-                import torch.distributed._symmetric_memory as symm
-                gt = symm.empty((world, npairs, Kc), dtype=torch.int32, device=dev)
-                gh = symm.empty((world, npairs, Kc), dtype=torch.int32, device=dev)
-                gn = symm.empty((world, npairs), dtype=torch.int32, device=dev)
-                hdl_t = symm.rendezvous(gt, dist.group.WORLD)
-                hdl_h = symm.rendezvous(gh, dist.group.WORLD)
-                hdl_n = symm.rendezvous(gn, dist.group.WORLD)
-                gather_mode = "p2p-store into rank 0 (symmetric memory) + barrier"
-            except Exception as e:          # pragma: no cover
-                gather_mode = "nccl-all-gather (symmetric memory unavailable: %s)" % type(e).__name__
-                hdl_t = None
-    if hdl_t is None:
-        gt = torch.empty((world, npairs, Kc), dtype=torch.int32, device=dev)
-        gh = torch.empty((world, npairs, Kc), dtype=torch.int32, device=dev)
-        gn = torch.empty((world, npairs), dtype=torch.int32, device=dev)
-    mt = torch.empty((npairs, Kc), dtype=torch.int32, device=dev)
-    mh = torch.empty((npairs, Kc), dtype=torch.int32, device=dev)
-    mn = torch.empty(npairs, dtype=torch.int32, device=dev)
-    best = torch.empty(npairs, dtype=torch.int32, device=dev)
-    brank = torch.empty(npairs, dtype=torch.int32, device=dev)
-    stats = torch.zeros(22, dtype=torch.int64, device=dev)
-    if hdl_t is not None:
-        out_t = hdl_t.buffer_ptrs[0] + rank * npairs * Kc * 4
-        out_h = hdl_h.buffer_ptrs[0] + rank * npairs * Kc * 4
-        out_n = hdl_n.buffer_ptrs[0] + rank * npairs * 4
-    else:
-        out_t, out_h, out_n = lt.data_ptr(), lh.data_ptr(), ln.data_ptr()
+    # ---- sketching only: 1 Gbp of this rank's genomes (BASELINE.json configs[1])
+    G1 = min(Gper, 250)
+    bp = G1 * GLEN
+    cfg = api.SketchCfg(K, S, WINLEN, STRIDE)
+    o1g = goffs[:G1 + 1].copy()
+    nwin = ctx.count_windows(cfg, o1g)
+    d_off = torch.from_numpy(o1g).to(dev)
+    d_feat = torch.empty(nwin * S, dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
 
-    def qstep():
-        rc = L.mcg_query_batch_dev(db.h, C.byref(q), d1.data_ptr(), do1.data_ptr(), len(b1), d2.data_ptr(), do2.data_ptr(), len(b2),
-                                   npairs, 150, out_t, out_h, out_n)
-        if rc != 0:
-            raise RuntimeError(L.mcg_last_error().decode())
-        if hdl_t is not None:
-            hdl_t.barrier(channel=0)            # all shards' lists have landed in rank 0's memory
-            ct, ch, cn = gt, gh, gn
-        elif world > 1:
-            dist.all_gather_into_tensor(gt.view(world * npairs, Kc), lt)
-            dist.all_gather_into_tensor(gh.view(world * npairs, Kc), lh)
-            dist.all_gather_into_tensor(gn.view(world * npairs), ln)
-            ct, ch, cn = gt, gh, gn
-        else:
-            ct, ch, cn = lt, lh, ln
-        if rank == 0:
-            stats.zero_()
-            rc = L.mcg_merge_classify_dev(ctx.h, C.byref(q), ct.data_ptr(), ch.data_ptr(), cn.data_ptr(), world, npairs,
-                                          mt.data_ptr(), mh.data_ptr(), mn.data_ptr(), best.data_ptr(), brank.data_ptr(),
-                                          stats.data_ptr())
-            if rc != 0:
-                raise RuntimeError(L.mcg_last_error().decode())
-        if hdl_t is not None:
-            hdl_t.barrier(channel=1)            # rank 0 is done reading before the next batch overwrites
-
+    def sk():
+        check(L.mcg_sketch_windows_dev(ctx.h, C.byref(cfg), genomes.data_ptr(), bp, d_off.data_ptr(), G1, nwin, d_feat.data_ptr(), None))
     for _ in range(3):
-        qstep()
+        sk()
     barrier()
-    l0 = ctx.launches()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    qsteps = 10
+    ST = 20
     e0.record(stream)
-    for _ in range(qsteps):
-        qstep()
+    for _ in range(ST):
+        sk()
     e1.record(stream)
     barrier()
-    qms = max_over_ranks(e0.elapsed_time(e1)) / qsteps
-    launches_q = int((ctx.launches() - l0) / qsteps)
-    st = stats.cpu().numpy()
-    # the same batch through the host entry point: pinned host reads in, top lists out (H2D / query / D2H pipelined)
-    qe2e = None
-    try:
-        hb1 = torch.from_numpy(b1).pin_memory(); hb2 = torch.from_numpy(b2).pin_memory()
-        hot = torch.empty((npairs, Kc), dtype=torch.int32, pin_memory=True)
-        hoh = torch.empty((npairs, Kc), dtype=torch.int32, pin_memory=True)
-        hon = torch.empty(npairs, dtype=torch.int32, pin_memory=True)
+    ms = max_over_ranks(e0.elapsed_time(e1)) / ST
+    hseq = genomes[:bp].cpu().pin_memory()
+    hfeat = torch.empty(nwin * S, dtype=torch.int32).pin_memory()
+    nw_out = C.c_int64()
 
-        def qhost():
-            rc = L.mcg_query_batch(db.h, C.byref(q), hb1.data_ptr(), o1.ctypes.data, hb2.data_ptr(), o2.ctypes.data, npairs,
-                                   hot.data_ptr(), hoh.data_ptr(), hon.data_ptr())
-            if rc != 0:
-                raise RuntimeError(L.mcg_last_error().decode())
-        qhost()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(3):
-            qhost()
-        barrier()
-        qe = max_over_ranks(time.perf_counter() - t0) / 3
-        same_q = bool((hon.numpy() == ln.cpu().numpy()).all()) if world == 1 else None
-        qe2e = {"value": 2 * npairs / qe, "unit": "reads/s", "ms_per_batch": 1e3 * qe,
-                "h2d_bytes_per_step": int(len(b1) + len(b2) + 16 * (npairs + 1)), "d2h_bytes_per_step": int(npairs * (8 * Kc + 4)),
-                "api": "mcg_query_batch (pinned host buffers, per-shard top lists)", "same_as_device_path": same_q}
-    except Exception as e:
-        qe2e = {"error": repr(e)}
-    # N > 1: every rank copying all reads over PCIe itself (above) is bounded by the host.  The reads of a batch
-    # cross PCIe ONCE (rank 0), travel to the other GPUs by an NCCL broadcast over NVLink, every GPU queries its
-    # shard, the per-shard top lists land in rank 0 (P2P stores / all-gather), rank 0 merges, classifies and
-    # copies the result to the host.
-    if world > 1 and isinstance(qe2e, dict) and "error" not in qe2e:
+    def ske():
+        check(L.mcg_sketch_windows(ctx.h, C.byref(cfg), hseq.data_ptr(), o1g.ctypes.data, G1, hfeat.data_ptr(), None, C.byref(nw_out)))
+    ske()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        ske()
+    barrier()
+    es = max_over_ranks(time.perf_counter() - t0) / 3
+    same = bool((d_feat.cpu() == hfeat).all().item())
+    ach = ALG_SKETCH * bp / (ms * 1e-3) / 1e9
+    out["sketch"] = {"metric": "sketch_bp_per_s", "value": bp * world / (ms * 1e-3), "unit": "bp/s", "ms_per_step": ms,
+                     "workload": "sketching only: %d Mbp of reference genomes per GPU (%d x 4 Mbp), k=16 sketchlen=16 winlen=128 winstride=113 "
+                                 "(BASELINE.json configs[1]); weak scaling, no collective" % (bp // 1_000_000, G1),
+                     "e2e": {"value": bp * world / es, "unit": "bp/s", "h2d_bytes_per_step": int(bp + 8 * (G1 + 1)) * world,
+                             "d2h_bytes_per_step": int(nwin * S * 4) * world, "api": "mcg_sketch_windows (pinned host buffers)",
+                             "same_as_device_path": same},
+                     "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                                  "traffic": (tr.get("sketch_kernel", {}).get("dram_bytes_per_bp") or 0) * bp or None,
+                                  "kernel": "mcg::sketch_tpw_kernel", "algorithmic_bytes_per_bp": ALG_SKETCH,
+                                  "note": "instruction-throughput bound (ALU pipe), see profiles/"}}
+    if world == 1 and not args.no_cpu:
         try:
-            hdo1 = torch.from_numpy(o1).pin_memory(); hdo2 = torch.from_numpy(o2).pin_memory()
-            hbest = torch.empty(npairs, dtype=torch.int32, pin_memory=True)
-            hmt = torch.empty((npairs, Kc), dtype=torch.int32, pin_memory=True)
-            hmh = torch.empty((npairs, Kc), dtype=torch.int32, pin_memory=True)
-            n1, n2 = len(b1), len(b2)
+            from oracle import pyoracle as po
+            cores = os.cpu_count() or 1
+            impl, kind = (po.Reference(), "reference") if po.have_reference() else (po.Oracle(), "port")
+            sg = int(max(2, min(G1, 10 * cores)))
+            t, cs, nw = impl.sketch_throughput(hseq.numpy()[:sg * GLEN], o1g[:sg + 1].copy(), K, S, WINLEN, STRIDE, threads=cores)
+            out["sketch"]["cpu_baseline"] = {"value": sg * GLEN / t, "unit": "bp/s", "cores": cores, "kind": kind,
+                                             "sample": "the reference's hash_dna.h sketcher on %d of the genomes (%d Mbp), %d threads, %.1f s" % (sg, sg * 4, cores, t)}
+        except Exception as e:
+            out["sketch"]["cpu_baseline"] = {"error": repr(e)}
+    del hseq, hfeat, d_feat
+    log("sketch extra done")
 
-            # sub-batches: while sub-batch j is broadcast and queried, rank 0 copies sub-batch j + 1 over PCIe
-            NSUB = 4
-            assert npairs % NSUB == 0
-            ns = npairs // NSUB
-            rel = torch.from_numpy(np.arange(ns + 1, dtype=np.int64) * 150).pin_memory()     # offsets of a sub-batch
-            drel = torch.empty(ns + 1, dtype=torch.int64, device=dev)
-            copy_stream = torch.cuda.Stream(device=dev)
-            ev_in = [torch.cuda.Event() for _ in range(NSUB)]
-            ev_free = torch.cuda.Event()
-
-            def qbcast():
-                cur = torch.cuda.current_stream()
-                if rank == 0:
-                    ev_free.record(cur)                       # the previous batch no longer reads d1 / d2
-                    with torch.cuda.stream(copy_stream):
-                        copy_stream.wait_event(ev_free)
-                        drel.copy_(rel, non_blocking=True)
-                        for j in range(NSUB):
-                            d1[j * ns * 150:(j + 1) * ns * 150].copy_(hb1[j * ns * 150:(j + 1) * ns * 150], non_blocking=True)
-                            d2[j * ns * 150:(j + 1) * ns * 150].copy_(hb2[j * ns * 150:(j + 1) * ns * 150], non_blocking=True)
-                            ev_in[j].record(copy_stream)
-                for j in range(NSUB):
-                    if rank == 0:
-                        cur.wait_event(ev_in[j])
-                    if j == 0:
-                        dist.broadcast(drel, src=0)
-                    s1 = d1[j * ns * 150:(j + 1) * ns * 150 + (64 if j == NSUB - 1 else 0)]
-                    s2 = d2[j * ns * 150:(j + 1) * ns * 150 + (64 if j == NSUB - 1 else 0)]
-                    dist.broadcast(s1, src=0)
-                    dist.broadcast(s2, src=0)
-                    rc = L.mcg_query_batch_dev(db.h, C.byref(q), d1.data_ptr() + j * ns * 150, drel.data_ptr(), ns * 150,
-                                               d2.data_ptr() + j * ns * 150, drel.data_ptr(), ns * 150, ns, 150,
-                                               out_t + j * ns * Kc * 4, out_h + j * ns * Kc * 4, out_n + j * ns * 4)
-                    if rc != 0:
-                        raise RuntimeError(L.mcg_last_error().decode())
-                if hdl_t is not None:
-                    hdl_t.barrier(channel=0)
-                    ct, ch, cn = gt, gh, gn
-                else:
-                    dist.all_gather_into_tensor(gt.view(world * npairs, Kc), lt)
-                    dist.all_gather_into_tensor(gh.view(world * npairs, Kc), lh)
-                    dist.all_gather_into_tensor(gn.view(world * npairs), ln)
-                    ct, ch, cn = gt, gh, gn
-                if rank == 0:
-                    stats.zero_()
-                    rc = L.mcg_merge_classify_dev(ctx.h, C.byref(q), ct.data_ptr(), ch.data_ptr(), cn.data_ptr(), world, npairs,
-                                                  mt.data_ptr(), mh.data_ptr(), mn.data_ptr(), best.data_ptr(), brank.data_ptr(),
-                                                  stats.data_ptr())
-                    if rc != 0:
-                        raise RuntimeError(L.mcg_last_error().decode())
-                    hbest.copy_(best, non_blocking=True); hmt.copy_(mt, non_blocking=True); hmh.copy_(mh, non_blocking=True)
-                if hdl_t is not None:
-                    hdl_t.barrier(channel=1)
-                torch.cuda.synchronize()
-            st_before = stats.clone()
-            qbcast()
-            barrier()
-            t0 = time.perf_counter()
-            for _ in range(3):
-                qbcast()
-            barrier()
-            qb = max_over_ranks(time.perf_counter() - t0) / 3
-            same_b = bool((stats == st_before).all().item()) if rank == 0 else None
-            qe2e = {"value": 2 * npairs / qb, "unit": "reads/s", "ms_per_batch": 1e3 * qb,
-                    "h2d_bytes_per_step": int(n1 + n2 + 16 * (npairs + 1)), "d2h_bytes_per_step": int(npairs * (8 * Kc + 4)),
-                    "api": "rank 0: pinned host reads -> H2D once -> NCCL broadcast over NVLink -> mcg_query_batch_dev on every "
-                           "shard -> top lists into rank 0 -> mcg_merge_classify_dev -> D2H of taxa and merged lists; "
-                           "%d sub-batches, the PCIe copy of one overlaps the broadcast and query of the previous" % NSUB,
-                    "same_statistics_as_device_path": same_b,
-                    "every_rank_copies_all_reads_itself": qe2e}
-        except Exception as e:      # pragma: no cover
-            qe2e["broadcast_error"] = repr(e)
-    # byte accounting per pair on this shard: 300 B reads + 32 B per probed feature + 8 B per location + 8K
-    nfeat = 4 * 16
-    mloc = None
+    # ---- long reads: BASELINE.json configs[4] shape, 10 kbp single-end reads, many windows per read
     try:
-        cnt = np.zeros(2000, np.int64)
-        _, tgx, _ = db.query_matches(q, b1[:2000 * 150], o1[:2001].copy(), b2[:2000 * 150], o2[:2001].copy())
-        mloc = len(tgx) / 2000.0
-    except Exception:
-        pass
-    algq = (300 + 32 * nfeat + 8 * (mloc or 0) + 8 * Kc) * npairs
-    out["query"] = {"metric": "query_reads_per_s", "value": 2 * npairs / (qms * 1e-3), "unit": "reads/s",
-                    "pairs_per_s": npairs / (qms * 1e-3), "ms_per_batch": qms,
-                    "workload": "%d pairs 2x150 bp per batch vs %d x 5 Mbp database sharded over %d GPU(s); -lowest species "
-                                "-maxcand 4 -hitmin 4 -hitdiff 80; reads resident, per-rank top lists: %s, merge+classify on rank 0"
-                                % (npairs, QG, world, gather_mode),
-                    "classified": int(st[20]), "unclassified": int(st[21]),
-                    "mean_locations_per_pair_shard0": mloc, "gpu_launches_per_batch": launches_q, "e2e": qe2e,
-                    "roofline": {"bound": "hbm", "achieved": algq / (qms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                                 "frac": algq / (qms * 1e-3) / 1e9 / peak,
-                                 "traffic": (load_traffic().get("query_fused_kernel", {}).get("dram_bytes_per_pair") or 0) * npairs or None,
-                                 "note": "traffic: DRAM bytes of the fused kernel per batch from the committed ncu capture (1-GPU database); "
-                                         "a probe fills a 128-byte line for 64 useful bytes"}}
-    # long reads (BASELINE.json configs[4] shape): 10 kbp reads, ~89 windows / ~1400 features per read, staged path
-    try:
-        nlong = 20_000
-        src = [synth.genome(g, GENOME_LEN) for g in range(0, QG, max(QG // 8, 1))]
-        lb, lo, _ = synth.make_long_reads(src, nlong, readlen=10_000)
-        del src
-        dl = torch.from_numpy(np.concatenate([lb, np.zeros(64, np.uint8)])).to(dev)
-        dlo = torch.from_numpy(lo).to(dev)
-        llt = torch.empty((nlong, Kc), dtype=torch.int32, device=dev)
-        llh = torch.empty((nlong, Kc), dtype=torch.int32, device=dev)
-        lln = torch.empty(nlong, dtype=torch.int32, device=dev)
+        nlong_tot = 100_000
+        bnd = [nlong_tot * r // world for r in range(world + 1)]
+        nl_ = bnd[rank + 1] - bnd[rank]
+        RL = 10_000
+        lr = synth.long_reads_fast(genomes[:Gper * GLEN], GLEN, nl_, first_read=bnd[rank])
+        lr = torch.cat([lr, torch.zeros(64, dtype=torch.uint8, device=dev)])
+        lo = torch.from_numpy(np.arange(nl_ + 1, dtype=np.int64) * RL).to(dev)
+        t_ = torch.empty((max(nl_, 1), KC), dtype=torch.int32, device=dev); h_ = torch.empty((max(nl_, 1), KC), dtype=torch.int32, device=dev)
+        n_ = torch.empty(max(nl_, 1), dtype=torch.int32, device=dev); b_ = torch.empty(max(nl_, 1), dtype=torch.int32, device=dev)
+        r_ = torch.empty(max(nl_, 1), dtype=torch.int32, device=dev); st_ = torch.zeros(22, dtype=torch.int64, device=dev)
 
         def lstep():
-            rc = L.mcg_query_batch_dev(db.h, C.byref(q), dl.data_ptr(), dlo.data_ptr(), len(lb), None, None, 0,
-                                       nlong, 10_000, llt.data_ptr(), llh.data_ptr(), lln.data_ptr())
-            if rc != 0:
-                raise RuntimeError(L.mcg_last_error().decode())
-        for _ in range(2):
-            lstep()
+            check(L.mcg_query_batch_sharded_dev(db.h, comm.h, C.byref(q), lr.data_ptr(), lo.data_ptr(), nl_ * RL, None, None, 0, nl_, RL,
+                                                t_.data_ptr(), h_.data_ptr(), n_.data_ptr(), b_.data_ptr(), r_.data_ptr(), st_.data_ptr()))
+        lstep()
         barrier()
+        st_.zero_()
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        LS = 3
         f0.record(stream)
-        for _ in range(5):
+        for _ in range(LS):
             lstep()
         f1.record(stream)
         barrier()
-        lms = max_over_ranks(f0.elapsed_time(f1)) / 5
-        out["query_long"] = {"metric": "query_reads_per_s", "value": nlong / (lms * 1e-3), "unit": "reads/s",
-                             "bp_per_s": nlong * 10_000 / (lms * 1e-3), "ms_per_batch": lms,
-                             "workload": "%d single-end reads x 10 kbp (10 %% substitutions) per batch vs the shard of this rank "
-                                         "(%d x 5 Mbp over %d GPU(s)); per-shard top lists only" % (nlong, QG, world),
-                             "mean_candidates": float(lln.float().mean().item())}
+        lms = max_over_ranks(f0.elapsed_time(f1)) / LS
+        stl = st_.cpu().numpy()
+        out["query_long"] = {"metric": "query_reads_per_s", "value": nlong_tot / (lms * 1e-3), "unit": "reads/s",
+                             "bp_per_s": nlong_tot * RL / (lms * 1e-3), "ms_per_step": lms,
+                             "workload": "long reads, BASELINE.json configs[4] shape: %d single-end reads x 10 kbp (10 %% substitutions, ~89 windows / "
+                                         "~1400 features per read) per step = 10 %% of configs[4]'s 1 M reads, vs the same %d-shard database; staged path "
+                                         "(find, scan, gather, size-binned per-read sorters)" % (nlong_tot, world),
+                             "classified_per_step_this_rank": int(stl[20] // LS)}
     except Exception as e:
         out["query_long"] = {"error": repr(e)}
-    db.close()
-    # the reference's own build / query code (oracle/_ref, one MPI rank = one thread, as in the reference: build is
-    # single-threaded per rank, querying.h runs T such workers per rank) on a bounded sample of the same data
-    if world == 1 and not args.no_cpu:
-        try:
-            sys.path.insert(0, ROOT)
-            from oracle import pyoracle as po
-            if po.have_reference():
-                ref = po.Reference()
-                rdb = ref.db_create()
-                rdb.set_taxonomy(ids, par, rk)
-                ng = 4
-                t0 = time.perf_counter()
-                for g in range(ng):
-                    rdb.add_target(genomes[g], "SYN%06d.1" % g, int(species[g]), 1, 0)
-                tb = time.perf_counter() - t0
-                out["build"]["cpu_baseline"] = {"value": ng * GENOME_LEN / tb, "unit": "bp/s", "cores": 1, "kind": "reference",
-                                                "sample": "database::add_target_distributed on %d of the %d genomes (%d Mbp), one rank = "
-                                                          "one thread, %.1f s; the reference scales with the number of MPI ranks"
-                                                          % (ng, QG, ng * GENOME_LEN // 1_000_000, tb)}
-                sub = [genomes[g] for g in range(ng)]
-                sb1, so1, sb2, so2, _ = synth.make_read_pairs(sub, 20_000, seed=7)
-                t0 = time.perf_counter()
-                for i in range(20_000):
-                    rdb.query_local(sb1[so1[i]:so1[i + 1]], sb2[so2[i]:so2[i + 1]], 4, 4)
-                tq = time.perf_counter() - t0
-                out["query"]["cpu_baseline"] = {"value": 2 * 20_000 / tq, "unit": "reads/s", "cores": 1, "kind": "reference",
-                                                "sample": "accumulate_matches + candidate generation for 20000 pairs against the %d-genome "
-                                                          "database above, one worker thread, %.1f s (ctypes call per read included)" % (ng, tq)}
-        except Exception as e:      # pragma: no cover
-            out["build"]["cpu_baseline"] = {"error": repr(e)}
+    log("long reads extra done")
     return out
 
 
@@ -680,6 +730,7 @@ def main():
     os.dup2(2, 1)
     real_stdout = os.fdopen(saved, "w")
     global print_json
+
     def print_json(obj):
         real_stdout.write(json.dumps(obj) + "\n")
         real_stdout.flush()

@@ -105,6 +105,12 @@ int  mcg_ctx_sync(mcg_ctx*);
 void* mcg_ctx_stream(mcg_ctx*);
 /* number of kernels this library launched on the ctx since creation */
 int64_t mcg_ctx_launches(mcg_ctx*);
+/* measurement hook: while enabled, the library brackets every launch of its three dominant kernels with CUDA
+ * events on the ctx stream (no synchronisation: an event record costs the stream nothing).  mcg_ctx_kernel_times
+ * waits for the stream and returns the summed device time [ms] and the launch count per kernel since the
+ * last call: which = 0 sketch (K1), 1 fused query kernel (K3-K5), 2 radix-sort scatter (K2). */
+int  mcg_ctx_profile(mcg_ctx*, int enable);
+int  mcg_ctx_kernel_times(mcg_ctx*, int which, double* ms, int64_t* launches);
 /* device memory helpers for callers that keep data resident (bench, tests) */
 int  mcg_dev_alloc(mcg_ctx*, int64_t bytes, void** dptr);
 int  mcg_dev_free(mcg_ctx*, void* dptr);
@@ -144,6 +150,10 @@ int  mcg_db_destroy(mcg_db*);
  * out_windows[n] receives source.windows (0 for foreign targets); may be NULL. */
 int  mcg_db_add_targets(mcg_db*, const char* seq_bytes, const int64_t* seq_offsets,
                         const uint32_t* target_ids, int64_t n, uint32_t* out_windows);
+/* same with the sequence bytes resident on the device (seq_offsets and target_ids stay host arrays); the
+ * bytes must be 16-byte aligned and readable up to the last offset + 64 */
+int  mcg_db_add_targets_dev(mcg_db*, const char* d_seq_bytes, const int64_t* seq_offsets,
+                            const uint32_t* target_ids, int64_t n, uint32_t* out_windows);
 /* ends the insert phase: builds the feature -> location-list multimap with the
  * reference's capping semantics (hash_multimap.h:653,706; sketch_database.h:
  * 1089-1092: first maxlocs locations in ascending (tgt,win)) */

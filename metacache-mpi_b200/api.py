@@ -64,6 +64,9 @@ def load_library():
     L.mcg_ctx_stream.argtypes = [vp]
     L.mcg_ctx_launches.restype = i64
     L.mcg_ctx_launches.argtypes = [vp]
+    L.mcg_ctx_profile.argtypes = [vp, C.c_int]
+    L.mcg_ctx_kernel_times.argtypes = [vp, C.c_int, C.POINTER(C.c_double), C.POINTER(i64)]
+    L.mcg_db_add_targets_dev.argtypes = [vp, vp, vp, vp, i64, vp]
     L.mcg_dev_alloc.argtypes = [vp, i64, C.POINTER(vp)]
     L.mcg_dev_free.argtypes = [vp, vp]
     L.mcg_host_alloc.argtypes = [i64, C.POINTER(vp)]
@@ -163,6 +166,15 @@ class Context:
 
     def launches(self):
         return self.L.mcg_ctx_launches(self.h)
+
+    def profile(self, on=True):
+        _check(self.L.mcg_ctx_profile(self.h, 1 if on else 0))
+
+    def kernel_times(self, which):
+        """(summed device ms, launches) of kernel class `which` (0 sketch, 1 fused query, 2 radix scatter) since the last call"""
+        ms, n = C.c_double(), C.c_int64()
+        _check(self.L.mcg_ctx_kernel_times(self.h, which, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
 
     # ---- sketcher::operator() over all windows (hash_dna.h:115)
     def count_windows(self, cfg, offs):

@@ -614,8 +614,9 @@ int mcg_db_destroy(mcg_db* db)
     return MCG_OK;
 }
 
-int mcg_db_add_targets(mcg_db* db, const char* seq_bytes, const int64_t* seq_offsets,
-                       const uint32_t* target_ids, int64_t n, uint32_t* out_windows)
+// shared body of mcg_db_add_targets / mcg_db_add_targets_dev: `dev` = the sequences already are on the device
+static int add_targets(mcg_db* db, const char* seq_bytes, const int64_t* seq_offsets,
+                       const uint32_t* target_ids, int64_t n, uint32_t* out_windows, bool dev)
 {
     MCG_REQUIRE(db != nullptr && seq_offsets != nullptr && target_ids != nullptr, "mcg_db_add_targets: NULL argument");
     MCG_REQUIRE(n >= 0, "n < 0");
@@ -650,25 +651,30 @@ int mcg_db_add_targets(mcg_db* db, const char* seq_bytes, const int64_t* seq_off
     }
     MCG_REQUIRE((db->nwin + uint64_t(nwin)) * uint64_t(s) < (1ull << 32),
                 "shard would exceed 2^32-1 feature slots");
-    // stage the owned sequences contiguously on the device
-    MCG_TRY(c->seq.reserve(size_t(total) + 64));
-    MCG_TRY(c->seqoff.reserve(size_t(m + 1) * 8));
-    {
+    // the owned sequences contiguously on the device: staged from the host, or -- device input whose
+    // targets all belong to this shard -- used where they lie
+    const bool in_place = dev && m == n;
+    const char* d_seq = seq_bytes + seq_offsets[0];
+    if(!in_place) {
+        MCG_TRY(c->seq.reserve(size_t(total) + 64));
         int64_t j = 0;
         while(j < m) {                  // coalesce runs of adjacent source targets into one copy
             int64_t e = j;
             while(e + 1 < m && src[e + 1] == src[e] + 1) ++e;
             const int64_t b0 = seq_offsets[src[j]], b1 = seq_offsets[src[e] + 1];
-            MCG_TRY(copy_in(c, c->seq.as<char>() + offs[j], seq_bytes + b0, size_t(b1 - b0)));
+            MCG_CUDA(cudaMemcpyAsync(c->seq.as<char>() + offs[j], seq_bytes + b0, size_t(b1 - b0),
+                                     dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
             j = e + 1;
         }
+        d_seq = c->seq.as<char>();
     }
+    MCG_TRY(c->seqoff.reserve(size_t(m + 1) * 8));
     MCG_TRY(copy_in(c, c->seqoff.p, offs.data(), size_t(m + 1) * 8));
     // append the sketches of the new windows to the slot array
     MCG_TRY(db->feat.reserve_keep((db->nwin + uint64_t(nwin)) * s * 4, db->nwin * s * 4, c->stream));
     MCG_TRY(c->winfirst.reserve(size_t(m + 2) * 4));
     MCG_TRY(window_prefix(c, db->cfg.winlen, db->cfg.winstride, c->seqoff.as<int64_t>(), m, c->winfirst.as<uint32_t>(), nullptr));
-    MCG_TRY(sketch_launch(c, db->cfg, s, db->cfg.winlen, db->cfg.winstride, c->seq.as<char>(), total,
+    MCG_TRY(sketch_launch(c, db->cfg, s, db->cfg.winlen, db->cfg.winstride, d_seq, total,
                           c->seqoff.as<int64_t>(), m, c->winfirst.as<uint32_t>(), c->winfirst.as<uint32_t>(),
                           uint64_t(nwin), db->feat.as<uint32_t>() + db->nwin * s, nullptr));
     MCG_CUDA(cudaStreamSynchronize(c->stream));       // offs (host vector) was a copy source
@@ -679,6 +685,21 @@ int mcg_db_add_targets(mcg_db* db, const char* seq_bytes, const int64_t* seq_off
     }
     db->nwin += uint64_t(nwin);
     return MCG_OK;
+}
+
+int mcg_db_add_targets(mcg_db* db, const char* seq_bytes, const int64_t* seq_offsets,
+                       const uint32_t* target_ids, int64_t n, uint32_t* out_windows)
+{
+    return add_targets(db, seq_bytes, seq_offsets, target_ids, n, out_windows, false);
+}
+
+int mcg_db_add_targets_dev(mcg_db* db, const char* d_seq_bytes, const int64_t* seq_offsets,
+                           const uint32_t* target_ids, int64_t n, uint32_t* out_windows)
+{
+    MCG_REQUIRE(n == 0 || d_seq_bytes != nullptr, "mcg_db_add_targets_dev: NULL argument");
+    MCG_REQUIRE(n == 0 || ((reinterpret_cast<uintptr_t>(d_seq_bytes) + uintptr_t(seq_offsets ? seq_offsets[0] : 0)) & 15u) == 0,
+                "device sequences must be 16-byte aligned");
+    return add_targets(db, d_seq_bytes, seq_offsets, target_ids, n, out_windows, true);
 }
 
 int mcg_db_finalize(mcg_db* db)

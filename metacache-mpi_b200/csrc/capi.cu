@@ -257,6 +257,32 @@ void* mcg_ctx_stream(mcg_ctx* c) { return c ? static_cast<void*>(c->stream) : nu
 
 int64_t mcg_ctx_launches(mcg_ctx* c) { return c ? c->launches : 0; }
 
+int mcg_ctx_profile(mcg_ctx* c, int enable)
+{
+    MCG_REQUIRE(c != nullptr, "ctx is NULL");
+    c->profile = enable != 0;
+    return MCG_OK;
+}
+
+int mcg_ctx_kernel_times(mcg_ctx* c, int which, double* ms, int64_t* launches)
+{
+    MCG_REQUIRE(c != nullptr && which >= 0 && which < 3, "mcg_ctx_kernel_times: bad argument");
+    MCG_CUDA(cudaSetDevice(c->device));
+    MCG_CUDA(cudaStreamSynchronize(c->stream));
+    double tot = 0.0;
+    std::vector<cudaEvent_t>& ev = c->prof_ev[which];
+    for(size_t i = 0; i + 1 < ev.size(); i += 2) {
+        float t = 0.f;
+        if(cudaEventSynchronize(ev[i + 1]) == cudaSuccess && cudaEventElapsedTime(&t, ev[i], ev[i + 1]) == cudaSuccess) tot += double(t);
+        cudaEventDestroy(ev[i]); cudaEventDestroy(ev[i + 1]);
+    }
+    cudaGetLastError();
+    if(ms) *ms = tot;
+    if(launches) *launches = int64_t(ev.size() / 2);
+    ev.clear();
+    return MCG_OK;
+}
+
 int mcg_dev_alloc(mcg_ctx* c, int64_t bytes, void** dptr)
 {
     MCG_REQUIRE(c != nullptr && dptr != nullptr && bytes >= 0, "mcg_dev_alloc: bad argument");

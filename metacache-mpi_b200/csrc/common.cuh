@@ -93,6 +93,22 @@ struct mcg_ctx {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     int64_t launches = 0;
+    // measurement hook (mcg_ctx_profile): event pairs around the launches of the dominant kernels
+    bool profile = false;
+    std::vector<cudaEvent_t> prof_ev[3];      // start, stop, start, stop, ... per kernel class
+    void prof_begin(int which, cudaStream_t st)
+    {
+        if(!profile) return;
+        cudaEvent_t a = nullptr, b = nullptr;
+        cudaEventCreate(&a); cudaEventCreate(&b);
+        prof_ev[which].push_back(a); prof_ev[which].push_back(b);
+        cudaEventRecord(a, st);
+    }
+    void prof_end(int which, cudaStream_t st)
+    {
+        if(!profile || prof_ev[which].empty()) return;
+        cudaEventRecord(prof_ev[which].back(), st);
+    }
     // taxonomy tables (replicated per GPU)
     mcg::DevBuf lineage, rank;
     int64_t ntaxa = 0, ntargets = 0;

@@ -1341,8 +1341,10 @@ static int qa_fused(mcg_db* db, const mcg_query_opts* o, QPart& part, int slot, 
         g = unsigned(std::min<uint64_t>(uint64_t(n + 63) / 64, uint64_t(c->num_sms) * uint64_t(std::max(1, per_sm)))); \
         kern<<<g, 256, smem, c->stream>>>(p, f);                                                                     \
     } while(0)
+    c->prof_begin(1, c->stream);
     if(db->key32) { if(nc2) QF_LAUNCH(uint32_t, 2); else QF_LAUNCH(uint32_t, 4); }
     else          { if(nc2) QF_LAUNCH(uint64_t, 2); else QF_LAUNCH(uint64_t, 4); }
+    c->prof_end(1, c->stream);
 #undef QF_LAUNCH
 #undef QF_LAUNCH_CAP
     c->launches++;

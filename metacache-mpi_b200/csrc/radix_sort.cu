@@ -200,8 +200,10 @@ int radix_sort_pairs(mcg_ctx* c, uint32_t* keys, uint32_t* vals, uint32_t* keys_
         else               rs_hist_kernel<512><<<ntiles, 512, 0, c->stream>>>(ki, n, shift, hist, ntiles);
         c->launches++;
         MCG_TRY(exclusive_scan_u32_to_u32(c, hist, hist, nh));
+        c->prof_begin(2, c->stream);
         if(threads == 256) rs_scatter_kernel<256><<<ntiles, 256, smem, c->stream>>>(ki, vi, ko, vo, n, shift, hist, ntiles, iota);
         else               rs_scatter_kernel<512><<<ntiles, 512, smem, c->stream>>>(ki, vi, ko, vo, n, shift, hist, ntiles, iota);
+        c->prof_end(2, c->stream);
         c->launches++;
         MCG_CUDA(cudaGetLastError());
         uint32_t* t = ki; ki = ko; ko = t;

@@ -552,7 +552,13 @@ int sketch_launch(mcg_ctx* c, const mcg_sketch_cfg& cfg, int sketchlen, int64_t 
                                                                          p.tile_ctr);
     c->launches++;
     p.cta_seq = tile_seq;
-    if(tpw) return tpw_launch(c, p, cfg, nblocks, stream);
+    if(tpw) {
+        c->prof_begin(0, stream);
+        const int rc = tpw_launch(c, p, cfg, nblocks, stream);
+        c->prof_end(0, stream);
+        return rc;
+    }
+    c->prof_begin(0, stream);
 #define SK_LAUNCH(K16, PT)                                                                                        \
     do {                                                                                                          \
         auto kern = sketch_kernel<K16, PT>;                                                                       \
@@ -567,6 +573,7 @@ int sketch_launch(mcg_ctx* c, const mcg_sketch_cfg& cfg, int sketchlen, int64_t 
     else if(cfg.k == 16)                           SK_LAUNCH(true, 0);
     else                                           SK_LAUNCH(false, 0);
 #undef SK_LAUNCH
+    c->prof_end(0, stream);
     c->launches++;
     MCG_CUDA(cudaGetLastError());
     return MCG_OK;

@@ -165,3 +165,134 @@ def write_taxonomy_files(dirname, ids, parents, ranks):
     with open(os.path.join(dirname, "names.dmp"), "w") as f:
         for i in ids:
             f.write("%d\t|\ttaxon%d\t|\t\t|\tscientific name\t|\n" % (i, i))
+
+
+# ---- counter-based generator ("bases iid uniform from a counter-based PRNG, e.g. splitmix64") -------
+# Same shapes as genome() / make_read_pairs() above, but every base is a pure function of (stream, genome, position):
+# any slice can be produced anywhere -- on the GPU with torch ops at configs[2] / configs[3] size (20 Gbp, 50 M
+# pairs), on the CPU with the same code for the reference arm and the tests.  Bench data only; the parity tests keep
+# the numpy generator above.
+_M64 = (1 << 64) - 1
+
+
+def _i64(x):
+    """python int (mod 2^64) -> the same bit pattern as a signed 64-bit value (torch has no uint64 arithmetic)"""
+    x &= _M64
+    return x - (1 << 64) if x >= (1 << 63) else x
+
+
+def splitmix64_py(x):
+    z = (x + 0x9E3779B97F4A7C15) & _M64
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & _M64
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & _M64
+    return z ^ (z >> 31)
+
+
+def _lsr(z, k):
+    """logical shift right of int64 tensors"""
+    return (z >> k) & ((1 << (64 - k)) - 1)
+
+
+def splitmix64_t(x):
+    """splitmix64 on torch int64 tensors (two's complement wrap-around == arithmetic mod 2^64)"""
+    z = x + _i64(0x9E3779B97F4A7C15)
+    z = (z ^ _lsr(z, 30)) * _i64(0xBF58476D1CE4E5B9)
+    z = (z ^ _lsr(z, 27)) * _i64(0x94D049BB133111EB)
+    return z ^ _lsr(z, 31)
+
+
+def _key(stream, g):
+    return _i64(splitmix64_py((GENOME_SEED << 8) + stream) ^ ((g & 0xFFFFFF) << 40))
+
+
+def hash_py(stream, g, pos):
+    return splitmix64_py((splitmix64_py((GENOME_SEED << 8) + stream) ^ ((g & 0xFFFFFF) << 40) ^ pos) & _M64)
+
+
+def genome_fast(g, length, device="cpu", out=None):
+    """genome g as a torch uint8 tensor: even g = iid uniform ACGT, odd g = genome g-1 with 5 % substitutions,
+    0.1 % of the aligned 50-base blocks are runs of 'N', 1 % of the positions lower-cased"""
+    import torch
+    pos = torch.arange(length, dtype=torch.int64, device=device)
+    acgt = torch.tensor([65, 67, 71, 84], dtype=torch.uint8, device=device)
+    base_g = g - (g % 2)
+    code = _lsr(splitmix64_t(pos ^ _key(0, base_g)), 62)
+    if g % 2 == 1:
+        sub = _lsr(splitmix64_t(pos ^ _key(1, g)), 32) < int(0.05 * (1 << 32))
+        code = torch.where(sub, _lsr(splitmix64_t(pos ^ _key(2, g)), 62), code)
+    s = acgt[code]
+    nrun = _lsr(splitmix64_t((pos // 50) ^ _key(3, g)), 32) < int(0.001 * (1 << 32))
+    s = torch.where(nrun, torch.full_like(s, 78), s)
+    low = _lsr(splitmix64_t(pos ^ _key(4, g)), 32) < int(0.01 * (1 << 32))
+    s = torch.where(low, s | 0x20, s)
+    if out is not None:
+        out.copy_(s)
+        return out
+    return s
+
+
+def read_pairs_fast(genomes, glen, npairs, first_pair=0, readlen=150, seed=7, sub=0.01, insert=(300, 500), chunk=1 << 17):
+    """`npairs` read pairs (global pair indices first_pair ...) sampled from `genomes`: a 1-D torch uint8 tensor of
+    len(genomes) // glen genomes of glen bases back to back, on any device.  Same shape as make_read_pairs():
+    insert size U[insert], mate 1 = first readlen bases of the fragment, mate 2 = reverse complement of its last
+    readlen bases, `sub` substitutions of which 1 in 5 an 'N'.  Returns (b1, b2, genome index per pair) on that device."""
+    import torch
+    dev = genomes.device
+    G = genomes.numel() // glen
+    comp = torch.arange(256, dtype=torch.uint8, device=dev)
+    for a, b in zip(b"ACGTacgt", b"TGCAtgca"):
+        comp[a] = b
+    acgt = torch.tensor([65, 67, 71, 84], dtype=torch.uint8, device=dev)
+    b1 = torch.empty(npairs * readlen, dtype=torch.uint8, device=dev)
+    b2 = torch.empty(npairs * readlen, dtype=torch.uint8, device=dev)
+    gsel_all = torch.empty(npairs, dtype=torch.int64, device=dev)
+    ar = torch.arange(readlen, dtype=torch.int64, device=dev)
+    k = [_i64(splitmix64_py((seed << 16) + i)) for i in range(8)]
+    for lo in range(0, npairs, chunk):
+        hi = min(lo + chunk, npairs)
+        idx = torch.arange(first_pair + lo, first_pair + hi, dtype=torch.int64, device=dev)
+        gsel = _lsr(splitmix64_t(idx ^ k[0]), 1) % G
+        ins = insert[0] + _lsr(splitmix64_t(idx ^ k[1]), 1) % (insert[1] - insert[0] + 1)
+        p = _lsr(splitmix64_t(idx ^ k[2]), 1) % (glen - ins + 1) + gsel * glen
+        m1 = genomes[(p[:, None] + ar[None, :]).reshape(-1)]
+        e = p + ins - 1
+        m2 = comp[genomes[(e[:, None] - ar[None, :]).reshape(-1)].long()]
+        for mate, m in ((0, m1), (1, m2)):
+            j = (idx[:, None] * readlen + ar[None, :]).reshape(-1)
+            h = splitmix64_t(j ^ k[3 + mate])
+            hit = _lsr(h, 32) < int(sub * (1 << 32))
+            nb = acgt[_lsr(splitmix64_t(j ^ k[5 + mate]), 62)]
+            nb = torch.where((_lsr(h, 3) & 0xFFFF) % 5 == 0, torch.full_like(nb, 78), nb)
+            m.copy_(torch.where(hit, nb, m))
+        b1[lo * readlen:hi * readlen] = m1
+        b2[lo * readlen:hi * readlen] = m2
+        gsel_all[lo:hi] = gsel
+    return b1, b2, gsel_all
+
+
+def long_reads_fast(genomes, glen, nreads, first_read=0, readlen=10000, seed=11, sub=0.10, chunk=1 << 11):
+    """`nreads` single-end reads of `readlen` bases, random strand, `sub` substitutions (configs[4] shape)"""
+    import torch
+    dev = genomes.device
+    G = genomes.numel() // glen
+    comp = torch.arange(256, dtype=torch.uint8, device=dev)
+    for a, b in zip(b"ACGTacgt", b"TGCAtgca"):
+        comp[a] = b
+    acgt = torch.tensor([65, 67, 71, 84], dtype=torch.uint8, device=dev)
+    out = torch.empty(nreads * readlen, dtype=torch.uint8, device=dev)
+    ar = torch.arange(readlen, dtype=torch.int64, device=dev)
+    k = [_i64(splitmix64_py((seed << 16) + 100 + i)) for i in range(6)]
+    for lo in range(0, nreads, chunk):
+        hi = min(lo + chunk, nreads)
+        idx = torch.arange(first_read + lo, first_read + hi, dtype=torch.int64, device=dev)
+        gsel = _lsr(splitmix64_t(idx ^ k[0]), 1) % G
+        p = _lsr(splitmix64_t(idx ^ k[1]), 1) % (glen - readlen + 1) + gsel * glen
+        rev = (_lsr(splitmix64_t(idx ^ k[2]), 40) & 1) == 1
+        fwd = genomes[(p[:, None] + ar[None, :]).reshape(-1)].view(hi - lo, readlen)
+        bwd = comp[genomes[((p + readlen - 1)[:, None] - ar[None, :]).reshape(-1)].long()].view(hi - lo, readlen)
+        m = torch.where(rev[:, None], bwd, fwd).reshape(-1)
+        j = (idx[:, None] * readlen + ar[None, :]).reshape(-1)
+        hit = _lsr(splitmix64_t(j ^ k[3]), 32) < int(sub * (1 << 32))
+        nb = acgt[_lsr(splitmix64_t(j ^ k[4]), 62)]
+        out[lo * readlen:hi * readlen] = torch.where(hit, nb, m)
+    return out

@@ -282,6 +282,81 @@ int64_t mco_db_add_target(mco_db* d, const char* seq, int64_t len, uint32_t targ
     return nw;
 }
 
+/* bench.py's parity sample at full database size: the lists of a GIVEN set of features only.  A database
+ * restricted to the keys in allowed[] (ascending) answers lookups of those keys exactly like the whole
+ * database (every list is built from the same insertions in the same order), and sketching -- the part that
+ * cannot be skipped -- runs on `threads` pthreads over the targets. */
+typedef struct {
+    const mco_db* d; const char* buf; const int64_t* offs; const uint32_t* ids; int64_t n;
+    const uint32_t* allowed; int64_t nallowed;
+    int64_t* next; pthread_mutex_t* mtx;
+    tuple3* tup; uint64_t ntup, captup; int64_t wins;
+} rs_arg;
+
+static int key_allowed(const uint32_t* a, int64_t n, uint32_t key)
+{
+    int64_t lo = 0, hi = n;
+    while(lo < hi) { const int64_t mid = (lo + hi) / 2; if(a[mid] < key) lo = mid + 1; else hi = mid; }
+    return lo < n && a[lo] == key;
+}
+
+static void* rs_worker(void* p)
+{
+    rs_arg* a = (rs_arg*)p;
+    uint32_t tmp[256];
+    for(;;) {
+        pthread_mutex_lock(a->mtx);
+        const int64_t q = (*a->next)++;
+        pthread_mutex_unlock(a->mtx);
+        if(q >= a->n) break;
+        if((int)(a->ids[q] % (uint32_t)a->d->nshards) != a->d->shard) continue;        /* sketch_database.h:540 */
+        const char* s = a->buf + a->offs[q];
+        const int64_t len = a->offs[q + 1] - a->offs[q];
+        const int64_t nw = mco_num_windows(len, a->d->winlen, a->d->stride);
+        for(int64_t w = 0; w < nw; ++w) {
+            int64_t b, e;
+            mco_window(len, a->d->winlen, a->d->stride, w, &b, &e);
+            const int c = mco_sketch_window(s + b, e - b, a->d->k, a->d->sketchlen, tmp);
+            for(int i = 0; i < c; ++i) {
+                if(!key_allowed(a->allowed, a->nallowed, tmp[i])) continue;
+                if(a->ntup + 1 > a->captup) { a->captup = a->captup ? a->captup * 2 : 4096; a->tup = (tuple3*)realloc(a->tup, a->captup * sizeof(tuple3)); }
+                a->tup[a->ntup++] = (tuple3){tmp[i], a->ids[q], (uint32_t)w};
+            }
+        }
+        a->wins += nw;
+    }
+    return NULL;
+}
+
+int64_t mco_db_add_targets_restricted(mco_db* d, const char* buf, const int64_t* offs, const uint32_t* ids, int64_t n,
+                                      const uint32_t* allowed, int64_t nallowed, int threads)
+{
+    if(threads < 1) threads = 1;
+    if(threads > 256) threads = 256;
+    pthread_t th[256];
+    rs_arg args[256];
+    int64_t next = 0, wins = 0;
+    pthread_mutex_t mtx = PTHREAD_MUTEX_INITIALIZER;
+    for(int t = 0; t < threads; ++t) {
+        args[t] = (rs_arg){d, buf, offs, ids, n, allowed, nallowed, &next, &mtx, NULL, 0, 0, 0};
+        pthread_create(&th[t], NULL, rs_worker, &args[t]);
+    }
+    for(int t = 0; t < threads; ++t) {
+        pthread_join(th[t], NULL);
+        if(d->ntup + args[t].ntup > d->captup) {
+            d->captup = d->captup ? d->captup : (1u << 16);
+            while(d->captup < d->ntup + args[t].ntup) d->captup *= 2;
+            d->tup = (tuple3*)realloc(d->tup, d->captup * sizeof(tuple3));
+        }
+        if(args[t].ntup) memcpy(d->tup + d->ntup, args[t].tup, args[t].ntup * sizeof(tuple3));
+        d->ntup += args[t].ntup;
+        wins += args[t].wins;
+        free(args[t].tup);
+    }
+    d->finalized = 0;          /* finalize sorts by (key, tgt, win): the order the threads finished in is irrelevant */
+    return wins;
+}
+
 static int cmp_tuple(const void* a, const void* b)
 {
     const tuple3* x = (const tuple3*)a;

@@ -108,6 +108,9 @@ class Oracle:
         L.mco_db_maxlocs.argtypes = [C.c_void_p]
         L.mco_db_add_target.restype = C.c_int64
         L.mco_db_add_target.argtypes = [C.c_void_p, C.c_char_p, C.c_int64, C.c_uint32]
+        L.mco_db_add_targets_restricted.restype = C.c_int64
+        L.mco_db_add_targets_restricted.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                                    C.c_void_p, C.c_int64, C.c_int]
         L.mco_db_finalize.argtypes = [C.c_void_p]
         L.mco_db_counts.argtypes = [C.c_void_p] + [C.POINTER(C.c_uint64)] * 3
         L.mco_db_export.argtypes = [C.c_void_p, _u32p, _u32p, _u32p, _u32p]
@@ -237,6 +240,15 @@ class OracleDB:
     def add_target(self, seq, target_id):
         s = _bytes(seq)
         return self.o.L.mco_db_add_target(self.h, s, len(s), target_id)
+
+    def add_targets_restricted(self, buf, offs, ids, allowed, threads=1):
+        """many targets at once, multi-threaded, keeping only the features in `allowed` (see mc_oracle.h)"""
+        buf = np.ascontiguousarray(buf, np.uint8)
+        offs = np.ascontiguousarray(offs, np.int64)
+        ids = np.ascontiguousarray(ids, np.uint32)
+        allowed = np.unique(np.ascontiguousarray(allowed, np.uint32))
+        return self.o.L.mco_db_add_targets_restricted(self.h, buf.ctypes.data, offs.ctypes.data, ids.ctypes.data, len(ids),
+                                                      allowed.ctypes.data, len(allowed), threads)
 
     def finalize(self):
         self.o.L.mco_db_finalize(self.h)

@@ -61,21 +61,77 @@ def test_sorting_network_include_is_valid():
 
 
 def test_bench_reference_arm_prints_the_contract_line():
-    """`bench.py --impl reference` (the reference's own sketcher on the host cores, no GPU) prints one JSON
-    line with the keys of the measurement contract"""
+    """`bench.py --impl reference` (the reference PROGRAM under the MPI shim on the host cores, no GPU) prints one
+    JSON line with the keys of the measurement contract; here on a tiny sample (2 genomes, 2000 pairs)"""
     import json
     import os
     import subprocess
     import sys
+    import pytest
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0", "--mbp", "10"],
+    if not os.path.exists(os.path.join(root, "oracle", "_ref", "metacache_mpi_ref")):
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--ref-genomes", "2", "--ref-pairs", "2000"],
                        stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=600, cwd=root)
     assert r.returncode == 0, r.stderr.decode()[-2000:]
     lines = [l for l in r.stdout.decode().splitlines() if l.strip()]
     assert len(lines) == 1
     d = json.loads(lines[0])
-    assert d["impl"] == "reference" and d["metric"] == "sketch_bp_per_s" and d["unit"] == "bp/s" and d["higher_is_better"] is True
+    assert d["impl"] == "reference" and d["metric"] == "query_reads_per_s" and d["unit"] == "reads/s" and d["higher_is_better"] is True
     assert d["value"] > 0 and d["steps"] == 1 and d["n_gpus"] == 1
-    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
+    assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
-    assert "workload" in d["config"] and "sample" in d["config"]
+    assert "workload" in d["config"] and "sample" in d["config"] and "configs[3]" in d["config"]["workload"]
+    assert d["build"]["value"] > 0
+
+
+def test_counter_based_generator_follows_its_specification():
+    """synth.genome_fast / read_pairs_fast (bench data, torch ops on any device) against the scalar definition"""
+    import torch
+    from metacache_mpi_b200 import synth
+    L = 20000
+    g2, g3 = synth.genome_fast(2, L), synth.genome_fast(3, L)
+    for pos in (0, 1, 49, 50, 777, L - 1):
+        want = "ACGT"[synth.hash_py(0, 2, pos) >> 62]
+        if (synth.hash_py(3, 2, pos // 50) >> 32) < int(0.001 * (1 << 32)):
+            want = "N"
+        if (synth.hash_py(4, 2, pos) >> 32) < int(0.01 * (1 << 32)) and want != "N":
+            want = want.lower()
+        elif (synth.hash_py(4, 2, pos) >> 32) < int(0.01 * (1 << 32)):
+            want = chr(ord("N") | 0x20)
+        assert chr(int(g2[pos])) == want
+    diff = float((g2 != g3).float().mean())
+    assert 0.03 < diff < 0.08                                  # 5 % substitutions (3/4 of them change the base) + own N / case
+    assert (synth.genome_fast(2, L) == g2).all()               # pure function of (genome, position)
+    cat = torch.cat([g2, g3])
+    b1, b2, gs = synth.read_pairs_fast(cat, L, 500)
+    assert b1.numel() == 500 * 150 and set(gs.tolist()) == {0, 1}
+    c1, c2, _ = synth.read_pairs_fast(cat, L, 100, first_pair=200)
+    assert (c1 == b1[200 * 150:300 * 150]).all() and (c2 == b2[200 * 150:300 * 150]).all()     # slices of one stream
+    assert 0.0005 < float((b1 == 78).float().mean()) < 0.01
+
+
+def test_oracle_restricted_build_answers_like_the_whole_database(oracle):
+    """bench.py's parity sample: a database restricted to the sample's features (multi-threaded build) gives the same
+    per-read lists, taxa and statistics as the whole database"""
+    import numpy as np
+    from oracle import pyoracle as po
+    from util import World
+    w = World(G=8, L=30000, npairs=60)
+    full = w.oracle_shards(oracle, 2, maxlocs=5)
+    f1, _ = oracle.sketch_sequences(w.b1, w.o1)
+    f2, _ = oracle.sketch_sequences(w.b2, w.o2)
+    allowed = np.unique(np.concatenate([f1.ravel(), f2.ravel()]))
+    allowed = allowed[allowed != 0xFFFFFFFF]
+    rs = []
+    for r in range(2):
+        d = oracle.db_create(shard=r, nshards=2, maxlocs=5)
+        d.add_targets_restricted(w.buf, w.offs, np.arange(w.G, dtype=np.uint32), allowed, threads=3)
+        d.finalize()
+        rs.append(d)
+        assert d.counts()[0] < full[r].counts()[0]
+    q = po.make_qopt(maxcand=4, lowest=4, hitmin=4, hitdiff=0.8)
+    a = oracle.query_batch(full, w.tax, q, w.b1, w.o1, w.b2, w.o2)
+    b = oracle.query_batch(rs, w.tax, q, w.b1, w.o1, w.b2, w.o2)
+    assert all((x == y).all() for x, y in zip(a, b))
