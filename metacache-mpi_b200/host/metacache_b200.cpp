@@ -1349,6 +1349,49 @@ int mode_selftest_shard(const Args& a)
     return ok ? 0 : 1;
 }
 
+// shards-equal <file a> <file b>: same header parameters, taxa, target count and -- order-insensitively, the
+// reference writes buckets in hash-table order -- the same buckets with the same location lists
+int mode_shards_equal(const Args& a)
+{
+    if(a.pos.size() < 2) die("usage: metacache_b200 shards-equal <shard file> <shard file>");
+    DbMeta m[2];
+    std::vector<uint32_t> keys[2], sizes[2], tg[2], wn[2];
+    for(int i = 0; i < 2; ++i) read_shard(a.pos[size_t(i)], m[i], false, keys[i], sizes[i], tg[i], wn[i]);
+    bool ok = m[0].tcfg.k == m[1].tcfg.k && m[0].tcfg.sketchlen == m[1].tcfg.sketchlen && m[0].tcfg.winlen == m[1].tcfg.winlen &&
+              m[0].tcfg.winstride == m[1].tcfg.winstride && m[0].qsketch == m[1].qsketch && m[0].qwinlen == m[1].qwinlen &&
+              m[0].qstride == m[1].qstride && m[0].maxlocs == m[1].maxlocs && m[0].ntargets == m[1].ntargets &&
+              m[0].tax.taxa.size() == m[1].tax.taxa.size() && keys[0].size() == keys[1].size() && tg[0].size() == tg[1].size();
+    if(ok) {
+        auto ia = m[0].tax.taxa.begin(), ib = m[1].tax.taxa.begin();
+        for(; ia != m[0].tax.taxa.end(); ++ia, ++ib) {
+            const Taxon &x = ia->second, &y = ib->second;
+            auto base = [](const std::string& f) { const size_t p = f.rfind('/'); return p == std::string::npos ? f : f.substr(p + 1); };
+            if(x.id != y.id || x.parent != y.parent || x.rank != y.rank || x.name != y.name || base(x.file) != base(y.file) ||
+               x.index != y.index || x.windows != y.windows) { ok = false; break; }
+        }
+    }
+    if(ok) {
+        // bucket order by key on both sides
+        std::vector<uint64_t> start[2];
+        std::vector<uint32_t> ord[2];
+        for(int i = 0; i < 2; ++i) {
+            start[i].assign(keys[i].size() + 1, 0);
+            for(size_t j = 0; j < keys[i].size(); ++j) start[i][j + 1] = start[i][j] + sizes[i][j];
+            ord[i].resize(keys[i].size());
+            for(size_t j = 0; j < ord[i].size(); ++j) ord[i][j] = uint32_t(j);
+            std::sort(ord[i].begin(), ord[i].end(), [&](uint32_t x, uint32_t y) { return keys[i][x] < keys[i][y]; });
+        }
+        for(size_t j = 0; j < ord[0].size() && ok; ++j) {
+            const uint32_t x = ord[0][j], y = ord[1][j];
+            if(keys[0][x] != keys[1][y] || sizes[0][x] != sizes[1][y]) { ok = false; break; }
+            const uint64_t n = sizes[0][x];
+            if(std::memcmp(&tg[0][start[0][x]], &tg[1][start[1][y]], n * 4) != 0 || std::memcmp(&wn[0][start[0][x]], &wn[1][start[1][y]], n * 4) != 0) ok = false;
+        }
+    }
+    std::cout << (ok ? "shards equal" : "shards DIFFER") << ": " << keys[0].size() << " buckets, " << tg[0].size() << " locations" << std::endl;
+    return ok ? 0 : 1;
+}
+
 // selftest-abundance <taxonomy dir> <rank> <taxid:count> ...: the two tables of -abundances / -abundance-per
 int mode_selftest_abundance(const Args& a)
 {
@@ -1395,6 +1438,7 @@ int main(int argc, char** argv)
     else if(mode == "query") rc = mode_query(a);
     else if(mode == "selftest-shard") return mode_selftest_shard(a);
     else if(mode == "selftest-abundance") return mode_selftest_abundance(a);
+    else if(mode == "shards-equal") return mode_shards_equal(a);
     else die("unknown mode '" + mode + "' (build and query are implemented, like in the reference: README.md:37)");
     wait_gpu_init();
     total("whole run before teardown");
