@@ -66,7 +66,7 @@ def parse_args():
     ap.add_argument("--impl", default="mcgpu", choices=["mcgpu", "reference"])
     ap.add_argument("--db-mbp", type=int, default=2500, help="Mbp of reference genomes per GPU (default = configs[2] / 8)")
     ap.add_argument("--pairs", type=int, default=1_000_000, help="read pairs per step, whole job")
-    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--e2e-steps", type=int, default=6)
     ap.add_argument("--no-extras", action="store_true", help="skip the sketch / build / long-read extra objects")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
     ap.add_argument("--no-check", action="store_true", help="skip the oracle sample check")
@@ -378,8 +378,9 @@ def run_mcgpu(args):
         r1, r2, _ = synth.read_pairs_fast(gview, GLEN, n_loc, first_pair=b * args.pairs + bnd[rank], seed=7 + b)
         pad = torch.zeros(64, dtype=torch.uint8, device=dev)
         slices.append((torch.cat([r1, pad]), torch.cat([r2, pad])))
-    offs = np.arange(n_loc + 1, dtype=np.int64) * READLEN
-    d_offs = torch.from_numpy(offs).to(dev)
+    offs_t = (torch.arange(n_loc + 1, dtype=torch.int64) * READLEN).pin_memory()       # pinned like the reads
+    offs = offs_t.numpy()
+    d_offs = offs_t.to(dev)
     nbytes = n_loc * READLEN
     q = api.make_query_opts(**QFLAGS)
     o_t = torch.empty((max(n_loc, 1), KC), dtype=torch.int32, device=dev)
@@ -404,7 +405,8 @@ def run_mcgpu(args):
     barrier()
     d_stats.zero_()
     ctx.profile(True)
-    ctx.kernel_times(0); ctx.kernel_times(1)
+    for w_ in range(8):
+        ctx.kernel_times(w_)
     l0 = ctx.launches()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler.start()
@@ -417,6 +419,10 @@ def run_mcgpu(args):
     launches = ctx.launches() - l0
     fused_ms, fused_n = ctx.kernel_times(1)
     qk1_ms, qk1_n = ctx.kernel_times(0)
+    phases = {name: ctx.kernel_times(w)[0] / max(args.steps, 1) for w, name in
+              ((3, "bookkeeping_and_K1_of_the_slice"), (4, "exchange_of_sketches"), (5, "left_over_reads_staged_path"),
+               (6, "exchange_of_top_lists"), (7, "merge_and_decision"))}
+    phases["fused_kernel"] = fused_ms / max(args.steps, 1)
     ctx.profile(False)
     stats_dev = d_stats.cpu().numpy().astype(np.int64)
     value = 2.0 * args.pairs * args.steps / (dev_ms * 1e-3)
@@ -497,6 +503,7 @@ def run_mcgpu(args):
                      "formula": "len1 + len2 + 32 B x F (F = 64 feature probes) + 8 B x M (locations gathered) + 8 B x K (SURVEY 8d), x %d pairs per launch" % args.pairs,
                      "note": "random 128-byte line fills (one per probe) + dependent location gathers: the kernel is latency / issue bound, see profiles/"},
         "sketch_in_query": {"ms_per_step": qk1_ms / max(args.steps, 1), "launches": int(qk1_n)},
+        "phases_ms_per_step_rank0": phases,
     }
     line.update(out_extra)
 

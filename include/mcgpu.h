@@ -108,7 +108,9 @@ int64_t mcg_ctx_launches(mcg_ctx*);
 /* measurement hook: while enabled, the library brackets every launch of its three dominant kernels with CUDA
  * events on the ctx stream (no synchronisation: an event record costs the stream nothing).  mcg_ctx_kernel_times
  * waits for the stream and returns the summed device time [ms] and the launch count per kernel since the
- * last call: which = 0 sketch (K1), 1 fused query kernel (K3-K5), 2 radix-sort scatter (K2). */
+ * last call: which = 0 sketch (K1), 1 fused query kernel (K3-K5), 2 radix-sort scatter (K2); phases of the
+ * sharded query: 3 window bookkeeping + K1 of the slice, 4 exchange of sketches, 5 left-over reads (staged
+ * path), 6 exchange of top lists, 7 merge + decision. */
 int  mcg_ctx_profile(mcg_ctx*, int enable);
 int  mcg_ctx_kernel_times(mcg_ctx*, int which, double* ms, int64_t* launches);
 /* device memory helpers for callers that keep data resident (bench, tests) */
@@ -239,7 +241,8 @@ int  mcg_query_matches(mcg_db*, const mcg_query_opts*,
  * Replaces the reference's replicated sketching of every read on every rank and its blocking tree reduce
  * to rank 0 (querying.h:867-1071).  comm may be NULL or of size 1 (single shard: no exchange).
  * out_tax/out_hits [n_local][maxcand], out_ncand/out_best/out_best_rank [n_local]; any of them may be
- * NULL; out_stats22 (may be NULL): the slice's counters are ADDED. */
+ * NULL; out_stats22 (may be NULL): the slice's counters are ADDED.  offs1[0] / offs2[0] need not be 0 (read i =
+ * reads1[offs1[i] .. offs1[i+1])): a slice of a larger batch is passed by pointing into its offset arrays. */
 int  mcg_query_batch_sharded(mcg_db*, mcg_comm*, const mcg_query_opts*,
                              const char* reads1, const int64_t* offs1,
                              const char* reads2, const int64_t* offs2, int64_t n_local,

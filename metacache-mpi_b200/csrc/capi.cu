@@ -266,7 +266,7 @@ int mcg_ctx_profile(mcg_ctx* c, int enable)
 
 int mcg_ctx_kernel_times(mcg_ctx* c, int which, double* ms, int64_t* launches)
 {
-    MCG_REQUIRE(c != nullptr && which >= 0 && which < 3, "mcg_ctx_kernel_times: bad argument");
+    MCG_REQUIRE(c != nullptr && which >= 0 && which < 8, "mcg_ctx_kernel_times: bad argument");
     MCG_CUDA(cudaSetDevice(c->device));
     MCG_CUDA(cudaStreamSynchronize(c->stream));
     double tot = 0.0;

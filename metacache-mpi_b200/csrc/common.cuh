@@ -95,7 +95,7 @@ struct mcg_ctx {
     int64_t launches = 0;
     // measurement hook (mcg_ctx_profile): event pairs around the launches of the dominant kernels
     bool profile = false;
-    std::vector<cudaEvent_t> prof_ev[3];      // start, stop, start, stop, ... per kernel class
+    std::vector<cudaEvent_t> prof_ev[8];      // start, stop, start, stop, ... per kernel / phase class
     void prof_begin(int which, cudaStream_t st)
     {
         if(!profile) return;

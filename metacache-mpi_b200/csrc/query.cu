@@ -47,38 +47,110 @@ constexpr int Q_LARGE = 16384;     // by one 512-thread CTA with 192 KB of share
 static inline unsigned grid_for(uint64_t n, int threads = 256) { return unsigned((n + threads - 1) / threads); }
 
 // ------------------------------------------------------------------ window bookkeeping
-// per read: windows of mate 1 / mate 2 (dna_encoding.h:261-276) and meta = {windows of the read (pair),
-// window-range width numWindows = 2 + max(len1 + len2, insertsize) / target stride (classification.cpp:217-219)}
-__global__ void q_window_counts_kernel(const int64_t* offs1, const int64_t* offs2, int64_t n,
-                                       int64_t winlen, int64_t stride, int64_t insertsize, int64_t tstride,
-                                       uint32_t* nw1, uint32_t* nw2, uint32_t* nws, uint2* meta)
+// ------------------------------------------------------------------ window bookkeeping, one pass
+// Per read: windows of mate 1 / mate 2 (dna_encoding.h:261-276) and meta = {windows of the read (pair),
+// window-range width numWindows = 2 + max(len1 + len2, insertsize) / target stride (classification.cpp:217-219)};
+// over all reads: the exclusive prefixes wf1 / wf2 (processing order of the two K1 launches), W = wf1 + wf2
+// (read-major output order) and of2 = W + windows of mate 1 (where mate 2's sketches go) -- one kernel, a
+// single-pass chained scan (decoupled look-back): tiles are taken in order from a counter, a tile publishes its
+// aggregate, then walks back over its predecessors until it meets an inclusive prefix.  The two running sums
+// (< 2^31 each) and the 2 status bits share one 64-bit word, so a status is read and written atomically.
+constexpr int QP_THREADS = 256, QP_ITEMS = 4, QP_TILE = QP_THREADS * QP_ITEMS;
+constexpr unsigned long long QP_AGG = 1ull << 62, QP_INC = 2ull << 62, QP_VAL = (1ull << 62) - 1;
+
+struct PrepParams {
+    const int64_t* offs1;
+    const int64_t* offs2;
+    int64_t n;
+    int64_t winlen, stride, insertsize, tstride;
+    uint32_t *wf1, *wf2, *W, *of2;         // [n + 1] each (of2: [n]); wf2 / of2 may be NULL (single-end)
+    uint2* meta;                           // [n]
+    unsigned long long* status;            // [tiles], zeroed; followed by the tile counter
+    uint32_t* tile_ctr;
+    uint32_t* clear8;                      // 8 bytes zeroed on the way (the fused kernel's counters); may be NULL
+};
+
+__global__ void __launch_bounds__(QP_THREADS)
+q_prep_kernel(const PrepParams p)
 {
-    const int64_t r = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
-    if(r >= n) return;
-    const int64_t l1 = offs1[r + 1] - offs1[r], l2 = offs2 ? offs2[r + 1] - offs2[r] : 0;
-    const uint32_t a = uint32_t(num_windows(l1, winlen, stride));
-    const uint32_t b = offs2 ? uint32_t(num_windows(l2, winlen, stride)) : 0u;
-    nw1[r] = a;
-    nw2[r] = b;
-    nws[r] = a + b;
-    int64_t span = l1 + l2;
-    if(insertsize > span) span = insertsize;
-    // 32-bit division when possible (the 64-bit one is emulated with ~150 instructions)
-    const uint64_t nwr = (span < (int64_t(1) << 31) && tstride < (int64_t(1) << 31)) ? 2u + uint32_t(span) / uint32_t(tstride)
-                                                                                      : uint64_t(2 + span / tstride);
-    meta[r] = make_uint2(a + b, uint32_t(nwr < 0xFFFFFFFFull ? nwr : 0xFFFFFFFFull));
+    __shared__ unsigned long long s_warp[QP_THREADS / 32];
+    __shared__ unsigned long long s_base;
+    __shared__ uint32_t s_tile;
+    if(threadIdx.x == 0) s_tile = atomicAdd(p.tile_ctr, 1u);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    if(tile == 0 && threadIdx.x == 0 && p.clear8 != nullptr) { p.clear8[0] = 0u; p.clear8[1] = 0u; }
+    const int64_t r0 = int64_t(tile) * QP_TILE + int64_t(threadIdx.x) * QP_ITEMS;
+    uint32_t a[QP_ITEMS], b[QP_ITEMS];
+    unsigned long long mine = 0;
+#pragma unroll
+    for(int i = 0; i < QP_ITEMS; ++i) {
+        const int64_t r = r0 + i;
+        a[i] = 0; b[i] = 0;
+        if(r < p.n) {
+            const int64_t l1 = p.offs1[r + 1] - p.offs1[r], l2 = p.offs2 ? p.offs2[r + 1] - p.offs2[r] : 0;
+            a[i] = uint32_t(num_windows(l1, p.winlen, p.stride));
+            b[i] = p.offs2 ? uint32_t(num_windows(l2, p.winlen, p.stride)) : 0u;
+            int64_t span = l1 + l2;
+            if(p.insertsize > span) span = p.insertsize;
+            // 32-bit division when possible (the 64-bit one is emulated with ~150 instructions)
+            const uint64_t nwr = (span < (int64_t(1) << 31) && p.tstride < (int64_t(1) << 31)) ? 2u + uint32_t(span) / uint32_t(p.tstride)
+                                                                                              : uint64_t(2 + span / p.tstride);
+            p.meta[r] = make_uint2(a[i] + b[i], uint32_t(nwr < 0xFFFFFFFFull ? nwr : 0xFFFFFFFFull));
+        }
+        mine += (unsigned long long)a[i] | ((unsigned long long)b[i] << 31);
+    }
+    // block-exclusive scan of the packed pair
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned long long inc = mine;
+#pragma unroll
+    for(int d = 1; d < 32; d <<= 1) {
+        const unsigned long long o = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+        if(lane >= d) inc += o;
+    }
+    if(lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    unsigned long long wbase = 0, agg = 0;
+#pragma unroll
+    for(int w = 0; w < QP_THREADS / 32; ++w) { const unsigned long long x = s_warp[w]; if(w < warp) wbase += x; agg += x; }
+    if(threadIdx.x == 0) {
+        volatile unsigned long long* st = p.status;
+        unsigned long long base = 0;
+        if(tile == 0) {
+            st[0] = QP_INC | agg;
+        } else {
+            st[tile] = QP_AGG | agg;
+            __threadfence();
+            for(int64_t q = int64_t(tile) - 1; q >= 0; --q) {
+                unsigned long long v;
+                do { v = st[q]; } while((v >> 62) == 0ull);
+                base += v & QP_VAL;
+                if((v >> 62) == 2ull) break;
+            }
+            st[tile] = QP_INC | ((base + agg) & QP_VAL);
+        }
+        s_base = base;
+    }
+    __syncthreads();
+    unsigned long long ex = s_base + wbase + inc - mine;
+#pragma unroll
+    for(int i = 0; i < QP_ITEMS; ++i) {
+        const int64_t r = r0 + i;
+        const uint32_t e1 = uint32_t(ex & 0x7FFFFFFFull), e2 = uint32_t((ex >> 31) & 0x7FFFFFFFull);
+        if(r <= p.n) {                                           // index n receives the totals
+            p.wf1[r] = e1;
+            if(p.wf2) p.wf2[r] = e2;
+            p.W[r] = e1 + e2;
+            if(p.of2 && r < p.n) p.of2[r] = e1 + e2 + a[i];
+        }
+        ex += (unsigned long long)a[i] | ((unsigned long long)b[i] << 31);
+    }
 }
 
 __global__ void q_meta_windows_kernel(const uint2* meta, int64_t n, uint32_t* nws)
 {
     const int64_t r = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
     if(r < n) nws[r] = meta[r].x;
-}
-
-__global__ void q_out_first2_kernel(const uint32_t* W, const uint32_t* wf1, int64_t n, uint32_t* of2)
-{
-    const int64_t r = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
-    if(r < n) of2[r] = W[r] + (wf1[r + 1] - wf1[r]);
 }
 
 // ------------------------------------------------------------------ K3: find
@@ -117,14 +189,17 @@ q_find_kernel(const uint32_t* __restrict__ feat, uint64_t nslots, const uint32_t
 // counters: [0] small [1] medium [2] large [3] xl
 __global__ void q_bin_reads_kernel(const uint64_t* fpos, const uint32_t* W, int s, int64_t n,
                                    uint32_t* lists /* [4][n] */, uint32_t* counters,
-                                   int32_t* out_n, const uint8_t* done, const uint32_t* rmap)
+                                   int32_t* out_n, int32_t* out_tax, uint32_t* out_hits, int K, const uint8_t* done, const uint32_t* rmap)
 {
     const int64_t r = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
     int cls = 4;                                          // 4 = nothing to do
     if(r < n && !(done != nullptr && done[r])) {
         const uint64_t m = fpos[uint64_t(W[r + 1]) * s] - fpos[uint64_t(W[r]) * s];
-        if(m == 0) out_n[rmap ? rmap[r] : uint32_t(r)] = 0;
-        else cls = m <= Q_SMALL ? 0 : (m <= Q_MED ? 1 : (m <= Q_LARGE ? 2 : 3));
+        if(m == 0) {
+            const uint64_t o = rmap ? rmap[r] : uint32_t(r);
+            out_n[o] = 0;
+            for(int c = 0; c < K; ++c) { out_tax[o * K + c] = -1; out_hits[o * K + c] = 0u; }
+        } else cls = m <= Q_SMALL ? 0 : (m <= Q_MED ? 1 : (m <= Q_LARGE ? 2 : 3));
     }
     // one atomic per class per warp
     const int lane = threadIdx.x & 31;
@@ -256,7 +331,7 @@ __device__ __forceinline__ void gsync()
 
 template<class KeyT> __device__ __forceinline__ uint32_t tgt_of(KeyT k, int wbits) { return uint32_t(k >> wbits); }
 
-// window-range width of a read (classification.cpp:217-219), precomputed by q_window_counts_kernel
+// window-range width of a read (classification.cpp:217-219), precomputed by q_prep_kernel
 __device__ __forceinline__ uint32_t num_windows_in_range(const CandParams& p, uint32_t r)
 {
     return __ldg(&p.meta[r].y);
@@ -837,6 +912,7 @@ q_fused_warp_kernel(const CandParams p, const FusedParams f)
         if(lane == 0) f.done[r] = 1;
         if(m == 0) {
             if(lane == 0) p.out_n[r] = 0;
+            if(lane < p.K) { p.out_tax[uint64_t(r) * p.K + lane] = -1; p.out_hits[uint64_t(r) * p.K + lane] = 0u; }
             continue;
         }
         // (3) matches into shared memory: lists of <= 2 straight from the slot, longer ones gathered
@@ -1143,13 +1219,34 @@ static uint64_t windows_bound(int64_t bytes, int64_t n, int64_t stride, int64_t 
     return b;
 }
 
+// window bookkeeping of n reads in one launch (+ one memset of its status words)
+static int launch_prep(mcg_db* db, const mcg_query_opts* o, const int64_t* doffs1, const int64_t* doffs2, int64_t n,
+                       uint32_t* wf1, uint32_t* wf2, uint32_t* W, uint32_t* of2, uint2* meta, uint32_t* clear8)
+{
+    mcg_ctx* c = db->ctx;
+    const uint32_t ntiles = uint32_t((n + 1 + QP_TILE - 1) / QP_TILE);
+    MCG_TRY(c->scan_tmp.reserve((size_t(ntiles) + 2) * 8));
+    MCG_CUDA(cudaMemsetAsync(c->scan_tmp.p, 0, (size_t(ntiles) + 1) * 8, c->stream));
+    PrepParams p;
+    p.offs1 = doffs1; p.offs2 = doffs2; p.n = n;
+    p.winlen = o->winlen; p.stride = o->winstride; p.insertsize = o->insertsize; p.tstride = db->cfg.winstride;
+    p.wf1 = wf1; p.wf2 = wf2; p.W = W; p.of2 = of2; p.meta = meta;
+    p.status = c->scan_tmp.as<unsigned long long>();
+    p.tile_ctr = reinterpret_cast<uint32_t*>(p.status + ntiles);
+    p.clear8 = clear8;
+    q_prep_kernel<<<ntiles, QP_THREADS, 0, c->stream>>>(p);
+    c->launches++;
+    MCG_CUDA(cudaGetLastError());
+    return MCG_OK;
+}
+
 // stage A, local part: window bookkeeping + K1 of both mates of n device-resident reads.  Sketches land
 // read-major at feat_out[W[r] * s ...], W (exclusive prefix, total at [n]) and meta are written; nothing
 // returns to the host.  feat_out must hold *wbound * s features.
 static int qa_sketch(mcg_db* db, const mcg_query_opts* o,
                      const char* d1, const int64_t* doffs1, int64_t bytes1,
                      const char* d2, const int64_t* doffs2, int64_t bytes2, int64_t n, int64_t max_len,
-                     uint32_t* W, uint2* meta, uint32_t* feat_out, uint64_t wb1, uint64_t wb2)
+                     uint32_t* W, uint2* meta, uint32_t* feat_out, uint64_t wb1, uint64_t wb2, uint32_t* clear8 = nullptr)
 {
     mcg_ctx* c = db->ctx;
     const int s = o->sketchlen;
@@ -1159,26 +1256,18 @@ static int qa_sketch(mcg_db* db, const mcg_query_opts* o,
     uint32_t* wf1 = c->tmp0.as<uint32_t>();
     uint32_t* wf2 = c->tmp1.as<uint32_t>();
     uint32_t* of2 = c->tmp3.as<uint32_t>();
-    q_window_counts_kernel<<<grid_for(n), 256, 0, c->stream>>>(doffs1, d2 ? doffs2 : nullptr, n, o->winlen, o->winstride, o->insertsize,
-                                                              db->cfg.winstride, wf1, wf2, W, meta);
-    c->launches++;
-    MCG_TRY(exclusive_scan_u32_to_u32(c, wf1, wf1, n));
-    if(d2) MCG_TRY(exclusive_scan_u32_to_u32(c, wf2, wf2, n));
-    MCG_TRY(exclusive_scan_u32_to_u32(c, W, W, n));
+    MCG_TRY(launch_prep(db, o, doffs1, d2 ? doffs2 : nullptr, n, wf1, d2 ? wf2 : nullptr, W, d2 ? of2 : nullptr, meta, clear8));
     mcg_sketch_cfg cfg = db->cfg;
     (void)max_len;
     MCG_TRY(sketch_launch(c, cfg, s, o->winlen, o->winstride, d1, bytes1, doffs1, n, wf1, W, wb1, feat_out, nullptr, 0, nullptr, nullptr, wf1 + n));
-    if(d2) {
-        q_out_first2_kernel<<<grid_for(n), 256, 0, c->stream>>>(W, wf1, n, of2);
-        c->launches++;
-        MCG_TRY(sketch_launch(c, cfg, s, o->winlen, o->winstride, d2, bytes2, doffs2, n, wf2, of2, wb2, feat_out, nullptr, 0, nullptr, nullptr, wf2 + n));
-    }
+    if(d2) MCG_TRY(sketch_launch(c, cfg, s, o->winlen, o->winstride, d2, bytes2, doffs2, n, wf2, of2, wb2, feat_out, nullptr, 0, nullptr, nullptr, wf2 + n));
     MCG_CUDA(cudaGetLastError());
     return MCG_OK;
 }
 
 // staged path: find -> scan -> binning -> gather (reads marked done are skipped)
-static int query_find_gather(mcg_db* db, const mcg_query_opts* o, int64_t n, int32_t* d_out_n, const uint8_t* d_done, QueryRun* run)
+static int query_find_gather(mcg_db* db, const mcg_query_opts* o, int64_t n, int32_t* d_out_tax, uint32_t* d_out_hits, int32_t* d_out_n,
+                             const uint8_t* d_done, QueryRun* run)
 {
     mcg_ctx* c = db->ctx;
     const int s = o->sketchlen;
@@ -1199,7 +1288,8 @@ static int query_find_gather(mcg_db* db, const mcg_query_opts* o, int64_t n, int
     MCG_TRY(c->q_rinfo.reserve(64));
     uint32_t* counters = c->q_rinfo.as<uint32_t>();
     MCG_CUDA(cudaMemsetAsync(counters, 0, 16, c->stream));
-    q_bin_reads_kernel<<<grid_for(n), 256, 0, c->stream>>>(c->q_fpos.as<uint64_t>(), W, s, n, c->q_cls.as<uint32_t>(), counters, d_out_n, d_done, run->rmap);
+    q_bin_reads_kernel<<<grid_for(n), 256, 0, c->stream>>>(c->q_fpos.as<uint64_t>(), W, s, n, c->q_cls.as<uint32_t>(), counters, d_out_n, d_out_tax, d_out_hits,
+                                                          o->maxcand, d_done, run->rmap);
     c->launches++;
     uint64_t total = 0;
     MCG_CUDA(cudaMemcpyAsync(&total, c->q_fpos.as<uint64_t>() + nslots, 8, cudaMemcpyDeviceToHost, c->stream));
@@ -1300,18 +1390,14 @@ static int query_back(mcg_db* db, const mcg_query_opts* o, const uint2* meta, in
 // stage A, fused kernel: all reads of the part (features / W / meta in `part`) -> per-read top lists; the
 // number of reads it could not hold goes to pinned memory (h_left), followed by part.evA
 static int qa_fused(mcg_db* db, const mcg_query_opts* o, QPart& part, int slot, int64_t n, double slots_per_read,
-                    int32_t* d_out_tax, uint32_t* d_out_hits, int32_t* d_out_n)
+                    int32_t* d_out_tax, uint32_t* d_out_hits, int32_t* d_out_n, bool ctr_cleared)
 {
     mcg_ctx* c = db->ctx;
-    const int K = o->maxcand;
-    // unused slots: taxon -1, hits 0
-    MCG_CUDA(cudaMemsetAsync(d_out_tax, 0xFF, size_t(n) * K * 4, c->stream));
-    MCG_CUDA(cudaMemsetAsync(d_out_hits, 0, size_t(n) * K * 4, c->stream));
-    MCG_TRY(part.ctr.reserve(64));
+    // (every read gets its whole row -- K slots, unused ones taxon -1 / hits 0 -- from the kernel that finishes it)
     MCG_TRY(part.done.reserve(size_t(n) + 16));
     MCG_TRY(part.left_list.reserve(size_t(n + 2) * 4));
     uint32_t* left = part.ctr.as<uint32_t>();
-    MCG_CUDA(cudaMemsetAsync(left, 0, 8, c->stream));
+    if(!ctr_cleared) MCG_CUDA(cudaMemsetAsync(left, 0, 8, c->stream));
     CandParams p;
     fill_cand_params(db, o, part.W.as<uint32_t>(), part.meta.as<uint2>(), d_out_tax, d_out_hits, d_out_n, 0, &p);
     FusedParams f;
@@ -1406,7 +1492,7 @@ static int qb_leftovers(mcg_db* db, const mcg_query_opts* o, QPart& part, int sl
         run.nwin = wtot;
         run.nslots = uint64_t(wtot) * uint64_t(o->sketchlen);
     }
-    MCG_TRY(query_find_gather(db, o, n_staged, d_out_n, d_done, &run));
+    MCG_TRY(query_find_gather(db, o, n_staged, d_out_tax, d_out_hits, d_out_n, d_done, &run));
     MCG_TRY(query_back(db, o, part.meta.as<uint2>(), n_staged, run, d_out_tax, d_out_hits, d_out_n, 0));
     return MCG_OK;
 }
@@ -1433,9 +1519,10 @@ int query_batch_dev(mcg_db* db, const mcg_query_opts* o,
     MCG_TRY(part.W.reserve(size_t(n + 2) * 4));
     MCG_TRY(part.meta.reserve(size_t(n + 1) * 8));
     MCG_TRY(part.feat.reserve(((wb1 + wb2) * s + 1) * 4));
+    MCG_TRY(part.ctr.reserve(64));
     MCG_TRY(qa_sketch(db, o, d1, doffs1, bytes1, d2, doffs2, bytes2, n, max_len, part.W.as<uint32_t>(), part.meta.as<uint2>(),
-                      part.feat.as<uint32_t>(), wb1, wb2));
-    MCG_TRY(qa_fused(db, o, part, slot, n, est_slots_per_read(o, bytes1, bytes2, n, d2 != nullptr), d_out_tax, d_out_hits, d_out_n));
+                      part.feat.as<uint32_t>(), wb1, wb2, part.ctr.as<uint32_t>()));
+    MCG_TRY(qa_fused(db, o, part, slot, n, est_slots_per_read(o, bytes1, bytes2, n, d2 != nullptr), d_out_tax, d_out_hits, d_out_n, true));
     if(finish) MCG_TRY(qb_leftovers(db, o, part, slot, n, d_out_tax, d_out_hits, d_out_n));
     return MCG_OK;
 }
@@ -1468,7 +1555,7 @@ static int query_staged_sorted(mcg_db* db, const mcg_query_opts* o,
     run.rmap = nullptr;
     run.nwin = wtot;
     run.nslots = uint64_t(wtot) * uint64_t(s);
-    MCG_TRY(query_find_gather(db, o, n, d_out_n, nullptr, &run));
+    MCG_TRY(query_find_gather(db, o, n, d_out_tax, d_out_hits, d_out_n, nullptr, &run));
     MCG_TRY(query_back(db, o, part.meta.as<uint2>(), n, run, d_out_tax, d_out_hits, d_out_n, 1));
     if(run_out) *run_out = run;
     return MCG_OK;
@@ -1541,11 +1628,8 @@ static int qs_plan(mcg_db* db, mcg_comm* comm, const mcg_query_opts* o, const in
     MCG_TRY(c->plan.reserve(size_t(QS_MAX_PARTS + 2) * 8));
     uint32_t* Ww = c->tmp5.as<uint32_t>();
     if(n_loc > 0) {
-        q_window_counts_kernel<<<grid_for(n_loc), 256, 0, c->stream>>>(doffs1, doffs2, n_loc, o->winlen, o->winstride, o->insertsize,
-                                                                  db->cfg.winstride, c->tmp0.as<uint32_t>(), c->tmp1.as<uint32_t>(), Ww,
-                                                                  c->tmp4.as<uint2>());
-        c->launches++;
-        MCG_TRY(exclusive_scan_u32_to_u32(c, Ww, Ww, n_loc));
+        MCG_TRY(launch_prep(db, o, doffs1, doffs2, n_loc, c->tmp0.as<uint32_t>(), doffs2 ? c->tmp1.as<uint32_t>() : nullptr, Ww, nullptr,
+                            c->tmp4.as<uint2>(), nullptr));
     } else {
         MCG_CUDA(cudaMemsetAsync(Ww, 0, 8, c->stream));
     }
@@ -1592,10 +1676,14 @@ static int qs_stage_a(mcg_db* db, mcg_comm* comm, const mcg_query_opts* o, const
     MCG_TRY(part.lt.reserve(size_t(N + 1) * K * 4)); MCG_TRY(part.lh.reserve(size_t(N + 1) * K * 4)); MCG_TRY(part.ln.reserve(size_t(N + 1) * 4));
     uint32_t* Wl = part.W.as<uint32_t>();
     if(P > 1) { MCG_TRY(c->tmp2.reserve(size_t(n_loc + 2) * 4)); Wl = c->tmp2.as<uint32_t>(); }
+    c->prof_begin(3, c->stream);
+    MCG_TRY(part.ctr.reserve(64));
     if(n_loc > 0)
         MCG_TRY(qa_sketch(db, o, d1, do1, b1, d2, do2, b2, n_loc, max_len, Wl, part.meta.as<uint2>() + nb,
-                          part.feat.as<uint32_t>() + wb * uint64_t(s), wb1, wb2));
+                          part.feat.as<uint32_t>() + wb * uint64_t(s), wb1, wb2, part.ctr.as<uint32_t>()));
+    c->prof_end(3, c->stream);
     if(P > 1) {
+        c->prof_begin(4, c->stream);
         std::vector<uint64_t> off(static_cast<size_t>(P)), len(static_cast<size_t>(P));
         uint64_t a = 0;
         for(int r = 0; r < P; ++r) { off[size_t(r)] = a * uint64_t(s) * 4; len[size_t(r)] = pl.rw(j, r) * uint64_t(s) * 4; a += pl.rw(j, r); }
@@ -1608,10 +1696,11 @@ static int qs_stage_a(mcg_db* db, mcg_comm* comm, const mcg_query_opts* o, const
             c->launches++;
         }
         MCG_TRY(exclusive_scan_u32_to_u32(c, part.W.as<uint32_t>(), part.W.as<uint32_t>(), N));
+        c->prof_end(4, c->stream);
     }
     if(N == 0) { c->h_left[slot] = 0; MCG_CUDA(cudaEventRecord(part.evA, c->stream)); return MCG_OK; }
     const double spr = est_slots_per_read(o, b1, b2, std::max<int64_t>(n_loc, 1), d2 != nullptr);
-    return qa_fused(db, o, part, slot, int64_t(N), n_loc > 0 ? spr : 64.0, part.lt.as<int32_t>(), part.lh.as<uint32_t>(), part.ln.as<int32_t>());
+    return qa_fused(db, o, part, slot, int64_t(N), n_loc > 0 ? spr : 64.0, part.lt.as<int32_t>(), part.lh.as<uint32_t>(), part.ln.as<int32_t>(), n_loc > 0);
 }
 
 // stage B of part j: left-over reads, exchange of the per-read lists, merge + decision of the own block
@@ -1625,11 +1714,18 @@ static int qs_stage_b(mcg_db* db, mcg_comm* comm, const mcg_query_opts* o, const
     uint64_t N = 0, nb = 0;
     for(int r = 0; r < P; ++r) { if(r == me) nb = N; N += pl.rn(j, r); }
     const uint64_t n_me = pl.rn(j, me);
-    if(N > 0) MCG_TRY(qb_leftovers(db, o, part, slot, int64_t(N), part.lt.as<int32_t>(), part.lh.as<uint32_t>(), part.ln.as<int32_t>()));
+    if(N > 0) {
+        MCG_CUDA(cudaEventSynchronize(part.evA));
+        const bool left = c->h_left[slot] != 0;
+        if(left) c->prof_begin(5, c->stream);
+        MCG_TRY(qb_leftovers(db, o, part, slot, int64_t(N), part.lt.as<int32_t>(), part.lh.as<uint32_t>(), part.ln.as<int32_t>()));
+        if(left) c->prof_end(5, c->stream);
+    }
     const int32_t* ct = part.lt.as<int32_t>();
     const uint32_t* ch = part.lh.as<uint32_t>();
     const int32_t* cn = part.ln.as<int32_t>();
     if(P > 1) {
+        c->prof_begin(6, c->stream);
         MCG_TRY(part.ct.reserve(size_t(P) * (n_me + 1) * K * 4)); MCG_TRY(part.ch.reserve(size_t(P) * (n_me + 1) * K * 4));
         MCG_TRY(part.cn.reserve(size_t(P) * (n_me + 1) * 4));
         std::vector<uint64_t> so(static_cast<size_t>(P)), sl(static_cast<size_t>(P)), ro(static_cast<size_t>(P)), rl(static_cast<size_t>(P));
@@ -1648,10 +1744,13 @@ static int qs_stage_b(mcg_db* db, mcg_comm* comm, const mcg_query_opts* o, const
             }
         }
         ct = part.ct.as<int32_t>(); ch = part.ch.as<uint32_t>(); cn = part.cn.as<int32_t>();
+        c->prof_end(6, c->stream);
     }
     (void)nb;
+    c->prof_begin(7, c->stream);
     if(n_me > 0)
         MCG_TRY(mcg_merge_classify_dev(c, o, ct, ch, cn, P, int64_t(n_me), d_out_tax, d_out_hits, d_out_n, d_out_best, d_out_brank, d_stats));
+    c->prof_end(7, c->stream);
     MCG_CUDA(cudaEventRecord(part.evB, c->stream));
     return MCG_OK;
 }
@@ -1938,8 +2037,8 @@ int mcg_query_batch_sharded(mcg_db* db, mcg_comm* comm, const mcg_query_opts* o,
 {
     MCG_REQUIRE(db != nullptr && o != nullptr, "mcg_query_batch_sharded: NULL argument");
     MCG_REQUIRE(n >= 0 && n < (1ll << 31), "read count out of range");
-    MCG_REQUIRE(n == 0 || (reads1 != nullptr && offs1 != nullptr && offs1[0] == 0), "reads1 / offs1 (offs1[0] must be 0)");
-    if(reads2 != nullptr) MCG_REQUIRE(offs2 != nullptr && offs2[0] == 0, "offs2[0] must be 0");
+    MCG_REQUIRE(n == 0 || (reads1 != nullptr && offs1 != nullptr), "reads1 / offs1 are NULL");
+    if(reads2 != nullptr) MCG_REQUIRE(offs2 != nullptr, "offs2 is NULL");
     mcg_ctx* c = db->ctx;
     MCG_CUDA(cudaSetDevice(c->device));
     MCG_TRY(check_ready(db, o));

@@ -1180,12 +1180,10 @@ int mode_query(const Args& a)
             for_each_shard_parallel(P, [&](int r) {
                 const size_t a = n * size_t(r) / size_t(P), b = n * size_t(r + 1) / size_t(P);
                 part[size_t(r)].fill(0);
-                // slice r: offsets re-based to the slice (the library wants offs[0] == 0)
-                std::vector<int64_t> so1(b - a + 1), so2(paired ? b - a + 1 : 1);
-                for(size_t i = a; i <= b; ++i) { so1[i - a] = B.o1[i] - B.o1[a]; if(paired) so2[i - a] = B.o2[i] - B.o2[a]; }
+                // slice r: reads [a, b) of the batch -- the library takes a window of the (pinned) offset arrays
                 check(mcg_query_batch_sharded(dbs[size_t(r)], P > 1 ? comms[size_t(r)] : nullptr, &q,
-                                              B.b1.data() + B.o1[a], so1.data(), paired ? B.b2.data() + B.o2[a] : nullptr,
-                                              paired ? so2.data() : nullptr, int64_t(b - a),
+                                              B.b1.data(), B.o1.data() + a, paired ? B.b2.data() : nullptr,
+                                              paired ? B.o2.data() + a : nullptr, int64_t(b - a),
                                               B.mtax.data() + a * K, B.mhits.data() + a * K, B.mn.data() + a, B.best.data() + a,
                                               B.brank.data() + a, part[size_t(r)].data()), "mcg_query_batch_sharded");
             });
