@@ -390,42 +390,80 @@ std::string trimmed(const std::string& s)
     return a == std::string::npos ? "" : s.substr(a, b - a + 1);
 }
 
-// sequence id = NCBI-style accession (sequence_io.cpp:576-716): known prefix + version, plain
-// "name.version" at the start of the text, prefix without version, or gi number
-size_t end_of_accession(const std::string& t, size_t start)
+// ---- sequence id of a FASTA header.  Behaviour to match (what the reference's database stores as target name,
+// observed through `info` dumps and the query output; its extractor lives in sequence_io.cpp:576-716):
+//   1. the first of a fixed list of NCBI accession prefixes (in list order, not in text order) that occurs in the
+//      header and is followed by a '.' at most 25 characters after its start: prefix ... '.' version;
+//   2. otherwise a leading "name.version" whose '.' comes within the first 25 characters;
+//   3. otherwise the first listed prefix that occurs at all, without a version;
+//   4. otherwise the number after "gi|";
+//   an id ends before the first of '|', ' ', '-', '_', ',' -- tried in THIS order -- found after its start.
+// Written as a small rule table over string views of the header, not as a port of that code.
+struct IdSpan { size_t from = 0, to = 0; bool ok = false; };
+
+size_t id_end(const std::string& t, size_t from)
 {
-    if(start >= t.size()) return t.size();
-    for(char c : {'|', ' ', '-', '_', ','}) { size_t k = t.find(c, start); if(k != std::string::npos) return k; }
+    if(from >= t.size()) return t.size();
+    static const char stops[] = {'|', ' ', '-', '_', ','};
+    for(char c : stops) { const size_t k = t.find(c, from); if(k != std::string::npos) return k; }
     return t.size();
+}
+
+const std::vector<std::string>& accession_prefixes()
+{
+    static const std::vector<std::string> v = {"GCF_", "AC_", "NC_", "NG_", "NS_", "NT_", "NW_", "NZ_", "MKHE", "AE", "AJ", "AL", "AM",
+                                               "AP", "AY", "BA", "BK", "BX", "CC", "CM", "CP", "CR", "CT", "CU", "FM", "FN", "FO", "FP", "FQ", "FR"};
+    return v;
 }
 
 std::string extract_accession(const std::string& text)
 {
-    static const char* const prefixes[] = {"GCF_", "AC_", "NC_", "NG_", "NS_", "NT_", "NW_", "NZ_", "MKHE", "AE", "AJ", "AL", "AM",
-        "AP", "AY", "BA", "BK", "BX", "CC", "CM", "CP", "CR", "CT", "CU", "FM", "FN", "FO", "FP", "FQ", "FR"};
     if(text.size() < 2) return "";
-    for(auto p : prefixes) {
-        size_t i = text.find(p);
-        if(i == std::string::npos) continue;
-        size_t s = text.find('.', i + std::strlen(p));
-        if(s == std::string::npos || (s - i) > 25) continue;
-        return trimmed(text.substr(i, end_of_accession(text, s + 1) - i));
-    }
-    size_t s = text.find('.', 1);
-    if(s < 25) return trimmed(text.substr(0, end_of_accession(text, s + 1)));
-    for(auto p : prefixes) {
-        size_t i = text.find(p);
-        if(i == std::string::npos) continue;
-        size_t j = i + std::strlen(p), k = end_of_accession(text, j), l = text.find('.', j);
-        if(l < k) k = l;
-        return trimmed(text.substr(i, k - i));
-    }
-    size_t i = text.find("gi|");
-    if(i != std::string::npos) {
-        i += 3;
-        size_t j = text.find('|', i);
-        if(j == std::string::npos) { j = text.find(' ', i); if(j == std::string::npos) j = text.size(); }
-        return trimmed(text.substr(i, j - i));
+    using Rule = IdSpan (*)(const std::string&);
+    static const Rule rules[] = {
+        [](const std::string& t) {                       // 1. listed prefix with version
+            IdSpan r;
+            for(const std::string& p : accession_prefixes()) {
+                const size_t i = t.find(p);
+                if(i == std::string::npos) continue;
+                const size_t dot = t.find('.', i + p.size());
+                if(dot == std::string::npos || dot - i > 25) continue;
+                r.from = i; r.to = id_end(t, dot + 1); r.ok = true;
+                break;
+            }
+            return r;
+        },
+        [](const std::string& t) {                       // 2. leading name.version
+            IdSpan r;
+            const size_t dot = t.find('.', 1);
+            if(dot < 25) { r.from = 0; r.to = id_end(t, dot + 1); r.ok = true; }
+            return r;
+        },
+        [](const std::string& t) {                       // 3. listed prefix without version
+            IdSpan r;
+            for(const std::string& p : accession_prefixes()) {
+                const size_t i = t.find(p);
+                if(i == std::string::npos) continue;
+                const size_t body = i + p.size();
+                r.from = i; r.to = std::min(id_end(t, body), t.find('.', body)); r.ok = true;
+                break;
+            }
+            return r;
+        },
+        [](const std::string& t) {                       // 4. gi number
+            IdSpan r;
+            const size_t i = t.find("gi|");
+            if(i == std::string::npos) return r;
+            r.from = i + 3;
+            r.to = t.find('|', r.from);
+            if(r.to == std::string::npos) r.to = t.find(' ', r.from);
+            if(r.to == std::string::npos) r.to = t.size();
+            r.ok = true;
+            return r;
+        }};
+    for(Rule rule : rules) {
+        const IdSpan r = rule(text);
+        if(r.ok) return trimmed(text.substr(r.from, r.to - r.from));
     }
     return "";
 }
@@ -897,50 +935,67 @@ struct TaxaByRank {                                   // root first, then by id 
 };
 using TaxCountMap = std::map<const Taxon*, float, TaxaByRank>;
 
+// Abundance estimate at `rank`.  Behaviour to match (the table the reference prints for -abundance-per; its code is
+// classification.cpp:362-428; pinned by tests/test_host_driver_cpu.py against tables the reference printed):
+//   a. counts of taxa below the estimation rank move to their closest ancestor at or above that rank;
+//   b. among the taxa that hold counts, every taxon hangs below its closest counted ancestor; a taxon's weight is the
+//      total count below it;
+//   c. top down, a counted taxon with counted descendants hands its own count to its children in proportion to
+//      (child count + child weight) / own weight, and leaves the table.
+// Counts are single-precision and weights 64-bit integers in the reference, and rows are visited in table order
+// (higher ranks first, then taxon id): the same types and visiting order are kept here, because they decide the
+// rounding of the printed numbers.  Implemented over one flat, ordered node array with parent / child indices.
 void estimate_abundance(const TaxTables& tt, TaxCountMap& all, int rank)
 {
-    auto lineage_at = [&](const Taxon* t, unsigned r) -> const Taxon* {
+    auto ancestor_at = [&](const Taxon* t, unsigned r) -> const Taxon* {
         const int32_t x = tt.lineage[size_t(tt.index_of.at(t->id)) * 21 + r];
         return x >= 0 ? tt.tax[size_t(x)] : nullptr;
     };
-    if(rank != 0) {
-        // taxa below the estimation rank are added to their ancestor at (or above) it
-        Taxon probe;
-        probe.id = 0; probe.rank = uint8_t(rank - 1);
-        for(auto tc = all.lower_bound(&probe); tc != all.end();) {
-            const Taxon* anc = nullptr;
-            unsigned index = unsigned(rank);
-            while(!anc && index < 21) anc = lineage_at(tc->first, index++);
-            if(anc) { all[anc] += tc->second; tc = all.erase(tc); } else ++tc;
+    // (a) fold what lies below the estimation rank, in table order
+    if(rank > 0) {
+        std::vector<const Taxon*> low;
+        for(const auto& kv : all) if(int(kv.first->rank) < rank) low.push_back(kv.first);
+        for(const Taxon* t : low) {
+            const Taxon* up = nullptr;
+            for(unsigned r = unsigned(rank); r < 21 && up == nullptr; ++r) up = ancestor_at(t, r);
+            if(up == nullptr) continue;                      // nothing above it at that rank: the row stays
+            const float moved = all[t];
+            all[up] += moved;
+            all.erase(t);
         }
     }
-    std::unordered_map<const Taxon*, std::vector<const Taxon*>> children;
-    std::unordered_map<const Taxon*, uint64_t> weights;
-    for(const auto& tc : all) weights[tc.first] = 0;
-    // leaves to root: every taxon adds its count to the closest ancestor that has a count itself
-    for(auto tc = all.rbegin(); tc != all.rend(); ++tc) {
-        uint8_t index = uint8_t(tc->first->rank + 1);
-        while(index < 21) {
-            const Taxon* parent = lineage_at(tc->first, index++);
-            if(parent && weights.count(parent)) {
-                weights[parent] += weights[tc->first] + tc->second;
-                children[parent].emplace_back(tc->first);
-                break;
-            }
+    // (b) flat node array in table order; parent = closest counted ancestor
+    struct Node { const Taxon* tax; float count; uint64_t weight; int parent; std::vector<int> kids; bool gone; };
+    std::vector<Node> nodes;
+    nodes.reserve(all.size());
+    std::unordered_map<const Taxon*, int> where;
+    for(const auto& kv : all) { where[kv.first] = int(nodes.size()); nodes.push_back(Node{kv.first, kv.second, 0, -1, {}, false}); }
+    for(int i = int(nodes.size()) - 1; i >= 0; --i) {         // leaves first: a node's weight is final before it is handed up
+        Node& n = nodes[size_t(i)];
+        for(unsigned r = unsigned(n.tax->rank) + 1; r < 21; ++r) {
+            const Taxon* up = ancestor_at(n.tax, r);
+            if(up == nullptr) continue;
+            auto it = where.find(up);
+            if(it == where.end()) continue;
+            Node& par = nodes[size_t(it->second)];
+            n.parent = it->second;
+            par.weight += n.weight + n.count;                // integer += (integer + float): evaluated in float, stored as integer
+            par.kids.push_back(i);
+            break;
         }
     }
-    // root to leaves: counts of inner taxa are distributed proportionally, inner taxa disappear
-    for(auto tc = all.begin(); tc != all.end();) {
-        auto ch = children.find(tc->first);
-        if(ch != children.end()) {
-            const uint64_t sum_children = weights[tc->first];
-            for(const Taxon* child : ch->second)
-                all[child] += tc->second * (all[child] + weights[child]) / sum_children;
-            tc = all.erase(tc);
-        } else {
-            ++tc;
+    // (c) top down
+    for(Node& n : nodes) {
+        if(n.kids.empty()) continue;
+        const uint64_t below = n.weight;
+        for(int k : n.kids) {
+            Node& ch = nodes[size_t(k)];
+            ch.count += n.count * (ch.count + ch.weight) / below;
         }
+        n.gone = true;
     }
+    all.clear();
+    for(const Node& n : nodes) if(!n.gone) all[n.tax] = n.count;
 }
 
 void show_abundance_table(std::ostream& os, const TaxCountMap& all, uint64_t total, const std::string& ranksuf, const std::string& col)
