@@ -233,7 +233,7 @@ int mcg_ctx_destroy(mcg_ctx* c)
                       &c->m_brank, &c->m_stats, &c->m_bad, &c->tilectr};
     for(DevBuf* b : bufs) b->release();
     c->qp[0].release_all(); c->qp[1].release_all();
-    c->s_wc.release(); c->s_featc.release(); c->plan.release();
+    c->s_wc.release(); c->s_featc.release(); c->plan.release(); c->q_spill.release();
     if(c->h_left != nullptr) cudaFreeHost(c->h_left);
     if(c->pinned != nullptr) cudaFreeHost(c->pinned);
     if(c->s_h2d) cudaStreamDestroy(c->s_h2d);

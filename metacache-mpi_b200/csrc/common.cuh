@@ -71,14 +71,14 @@ namespace mcg {
 // enqueued before the host looks at the previous part's left-over count, so what stage A writes and the
 // later stages (left-over reads, list exchange, merge, copy-out) read exists twice.
 struct QPart {
-    DevBuf W, feat, meta, left_list, done, ctr;        // window prefix, features, per-read meta; fused kernel bookkeeping
+    DevBuf W, feat, meta, left_list, left_list2, done, ctr;   // window prefix, features, per-read meta; fused / spill kernel bookkeeping
     DevBuf lt, lh, ln;                                 // per-read top lists of every read of the part
     DevBuf ct, ch, cn;                                 // lists received from the other shards for the own block [P][n][K]
     DevBuf mt, mh, mn, mbest, mbrank;                  // merged lists + decision of the own block
     cudaEvent_t evA = nullptr, evB = nullptr;
     void release_all()
     {
-        DevBuf* b[] = {&W, &feat, &meta, &left_list, &done, &ctr, &lt, &lh, &ln, &ct, &ch, &cn, &mt, &mh, &mn, &mbest, &mbrank};
+        DevBuf* b[] = {&W, &feat, &meta, &left_list, &left_list2, &done, &ctr, &lt, &lh, &ln, &ct, &ch, &cn, &mt, &mh, &mn, &mbest, &mbrank};
         for(DevBuf* x : b) x->release();
         if(evA) cudaEventDestroy(evA);
         if(evB) cudaEventDestroy(evB);
@@ -122,6 +122,7 @@ struct mcg_ctx {
     mcg::QPart qp[2];                 // query parts in flight (see QPart)
     uint32_t* h_left = nullptr;       // pinned: left-over counts of the two parts
     mcg::DevBuf s_wc, s_featc, plan;  // left-over path: compacted window prefix / features; sharded query: part sizes
+    mcg::DevBuf q_spill;              // match lists of the spill kernel (global memory, per warp)
     // copy streams + events of the pipelined host entry points
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
     cudaEvent_t ev_h2d[4] = {nullptr, nullptr, nullptr, nullptr};

@@ -67,7 +67,7 @@ struct PrepParams {
     uint2* meta;                           // [n]
     unsigned long long* status;            // [tiles], zeroed; followed by the tile counter
     uint32_t* tile_ctr;
-    uint32_t* clear8;                      // 8 bytes zeroed on the way (the fused kernel's counters); may be NULL
+    uint32_t* clear8;                      // 16 bytes zeroed on the way (the counters of the fused / spill kernels); may be NULL
 };
 
 __global__ void __launch_bounds__(QP_THREADS)
@@ -79,7 +79,7 @@ q_prep_kernel(const PrepParams p)
     if(threadIdx.x == 0) s_tile = atomicAdd(p.tile_ctr, 1u);
     __syncthreads();
     const uint32_t tile = s_tile;
-    if(tile == 0 && threadIdx.x == 0 && p.clear8 != nullptr) { p.clear8[0] = 0u; p.clear8[1] = 0u; }
+    if(tile == 0 && threadIdx.x == 0 && p.clear8 != nullptr) { p.clear8[0] = 0u; p.clear8[1] = 0u; p.clear8[2] = 0u; p.clear8[3] = 0u; }
     const int64_t r0 = int64_t(tile) * QP_TILE + int64_t(threadIdx.x) * QP_ITEMS;
     uint32_t a[QP_ITEMS], b[QP_ITEMS];
     unsigned long long mine = 0;
@@ -986,6 +986,113 @@ q_fused_warp_kernel(const CandParams p, const FusedParams f)
     }
 }
 
+// Reads the fused kernel left over although they are short (more matches than it holds per warp, or more
+// feature slots than its variant holds per lane -- up to Q_SPILL_SLOTS): the same per-read pipeline, one warp per
+// read, with the match list in a per-warp region of GLOBAL memory sized for the worst case (every slot a full
+// list).  They are rare (about 1 in 1000 read pairs against a 2.5 Gbp shard), so this kernel's speed does not
+// matter; what matters is that it needs no decision of the host: it is launched unconditionally behind the fused
+// kernel and finds its work in the left-over list.  Long reads (more slots) are passed on in left_list2 for the
+// staged path.
+constexpr int Q_SPILL_SLOTS = 128;
+constexpr int Q_SPILL_WARPS = 4;
+
+struct SpillParams {
+    const uint32_t* feat;
+    const uint32_t* table;
+    TableGeom geom;
+    const uint64_t* locs;
+    uint8_t* done;
+    const uint32_t* left_count;   // reads left over by the fused kernel
+    const uint32_t* left_list;
+    uint32_t* left_count2;        // reads passed on to the staged path
+    uint32_t* left_list2;
+    unsigned char* scratch;       // [warps of the grid][cap * (sizeof(KeyT) + 12)]
+    uint32_t cap;                 // Q_SPILL_SLOTS * maxlocs
+};
+
+template<class KeyT>
+__global__ void __launch_bounds__(Q_SPILL_WARPS * 32)
+q_spill_warp_kernel(const CandParams p, const SpillParams f)
+{
+    const int lane = threadIdx.x & 31;
+    const uint32_t gw = blockIdx.x * Q_SPILL_WARPS + (threadIdx.x >> 5), nw = gridDim.x * Q_SPILL_WARPS;
+    unsigned char* base = f.scratch + size_t(gw) * f.cap * (sizeof(KeyT) + 12);
+    KeyT* A = reinterpret_cast<KeyT*>(base);
+    uint32_t* Hh = reinterpret_cast<uint32_t*>(base + size_t(f.cap) * sizeof(KeyT));
+    int32_t* Ct = reinterpret_cast<int32_t*>(Hh + f.cap);
+    uint32_t* Ch = reinterpret_cast<uint32_t*>(Ct + f.cap);
+    const uint32_t nleft = *f.left_count;
+    constexpr int NCS = Q_SPILL_SLOTS / 32;
+    for(uint32_t it = gw; it < nleft; it += nw) {
+        const uint32_t r = f.left_list[it];
+        const uint64_t s0 = uint64_t(p.W[r]) * p.s, s1 = uint64_t(p.W[r + 1]) * p.s;
+        if(s1 - s0 > uint64_t(Q_SPILL_SLOTS)) {
+            if(lane == 0) f.left_list2[atomicAdd(f.left_count2, 1u)] = r;
+            continue;
+        }
+        const uint32_t ns = uint32_t(s1 - s0);
+        uint32_t len[NCS];
+        uint64_t off[NCS], loc0[NCS], loc1[NCS];
+        uint32_t tot = 0;
+#pragma unroll
+        for(int c = 0; c < NCS; ++c) {
+            len[c] = 0; off[c] = 0; loc0[c] = 0; loc1[c] = 0;
+            const uint32_t sl = uint32_t(c) * 32u + uint32_t(lane);
+            const uint32_t key = sl < ns ? f.feat[s0 + sl] : EMPTY_KEY;
+            if(key != EMPTY_KEY) {
+                uint32_t b = table_bucket(key, f.geom);
+                for(;;) {
+                    const uint32_t* line = f.table + uint64_t(b) * TABLE_BUCKET_WORDS;
+                    const uint4 k4 = __ldg(reinterpret_cast<const uint4*>(line));
+                    const int t = table_match(k4, key);
+                    if(t >= 0) {
+                        const uint4* pay = reinterpret_cast<const uint4*>(line + 8 + 8 * t);
+                        const uint4 q0 = __ldg(pay), q1 = __ldg(pay + 1);
+                        len[c] = q0.x;
+                        off[c] = uint64_t(q0.z) | (uint64_t(q0.w) << 32);
+                        loc0[c] = uint64_t(q1.x) | (uint64_t(q1.y) << 32);
+                        loc1[c] = uint64_t(q1.z) | (uint64_t(q1.w) << 32);
+                        break;
+                    }
+                    if(t == -1) break;
+                    ++b;
+                }
+            }
+            tot += len[c];
+        }
+        uint32_t inc = tot;
+#pragma unroll
+        for(int d = 1; d < 32; d <<= 1) {
+            const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+            if(lane >= d) inc += o;
+        }
+        const uint32_t m = __shfl_sync(0xFFFFFFFFu, inc, 31);
+        if(lane == 0) f.done[r] = 1;
+        if(m == 0) {
+            if(lane == 0) p.out_n[r] = 0;
+            if(lane < p.K) { p.out_tax[uint64_t(r) * p.K + lane] = -1; p.out_hits[uint64_t(r) * p.K + lane] = 0u; }
+            continue;
+        }
+        // matches in feature-slot order (any order would do: they are sorted next)
+        uint32_t pos = inc - tot;
+#pragma unroll
+        for(int c = 0; c < NCS; ++c) {
+            const uint32_t L = len[c];
+            if(L >= 1) A[pos] = make_key<KeyT>(loc0[c], p.wbits);
+            if(L >= 2) A[pos + 1] = make_key<KeyT>(loc1[c], p.wbits);
+            for(uint32_t t = 2; t < L; ++t) A[pos + t] = make_key<KeyT>(f.locs[off[c] + t], p.wbits);
+            pos += L;
+        }
+        __syncwarp();
+        bitonic_sort<true>(A, m, lane, 32);
+        __syncwarp();
+        const uint32_t numwin = num_windows_in_range(p, r);
+        for(uint32_t i = lane; i < m; i += 32) Hh[i] = hits_ending_at(A, i, numwin, p.wbits);
+        __syncwarp();
+        toplist_from_sorted<KeyT>(p, r, A, Hh, m, Ct, Ch, lane);
+    }
+}
+
 // medium / large reads: one CTA per read, capacity fixed by the launch
 template<class KeyT>
 __global__ void q_cand_cta_kernel(const CandParams p, uint32_t capacity)
@@ -1397,7 +1504,7 @@ static int qa_fused(mcg_db* db, const mcg_query_opts* o, QPart& part, int slot, 
     MCG_TRY(part.done.reserve(size_t(n) + 16));
     MCG_TRY(part.left_list.reserve(size_t(n + 2) * 4));
     uint32_t* left = part.ctr.as<uint32_t>();
-    if(!ctr_cleared) MCG_CUDA(cudaMemsetAsync(left, 0, 8, c->stream));
+    if(!ctr_cleared) MCG_CUDA(cudaMemsetAsync(left, 0, 16, c->stream));
     CandParams p;
     fill_cand_params(db, o, part.W.as<uint32_t>(), part.meta.as<uint2>(), d_out_tax, d_out_hits, d_out_n, 0, &p);
     FusedParams f;
@@ -1435,7 +1542,24 @@ static int qa_fused(mcg_db* db, const mcg_query_opts* o, QPart& part, int slot, 
 #undef QF_LAUNCH_CAP
     c->launches++;
     MCG_CUDA(cudaGetLastError());
-    MCG_CUDA(cudaMemcpyAsync(c->h_left + slot, left, 4, cudaMemcpyDeviceToHost, c->stream));
+    // short reads it left over: finished by the spill kernel, without the host
+    {
+        const unsigned g = unsigned(c->num_sms);
+        const size_t cap = size_t(Q_SPILL_SLOTS) * size_t(db->maxlocs);
+        const size_t per_warp = cap * ((db->key32 ? 4 : 8) + 12);
+        MCG_TRY(c->q_spill.reserve(size_t(g) * Q_SPILL_WARPS * per_warp));
+        MCG_TRY(part.left_list2.reserve(size_t(n + 2) * 4));
+        SpillParams sp;
+        sp.feat = part.feat.as<uint32_t>(); sp.table = db->table.as<uint32_t>(); sp.geom = db->geom(); sp.locs = db->locs.as<uint64_t>();
+        sp.done = part.done.as<uint8_t>(); sp.left_count = left; sp.left_list = part.left_list.as<uint32_t>();
+        sp.left_count2 = left + 2; sp.left_list2 = part.left_list2.as<uint32_t>();
+        sp.scratch = c->q_spill.as<unsigned char>(); sp.cap = uint32_t(cap);
+        if(db->key32) q_spill_warp_kernel<uint32_t><<<g, Q_SPILL_WARPS * 32, 0, c->stream>>>(p, sp);
+        else          q_spill_warp_kernel<uint64_t><<<g, Q_SPILL_WARPS * 32, 0, c->stream>>>(p, sp);
+        c->launches++;
+        MCG_CUDA(cudaGetLastError());
+    }
+    MCG_CUDA(cudaMemcpyAsync(c->h_left + slot, left + 2, 4, cudaMemcpyDeviceToHost, c->stream));
     MCG_CUDA(cudaEventRecord(part.evA, c->stream));
     return MCG_OK;
 }
@@ -1461,7 +1585,7 @@ static int qb_leftovers(mcg_db* db, const mcg_query_opts* o, QPart& part, int sl
         // are per feature slot of the batch they are given)
         MCG_TRY(c->s_wc.reserve(size_t(h_left + 2) * 4));
         uint32_t* Wc = c->s_wc.as<uint32_t>();
-        const uint32_t* left_list = part.left_list.as<uint32_t>();
+        const uint32_t* left_list = part.left_list2.as<uint32_t>();
         q_left_counts_kernel<<<grid_for(h_left), 256, 0, c->stream>>>(W, left_list, h_left, Wc);
         c->launches++;
         MCG_TRY(exclusive_scan_u32_to_u32(c, Wc, Wc, h_left));
@@ -1845,7 +1969,7 @@ int mcg_query_batch(mcg_db* db, const mcg_query_opts* o,
         const int64_t a = i * sub_reads, b = std::min(n, a + sub_reads);
         char* dbuf = c->seq.as<char>() + size_t(slot) * bufsz;
         int64_t* doff = c->seqoff.as<int64_t>() + size_t(slot) * 2 * offsz;
-        if(i >= 2) MCG_CUDA(cudaStreamWaitEvent(c->s_h2d, c->ev_k[slot], 0));      // the buffer's previous user is done
+        if(i >= 2) MCG_CUDA(cudaStreamWaitEvent(c->s_h2d, c->qp[slot].evA, 0));     // stage A of part i-2 has consumed the buffer
         // the (small) offset arrays first: they usually come from pageable memory, whose copy blocks the
         // host until everything queued before it on the stream is done
         MCG_CUDA(cudaMemcpyAsync(doff, offs1 + a, size_t(b - a + 1) * 8, cudaMemcpyHostToDevice, c->s_h2d));
@@ -1872,8 +1996,8 @@ int mcg_query_batch(mcg_db* db, const mcg_query_opts* o,
     for(int64_t i = 0; i < nsub; ++i) {
         const int slot = int(i & 1);
         const int64_t a = i * sub_reads, b = std::min(n, a + sub_reads);
-        // (the staging buffer of part i+1 is the one part i-1 used: its stage B must be enqueued first)
-        if(i >= 1) MCG_TRY(finish(i - 1));
+        // stage A of part i is enqueued BEFORE the host waits for part i-1's left-over count (finish): the GPU
+        // never idles on the host.  (Stage B reads no staging buffer: the per-read meta carries what it needs.)
         if(i + 1 < nsub) MCG_TRY(stage(i + 1));
         MCG_CUDA(cudaStreamWaitEvent(c->stream, c->ev_h2d[slot], 0));
         // the offsets keep their values of the whole batch: the base pointers are moved instead
@@ -1884,6 +2008,7 @@ int mcg_query_batch(mcg_db* db, const mcg_query_opts* o,
         MCG_TRY(query_batch_dev(db, o, d1, do1, offs1[b] - offs1[a], d2, do2, reads2 ? offs2[b] - offs2[a] : 0, b - a, 0,
                                 c->q_out_tax.as<int32_t>() + a * K, c->q_out_hits.as<uint32_t>() + a * K,
                                 c->q_out_n.as<int32_t>() + a, slot, false));
+        if(i >= 1) MCG_TRY(finish(i - 1));
     }
     MCG_TRY(finish(nsub - 1));
     MCG_CUDA(cudaStreamSynchronize(c->s_d2h));
@@ -2090,7 +2215,7 @@ int mcg_query_batch_sharded(mcg_db* db, mcg_comm* comm, const mcg_query_opts* o,
         const int slot = j & 1;
         const int64_t a = lo[size_t(j)], b = lo[size_t(j) + 1];
         char* dbuf = c->seq.as<char>() + size_t(slot) * bufsz;
-        if(j >= 2) MCG_CUDA(cudaStreamWaitEvent(c->s_h2d, c->ev_k[slot], 0));      // the buffer's previous user is done
+        if(j >= 2) MCG_CUDA(cudaStreamWaitEvent(c->s_h2d, c->qp[slot].evA, 0));     // stage A of part j-2 has consumed the buffer
         if(b > a) {
             MCG_CUDA(cudaMemcpyAsync(dbuf, reads1 + offs1[a], size_t(offs1[b] - offs1[a]), cudaMemcpyHostToDevice, c->s_h2d));
             if(paired) MCG_CUDA(cudaMemcpyAsync(dbuf + pad1, reads2 + offs2[a], size_t(offs2[b] - offs2[a]), cudaMemcpyHostToDevice, c->s_h2d));
@@ -2121,7 +2246,7 @@ int mcg_query_batch_sharded(mcg_db* db, mcg_comm* comm, const mcg_query_opts* o,
     for(int j = 0; j < np; ++j) {
         const int slot = j & 1;
         const int64_t a = lo[size_t(j)], b = lo[size_t(j) + 1];
-        if(j >= 1) MCG_TRY(finish(j - 1));
+        // stage A of part j is enqueued BEFORE the host waits for part j-1's left-over count (finish)
         if(j + 1 < np) MCG_TRY(stage(j + 1));
         MCG_CUDA(cudaStreamWaitEvent(c->stream, c->ev_h2d[slot], 0));
         if(j >= 2) MCG_CUDA(cudaStreamWaitEvent(c->stream, c->ev_h2d[2 + slot], 0));   // q.m* of this slot are free again
@@ -2130,6 +2255,7 @@ int mcg_query_batch_sharded(mcg_db* db, mcg_comm* comm, const mcg_query_opts* o,
         const char* d2 = paired ? c->seq.as<char>() + size_t(slot) * bufsz + pad1 - offs2[a] : nullptr;
         MCG_TRY(qs_stage_a(db, comm, o, pl, j, slot, d1, do1 + a, offs1[b] - offs1[a], d2, paired ? do2 + a : nullptr,
                            paired ? offs2[b] - offs2[a] : 0, 0));
+        if(j >= 1) MCG_TRY(finish(j - 1));
     }
     MCG_TRY(finish(np - 1));
     uint64_t st[22];
