@@ -447,12 +447,20 @@ def run_mcgpu(args):
         step_e2e(i)
     barrier()
     hstats[:] = 0
+    e2e_prof = bool(os.environ.get("MCG_BENCH_E2E_PROFILE"))        # development aid: GPU time per phase inside the e2e calls
+    if e2e_prof:
+        ctx.profile(True)
+        for w_ in range(8):
+            ctx.kernel_times(w_)
     t0 = time.perf_counter()
     for i in range(args.e2e_steps):
         step_e2e(i)
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     sampler.stop()
+    if e2e_prof:
+        log("e2e GPU ms per step by phase: %s" % {w_: round(ctx.kernel_times(w_)[0] / args.e2e_steps, 3) for w_ in range(8)})
+        ctx.profile(False)
     e2e_value = 2.0 * args.pairs * args.e2e_steps / e2e_s
     log("e2e: %.3f ms per step" % (1e3 * e2e_s / args.e2e_steps))
     # what the e2e call returned for the batch it ran last ((e2e_steps - 1) % NB), kept for the parity sample

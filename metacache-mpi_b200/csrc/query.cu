@@ -25,6 +25,8 @@
 //   The host entry point mcg_query_batch cuts a batch into sub-batches and overlaps H2D, query and D2H.
 #include "common.cuh"
 
+#include <ctime>
+
 namespace mcg {
 
 int copy_in(mcg_ctx* c, void* d, const void* h, size_t bytes);
@@ -2172,7 +2174,9 @@ int mcg_query_batch_sharded(mcg_db* db, mcg_comm* comm, const mcg_query_opts* o,
     if(P == 1 && n == 0) return MCG_OK;
     const int K = o->maxcand;
     static const int64_t sub_reads = [] { const char* e = getenv("MCG_QUERY_SUB"); const int64_t v = e ? atoll(e) : 262144; return v < 1 ? int64_t(1) : v; }();
-    static const int np_env = getenv("MCG_SHARD_PARTS") ? atoi(getenv("MCG_SHARD_PARTS")) : 4;
+    // parts per call with P > 1: the slice of a rank is 1/P of the batch, its PCIe copy is short; every part costs
+    // launch tails and one NCCL group per exchange, so two parts (copy of one behind the kernels of the other) do
+    static const int np_env = getenv("MCG_SHARD_PARTS") ? atoi(getenv("MCG_SHARD_PARTS")) : 2;
     const bool paired = reads2 != nullptr;
     // the offsets of the whole slice go to the device first (the plan needs them), the bases follow part by part
     static const int64_t zero_off[1] = {0};
@@ -2242,12 +2246,17 @@ int mcg_query_batch_sharded(mcg_db* db, mcg_comm* comm, const mcg_query_opts* o,
         MCG_CUDA(cudaEventRecord(c->ev_h2d[2 + slot], c->s_d2h));      // the merged results of this slot have left the device
         return MCG_OK;
     };
+    static const bool trace = getenv("MCG_TRACE") != nullptr;
+    auto now = [] { timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec + 1e-9 * t.tv_nsec; };
+    double t_stage = 0, t_a = 0, t_fin = 0, t0 = now(), tt = 0;
     MCG_TRY(stage(0));
     for(int j = 0; j < np; ++j) {
         const int slot = j & 1;
         const int64_t a = lo[size_t(j)], b = lo[size_t(j) + 1];
         // stage A of part j is enqueued BEFORE the host waits for part j-1's left-over count (finish)
+        tt = now();
         if(j + 1 < np) MCG_TRY(stage(j + 1));
+        t_stage += now() - tt; tt = now();
         MCG_CUDA(cudaStreamWaitEvent(c->stream, c->ev_h2d[slot], 0));
         if(j >= 2) MCG_CUDA(cudaStreamWaitEvent(c->stream, c->ev_h2d[2 + slot], 0));   // q.m* of this slot are free again
         // the offsets keep their values of the whole slice: the base pointers are moved instead
@@ -2255,13 +2264,20 @@ int mcg_query_batch_sharded(mcg_db* db, mcg_comm* comm, const mcg_query_opts* o,
         const char* d2 = paired ? c->seq.as<char>() + size_t(slot) * bufsz + pad1 - offs2[a] : nullptr;
         MCG_TRY(qs_stage_a(db, comm, o, pl, j, slot, d1, do1 + a, offs1[b] - offs1[a], d2, paired ? do2 + a : nullptr,
                            paired ? offs2[b] - offs2[a] : 0, 0));
+        t_a += now() - tt; tt = now();
         if(j >= 1) MCG_TRY(finish(j - 1));
+        t_fin += now() - tt;
     }
+    tt = now();
     MCG_TRY(finish(np - 1));
+    t_fin += now() - tt;
     uint64_t st[22];
     MCG_CUDA(cudaMemcpyAsync(st, c->m_stats.p, 22 * 8, cudaMemcpyDeviceToHost, c->stream));
+    tt = now();
     MCG_CUDA(cudaStreamSynchronize(c->s_d2h));
     MCG_CUDA(cudaStreamSynchronize(c->stream));
+    if(trace) fprintf(stderr, "[mcg sharded host] %d parts: stage %.3f ms, stage A %.3f ms, finish %.3f ms, final wait %.3f ms, call %.3f ms\n",
+                      np, 1e3 * t_stage, 1e3 * t_a, 1e3 * t_fin, 1e3 * (now() - tt), 1e3 * (now() - t0));
     if(out_stats22) for(int i = 0; i < 22; ++i) out_stats22[i] += st[i];
     return MCG_OK;
 }
