@@ -103,6 +103,9 @@ int  mcg_ctx_create(int device, void* stream, mcg_ctx** out);
 int  mcg_ctx_destroy(mcg_ctx*);
 int  mcg_ctx_sync(mcg_ctx*);
 void* mcg_ctx_stream(mcg_ctx*);
+/* scratch blocks the library released are parked for reuse (cudaFree of multi-GB blocks is slow and synchronises
+ * the device), at most 8 GB per device (MCG_CACHE_CAP_MB); mcg_ctx_trim returns all of them to the driver */
+int  mcg_ctx_trim(mcg_ctx*);
 /* number of kernels this library launched on the ctx since creation */
 int64_t mcg_ctx_launches(mcg_ctx*);
 /* measurement hook: while enabled, the library brackets every launch of its three dominant kernels with CUDA

@@ -64,6 +64,7 @@ def load_library():
     L.mcg_ctx_stream.argtypes = [vp]
     L.mcg_ctx_launches.restype = i64
     L.mcg_ctx_launches.argtypes = [vp]
+    L.mcg_ctx_trim.argtypes = [vp]
     L.mcg_ctx_profile.argtypes = [vp, C.c_int]
     L.mcg_ctx_kernel_times.argtypes = [vp, C.c_int, C.POINTER(C.c_double), C.POINTER(i64)]
     L.mcg_db_add_targets_dev.argtypes = [vp, vp, vp, vp, i64, vp]

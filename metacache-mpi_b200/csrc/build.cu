@@ -526,7 +526,6 @@ int db_finalize(mcg_db* db)
     MCG_TRY(build_table(db));
     MCG_CUDA(cudaStreamSynchronize(c->stream));
     TRACE("table");
-    trim_cached_device_memory(size_t(1) << 30);      // the sort scratch does not stay parked
     {
         uint64_t maxwin = 0;
         for(size_t t = 0; t + 1 < db->h_tgt_firstwin.size(); ++t) maxwin = std::max<uint64_t>(maxwin, db->h_tgt_firstwin[t + 1] - db->h_tgt_firstwin[t]);

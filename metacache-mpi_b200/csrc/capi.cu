@@ -153,6 +153,10 @@ void DevBuf::release()
     }
     p = nullptr;
     cap = 0;
+    // parked memory is capped (MCG_CACHE_CAP_MB, default 8 GB per device): beyond that the largest blocks go back
+    // to the driver, so that other allocators of the process (torch, NCCL) are not starved; mcg_ctx_trim frees all
+    static const size_t cap_bytes = size_t(getenv("MCG_CACHE_CAP_MB") ? atoll(getenv("MCG_CACHE_CAP_MB")) : 8192) << 20;
+    trim_cached_device_memory(cap_bytes);
 }
 
 // host pointer -> device, asynchronous when the host memory is page-locked
@@ -256,6 +260,15 @@ int mcg_ctx_sync(mcg_ctx* c)
 void* mcg_ctx_stream(mcg_ctx* c) { return c ? static_cast<void*>(c->stream) : nullptr; }
 
 int64_t mcg_ctx_launches(mcg_ctx* c) { return c ? c->launches : 0; }
+
+int mcg_ctx_trim(mcg_ctx* c)
+{
+    MCG_REQUIRE(c != nullptr, "ctx is NULL");
+    MCG_CUDA(cudaSetDevice(c->device));
+    MCG_CUDA(cudaStreamSynchronize(c->stream));
+    trim_cached_device_memory(0);
+    return MCG_OK;
+}
 
 int mcg_ctx_profile(mcg_ctx* c, int enable)
 {

@@ -165,6 +165,22 @@ int comm_alltoallv(mcg_comm* m, const void* send, const uint64_t* soff, const ui
     return MCG_OK;
 }
 
+// several exchanges as ONE NCCL group (one kernel launch): used for the pieces of a logical record that live in
+// separate arrays (features + per-read meta; taxa + hits + counts of the top lists)
+int comm_group_begin(mcg_comm* m)
+{
+    if(m == nullptr || m->nranks == 1) return MCG_OK;
+    MCG_NCCL(g_nccl.GroupStart());
+    return MCG_OK;
+}
+
+int comm_group_end(mcg_comm* m)
+{
+    if(m == nullptr || m->nranks == 1) return MCG_OK;
+    MCG_NCCL(g_nccl.GroupEnd());
+    return MCG_OK;
+}
+
 int comm_allreduce_sum_u64(mcg_comm* m, uint64_t* d_buf, int count, cudaStream_t st)
 {
     if(m == nullptr || m->nranks == 1) return MCG_OK;

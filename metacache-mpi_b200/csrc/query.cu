@@ -40,6 +40,8 @@ int comm_allgather_dev_u64(mcg_comm* m, const uint64_t* d_mine, int count, uint6
 int comm_allgatherv_inplace(mcg_comm* m, void* buf, const uint64_t* off, const uint64_t* len, cudaStream_t st);
 int comm_alltoallv(mcg_comm* m, const void* send, const uint64_t* soff, const uint64_t* slen,
                    void* recv, const uint64_t* roff, const uint64_t* rlen, cudaStream_t st);
+int comm_group_begin(mcg_comm* m);
+int comm_group_end(mcg_comm* m);
 
 constexpr uint32_t EMPTY_KEY = 0xFFFFFFFFu;
 constexpr int Q_SMALL = 512;       // matches per read handled by one warp
@@ -1812,11 +1814,13 @@ static int qs_stage_a(mcg_db* db, mcg_comm* comm, const mcg_query_opts* o, const
         c->prof_begin(4, c->stream);
         std::vector<uint64_t> off(static_cast<size_t>(P)), len(static_cast<size_t>(P));
         uint64_t a = 0;
+        MCG_TRY(comm_group_begin(comm));                       // sketches + per-read meta: one NCCL group
         for(int r = 0; r < P; ++r) { off[size_t(r)] = a * uint64_t(s) * 4; len[size_t(r)] = pl.rw(j, r) * uint64_t(s) * 4; a += pl.rw(j, r); }
         MCG_TRY(comm_allgatherv_inplace(comm, part.feat.p, off.data(), len.data(), c->stream));
         a = 0;
         for(int r = 0; r < P; ++r) { off[size_t(r)] = a * 8; len[size_t(r)] = pl.rn(j, r) * 8; a += pl.rn(j, r); }
         MCG_TRY(comm_allgatherv_inplace(comm, part.meta.p, off.data(), len.data(), c->stream));
+        MCG_TRY(comm_group_end(comm));
         if(N > 0) {
             q_meta_windows_kernel<<<grid_for(N), 256, 0, c->stream>>>(part.meta.as<uint2>(), int64_t(N), part.W.as<uint32_t>());
             c->launches++;
@@ -1855,6 +1859,7 @@ static int qs_stage_b(mcg_db* db, mcg_comm* comm, const mcg_query_opts* o, const
         MCG_TRY(part.ct.reserve(size_t(P) * (n_me + 1) * K * 4)); MCG_TRY(part.ch.reserve(size_t(P) * (n_me + 1) * K * 4));
         MCG_TRY(part.cn.reserve(size_t(P) * (n_me + 1) * 4));
         std::vector<uint64_t> so(static_cast<size_t>(P)), sl(static_cast<size_t>(P)), ro(static_cast<size_t>(P)), rl(static_cast<size_t>(P));
+        MCG_TRY(comm_group_begin(comm));                       // taxa + hits + counts: one NCCL group
         for(int pass = 0; pass < 2; ++pass) {
             const uint64_t row = pass == 0 ? uint64_t(K) * 4 : 4;       // bytes per read: lists, counts
             uint64_t a = 0;
@@ -1869,6 +1874,7 @@ static int qs_stage_b(mcg_db* db, mcg_comm* comm, const mcg_query_opts* o, const
                 MCG_TRY(comm_alltoallv(comm, part.ln.p, so.data(), sl.data(), part.cn.p, ro.data(), rl.data(), c->stream));
             }
         }
+        MCG_TRY(comm_group_end(comm));
         ct = part.ct.as<int32_t>(); ch = part.ch.as<uint32_t>(); cn = part.cn.as<int32_t>();
         c->prof_end(6, c->stream);
     }
