@@ -53,12 +53,28 @@ __device__ __forceinline__ void rn_load8(const uint32_t* a, uint64_t e0, uint64_
     }
 }
 
+// target of a global window: coarse[c] = largest t with firstwin[t] <= c << TGT_COARSE_SHIFT
+constexpr int TGT_COARSE_SHIFT = 10;
+
+__global__ void tgt_coarse_kernel(const uint64_t* __restrict__ firstwin, uint32_t ntgt, uint32_t ncells, uint32_t* __restrict__ coarse)
+{
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if(c > ncells) return;
+    const uint64_t w = uint64_t(c) << TGT_COARSE_SHIFT;
+    uint32_t lo = 0, hi = ntgt;
+    while(hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if(firstwin[mid] <= w) lo = mid; else hi = mid;
+    }
+    coarse[c] = lo;
+}
+
 template<bool EMIT>
 __global__ void __launch_bounds__(RN_THREADS)
 runs_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ slots, uint64_t n, uint32_t maxlocs,
             uint32_t* __restrict__ tile_heads, uint32_t* __restrict__ tile_kept,      // COUNT: per-tile counts out; EMIT: their exclusive prefixes
             uint32_t* __restrict__ ukeys, uint8_t* __restrict__ sizes, uint64_t* __restrict__ offs, uint64_t* __restrict__ locs,
-            uint32_t sketchlen, const uint64_t* __restrict__ tgt_firstwin, const uint32_t* __restrict__ tgt_id, uint32_t ntgt)
+            const uint32_t* __restrict__ tgt_coarse, const uint64_t* __restrict__ tgt_firstwin, const uint32_t* __restrict__ tgt_id, uint32_t ntgt)
 {
     __shared__ long long s_max[RN_THREADS / 32];
     __shared__ unsigned long long s_sum[RN_THREADS / 32];
@@ -153,8 +169,11 @@ runs_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ slot
         const uint32_t nk = i + 1 < RN_ITEMS ? k[i + 1] : next;
         if(k[i] != EMPTY_KEY && nk != k[i]) sizes[kidx] = uint8_t(min(pos[i] + 1u, maxlocs));
         if(kmask >> i & 1u) {
-            const uint64_t gw = sl[i] / sketchlen;             // global window of the shard
-            uint32_t lo = 0, hi = ntgt;                        // largest t with firstwin[t] <= gw
+            // the sort carried the GLOBAL WINDOW of every slot; its target = largest t with firstwin[t] <= gw, looked
+            // up between the targets that hold the first window of this and of the next coarse cell (usually the same)
+            const uint64_t gw = sl[i];
+            const uint32_t cell = uint32_t(gw >> TGT_COARSE_SHIFT);
+            uint32_t lo = __ldg(tgt_coarse + cell), hi = min(__ldg(tgt_coarse + cell + 1) + 1u, ntgt);
             while(hi - lo > 1) {
                 const uint32_t mid = (lo + hi) >> 1;
                 if(__ldg(tgt_firstwin + mid) <= gw) lo = mid; else hi = mid;
@@ -480,7 +499,7 @@ int db_finalize(mcg_db* db)
     uint32_t* skeys = db->feat.as<uint32_t>();
     uint32_t* svals = c->tmp0.as<uint32_t>();
     TRACE("alloc sort buffers");
-    MCG_TRY(radix_sort_pairs(c, skeys, svals, c->tmp1.as<uint32_t>(), c->tmp2.as<uint32_t>(), nslots, 32, true));
+    MCG_TRY(radix_sort_pairs(c, skeys, svals, c->tmp1.as<uint32_t>(), c->tmp2.as<uint32_t>(), nslots, 32, true, s));   // value = slot / s = window
     TRACE("radix sort");
     // (2) runs of equal feature: counts per tile, scan, then keys / sizes / offsets / locations in one pass
     const uint32_t ntiles = uint32_t((nslots + RN_TILE - 1) / RN_TILE);
@@ -493,8 +512,12 @@ int db_finalize(mcg_db* db)
     MCG_TRY(c->tmp4.reserve((size_t(ntgt) + 2) * 4 + 64));
     MCG_CUDA(cudaMemcpyAsync(c->tmp3.p, db->h_tgt_firstwin.data(), (size_t(ntgt) + 1) * 8, cudaMemcpyHostToDevice, c->stream));
     MCG_CUDA(cudaMemcpyAsync(c->tmp4.p, db->h_tgt_id.data(), size_t(ntgt) * 4, cudaMemcpyHostToDevice, c->stream));
+    const uint32_t ncells = uint32_t(db->nwin >> TGT_COARSE_SHIFT) + 1;
+    MCG_TRY(c->tmp5.reserve((size_t(ncells) + 2) * 4));
+    tgt_coarse_kernel<<<grid_for(ncells + 1), 256, 0, c->stream>>>(c->tmp3.as<uint64_t>(), ntgt, ncells, c->tmp5.as<uint32_t>());
     runs_kernel<false><<<ntiles, RN_THREADS, 0, c->stream>>>(skeys, svals, nslots, uint32_t(db->maxlocs), th, tk, nullptr, nullptr, nullptr, nullptr,
-                                                             s, nullptr, nullptr, 0);
+                                                             nullptr, nullptr, nullptr, 0);
+    c->launches++;
     c->launches++;
     MCG_TRY(exclusive_scan_u32_to_u32(c, th, th, ntiles));
     MCG_TRY(exclusive_scan_u32_to_u32(c, tk, tk, ntiles));
@@ -512,7 +535,7 @@ int db_finalize(mcg_db* db)
     MCG_TRY(db->locs.reserve((nlocs + 2) * 8));
     runs_kernel<true><<<ntiles, RN_THREADS, 0, c->stream>>>(skeys, svals, nslots, uint32_t(db->maxlocs), th, tk, db->keys.as<uint32_t>(),
                                                             db->sizes.as<uint8_t>(), db->offs.as<uint64_t>(), db->locs.as<uint64_t>(),
-                                                            s, c->tmp3.as<uint64_t>(), c->tmp4.as<uint32_t>(), ntgt);
+                                                            c->tmp5.as<uint32_t>(), c->tmp3.as<uint64_t>(), c->tmp4.as<uint32_t>(), ntgt);
     set_u64_kernel<<<1, 1, 0, c->stream>>>(db->offs.as<uint64_t>() + nkeys, nlocs);
     c->launches += 2;
     MCG_CUDA(cudaGetLastError());

@@ -239,9 +239,10 @@ int exclusive_scan_u32_to_u64(mcg_ctx* c, const uint32_t* d_in, uint64_t* d_out,
 // exclusive prefix sum of n uint8 -> uint64 out[n+1]
 int exclusive_scan_u8_to_u64(mcg_ctx* c, const uint8_t* d_in, uint64_t* d_out, uint64_t n);
 // stable LSD radix sort of (key,val) uint32 pairs on bits [0, key_bits); result in keys/vals
-// (alt buffers are scratch of the same size)
+// (alt buffers are scratch of the same size); iota_vals: the values are not read but generated, value of
+// element i = i / iota_div
 int radix_sort_pairs(mcg_ctx* c, uint32_t* keys, uint32_t* vals, uint32_t* keys_alt, uint32_t* vals_alt,
-                     uint64_t n, int key_bits, bool iota_vals);
+                     uint64_t n, int key_bits, bool iota_vals, uint32_t iota_div = 1);
 
 // ------------------------------------------------------------------ stages
 int sketch_launch(mcg_ctx* c, const mcg_sketch_cfg& cfg, int sketchlen, int64_t winlen, int64_t stride,

@@ -54,7 +54,7 @@ template<int THREADS>
 __global__ void __launch_bounds__(THREADS, 1024 / THREADS)
 rs_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                   uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
-                  uint64_t n, int shift, const uint32_t* __restrict__ offsets, uint32_t ntiles, int iota)
+                  uint64_t n, int shift, const uint32_t* __restrict__ offsets, uint32_t ntiles, uint32_t iota)
 {
     constexpr int TILE = THREADS * RS_ROUNDS, WARPS = THREADS / 32;
     extern __shared__ __align__(16) uint32_t rs_sm[];
@@ -149,7 +149,7 @@ rs_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restri
         const uint32_t d = (mykey[r] >> shift) & 255u;
         const uint32_t pos = s_start[d] + wc[d] + ((r & 1) ? (myrank[r >> 1] >> 16) : (myrank[r >> 1] & 0xFFFFu));
         if(r & 1) myrank[r >> 1] = (myrank[r >> 1] & 0xFFFFu) | (pos << 16); else myrank[r >> 1] = (myrank[r >> 1] & 0xFFFF0000u) | pos;
-        if(li < tile_n) s_val[pos] = iota ? uint32_t(base + li) : s_key[li];
+        if(li < tile_n) s_val[pos] = iota ? uint32_t(base + li) / iota : s_key[li];      // iota = divisor of the element index (0: values given)
     }
     __syncthreads();
 #pragma unroll
@@ -170,15 +170,16 @@ rs_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restri
     }
 }
 
-__global__ void iota_kernel(uint32_t* v, uint64_t n)
+__global__ void iota_kernel(uint32_t* v, uint64_t n, uint32_t div)
 {
     const uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
-    if(i < n) v[i] = uint32_t(i);
+    if(i < n) v[i] = uint32_t(i) / div;
 }
 
 int radix_sort_pairs(mcg_ctx* c, uint32_t* keys, uint32_t* vals, uint32_t* keys_alt, uint32_t* vals_alt,
-                     uint64_t n, int key_bits, bool iota_vals)
+                     uint64_t n, int key_bits, bool iota_vals, uint32_t iota_div)
 {
+    if(iota_div == 0) iota_div = 1;
     if(n == 0) return MCG_OK;
     MCG_REQUIRE(n < (1ull << 32), "radix_sort_pairs: more than 2^32-1 elements");
     static const int threads = [] { const char* e = getenv("MCG_RS_THREADS"); return (e && atoi(e) == 512) ? 512 : 256; }();
@@ -195,7 +196,7 @@ int radix_sort_pairs(mcg_ctx* c, uint32_t* keys, uint32_t* vals, uint32_t* keys_
     uint32_t* ki = keys; uint32_t* vi = vals; uint32_t* ko = keys_alt; uint32_t* vo = vals_alt;
     for(int p = 0; p < passes; ++p) {
         const int shift = 8 * p;
-        const int iota = (iota_vals && p == 0) ? 1 : 0;
+        const uint32_t iota = (iota_vals && p == 0) ? iota_div : 0u;
         if(threads == 256) rs_hist_kernel<256><<<ntiles, 256, 0, c->stream>>>(ki, n, shift, hist, ntiles);
         else               rs_hist_kernel<512><<<ntiles, 512, 0, c->stream>>>(ki, n, shift, hist, ntiles);
         c->launches++;
@@ -210,7 +211,7 @@ int radix_sort_pairs(mcg_ctx* c, uint32_t* keys, uint32_t* vals, uint32_t* keys_
         t = vi; vi = vo; vo = t;
     }
     if(passes == 0 && iota_vals) {
-        iota_kernel<<<unsigned(div_up(int64_t(n), 256)), 256, 0, c->stream>>>(vals, n);
+        iota_kernel<<<unsigned(div_up(int64_t(n), 256)), 256, 0, c->stream>>>(vals, n, iota_div);
         c->launches++;
     }
     if(ki != keys) {        // odd number of passes: result sits in the alt buffers
