@@ -1191,7 +1191,9 @@ int mode_query(const Args& a)
     // GPU r ingests slice r of the batch over its own PCIe link, the sketches travel by NCCL all-gather, the top
     // lists by all-to-all, every GPU merges and classifies its slice.  More shards than GPUs (NCCL has one rank per
     // device): every shard is queried with all reads, the lists are merged on GPU 0 from host arrays.
-    const bool sharded = P == 1 || P <= mcg_device_count();
+    // Small inputs (< 256 k reads) are not worth the NCCL start-up (1-2 s for the first communicator of a process).
+    const size_t NCCL_MIN_READS = getenv("MCG_NCCL_MIN_READS") ? size_t(atoll(getenv("MCG_NCCL_MIN_READS"))) : (size_t(1) << 18);
+    const bool sharded = P == 1 || (P <= mcg_device_count() && nreads >= NCCL_MIN_READS);
     std::vector<mcg_comm*> comms;
     if(sharded && P > 1) comms = make_comms(P);
     lap("communicator");

@@ -27,8 +27,11 @@ QFLAGS = ["-pairfiles", "-lowest", "species", "-maxcand", "4", "-hitmin", "4", "
 G, L, NPAIRS = 10, 5_000_000, 50_000
 
 
+ENV = dict(os.environ, MCG_NCCL_MIN_READS="0")      # one GPU per shard: through the NCCL path also at this size
+
+
 def run(cmd, cwd):
-    r = subprocess.run(cmd, cwd=cwd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=1200)
+    r = subprocess.run(cmd, cwd=cwd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=1200, env=ENV)
     assert r.returncode == 0, r.stdout.decode()[-3000:]
     return r.stdout.decode()
 

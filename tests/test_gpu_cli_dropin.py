@@ -87,8 +87,13 @@ def stable_lines(path):
     return out
 
 
+# on a box with one GPU per shard the driver runs the NCCL path of libmcgpu (mcg_query_batch_sharded per GPU thread);
+# its small-input shortcut (no NCCL below 256 k reads) is switched off so that these small cases go through it
+ENV = dict(os.environ, MCG_NCCL_MIN_READS="0")
+
+
 def run(cmd, cwd):
-    r = subprocess.run(cmd, cwd=cwd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=600)
+    r = subprocess.run(cmd, cwd=cwd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=600, env=ENV)
     assert r.returncode == 0, r.stdout.decode()[-2000:]
     return r.stdout.decode()
 
