@@ -278,7 +278,7 @@ constexpr int TBL_CH = 256;
 __global__ void __launch_bounds__(TB_THREADS)
 table_build_kernel(uint4* __restrict__ table4, const uint32_t* __restrict__ ukeys, const uint8_t* __restrict__ sizes,
                    const uint64_t* __restrict__ offs, const uint64_t* __restrict__ locs,
-                   uint32_t nkeys, TableGeom g, const int64_t* __restrict__ tcarry, uint64_t cap, uint32_t ntiles)
+                   uint32_t nkeys, TableGeom g, const int64_t* __restrict__ tcarry, uint64_t cap, uint32_t ntiles, int key32, int wbits)
 {
     extern __shared__ __align__(16) uint4 lines[];              // [TBL_CH][8]
     __shared__ int64_t s[TB_THREADS / 32];
@@ -365,10 +365,19 @@ table_build_kernel(uint4* __restrict__ table4, const uint32_t* __restrict__ ukey
             const uint32_t b = rel / TABLE_BUCKET_SLOTS, st = rel - b * TABLE_BUCKET_SLOTS;
             const uint32_t size = sizes[j];
             const uint64_t o = offs[j];
-            const uint64_t l0 = size > 0 ? locs[o] : 0ull, l1 = size > 1 ? locs[o + 1] : 0ull;
+            uint32_t w[6] = {0u, 0u, 0u, 0u, 0u, 0u};
+            if(key32) {
+#pragma unroll
+                for(uint32_t t = 0; t < TABLE_INLINE_32; ++t)
+                    if(t < size) { const uint64_t l = locs[o + t]; w[t] = (uint32_t(l >> 32) << wbits) | uint32_t(l); }
+            } else {
+#pragma unroll
+                for(uint32_t t = 0; t < TABLE_INLINE_64; ++t)
+                    if(t < size) { const uint64_t l = locs[o + t]; w[2 * t] = uint32_t(l); w[2 * t + 1] = uint32_t(l >> 32); }
+            }
             words[b * TABLE_BUCKET_WORDS + st] = ukeys[j];
-            lines[b * 8 + 2 + 2 * st] = make_uint4(size, 0u, uint32_t(o), uint32_t(o >> 32));
-            lines[b * 8 + 3 + 2 * st] = make_uint4(uint32_t(l0), uint32_t(l0 >> 32), uint32_t(l1), uint32_t(l1 >> 32));
+            lines[b * 8 + 2 + 2 * st] = make_uint4(size, uint32_t(o), w[0], w[1]);
+            lines[b * 8 + 3 + 2 * st] = make_uint4(w[2], w[3], w[4], w[5]);
         }
         __syncthreads();
         uint4* out = table4 + cb * 8;
@@ -431,6 +440,7 @@ static int build_table(mcg_db* db)
     mcg_ctx* c = db->ctx;
     const uint64_t nkeys = db->nkeys;
     MCG_REQUIRE(nkeys < (1ull << 32), "too many keys in one shard");
+    MCG_REQUIRE(db->nlocs < (1ull << 32), "too many locations in one shard");       // slots hold 32-bit offsets into locs
     static double load = -1.0;
     if(load < 0) { const char* e = getenv("MCG_TABLE_LOAD"); load = e ? atof(e) : TABLE_LOAD; if(load < 0.05 || load > 0.95) load = TABLE_LOAD; }
     const uint64_t home = uint64_t(double(nkeys) / load / double(TABLE_BUCKET_SLOTS)) + 1;      // home buckets
@@ -461,7 +471,7 @@ static int build_table(mcg_db* db)
         MCG_CUDA(cudaFuncSetAttribute(table_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TBL_CH * 128));
         table_build_kernel<<<ntiles, TB_THREADS, TBL_CH * 128, c->stream>>>(db->table.as<uint4>(), db->keys.as<uint32_t>(), db->sizes.as<uint8_t>(),
                                                                           db->offs.as<uint64_t>(), db->locs.as<uint64_t>(), uint32_t(nkeys), g,
-                                                                          c->tmp5.as<int64_t>(), cap, ntiles);
+                                                                          c->tmp5.as<int64_t>(), cap, ntiles, db->key32 ? 1 : 0, db->wbits);
     } else {
         table_clear_kernel<<<grid_for(2 * cap), 256, 0, c->stream>>>(db->table.as<uint4>(), cap);
     }
@@ -545,16 +555,16 @@ int db_finalize(mcg_db* db)
     db->feat.release();
     c->tmp0.release(); c->tmp1.release(); c->tmp2.release();
     TRACE("free scratch");
-    // (5) open-addressing table over the unique keys
-    MCG_TRY(build_table(db));
-    MCG_CUDA(cudaStreamSynchronize(c->stream));
-    TRACE("table");
+    // (5) open-addressing table over the unique keys (its slots hold match keys in the shard's key layout)
     {
         uint64_t maxwin = 0;
         for(size_t t = 0; t + 1 < db->h_tgt_firstwin.size(); ++t) maxwin = std::max<uint64_t>(maxwin, db->h_tgt_firstwin[t + 1] - db->h_tgt_firstwin[t]);
         db->set_key_layout(db->h_tgt_id.empty() ? 0 : db->h_tgt_id.back(), maxwin);
         if(getenv("MCG_FORCE_KEY64")) { db->wbits = 32; db->key32 = false; }
     }
+    MCG_TRY(build_table(db));
+    MCG_CUDA(cudaStreamSynchronize(c->stream));
+    TRACE("table");
     db->finalized = true;
     return MCG_OK;
 }

@@ -190,7 +190,10 @@ __host__ __device__ __forceinline__ uint32_t slot_mix(uint32_t x)
 // Buckets of one 128-byte line = 3 slots, one 32-byte DRAM sector each for the keys and for
 // every slot's payload (uint32 words of the line):
 //   [0..2] keys   [3..7] unused
-//   [8 + 8t ..] payload of slot t: size (u32), pad, off (u64 index into locs), loc0 (u64), loc1 (u64)
+//   [8 + 8t ..] payload of slot t: size (u32), off (u32 index into locs: < 2^32 locations per shard), then 24 bytes of
+//               inline matches: when target and window ids of the shard fit 32 bits together (db->key32) the first SIX
+//               locations as packed match keys (tgt << wbits) | win -- the form the per-read sort works on --
+//               otherwise the first THREE locations as stored (tgt << 32 | win)
 // The home bucket of a key is MONOTONE in the key: bucket = rank_estimate(key) * nbuckets / nkeys,
 // where rank_estimate interpolates a 4096-cell cumulative histogram of the shard's keys (16 KB,
 // stays in L1).  Keys are bottom-s hashes, i.e. far from uniform, but locally uniform inside a
@@ -199,11 +202,12 @@ __host__ __device__ __forceinline__ uint32_t slot_mix(uint32_t x)
 // (slot_j = max(3 * home_j, slot_{j-1} + 1)): no atomics, no random writes.  A key lives in the
 // first bucket at or after its home bucket that had a free slot when it was placed; lookups walk
 // forward until the key or a free slot shows up (the table ends with an empty bucket: no wrap).
-// A probe is ONE line -- what an L1 miss fetches anyway -- with the first two locations of the list.
+// A probe is ONE line -- what an L1 miss fetches anyway -- with the first six (three) locations of the list.
 constexpr uint32_t TABLE_EMPTY = 0xFFFFFFFFu;
 constexpr int TABLE_BUCKET_WORDS = 32;
 constexpr int TABLE_BUCKET_SLOTS = 3;
 constexpr int TABLE_CDF_BITS = 12;
+constexpr uint32_t TABLE_INLINE_32 = 6, TABLE_INLINE_64 = 3;      // inline matches per slot (packed 32-bit keys / 64-bit locations)
 
 __device__ __forceinline__ uint32_t table_bucket(uint32_t key, const TableGeom& g)
 {

@@ -178,7 +178,7 @@ q_find_kernel(const uint32_t* __restrict__ feat, uint64_t nslots, const uint32_t
             if(t >= 0) {
                 const uint4 q0 = __ldg(reinterpret_cast<const uint4*>(line + 8 + 8 * t));
                 len = q0.x;
-                off = uint64_t(q0.z) | (uint64_t(q0.w) << 32);
+                off = q0.y;
                 break;
             }
             if(t == -1) break;
@@ -852,8 +852,11 @@ q_fused_warp_kernel(const CandParams p, const FusedParams f)
         // (1) probe.  A pass loads the bucket line (keys + sizes) of every unresolved feature of the
         //     lane at once; a feature leaves when its key or a free slot is found.  Passes repeat
         //     while any lane still has a feature whose bucket was full (few: <= 2 in most reads).
+        // pl[c][0..5]: the slot's inline match keys (common.cuh, "feature table": 6 packed 32-bit keys or 3 64-bit
+        // locations); a list longer than that has its offset into locs in pl[c][5] instead
+        constexpr uint32_t INL = sizeof(KeyT) == 4 ? TABLE_INLINE_32 : TABLE_INLINE_64;
         uint32_t key[NC], len[NC], bkt[NC];
-        uint64_t off[NC], loc0[NC], loc1[NC];
+        uint32_t pl[NC][6];
         bool pend[NC];
 #pragma unroll
         for(int c = 0; c < NC; ++c) {
@@ -864,7 +867,9 @@ q_fused_warp_kernel(const CandParams p, const FusedParams f)
             }
             pend[c] = key[c] != EMPTY_KEY;
             bkt[c] = pend[c] ? table_bucket(key[c], f.geom) : 0u;
-            len[c] = 0; off[c] = 0; loc0[c] = 0; loc1[c] = 0;
+            len[c] = 0;
+#pragma unroll
+            for(int w = 0; w < 6; ++w) pl[c][w] = 0;
         }
         for(;;) {
             uint4 k4[NC];
@@ -882,9 +887,8 @@ q_fused_warp_kernel(const CandParams p, const FusedParams f)
                         const uint4* pay = reinterpret_cast<const uint4*>(f.table + uint64_t(bkt[c]) * TABLE_BUCKET_WORDS + 8 + 8 * t);
                         const uint4 q0 = __ldg(pay), q1 = __ldg(pay + 1);
                         len[c] = q0.x;
-                        off[c] = uint64_t(q0.z) | (uint64_t(q0.w) << 32);
-                        loc0[c] = uint64_t(q1.x) | (uint64_t(q1.y) << 32);
-                        loc1[c] = uint64_t(q1.z) | (uint64_t(q1.w) << 32);
+                        pl[c][0] = q0.z; pl[c][1] = q0.w; pl[c][2] = q1.x; pl[c][3] = q1.y; pl[c][4] = q1.z;
+                        pl[c][5] = q0.x > INL ? q0.y : q1.w;
                         pend[c] = false;
                     } else if(t == -1) {
                         pend[c] = false;
@@ -919,20 +923,26 @@ q_fused_warp_kernel(const CandParams p, const FusedParams f)
             if(lane < p.K) { p.out_tax[uint64_t(r) * p.K + lane] = -1; p.out_hits[uint64_t(r) * p.K + lane] = 0u; }
             continue;
         }
-        // (3) matches into shared memory: lists of <= 2 straight from the slot, longer ones gathered
+        // (3) matches into shared memory: short lists straight from the slot, longer ones gathered
         uint32_t pos = inc - tot;
 #pragma unroll
         for(int c = 0; c < NC; ++c) {
             if(c < nc) {
                 const uint32_t L = len[c];
-                if(L >= 1 && L <= 2) {
-                    A[pos] = make_key<KeyT>(loc0[c], p.wbits);
-                    if(L == 2) A[pos + 1] = make_key<KeyT>(loc1[c], p.wbits);
+                if(L >= 1 && L <= INL) {
+                    if(sizeof(KeyT) == 4) {
+#pragma unroll
+                        for(uint32_t t = 0; t < TABLE_INLINE_32; ++t) if(t < L) A[pos + t] = KeyT(pl[c][t]);
+                    } else {
+#pragma unroll
+                        for(uint32_t t = 0; t < TABLE_INLINE_64; ++t)
+                            if(t < L) A[pos + t] = KeyT(uint64_t(pl[c][2 * t]) | (uint64_t(pl[c][2 * t + 1]) << 32));
+                    }
                 }
-                if(L > 2 && L <= Q_LANE_GATHER) {
+                if(L > INL && L <= Q_LANE_GATHER) {
                     // short lists: every lane copies its own (a whole-warp copy per list costs more
                     // instructions than the list has elements)
-                    const uint64_t* src = f.locs + off[c];
+                    const uint64_t* src = f.locs + pl[c][5];
                     for(uint32_t t = 0; t < L; t += 4) {
                         uint64_t x0 = __ldg(src + t), x1 = 0, x2 = 0, x3 = 0;
                         if(t + 1 < L) x1 = __ldg(src + t + 1);
@@ -949,7 +959,7 @@ q_fused_warp_kernel(const CandParams p, const FusedParams f)
                     const int src = __ffs(int(big)) - 1;
                     big &= big - 1;
                     const uint32_t Ls = __shfl_sync(0xFFFFFFFFu, L, src);
-                    const uint64_t Os = __shfl_sync(0xFFFFFFFFu, off[c], src);
+                    const uint32_t Os = __shfl_sync(0xFFFFFFFFu, pl[c][5], src);
                     const uint32_t Ps = __shfl_sync(0xFFFFFFFFu, pos, src);
                     for(uint32_t t = lane; t < Ls; t += 32) A[Ps + t] = make_key<KeyT>(f.locs[Os + t], p.wbits);
                 }
@@ -1035,12 +1045,15 @@ q_spill_warp_kernel(const CandParams p, const SpillParams f)
             continue;
         }
         const uint32_t ns = uint32_t(s1 - s0);
-        uint32_t len[NCS];
-        uint64_t off[NCS], loc0[NCS], loc1[NCS];
+        constexpr uint32_t INL = sizeof(KeyT) == 4 ? TABLE_INLINE_32 : TABLE_INLINE_64;
+        uint32_t len[NCS], off[NCS];
+        uint32_t pl[NCS][6];
         uint32_t tot = 0;
 #pragma unroll
         for(int c = 0; c < NCS; ++c) {
-            len[c] = 0; off[c] = 0; loc0[c] = 0; loc1[c] = 0;
+            len[c] = 0; off[c] = 0;
+#pragma unroll
+            for(int w = 0; w < 6; ++w) pl[c][w] = 0;
             const uint32_t sl = uint32_t(c) * 32u + uint32_t(lane);
             const uint32_t key = sl < ns ? f.feat[s0 + sl] : EMPTY_KEY;
             if(key != EMPTY_KEY) {
@@ -1053,9 +1066,8 @@ q_spill_warp_kernel(const CandParams p, const SpillParams f)
                         const uint4* pay = reinterpret_cast<const uint4*>(line + 8 + 8 * t);
                         const uint4 q0 = __ldg(pay), q1 = __ldg(pay + 1);
                         len[c] = q0.x;
-                        off[c] = uint64_t(q0.z) | (uint64_t(q0.w) << 32);
-                        loc0[c] = uint64_t(q1.x) | (uint64_t(q1.y) << 32);
-                        loc1[c] = uint64_t(q1.z) | (uint64_t(q1.w) << 32);
+                        off[c] = q0.y;
+                        pl[c][0] = q0.z; pl[c][1] = q0.w; pl[c][2] = q1.x; pl[c][3] = q1.y; pl[c][4] = q1.z; pl[c][5] = q1.w;
                         break;
                     }
                     if(t == -1) break;
@@ -1082,9 +1094,13 @@ q_spill_warp_kernel(const CandParams p, const SpillParams f)
 #pragma unroll
         for(int c = 0; c < NCS; ++c) {
             const uint32_t L = len[c];
-            if(L >= 1) A[pos] = make_key<KeyT>(loc0[c], p.wbits);
-            if(L >= 2) A[pos + 1] = make_key<KeyT>(loc1[c], p.wbits);
-            for(uint32_t t = 2; t < L; ++t) A[pos + t] = make_key<KeyT>(f.locs[off[c] + t], p.wbits);
+            if(L <= INL) {
+#pragma unroll
+                for(uint32_t t = 0; t < INL; ++t)
+                    if(t < L) A[pos + t] = sizeof(KeyT) == 4 ? KeyT(pl[c][t]) : KeyT(uint64_t(pl[c][2 * t]) | (uint64_t(pl[c][2 * t + 1]) << 32));
+            } else {
+                for(uint32_t t = 0; t < L; ++t) A[pos + t] = make_key<KeyT>(f.locs[off[c] + t], p.wbits);
+            }
             pos += L;
         }
         __syncwarp();
