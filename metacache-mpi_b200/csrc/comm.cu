@@ -134,6 +134,15 @@ int comm_allgatherv_inplace(mcg_comm* m, void* buf, const uint64_t* off, const u
 {
     if(m == nullptr || m->nranks == 1) return MCG_OK;
     char* b = static_cast<char*>(buf);
+    // equal blocks back to back (equal slices of equal-length reads): NCCL's own in-place all-gather, which on an
+    // NVSwitch system multicasts every block once (NVLS) instead of sending it P-1 times
+    static const bool no_ag = getenv("MCG_NO_NCCL_ALLGATHER") != nullptr;
+    bool uniform = !no_ag && len[0] > 0;
+    for(int q = 0; q < m->nranks && uniform; ++q) uniform = len[q] == len[0] && off[q] == uint64_t(q) * len[0];
+    if(uniform) {
+        MCG_NCCL(g_nccl.AllGather(b + off[m->rank], b, len[0], ncclUint8, m->nccl, st));
+        return MCG_OK;
+    }
     MCG_NCCL(g_nccl.GroupStart());
     for(int q = 0; q < m->nranks; ++q) {
         if(q == m->rank) continue;

@@ -350,7 +350,15 @@ __device__ __forceinline__ uint32_t hits_ending_at(const KeyT* A, uint32_t i, ui
     const KeyT wmask = (KeyT(1) << wbits) - 1;
     const KeyT win = key & wmask;
     const KeyT lowkey = (key & ~wmask) | (win >= KeyT(numwin - 1) ? win - KeyT(numwin - 1) : KeyT(0));
-    uint32_t lo = 0, hi = i;
+    // most matches of a read against a large database are chance hits on targets of their own (runs of one element):
+    // look at the neighbour first, then gallop backwards, then bisect what is left
+    if(i == 0 || A[i - 1] < lowkey) return 1u;
+    uint32_t lo = 0, hi = i - 1, step = 1;                 // A[hi] >= lowkey
+    while(hi >= step) {
+        if(A[hi - step] < lowkey) { lo = hi - step + 1; break; }
+        hi -= step;
+        step <<= 1;
+    }
     while(lo < hi) {
         const uint32_t mid = (lo + hi) >> 1;
         if(A[mid] < lowkey) lo = mid + 1; else hi = mid;
