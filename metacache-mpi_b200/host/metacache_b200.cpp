@@ -4,12 +4,15 @@
 //
 //   metacache_b200 build <db> <fasta files / directories ...> [-gpus P] [-kmerlen 16]
 //       [-sketchlen 16] [-winlen 128] [-winstride winlen-k+1] [-max-locations-per-feature 254]
-//       [-remove-overpopulated-features] [-taxonomy dir]                  (mode_build.cpp:93-138)
+//       [-remove-overpopulated-features] [-taxonomy dir] [-taxpostmap file]  (mode_build.cpp:93-138; targets without a
+//       taxon are looked up in <dir>/*.accession2taxid, mode_build.cpp:493-522)
 //   metacache_b200 query <db> <r1.fq> <r2.fq> -pairfiles [-gpus P] [-lowest rank] [-highest rank]
 //       [-hitmin n] [-hitdiff f] [-maxcand n] [-insertsize n] [-winlen n] [-winstride n]
 //       [-sketchlen n] [-out file] [-tophits] [-queryids] [-taxids|-taxids-only] [-lineage]
 //       [-mapped-only|-nomap] [-no-summary] [-no-query-params] [-abundances [file]] [-abundance-per rank]
 //       [-hits-per-seq [file]] [-reference-compat]                       (query_options.cpp)
+//   metacache_b200 merge <result files ...> -taxonomy dir [-lowest rank] [-highest rank] [-hitmin n] [-hitdiff f]
+//       [-maxcand n] [-out file] [-tophits] [-queryids] ...              (mode_merge.cpp, docs/merge.txt)
 //
 // `-threads T` and `-query-limit n` are accepted and have no effect: in the reference they only set the size of the
 // blocks its workers take (querying.h:764-765, 1321); every read is classified either way (checked with the reference:
@@ -497,6 +500,63 @@ void list_files(const std::string& path, std::vector<std::string>& out)
     }
 }
 
+// Targets whose header and mapping files gave no parent taxon are looked up in NCBI accession -> taxon tables after all
+// sequences are in.  Behaviour to match (mode_build.cpp:493-522 with :249-311, args_handling.cpp:121-145,
+// sketch_database.h:632-639): files in this order: -taxpostmap <file>, then nucl_gb / nucl_wgs / nucl_est / nucl_gss
+// .accession2taxid of the taxonomy directory, then every other *.accession2taxid found there; one header line, then rows
+// "accession accession.version taxid gi"; a row names a target by (1) accession.version == target name, (2) the first
+// target name greater than the accession that starts with it, (3) gi == target name; the first row that names a still
+// unranked target sets its parent.
+void rank_unranked_targets(Taxonomy& tax, uint32_t ntargets, std::string taxdir, const std::string& postmap)
+{
+    std::map<std::string, int64_t> by_name;            // target name -> taxon id -(t)-1
+    std::set<int64_t> unranked;
+    for(uint32_t t = 0; t < ntargets; ++t) {
+        const Taxon& x = tax.taxa[-int64_t(t) - 1];
+        by_name.emplace(x.name, x.id);
+        if(x.parent == 0) unranked.insert(x.id);
+    }
+    if(!unranked.empty()) {
+        std::cout << unranked.size() << " targets are unranked." << std::endl;
+        if(!taxdir.empty() && taxdir.back() != '/') taxdir += '/';
+        std::vector<std::string> files;
+        if(!postmap.empty()) files.push_back(postmap);
+        for(const char* f : {"nucl_gb", "nucl_wgs", "nucl_est", "nucl_gss"}) files.push_back(taxdir + f + ".accession2taxid");
+        if(!taxdir.empty()) {
+            std::vector<std::string> more;
+            list_files(taxdir.substr(0, taxdir.size() - 1), more);
+            std::sort(more.begin(), more.end());
+            for(const auto& f : more)
+                if(f.find(".accession2taxid") != std::string::npos && std::find(files.begin(), files.end(), f) == files.end()) files.push_back(f);
+        }
+        for(const auto& file : files) {
+            std::ifstream is(file);
+            if(!is.good()) continue;
+            std::cout << "Try to map sequences to taxa using '" << file << "'" << std::endl;
+            std::string acc, accver, gi;
+            uint64_t taxid = 0;
+            std::getline(is, acc);                                // header line
+            while(is >> acc >> accver >> taxid >> gi) {
+                auto hit = by_name.find(accver);
+                if(hit == by_name.end() && !acc.empty()) {
+                    auto near = by_name.upper_bound(acc);
+                    if(near != by_name.end() && near->first.compare(0, acc.size(), acc) == 0) hit = near;
+                    else hit = by_name.find(gi);
+                }
+                if(hit == by_name.end()) continue;
+                auto u = unranked.find(hit->second);
+                if(u == unranked.end()) continue;
+                tax.taxa[hit->second].parent = int64_t(taxid);
+                unranked.erase(u);
+                if(unranked.empty()) break;
+            }
+            if(unranked.empty()) break;
+        }
+    }
+    if(unranked.empty()) std::cout << "All targets are ranked." << std::endl;
+    else std::cout << unranked.size() << " targets remain unranked." << std::endl;
+}
+
 // ------------------------------------------------------------------------------- shard files
 struct DbMeta {
     mcg_sketch_cfg tcfg{16, 16, 128, 113};
@@ -830,6 +890,8 @@ int mode_build(const Args& a)
         }
     }
     lap("parse sequence files");
+    rank_unranked_targets(m.tax, ntargets, taxdir, a.get({"taxpostmap", "taxonomy-postmap"}, ""));
+    lap("rank unranked targets");
     ensure_dbs();
     lap("wait for CUDA start-up");
     for_each_shard_parallel(P, [&](int r) { flush(r); });
@@ -1364,6 +1426,231 @@ int mode_query(const Args& a)
     return 0;
 }
 
+// ------------------------------------------------------------------------------- merge
+// `merge <result files ...> -taxonomy <dir>`: classifies reads from the top-hit lists of several independent query
+// runs (docs/merge.txt, mode_merge.cpp).  Behaviour: result files in sorted order; each must have been written with
+// -tophits -queryids at -lowest species or above; per query the `taxid:hits` entries of every file are inserted, file
+// after file, into one candidate list (candidates.h:236-285, merge below -lowest >= species), then classify + statistics
+// as in a query.  Here the files play the role of shards: their lists go to mcg_merge_classify in file order.
+int mode_merge(const Args& a)
+{
+    if(a.pos.size() < 1) die("usage: metacache_b200 merge <result files / directories ...> -taxonomy <dir> [options]");
+    std::vector<std::string> files;
+    for(const auto& p : a.pos) list_files(p, files);
+    std::sort(files.begin(), files.end());
+    const std::string taxdir = a.get({"taxonomy"}, "");
+    if(taxdir.empty()) { std::cout << "No taxonomy specified. Unable to perform merge." << std::endl; return 0; }
+    if(files.size() < 2) { std::cout << "Please provide at least two files to be merged!" << std::endl; return 0; }
+    start_gpu_init(1);
+    Taxonomy tax;
+    tax.load(taxdir);
+    TaxTables tt;
+    tt.build(tax, 0);
+    std::cout << "Taxonomy applied to database." << std::endl;
+    mcg_query_opts q{};
+    q.sketchlen = 16; q.winlen = 128; q.winstride = 113;
+    q.lowest = 4; q.highest = 19;                                               // mode_merge.cpp:83-86: species at least
+    { const std::string s = a.get({"lowest"}, ""); if(!s.empty()) { int r = rank_from_name(s); if(r < 21 && r > 4) q.lowest = r; } }
+    { const std::string s = a.get({"highest"}, ""); if(!s.empty()) { int r = rank_from_name(s); if(r <= 20) q.highest = r; } }
+    if(q.lowest > q.highest) q.lowest = q.highest;
+    q.hitmin = int32_t(a.geti({"hitmin"}, 0));
+    if(q.hitmin < 1) q.hitmin = 5;                                              // mode_merge.cpp:81-82
+    {
+        float f = float(std::atof(a.get({"hitdiff"}, "1").c_str()));
+        if(f > 1) f = float(double(f) * 0.01);
+        q.hitdiff = f;
+    }
+    q.maxcand = int32_t(a.geti({"max-cand", "maxcand", "max_cand", "max-candidates", "maxcandidates"}, 2));
+    if(q.maxcand < 1) q.maxcand = 2;                                            // mode_merge.cpp:284-286: "else default to 2"
+    if(q.maxcand > MCG_MAX_CAND) q.maxcand = MCG_MAX_CAND;
+    const int K = q.maxcand;
+    OutOpt o;
+    o.queryids = a.has({"queryids", "query-ids", "queryid", "query-id"});
+    o.tophits = a.has({"tophits", "top-hits"});
+    o.lineage = a.has({"lineage"});
+    o.show_ranks = !a.has({"omit-ranks", "omitranks"});
+    if(a.has({"taxidsonly", "taxids-only", "taxidonly", "taxid-only"})) o.mode = 1;
+    else if(a.has({"taxids", "taxid"})) o.mode = 2;
+    if(a.has({"nomap", "no-map"})) o.map = 2; else if(a.has({"mapped-only", "mappedonly"})) o.map = 1;
+    o.summary = !a.has({"no-summary", "nosummary"});
+    o.params = !a.has({"no-query-params", "noqueryparams"});
+    o.lowest = q.lowest; o.highest = q.highest;
+
+    // ---- parse the result files
+    struct Source { std::string text; size_t begin = 0, nq = 0; int tophits_col = 0; };
+    std::vector<Source> src(files.size());
+    size_t n = 0;
+    for(size_t f = 0; f < files.size(); ++f) {
+        Source& S = src[f];
+        if(!read_text_file(files[f], S.text)) die("could not open file " + files[f]);
+        size_t p = 0;
+        bool have_rank = false, have_layout = false;
+        while(p < S.text.size() && S.text[p] == '#') {
+            size_t e = S.text.find('\n', p);
+            if(e == std::string::npos) e = S.text.size();
+            const std::string line = S.text.substr(p, e - p);
+            if(!have_rank && line.compare(0, 16, "# Classification") == 0) {
+                if(line.find("sequence") != std::string::npos) die("cannot merge results on sequence level (" + files[f] + ")");
+                have_rank = true;
+            }
+            if(line.compare(0, 15, "# TABLE_LAYOUT:") == 0) {
+                std::vector<std::string> cols;
+                size_t c0 = 15;
+                while(c0 <= line.size()) {
+                    size_t c1 = line.find('|', c0);
+                    if(c1 == std::string::npos) c1 = line.size();
+                    cols.push_back(trimmed(line.substr(c0, c1 - c0)));
+                    c0 = c1 + 1;
+                }
+                if(cols.empty() || cols[0] != "query_id") die("no query_id in file " + files[f]);
+                for(size_t c = 1; c < cols.size(); ++c) if(cols[c] == "top_hits") { S.tophits_col = int(c); break; }
+                have_layout = true;
+            }
+            p = e + 1;
+        }
+        if(!have_rank) die("classificaion ranks not found in file " + files[f]);
+        if(!have_layout) die("TABLE_LAYOUT not found in file " + files[f]);
+        if(S.tophits_col < 1) die("no top_hits in file " + files[f]);
+        S.begin = p;
+        for(size_t i = p; i < S.text.size();) {
+            if(S.text[i] != '#') ++S.nq;
+            const size_t e = S.text.find('\n', i);
+            if(e == std::string::npos) break;
+            i = e + 1;
+        }
+        n = std::max(n, S.nq);
+    }
+    const size_t F = files.size();
+    std::vector<std::string> headers(n);
+    std::vector<int32_t> ctax(F * n * size_t(K), -1), cn(F * n, 0);
+    std::vector<uint32_t> chits(F * n * size_t(K), 0);
+    for(size_t f = 0; f < F; ++f) {
+        const Source& S = src[f];
+        size_t p = S.begin;
+        while(p < S.text.size()) {
+            size_t e = S.text.find('\n', p);
+            if(e == std::string::npos) e = S.text.size();
+            if(S.text[p] != '#' && e > p) {
+                // columns are separated by "\t|\t"
+                std::vector<std::pair<size_t, size_t>> col;
+                size_t c0 = p;
+                while(c0 <= e) {
+                    size_t c1 = S.text.find("\t|\t", c0);
+                    if(c1 == std::string::npos || c1 > e) c1 = e;
+                    col.emplace_back(c0, c1);
+                    c0 = c1 + 3;
+                }
+                size_t qid = size_t(std::atoll(S.text.c_str() + col[0].first));
+                if(qid > 0) --qid;
+                if(qid < n && int(col.size()) > S.tophits_col) {
+                    if(headers[qid].empty() && col.size() > 1) {
+                        std::string h = S.text.substr(col[1].first, col[1].second - col[1].first);
+                        const size_t sp = h.find_first_of(" \t");
+                        headers[qid] = sp == std::string::npos ? h : h.substr(0, sp);
+                    }
+                    size_t t = col[size_t(S.tophits_col)].first;
+                    const size_t te = col[size_t(S.tophits_col)].second;
+                    int32_t& cnt = cn[f * n + qid];
+                    while(t < te && cnt < K) {
+                        const int64_t taxid = std::atoll(S.text.c_str() + t);
+                        const size_t colon = S.text.find(':', t);
+                        if(colon == std::string::npos || colon >= te) break;
+                        const uint32_t hits = uint32_t(std::atoll(S.text.c_str() + colon + 1));
+                        auto it = tt.index_of.find(taxid);
+                        if(it != tt.index_of.end()) {
+                            ctax[(f * n + qid) * size_t(K) + size_t(cnt)] = it->second;
+                            chits[(f * n + qid) * size_t(K) + size_t(cnt)] = hits;
+                            ++cnt;
+                        } else {
+                            std::cerr << "taxid not found" << std::endl;
+                        }
+                        size_t comma = S.text.find(',', colon);
+                        if(comma == std::string::npos || comma >= te) break;
+                        t = comma + 1;
+                    }
+                }
+            }
+            p = e + 1;
+        }
+    }
+    // ---- merge + decision on the device
+    wait_gpu_init();
+    mcg_ctx* c = ctx_for_shard(0);
+    check(mcg_tax_upload(c, tt.lineage.data(), tt.rank.data(), int64_t(tt.rank.size()), 0), "mcg_tax_upload");
+    std::vector<int32_t> mtax(n * size_t(K)), mn(n), best(n), brank(n);
+    std::vector<uint32_t> mhits(n * size_t(K));
+    uint64_t stats[22] = {0};
+    const double t0 = now();
+    check(mcg_merge_classify(c, &q, ctax.data(), chits.data(), cn.data(), int32_t(F), int64_t(n), mtax.data(), mhits.data(), mn.data(),
+                             best.data(), brank.data(), stats), "mcg_merge_classify");
+    const double t1 = now();
+    // ---- output (mode_merge.cpp:330-375, classification.cpp:889-925)
+    std::ofstream fout;
+    const std::string outname = a.get({"out"}, "");
+    if(!outname.empty()) {
+        fout.open(outname);
+        if(!fout.good()) die("Could not write to file " + outname);
+        std::cout << "Per-Read mappings will be written to file: " << outname << std::endl;
+    }
+    std::ostream& os = outname.empty() ? std::cout : fout;
+    const std::string& cm = o.comment;
+    if(o.params) {
+        if(o.map != 2) {
+            os << cm << "Reporting per-read mappings (non-mapping lines start with '" << cm << "').\n";
+            os << cm << (o.lineage ? "The complete lineage will be reported starting with the lowest match.\n"
+                                   : "Only the lowest matching rank will be reported.\n");
+        } else {
+            os << cm << "Per-Read mappings will not be shown.\n";
+        }
+        os << cm << "Classification will be constrained to ranks from '" << RANK_NAMES[q.lowest] << "' to '" << RANK_NAMES[q.highest] << "'.\n";
+        os << cm << "Classification hit threshold is " << q.hitmin << " per query\n";
+        os << cm << "At maximum " << q.maxcand << " classification candidates will be considered per query.\n";
+        os << cm << "Using 1 threads\n";
+    }
+    os << cm << "Merging " << F << " files:\n";
+    for(const auto& f : files) os << cm << f << '\n';
+    if(o.map != 2) {
+        StrOut ls;
+        for(size_t i = 0; i < n; ++i) {
+            if(o.map == 1 && best[i] < 0) continue;
+            if(o.queryids) ls << (i + 1) << o.col;
+            ls << headers[i] << o.col;
+            if(o.tophits) {
+                for(int k = 0; k < mn[i] && mhits[i * size_t(K) + size_t(k)] > 0; ++k) {
+                    if(k > 0) ls << ',';
+                    ls << tt.taxid[size_t(mtax[i * size_t(K) + size_t(k)])] << ':' << mhits[i * size_t(K) + size_t(k)];
+                }
+                ls << o.col;
+            }
+            show_classification(ls, o, tt, best[i]);
+            ls << '\n';
+        }
+        os.write(ls.s.data(), std::streamsize(ls.s.size()));
+    }
+    if(o.summary) {
+        const uint64_t total = stats[20] + stats[21];
+        const double minutes = (t1 - t0) / 60.0;
+        os << cm << "queries: " << total << '\n' << cm << "time:    " << int64_t((t1 - t0) * 1000) << " ms\n"
+           << cm << "speed:   " << (double(total) / minutes) << " queries/min\n";
+        if(total > 0) {
+            if(stats[20] < 1) os << "None of the input sequences could be classified.\n";
+            else {
+                if(stats[21] > 0) os << cm << "unclassified: " << (100 * (double(stats[21]) / double(total))) << "% (" << stats[21] << ")\n";
+                os << cm << "classified:\n";
+                const int ranks[] = {0, 3, 4, 6, 10, 12, 14, 16, 18, 19, 20};
+                for(int r : ranks) {
+                    if(stats[r] > 0) {
+                        std::string rn = RANK_NAMES[r];
+                        rn.resize(11, ' ');
+                        os << cm << "  " << rn << (100 * (double(stats[r]) / double(total))) << "% (" << stats[r] << ")\n";
+                    }
+                }
+            }
+        }
+    }
+    return 0;
+}
+
 // ------------------------------------------------------------------------------- host-only self tests
 // (no CUDA call: they run in the CPU test suite)
 
@@ -1491,10 +1778,11 @@ int main(int argc, char** argv)
     int rc = 1;
     if(mode == "build") rc = mode_build(a);
     else if(mode == "query") rc = mode_query(a);
+    else if(mode == "merge") rc = mode_merge(a);
     else if(mode == "selftest-shard") return mode_selftest_shard(a);
     else if(mode == "selftest-abundance") return mode_selftest_abundance(a);
     else if(mode == "shards-equal") return mode_shards_equal(a);
-    else die("unknown mode '" + mode + "' (build and query are implemented, like in the reference: README.md:37)");
+    else die("unknown mode '" + mode + "' (build, query and merge are implemented)");
     wait_gpu_init();
     total("whole run before teardown");
     std::cout.flush();

@@ -46,6 +46,26 @@ if __name__ == "__main__":
                 f.write("\n".join(t.stable_lines(os.path.join(d, "res.txt"))) + "\n")
             print("wrote", name)
     with tempfile.TemporaryDirectory() as d:
+        # merge mode: the reference's own query results of two half databases, merged by the reference
+        t.make_split_files(d)
+        for nm in ("A", "B"):
+            t.run([sys.executable, t.SHIM, "-np", "2", "--", t.REF, "build", "db" + nm, "g" + nm, "-taxonomy", "tax"], d)
+            t.run([sys.executable, t.SHIM, "-np", "2", "--", t.REF, "query", "db" + nm, "r1.fq", "r2.fq", "-pairfiles"] + t.MERGE_FLAGS +
+                  ["-threads", "1", "-query-limit", "300", "-out", "res%s.txt" % nm], d)
+        t.run([sys.executable, t.SHIM, "-np", "1", "--", t.REF, "merge", "resA.txt", "resB.txt", "-taxonomy", "tax"] + t.MERGE_FLAGS +
+              ["-out", "merged.txt"], d)
+        with open(os.path.join(ROOT, "tests", "golden", "cli_merge_two_databases.txt"), "w") as f:
+            f.write("\n".join(t.stable_lines(os.path.join(d, "merged.txt"))) + "\n")
+        print("wrote cli_merge_two_databases.txt")
+    with tempfile.TemporaryDirectory() as d:
+        t.make_unranked_files(d)
+        t.run([sys.executable, t.SHIM, "-np", "2", "--", t.REF, "build", "rdb", "genomes", "-taxonomy", "tax"], d)
+        t.run([sys.executable, t.SHIM, "-np", "2", "--", t.REF, "query", "rdb", "r1.fq", "r2.fq"] + t.QFLAGS +
+              ["-threads", "1", "-query-limit", "300", "-out", "res.txt"], d)
+        with open(os.path.join(ROOT, "tests", "golden", "cli_np2_rank_unranked.txt"), "w") as f:
+            f.write("\n".join(t.stable_lines(os.path.join(d, "res.txt"))) + "\n")
+        print("wrote cli_np2_rank_unranked.txt")
+    with tempfile.TemporaryDirectory() as d:
         t.make_files(d)
         t.run([sys.executable, t.SHIM, "-np", "2", "--", t.REF, "build", "rdb", "genomes", "-taxonomy", "tax"], d)
         for name, flags in CASES.items():

@@ -251,3 +251,85 @@ def test_cli_unlimited_maxcand(tmp_path):
         run([sys.executable, SHIM, "-np", "2", "--", REF, "query", "rdb", "r1.fq", "r2.fq"] + flags +
             ["-threads", "1", "-query-limit", "300", "-out", "res_ref.txt"], d)
         assert mine == stable_lines(os.path.join(d, "res_ref.txt"))
+
+
+def make_unranked_files(d):
+    """no genome carries a taxid in its header; NCBI-style accession -> taxon tables in the taxonomy directory name
+    four of them by accession.version, one by accession only (another version), one not at all"""
+    make_files(d, no_taxid=range(6))
+    with open(os.path.join(d, "tax", "nucl_gb.accession2taxid"), "w") as f:
+        f.write("accession\taccession.version\ttaxid\tgi\n")
+        f.write("XX000009\tXX000009.1\t100005\t77\n")
+        for g in range(4):
+            f.write("SYN%06d\tSYN%06d.1\t%d\t%d\n" % (g, g, 100000 + g, 1000 + g))
+    with open(os.path.join(d, "tax", "zz_more.accession2taxid"), "w") as f:
+        f.write("accession\taccession.version\ttaxid\tgi\n")
+        f.write("SYN000004\tSYN000004.7\t100004\t1004\n")
+
+
+def test_cli_rank_unranked_targets(tmp_path):
+    """targets without a taxon in their header get their parent from *.accession2taxid files of the taxonomy directory
+    (mode_build.cpp:493-522): same shard files (taxon records) and same classification as the reference"""
+    d = str(tmp_path)
+    make_unranked_files(d)
+    out = run([EXE, "build", "gdb", "genomes", "-taxonomy", "tax", "-gpus", "2"], d)
+    assert "6 targets are unranked." in out and "1 targets remain unranked." in out
+    run([EXE, "query", "gdb", "r1.fq", "r2.fq"] + QFLAGS + ["-out", "res_gpu.txt"], d)
+    mine = stable_lines(os.path.join(d, "res_gpu.txt"))
+    golden = os.path.join(ROOT, "tests", "golden", "cli_np2_rank_unranked.txt")
+    if os.path.exists(golden):
+        assert mine == open(golden).read().splitlines()
+    if not os.path.exists(REF):
+        assert os.path.exists(golden), "neither oracle/_ref nor the golden output is available"
+        return
+    run([sys.executable, SHIM, "-np", "2", "--", REF, "build", "rdb", "genomes", "-taxonomy", "tax"], d)
+    run([sys.executable, SHIM, "-np", "2", "--", REF, "query", "rdb", "r1.fq", "r2.fq"] + QFLAGS +
+        ["-threads", "1", "-query-limit", "300", "-out", "res_ref.txt"], d)
+    assert mine == stable_lines(os.path.join(d, "res_ref.txt"))
+    for r in range(2):
+        assert "shards equal" in run([EXE, "shards-equal", "gdb.db_%d" % r, "rdb.db_%d" % r], d)
+
+
+MERGE_FLAGS = ["-lowest", "species", "-maxcand", "4", "-hitmin", "4", "-hitdiff", "80", "-tophits", "-queryids"]
+
+
+def make_split_files(d):
+    """the six genomes as two independent databases (A: genomes 0-2, B: genomes 3-5), one read set"""
+    G, L = 6, 30000
+    genomes = synth.make_genomes(G, L)
+    ids, par, rk, species = synth.make_taxonomy(G)
+    for name, gs in (("gA", range(0, 3)), ("gB", range(3, 6))):
+        os.makedirs(os.path.join(d, name), exist_ok=True)
+        for g in gs:
+            synth.write_fasta(os.path.join(d, name, "g%05d.fna" % g), "SYN%06d.1 taxid=%d synthetic genome %d" % (g, species[g], g), genomes[g])
+    synth.write_taxonomy_files(os.path.join(d, "tax"), ids, par, rk)
+    b1, o1, b2, o2, t = synth.make_read_pairs(genomes, 300, seed=5)
+    synth.write_fastq_pair(os.path.join(d, "r1.fq"), os.path.join(d, "r2.fq"), b1, o1, b2, o2, t)
+
+
+def test_cli_merge_mode(tmp_path):
+    """`merge` (mode_merge.cpp, docs/merge.txt): the top-hit lists of two independent query runs (two databases holding
+    half of the genomes each) are merged per read and classified; output identical to the reference's merge of the same
+    result files"""
+    d = str(tmp_path)
+    make_split_files(d)
+    for nm in ("A", "B"):
+        run([EXE, "build", "db" + nm, "g" + nm, "-taxonomy", "tax", "-gpus", "2"], d)
+        run([EXE, "query", "db" + nm, "r1.fq", "r2.fq", "-pairfiles"] + MERGE_FLAGS + ["-out", "res%s.txt" % nm], d)
+    run([EXE, "merge", "resA.txt", "resB.txt", "-taxonomy", "tax"] + MERGE_FLAGS + ["-out", "merged_gpu.txt"], d)
+    mine = stable_lines(os.path.join(d, "merged_gpu.txt"))
+    golden = os.path.join(ROOT, "tests", "golden", "cli_merge_two_databases.txt")
+    if os.path.exists(golden):
+        assert mine == open(golden).read().splitlines()
+    # merging finds the genomes of both halves: more reads classified at species level than either run alone
+    def species_count(path):
+        return [int(l[l.rindex("(") + 1:l.rindex(")")]) for l in open(path).read().splitlines() if l.startswith("#   species")][0]
+    assert species_count(os.path.join(d, "merged_gpu.txt")) > max(species_count(os.path.join(d, "resA.txt")), species_count(os.path.join(d, "resB.txt")))
+    if os.path.exists(REF):
+        run([sys.executable, SHIM, "-np", "1", "--", REF, "merge", "resA.txt", "resB.txt", "-taxonomy", "tax"] + MERGE_FLAGS +
+            ["-out", "merged_ref.txt"], d)
+        assert mine == stable_lines(os.path.join(d, "merged_ref.txt"))
+        # plain output (no ids, no top hits), reference defaults for everything but the rank
+        run([EXE, "merge", "resA.txt", "resB.txt", "-taxonomy", "tax", "-out", "m2_gpu.txt"], d)
+        run([sys.executable, SHIM, "-np", "1", "--", REF, "merge", "resA.txt", "resB.txt", "-taxonomy", "tax", "-out", "m2_ref.txt"], d)
+        assert stable_lines(os.path.join(d, "m2_gpu.txt")) == stable_lines(os.path.join(d, "m2_ref.txt"))
