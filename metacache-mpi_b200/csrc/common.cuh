@@ -218,14 +218,17 @@ __device__ __forceinline__ uint32_t table_bucket(uint32_t key, const TableGeom& 
     return uint32_t((uint64_t(rank) * g.scale) >> 32);
 }
 
-// slot of `key` in a bucket whose key sector starts with k4: 0..2, -1 = absent but the bucket
-// has a free slot (the key is not in the table), -2 = absent and the bucket is full (next bucket)
+// slot of `key` in a bucket whose key sector starts with k4: 0..2, -1 = the key is not in the table, -2 = look
+// in the next bucket.  Slots are handed out in key order, so the table as a whole is sorted: a walk that starts
+// at the key's home bucket goes on only past a FULL bucket whose largest key (its last slot) is smaller than the
+// key; a free slot, or a larger key in the bucket, proves absence -- most probes of absent keys that land in a full
+// bucket end there instead of costing another dependent line fill.
 __device__ __forceinline__ int table_match(const uint4& k4, uint32_t key)
 {
     if(k4.x == key) return 0;
     if(k4.y == key) return 1;
     if(k4.z == key) return 2;
-    return (k4.x == TABLE_EMPTY || k4.y == TABLE_EMPTY || k4.z == TABLE_EMPTY) ? -1 : -2;
+    return (k4.z != TABLE_EMPTY && k4.z < key) ? -2 : -1;
 }
 
 __host__ __device__ __forceinline__ int64_t num_windows(int64_t len, int64_t winlen, int64_t stride)
