@@ -1743,11 +1743,21 @@ static int stage_reads(mcg_ctx* c, const char* reads1, const int64_t* offs1, con
 }
 
 // ------------------------------------------------------------------ sharded query (all ranks, one call)
-// window totals of the np parts a slice of n reads is cut into: part j = reads [n*j/np, n*(j+1)/np)
+// A slice of n reads is cut into np parts at part_cut(n, np, 0..np).  A call costs the PCIe copy of its first part
+// (nothing to overlap it with) plus the kernels of its last part: with three or more parts the first and the last
+// are half as long as the ones in between.
+__host__ __device__ __forceinline__ int64_t part_cut(int64_t n, int np, int j)
+{
+    if(j <= 0) return 0;
+    if(j >= np) return n;
+    return np >= 3 ? n * (2 * j - 1) / (2 * (np - 1)) : n * j / np;
+}
+
+// window totals of the parts of a slice
 __global__ void q_plan_kernel(const uint32_t* W, int64_t n, int np, uint64_t* out)
 {
     const int j = threadIdx.x;
-    if(j < np) out[1 + j] = uint64_t(W[n * (j + 1) / np] - W[n * j / np]);
+    if(j < np) out[1 + j] = uint64_t(W[part_cut(n, np, j + 1)] - W[part_cut(n, np, j)]);
     if(j == 0) out[0] = uint64_t(n);
 }
 
@@ -1771,7 +1781,7 @@ static int qs_plan(mcg_db* db, mcg_comm* comm, const mcg_query_opts* o, const in
     if(P == 1) {
         pl->np = np_want;
         pl->n.assign(size_t(np_want), 0); pl->w.assign(size_t(np_want), 0);
-        for(int j = 0; j < np_want; ++j) pl->n[size_t(j)] = uint64_t(n_loc * (j + 1) / np_want - n_loc * j / np_want);
+        for(int j = 0; j < np_want; ++j) pl->n[size_t(j)] = uint64_t(part_cut(n_loc, np_want, j + 1) - part_cut(n_loc, np_want, j));
         return MCG_OK;                                        // w stays unknown (0): callers use bounds
     }
     const int NP = np_want;
@@ -1800,7 +1810,7 @@ static int qs_plan(mcg_db* db, mcg_comm* comm, const mcg_query_opts* o, const in
         const int64_t nr = int64_t(a[0]);
         for(int j = 0; j < NP; ++j) {
             const int jj = collapse ? 0 : j;
-            pl->n[size_t(jj) * size_t(P) + size_t(r)] += uint64_t(nr * (j + 1) / NP - nr * j / NP);
+            pl->n[size_t(jj) * size_t(P) + size_t(r)] += uint64_t(part_cut(nr, NP, j + 1) - part_cut(nr, NP, j));
             pl->w[size_t(jj) * size_t(P) + size_t(r)] += a[1 + j];
         }
     }
@@ -2205,8 +2215,8 @@ int mcg_query_batch_sharded(mcg_db* db, mcg_comm* comm, const mcg_query_opts* o,
     const int K = o->maxcand;
     static const int64_t sub_reads = [] { const char* e = getenv("MCG_QUERY_SUB"); const int64_t v = e ? atoll(e) : 262144; return v < 1 ? int64_t(1) : v; }();
     // parts per call with P > 1: the slice of a rank is 1/P of the batch, its PCIe copy is short; every part costs
-    // launch tails and one NCCL group per exchange, so two parts (copy of one behind the kernels of the other) do
-    static const int np_env = getenv("MCG_SHARD_PARTS") ? atoi(getenv("MCG_SHARD_PARTS")) : 2;
+    // launch tails and one NCCL group per exchange: three parts (1/4, 1/2, 1/4 of the slice)
+    static const int np_env = getenv("MCG_SHARD_PARTS") ? atoi(getenv("MCG_SHARD_PARTS")) : 3;
     const bool paired = reads2 != nullptr;
     // the offsets of the whole slice go to the device first (the plan needs them), the bases follow part by part
     static const int64_t zero_off[1] = {0};
@@ -2219,7 +2229,7 @@ int mcg_query_batch_sharded(mcg_db* db, mcg_comm* comm, const mcg_query_opts* o,
     MCG_CUDA(cudaStreamWaitEvent(c->s_d2h, c->ev_misc, 0));
     MCG_CUDA(cudaMemcpyAsync(do1, offs1, size_t(n + 1) * 8, cudaMemcpyHostToDevice, c->stream));
     if(paired) MCG_CUDA(cudaMemcpyAsync(do2, offs2, size_t(n + 1) * 8, cudaMemcpyHostToDevice, c->stream));
-    int np_want = P == 1 ? int(std::min<int64_t>(QS_MAX_PARTS, std::max<int64_t>(1, (n + sub_reads - 1) / sub_reads)))
+    int np_want = P == 1 ? int(std::min<int64_t>(QS_MAX_PARTS, n >= 2 * sub_reads ? (n + sub_reads - 1) / sub_reads + 1 : std::max<int64_t>(1, (n + sub_reads - 1) / sub_reads)))
                          : std::max(1, std::min(np_env, QS_MAX_PARTS));
     ShardPlan pl;
     MCG_TRY(qs_plan(db, comm, o, do1, paired ? do2 : nullptr, n, np_want, &pl));
