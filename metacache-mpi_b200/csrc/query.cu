@@ -441,6 +441,31 @@ __device__ __forceinline__ void wsort64(KeyT& a, KeyT& b, int lane)
     }
 }
 
+// 96 keys (element e = 32 * i + lane in a, b, c): the 128-key network with its last quarter known to be +infinity --
+// the merge's flip step pairs the first quarter with infinity (no-op), the 32-distance step of the upper half too
+template<class KeyT>
+__device__ __forceinline__ void wsort96(KeyT& a, KeyT& b, KeyT& c, int lane)
+{
+    wsort64(a, b, lane);
+    c = wsort32(c, lane);
+    {
+        const KeyT oc = __shfl_sync(0xFFFFFFFFu, c, 31 - lane), ob = __shfl_sync(0xFFFFFFFFu, b, 31 - lane);
+        b = min(b, oc);
+        c = max(c, ob);
+    }
+    {
+        const KeyT lo = min(a, b), hi = max(a, b);
+        a = lo; b = hi;
+    }
+#pragma unroll
+    for(int j = 16; j > 0; j >>= 1) {
+        const KeyT oa = __shfl_xor_sync(0xFFFFFFFFu, a, j), ob = __shfl_xor_sync(0xFFFFFFFFu, b, j), oc = __shfl_xor_sync(0xFFFFFFFFu, c, j);
+        a = (lane & j) ? max(a, oa) : min(a, oa);
+        b = (lane & j) ? max(b, ob) : min(b, ob);
+        c = (lane & j) ? max(c, oc) : min(c, oc);
+    }
+}
+
 // 128 keys: element e = 32 * i + lane lives in v[i]
 template<class KeyT>
 __device__ __forceinline__ void wsort128(KeyT (&v)[4], int lane)
@@ -988,6 +1013,14 @@ q_fused_warp_kernel(const CandParams p, const FusedParams f)
             wsort64(a, b2, lane);
             A[lane] = a;
             A[lane + 32] = b2;
+        } else if(m <= 96) {
+            KeyT a = A[lane], b2 = A[lane + 32];
+            KeyT c2 = lane + 64 < int(m) ? A[lane + 64] : KMAX;
+            __syncwarp();
+            wsort96(a, b2, c2, lane);
+            A[lane] = a;
+            A[lane + 32] = b2;
+            A[lane + 64] = c2;
         } else if(m <= 128) {
             KeyT v[4];
 #pragma unroll
