@@ -104,7 +104,7 @@ int  mcg_ctx_destroy(mcg_ctx*);
 int  mcg_ctx_sync(mcg_ctx*);
 void* mcg_ctx_stream(mcg_ctx*);
 /* scratch blocks the library released are parked for reuse (cudaFree of multi-GB blocks is slow and synchronises
- * the device), at most 8 GB per device (MCG_CACHE_CAP_MB); mcg_ctx_trim returns all of them to the driver */
+ * the device), at most a quarter of the device memory (MCG_CACHE_CAP_MB); mcg_ctx_trim returns all of them to the driver */
 int  mcg_ctx_trim(mcg_ctx*);
 /* number of kernels this library launched on the ctx since creation */
 int64_t mcg_ctx_launches(mcg_ctx*);

@@ -153,9 +153,15 @@ void DevBuf::release()
     }
     p = nullptr;
     cap = 0;
-    // parked memory is capped (MCG_CACHE_CAP_MB, default 8 GB per device): beyond that the largest blocks go back
-    // to the driver, so that other allocators of the process (torch, NCCL) are not starved; mcg_ctx_trim frees all
-    static const size_t cap_bytes = size_t(getenv("MCG_CACHE_CAP_MB") ? atoll(getenv("MCG_CACHE_CAP_MB")) : 8192) << 20;
+    // parked memory is capped (MCG_CACHE_CAP_MB, default a quarter of the device memory): beyond that the largest
+    // blocks go back to the driver, so that other allocators of the process (torch, NCCL) are not starved;
+    // mcg_ctx_trim frees all
+    static const size_t cap_bytes = [] {
+        if(getenv("MCG_CACHE_CAP_MB")) return size_t(atoll(getenv("MCG_CACHE_CAP_MB"))) << 20;
+        size_t fr = 0, tot = 0;
+        if(cudaMemGetInfo(&fr, &tot) != cudaSuccess) { cudaGetLastError(); return size_t(8) << 30; }
+        return tot / 4;
+    }();
     trim_cached_device_memory(cap_bytes);
 }
 
