@@ -40,6 +40,10 @@ int comm_allgather_dev_u64(mcg_comm* m, const uint64_t* d_mine, int count, uint6
 int comm_allgatherv_inplace(mcg_comm* m, void* buf, const uint64_t* off, const uint64_t* len, cudaStream_t st);
 int comm_alltoallv(mcg_comm* m, const void* send, const uint64_t* soff, const uint64_t* slen,
                    void* recv, const uint64_t* roff, const uint64_t* rlen, cudaStream_t st);
+int merge_classify_rows(mcg_ctx* c, const mcg_query_opts* o, const int32_t* d_cand_tax, const uint32_t* d_cand_hits, const int32_t* d_cand_n,
+                        uint32_t rs, uint32_t ns, int32_t nshards, int64_t n,
+                        int32_t* d_out_tax, uint32_t* d_out_hits, int32_t* d_out_ncand,
+                        int32_t* d_out_best, int32_t* d_out_best_rank, uint64_t* d_stats22);
 int comm_group_begin(mcg_comm* m);
 int comm_group_end(mcg_comm* m);
 
@@ -193,7 +197,8 @@ q_find_kernel(const uint32_t* __restrict__ feat, uint64_t nslots, const uint32_t
 // counters: [0] small [1] medium [2] large [3] xl
 __global__ void q_bin_reads_kernel(const uint64_t* fpos, const uint32_t* W, int s, int64_t n,
                                    uint32_t* lists /* [4][n] */, uint32_t* counters,
-                                   int32_t* out_n, int32_t* out_tax, uint32_t* out_hits, int K, const uint8_t* done, const uint32_t* rmap)
+                                   int32_t* out_n, int32_t* out_tax, uint32_t* out_hits, int K, uint32_t rs, uint32_t ns,
+                                   const uint8_t* done, const uint32_t* rmap)
 {
     const int64_t r = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
     int cls = 4;                                          // 4 = nothing to do
@@ -201,8 +206,8 @@ __global__ void q_bin_reads_kernel(const uint64_t* fpos, const uint32_t* W, int 
         const uint64_t m = fpos[uint64_t(W[r + 1]) * s] - fpos[uint64_t(W[r]) * s];
         if(m == 0) {
             const uint64_t o = rmap ? rmap[r] : uint32_t(r);
-            out_n[o] = 0;
-            for(int c = 0; c < K; ++c) { out_tax[o * K + c] = -1; out_hits[o * K + c] = 0u; }
+            out_n[o * ns] = 0;
+            for(int c = 0; c < K; ++c) { out_tax[o * rs + c] = -1; out_hits[o * rs + c] = 0u; }
         } else cls = m <= Q_SMALL ? 0 : (m <= Q_MED ? 1 : (m <= Q_LARGE ? 2 : 3));
     }
     // one atomic per class per warp
@@ -324,6 +329,8 @@ struct CandParams {
     int32_t* out_tax;
     uint32_t* out_hits;
     int32_t* out_n;
+    uint32_t rs, ns;             // row strides in words of out_tax / out_hits (K when the arrays are separate) and of out_n (1);
+                                 // a packed record per read {tax[K], hits[K], n} has rs = ns = 2K + 1 (one exchange instead of three)
     int write_sorted;
 };
 
@@ -690,10 +697,10 @@ __device__ __forceinline__ void process_read_cta(const CandParams& p, uint32_t r
         L.tax = -1; L.hits = 0; L.n = 0;
         warp_toplist_insert_all(L, p.K, Ct, Ch, ncand, lane);
         if(lane < p.K) {
-            p.out_tax[uint64_t(r) * p.K + lane] = lane < L.n ? L.tax : -1;
-            p.out_hits[uint64_t(r) * p.K + lane] = lane < L.n ? L.hits : 0u;
+            p.out_tax[uint64_t(r) * p.rs + lane] = lane < L.n ? L.tax : -1;
+            p.out_hits[uint64_t(r) * p.rs + lane] = lane < L.n ? L.hits : 0u;
         }
-        if(lane == 0) p.out_n[r] = L.n;
+        if(lane == 0) p.out_n[uint64_t(r) * p.ns] = L.n;
     }
     __syncthreads();
 }
@@ -817,10 +824,10 @@ __device__ __forceinline__ void toplist_from_sorted(const CandParams& p, uint32_
     L.tax = -1; L.hits = 0; L.n = 0;
     warp_toplist_insert_all(L, p.K, Ct, Ch, ncand, lane);
     if(lane < p.K) {
-        p.out_tax[uint64_t(r) * p.K + lane] = lane < L.n ? L.tax : -1;
-        p.out_hits[uint64_t(r) * p.K + lane] = lane < L.n ? L.hits : 0u;
+        p.out_tax[uint64_t(r) * p.rs + lane] = lane < L.n ? L.tax : -1;
+        p.out_hits[uint64_t(r) * p.rs + lane] = lane < L.n ? L.hits : 0u;
     }
-    if(lane == 0) p.out_n[r] = L.n;
+    if(lane == 0) p.out_n[uint64_t(r) * p.ns] = L.n;
     __syncwarp();
 }
 
@@ -952,8 +959,8 @@ q_fused_warp_kernel(const CandParams p, const FusedParams f)
         // should any read of the batch be left over)
         if(lane == 0) f.done[r] = 1;
         if(m == 0) {
-            if(lane == 0) p.out_n[r] = 0;
-            if(lane < p.K) { p.out_tax[uint64_t(r) * p.K + lane] = -1; p.out_hits[uint64_t(r) * p.K + lane] = 0u; }
+            if(lane == 0) p.out_n[uint64_t(r) * p.ns] = 0;
+            if(lane < p.K) { p.out_tax[uint64_t(r) * p.rs + lane] = -1; p.out_hits[uint64_t(r) * p.rs + lane] = 0u; }
             continue;
         }
         // (3) matches into shared memory: short lists straight from the slot, longer ones gathered
@@ -1126,8 +1133,8 @@ q_spill_warp_kernel(const CandParams p, const SpillParams f)
         const uint32_t m = __shfl_sync(0xFFFFFFFFu, inc, 31);
         if(lane == 0) f.done[r] = 1;
         if(m == 0) {
-            if(lane == 0) p.out_n[r] = 0;
-            if(lane < p.K) { p.out_tax[uint64_t(r) * p.K + lane] = -1; p.out_hits[uint64_t(r) * p.K + lane] = 0u; }
+            if(lane == 0) p.out_n[uint64_t(r) * p.ns] = 0;
+            if(lane < p.K) { p.out_tax[uint64_t(r) * p.rs + lane] = -1; p.out_hits[uint64_t(r) * p.rs + lane] = 0u; }
             continue;
         }
         // matches in feature-slot order (any order would do: they are sorted next)
@@ -1205,6 +1212,7 @@ struct MergeParams {
     const int32_t* cand_tax;
     const uint32_t* cand_hits;
     const int32_t* cand_n;
+    uint32_t rs, ns;             // row strides in words of cand_tax / cand_hits and of cand_n (K and 1, or 2K + 1 for packed records)
     int P;
     int64_t n;
     int K;
@@ -1238,14 +1246,14 @@ __device__ __forceinline__ void merge_lists(TopK& dst, const TopK& src, const Me
 __device__ __forceinline__ void load_list(TopK& L, const MergeParams& p, int q, int64_t r)
 {
     const int64_t row = int64_t(q) * p.n + r;
-    int cnt = p.cand_n[row];
+    int cnt = p.cand_n[row * p.ns];
     if(cnt < 0 || cnt > p.K) { atomicOr(p.bad, 2u); cnt = cnt < 0 ? 0 : p.K; }
     L.n = 0;
     for(int c = 0; c < cnt; ++c) {
-        const int32_t t = p.cand_tax[row * p.K + c];
+        const int32_t t = p.cand_tax[row * p.rs + c];
         if(t < 0 || t >= p.ntaxa) { if(t != -1) atomicOr(p.bad, 1u); continue; }
         // a per-shard list is a valid top list already: re-inserting it (querying.h:910-940) reproduces it
-        topk_insert(L, p.K, t, p.cand_hits[row * p.K + c], p.lowest, p.lineage, p.rank);
+        topk_insert(L, p.K, t, p.cand_hits[row * p.rs + c], p.lowest, p.lineage, p.rank);
     }
 }
 
@@ -1262,12 +1270,12 @@ q_merge_classify_kernel(const MergeParams p)
         if(!p.compat) {
             for(int q = 0; q < p.P; ++q) {                   // rank order (querying.h:905-971)
                 const int64_t row = int64_t(q) * p.n + r;
-                int cnt = p.cand_n[row];
+                int cnt = p.cand_n[row * p.ns];
                 if(cnt < 0 || cnt > p.K) { atomicOr(p.bad, 2u); cnt = cnt < 0 ? 0 : p.K; }
                 for(int c = 0; c < cnt; ++c) {
-                    const int32_t t = p.cand_tax[row * p.K + c];
+                    const int32_t t = p.cand_tax[row * p.rs + c];
                     if(t < 0 || t >= p.ntaxa) { if(t != -1) atomicOr(p.bad, 1u); continue; }
-                    topk_insert(L, p.K, t, p.cand_hits[row * p.K + c], p.lowest, p.lineage, p.rank);
+                    topk_insert(L, p.K, t, p.cand_hits[row * p.rs + c], p.lowest, p.lineage, p.rank);
                 }
             }
         } else if((p.P & (p.P - 1)) == 0) {
@@ -1435,7 +1443,7 @@ static int qa_sketch(mcg_db* db, const mcg_query_opts* o,
 
 // staged path: find -> scan -> binning -> gather (reads marked done are skipped)
 static int query_find_gather(mcg_db* db, const mcg_query_opts* o, int64_t n, int32_t* d_out_tax, uint32_t* d_out_hits, int32_t* d_out_n,
-                             const uint8_t* d_done, QueryRun* run)
+                             uint32_t rs, uint32_t ns, const uint8_t* d_done, QueryRun* run)
 {
     mcg_ctx* c = db->ctx;
     const int s = o->sketchlen;
@@ -1457,7 +1465,7 @@ static int query_find_gather(mcg_db* db, const mcg_query_opts* o, int64_t n, int
     uint32_t* counters = c->q_rinfo.as<uint32_t>();
     MCG_CUDA(cudaMemsetAsync(counters, 0, 16, c->stream));
     q_bin_reads_kernel<<<grid_for(n), 256, 0, c->stream>>>(c->q_fpos.as<uint64_t>(), W, s, n, c->q_cls.as<uint32_t>(), counters, d_out_n, d_out_tax, d_out_hits,
-                                                          o->maxcand, d_done, run->rmap);
+                                                          o->maxcand, rs, ns, d_done, run->rmap);
     c->launches++;
     uint64_t total = 0;
     MCG_CUDA(cudaMemcpyAsync(&total, c->q_fpos.as<uint64_t>() + nslots, 8, cudaMemcpyDeviceToHost, c->stream));
@@ -1479,9 +1487,20 @@ static int query_find_gather(mcg_db* db, const mcg_query_opts* o, int64_t n, int
     return MCG_OK;
 }
 
+// where the per-read lists go: separate arrays (rs = K, ns = 1) or one packed record per read
+struct OutRows {
+    int32_t* tax; uint32_t* hits; int32_t* n; uint32_t rs, ns;
+    static OutRows separate(int32_t* t, uint32_t* h, int32_t* n_, int K) { return OutRows{t, h, n_, uint32_t(K), 1u}; }
+    static OutRows packed(uint32_t* base, int K)
+    {
+        return OutRows{reinterpret_cast<int32_t*>(base), base + K, reinterpret_cast<int32_t*>(base + 2 * K), uint32_t(2 * K + 1), uint32_t(2 * K + 1)};
+    }
+};
+
 static void fill_cand_params(mcg_db* db, const mcg_query_opts* o, const uint32_t* W, const uint2* meta,
-                             int32_t* d_out_tax, uint32_t* d_out_hits, int32_t* d_out_n, int write_sorted, CandParams* pp)
+                             const OutRows& out, int write_sorted, CandParams* pp)
 {
+    int32_t* d_out_tax = out.tax; uint32_t* d_out_hits = out.hits; int32_t* d_out_n = out.n;
     mcg_ctx* c = db->ctx;
     CandParams& p = *pp;
     p.fpos = c->q_fpos.as<uint64_t>();
@@ -1503,15 +1522,16 @@ static void fill_cand_params(mcg_db* db, const mcg_query_opts* o, const uint32_t
     p.out_tax = d_out_tax;
     p.out_hits = d_out_hits;
     p.out_n = d_out_n;
+    p.rs = out.rs; p.ns = out.ns;
     p.write_sorted = write_sorted;
 }
 
 static int query_back(mcg_db* db, const mcg_query_opts* o, const uint2* meta, int64_t n,
-                      const QueryRun& run, int32_t* d_out_tax, uint32_t* d_out_hits, int32_t* d_out_n, int write_sorted)
+                      const QueryRun& run, const OutRows& out, int write_sorted)
 {
     mcg_ctx* c = db->ctx;
     CandParams p;
-    fill_cand_params(db, o, run.W, meta, d_out_tax, d_out_hits, d_out_n, write_sorted, &p);
+    fill_cand_params(db, o, run.W, meta, out, write_sorted, &p);
     const uint32_t* lists = c->q_cls.as<uint32_t>();
     const uint32_t* counters = c->q_rinfo.as<uint32_t>();
     p.rmap = run.rmap;
@@ -1558,7 +1578,7 @@ static int query_back(mcg_db* db, const mcg_query_opts* o, const uint2* meta, in
 // stage A, fused kernel: all reads of the part (features / W / meta in `part`) -> per-read top lists; the
 // number of reads it could not hold goes to pinned memory (h_left), followed by part.evA
 static int qa_fused(mcg_db* db, const mcg_query_opts* o, QPart& part, int slot, int64_t n, double slots_per_read,
-                    int32_t* d_out_tax, uint32_t* d_out_hits, int32_t* d_out_n, bool ctr_cleared)
+                    const OutRows& out, bool ctr_cleared)
 {
     mcg_ctx* c = db->ctx;
     // (every read gets its whole row -- K slots, unused ones taxon -1 / hits 0 -- from the kernel that finishes it)
@@ -1567,7 +1587,7 @@ static int qa_fused(mcg_db* db, const mcg_query_opts* o, QPart& part, int slot, 
     uint32_t* left = part.ctr.as<uint32_t>();
     if(!ctr_cleared) MCG_CUDA(cudaMemsetAsync(left, 0, 16, c->stream));
     CandParams p;
-    fill_cand_params(db, o, part.W.as<uint32_t>(), part.meta.as<uint2>(), d_out_tax, d_out_hits, d_out_n, 0, &p);
+    fill_cand_params(db, o, part.W.as<uint32_t>(), part.meta.as<uint2>(), out, 0, &p);
     FusedParams f;
     f.feat = part.feat.as<uint32_t>(); f.table = db->table.as<uint32_t>(); f.geom = db->geom();
     f.locs = db->locs.as<uint64_t>(); f.n = n; f.done = part.done.as<uint8_t>(); f.left_over = left;
@@ -1627,8 +1647,7 @@ static int qa_fused(mcg_db* db, const mcg_query_opts* o, QPart& part, int slot, 
 
 // stage B, first half: waits for the part's fused kernel and sends the reads it left over through the
 // staged path (find -> scan -> binning -> gather -> size-binned candidate kernels).  Synchronises.
-static int qb_leftovers(mcg_db* db, const mcg_query_opts* o, QPart& part, int slot, int64_t n,
-                        int32_t* d_out_tax, uint32_t* d_out_hits, int32_t* d_out_n)
+static int qb_leftovers(mcg_db* db, const mcg_query_opts* o, QPart& part, int slot, int64_t n, const OutRows& out)
 {
     mcg_ctx* c = db->ctx;
     MCG_CUDA(cudaEventSynchronize(part.evA));
@@ -1677,8 +1696,8 @@ static int qb_leftovers(mcg_db* db, const mcg_query_opts* o, QPart& part, int sl
         run.nwin = wtot;
         run.nslots = uint64_t(wtot) * uint64_t(o->sketchlen);
     }
-    MCG_TRY(query_find_gather(db, o, n_staged, d_out_tax, d_out_hits, d_out_n, d_done, &run));
-    MCG_TRY(query_back(db, o, part.meta.as<uint2>(), n_staged, run, d_out_tax, d_out_hits, d_out_n, 0));
+    MCG_TRY(query_find_gather(db, o, n_staged, out.tax, out.hits, out.n, out.rs, out.ns, d_done, &run));
+    MCG_TRY(query_back(db, o, part.meta.as<uint2>(), n_staged, run, out, 0));
     return MCG_OK;
 }
 
@@ -1707,8 +1726,9 @@ int query_batch_dev(mcg_db* db, const mcg_query_opts* o,
     MCG_TRY(part.ctr.reserve(64));
     MCG_TRY(qa_sketch(db, o, d1, doffs1, bytes1, d2, doffs2, bytes2, n, max_len, part.W.as<uint32_t>(), part.meta.as<uint2>(),
                       part.feat.as<uint32_t>(), wb1, wb2, part.ctr.as<uint32_t>()));
-    MCG_TRY(qa_fused(db, o, part, slot, n, est_slots_per_read(o, bytes1, bytes2, n, d2 != nullptr), d_out_tax, d_out_hits, d_out_n, true));
-    if(finish) MCG_TRY(qb_leftovers(db, o, part, slot, n, d_out_tax, d_out_hits, d_out_n));
+    const OutRows out = OutRows::separate(d_out_tax, d_out_hits, d_out_n, o->maxcand);
+    MCG_TRY(qa_fused(db, o, part, slot, n, est_slots_per_read(o, bytes1, bytes2, n, d2 != nullptr), out, true));
+    if(finish) MCG_TRY(qb_leftovers(db, o, part, slot, n, out));
     return MCG_OK;
 }
 
@@ -1740,8 +1760,9 @@ static int query_staged_sorted(mcg_db* db, const mcg_query_opts* o,
     run.rmap = nullptr;
     run.nwin = wtot;
     run.nslots = uint64_t(wtot) * uint64_t(s);
-    MCG_TRY(query_find_gather(db, o, n, d_out_tax, d_out_hits, d_out_n, nullptr, &run));
-    MCG_TRY(query_back(db, o, part.meta.as<uint2>(), n, run, d_out_tax, d_out_hits, d_out_n, 1));
+    const OutRows out = OutRows::separate(d_out_tax, d_out_hits, d_out_n, K);
+    MCG_TRY(query_find_gather(db, o, n, out.tax, out.hits, out.n, out.rs, out.ns, nullptr, &run));
+    MCG_TRY(query_back(db, o, part.meta.as<uint2>(), n, run, out, 1));
     if(run_out) *run_out = run;
     return MCG_OK;
 }
@@ -1868,7 +1889,7 @@ static int qs_stage_a(mcg_db* db, mcg_comm* comm, const mcg_query_opts* o, const
     MCG_TRY(part.W.reserve(size_t(N + 2) * 4));
     MCG_TRY(part.meta.reserve(size_t(N + 1) * 8));
     MCG_TRY(part.feat.reserve((Wt * s + 1) * 4));
-    MCG_TRY(part.lt.reserve(size_t(N + 1) * K * 4)); MCG_TRY(part.lh.reserve(size_t(N + 1) * K * 4)); MCG_TRY(part.ln.reserve(size_t(N + 1) * 4));
+    MCG_TRY(part.lt.reserve(size_t(N + 1) * size_t(2 * K + 1) * 4));       // one packed record per read: {tax[K], hits[K], n}
     uint32_t* Wl = part.W.as<uint32_t>();
     if(P > 1) { MCG_TRY(c->tmp2.reserve(size_t(n_loc + 2) * 4)); Wl = c->tmp2.as<uint32_t>(); }
     c->prof_begin(3, c->stream);
@@ -1897,7 +1918,7 @@ static int qs_stage_a(mcg_db* db, mcg_comm* comm, const mcg_query_opts* o, const
     }
     if(N == 0) { c->h_left[slot] = 0; MCG_CUDA(cudaEventRecord(part.evA, c->stream)); return MCG_OK; }
     const double spr = est_slots_per_read(o, b1, b2, std::max<int64_t>(n_loc, 1), d2 != nullptr);
-    return qa_fused(db, o, part, slot, int64_t(N), n_loc > 0 ? spr : 64.0, part.lt.as<int32_t>(), part.lh.as<uint32_t>(), part.ln.as<int32_t>(), n_loc > 0);
+    return qa_fused(db, o, part, slot, int64_t(N), n_loc > 0 ? spr : 64.0, OutRows::packed(part.lt.as<uint32_t>(), K), n_loc > 0);
 }
 
 // stage B of part j: left-over reads, exchange of the per-read lists, merge + decision of the own block
@@ -1915,40 +1936,30 @@ static int qs_stage_b(mcg_db* db, mcg_comm* comm, const mcg_query_opts* o, const
         MCG_CUDA(cudaEventSynchronize(part.evA));
         const bool left = c->h_left[slot] != 0;
         if(left) c->prof_begin(5, c->stream);
-        MCG_TRY(qb_leftovers(db, o, part, slot, int64_t(N), part.lt.as<int32_t>(), part.lh.as<uint32_t>(), part.ln.as<int32_t>()));
+        MCG_TRY(qb_leftovers(db, o, part, slot, int64_t(N), OutRows::packed(part.lt.as<uint32_t>(), K)));
         if(left) c->prof_end(5, c->stream);
     }
-    const int32_t* ct = part.lt.as<int32_t>();
-    const uint32_t* ch = part.lh.as<uint32_t>();
-    const int32_t* cn = part.ln.as<int32_t>();
+    const uint64_t row = uint64_t(2 * K + 1) * 4;               // bytes of a packed record
+    const uint32_t* recs = part.lt.as<uint32_t>();              // P == 1: the own records, in place
     if(P > 1) {
         c->prof_begin(6, c->stream);
-        MCG_TRY(part.ct.reserve(size_t(P) * (n_me + 1) * K * 4)); MCG_TRY(part.ch.reserve(size_t(P) * (n_me + 1) * K * 4));
-        MCG_TRY(part.cn.reserve(size_t(P) * (n_me + 1) * 4));
+        MCG_TRY(part.ct.reserve(size_t(P) * (n_me + 1) * row));
         std::vector<uint64_t> so(static_cast<size_t>(P)), sl(static_cast<size_t>(P)), ro(static_cast<size_t>(P)), rl(static_cast<size_t>(P));
-        MCG_TRY(comm_group_begin(comm));                       // taxa + hits + counts: one NCCL group
-        for(int pass = 0; pass < 2; ++pass) {
-            const uint64_t row = pass == 0 ? uint64_t(K) * 4 : 4;       // bytes per read: lists, counts
-            uint64_t a = 0;
-            for(int r = 0; r < P; ++r) {
-                so[size_t(r)] = a * row; sl[size_t(r)] = pl.rn(j, r) * row; a += pl.rn(j, r);
-                ro[size_t(r)] = uint64_t(r) * n_me * row; rl[size_t(r)] = n_me * row;
-            }
-            if(pass == 0) {
-                MCG_TRY(comm_alltoallv(comm, part.lt.p, so.data(), sl.data(), part.ct.p, ro.data(), rl.data(), c->stream));
-                MCG_TRY(comm_alltoallv(comm, part.lh.p, so.data(), sl.data(), part.ch.p, ro.data(), rl.data(), c->stream));
-            } else {
-                MCG_TRY(comm_alltoallv(comm, part.ln.p, so.data(), sl.data(), part.cn.p, ro.data(), rl.data(), c->stream));
-            }
+        uint64_t a = 0;
+        for(int r = 0; r < P; ++r) {
+            so[size_t(r)] = a * row; sl[size_t(r)] = pl.rn(j, r) * row; a += pl.rn(j, r);
+            ro[size_t(r)] = uint64_t(r) * n_me * row; rl[size_t(r)] = n_me * row;
         }
-        MCG_TRY(comm_group_end(comm));
-        ct = part.ct.as<int32_t>(); ch = part.ch.as<uint32_t>(); cn = part.cn.as<int32_t>();
+        MCG_TRY(comm_alltoallv(comm, part.lt.p, so.data(), sl.data(), part.ct.p, ro.data(), rl.data(), c->stream));
+        recs = part.ct.as<uint32_t>();
         c->prof_end(6, c->stream);
     }
     (void)nb;
     c->prof_begin(7, c->stream);
     if(n_me > 0)
-        MCG_TRY(mcg_merge_classify_dev(c, o, ct, ch, cn, P, int64_t(n_me), d_out_tax, d_out_hits, d_out_n, d_out_best, d_out_brank, d_stats));
+        MCG_TRY(merge_classify_rows(c, o, reinterpret_cast<const int32_t*>(recs), recs + K, reinterpret_cast<const int32_t*>(recs + 2 * K),
+                                    uint32_t(2 * K + 1), uint32_t(2 * K + 1), P, int64_t(n_me), d_out_tax, d_out_hits, d_out_n, d_out_best,
+                                    d_out_brank, d_stats));
     c->prof_end(7, c->stream);
     MCG_CUDA(cudaEventRecord(part.evB, c->stream));
     return MCG_OK;
@@ -2058,8 +2069,8 @@ int mcg_query_batch(mcg_db* db, const mcg_query_opts* o,
     auto finish = [&](int64_t i) -> int {
         const int slot = int(i & 1);
         const int64_t a = i * sub_reads, b = std::min(n, a + sub_reads);
-        MCG_TRY(qb_leftovers(db, o, c->qp[slot], slot, b - a, c->q_out_tax.as<int32_t>() + a * K, c->q_out_hits.as<uint32_t>() + a * K,
-                             c->q_out_n.as<int32_t>() + a));
+        MCG_TRY(qb_leftovers(db, o, c->qp[slot], slot, b - a, OutRows::separate(c->q_out_tax.as<int32_t>() + a * K, c->q_out_hits.as<uint32_t>() + a * K,
+                                                                                   c->q_out_n.as<int32_t>() + a, K)));
         MCG_CUDA(cudaEventRecord(c->ev_k[slot], c->stream));
         MCG_CUDA(cudaStreamWaitEvent(c->s_d2h, c->ev_k[slot], 0));
         MCG_CUDA(cudaMemcpyAsync(out_tax + a * K, c->q_out_tax.as<int32_t>() + a * K, size_t(b - a) * K * 4, cudaMemcpyDeviceToHost, c->s_d2h));
@@ -2140,6 +2151,18 @@ int mcg_merge_classify_dev(mcg_ctx* c, const mcg_query_opts* o,
                            int32_t* d_out_best, int32_t* d_out_best_rank, uint64_t* d_stats22)
 {
     MCG_REQUIRE(c != nullptr && o != nullptr, "mcg_merge_classify_dev: NULL argument");
+    return mcg::merge_classify_rows(c, o, d_cand_tax, d_cand_hits, d_cand_n, uint32_t(o->maxcand), 1u, nshards, n, d_out_tax, d_out_hits,
+                                    d_out_ncand, d_out_best, d_out_best_rank, d_stats22);
+}
+
+}  // extern "C"
+
+namespace mcg {
+int merge_classify_rows(mcg_ctx* c, const mcg_query_opts* o, const int32_t* d_cand_tax, const uint32_t* d_cand_hits, const int32_t* d_cand_n,
+                        uint32_t rs, uint32_t ns, int32_t nshards, int64_t n,
+                        int32_t* d_out_tax, uint32_t* d_out_hits, int32_t* d_out_ncand,
+                        int32_t* d_out_best, int32_t* d_out_best_rank, uint64_t* d_stats22)
+{
     MCG_REQUIRE(nshards >= 1 && n >= 0, "bad shard / read count");
     MCG_REQUIRE(o->maxcand >= 1 && o->maxcand <= MCG_MAX_CAND, "maxcand %d outside 1..%d", o->maxcand, MCG_MAX_CAND);
     MCG_REQUIRE(o->lowest >= 0 && o->lowest < MCG_NUM_RANKS && o->highest >= 0 && o->highest < MCG_NUM_RANKS, "rank out of range");
@@ -2153,6 +2176,7 @@ int mcg_merge_classify_dev(mcg_ctx* c, const mcg_query_opts* o,
     MergeParams p;
     p.compat = o->reference_compat; p.ntaxa = int32_t(c->ntaxa); p.ntargets = int32_t(c->ntargets); p.bad = c->m_bad.as<uint32_t>();
     p.cand_tax = d_cand_tax; p.cand_hits = d_cand_hits; p.cand_n = d_cand_n;
+    p.rs = rs; p.ns = ns;
     p.P = nshards; p.n = n; p.K = o->maxcand;
     p.lowest = o->lowest; p.highest = o->highest; p.hitmin = o->hitmin; p.hitdiff = o->hitdiff;
     p.lineage = c->lineage.as<int32_t>(); p.rank = c->rank.as<uint8_t>();
@@ -2164,6 +2188,9 @@ int mcg_merge_classify_dev(mcg_ctx* c, const mcg_query_opts* o,
     MCG_CUDA(cudaGetLastError());
     return MCG_OK;
 }
+}  // namespace mcg
+
+extern "C" {
 
 int mcg_merge_classify(mcg_ctx* c, const mcg_query_opts* o,
                        const int32_t* cand_tax, const uint32_t* cand_hits,

@@ -48,6 +48,18 @@ def run():
     et, eh, en, eb, er, es = O.query_batch(od, tax, oq, b1, o1, b2, o2)
     assert (mt == et).all() and (mh == eh).all() and (mn == en).all(), "top-hit mismatch"
     assert (best == eb).all() and (brank == er).all() and (stats == es).all(), "classification mismatch"
+    # the one-call form (mcg_query_batch_sharded; a single shard needs no communicator): query + merge + decision
+    g1 = api.Database(ctx)
+    g1.add_targets(buf, offs, np.arange(G, dtype=np.uint32))
+    g1.finalize()
+    o1db = O.db_create()
+    for g in range(G):
+        o1db.add_target(genomes[g], g)
+    o1db.finalize()
+    st, sh, sn, sb, sr, ss = g1.query_batch_sharded(None, q, b1, o1, b2, o2)
+    et1, eh1, en1, eb1, er1, es1 = O.query_batch([o1db], tax, oq, b1, o1, b2, o2)
+    assert (st == et1).all() and (sh == eh1).all() and (sn == en1).all() and (sb == eb1).all() and (sr == er1).all(), "sharded call mismatch"
+    assert (ss == es1).all(), "sharded call statistics mismatch"
     print("smoke ok: %d windows, %d reads, %d classified, %d kernel launches"
           % (len(fg), len(o1) - 1, int(stats[20]), ctx.launches()))
     ctx.close()
