@@ -236,7 +236,7 @@ int mcg_ctx_destroy(mcg_ctx* c)
     if(c == nullptr) return MCG_OK;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    DevBuf* bufs[] = {&c->lineage, &c->rank, &c->seq, &c->seqoff, &c->winfirst, &c->outfirst, &c->tmp0, &c->tmp1,
+    DevBuf* bufs[] = {&c->lineage, &c->rank, &c->lift, &c->seq, &c->seqoff, &c->winfirst, &c->outfirst, &c->tmp0, &c->tmp1,
                       &c->tmp2, &c->tmp3, &c->tmp4, &c->tmp5, &c->scan_tmp, &c->q_feat, &c->q_flen, &c->q_foff,
                       &c->q_fpos, &c->q_loc, &c->q_rinfo, &c->q_cls, &c->q_out_tax, &c->q_out_hits, &c->q_out_n, &c->q_done,
                       &c->m_tax, &c->m_hits, &c->m_n, &c->m_o_tax, &c->m_o_hits, &c->m_o_n, &c->m_best,

@@ -110,8 +110,9 @@ struct mcg_ctx {
         cudaEventRecord(prof_ev[which].back(), st);
     }
     // taxonomy tables (replicated per GPU)
-    mcg::DevBuf lineage, rank;
+    mcg::DevBuf lineage, rank, lift;  // lift: per target, the taxon its candidates are listed under at `lift_lowest`
     int64_t ntaxa = 0, ntargets = 0;
+    int lift_lowest = -1;
     // scratch
     mcg::DevBuf seq, seqoff, winfirst, outfirst, tmp0, tmp1, tmp2, tmp3, tmp4, tmp5, scan_tmp, tilectr;
     mcg::DevBuf q_feat, q_flen, q_foff, q_fpos, q_loc, q_rinfo, q_cls, q_out_tax, q_out_hits, q_out_n, q_done;

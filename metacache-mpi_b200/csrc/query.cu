@@ -326,6 +326,9 @@ struct CandParams {
     int lowest;
     const int32_t* lineage;
     const uint8_t* rank;
+    const int32_t* lift;         // [ntargets] taxon a target's candidates are listed under at -lowest (candidates.h:242-245:
+                                 // its ancestor at that rank if it has one, else its own sequence-level taxon), bit 31 = that
+                                 // taxon is of sequence rank: 4 bytes per target instead of two dependent loads from the lineage table
     int32_t* out_tax;
     uint32_t* out_hits;
     int32_t* out_n;
@@ -672,12 +675,7 @@ __device__ __forceinline__ void process_read_cta(const CandParams& p, uint32_t r
         int32_t tax = 0;
         if(tail) {
             v = Hh[i];
-            tax = int32_t(tgt);
-            if(p.lowest > MCG_RANK_SEQUENCE) {
-                const int32_t anc = __ldg(p.lineage + int64_t(tax) * MCG_NUM_RANKS + p.lowest);
-                if(anc >= 0) tax = anc;
-            }
-            if(__ldg(p.rank + tax) == MCG_RANK_SEQUENCE) tax |= int32_t(0x80000000u);
+            tax = __ldg(p.lift + tgt);            // the target's taxon at -lowest, sequence-rank flag in bit 31
         }
         const uint32_t bal = __ballot_sync(0xFFFFFFFFu, tail);
         if(lane == 0) s_wcount[warp] = __popc(bal);
@@ -807,14 +805,8 @@ __device__ __forceinline__ void toplist_from_sorted(const CandParams& p, uint32_
         carry = __shfl_sync(0xFFFFFFFFu, v, 31);
         const uint32_t tm = __ballot_sync(0xFFFFFFFFu, tail);
         if(tail) {
-            int32_t tax = int32_t(tgt);
-            if(p.lowest > MCG_RANK_SEQUENCE) {
-                const int32_t anc = __ldg(p.lineage + int64_t(tax) * MCG_NUM_RANKS + p.lowest);
-                if(anc >= 0) tax = anc;
-            }
-            const bool seq = __ldg(p.rank + tax) == MCG_RANK_SEQUENCE;
             const uint32_t j = ncand + __popc(tm & ltmask);
-            Ct[j] = tax | (seq ? int32_t(0x80000000u) : 0);
+            Ct[j] = __ldg(p.lift + tgt);          // the target's taxon at -lowest, sequence-rank flag in bit 31
             Ch[j] = v;
         }
         ncand += __popc(tm);
@@ -889,6 +881,8 @@ q_fused_warp_kernel(const CandParams p, const FusedParams f)
             continue;
         }
         const int nc = int(ns + 31) >> 5;                 // feature slots per lane (uniform)
+        // the features of the next read (they follow in memory: reads are taken 8 in a row) towards L1 meanwhile
+        if(lane < 2) asm volatile("prefetch.global.L1 [%0];" :: "l"(f.feat + s1 + 32 * lane));
         // (1) probe.  A pass loads the bucket line (keys + sizes) of every unresolved feature of the
         //     lane at once; a feature leaves when its key or a free slot is found.  Passes repeat
         //     while any lane still has a feature whose bucket was full (few: <= 2 in most reads).
@@ -1207,6 +1201,19 @@ __global__ void q_read_counts_kernel(const uint64_t* fpos, const uint32_t* W, in
     if(r < n) out[r] = int64_t(fpos[uint64_t(W[r + 1]) * s] - fpos[uint64_t(W[r]) * s]);
 }
 
+__global__ void q_lift_kernel(const int32_t* lineage, const uint8_t* rank, int64_t ntargets, int lowest, int32_t* lift)
+{
+    const int64_t t = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+    if(t >= ntargets) return;
+    int32_t tax = int32_t(t);
+    if(lowest > MCG_RANK_SEQUENCE) {
+        const int32_t anc = lineage[t * MCG_NUM_RANKS + lowest];
+        if(anc >= 0) tax = anc;
+    }
+    if(rank[tax] == MCG_RANK_SEQUENCE) tax |= int32_t(0x80000000u);
+    lift[t] = tax;
+}
+
 // ------------------------------------------------------------------ K6: merge + classify + statistics
 struct MergeParams {
     const int32_t* cand_tax;
@@ -1382,7 +1389,18 @@ static int check_ready(mcg_db* db, const mcg_query_opts* o)
 {
     MCG_TRY(check_opts(db, o));
     if(!db->finalized) { set_error("database not finalized"); return MCG_ERR_STATE; }
-    if(db->ctx->lineage.p == nullptr) { set_error("taxonomy not uploaded (mcg_tax_upload)"); return MCG_ERR_STATE; }
+    mcg_ctx* c = db->ctx;
+    if(c->lineage.p == nullptr) { set_error("taxonomy not uploaded (mcg_tax_upload)"); return MCG_ERR_STATE; }
+    if(c->lift_lowest != o->lowest) {                    // per-target lifting table of this -lowest (rebuilt when it changes)
+        MCG_TRY(c->lift.reserve(size_t(c->ntargets + 1) * 4));
+        if(c->ntargets > 0) {
+            q_lift_kernel<<<grid_for(uint64_t(c->ntargets)), 256, 0, c->stream>>>(c->lineage.as<int32_t>(), c->rank.as<uint8_t>(), c->ntargets,
+                                                                                  o->lowest, c->lift.as<int32_t>());
+            c->launches++;
+            MCG_CUDA(cudaGetLastError());
+        }
+        c->lift_lowest = o->lowest;
+    }
     return MCG_OK;
 }
 
@@ -1519,6 +1537,7 @@ static void fill_cand_params(mcg_db* db, const mcg_query_opts* o, const uint32_t
     p.lowest = o->lowest;
     p.lineage = c->lineage.as<int32_t>();
     p.rank = c->rank.as<uint8_t>();
+    p.lift = c->lift.as<int32_t>();
     p.out_tax = d_out_tax;
     p.out_hits = d_out_hits;
     p.out_n = d_out_n;
@@ -1722,7 +1741,7 @@ int query_batch_dev(mcg_db* db, const mcg_query_opts* o,
     MCG_REQUIRE((wb1 + wb2) * uint64_t(s) < (1ull << 32), "too many feature slots in one query part");
     MCG_TRY(part.W.reserve(size_t(n + 2) * 4));
     MCG_TRY(part.meta.reserve(size_t(n + 1) * 8));
-    MCG_TRY(part.feat.reserve(((wb1 + wb2) * s + 1) * 4));
+    MCG_TRY(part.feat.reserve(((wb1 + wb2) * s + 65) * 4));       // (+ 64: the fused kernel prefetches one read ahead)
     MCG_TRY(part.ctr.reserve(64));
     MCG_TRY(qa_sketch(db, o, d1, doffs1, bytes1, d2, doffs2, bytes2, n, max_len, part.W.as<uint32_t>(), part.meta.as<uint2>(),
                       part.feat.as<uint32_t>(), wb1, wb2, part.ctr.as<uint32_t>()));
@@ -1746,7 +1765,7 @@ static int query_staged_sorted(mcg_db* db, const mcg_query_opts* o,
     MCG_REQUIRE((wb1 + wb2) * uint64_t(s) < (1ull << 32), "too many feature slots in one query part");
     MCG_TRY(part.W.reserve(size_t(n + 2) * 4));
     MCG_TRY(part.meta.reserve(size_t(n + 1) * 8));
-    MCG_TRY(part.feat.reserve(((wb1 + wb2) * s + 1) * 4));
+    MCG_TRY(part.feat.reserve(((wb1 + wb2) * s + 65) * 4));       // (+ 64: the fused kernel prefetches one read ahead)
     MCG_CUDA(cudaMemsetAsync(d_out_tax, 0xFF, size_t(n) * K * 4, c->stream));
     MCG_CUDA(cudaMemsetAsync(d_out_hits, 0, size_t(n) * K * 4, c->stream));
     MCG_TRY(qa_sketch(db, o, d1, doffs1, bytes1, d2, doffs2, bytes2, n, 0, part.W.as<uint32_t>(), part.meta.as<uint2>(),
@@ -1888,7 +1907,7 @@ static int qs_stage_a(mcg_db* db, mcg_comm* comm, const mcg_query_opts* o, const
     MCG_REQUIRE((Wt + 1) * uint64_t(s) < (1ull << 32) && N < (1ull << 31), "too many reads / feature slots in one query part");
     MCG_TRY(part.W.reserve(size_t(N + 2) * 4));
     MCG_TRY(part.meta.reserve(size_t(N + 1) * 8));
-    MCG_TRY(part.feat.reserve((Wt * s + 1) * 4));
+    MCG_TRY(part.feat.reserve((Wt * s + 65) * 4));
     MCG_TRY(part.lt.reserve(size_t(N + 1) * size_t(2 * K + 1) * 4));       // one packed record per read: {tax[K], hits[K], n}
     uint32_t* Wl = part.W.as<uint32_t>();
     if(P > 1) { MCG_TRY(c->tmp2.reserve(size_t(n_loc + 2) * 4)); Wl = c->tmp2.as<uint32_t>(); }
@@ -1990,6 +2009,7 @@ int mcg_tax_upload(mcg_ctx* c, const int32_t* lineage, const uint8_t* rank, int6
     MCG_CUDA(cudaStreamSynchronize(c->stream));
     c->ntaxa = ntaxa;
     c->ntargets = ntargets;
+    c->lift_lowest = -1;
     return MCG_OK;
 }
 
