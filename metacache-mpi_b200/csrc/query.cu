@@ -503,7 +503,7 @@ __device__ __forceinline__ void wsort128(KeyT (&v)[4], int lane)
 
 template<class KeyT>
 __device__ __forceinline__ void toplist_from_sorted(const CandParams& p, uint32_t r, const KeyT* A, const uint32_t* Hh,
-                                                    uint32_t m, int32_t* Ct, uint32_t* Ch, int lane);
+                                                    uint32_t m, int32_t* Ct, uint32_t* Ch, int lane, uint32_t numwin = 0);
 
 // one read handled by one warp (<= Q_SMALL matches); Ct, Ch: candidate scratch of Q_SMALL entries
 template<class KeyT>
@@ -777,22 +777,44 @@ __device__ __forceinline__ void warp_topk_insert_lifted(WarpTopK& L, int K, int3
 // maxima taken (segmented warp scan) and their taxa lifted by all lanes at once (the lineage
 // loads of all candidates are in flight together); only the order-dependent list insertion
 // (candidates.h:236-285) runs one candidate after the other, out of shared memory.
+// Hh == nullptr: the range hits (hits_ending_at) are computed here instead of by a pass of their own -- from the start of
+// an element's target run (running maximum of the run-head indices): as long as the run spans fewer than numwin
+// windows up to the element, ALL its elements so far are in range (the usual case for a short read); only otherwise
+// the range is searched.
 template<class KeyT>
 __device__ __forceinline__ void toplist_from_sorted(const CandParams& p, uint32_t r, const KeyT* A, const uint32_t* Hh,
-                                                    uint32_t m, int32_t* Ct, uint32_t* Ch, int lane)
+                                                    uint32_t m, int32_t* Ct, uint32_t* Ch, int lane, uint32_t numwin)
 {
     const uint32_t ltmask = (1u << lane) - 1u;
-    uint32_t ncand = 0, carry = 0, last_tgt = 0xFFFFFFFFu;
+    uint32_t ncand = 0, carry = 0, last_tgt = 0xFFFFFFFFu, run_start = 0;
     for(uint32_t b = 0; b < m; b += 32) {
         const uint32_t i = b + lane;
         const bool valid = i < m;
-        const uint32_t tgt = valid ? tgt_of(A[i], p.wbits) : 0xFFFFFFFFu;
+        const KeyT key = valid ? A[i] : KeyT(0);
+        const uint32_t tgt = valid ? tgt_of(key, p.wbits) : 0xFFFFFFFFu;
         uint32_t prev = __shfl_up_sync(0xFFFFFFFFu, tgt, 1);
         if(lane == 0) prev = last_tgt;
         last_tgt = __shfl_sync(0xFFFFFFFFu, tgt, 31);
         const bool head = valid && (i == 0 || prev != tgt);
         const bool tail = valid && (i + 1 == m || tgt_of(A[i + 1], p.wbits) != tgt);
-        uint32_t v = valid ? Hh[i] : 0u;
+        uint32_t v = 0u;
+        if(Hh != nullptr) {
+            if(valid) v = Hh[i];
+        } else {
+            uint32_t st = head ? i : 0u;
+            if(lane == 0 && !head) st = run_start;
+#pragma unroll
+            for(int d = 1; d < 32; d <<= 1) {
+                const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, st, d);
+                if(lane >= d) st = max(st, o);
+            }
+            run_start = __shfl_sync(0xFFFFFFFFu, st, 31);
+            if(valid) {
+                const KeyT wmask = (KeyT(1) << p.wbits) - 1;
+                const uint32_t win = uint32_t(key & wmask), win0 = uint32_t(A[st] & wmask);
+                v = (win - win0 < numwin) ? i - st + 1u : hits_ending_at(A, i, numwin, p.wbits);
+            }
+        }
         if(lane == 0 && !head) v = max(v, carry);
         const uint32_t hm = __ballot_sync(0xFFFFFFFFu, head);
         // inclusive segmented max scan: take the value d lanes down unless a run starts in between
@@ -857,11 +879,10 @@ q_fused_warp_kernel(const CandParams p, const FusedParams f)
 {
     extern __shared__ __align__(16) unsigned char sm[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // per warp: A[CAP] keys, Hh[CAP], Ct[CAP], Ch[CAP]
-    unsigned char* wbase = sm + size_t(warp) * CAP * (sizeof(KeyT) + 12);
+    // per warp: A[CAP] keys, Ct[CAP], Ch[CAP] (the range hits are computed on the fly: no array of their own)
+    unsigned char* wbase = sm + size_t(warp) * CAP * (sizeof(KeyT) + 8);
     KeyT* A = reinterpret_cast<KeyT*>(wbase);
-    uint32_t* Hh = reinterpret_cast<uint32_t*>(wbase + size_t(CAP) * sizeof(KeyT));
-    int32_t* Ct = reinterpret_cast<int32_t*>(Hh + CAP);
+    int32_t* Ct = reinterpret_cast<int32_t*>(wbase + size_t(CAP) * sizeof(KeyT));
     uint32_t* Ch = reinterpret_cast<uint32_t*>(Ct + CAP);
     const KeyT KMAX = ~KeyT(0);
     // reads are handed out 8 at a time by an atomic counter (their cost varies with their matches)
@@ -1036,9 +1057,7 @@ q_fused_warp_kernel(const CandParams p, const FusedParams f)
         __syncwarp();
         // (5) window ranges + top list
         const uint32_t numwin = num_windows_in_range(p, uint32_t(r));
-        for(uint32_t i = lane; i < m; i += 32) Hh[i] = hits_ending_at(A, i, numwin, p.wbits);
-        __syncwarp();
-        toplist_from_sorted<KeyT>(p, uint32_t(r), A, Hh, m, Ct, Ch, lane);
+        toplist_from_sorted<KeyT>(p, uint32_t(r), A, nullptr, m, Ct, Ch, lane, numwin);
     }
 }
 
@@ -1622,12 +1641,13 @@ static int qa_fused(mcg_db* db, const mcg_query_opts* o, QPart& part, int slot, 
     static const int cap_env = getenv("MCG_FUSED_CAP") ? atoi(getenv("MCG_FUSED_CAP")) : 0;
     const bool cap256 = cap_env ? cap_env >= 256 : (double(db->nlocs) > 2.1 * double(db->nkeys));
     // shared memory comes out of L1, which the probes live on: ask for no more than the 5 CTAs need
-    const int carve = cap256 ? 70 : 38;
+    static const int carve_env = getenv("MCG_FUSED_CARVE") ? atoi(getenv("MCG_FUSED_CARVE")) : -1;
+    const int carve = carve_env >= 0 ? carve_env : (cap256 ? 56 : 30);
 #define QF_LAUNCH(KT, NC) do { if(cap256) QF_LAUNCH_CAP(KT, NC, 256); else QF_LAUNCH_CAP(KT, NC, Q_FUSED); } while(0)
 #define QF_LAUNCH_CAP(KT, NC, CAP)                                                                                   \
     do {                                                                                                             \
         auto kern = q_fused_warp_kernel<KT, NC, CAP>;                                                                \
-        const int smem = 8 * CAP * (int(sizeof(KT)) + 12);                                                           \
+        const int smem = 8 * CAP * (int(sizeof(KT)) + 8);                                                            \
         MCG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));                     \
         if(carve >= 0) MCG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve));    \
         MCG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem));                           \
