@@ -873,8 +873,9 @@ __global__ void q_hide_done_kernel(uint32_t* feat, const uint32_t* W, int s, con
     for(uint64_t i = s0 + lane; i < s1; i += 32) feat[i] = EMPTY_KEY;
 }
 
+// (launch bound: the 2-slot, 128-match variant fits 40 registers without spills = 6 resident CTAs, 48 warps per SM)
 template<class KeyT, int NC, int CAP>  // NC: feature slots per lane (reads with more than 32*NC slots are left over); CAP: matches per read
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, NC == 2 ? ((CAP <= 128 && sizeof(KeyT) == 4) ? 6 : 5) : 3)
 q_fused_warp_kernel(const CandParams p, const FusedParams f)
 {
     extern __shared__ __align__(16) unsigned char sm[];
@@ -1642,7 +1643,7 @@ static int qa_fused(mcg_db* db, const mcg_query_opts* o, QPart& part, int slot, 
     const bool cap256 = cap_env ? cap_env >= 256 : (double(db->nlocs) > 2.1 * double(db->nkeys));
     // shared memory comes out of L1, which the probes live on: ask for no more than the 5 CTAs need
     static const int carve_env = getenv("MCG_FUSED_CARVE") ? atoi(getenv("MCG_FUSED_CARVE")) : -1;
-    const int carve = carve_env >= 0 ? carve_env : (cap256 ? 56 : 30);
+    const int carve = carve_env >= 0 ? carve_env : (cap256 ? 56 : 36);
 #define QF_LAUNCH(KT, NC) do { if(cap256) QF_LAUNCH_CAP(KT, NC, 256); else QF_LAUNCH_CAP(KT, NC, Q_FUSED); } while(0)
 #define QF_LAUNCH_CAP(KT, NC, CAP)                                                                                   \
     do {                                                                                                             \
