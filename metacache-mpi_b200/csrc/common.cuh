@@ -72,13 +72,13 @@ namespace mcg {
 // later stages (left-over reads, list exchange, merge, copy-out) read exists twice.
 struct QPart {
     DevBuf W, feat, meta, left_list, left_list2, done, ctr;   // window prefix, features, per-read meta; fused / spill kernel bookkeeping
-    DevBuf lt, lh, ln;                                 // per-read top lists of every read of the part
-    DevBuf ct, ch, cn;                                 // lists received from the other shards for the own block [P][n][K]
+    DevBuf lt;                                         // per-read records {tax[K], hits[K], n} of every read of the part
+    DevBuf ct;                                         // records received from the other shards for the own block [P][n]
     DevBuf mt, mh, mn, mbest, mbrank;                  // merged lists + decision of the own block
     cudaEvent_t evA = nullptr, evB = nullptr;
     void release_all()
     {
-        DevBuf* b[] = {&W, &feat, &meta, &left_list, &left_list2, &done, &ctr, &lt, &lh, &ln, &ct, &ch, &cn, &mt, &mh, &mn, &mbest, &mbrank};
+        DevBuf* b[] = {&W, &feat, &meta, &left_list, &left_list2, &done, &ctr, &lt, &ct, &mt, &mh, &mn, &mbest, &mbrank};
         for(DevBuf* x : b) x->release();
         if(evA) cudaEventDestroy(evA);
         if(evB) cudaEventDestroy(evB);

@@ -12,17 +12,19 @@
 //   classification.cpp:236-265 threshold + ranked LCA (taxonomy.h:531-537)
 //   classification_statistics.h:70-78 assign
 //
-// Pipeline per batch (all on the ctx stream):
-//   window counts -> 3 scans -> K1 (mate 1, mate 2) -> q_fused_warp_kernel: one warp per read
-//   (pair) probes the bucket table (one 128-byte line per probe, common.cuh "feature table"),
-//   gathers, sorts, scans the window ranges and builds the top list, all in shared memory.
-//   Reads it cannot hold (> 128 matches or > 32 * NC feature slots, i.e. long reads) take the
-//   staged path: find -> scan of list lengths -> read binning -> gather -> size-binned sorters
-//   (warp / CTA / big CTA / global-memory fallback) with the same window-range + top-list logic.
-//   When only a few reads are left over (< 1/8 of the batch) their windows and features are first
-//   compacted into a sub-batch of their own (q_left_*), so that the staged kernels, which run per
-//   feature slot of the batch they are given, do not pass over the whole batch.
-//   The host entry point mcg_query_batch cuts a batch into sub-batches and overlaps H2D, query and D2H.
+// Pipeline of one part of a call (all on the ctx stream, 8 launches, no host round trip):
+//   q_prep_kernel (window counts, prefixes, per-read meta: one single-pass chained scan) -> K1 of mate 1 and mate 2
+//   -> [sharded: exchange of sketches + meta, comm.cu] -> q_fused_warp_kernel: one warp per read (pair) probes the
+//   bucket table (one 128-byte line per probe, common.cuh "feature table"), takes short lists out of the slot itself,
+//   gathers longer ones, sorts, derives range hits and the top list -- all in registers / shared memory
+//   -> q_spill_warp_kernel: the few short reads with more matches than a warp holds in shared memory (global scratch)
+//   -> [sharded: all-to-all of the per-read records] -> q_merge_classify_kernel.
+//   Long reads (> 128 feature slots) take the staged path: find -> scan of list lengths -> read binning -> gather ->
+//   size-binned sorters (warp / CTA / big CTA / global-memory fallback) with the same window-range + top-list logic;
+//   when only a few reads are left over (< 1/8 of the part) their windows and features are first compacted into a
+//   sub-batch of their own (q_left_*).  The host learns ONE number per part (how many long reads are left) and reads it
+//   after the next part's stage A is enqueued.  Host entry points cut a call into parts and overlap H2D, kernels and D2H;
+//   mcg_query_batch_sharded runs the whole of query_batched_parallel2 (querying.h:721-1173) across ranks.
 #include "common.cuh"
 
 #include <ctime>
