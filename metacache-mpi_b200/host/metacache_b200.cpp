@@ -4,7 +4,8 @@
 //
 //   metacache_b200 build <db> <fasta files / directories ...> [-gpus P] [-kmerlen 16]
 //       [-sketchlen 16] [-winlen 128] [-winstride winlen-k+1] [-max-locations-per-feature 254]
-//       [-remove-overpopulated-features] [-taxonomy dir] [-taxpostmap file]  (mode_build.cpp:93-138; targets without a
+//       [-remove-overpopulated-features] [-taxonomy dir] [-taxpostmap file]  (mode_build.cpp:93-138; an
+//       `assembly_summary.txt` next to the sequence files names their taxa, taxonomy_io.cpp:190-311; targets still without a
 //       taxon are looked up in <dir>/*.accession2taxid, mode_build.cpp:493-522)
 //   metacache_b200 query <db> <r1.fq> <r2.fq> -pairfiles [-gpus P] [-lowest rank] [-highest rank]
 //       [-hitmin n] [-hitdiff f] [-maxcand n] [-insertsize n] [-winlen n] [-winstride n]
@@ -484,6 +485,86 @@ int64_t extract_taxid(const std::string& text)          // sequence_io.cpp:724-7
     return std::atoll(num.c_str());
 }
 
+// Sequence -> taxon tables that lie next to the sequence files ("assembly_summary.txt" of an NCBI RefSeq download).
+// Behaviour to match (args_handling.cpp:120, taxonomy_io.cpp:190-311, mode_build.cpp:531-604): every directory that holds an
+// input file is searched for the table; of its first ten lines the last leading '#' line is the column header (the word
+// before the first column name, "#", is not a column); the columns named "taxid" and "assembly_accession" /
+// "accession.version" give the taxon and the key, the taxon column counted from the key column on; a table without a
+// "taxid" column is read from its first line as key <tab> taxon; the first row of a key wins, a row that does not hold a
+// key and a number ends the table.  A sequence is named by the accession of its header, then by the accession in its file
+// name; a table key that merely starts with that name counts when no key equals it.
+struct SequenceTaxa {
+    std::map<std::string, int64_t> by_key;
+
+    void read_table(const std::string& path)
+    {
+        std::string txt;
+        if(!read_text_file(path, txt)) return;
+        std::cout << "Reading sequence to taxon mappings from " << path << std::endl;
+        std::vector<std::pair<size_t, size_t>> lines;                 // [from, to) without the line feed
+        for(size_t i = 0; i < txt.size();) {
+            size_t e = txt.find('\n', i);
+            if(e == std::string::npos) e = txt.size();
+            lines.emplace_back(i, e);
+            i = e + 1;
+        }
+        size_t lead = 0;
+        while(lead < lines.size() && lead < 10 && lines[lead].second > lines[lead].first && txt[lines[lead].first] == '#') ++lead;
+        const size_t head = lead ? lead - 1 : 0;
+        size_t keycol = 0, taxcol = 0, first_row = head + 1;
+        if(head < lines.size()) {
+            std::istringstream words(txt.substr(lines[head].first, lines[head].second - lines[head].first));
+            std::string w;
+            words >> w;
+            for(size_t col = 0; words >> w; ++col) {
+                if(w == "taxid") taxcol = col;
+                else if(w == "accession.version" || w == "assembly_accession") keycol = col;
+            }
+        }
+        if(taxcol < 1) { taxcol = 1; first_row = 0; }
+        for(size_t l = first_row; l < lines.size(); ++l) {
+            const char* b = txt.data() + lines[l].first;
+            const char* e = txt.data() + lines[l].second;
+            if(std::all_of(b, e, [](char c) { return c == ' ' || c == '\t' || c == '\r'; })) continue;
+            std::vector<const char*> field{b};
+            for(const char* q = b; q < e; ++q) if(*q == '\t') field.push_back(q + 1);
+            field.push_back(e + 1);
+            if(keycol + taxcol + 1 >= field.size()) break;
+            const char* k0 = field[keycol];
+            const char* k1 = field[keycol + 1] - 1;
+            while(k0 < k1 && *k0 == ' ') ++k0;
+            const char* kend = std::find_if(k0, k1, [](char c) { return c == ' ' || c == '\r'; });
+            if(kend == k0) break;
+            const char* t0 = field[keycol + taxcol];
+            const char* t1 = field[keycol + taxcol + 1] - 1;
+            while(t0 < t1 && *t0 == ' ') ++t0;
+            const bool neg = t0 < t1 && *t0 == '-';
+            const char* dg = t0 + ((t0 < t1 && (*t0 == '-' || *t0 == '+')) ? 1 : 0);
+            int64_t v = 0;
+            const char* q = dg;
+            for(; q < t1 && *q >= '0' && *q <= '9'; ++q) v = v * 10 + (*q - '0');
+            by_key.emplace(std::string(k0, kend), q == dg ? 0 : (neg ? -v : v));
+            if(q == dg) break;
+        }
+    }
+
+    void read_tables_next_to(const std::vector<std::string>& files)
+    {
+        std::set<std::string> dirs;
+        for(const auto& f : files) dirs.insert(f.substr(0, f.find_last_of("/\\")));
+        for(const auto& d : dirs) read_table(d + "/assembly_summary.txt");
+    }
+
+    int64_t taxon_of(const std::string& name) const
+    {
+        if(by_key.empty() || name.empty()) return 0;
+        auto it = by_key.find(name);
+        if(it != by_key.end()) return it->second;
+        it = by_key.upper_bound(name);
+        return it != by_key.end() && it->first.compare(0, name.size(), name) == 0 ? it->second : 0;
+    }
+};
+
 void list_files(const std::string& path, std::vector<std::string>& out)
 {
     struct stat st;
@@ -861,10 +942,13 @@ int mode_build(const Args& a)
     uint32_t ntargets = 0;
     uint64_t total_bp = 0;
     std::string txt;
+    SequenceTaxa mapped;
+    mapped.read_tables_next_to(files);
     for(const auto& f : files) {
         if(!read_text_file(f, txt)) continue;
         std::vector<Record> recs;
         parse_sequences(txt, recs);
+        const std::string file_id = extract_accession(f);
         uint64_t index = 0;
         for(auto& rec : recs) {
             ++index;
@@ -873,7 +957,9 @@ int mode_build(const Args& a)
             if(sid.empty()) sid = rec.header;
             if(names.count(sid)) continue;                                      // sketch_database.h:534
             names.insert(sid);
-            int64_t parent = extract_taxid(rec.header);
+            int64_t parent = mapped.taxon_of(sid);                              // mode_build.cpp:598-604
+            if(parent == 0) parent = mapped.taxon_of(file_id);
+            if(parent == 0) parent = extract_taxid(rec.header);
             if(parent < 1) parent = 0;
             const uint32_t tgt = ntargets++;
             const int r = int(tgt % uint32_t(P));
@@ -1734,6 +1820,34 @@ int mode_shards_equal(const Args& a)
     return ok ? 0 : 1;
 }
 
+// selftest-taxmap <sequence files / directories ...>: the parent taxon `build` gives every sequence (tables next to the
+// files, then the header), one "file <tab> sequence id <tab> taxon" line per sequence
+int mode_selftest_taxmap(const Args& a)
+{
+    std::vector<std::string> files;
+    for(const auto& p : a.pos) list_files(p, files);
+    std::sort(files.begin(), files.end());
+    SequenceTaxa mapped;
+    mapped.read_tables_next_to(files);
+    std::string txt;
+    for(const auto& f : files) {
+        if(!read_text_file(f, txt)) continue;
+        std::vector<Record> recs;
+        parse_sequences(txt, recs);
+        const std::string file_id = extract_accession(f);
+        for(const auto& rec : recs) {
+            if(rec.data.empty()) continue;
+            std::string sid = extract_accession(rec.header);
+            if(sid.empty()) sid = rec.header;
+            int64_t parent = mapped.taxon_of(sid);
+            if(parent == 0) parent = mapped.taxon_of(file_id);
+            if(parent == 0) parent = extract_taxid(rec.header);
+            std::cout << f.substr(f.find_last_of('/') + 1) << "\t" << sid << "\t" << (parent < 1 ? 0 : parent) << "\n";
+        }
+    }
+    return 0;
+}
+
 // selftest-abundance <taxonomy dir> <rank> <taxid:count> ...: the two tables of -abundances / -abundance-per
 int mode_selftest_abundance(const Args& a)
 {
@@ -1781,6 +1895,7 @@ int main(int argc, char** argv)
     else if(mode == "merge") rc = mode_merge(a);
     else if(mode == "selftest-shard") return mode_selftest_shard(a);
     else if(mode == "selftest-abundance") return mode_selftest_abundance(a);
+    else if(mode == "selftest-taxmap") return mode_selftest_taxmap(a);
     else if(mode == "shards-equal") return mode_shards_equal(a);
     else die("unknown mode '" + mode + "' (build, query and merge are implemented)");
     wait_gpu_init();

@@ -58,6 +58,14 @@ if __name__ == "__main__":
             f.write("\n".join(t.stable_lines(os.path.join(d, "merged.txt"))) + "\n")
         print("wrote cli_merge_two_databases.txt")
     with tempfile.TemporaryDirectory() as d:
+        t.make_assembly_summary_files(d)
+        t.run([sys.executable, t.SHIM, "-np", "2", "--", t.REF, "build", "rdb", "genomes", "-taxonomy", "tax"], d)
+        t.run([sys.executable, t.SHIM, "-np", "2", "--", t.REF, "query", "rdb", "r1.fq", "r2.fq"] + t.QFLAGS +
+              ["-threads", "1", "-query-limit", "300", "-out", "res.txt"], d)
+        with open(os.path.join(ROOT, "tests", "golden", "cli_np2_assembly_summary.txt"), "w") as f:
+            f.write("\n".join(t.stable_lines(os.path.join(d, "res.txt"))) + "\n")
+        print("wrote cli_np2_assembly_summary.txt")
+    with tempfile.TemporaryDirectory() as d:
         t.make_unranked_files(d)
         t.run([sys.executable, t.SHIM, "-np", "2", "--", t.REF, "build", "rdb", "genomes", "-taxonomy", "tax"], d)
         t.run([sys.executable, t.SHIM, "-np", "2", "--", t.REF, "query", "rdb", "r1.fq", "r2.fq"] + t.QFLAGS +

@@ -292,6 +292,56 @@ def test_cli_rank_unranked_targets(tmp_path):
         assert "shards equal" in run([EXE, "shards-equal", "gdb.db_%d" % r, "rdb.db_%d" % r], d)
 
 
+def make_assembly_summary_files(d):
+    """an NCBI RefSeq style download: no taxid in any header; `assembly_summary.txt` next to the sequence files maps
+    assembly accessions (= the start of the file names) to taxa; genome 1 is named by its sequence accession, genome 4
+    has a row with a longer key (prefix match), genome 5 has no row and keeps the taxid of its header"""
+    G, L = 6, 30000
+    genomes = synth.make_genomes(G, L)
+    ids, par, rk, species = synth.make_taxonomy(G)
+    gd = os.path.join(d, "genomes")
+    os.makedirs(gd, exist_ok=True)
+    for g in range(G):
+        head = "NC_%06d.1 synthetic genome %d" % (900 + g, g)
+        if g == 5:
+            head = "NC_%06d.1 taxid=%d synthetic genome %d" % (900 + g, species[g], g)
+        name = "GCF_%09d.%d_ASM%dv1_genomic.fna" % (100 + g, 2 if g == 4 else 1, g)
+        synth.write_fasta(os.path.join(gd, name), head, genomes[g])
+    with open(os.path.join(gd, "assembly_summary.txt"), "w") as f:
+        f.write("#   See ftp://ftp.ncbi.nlm.nih.gov/genomes/README_assembly_summary.txt for a description of the columns in this file.\n")
+        f.write("# assembly_accession\tbioproject\tbiosample\twgs_master\trefseq_category\ttaxid\tspecies_taxid\torganism_name\n")
+        for g in (0, 2, 3):
+            f.write("GCF_%09d.1\tPRJNA%d\tSAMN%d\t\treference genome\t%d\t%d\tSynthetic organism %d\n" % (100 + g, g, g, species[g], species[g], g))
+        f.write("NC_%06d.1\tPRJNA1\tSAMN1\t\tna\t%d\t%d\tSynthetic organism 1\n" % (901, species[1], species[1]))
+        f.write("GCF_%09d.2x\tPRJNA4\tSAMN4\t\tna\t%d\t%d\tSynthetic organism 4\n" % (104, species[4], species[4]))
+    synth.write_taxonomy_files(os.path.join(d, "tax"), ids, par, rk)
+    b1, o1, b2, o2, t = synth.make_read_pairs(genomes, 300, seed=5)
+    synth.write_fastq_pair(os.path.join(d, "r1.fq"), os.path.join(d, "r2.fq"), b1, o1, b2, o2, t)
+
+
+def test_cli_assembly_summary_mapping(tmp_path):
+    """`assembly_summary.txt` in a directory of sequence files maps sequence / file accessions to taxa before the headers
+    are consulted (args_handling.cpp:120, taxonomy_io.cpp:190-311, mode_build.cpp:531-604): same shard files (taxon
+    records) and same classification as the reference"""
+    d = str(tmp_path)
+    make_assembly_summary_files(d)
+    run([EXE, "build", "gdb", "genomes", "-taxonomy", "tax", "-gpus", "2"], d)
+    run([EXE, "query", "gdb", "r1.fq", "r2.fq"] + QFLAGS + ["-out", "res_gpu.txt"], d)
+    mine = stable_lines(os.path.join(d, "res_gpu.txt"))
+    golden = os.path.join(ROOT, "tests", "golden", "cli_np2_assembly_summary.txt")
+    if os.path.exists(golden):
+        assert mine == open(golden).read().splitlines()
+    if not os.path.exists(REF):
+        assert os.path.exists(golden), "neither oracle/_ref nor the golden output is available"
+        return
+    run([sys.executable, SHIM, "-np", "2", "--", REF, "build", "rdb", "genomes", "-taxonomy", "tax"], d)
+    run([sys.executable, SHIM, "-np", "2", "--", REF, "query", "rdb", "r1.fq", "r2.fq"] + QFLAGS +
+        ["-threads", "1", "-query-limit", "300", "-out", "res_ref.txt"], d)
+    assert mine == stable_lines(os.path.join(d, "res_ref.txt"))
+    for r in range(2):
+        assert "shards equal" in run([EXE, "shards-equal", "gdb.db_%d" % r, "rdb.db_%d" % r], d)
+
+
 MERGE_FLAGS = ["-lowest", "species", "-maxcand", "4", "-hitmin", "4", "-hitdiff", "80", "-tophits", "-queryids"]
 
 

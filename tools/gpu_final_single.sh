@@ -13,4 +13,3 @@ print('reference arm', r['value'], r['ms_per_step'])
 PY
 CMD="python bench.py --steps 2 --warmup 1 --no-extras --no-cpu --no-check"
 ncu --metrics gpu__time_duration.sum --clock-control none -k 'regex:^(q_|rs_|runs_|table_|tile_|sketch_|cta_seq|window_count|count_sizes|set_|exp_|imp_|ovp_|remove_keys|tgt_)' -c 400 --csv --log-file gpurun_out/r02_bench_launches.csv $CMD > gpurun_out/ncu1.log 2>&1; echo ncu1=$?
-ncu --set full --clock-control none --import-source on -k regex:q_fused_warp -s 2 -c 1 -o gpurun_out/r02_query_fused_kernel -f $CMD > gpurun_out/ncu2.log 2>&1; echo ncu2=$?
