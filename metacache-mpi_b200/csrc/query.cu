@@ -564,6 +564,26 @@ __device__ __forceinline__ void warp_toplist_insert_all(WarpTopK& L, int K, cons
     }
 }
 
+// The same list for at most 32 candidates (lane j holds candidate j: t = lifted taxon | sequence-rank flag, h = hits, 0 =
+// none), without replaying the insertions: insert() (candidates.h:236-285) keeps per taxon the MAXIMUM of its candidates'
+// hits, places an entry behind every entry with at least as many hits at the moment it reaches its value, and an entry
+// pushed out of a full list can never return with the same value -- so the final list is the first K taxa ordered by
+// (hits descending, position of the first candidate that carries the taxon's maximum ascending).  That candidate is the
+// warp-wide maximum of (hits, 31 - lane); it is taken K times, each time retiring all candidates of its taxon
+// (sequence-rank candidates carry distinct values, so they retire alone).  ~7 instructions per list entry.
+__device__ __forceinline__ void warp_toplist_select32(WarpTopK& L, int K, int32_t t, uint32_t h, int lane)
+{
+    uint32_t key = h ? ((h << 5) | uint32_t(31 - lane)) : 0u;          // h < 2^27: a read has far fewer features
+    for(int k = 0; k < K; ++k) {
+        const uint32_t best = __reduce_max_sync(0xFFFFFFFFu, key);
+        if(best == 0u) break;
+        const int32_t bt = __shfl_sync(0xFFFFFFFFu, t, 31 - int(best & 31u));
+        if(lane == k) { L.tax = bt & 0x7FFFFFFF; L.hits = best >> 5; }
+        if(t == bt) key = 0u;
+        L.n = k + 1;
+    }
+}
+
 // Stable LSD radix sort of m 32-bit keys in shared memory by a whole CTA, 8 bits per pass over the
 // `bits` significant bits: A -> B -> A ...; the result ends in A.  Every warp owns a contiguous chunk;
 // pass = count (shared atomics on warp-private digit counters) -> prefix over (digit, warp) -> rank
@@ -776,13 +796,15 @@ __device__ __forceinline__ void warp_topk_insert_lifted(WarpTopK& L, int K, int3
 }
 
 // sorted matches A[0..m) + per-element range hits Hh -> top list.  The target runs are found, their
-// maxima taken (segmented warp scan) and their taxa lifted by all lanes at once (the lineage
-// loads of all candidates are in flight together); only the order-dependent list insertion
-// (candidates.h:236-285) runs one candidate after the other, out of shared memory.
+// maxima taken (segmented warp scan) and their taxa lifted by all lanes at once (the lift-table
+// loads of all candidates are in flight together).  Up to 32 candidates the list is SELECTED
+// (warp_toplist_select32); beyond that the order-dependent insertion (candidates.h:236-285) is
+// replayed one candidate after the other, out of shared memory.
 // Hh == nullptr: the range hits (hits_ending_at) are computed here instead of by a pass of their own -- from the start of
-// an element's target run (running maximum of the run-head indices): as long as the run spans fewer than numwin
-// windows up to the element, ALL its elements so far are in range (the usual case for a short read); only otherwise
-// the range is searched.
+// an element's target run (the nearest run head at or before it, out of the ballot of heads): as long as the run spans
+// fewer than numwin windows up to the element, ALL its elements so far are in range (the usual case for a short read) and
+// the value rises along the run, so the run's maximum is simply its last value; only otherwise the range is searched and
+// the maximum taken by a segmented scan.
 template<class KeyT>
 __device__ __forceinline__ void toplist_from_sorted(const CandParams& p, uint32_t r, const KeyT* A, const uint32_t* Hh,
                                                     uint32_t m, int32_t* Ct, uint32_t* Ch, int lane, uint32_t numwin)
@@ -799,32 +821,33 @@ __device__ __forceinline__ void toplist_from_sorted(const CandParams& p, uint32_
         last_tgt = __shfl_sync(0xFFFFFFFFu, tgt, 31);
         const bool head = valid && (i == 0 || prev != tgt);
         const bool tail = valid && (i + 1 == m || tgt_of(A[i + 1], p.wbits) != tgt);
+        const uint32_t hm = __ballot_sync(0xFFFFFFFFu, head);
         uint32_t v = 0u;
+        bool rising = false;            // every element's range reaches back to the start of its run: v rises along each run
         if(Hh != nullptr) {
             if(valid) v = Hh[i];
         } else {
-            uint32_t st = head ? i : 0u;
-            if(lane == 0 && !head) st = run_start;
-#pragma unroll
-            for(int d = 1; d < 32; d <<= 1) {
-                const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, st, d);
-                if(lane >= d) st = max(st, o);
-            }
-            run_start = __shfl_sync(0xFFFFFFFFu, st, 31);
+            const uint32_t below = hm & (ltmask | (1u << lane));             // run heads at or before this lane
+            const uint32_t st = below ? b + 31u - uint32_t(__clz(int(below))) : run_start;
+            if(hm) run_start = b + 31u - uint32_t(__clz(int(hm)));
+            bool whole = true;
             if(valid) {
                 const KeyT wmask = (KeyT(1) << p.wbits) - 1;
                 const uint32_t win = uint32_t(key & wmask), win0 = uint32_t(A[st] & wmask);
-                v = (win - win0 < numwin) ? i - st + 1u : hits_ending_at(A, i, numwin, p.wbits);
+                whole = win - win0 < numwin;
+                v = whole ? i - st + 1u : hits_ending_at(A, i, numwin, p.wbits);
             }
+            rising = __all_sync(0xFFFFFFFFu, whole);
         }
-        if(lane == 0 && !head) v = max(v, carry);
-        const uint32_t hm = __ballot_sync(0xFFFFFFFFu, head);
-        // inclusive segmented max scan: take the value d lanes down unless a run starts in between
+        if(!rising) {
+            if(lane == 0 && !head) v = max(v, carry);
+            // inclusive segmented max scan: take the value d lanes down unless a run starts in between
 #pragma unroll
-        for(int d = 1; d < 32; d <<= 1) {
-            const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, v, d);
-            const uint32_t between = (hm >> (lane >= d ? lane - d + 1 : 0)) & ((1u << d) - 1u);    // heads in (lane-d, lane]
-            if(lane >= d && between == 0u) v = max(v, o);
+            for(int d = 1; d < 32; d <<= 1) {
+                const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, v, d);
+                const uint32_t between = (hm >> (lane >= d ? lane - d + 1 : 0)) & ((1u << d) - 1u);    // heads in (lane-d, lane]
+                if(lane >= d && between == 0u) v = max(v, o);
+            }
         }
         carry = __shfl_sync(0xFFFFFFFFu, v, 31);
         const uint32_t tm = __ballot_sync(0xFFFFFFFFu, tail);
@@ -838,7 +861,8 @@ __device__ __forceinline__ void toplist_from_sorted(const CandParams& p, uint32_
     __syncwarp();
     WarpTopK L;
     L.tax = -1; L.hits = 0; L.n = 0;
-    warp_toplist_insert_all(L, p.K, Ct, Ch, ncand, lane);
+    if(ncand <= 32u) warp_toplist_select32(L, p.K, uint32_t(lane) < ncand ? Ct[lane] : 0, uint32_t(lane) < ncand ? Ch[lane] : 0u, lane);
+    else warp_toplist_insert_all(L, p.K, Ct, Ch, ncand, lane);
     if(lane < p.K) {
         p.out_tax[uint64_t(r) * p.rs + lane] = lane < L.n ? L.tax : -1;
         p.out_hits[uint64_t(r) * p.rs + lane] = lane < L.n ? L.hits : 0u;
