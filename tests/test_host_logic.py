@@ -135,3 +135,53 @@ def test_oracle_restricted_build_answers_like_the_whole_database(oracle):
     a = oracle.query_batch(full, w.tax, q, w.b1, w.o1, w.b2, w.o2)
     b = oracle.query_batch(rs, w.tax, q, w.b1, w.o1, w.b2, w.o2)
     assert all((x == y).all() for x, y in zip(a, b))
+
+
+def test_top_list_selection_rule_equals_replayed_insertion(oracle):
+    """The fused query kernel does not replay candidates.h:236-285 insert() candidate by candidate: it takes, K times, the
+    candidate with the most hits (the earliest of those) and retires every candidate of its taxon (query.cu
+    warp_toplist_select32).  Property checked here on the CPU, against the oracle's insertion (itself pinned to the
+    reference's insert by tests/test_oracle_vs_reference.py): both give the same list for random candidate streams with
+    many equal hit counts, taxa that appear several times, targets that stay at sequence level, and every list length."""
+    from oracle import pyoracle as po
+    from metacache_mpi_b200 import taxonomy as tx
+    G = 24
+    ids, par, rk, species = synth.make_taxonomy(G)
+    species = species.copy()
+    species[[3, 8, 9, 20]] = 0                                   # no taxon above the sequence: never merged, never lifted
+    tabs = tx.TaxonomyTables(ids, par, rk, species)
+    tax = po.TaxTables(tabs.lineage, tabs.rank, G)
+    rng = np.random.default_rng(11)
+    checked = 0
+    for lowest in (0, 4, 6, 10):                                 # sequence, species, genus, family
+        for K in (1, 2, 4, 7, 32):
+            for trial in range(60):
+                n = int(rng.integers(0, 33))
+                t = rng.integers(0, G, n).astype(np.int32)       # (the kernel sees ascending distinct targets; any order must hold)
+                if trial % 2 == 0:
+                    t = np.sort(rng.permutation(G)[:min(n, G)]).astype(np.int32)
+                    n = len(t)
+                h = rng.integers(1, 4 if trial % 3 else 40, n).astype(np.uint32)
+                q = po.make_qopt(maxcand=K, lowest=lowest, hitmin=1, hitdiff=1.0)
+                want_t, want_h, _, _ = oracle.merge_classify(tax, q, t, h)
+                # the selection rule, on lifted taxa
+                lifted, seq = [], []
+                for x in t:
+                    a = tabs.lineage[x][lowest] if lowest > 0 and tabs.lineage[x][lowest] >= 0 else x
+                    lifted.append(int(a)); seq.append(tabs.rank[a] == 0)
+                alive = [True] * n
+                got_t, got_h = [], []
+                for _ in range(K):
+                    best = -1
+                    for j in range(n):
+                        if alive[j] and (best < 0 or h[j] > h[best]):
+                            best = j
+                    if best < 0:
+                        break
+                    got_t.append(lifted[best]); got_h.append(int(h[best]))
+                    for j in range(n):
+                        if j == best or (not seq[best] and not seq[j] and lifted[j] == lifted[best]):
+                            alive[j] = False
+                assert list(want_t) == got_t and list(want_h) == got_h, (lowest, K, t, h)
+                checked += 1
+    assert checked == 4 * 5 * 60
